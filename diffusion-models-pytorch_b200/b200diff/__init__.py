@@ -1,0 +1,299 @@
+"""ctypes binding of libb200diff.so (C ABI in include/b200diff.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every arithmetic op on the diffusion hot
+path is a kernel of the shared library.  There is deliberately no fallback: if the library is missing or a
+kernel fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int8, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200diff.so')
+
+OUT_F32_NHWC, OUT_BF16_NHWC, OUT_F32_NCHW, OUT_BF16_NCHW = 0, 1, 2, 3
+OBJ = {'pred_eps': 0, 'pred_x0': 1, 'pred_v': 2}
+(SC_SQRT_RECIP_AC, SC_SQRT_RECIPM1_AC, SC_SQRT_AC, SC_SQRT_1M_AC, SC_X0_COEF, SC_XT_COEF, SC_EPS_COEF, SC_VAR,
+ SC_MIN_LOGVAR, SC_MAX_LOGVAR, SC_ADD_NOISE) = range(11)
+SC_COUNT = 12
+
+
+class ConvDesc(Structure):
+    _fields_ = [
+        ('a0', c_void_p), ('a0_C', c_int), ('a0_H', c_int), ('a0_W', c_int), ('a0_planes', c_int),
+        ('a1', c_void_p), ('a1_C', c_int), ('a1_H', c_int), ('a1_W', c_int), ('a1_planes', c_int),
+        ('w', c_void_p), ('w_rows', c_int), ('w_K', c_int), ('w_rows_per_phase', c_int),
+        ('B', c_int), ('Ho', c_int), ('Wo', c_int),
+        ('phases', c_int), ('N', c_int), ('ntaps0', c_int),
+        ('taps0', c_int8 * 144), ('tap1', c_int8 * 4),
+        ('bias', c_void_p), ('rowadd', c_void_p), ('rowadd_ld', c_int),
+        ('residual', c_void_p), ('res_ld', c_int),
+        ('out', c_void_p), ('out_mode', c_int), ('out_ld', c_int), ('out_H', c_int), ('out_W', c_int),
+        ('osy', c_int), ('osx', c_int),
+    ]
+
+
+class SamplerDesc(Structure):
+    _fields_ = [
+        ('model_out', c_void_p), ('model_out_uncond', c_void_p), ('xt', c_void_p), ('noise', c_void_p),
+        ('coef', c_void_p),
+        ('B', c_int), ('C', c_int), ('Cm', c_int), ('HW', c_int),
+        ('objective', c_int), ('clip', c_int), ('learned_range', c_int),
+        ('guidance_scale', c_double),
+        ('sample', c_void_p), ('mean', c_void_p), ('pred_x0', c_void_p), ('pred_eps', c_void_p),
+        ('var_out', c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built: there is no CPU/PyTorch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'(or `make -C diffusion-models-pytorch_b200/csrc`). There is no fallback path.')
+    L = ctypes.CDLL(LIB_PATH)
+    L.b200_version.restype = c_int
+    L.b200_last_error.restype = c_char_p
+    L.b200_launch_count.restype = c_longlong
+    L.b200_conv2d_fwd.argtypes = [POINTER(ConvDesc), c_void_p]
+    L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]
+    L.b200_groupnorm_silu_fwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p]
+    L.b200_cast_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_avgpool2_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_upsample2_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_attention_fwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, c_void_p]
+    L.b200_time_embed.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
+    L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    for name in ('b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_cast_bf16',
+                 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd', 'b200_time_embed',
+                 'b200_sampler_step', 'b200_diffuse'):
+        getattr(L, name).restype = c_int
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv3x3_first',
+    'b200_groupnorm_silu_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
+    'b200_time_embed', 'b200_sampler_step', 'b200_diffuse',
+)
+
+
+def launch_count() -> int:
+    return int(lib().b200_launch_count())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().b200_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'libb200diff {what} failed (code {rc}): {msg}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('b200diff kernels run on CUDA tensors only (no CPU fallback); got a '
+                               f'{t.device} tensor')
+
+
+# --------------------------------------------------------------------------------------------------
+# tap tables
+# --------------------------------------------------------------------------------------------------
+def taps_3x3_s1():
+    """3x3 stride 1 pad 1: tap k = r*3+s reads (ho + r - 1, wo + s - 1)."""
+    return [[(s - 1, r - 1, 0) for r in range(3) for s in range(3)]]
+
+
+def taps_1x1():
+    return [[(0, 0, 0)]]
+
+
+def taps_3x3_s2(pad_lo: int):
+    """3x3 stride 2 over 4 parity planes.  pad_lo = 1: symmetric pad 1 (models/modules.py:72);
+    pad_lo = 0: pad (0,1,0,1) then stride 2 (models/pesser/model.py:66-70).
+    Input row 2*ho + r - pad_lo lives in plane parity (r - pad_lo) & 1 at index ho + floor((r - pad_lo) / 2)."""
+    taps = []
+    for r in range(3):
+        for s in range(3):
+            ry, rx = r - pad_lo, s - pad_lo
+            taps.append((rx // 2, ry // 2, ((ry & 1) << 1) | (rx & 1)))
+    return [taps]
+
+
+def taps_up2_3x3():
+    """nearest-2x followed by 3x3 pad 1 == four 2x2-tap convolutions on the low-resolution grid.
+    Phase (a, b) = output pixel parity; tap (i, j) in {0,1}^2 reads low-res offset (dh, dw) with
+    dh = i - 1 + a, dw = j - 1 + b.  The matching weights are sums of the 3x3 taps (see pack_weight_up2)."""
+    out = []
+    for a in range(2):
+        for b in range(2):
+            out.append([(j - 1 + b, i - 1 + a, 0) for i in range(2) for j in range(2)])
+    return out
+
+
+def _fill_taps(desc, taps0, tap1):
+    flat = [0] * 144
+    for ph, taps in enumerate(taps0):
+        for k, (dw, dh, pl) in enumerate(taps):
+            base = (ph * 9 + k) * 4
+            flat[base], flat[base + 1], flat[base + 2] = dw, dh, pl
+    desc.taps0 = (c_int8 * 144)(*flat)
+    desc.tap1 = (c_int8 * 4)(tap1[0], tap1[1], tap1[2], 0)
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing (host side, once per weight update): OIHW fp32 -> [Cout][K] bf16, K = tap-major, channel-minor
+# --------------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, shortcut_w: torch.Tensor = None) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] -> bf16 [Cout, kh*kw*Cin (+ Cin_sc)] with k = (r*kw + s)*Cin + c."""
+    co, ci, kh, kw = w.shape
+    m = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+    if shortcut_w is not None:
+        m = torch.cat([m, shortcut_w.detach().reshape(co, -1)], dim=1)
+    return m.to(torch.bfloat16).contiguous()
+
+
+def pack_weight_up2(w: torch.Tensor) -> torch.Tensor:
+    """3x3 weights -> the four 2x2 phase kernels of 'nearest-2x then 3x3' stacked as [4*Cout][4*Cin] bf16.
+    Row taps: phase a=0 -> {W[0], W[1]+W[2]}, a=1 -> {W[0]+W[1], W[2]}; same for columns (summed in fp32)."""
+    co, ci, _, _ = w.shape
+    w = w.detach().float()
+    rows = {0: [w[:, :, 0:1], w[:, :, 1:2] + w[:, :, 2:3]], 1: [w[:, :, 0:1] + w[:, :, 1:2], w[:, :, 2:3]]}
+    mats = []
+    for a in range(2):
+        for b in range(2):
+            taps = []
+            for i in range(2):
+                wr = rows[a][i]  # [co, ci, 1, 3]
+                cols = {0: [wr[..., 0], wr[..., 1] + wr[..., 2]], 1: [wr[..., 0] + wr[..., 1], wr[..., 2]]}
+                for j in range(2):
+                    taps.append(cols[b][j].reshape(co, ci))
+            mats.append(torch.cat(taps, dim=1))
+    return torch.cat(mats, dim=0).to(torch.bfloat16).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel wrappers
+# --------------------------------------------------------------------------------------------------
+def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None, tap1=(0, 0, 0), bias=None,
+           rowadd=None, rowadd_ld=0, residual=None, res_ld=0, out=None, out_mode=OUT_F32_NHWC, out_ld=None,
+           out_H=None, out_W=None, w_rows_per_phase=None):
+    """a0_geom = (C, H, W, planes) of the bf16 source tensor [B][planes][H][W][C]."""
+    _need_cuda(a0, w_packed, out)
+    d = ConvDesc()
+    d.a0 = a0.data_ptr()
+    d.a0_C, d.a0_H, d.a0_W, d.a0_planes = a0_geom
+    if a1 is not None:
+        d.a1 = a1.data_ptr()
+        d.a1_C, d.a1_H, d.a1_W, d.a1_planes = a1_geom
+    d.w = w_packed.data_ptr()
+    d.w_rows, d.w_K = w_packed.shape
+    phases = len(taps0)
+    d.w_rows_per_phase = w_rows_per_phase if w_rows_per_phase is not None else N
+    d.B, d.Ho, d.Wo = B, Ho, Wo
+    d.phases, d.N, d.ntaps0 = phases, N, len(taps0[0])
+    _fill_taps(d, taps0, tap1)
+    d.bias = _ptr(bias)
+    d.rowadd, d.rowadd_ld = _ptr(rowadd), rowadd_ld
+    d.residual, d.res_ld = _ptr(residual), res_ld
+    d.out, d.out_mode = out.data_ptr(), out_mode
+    d.out_ld = out_ld if out_ld is not None else N
+    up = 2 if phases == 4 else 1
+    d.out_H = out_H if out_H is not None else Ho * up
+    d.out_W = out_W if out_W is not None else Wo * up
+    d.osy = d.osx = up
+    _check(lib().b200_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
+    return out
+
+
+def conv3x3_first(x, w, bias, out):
+    _need_cuda(x, w, out)
+    B, Cin, H, W = x.shape
+    _check(lib().b200_conv3x3_first(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, Cin, H, W, w.shape[0],
+                                    _stream()), 'conv3x3_first')
+    return out
+
+
+def groupnorm_silu(x0, C0, x1, C1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None, shift=None, ss_ld=0,
+                   silu=True, resample=0, raw_out=None):
+    _need_cuda(x0, out)
+    _check(lib().b200_groupnorm_silu_fwd(x0.data_ptr(), C0, _ptr(x1), C1, B, HW, W, groups, _ptr(gamma), _ptr(beta),
+                                         float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu), resample,
+                                         out.data_ptr(), _ptr(raw_out), _stream()), 'groupnorm_silu_fwd')
+    return out
+
+
+def cast_bf16(x, out, B, H, W, C, parity_split=False):
+    _need_cuda(x, out)
+    _check(lib().b200_cast_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C, int(parity_split), _stream()), 'cast_bf16')
+    return out
+
+
+def avgpool2_f32(x, out, B, H, W, C):
+    _check(lib().b200_avgpool2_f32(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream()), 'avgpool2_f32')
+    return out
+
+
+def upsample2_f32(x, out, B, H, W, C):
+    _check(lib().b200_upsample2_f32(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream()), 'upsample2_f32')
+    return out
+
+
+def attention(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale):
+    _need_cuda(qk, vt, out)
+    _check(lib().b200_attention_fwd(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(), ld_out, B, T,
+                                    heads, d, float(scale), _stream()), 'attention_fwd')
+    return out
+
+
+def time_embed(t, freqs, dim, E, cos_first, w1, b1, w2, b2, out, *, y=None, class_embed=None, out_silu_bf16=None):
+    _need_cuda(t, out)
+    _check(lib().b200_time_embed(t.data_ptr(), t.shape[0], freqs.data_ptr(), dim, E, int(cos_first), w1.data_ptr(),
+                                 b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), _ptr(y), _ptr(class_embed),
+                                 out.data_ptr(), _ptr(out_silu_bf16), _stream()), 'time_embed')
+    return out
+
+
+def sampler_step(model_out, xt, coef_row, *, objective='pred_eps', clip=True, learned_range=False, noise=None,
+                 model_out_uncond=None, guidance_scale=1.0, sample=None, mean=None, pred_x0=None, pred_eps=None,
+                 var_out=None):
+    _need_cuda(model_out, xt, coef_row)
+    d = SamplerDesc()
+    d.model_out, d.model_out_uncond = model_out.data_ptr(), _ptr(model_out_uncond)
+    d.xt, d.noise, d.coef = xt.data_ptr(), _ptr(noise), coef_row.data_ptr()
+    B, C = xt.shape[0], xt.shape[1]
+    d.B, d.C, d.Cm, d.HW = B, C, model_out.shape[1], xt[0, 0].numel()
+    d.objective, d.clip, d.learned_range = OBJ[objective], int(clip), int(learned_range)
+    d.guidance_scale = float(guidance_scale)
+    d.sample, d.mean, d.pred_x0, d.pred_eps, d.var_out = _ptr(sample), _ptr(mean), _ptr(pred_x0), _ptr(pred_eps), \
+        _ptr(var_out)
+    _check(lib().b200_sampler_step(ctypes.byref(d), _stream()), 'sampler_step')
+
+
+def diffuse(x0, eps, t, alphas_cumprod, out):
+    _need_cuda(x0, eps, t, alphas_cumprod, out)
+    _check(lib().b200_diffuse(x0.data_ptr(), eps.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
+                              x0.shape[0], x0[0].numel(), _stream()), 'diffuse')
+    return out

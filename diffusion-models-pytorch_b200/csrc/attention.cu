@@ -1,0 +1,237 @@
+// K2: fused attention softmax(q k^T * scale) v for the low-resolution self-attention blocks
+// (models/modules.py:92-97: q*scale, bmm, softmax, bmm; [B*h, T, T] is never materialised in HBM here).
+//
+// One CTA per (128-query tile, head, image), T <= 256 keys so the whole score row fits in TMEM:
+//   1. TMA: Q tile [128 x d] and K [Tp x d] (Tp = T rounded up to 64; out-of-range rows are zero-filled).
+//   2. tcgen05.mma: S[128 x Tp] = Q K^T   (fp32, TMEM columns [0, Tp)).
+//   3. 128 threads, one score row each: tcgen05.ld S, row max, p = exp2((s - max) * scale * log2e), row sum,
+//      P rounded to bf16 and written to smem in the 128B-swizzled K-major layout UMMA expects.
+//      Meanwhile TMA brings V^T [d x Tp] into the smem that held K.
+//   4. tcgen05.mma: O[128 x d] = P V      (TMEM columns [Tp, Tp + d)).
+//   5. tcgen05.ld O, scale by 1/rowsum, store bf16 [B][T][heads*d].
+#include "common.cuh"
+#include "../../include/b200diff.h"
+
+namespace b200 {
+extern long long g_launch_count;
+
+struct AttnParams {
+  int T, Tp, d;
+  int q_off, k_off;
+  float scale_log2e;
+  __nv_bfloat16* out;
+  int ld_out;
+  uint32_t tmem_cols;
+};
+
+struct __align__(8) AttnBars {
+  uint64_t qk_full, v_full, s_done, o_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1)
+attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int dk = p.d >> 6;    // 64-wide chunks of the head dim
+  const int tk = p.Tp >> 6;   // 64-wide chunks of the keys
+  const int qp_bytes = (dk > tk ? dk : tk) * 16384;  // Q tile, later P tile
+  uint8_t* sQ = smem;                 // [dk][128 rows][128 B]   (aliased by P: [tk][128 rows][128 B])
+  uint8_t* sK = smem + qp_bytes;      // [dk][Tp rows][128 B]    (aliased by V^T: [tk][d rows][128 B])
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sK + (size_t)dk * p.Tp * 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(&bars->qk_full, 1);
+    mbar_init(&bars->v_full, 1);
+    mbar_init(&bars->s_done, 1);
+    mbar_init(&bars->o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = bars->tmem_base;
+  const uint32_t tmem_o = tmem_s + (uint32_t)p.Tp;
+
+  if (threadIdx.x == 0) {
+    // ---- 1. loads + 2. S = Q K^T ----
+    mbar_arrive_expect_tx(&bars->qk_full, (uint32_t)(dk * 16384 + dk * p.Tp * 128));
+    for (int c = 0; c < dk; ++c) {
+      tma_load_3d(sQ + c * 16384, &mapQ, &bars->qk_full, p.q_off + h * p.d + c * 64, q0, b);
+      tma_load_3d(sK + (size_t)c * p.Tp * 128, &mapK, &bars->qk_full, p.k_off + h * p.d + c * 64, 0, b);
+    }
+    mbar_wait(&bars->qk_full, 0);
+    tc_fence_after();
+    const uint32_t idesc_s = umma_idesc_bf16_m128((uint32_t)p.Tp);
+    for (int c = 0; c < dk; ++c) {
+      const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sQ + c * 16384));
+      const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sK + (size_t)c * p.Tp * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_s, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+    }
+    umma_commit(&bars->s_done);
+  }
+  __syncwarp();
+
+  // ---- 3. softmax over the score row held by this thread ----
+  mbar_wait(&bars->s_done, 0);
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    // K is consumed: bring V^T into its place while the softmax runs
+    mbar_arrive_expect_tx(&bars->v_full, (uint32_t)(tk * p.d * 128));
+    for (int c = 0; c < tk; ++c)
+      tma_load_3d(sK + (size_t)c * p.d * 128, &mapV, &bars->v_full, c * 64, h * p.d, b);
+  }
+  __syncwarp();
+  const int r = warp * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  float m = -INFINITY;
+  for (int c = 0; c < p.Tp; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+  }
+  const float ms = m * p.scale_log2e;
+  float sum = 0.f;
+  for (int c = 0; c < p.Tp; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = (c + j < p.T) ? exp2f(__uint_as_float(v[j]) * p.scale_log2e - ms) : 0.f;
+      e[j] = x;
+      sum += x;
+    }
+    // P tile kt = c/64: row r at r*128 B, 16-byte chunk index ((c%64)/8 + i) XOR (r & 7)
+    uint8_t* prow = sQ + (size_t)(c >> 6) * 16384 + (size_t)r * 128;
+    const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(e[8 * i + 0], e[8 * i + 1]);
+      u.y = pack_bf16x2(e[8 * i + 2], e[8 * i + 3]);
+      u.z = pack_bf16x2(e[8 * i + 4], e[8 * i + 5]);
+      u.w = pack_bf16x2(e[8 * i + 6], e[8 * i + 7]);
+      *reinterpret_cast<uint4*>(prow + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+    }
+  }
+  // generic-proxy writes of P -> visible to the tensor-core (async) proxy
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- 4. O = P V ----
+  if (threadIdx.x == 0) {
+    mbar_wait(&bars->v_full, 0);
+    tc_fence_after();
+    const uint32_t idesc_o = umma_idesc_bf16_m128((uint32_t)p.d);
+    for (int c = 0; c < tk; ++c) {
+      const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sQ + c * 16384));
+      const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sK + (size_t)c * p.d * 128));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_o, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+    }
+    umma_commit(&bars->o_done);
+  }
+  __syncwarp();
+
+  // ---- 5. normalise and store ----
+  mbar_wait(&bars->o_done, 0);
+  tc_fence_after();
+  const float inv = 1.0f / sum;
+  const bool row_ok = (q0 + r) < p.T;
+  __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q0 + r) * p.ld_out + h * p.d;
+  for (int c = 0; c < p.d; c += 32) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(tmem_o + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c + 8 * i) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_s, p.tmem_cols);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
+                                  int B, int T, int heads, int d, float scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(qk && vt && out, "attention_fwd: null pointer");
+  B200_REQUIRE(d == 64 || d == 128 || d == 256, "attention_fwd: head dim %d not in {64,128,256}", d);
+  B200_REQUIRE(T >= 8 && T <= 256 && T % 8 == 0, "attention_fwd: T=%d must be a multiple of 8 in [8,256]", T);
+  B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
+  B200_REQUIRE(((uintptr_t)qk & 127) == 0 && ((uintptr_t)vt & 127) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: alignment");
+  const int Tp = (T + 63) / 64 * 64;
+  AttnParams p;
+  p.T = T; p.Tp = Tp; p.d = d; p.q_off = q_off; p.k_off = k_off;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(Tp + d)) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap mapQ, mapK, mapV;
+  {
+    uint64_t dims[3] = {(uint64_t)ld_qk, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)ld_qk * 2, (uint64_t)T * ld_qk * 2};
+    uint32_t boxq[3] = {64, 128, 1};
+    uint32_t boxk[3] = {64, (uint32_t)Tp, 1};
+    int rc = encode_tmap(&mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tmap(&mapK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxk, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)T, (uint64_t)heads * d, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)T * 2, (uint64_t)heads * d * T * 2};
+    uint32_t box[3] = {64, (uint32_t)d, 1};
+    int rc = encode_tmap(&mapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const int dk = d / 64, tk = Tp / 64;
+  const size_t smem = (size_t)(dk > tk ? dk : tk) * 16384 + (size_t)dk * Tp * 128 + sizeof(AttnBars) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  B200_REQUIRE(smem <= 227 * 1024, "attention_fwd: smem %zu too large", smem);
+  dim3 grid((T + 127) / 128, heads, B);
+  attention_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "attention_kernel launch");
+}

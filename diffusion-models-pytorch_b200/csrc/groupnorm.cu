@@ -1,0 +1,272 @@
+// K3: GroupNorm (+AdaGN scale/shift) (+SiLU) (+2x avg-pool / nearest-2x) over fp32 NHWC input(s), bf16 NHWC out.
+// Replaces nn.GroupNorm + nn.SiLU + torch.cat of the reference (models/unet.py:14-15,23-24,116-117,145;
+// models/modules.py:82,105-123; models/unet_categorial_adagn.py:52-57).
+//
+// One CTA owns (image n, a chunk of whole groups): the [HW x CC] fp32 slab is read from HBM exactly once into
+// shared memory, statistics are an exact two-pass (mean, then centred variance) over the slab, and the
+// normalised, activated values are rounded to bf16 exactly once on the way out.  HBM traffic = 4 B read +
+// 2 B written per element (+2 B when the raw bf16 copy for the 1x1 shortcut conv is requested).
+#include "common.cuh"
+#include "../../include/b200diff.h"
+
+namespace b200 {
+extern long long g_launch_count;
+
+struct GnParams {
+  const float* x0; int C0;
+  const float* x1; int C1;
+  int HW, W, groups, cpg, gpc;  // gpc = groups per CTA chunk
+  int chunks;
+  const float* gamma; const float* beta; float eps;
+  const float* scale; const float* shift; int ss_ld;
+  int apply_silu, resample;
+  __nv_bfloat16* out; __nv_bfloat16* raw;
+};
+
+template <int V> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+
+template <int V>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void lds_vec(const float* p, float (&v)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ void sts_vec(float* p, const float (&v)[V]) {
+  if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <int V>
+__device__ __forceinline__ void store_bf16_vec(__nv_bfloat16* p, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    uint2 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) groupnorm_kernel(const GnParams p) {
+  extern __shared__ float gsm[];
+  const int n = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - n * p.chunks;
+  const int g0 = chunk * p.gpc;
+  const int ng = min(p.gpc, p.groups - g0);
+  const int c0 = g0 * p.cpg;
+  const int CC = ng * p.cpg;          // channels handled by this CTA
+  const int pitch = p.gpc * p.cpg + 4;  // slab row pitch in floats (16 B pad -> conflict-free float4 columns)
+  const int nv = CC / V;
+  const int C = p.C0 + p.C1;
+  float* slab = gsm;
+  float* coefA = slab + (size_t)p.HW * pitch;  // [CC] multiplicative coefficient
+  float* coefB = coefA + p.gpc * p.cpg;        // [CC] additive coefficient
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- pass 0: HBM -> smem (single read of the input), optional raw bf16 copy ----
+  const int total = p.HW * nv;
+  for (int idx = tid; idx < total; idx += 256) {
+    const int px = idx / nv;
+    const int j = idx - px * nv;
+    const int c = c0 + j * V;
+    const float* src = (c < p.C0) ? p.x0 + ((size_t)n * p.HW + px) * p.C0 + c
+                                  : p.x1 + ((size_t)n * p.HW + px) * p.C1 + (c - p.C0);
+    float v[V];
+    load_vec<V>(src, v);
+    sts_vec<V>(slab + px * pitch + j * V, v);
+    if (p.raw) store_bf16_vec<V>(p.raw + ((size_t)n * p.HW + px) * C + c, v);
+  }
+  __syncthreads();
+
+  // ---- pass 1+2: per-group mean and centred variance from smem; one warp per group ----
+  const int vpg = p.cpg / V;
+  const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);
+  for (int g = warp; g < ng; g += 8) {
+    const float* base = slab + g * p.cpg;
+    float s = 0.f;
+    for (int px = lane; px < p.HW; px += 32)
+      for (int i = 0; i < vpg; ++i) {
+        float t[V];
+        lds_vec<V>(base + px * pitch + i * V, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s += t[e];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_cnt;
+    float q = 0.f;
+    for (int px = lane; px < p.HW; px += 32)
+      for (int i = 0; i < vpg; ++i) {
+        float t[V];
+        lds_vec<V>(base + px * pitch + i * V, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float d = t[e] - mean;
+          q += d * d;
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_cnt + p.eps);
+    // fold mean/rstd, affine and the AdaGN scale/shift into y = x * A + B
+    for (int cc = lane; cc < p.cpg; cc += 32) {
+      const int c = c0 + g * p.cpg + cc;
+      float ga = p.gamma ? __ldg(p.gamma + c) : 1.f;
+      float be = p.beta ? __ldg(p.beta + c) : 0.f;
+      if (p.scale) {
+        const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c);
+        ga *= sc;
+        be = be * sc + __ldg(p.shift + (size_t)n * p.ss_ld + c);
+      }
+      coefA[g * p.cpg + cc] = rstd * ga;
+      coefB[g * p.cpg + cc] = be - mean * rstd * ga;
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 3: normalise (+SiLU) (+resample) and write bf16 ----
+  if (p.resample == 0) {
+    for (int idx = tid; idx < total; idx += 256) {
+      const int px = idx / nv;
+      const int j = idx - px * nv;
+      float v[V], a[V], b[V];
+      lds_vec<V>(slab + px * pitch + j * V, v);
+      lds_vec<V>(coefA + j * V, a);
+      lds_vec<V>(coefB + j * V, b);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float y = v[i] * a[i] + b[i];
+        v[i] = p.apply_silu ? silu_f(y) : y;
+      }
+      store_bf16_vec<V>(p.out + ((size_t)n * p.HW + px) * C + c0 + j * V, v);
+    }
+  } else if (p.resample == 1) {  // 2x2 average pool of the activated values
+    const int H = p.HW / p.W, Wo = p.W / 2, Ho = H / 2;
+    const int total_o = Ho * Wo * nv;
+    for (int idx = tid; idx < total_o; idx += 256) {
+      const int po = idx / nv;
+      const int j = idx - po * nv;
+      const int oy = po / Wo, ox = po - oy * Wo;
+      float v[V], a[V], b[V];
+      lds_vec<V>(coefA + j * V, a);
+      lds_vec<V>(coefB + j * V, b);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int px = (2 * oy + dy) * p.W + 2 * ox + dx;
+          float t[V];
+          lds_vec<V>(slab + px * pitch + j * V, t);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float y = t[i] * a[i] + b[i];
+            v[i] += p.apply_silu ? silu_f(y) : y;
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] *= 0.25f;
+      store_bf16_vec<V>(p.out + ((size_t)n * (Ho * Wo) + po) * C + c0 + j * V, v);
+    }
+  } else {  // nearest 2x
+    const int Wo = p.W * 2;
+    for (int idx = tid; idx < total; idx += 256) {
+      const int px = idx / nv;
+      const int j = idx - px * nv;
+      const int iy = px / p.W, ix = px - iy * p.W;
+      float v[V], a[V], b[V];
+      lds_vec<V>(slab + px * pitch + j * V, v);
+      lds_vec<V>(coefA + j * V, a);
+      lds_vec<V>(coefB + j * V, b);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float y = v[i] * a[i] + b[i];
+        v[i] = p.apply_silu ? silu_f(y) : y;
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t po = (size_t)(2 * iy + dy) * Wo + 2 * ix + dx;
+          store_bf16_vec<V>(p.out + ((size_t)n * (4 * p.HW) + po) * C + c0 + j * V, v);
+        }
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, int B, int HW, int W,
+                                       int groups, const float* gamma, const float* beta, float eps,
+                                       const float* scale, const float* shift, int ss_ld, int apply_silu,
+                                       int resample, void* out_bf16, void* raw_out_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x0 && out_bf16, "groupnorm: null x0/out");
+  if (!x1) C1 = 0;
+  const int C = C0 + C1;
+  B200_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+  const int cpg = C / groups;
+  B200_REQUIRE(cpg % 2 == 0 && C0 % 2 == 0, "groupnorm: channels per group (%d) and C0 (%d) must be even", cpg, C0);
+  B200_REQUIRE(resample >= 0 && resample <= 2, "groupnorm: bad resample mode");
+  B200_REQUIRE(W > 0 && HW % W == 0, "groupnorm: HW=%d not a multiple of W=%d", HW, W);
+  if (resample == 1) B200_REQUIRE(W % 2 == 0 && (HW / W) % 2 == 0, "groupnorm: avg-pool needs even H, W");
+  B200_REQUIRE((scale == nullptr) == (shift == nullptr), "groupnorm: scale and shift must be given together");
+  const int V = (cpg % 4 == 0 && C0 % 4 == 0) ? 4 : 2;
+  // groups per CTA: largest power of two (<= groups) whose slab stays <= 64 KB; fall back to 1 group up to 200 KB
+  int gpc = 1;
+  for (int g = groups; g >= 1; g >>= 1) {
+    if ((size_t)HW * (g * cpg + 4) * 4 <= 64 * 1024) { gpc = g; break; }
+  }
+  const size_t smem = ((size_t)HW * (gpc * cpg + 4) + 2 * (size_t)gpc * cpg) * 4;
+  B200_REQUIRE(smem <= 200 * 1024, "groupnorm: slab of %zu bytes (HW=%d, %d ch/group) exceeds the single-CTA path",
+               smem, HW, cpg);
+  GnParams p;
+  p.x0 = x0; p.C0 = C0; p.x1 = x1; p.C1 = C1;
+  p.HW = HW; p.W = W; p.groups = groups; p.cpg = cpg; p.gpc = gpc;
+  p.chunks = (groups + gpc - 1) / gpc;
+  p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
+  p.apply_silu = apply_silu; p.resample = resample;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
+  const int grid = B * p.chunks;
+  if (V == 4) {
+    static bool attr4 = false;
+    if (!attr4) {
+      B200_CHECK(cudaFuncSetAttribute(groupnorm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr4 = true;
+    }
+    groupnorm_kernel<4><<<grid, 256, smem, stream>>>(p);
+  } else {
+    static bool attr2 = false;
+    if (!attr2) {
+      B200_CHECK(cudaFuncSetAttribute(groupnorm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr2 = true;
+    }
+    groupnorm_kernel<2><<<grid, 256, smem, stream>>>(p);
+  }
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "groupnorm_kernel launch");
+}

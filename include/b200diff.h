@@ -1,0 +1,175 @@
+/*
+ * b200diff.h -- C ABI of libb200diff.so: the B200 (sm_100a) kernels behind the diffusion hot path.
+ *
+ * The reference (xyfJASON/diffusion-models-pytorch) has no FFI of its own: its boundary is the Python
+ * call surface `model(x, t, **kw)` / `DDPM.denoise(...)`.  Each entry point below therefore cites the
+ * reference ATen call sequence it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer owned by the caller (PyTorch); the library never allocates
+ *     user-visible memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - activations handed between kernels are NHWC ("pixel-major"): fp32 for the residual stream,
+ *     bf16 for tensor-core operands; model inputs/outputs are the reference's NCHW fp32;
+ *   - return value 0 = ok; otherwise a cudaError_t or >= 1000 for argument errors,
+ *     with text from b200_last_error().
+ */
+#ifndef B200DIFF_H_
+#define B200DIFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DIFF_VERSION 100
+
+int b200_version(void);
+const char* b200_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+long long b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1: convolution as implicit GEMM on tcgen05/TMEM, operands fed by TMA.
+ * Replaces nn.Conv2d 3x3/1x1 (models/unet.py:16,26,28,72,118; models/modules.py:64,72,83-86) plus the
+ * adds fused around it: bias, time-embedding broadcast add (models/unet.py:41), residual / shortcut add
+ * (models/unet.py:43, models/modules.py:100) and the nearest-2x of Upsample (models/modules.py:63).
+ *
+ * D[M = B*Ho*Wo pixels, N] = sum over K-blocks of A[M, 64] * W[N, 64]^T, where K runs over
+ * (tap, 64-channel chunk) of source a0 and then over the 64-channel chunks of the optional source a1
+ * (used to fold the 1x1 shortcut conv of a ResBlock into the GEMM of its second 3x3 conv).
+ * A source is a bf16 tensor [B][planes][Hs][Ws][C]; the A rows of output pixel (n, ho, wo) for a tap
+ * (dw, dh, plane) are read at (n, plane, ho + dh, wo + dw, :) with zero fill outside [0,Hs)x[0,Ws).
+ * Stride-2 convs use 4 parity planes; plain convs use planes = 1.
+ * phases = 4 runs the four 2x2-tap sub-convolutions that together equal "nearest-2x then 3x3"; phase p
+ * writes output pixel (2*ho + (p>>1), 2*wo + (p&1)) and uses weight rows [p*w_rows_per_phase, ...).
+ * --------------------------------------------------------------------------------------------- */
+enum { B200_OUT_F32_NHWC = 0, B200_OUT_BF16_NHWC = 1, B200_OUT_F32_NCHW = 2, B200_OUT_BF16_NCHW = 3 };
+
+typedef struct b200_conv_desc {
+  const void* a0;      /* bf16 source 0 */
+  int a0_C, a0_H, a0_W, a0_planes;
+  const void* a1;      /* bf16 source 1 (single tap) or NULL */
+  int a1_C, a1_H, a1_W, a1_planes;
+  const void* w;       /* packed bf16 weights [w_rows][w_K], K contiguous: K = ntaps0*a0_C + a1_C */
+  int w_rows, w_K, w_rows_per_phase;
+  int B, Ho, Wo;       /* output-tile pixel grid */
+  int phases;          /* 1 or 4 */
+  int N;               /* output channels */
+  int ntaps0;          /* taps of source 0 (1, 4 or 9) */
+  int8_t taps0[4][9][4]; /* [phase][tap] = {dw, dh, plane, 0} */
+  int8_t tap1[4];      /* {dw, dh, plane, 0} of source 1 */
+  const float* bias;     /* [N] or NULL */
+  const float* rowadd;   /* per-image additive row [B][rowadd_ld] (time embedding projection) or NULL */
+  int rowadd_ld;
+  const float* residual; /* fp32 NHWC [B][out_H][out_W][res_ld] or NULL */
+  int res_ld;
+  void* out;
+  int out_mode;        /* B200_OUT_* */
+  int out_ld;          /* channel stride of NHWC outputs; for NCHW outputs the channel count */
+  int out_H, out_W;    /* output image size in pixels */
+  int osy, osx;        /* output pixel = (ho*osy + (phase>>1), wo*osx + (phase&1)) */
+} b200_conv_desc;
+
+int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
+
+/* First convolution of the UNet (models/unet.py:72,123): NCHW fp32 image, tiny Cin (1..4), 3x3 s1 p1,
+ * -> fp32 NHWC [B][H][W][Cout].  Weights are the reference's OIHW fp32 tensor as is. */
+int b200_conv3x3_first(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc,
+                       int B, int Cin, int H, int W, int Cout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3: GroupNorm (+ optional per-sample scale/shift = AdaGN) (+ optional SiLU), fp32 NHWC in, bf16 NHWC out.
+ * Replaces nn.GroupNorm + nn.SiLU (models/unet.py:14-15,23-24,116-117; models/modules.py:82,105-123) and
+ * the torch.cat of the skip connection (models/unet.py:145): two fp32 sources are normalised as one
+ * concatenated tensor of C0 + C1 channels.  Statistics are exact two-pass fp32 over a slab staged in
+ * shared memory.  raw_out (optional) receives the un-normalised concatenation rounded to bf16 (operand of
+ * the 1x1 shortcut conv).  resample: 0 none, 1 = 2x2 average pool, 2 = nearest 2x, applied to the activated values
+ * before the single rounding to bf16 (up/down ResBlocks, models/unet_categorial_adagn.py:52-57).
+ * --------------------------------------------------------------------------------------------- */
+int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, int B, int HW, int W, int groups,
+                            const float* gamma, const float* beta, float eps, const float* scale,
+                            const float* shift, int ss_ld, int apply_silu, int resample, void* out_bf16,
+                            void* raw_out_bf16, void* stream);
+
+/* fp32 NHWC -> bf16 NHWC, optionally split into the 4 parity planes [B][2*(h&1)+(w&1)][H/2][W/2][C] that
+ * the stride-2 convolution (models/modules.py:72) reads through unit-stride TMA boxes. */
+int b200_cast_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, int parity_split, void* stream);
+
+/* 2x2 average pool / nearest 2x on fp32 NHWC (models/unet_categorial_adagn.py:26-28). */
+int b200_avgpool2_f32(const float* x, float* out, int B, int H, int W, int C, void* stream);
+int b200_upsample2_f32(const float* x, float* out, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2: fused softmax(q k^T * scale) v for the low-resolution self-attention blocks
+ * (models/modules.py:92-97).  T <= 256 keys, head dim d in {64,128,256}; S and O live in TMEM.
+ * q, k: bf16 [B][T][ld_qk] at column offsets q_off + h*d / k_off + h*d; v transposed: bf16 [B][heads*d][T].
+ * out: bf16 [B][T][ld_out], head h at columns [h*d, (h+1)*d).
+ * --------------------------------------------------------------------------------------------- */
+int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
+                       int B, int T, int heads, int d, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Time embedding path (models/modules.py:40-57, models/unet.py:64-69,18-21).
+ * b200_time_embed: t[rows] (int64) -> [sin(t f), cos(t f)] over the dim/2 frequencies `freqs` (cos first when
+ *   cos_first, the ADM variant models/adm/nn.py:103-121) -> Linear(dim,E) -> SiLU -> Linear(E,E) (+ class
+ *   embedding row y[b] when y != NULL) -> out fp32 [rows][E]; out_silu_bf16 (optional) = SiLU(out) as bf16, the
+ *   operand of the per-ResBlock projections, which run on K1 as one 1x1 "conv" over all blocks.
+ * --------------------------------------------------------------------------------------------- */
+int b200_time_embed(const int64_t* t, int rows, const float* freqs, int dim, int E, int cos_first, const float* w1,
+                    const float* b1, const float* w2, const float* b2, const int64_t* y, const float* class_embed,
+                    float* out, void* out_silu_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4: fused sampler update (diffusions/ddpm.py:174-261, diffusions/ddim.py:57-86, CFG mix
+ * diffusions/ddim.py:177-187 / ddpm.py:335-347).  One elementwise pass over NCHW fp32 tensors:
+ *   [cond/uncond eps -> x0 -> clip -> eps] -> CFG mix -> x0 -> clip -> eps -> mean -> + sqrt(var)*noise.
+ * coef points at one row of the per-step coefficient table in DEVICE memory (so a captured CUDA graph
+ * can be replayed with a different row): see B200_SC_* indices.
+ * --------------------------------------------------------------------------------------------- */
+enum {
+  B200_SC_SQRT_RECIP_AC = 0, /* (1/ac_t)^0.5 */
+  B200_SC_SQRT_RECIPM1_AC,   /* (1/ac_t - 1)^0.5 */
+  B200_SC_SQRT_AC,           /* ac_t^0.5 (pred_v) */
+  B200_SC_SQRT_1M_AC,        /* (1-ac_t)^0.5 (pred_v) */
+  B200_SC_X0_COEF,           /* DDPM: mean_coef1; DDIM: sqrt(ac_prev) */
+  B200_SC_XT_COEF,           /* DDPM: mean_coef2; DDIM: 0 */
+  B200_SC_EPS_COEF,          /* DDPM: 0; DDIM: sqrt(1-ac_prev-var) */
+  B200_SC_VAR,               /* fixed variance (0 at t == 0) */
+  B200_SC_MIN_LOGVAR,        /* learned_range */
+  B200_SC_MAX_LOGVAR,        /* learned_range */
+  B200_SC_ADD_NOISE,         /* 1.0 if t != 0 else 0.0 */
+  B200_SC_COUNT = 12
+};
+enum { B200_OBJ_EPS = 0, B200_OBJ_X0 = 1, B200_OBJ_V = 2 };
+
+typedef struct b200_sampler_desc {
+  const float* model_out;    /* [B][Cm][HW], Cm = C or 2C (learned variance) */
+  const float* model_out_uncond; /* CFG second branch or NULL */
+  const float* xt;           /* [B][C][HW] */
+  const float* noise;        /* [B][C][HW] or NULL (treated as 0) */
+  const float* coef;         /* device pointer to B200_SC_COUNT floats */
+  int B, C, Cm, HW;
+  int objective;             /* B200_OBJ_*; for CFG the mix is always done in eps space */
+  int clip;                  /* clip_denoised */
+  int learned_range;         /* per-pixel variance from channels [C, 2C) of model_out */
+  double guidance_scale;     /* s; the mix is (1-s)*eps_uncond + s*eps_cond with both scalars rounded to fp32 */
+  float* sample;             /* outputs, each optional (NULL = skip) */
+  float* mean;
+  float* pred_x0;
+  float* pred_eps;
+  float* var_out;            /* only written when learned_range */
+} b200_sampler_desc;
+
+int b200_sampler_step(const b200_sampler_desc* d, void* stream);
+
+/* q(x_t | x_0) (diffusions/ddpm.py:152-172): xt = sqrt(ac[t_b]) x0 + sqrt(1-ac[t_b]) eps, per-sample t. */
+int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
+                 int B, int CHW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DIFF_H_ */

@@ -1,0 +1,442 @@
+"""Per-kernel parity cases for libb200diff (run on a B200).
+
+Each case calls ONE C-ABI entry point through the ctypes binding and compares with a plain PyTorch fp32
+restatement of the same op on the same (bf16-rounded where the kernel rounds) inputs.  Tolerances are written
+next to each case.  Run as `python tests/kernel_cases.py <case> [...]` (one process per case keeps a faulting
+kernel from poisoning the CUDA context of the others); `tests/test_kernels_gpu.py` drives it under pytest.
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'diffusion-models-pytorch_b200'))
+
+import b200diff as K  # noqa: E402
+
+DEV = 'cuda'
+
+
+def _report(name, got, ref, rtol, atol):
+    got = got.float()
+    ref = ref.float()
+    diff = (got - ref).abs()
+    denom = ref.norm().item() + 1e-30
+    rel_l2 = (got - ref).norm().item() / denom
+    bad = diff > (atol + rtol * ref.abs())
+    nbad = int(bad.sum().item())
+    info = {
+        'case': name, 'shape': list(got.shape), 'max_abs': diff.max().item(), 'rel_l2': rel_l2,
+        'ref_absmax': ref.abs().max().item(), 'mismatch': nbad, 'numel': got.numel(),
+        'finite': bool(torch.isfinite(got).all().item()),
+    }
+    if nbad:
+        idx = torch.nonzero(bad)
+        info['first_bad'] = idx[0].tolist()
+        info['last_bad'] = idx[-1].tolist()
+        flat = diff.flatten().argmax().item()
+        info['argmax'] = list(torch.unravel_index(torch.tensor(flat), got.shape))
+        info['argmax'] = [int(v) for v in info['argmax']]
+        info['got_at_max'] = got.flatten()[flat].item()
+        info['ref_at_max'] = ref.flatten()[flat].item()
+        # which slices along each dim are affected
+        for d in range(got.dim()):
+            other = [i for i in range(got.dim()) if i != d]
+            per = bad.sum(dim=other)
+            info[f'bad_along_dim{d}'] = [int(i) for i in torch.nonzero(per).flatten()[:16].tolist()]
+    info['ok'] = (nbad == 0) and info['finite']
+    print(json.dumps(info))
+    return info['ok']
+
+
+def _bf16r(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _nhwc_bf16(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ----------------------------------------------------------------------------------------------------
+# conv cases
+# ----------------------------------------------------------------------------------------------------
+def _conv_case(name, B, Cin, Cout, H, W, ksize=3, stride=1, bias=True, rowadd=False, residual=False,
+               out_mode=K.OUT_F32_NHWC, sc_cin=0, pad_lo=1):
+    x = _bf16r(_gen(B, Cin, H, W, seed=1))
+    w = _bf16r(_gen(Cout, Cin, ksize, ksize, seed=2, scale=1.0 / math.sqrt(Cin * ksize * ksize)))
+    b = _gen(Cout, seed=3) if bias else None
+    Ho, Wo = H // stride, W // stride
+    ra = _gen(B, Cout + 64, seed=4) if rowadd else None  # wider row to exercise the leading dimension
+    res_nchw = _gen(B, Cout, Ho, Wo, seed=5) if residual else None
+    x1 = w1 = None
+    if sc_cin:
+        x1 = _bf16r(_gen(B, sc_cin, Ho, Wo, seed=6))
+        w1 = _bf16r(_gen(Cout, sc_cin, 1, 1, seed=7, scale=1.0 / math.sqrt(sc_cin)))
+    # ---- reference ----
+    if stride == 1:
+        ref = F.conv2d(x, w, None, stride=1, padding=ksize // 2)
+    else:
+        xp = F.pad(x, (1, 1, 1, 1)) if pad_lo == 1 else F.pad(x, (0, 1, 0, 1))
+        ref = F.conv2d(xp, w, None, stride=2, padding=0)
+    if sc_cin:
+        ref = ref + F.conv2d(x1, w1)
+    if bias:
+        ref = ref + b[None, :, None, None]
+    if rowadd:
+        ref = ref + ra[:, :Cout, None, None]
+    if residual:
+        ref = ref + res_nchw
+    # ---- kernel ----
+    if stride == 1:
+        a0 = _nhwc_bf16(x)
+        geom = (Cin, H, W, 1)
+        taps = K.taps_3x3_s1() if ksize == 3 else K.taps_1x1()
+    else:
+        a0 = torch.empty(B, 4, H // 2, W // 2, Cin, device=DEV, dtype=torch.bfloat16)
+        K.cast_bf16(x.permute(0, 2, 3, 1).contiguous(), a0, B, H, W, Cin, parity_split=True)
+        geom = (Cin, H // 2, W // 2, 4)
+        taps = K.taps_3x3_s2(pad_lo)
+    wp = K.pack_weight(w, w1)
+    if out_mode in (K.OUT_F32_NHWC, K.OUT_BF16_NHWC):
+        out = torch.full((B, Ho, Wo, Cout), float('nan'), device=DEV,
+                         dtype=torch.float32 if out_mode == K.OUT_F32_NHWC else torch.bfloat16)
+    else:
+        out = torch.full((B, Cout, Ho, Wo), float('nan'), device=DEV,
+                         dtype=torch.float32 if out_mode == K.OUT_F32_NCHW else torch.bfloat16)
+    res = res_nchw.permute(0, 2, 3, 1).contiguous() if residual else None
+    K.conv2d(a0, wp, Cout, B, Ho, Wo, taps, a0_geom=geom,
+             a1=_nhwc_bf16(x1) if sc_cin else None, a1_geom=(sc_cin, Ho, Wo, 1) if sc_cin else None,
+             bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0, residual=res, res_ld=Cout, out=out,
+             out_mode=out_mode)
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2) if out_mode in (K.OUT_F32_NHWC, K.OUT_BF16_NHWC) else out
+    # fp32 accumulation order differs from cuDNN/cuBLAS: 1e-4 relative on O(1) values; bf16 outputs: 1 ulp = 2^-8
+    if out_mode in (K.OUT_BF16_NHWC, K.OUT_BF16_NCHW):
+        return _report(name, got, ref, rtol=1e-2, atol=1e-2)
+    return _report(name, got, ref, rtol=2e-4, atol=2e-4)
+
+
+def case_conv_basic():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _conv_case('conv3x3 128->128 @32 plain', 2, 128, 128, 32, 32, bias=False)
+
+
+def case_conv_epilogue():
+    torch.backends.cudnn.allow_tf32 = False
+    return _conv_case('conv3x3 128->128 @32 bias+temb+res', 4, 128, 128, 32, 32, bias=True, rowadd=True,
+                      residual=True)
+
+
+def case_conv_n256():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = _conv_case('conv3x3 256->256 @16', 3, 256, 256, 16, 16, bias=True, residual=True)
+    ok &= _conv_case('conv3x3 128->256 @16', 2, 128, 256, 16, 16, bias=True, rowadd=True)
+    return ok
+
+
+def case_conv_small_hw():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = _conv_case('conv3x3 256->256 @8 B=3 (2 images per tile, ragged)', 3, 256, 256, 8, 8, bias=True)
+    ok &= _conv_case('conv3x3 512->256 @4 B=9 (8 images per tile, ragged)', 9, 512, 256, 4, 4, bias=True,
+                     residual=True)
+    ok &= _conv_case('conv3x3 64->64 @32 (MNIST width)', 2, 64, 64, 32, 32, bias=True)
+    return ok
+
+
+def case_conv_1x1():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = _conv_case('conv1x1 256->512 @16 bf16 NHWC (q,k)', 2, 256, 512, 16, 16, ksize=1, bias=True,
+                    out_mode=K.OUT_BF16_NHWC)
+    ok &= _conv_case('conv1x1 256->256 @16 bf16 NCHW (v^T)', 2, 256, 256, 16, 16, ksize=1, bias=True,
+                     out_mode=K.OUT_BF16_NCHW)
+    ok &= _conv_case('conv1x1 256->256 @16 +res (attn proj)', 2, 256, 256, 16, 16, ksize=1, bias=True, residual=True)
+    return ok
+
+
+def case_conv_shortcut():
+    torch.backends.cudnn.allow_tf32 = False
+    return _conv_case('conv3x3 256->256 @16 + fused 1x1 shortcut 384->256', 2, 256, 256, 16, 16, bias=True,
+                      sc_cin=384)
+
+
+def case_conv_stride2():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = _conv_case('conv3x3 s2 p1 128->128 32->16', 2, 128, 128, 32, 32, stride=2, bias=True)
+    ok &= _conv_case('conv3x3 s2 p1 256->256 8->4', 9, 256, 256, 8, 8, stride=2, bias=True)
+    ok &= _conv_case('conv3x3 s2 pad(0,1,0,1) 128->128 32->16 (pesser)', 2, 128, 128, 32, 32, stride=2, bias=True,
+                     pad_lo=0)
+    return ok
+
+
+def case_conv_lastconv():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = _conv_case('conv3x3 128->3 @32 f32 NCHW (last conv)', 3, 128, 3, 32, 32, bias=True,
+                    out_mode=K.OUT_F32_NCHW)
+    ok &= _conv_case('conv3x3 64->1 @32 f32 NCHW (MNIST last conv)', 2, 64, 1, 32, 32, bias=True,
+                     out_mode=K.OUT_F32_NCHW)
+    return ok
+
+
+def case_conv_up2():
+    """nearest-2x + conv3x3 (models/modules.py:60-67) as the 4-phase 2x2 decomposition."""
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    for (B, C, Co, H) in [(2, 256, 256, 16), (3, 256, 256, 4)]:
+        x = _bf16r(_gen(B, C, H, H, seed=1))
+        w = _gen(Co, C, 3, 3, seed=2, scale=1.0 / math.sqrt(C * 9))
+        b = _gen(Co, seed=3)
+        wp = K.pack_weight_up2(w)  # [4*Co][4*C] bf16 (sums taken in fp32, rounded once)
+        # reference with the SAME effective (summed then rounded) weights: rebuild phase kernels in fp32
+        ref = torch.empty(B, Co, 2 * H, 2 * H, device=DEV)
+        wpf = wp.float().reshape(4, Co, 4, C)
+        xp = F.pad(x, (1, 1, 1, 1))
+        for a in range(2):
+            for bb in range(2):
+                ph = a * 2 + bb
+                k2 = wpf[ph].reshape(Co, 2, 2, C).permute(0, 3, 1, 2).contiguous()  # [Co, C, 2, 2]
+                # tap (i, j) reads low-res offset (i - 1 + a, j - 1 + bb): crop the padded input accordingly
+                sub = xp[:, :, a:a + H + 1, bb:bb + H + 1]
+                ref[:, :, a::2, bb::2] = F.conv2d(sub, k2) + b[None, :, None, None]
+        # and the reference semantics proper: nearest-2x then 3x3 with the unsummed bf16-rounded weights is only
+        # approximately equal (different rounding); check it loosely as well
+        ref_sem = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, b, padding=1)
+        out = torch.full((B, 2 * H, 2 * H, Co), float('nan'), device=DEV)
+        K.conv2d(_nhwc_bf16(x), wp, Co, B, H, H, K.taps_up2_3x3(), a0_geom=(C, H, H, 1), bias=b, out=out,
+                 out_mode=K.OUT_F32_NHWC, w_rows_per_phase=Co)
+        torch.cuda.synchronize()
+        got = out.permute(0, 3, 1, 2)
+        ok &= _report(f'up2+conv3x3 {C}->{Co} @{H}->{2 * H} vs phase-kernel ref', got, ref, 2e-4, 2e-4)
+        ok &= _report(f'up2+conv3x3 {C}->{Co} @{H}->{2 * H} vs nearest+conv fp32-weight ref', got, ref_sem, 2e-2, 2e-2)
+    return ok
+
+
+def case_conv_tproj():
+    """Per-ResBlock time-embedding projections as one 1x1 'conv' over a [B,1,1,E] bf16 operand."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, E, N = 37, 512, 1280
+    x = _bf16r(_gen(B, E, seed=1))
+    w = _bf16r(_gen(N, E, seed=2, scale=1.0 / math.sqrt(E)))
+    b = _gen(N, seed=3)
+    ref = x @ w.t() + b
+    out = torch.full((B, N), float('nan'), device=DEV)
+    K.conv2d(x.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous(), N, B, 1, 1, K.taps_1x1(),
+             a0_geom=(E, 1, 1, 1), bias=b, out=out, out_mode=K.OUT_F32_NHWC)
+    torch.cuda.synchronize()
+    return _report('time-proj linear 512->1280 B=37', out, ref, 2e-4, 2e-4)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GroupNorm
+# ----------------------------------------------------------------------------------------------------
+def _gn_case(name, B, C0, C1, H, W, silu=True, adagn=False, resample=0, raw=False, eps=1e-5):
+    C = C0 + C1
+    x0 = _gen(B, H, W, C0, seed=1) * 2.0 + 0.5
+    x1 = (_gen(B, H, W, C1, seed=2) * 0.5 - 1.0) if C1 else None
+    gamma = _gen(C, seed=3) * 0.2 + 1.0
+    beta = _gen(C, seed=4) * 0.2
+    ys = _gen(B, 2 * C + 8, seed=5) * 0.3 if adagn else None
+    xcat = torch.cat([x0, x1], dim=-1) if C1 else x0
+    xn = xcat.permute(0, 3, 1, 2)
+    ref = F.group_norm(xn, 32, gamma, beta, eps)
+    if adagn:
+        ref = ref * (1 + ys[:, :C, None, None]) + ys[:, C:2 * C, None, None]
+    if silu:
+        ref = F.silu(ref)
+    if resample == 1:
+        ref = F.avg_pool2d(ref, 2, 2)
+    elif resample == 2:
+        ref = F.interpolate(ref, scale_factor=2, mode='nearest')
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    out = torch.full((B, Ho, Wo, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+    rawo = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16) if raw else None
+    K.groupnorm_silu(x0, C0, x1, C1, B, H * W, W, 32, gamma, beta, eps, out,
+                     scale=ys if adagn else None, shift=ys[:, C:] if adagn else None, ss_ld=(2 * C + 8) if adagn else 0,
+                     silu=silu, resample=resample, raw_out=rawo)
+    torch.cuda.synchronize()
+    # output is rounded to bf16 once: half-ulp = 2^-9 relative
+    ok = _report(name, out.permute(0, 3, 1, 2), ref, rtol=5e-3, atol=5e-3)
+    if raw:
+        ok &= _report(name + ' [raw copy]', rawo, xcat.to(torch.bfloat16), 0, 0)
+    return ok
+
+
+def case_groupnorm():
+    ok = _gn_case('GN+SiLU C128 @32', 3, 128, 0, 32, 32)
+    ok &= _gn_case('GN+SiLU C256 @16', 3, 256, 0, 16, 16)
+    ok &= _gn_case('GN+SiLU cat(256,128)=384 @16 (group straddles sources) + raw', 2, 256, 128, 16, 16, raw=True)
+    ok &= _gn_case('GN+SiLU cat(256,256)=512 @4 + raw', 5, 256, 256, 4, 4, raw=True)
+    ok &= _gn_case('GN only C256 @16 (attention norm)', 2, 256, 0, 16, 16, silu=False)
+    ok &= _gn_case('GN+SiLU C64 @32 (2 ch/group, float2 path)', 2, 64, 0, 32, 32)
+    ok &= _gn_case('GN+SiLU cat(128,64)=192 @32 (6 ch/group)', 2, 128, 64, 32, 32, raw=True)
+    ok &= _gn_case('AdaGN+SiLU C256 @8', 3, 256, 0, 8, 8, adagn=True)
+    ok &= _gn_case('GN+SiLU+avgpool C128 @32->16', 2, 128, 0, 32, 32, resample=1)
+    ok &= _gn_case('GN+SiLU+nearest2x C256 @8->16', 2, 256, 0, 8, 8, resample=2)
+    ok &= _gn_case('GN+SiLU eps=1e-6 C128 @16 (pesser)', 2, 128, 0, 16, 16, eps=1e-6)
+    return ok
+
+
+# ----------------------------------------------------------------------------------------------------
+# misc kernels
+# ----------------------------------------------------------------------------------------------------
+def case_misc():
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    for (B, Cin, Cout, H) in [(3, 3, 128, 32), (2, 1, 64, 32)]:
+        x = _gen(B, Cin, H, H, seed=1)
+        w = _gen(Cout, Cin, 3, 3, seed=2, scale=0.3)
+        b = _gen(Cout, seed=3)
+        ref = F.conv2d(x, w, b, padding=1)
+        out = torch.full((B, H, H, Cout), float('nan'), device=DEV)
+        K.conv3x3_first(x, w, b, out)
+        torch.cuda.synchronize()
+        ok &= _report(f'first conv {Cin}->{Cout} @{H}', out.permute(0, 3, 1, 2), ref, 1e-5, 1e-5)
+    x = _gen(2, 8, 8, 128, seed=4)
+    o = torch.empty(2, 8, 8, 128, device=DEV, dtype=torch.bfloat16)
+    K.cast_bf16(x, o, 2, 8, 8, 128)
+    ok &= _report('cast bf16', o, x.to(torch.bfloat16), 0, 0)
+    o = torch.empty(2, 4, 4, 4, 128, device=DEV, dtype=torch.bfloat16)
+    K.cast_bf16(x, o, 2, 8, 8, 128, parity_split=True)
+    refp = torch.stack([x[:, a::2, b::2] for a in range(2) for b in range(2)], dim=1).to(torch.bfloat16)
+    ok &= _report('cast bf16 parity planes', o, refp, 0, 0)
+    o = torch.empty(2, 4, 4, 128, device=DEV)
+    K.avgpool2_f32(x, o, 2, 8, 8, 128)
+    ok &= _report('avgpool2 f32', o.permute(0, 3, 1, 2), F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2), 1e-6, 1e-6)
+    o = torch.empty(2, 16, 16, 128, device=DEV)
+    K.upsample2_f32(x, o, 2, 8, 8, 128)
+    ok &= _report('upsample2 f32', o.permute(0, 3, 1, 2),
+                  F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode='nearest'), 0, 0)
+    # time embedding MLP
+    for (dim, cos_first) in [(128, False), (64, False), (256, True)]:
+        E, Bn = dim * 4, 5
+        t = torch.tensor([0, 1, 500, 980, 999], device=DEV)
+        half = dim // 2
+        if cos_first:
+            freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(DEV)
+        else:
+            freqs = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).to(DEV)
+        w1, b1 = _gen(E, dim, seed=5, scale=0.1), _gen(E, seed=6, scale=0.1)
+        w2, b2 = _gen(E, E, seed=7, scale=0.05), _gen(E, seed=8, scale=0.1)
+        ce = _gen(10, E, seed=9)
+        y = torch.tensor([3, 0, 9, 1, 1], device=DEV)
+        ang = t[:, None].float() * freqs[None]
+        pe = torch.cat([ang.cos(), ang.sin()], -1) if cos_first else torch.cat([ang.sin(), ang.cos()], -1)
+        ref = F.silu(pe @ w1.t() + b1) @ w2.t() + b2 + ce[y]
+        out = torch.empty(Bn, E, device=DEV)
+        outs = torch.empty(Bn, E, device=DEV, dtype=torch.bfloat16)
+        K.time_embed(t, freqs, dim, E, cos_first, w1, b1, w2, b2, out, y=y, class_embed=ce, out_silu_bf16=outs)
+        torch.cuda.synchronize()
+        ok &= _report(f'time_embed dim={dim} cos_first={cos_first}', out, ref, 1e-4, 1e-4)
+        ok &= _report(f'time_embed silu bf16 dim={dim}', outs, F.silu(ref), 1e-2, 1e-2)
+    # diffuse
+    x0, eps = _gen(4, 3, 8, 8, seed=1), _gen(4, 3, 8, 8, seed=2)
+    ac = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000, dtype=torch.float64), 0).float().to(DEV)
+    t = torch.tensor([0, 10, 500, 999], device=DEV)
+    ref = (ac[t] ** 0.5)[:, None, None, None] * x0 + ((1. - ac[t]) ** 0.5)[:, None, None, None] * eps
+    out = torch.empty_like(x0)
+    K.diffuse(x0, eps, t, ac, out)
+    ok &= _report('diffuse', out, ref, 1e-6, 1e-6)
+    return ok
+
+
+# ----------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------
+def _attn_case(name, B, T, heads, d):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    C = heads * d
+    q = _bf16r(_gen(B, T, C, seed=1))
+    k = _bf16r(_gen(B, T, C, seed=2))
+    v = _bf16r(_gen(B, T, C, seed=3))
+    scale = d ** -0.5
+    qh = q.view(B, T, heads, d).transpose(1, 2)
+    kh = k.view(B, T, heads, d).transpose(1, 2)
+    vh = v.view(B, T, heads, d).transpose(1, 2)
+    att = torch.softmax((qh @ kh.transpose(-1, -2)) * scale, dim=-1)
+    ref = (att @ vh).transpose(1, 2).reshape(B, T, C)
+    qk = torch.cat([q, k], dim=-1).to(torch.bfloat16).contiguous()        # [B, T, 2C]
+    vt = v.transpose(1, 2).contiguous().to(torch.bfloat16)                # [B, C, T]
+    out = torch.full((B, T, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+    K.attention(qk, 2 * C, 0, C, vt, out, C, B, T, heads, d, scale)
+    torch.cuda.synchronize()
+    # P and the output are rounded to bf16: 2^-8 relative each
+    return _report(name, out, ref, rtol=2e-2, atol=1e-2)
+
+
+def case_attention():
+    ok = _attn_case('attention T=256 h=1 d=256 (CIFAR UNet)', 3, 256, 1, 256)
+    ok &= _attn_case('attention T=16 h=1 d=256 (bottleneck)', 5, 16, 1, 256)
+    ok &= _attn_case('attention T=256 h=4 d=64 (CFG UNet)', 2, 256, 4, 64)
+    ok &= _attn_case('attention T=64 h=4 d=64 (CFG UNet 8x8)', 3, 64, 4, 64)
+    ok &= _attn_case('attention T=256 h=2 d=128', 2, 256, 2, 128)
+    return ok
+
+
+# ----------------------------------------------------------------------------------------------------
+# sampler step vs the eager op sequence of the reference (restated in oracle/diffusion_ref.py)
+# ----------------------------------------------------------------------------------------------------
+def case_sampler():
+    sys.path.insert(0, ROOT)
+    from oracle import diffusion_ref as R
+    import diffusions
+    ok = True
+    B, C, H = 4, 3, 8
+    xt = _gen(B, C, H, H, seed=1)
+    noise = _gen(B, C, H, H, seed=2)
+    for kind in ('ddpm', 'ddim'):
+        for var_type in (('fixed_small', 'fixed_large', 'learned_range') if kind == 'ddpm' else ('fixed_large',)):
+            for eta in ((0.0, 0.5, 1.0) if kind == 'ddim' else (0.0,)):
+                for objective in ('pred_eps', 'pred_x0', 'pred_v'):
+                    for clip in (True, False):
+                        Cm = 2 * C if var_type == 'learned_range' else C
+                        mo = _gen(B, Cm, H, H, seed=3)
+                        kw = dict(total_steps=1000, objective=objective, clip_denoised=clip, respace_type='uniform',
+                                  respace_steps=50)
+                        if kind == 'ddpm':
+                            ours = diffusions.DDPM(var_type=var_type, device=DEV, **kw)
+                            ref = R.DDPMRef(var_type=var_type, **kw)
+                        else:
+                            ours = diffusions.DDIM(eta=eta, device=DEV, **kw)
+                            ref = R.DDIMRef(eta=eta, **kw)
+                        for (t, tp) in ((980, 960), (500, 480), (20, 0), (0, -1)):
+                            o = ours.denoise(mo.clone(), xt, t, tp, reverse_eps=noise)
+                            r = ref.denoise(mo.clone().cpu(), xt.cpu(), t, tp, reverse_eps=noise.cpu())
+                            for key in ('sample', 'mean', 'pred_x0', 'pred_eps', 'var'):
+                                rv = r[key] if torch.is_tensor(r[key]) else torch.tensor(r[key])
+                                ov = o[key]
+                                # same fp32 op order, non-contracted: agreement to 1e-6 abs + 1e-6 rel
+                                # (learned_range goes through expf: 1e-5)
+                                tol = 1e-5 if var_type == 'learned_range' else 1e-6
+                                good = torch.allclose(ov.cpu().float().expand_as(rv) if ov.dim() == 0 else ov.cpu(),
+                                                      rv, rtol=tol, atol=tol)
+                                if not good:
+                                    _report(f'sampler {kind} {var_type} eta={eta} {objective} clip={clip} t={t} {key}',
+                                            ov.cpu().expand_as(rv) if ov.dim() == 0 else ov.cpu(), rv, tol, tol)
+                                    ok = False
+    print(json.dumps({'case': 'sampler sweep', 'ok': ok}))
+    return ok
+
+
+CASES = {n[5:]: f for n, f in list(globals().items()) if n.startswith('case_')}
+
+if __name__ == '__main__':
+    names = sys.argv[1:] or list(CASES)
+    all_ok = True
+    for n in names:
+        try:
+            okc = CASES[n]()
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({'case': n, 'ok': False, 'exception': repr(e)}))
+            okc = False
+        print(f'=== {n}: {"PASS" if okc else "FAIL"}', flush=True)
+        all_ok &= bool(okc)
+    sys.exit(0 if all_ok else 1)

@@ -1,0 +1,255 @@
+"""Forward executor of the UNets: turns one `model(x, t, y)` call into a sequence of libb200diff kernel launches.
+
+Data layout in HBM:
+  * residual stream / skip connections: fp32 NHWC  [B, H, W, C]   (written by conv epilogues)
+  * tensor-core operands:               bf16 NHWC  [B, H, W, C]   (written once by GroupNorm+SiLU / casts)
+  * conv weights: bf16 [Cout, taps*Cin (+Cin_shortcut)] K-major, prepacked from the fp32 nn.Parameters and
+    re-packed automatically when a parameter changes (optimizer step, load_state_dict, EMA swap)
+  * model input / output: the reference's fp32 NCHW.
+All buffers are torch tensors owned by this object (a static arena per batch shape, which is also what makes
+the whole forward CUDA-graph capturable); the C library never allocates.
+
+Reference call sites replaced: models/unet.py:121-152 (UNet.forward), :30-43 (ResBlock.forward),
+models/modules.py:89-102 (SelfAttentionBlock.forward), models/unet_categorial_adagn.py:44-62,165-208.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+import b200diff as K
+
+
+class Act:
+    """fp32 NHWC activation [B, H, W, C]."""
+    __slots__ = ('t', 'B', 'H', 'W', 'C')
+
+    def __init__(self, t, B, H, W, C):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+
+
+class Engine:
+    def __init__(self, model: nn.Module):
+        self.model = model
+        self._packed: Dict = {}
+        self._sig = None
+        self._arena: Dict = {}
+        self._tproj_index: Optional[Dict[str, int]] = None
+
+    # ------------------------------------------------------------------------------------------
+    # buffers and packed weights
+    # ------------------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    def buf(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype, self.device)
+        t = self._arena.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._arena[key] = t
+        return t
+
+    def refresh(self):
+        """Drops the packed bf16 weights when any parameter was modified or moved."""
+        sig = tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        if sig != self._sig:
+            self._packed.clear()
+            self._sig = sig
+        dev = self.device
+        if dev.type != 'cuda':
+            raise RuntimeError('b200diff models run on a CUDA device only: there is no CPU/PyTorch fallback '
+                               f'(parameters are on {dev})')
+
+    def packed(self, key, make):
+        v = self._packed.get(key)
+        if v is None:
+            with torch.no_grad():
+                v = make()
+            self._packed[key] = v
+        return v
+
+    def w_conv(self, tag, conv: nn.Conv2d, shortcut: Optional[nn.Conv2d] = None):
+        def make():
+            w = K.pack_weight(conv.weight, None if shortcut is None else shortcut.weight)
+            b = conv.bias.detach().float().contiguous()
+            if shortcut is not None:
+                b = (b + shortcut.bias.detach().float()).contiguous()
+            return w, b
+        return self.packed(('conv', tag), make)
+
+    def w_up2(self, tag, conv: nn.Conv2d):
+        return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight),
+                                                  conv.bias.detach().float().contiguous()))
+
+    def w_qk(self, tag, blk):
+        def make():
+            w = torch.cat([K.pack_weight(blk.q.weight), K.pack_weight(blk.k.weight)], dim=0).contiguous()
+            b = torch.cat([blk.q.bias.detach(), blk.k.bias.detach()]).float().contiguous()
+            return w, b
+        return self.packed(('qk', tag), make)
+
+    def w_tproj(self, linears: List[nn.Linear]):
+        """All per-ResBlock embedding projections stacked into one [sum(out), E] bf16 matrix."""
+        def make():
+            w = torch.cat([l.weight.detach() for l in linears], dim=0).to(torch.bfloat16).contiguous()
+            b = torch.cat([l.bias.detach() for l in linears]).float().contiguous()
+            return w, b
+        return self.packed(('tproj',), make)
+
+    # ------------------------------------------------------------------------------------------
+    # ops
+    # ------------------------------------------------------------------------------------------
+    def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
+           ss_ld=0, resample=0):
+        C = x.C + (skip.C if skip is not None else 0)
+        Ho, Wo = x.H, x.W
+        if resample == 1:
+            Ho, Wo = x.H // 2, x.W // 2
+        elif resample == 2:
+            Ho, Wo = x.H * 2, x.W * 2
+        out = self.buf(tag + '.gn', (x.B, Ho, Wo, C), torch.bfloat16)
+        raw_out = self.buf(tag + '.raw', (x.B, x.H, x.W, C), torch.bfloat16) if raw else None
+        K.groupnorm_silu(x.t, x.C, None if skip is None else skip.t, 0 if skip is None else skip.C, x.B, x.H * x.W,
+                         x.W, norm.num_groups, norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift,
+                         ss_ld=ss_ld, silu=silu, resample=resample, raw_out=raw_out)
+        return out, raw_out
+
+    def conv3x3(self, tag, a, B, H, W, Cin, conv, *, rowadd=None, rowadd_ld=0, residual: Optional[Act] = None,
+                sc_a=None, sc_C=0, sc_conv=None, out_mode=K.OUT_F32_NHWC, out=None):
+        Cout = conv.out_channels
+        w, b = self.w_conv(tag, conv, sc_conv)
+        if out is None:
+            out = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
+        K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(Cin, H, W, 1),
+                 a1=sc_a, a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, bias=b,
+                 rowadd=rowadd, rowadd_ld=rowadd_ld, residual=None if residual is None else residual.t,
+                 res_ld=0 if residual is None else residual.C, out=out, out_mode=out_mode)
+        return out
+
+    def attention(self, tag, blk, x: Act) -> Act:
+        B, H, W, C = x.B, x.H, x.W, x.C
+        T, heads = H * W, blk.n_heads
+        d = C // heads
+        if d not in (64, 128, 256) or T > 256 or T % 8 != 0:
+            raise RuntimeError(f'attention block {tag}: T={T}, head_dim={d} not supported by b200_attention_fwd '
+                               '(T <= 256, d in {64,128,256})')
+        n, _ = self.gn(tag, x, None, blk.norm, silu=False)
+        wqk, bqk = self.w_qk(tag, blk)
+        qk = self.buf(tag + '.qk', (B, T, 2 * C), torch.bfloat16)
+        K.conv2d(n, wqk, 2 * C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bqk, out=qk,
+                 out_mode=K.OUT_BF16_NHWC)
+        wv, bv = self.w_conv(tag + '.v', blk.v)
+        vt = self.buf(tag + '.vt', (B, C, T), torch.bfloat16)
+        K.conv2d(n, wv, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bv, out=vt, out_mode=K.OUT_BF16_NCHW)
+        o = self.buf(tag + '.o', (B, T, C), torch.bfloat16)
+        K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, blk.scale)
+        wp, bp = self.w_conv(tag + '.proj', blk.proj)
+        out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
+        K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out)
+        return Act(out, B, H, W, C)
+
+    def downsample_conv(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
+        B, H, W, C = x.B, x.H, x.W, x.C
+        planes = self.buf(tag + '.planes', (B, 4, H // 2, W // 2, C), torch.bfloat16)
+        K.cast_bf16(x.t, planes, B, H, W, C, parity_split=True)
+        w, b = self.w_conv(tag, conv)
+        Cout = conv.out_channels
+        out = self.buf(tag + '.out', (B, H // 2, W // 2, Cout), torch.float32)
+        K.conv2d(planes, w, Cout, B, H // 2, W // 2, K.taps_3x3_s2(pad_lo), a0_geom=(C, H // 2, W // 2, 4), bias=b,
+                 out=out)
+        return Act(out, B, H // 2, W // 2, Cout)
+
+    def upsample_conv(self, tag, conv: nn.Conv2d, x: Act) -> Act:
+        """nearest-2x + conv3x3 as four 2x2-tap phase convolutions on the low-res grid (2.25x fewer MACs)."""
+        B, H, W, C = x.B, x.H, x.W, x.C
+        xb = self.buf(tag + '.bf16', (B, H, W, C), torch.bfloat16)
+        K.cast_bf16(x.t, xb, B, H, W, C)
+        w, b = self.w_up2(tag, conv)
+        Cout = conv.out_channels
+        out = self.buf(tag + '.out', (B, 2 * H, 2 * W, Cout), torch.float32)
+        K.conv2d(xb, w, Cout, B, H, W, K.taps_up2_3x3(), a0_geom=(C, H, W, 1), bias=b, out=out,
+                 w_rows_per_phase=Cout)
+        return Act(out, B, 2 * H, 2 * W, Cout)
+
+    def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
+        """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
+        B, H, W = x.B, x.H, x.W
+        Cin = x.C + (skip.C if skip is not None else 0)
+        conv1, conv2 = blk.blk1[2], blk.blk2[3]
+        Cout = conv1.out_channels
+        has_sc = isinstance(blk.shortcut, nn.Conv2d)
+        a1, raw = self.gn(tag + '.1', x, skip, blk.blk1[0], raw=has_sc)
+        h = self.conv3x3(tag + '.c1', a1, B, H, W, Cin, conv1, rowadd=tproj[:, tproj_off:], rowadd_ld=tproj_ld)
+        a2, _ = self.gn(tag + '.2', Act(h, B, H, W, Cout), None, blk.blk2[0])
+        if has_sc:
+            out = self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
+        else:
+            assert skip is None and Cin == Cout
+            out = self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, residual=x)
+        return Act(out, B, H, W, Cout)
+
+    def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
+        """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""
+        B, H, W = x.B, x.H, x.W
+        Cin = x.C + (skip.C if skip is not None else 0)
+        conv1, conv2 = blk.blk1[2], blk.blk2[2]
+        Cout = conv1.out_channels
+        has_sc = isinstance(blk.shortcut, nn.Conv2d)
+        resample = {'up': 2, 'down': 1}.get(blk.updown_kind, 0)
+        if resample and (has_sc or skip is not None):
+            raise RuntimeError('up/down ResBlocks with a projection shortcut are not supported')
+        a1, raw = self.gn(tag + '.1', x, skip, blk.blk1[0], raw=has_sc, resample=resample)
+        Ho, Wo = (H // 2, W // 2) if resample == 1 else (H * 2, W * 2) if resample == 2 else (H, W)
+        res_x = x
+        if resample == 1:
+            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
+            K.avgpool2_f32(x.t, r, B, H, W, x.C)
+            res_x = Act(r, B, Ho, Wo, x.C)
+        elif resample == 2:
+            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
+            K.upsample2_f32(x.t, r, B, H, W, x.C)
+            res_x = Act(r, B, Ho, Wo, x.C)
+        h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1)
+        a2, _ = self.gn(tag + '.2', Act(h, B, Ho, Wo, Cout), None, blk.adagn.gn, scale=ss[:, ss_off:],
+                        shift=ss[:, ss_off + Cout:], ss_ld=ss_ld)
+        if has_sc:
+            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
+        else:
+            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
+        return Act(out, B, Ho, Wo, Cout)
+
+    # ------------------------------------------------------------------------------------------
+    # embedding path
+    # ------------------------------------------------------------------------------------------
+    def embed(self, T, y, B, pos_emb, lin1, lin2, class_embed, proj_linears):
+        """Returns (proj [rows, sum_out] fp32, ld) where ld = 0 when one row serves the whole batch."""
+        dev = self.device
+        uniform = (T.dim() == 1 and T.shape[0] == B and (B == 1 or T.stride(0) == 0))
+        use_y = class_embed is not None and y is not None
+        rows = 1 if (uniform and not use_y) else B
+        t_rows = (T[:1] if uniform and rows == 1 else T).to(torch.long).contiguous()
+        if use_y:
+            y = y.to(torch.long).contiguous()
+        E = lin1.out_features
+        freqs = self.packed(('freqs',), lambda: pos_emb.frequencies(dev).float().contiguous())
+        emb = self.buf('emb', (rows, E), torch.float32)
+        semb = self.buf('semb', (rows, E), torch.bfloat16)
+        K.time_embed(t_rows, freqs, pos_emb.dim, E, False, lin1.weight, lin1.bias, lin2.weight, lin2.bias, emb,
+                     y=y if use_y else None, class_embed=class_embed.weight if use_y else None, out_silu_bf16=semb)
+        w, b = self.w_tproj(proj_linears)
+        total = w.shape[0]
+        proj = self.buf('tproj', (rows, total), torch.float32)
+        K.conv2d(semb, w, total, rows, 1, 1, K.taps_1x1(), a0_geom=(E, 1, 1, 1), bias=b, out=proj)
+        return proj, (0 if rows == 1 else total)
+
+    @staticmethod
+    def check_input(X, T, in_channels):
+        if X.dim() != 4 or X.shape[1] != in_channels:
+            raise RuntimeError(f'expected input [B, {in_channels}, H, W], got {tuple(X.shape)}')
+        if not X.is_cuda:
+            raise RuntimeError('b200diff models run on CUDA tensors only (no CPU fallback)')
+        if X.dtype != torch.float32:
+            raise RuntimeError(f'expected float32 input, got {X.dtype}')
+        return X.contiguous()

@@ -1,0 +1,122 @@
+"""CUDA-graph replay of the sampling loop's per-timestep work.
+
+The reference loop (diffusions/ddpm.py:263-281, ddim.py:161-191) launches ~480 eager ops per timestep.  Here one
+timestep = {UNet forward (two for classifier-free guidance), the per-step noise draw, the fused sampler update}
+is captured ONCE per (batch shape, conditioning layout) into a CUDA graph whose scalar inputs -- the timestep
+and the row of sampler coefficients -- live in device memory; each loop iteration then costs two 8/48-byte
+device-to-device copies plus one graph launch, with no host<->device synchronisation anywhere in the loop.
+The noise is drawn with torch's Philox generator inside the graph, once per step like the reference
+(ddim.py:76 / ddpm.py:251), so seeded runs consume the RNG stream identically.
+"""
+import torch
+import tqdm
+
+import b200diff as K
+
+
+class SamplingRunner:
+    def __init__(self, model, diffuser):
+        self.model = model
+        self.diffuser = diffuser
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _eager(self, init_noise, tqdm_kwargs, model_kwargs, guidance_scale, uncond_conditioning):
+        d = self.diffuser
+        sample = None
+        if guidance_scale is None:
+            loop = d.sample_loop(self.model, init_noise, tqdm_kwargs, model_kwargs)
+        else:
+            loop = d.sample_loop(self.model, init_noise, uncond_conditioning, tqdm_kwargs, model_kwargs)
+        for out in loop:
+            sample = out['sample']
+        return sample
+
+    def run(self, init_noise, tqdm_kwargs, model_kwargs, guidance_scale, uncond_conditioning):
+        d = self.diffuser
+        cfg = guidance_scale is not None
+        tqdm_kwargs = dict() if tqdm_kwargs is None else tqdm_kwargs
+        if cfg:
+            if d.cond_kwarg not in model_kwargs.keys():
+                raise ValueError(f'Condition argument `{d.cond_kwarg}` not found in model_kwargs.')
+        else:
+            model_kwargs = dict() if model_kwargs is None else model_kwargs
+        # graph mode supports tensor / None keyword arguments only
+        graphable = (init_noise.is_cuda and not torch.cuda.is_current_stream_capturing()
+                     and all(v is None or torch.is_tensor(v) for v in model_kwargs.values())
+                     and (uncond_conditioning is None or torch.is_tensor(uncond_conditioning)))
+        if not graphable:
+            return self._eager(init_noise, tqdm_kwargs, model_kwargs, guidance_scale, uncond_conditioning)
+
+        eng = self.model.engine
+        eng.refresh()
+        layout = tuple(sorted((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in model_kwargs.items()))
+        key = (tuple(init_noise.shape), init_noise.device, cfg, layout,
+               None if uncond_conditioning is None else tuple(uncond_conditioning.shape),
+               d.objective, d.clip_denoised, d.var_type, getattr(d, 'eta', None), guidance_scale)
+        g = self._graphs.get(key)
+        if g is None or g['sig'] != eng._sig:
+            g = self._capture(init_noise, model_kwargs, cfg, guidance_scale, uncond_conditioning)
+            g['sig'] = eng._sig
+            self._graphs[key] = g
+
+        pairs = d._step_pairs()
+        t_table = torch.tensor([t for t, _ in pairs], dtype=torch.long, device=init_noise.device)
+        coef_table = d._coef_table(pairs)
+        g['x'].copy_(init_noise)
+        for k, v in model_kwargs.items():
+            if v is not None:
+                g['kw'][k].copy_(v)
+        if cfg and uncond_conditioning is not None:
+            g['uncond'].copy_(uncond_conditioning)
+        pbar = tqdm.tqdm(total=len(pairs), **tqdm_kwargs)
+        for i in range(len(pairs)):
+            g['t'].copy_(t_table[i:i + 1])
+            g['coef'].copy_(coef_table[i])
+            g['graph'].replay()
+            pbar.update(1)
+        pbar.close()
+        return g['x'].clone()
+
+    # ------------------------------------------------------------------------------------------
+    def _capture(self, init_noise, model_kwargs, cfg, guidance_scale, uncond_conditioning):
+        d, model = self.diffuser, self.model
+        dev = init_noise.device
+        B = init_noise.shape[0]
+        rng = torch.cuda.get_rng_state(dev)   # building the graph must not consume the caller's RNG stream
+        st = {
+            'x': torch.zeros_like(init_noise),
+            't': torch.zeros(1, dtype=torch.long, device=dev),
+            'coef': d._coef_row(*d._step_pairs()[0]).clone(),
+            'kw': {k: (None if v is None else v.clone()) for k, v in model_kwargs.items()},
+            'uncond': None if uncond_conditioning is None else uncond_conditioning.clone(),
+        }
+        out_ch = getattr(model, 'out_channels', init_noise.shape[1])
+        st['out_c'] = torch.empty((B, out_ch) + tuple(init_noise.shape[2:]), dtype=torch.float32, device=dev)
+        st['out_u'] = torch.empty_like(st['out_c']) if cfg else None
+        learned = d.var_type == 'learned_range' and d._uses_learned_var()
+
+        def step():
+            tb = st['t'].expand(B)
+            model(st['x'], tb, out=st['out_c'], **st['kw'])
+            if cfg:
+                ukw = dict(st['kw'])
+                ukw[d.cond_kwarg] = st['uncond']
+                model(st['x'], tb, out=st['out_u'], **ukw)
+            noise = torch.randn_like(st['x'])
+            K.sampler_step(st['out_c'], st['x'], st['coef'], objective=d.objective, clip=d.clip_denoised,
+                           learned_range=learned, noise=noise, model_out_uncond=st['out_u'],
+                           guidance_scale=guidance_scale if cfg else 1.0, sample=st['x'])
+
+        # warm-up on a side stream (fills the arena, packs weights, sets kernel attributes); RNG state preserved
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            step()
+        torch.cuda.set_rng_state(rng, dev)
+        st['graph'] = graph
+        return st

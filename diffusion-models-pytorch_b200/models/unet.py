@@ -1,0 +1,187 @@
+"""DDPM-style UNet on the B200 kernels (drop-in for the reference's models/unet.py: same constructor
+arguments, parameter names, registration order and `model(X, T)` call, reference models/unet.py:46-152).
+
+The module owns fp32 parameters exactly like the reference (so `state_dict()` / `load_state_dict()` /
+`models.EMA` / torch optimizers interoperate); `forward` issues libb200diff kernels through models/engine.py:
+GroupNorm+SiLU (K3) -> tcgen05 implicit-GEMM convs with fused bias / time-embedding / shortcut (K1) ->
+fused attention (K2).  Dropout is the identity in eval mode; training mode is rejected until the backward
+kernels land (there is no autograd fallback).
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+import b200diff as K
+from models.engine import Act, Engine
+from models.modules import Downsample, SelfAttentionBlock, SinusoidalPosEmb, Upsample, _KernelOnly
+from models.runner import SamplingRunner
+
+
+class ResBlock(_KernelOnly):
+    """GN-SiLU-conv3x3 (+ time embedding) -> GN-SiLU-dropout-conv3x3, plus identity / 1x1 shortcut."""
+
+    def __init__(self, in_channels: int, out_channels: int, embed_dim: int, dropout: float = 0.1):
+        super().__init__()
+        self.blk1 = nn.Sequential(
+            nn.GroupNorm(32, in_channels), nn.SiLU(), nn.Conv2d(in_channels, out_channels, 3, stride=1, padding=1))
+        self.proj = nn.Sequential(nn.SiLU(), nn.Linear(embed_dim, out_channels))
+        self.blk2 = nn.Sequential(
+            nn.GroupNorm(32, out_channels), nn.SiLU(), nn.Dropout(dropout),
+            nn.Conv2d(out_channels, out_channels, 3, stride=1, padding=1))
+        self.shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
+
+
+class _EngineModel(nn.Module):
+    """Shared plumbing of the engine-backed UNets."""
+    use_cuda_graph = True
+
+    def _init_engine(self):
+        self.__dict__['_engine'] = Engine(self)     # not a submodule / not in state_dict
+        self.__dict__['_runners'] = {}
+
+    @property
+    def engine(self) -> Engine:
+        return self.__dict__['_engine']
+
+    def make_sampling_runner(self, diffuser):
+        """Per-diffuser CUDA-graph sampler used by DDPM/DDIM(.CFG).sample()."""
+        key = id(diffuser)
+        r = self.__dict__['_runners'].get(key)
+        if r is None or r.diffuser is not diffuser:
+            r = SamplingRunner(self, diffuser)
+            self.__dict__['_runners'][key] = r
+        return r
+
+    def _reject_training(self):
+        if self.training and torch.is_grad_enabled():
+            has_dropout = any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())
+            raise RuntimeError('b200diff UNet: the training step (backward kernels' +
+                               (', dropout' if has_dropout else '') + ') is not implemented yet; call model.eval() '
+                               'and run under torch.no_grad() for sampling')
+
+
+class UNet(_EngineModel):
+    def __init__(
+            self,
+            in_channels: int = 3,
+            out_channels: int = 3,
+            dim: int = 128,
+            dim_mults: List[int] = (1, 2, 2, 2),
+            use_attn: List[int] = (False, True, False, False),
+            num_res_blocks: int = 2,
+            n_heads: int = 1,
+            dropout: float = 0.1,
+    ):
+        super().__init__()
+        n_stages = len(dim_mults)
+        widths = [dim * m for m in dim_mults]
+        embed_dim = dim * 4
+        self.time_embed = nn.Sequential(
+            SinusoidalPosEmb(dim), nn.Linear(dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, embed_dim))
+        self.first_conv = nn.Conv2d(in_channels, dim, 3, stride=1, padding=1)
+
+        def res(cin, cout):
+            return ResBlock(cin, cout, embed_dim=embed_dim, dropout=dropout)
+
+        # encoder: per stage [res (attn)] * num_res_blocks (+ strided conv); every output is a skip connection
+        skip_widths = [dim]
+        cur = dim
+        self.down_blocks = nn.ModuleList()
+        for i, width in enumerate(widths):
+            stage = nn.ModuleList()
+            for _ in range(num_res_blocks):
+                stage.append(res(cur, width))
+                if use_attn[i]:
+                    stage.append(SelfAttentionBlock(width, n_heads=n_heads))
+                skip_widths.append(width)
+                cur = width
+            if i < n_stages - 1:
+                stage.append(Downsample(width, width))
+                skip_widths.append(width)
+            self.down_blocks.append(stage)
+
+        self.bottleneck_block = nn.ModuleList([res(cur, cur), SelfAttentionBlock(cur), res(cur, cur)])
+
+        # decoder: per stage [res(cat skip) (attn)] * (num_res_blocks + 1) (+ nearest-2x conv)
+        self.up_blocks = nn.ModuleList()
+        for i in reversed(range(n_stages)):
+            width = widths[i]
+            stage = nn.ModuleList()
+            for _ in range(num_res_blocks + 1):
+                stage.append(res(skip_widths.pop() + cur, width))
+                if use_attn[i]:
+                    stage.append(SelfAttentionBlock(width, n_heads=n_heads))
+                cur = width
+            if i > 0:
+                stage.append(Upsample(width, width))
+            self.up_blocks.append(stage)
+
+        self.last_conv = nn.Sequential(
+            nn.GroupNorm(32, cur), nn.SiLU(), nn.Conv2d(cur, out_channels, 3, stride=1, padding=1))
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self._init_engine()
+
+    def _res_blocks(self):
+        blocks = [(f'down_blocks.{i}.{j}', b) for i, st in enumerate(self.down_blocks) for j, b in enumerate(st)]
+        blocks += [(f'bottleneck_block.{j}', b) for j, b in enumerate(self.bottleneck_block)]
+        blocks += [(f'up_blocks.{i}.{j}', b) for i, st in enumerate(self.up_blocks) for j, b in enumerate(st)]
+        return [(n, b) for n, b in blocks if isinstance(b, ResBlock)]
+
+    def forward(self, X: Tensor, T: Tensor, out: Tensor = None):
+        """X: [B, C, H, W] fp32 (NCHW), T: [B] int64 -> [B, C_out, H, W] fp32.  (reference unet.py:121-152)"""
+        self._reject_training()
+        eng = self.engine
+        eng.refresh()
+        X = eng.check_input(X, T, self.in_channels)
+        B, _, H, W = X.shape
+
+        res_blocks = self._res_blocks()
+        offsets, off = {}, 0
+        for name, blk in res_blocks:
+            offsets[name] = off
+            off += blk.proj[1].out_features
+        tproj, tld = eng.embed(T, None, B, self.time_embed[0], self.time_embed[1], self.time_embed[3], None,
+                               [blk.proj[1] for _, blk in res_blocks])
+
+        h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
+        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0)
+        h = Act(h0, B, H, W, self.first_conv.out_channels)
+        skips = [h]
+
+        def run_res(name, blk, x, skip=None):
+            return eng.resblock(name, blk, x, skip, tproj, offsets[name], tld)
+
+        for i, stage in enumerate(self.down_blocks):
+            for j, blk in enumerate(stage):
+                name = f'down_blocks.{i}.{j}'
+                if isinstance(blk, ResBlock):
+                    h = run_res(name, blk, h)
+                    skips.append(h)
+                elif isinstance(blk, SelfAttentionBlock):
+                    h = eng.attention(name, blk, h)
+                    skips[-1] = h
+                else:
+                    h = eng.downsample_conv(name, blk, h)
+                    skips.append(h)
+
+        h = run_res('bottleneck_block.0', self.bottleneck_block[0], h)
+        h = eng.attention('bottleneck_block.1', self.bottleneck_block[1], h)
+        h = run_res('bottleneck_block.2', self.bottleneck_block[2], h)
+
+        for i, stage in enumerate(self.up_blocks):
+            for j, blk in enumerate(stage):
+                name = f'up_blocks.{i}.{j}'
+                if isinstance(blk, ResBlock):
+                    h = run_res(name, blk, h, skips.pop())
+                elif isinstance(blk, SelfAttentionBlock):
+                    h = eng.attention(name, blk, h)
+                else:
+                    h = eng.upsample_conv(name, blk[1], h)
+
+        a, _ = eng.gn('last_conv', h, None, self.last_conv[0])
+        if out is None:
+            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=X.device)
+        eng.conv3x3('last_conv.c', a, B, H, W, h.C, self.last_conv[2], out_mode=K.OUT_F32_NCHW, out=out)
+        return out

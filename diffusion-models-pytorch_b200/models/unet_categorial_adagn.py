@@ -1,0 +1,180 @@
+"""Class-conditional UNet with AdaGN and BigGAN-style up/down residual blocks on the B200 kernels (drop-in for the
+reference's models/unet_categorial_adagn.py:12-208: same constructor arguments, parameter names and order, and
+the `model(X, T, y=None)` call; `y=None` skips the class embedding, which is what classifier-free guidance uses
+for its unconditional branch).
+
+Per ResBlock: GN+SiLU (+2x avg-pool / nearest-2x fused before the single bf16 rounding) -> conv3x3 ->
+AdaGN (scale/shift folded into the GroupNorm kernel's per-channel coefficients) + SiLU -> conv3x3 + shortcut.
+All scale/shift projections Linear(SiLU(emb)) of a forward run as ONE tensor-core GEMM.
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+import b200diff as K
+from models.engine import Act
+from models.modules import AdaGN, Downsample, SelfAttentionBlock, SinusoidalPosEmb, Upsample, _KernelOnly
+from models.unet import _EngineModel
+
+
+class ResBlock(_KernelOnly):
+    def __init__(self, in_channels: int, out_channels: int, embed_dim: int, dropout: float = 0.1,
+                 up: bool = False, down: bool = False):
+        super().__init__()
+        assert not (up and down), 'up and down cannot both be True'
+        self.updown_kind = 'up' if up else 'down' if down else None
+        self.blk1 = nn.Sequential(
+            nn.GroupNorm(32, in_channels), nn.SiLU(), nn.Conv2d(in_channels, out_channels, 3, stride=1, padding=1))
+        self.adagn = AdaGN(32, out_channels, embed_dim)
+        self.blk2 = nn.Sequential(
+            nn.SiLU(), nn.Dropout(dropout), nn.Conv2d(out_channels, out_channels, 3, stride=1, padding=1))
+        self.shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
+
+
+class ResBlockUpsample(ResBlock):
+    def __init__(self, in_channels: int, out_channels: int, embed_dim: int, dropout: float = 0.1):
+        super().__init__(in_channels, out_channels, embed_dim, dropout, up=True)
+
+
+class ResBlockDownsample(ResBlock):
+    def __init__(self, in_channels: int, out_channels: int, embed_dim: int, dropout: float = 0.1):
+        super().__init__(in_channels, out_channels, embed_dim, dropout, down=True)
+
+
+class UNetCategorialAdaGN(_EngineModel):
+    """UNet conditioned on categorial labels with AdaGN."""
+
+    def __init__(
+            self,
+            in_channels: int = 3,
+            out_channels: int = 3,
+            dim: int = 128,
+            dim_mults: List[int] = (1, 2, 2, 2),
+            use_attn: List[int] = (False, True, True, False),
+            num_res_blocks: int = 2,
+            num_classes: int = None,
+            attn_head_dims: int = 64,
+            resblock_updown: bool = True,
+            dropout: float = 0.1,
+    ):
+        super().__init__()
+        n_stages = len(dim_mults)
+        widths = [dim * m for m in dim_mults]
+        embed_dim = dim * 4
+        self.time_embed = nn.Sequential(
+            SinusoidalPosEmb(dim), nn.Linear(dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, embed_dim))
+        self.class_embed = nn.Embedding(num_classes, embed_dim) if num_classes is not None else None
+        self.first_conv = nn.Conv2d(in_channels, dim, 3, stride=1, padding=1)
+
+        def attn(width):
+            assert width % attn_head_dims == 0
+            return SelfAttentionBlock(width, n_heads=width // attn_head_dims)
+
+        skip_widths = [dim]
+        cur = dim
+        self.down_blocks = nn.ModuleList()
+        for i, width in enumerate(widths):
+            stage = nn.ModuleList()
+            for _ in range(num_res_blocks):
+                stage.append(ResBlock(cur, width, embed_dim=embed_dim, dropout=dropout))
+                if use_attn[i]:
+                    stage.append(attn(width))
+                skip_widths.append(width)
+                cur = width
+            if i < n_stages - 1:
+                stage.append(ResBlockDownsample(width, width, embed_dim=embed_dim, dropout=dropout)
+                             if resblock_updown else Downsample(width, width))
+                skip_widths.append(width)
+            self.down_blocks.append(stage)
+
+        self.bottleneck_block = nn.ModuleList([
+            ResBlock(cur, cur, embed_dim=embed_dim, dropout=dropout),
+            SelfAttentionBlock(cur),
+            ResBlock(cur, cur, embed_dim=embed_dim, dropout=dropout),
+        ])
+
+        self.up_blocks = nn.ModuleList()
+        for i in reversed(range(n_stages)):
+            width = widths[i]
+            stage = nn.ModuleList()
+            for _ in range(num_res_blocks + 1):
+                stage.append(ResBlock(skip_widths.pop() + cur, width, embed_dim=embed_dim, dropout=dropout))
+                if use_attn[i]:
+                    stage.append(attn(width))
+                cur = width
+            if i > 0:
+                stage.append(ResBlockUpsample(width, width, embed_dim=embed_dim, dropout=dropout)
+                             if resblock_updown else Upsample(width, width))
+            self.up_blocks.append(stage)
+
+        self.last_conv = nn.Sequential(
+            nn.GroupNorm(32, cur), nn.SiLU(), nn.Conv2d(cur, out_channels, 3, stride=1, padding=1))
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self._init_engine()
+
+    def _res_blocks(self):
+        blocks = [(f'down_blocks.{i}.{j}', b) for i, st in enumerate(self.down_blocks) for j, b in enumerate(st)]
+        blocks += [(f'bottleneck_block.{j}', b) for j, b in enumerate(self.bottleneck_block)]
+        blocks += [(f'up_blocks.{i}.{j}', b) for i, st in enumerate(self.up_blocks) for j, b in enumerate(st)]
+        return [(n, b) for n, b in blocks if isinstance(b, ResBlock)]
+
+    def forward(self, X: Tensor, T: Tensor, y: Tensor = None, out: Tensor = None):
+        """X: [B, C, H, W] fp32, T: [B] int64, y: [B] int64 labels or None -> [B, C_out, H, W] fp32."""
+        self._reject_training()
+        eng = self.engine
+        eng.refresh()
+        X = eng.check_input(X, T, self.in_channels)
+        B, _, H, W = X.shape
+
+        res_blocks = self._res_blocks()
+        offsets, off = {}, 0
+        for name, blk in res_blocks:
+            offsets[name] = off
+            off += blk.adagn.proj[1].out_features
+        ss, ss_ld = eng.embed(T, y, B, self.time_embed[0], self.time_embed[1], self.time_embed[3], self.class_embed,
+                              [blk.adagn.proj[1] for _, blk in res_blocks])
+
+        h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
+        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0)
+        h = Act(h0, B, H, W, self.first_conv.out_channels)
+        skips = [h]
+
+        def run_res(name, blk, x, skip=None):
+            return eng.resblock_adagn(name, blk, x, skip, ss, offsets[name], ss_ld)
+
+        for i, stage in enumerate(self.down_blocks):
+            for j, blk in enumerate(stage):
+                name = f'down_blocks.{i}.{j}'
+                if isinstance(blk, ResBlock):          # includes ResBlockDownsample, as in the reference
+                    h = run_res(name, blk, h)
+                    skips.append(h)
+                elif isinstance(blk, SelfAttentionBlock):
+                    h = eng.attention(name, blk, h)
+                    skips[-1] = h
+                else:
+                    h = eng.downsample_conv(name, blk, h)
+                    skips.append(h)
+
+        h = run_res('bottleneck_block.0', self.bottleneck_block[0], h)
+        h = eng.attention('bottleneck_block.1', self.bottleneck_block[1], h)
+        h = run_res('bottleneck_block.2', self.bottleneck_block[2], h)
+
+        for i, stage in enumerate(self.up_blocks):
+            for j, blk in enumerate(stage):
+                name = f'up_blocks.{i}.{j}'
+                if isinstance(blk, ResBlockUpsample):
+                    h = run_res(name, blk, h)
+                elif isinstance(blk, ResBlock):
+                    h = run_res(name, blk, h, skips.pop())
+                elif isinstance(blk, SelfAttentionBlock):
+                    h = eng.attention(name, blk, h)
+                else:
+                    h = eng.upsample_conv(name, blk[1], h)
+
+        a, _ = eng.gn('last_conv', h, None, self.last_conv[0])
+        if out is None:
+            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=X.device)
+        eng.conv3x3('last_conv.c', a, B, H, W, h.C, self.last_conv[2], out_mode=K.OUT_F32_NCHW, out=out)
+        return out

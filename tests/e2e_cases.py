@@ -1,0 +1,204 @@
+"""End-to-end parity cases on a B200: the engine-backed UNet / samplers against the oracle (oracle/*.py run in
+PyTorch eager fp32 on the same GPU with TF32 disabled) on identical weights, inputs and injected noise.
+
+Gates (BASELINE.json north_star): per-step eps prediction rel-L2 <= 1e-2 (bf16 operands), DDIM-50 final samples
+PSNR >= 40 dB against the fp32 path (peak-to-peak 2.0 for data in [-1, 1]: PSNR = 10 log10(4 / MSE)).
+Run as `python tests/e2e_cases.py <case>`; tests/test_e2e_gpu.py drives it under pytest.
+"""
+import json
+import math
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'diffusion-models-pytorch_b200'))
+sys.path.insert(0, ROOT)
+
+import diffusions  # noqa: E402
+import models  # noqa: E402
+from oracle import diffusion_ref as R  # noqa: E402
+from oracle.unet_ref import UNetRef  # noqa: E402
+
+DEV = 'cuda'
+CIFAR = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, False, False],
+             num_res_blocks=2, n_heads=1, dropout=0.1)
+MNIST = dict(in_channels=1, out_channels=1, dim=64, dim_mults=[1, 2, 2, 2], use_attn=[False, True, False, False],
+             num_res_blocks=2, n_heads=1, dropout=0.1)
+
+
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _build(cfg, seed=2022):
+    torch.manual_seed(seed)
+    m = models.UNet(**cfg).to(DEV).eval()
+    ref = UNetRef(m.state_dict(), dim=cfg['dim'], n_heads=cfg['n_heads']).to(DEV)
+    return m, ref
+
+
+def _rel_l2(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _psnr(a, b):
+    mse = ((a - b) ** 2).mean().item()
+    return 10 * math.log10(4.0 / max(mse, 1e-20))
+
+
+def _emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def case_unet_forward():
+    """Single forward, CIFAR-10 and MNIST configs: rel-L2 of the raw model output vs the fp32 oracle <= 1e-2."""
+    _no_tf32()
+    ok = True
+    for name, cfg, B in (('cifar10', CIFAR, 8), ('mnist', MNIST, 16)):
+        m, ref = _build(cfg)
+        g = torch.Generator(device='cpu').manual_seed(1)
+        x = torch.randn(B, cfg['in_channels'], 32, 32, generator=g).to(DEV)
+        for tvals in ([20, 500, 980], ):
+            t = torch.tensor([tvals[i % len(tvals)] for i in range(B)], device=DEV)
+            with torch.no_grad():
+                got = m(x, t)
+                want = ref(x, t)
+            rel = _rel_l2(got, want)
+            good = rel <= 1e-2 and bool(torch.isfinite(got).all())
+            _emit(case=f'unet_forward {name} B={B} mixed t', rel_l2=rel, gate=1e-2, ok=good,
+                  out_absmax=got.abs().max().item())
+            ok &= good
+        # uniform-t path (stride-0 timestep tensor, one embedding row for the batch)
+        t = torch.full((1,), 500, device=DEV).expand(B)
+        with torch.no_grad():
+            got = m(x, t)
+            want = ref(x, t.contiguous())
+        rel = _rel_l2(got, want)
+        _emit(case=f'unet_forward {name} B={B} uniform t', rel_l2=rel, gate=1e-2, ok=rel <= 1e-2)
+        ok &= rel <= 1e-2
+    return ok
+
+
+def case_ddim50():
+    """DDIM-50 (eta=0, uniform respacing) CIFAR-10 config, B=16: graph-mode sample() vs the fp32 oracle loop."""
+    _no_tf32()
+    m, ref = _build(CIFAR)
+    B = 16
+    g = torch.Generator(device='cpu').manual_seed(2022)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    ours = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, device=DEV)
+    orc = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=50)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    ok = bool(torch.equal(ours.respaced_seq.cpu(), orc.respaced_seq)) and \
+        bool(torch.equal(ours.alphas_cumprod, orc.alphas_cumprod))
+    _emit(case='ddim50 schedules bit-exact', ok=ok)
+    with torch.no_grad():
+        torch.manual_seed(7)
+        got_graph = ours.sample(m, x0, tqdm_kwargs=dict(disable=True))
+        torch.manual_seed(7)
+        got_eager = None
+        eps_rel = []
+        xs = x0
+        for i, out in enumerate(ours.sample_loop(m, x0, tqdm_kwargs=dict(disable=True))):
+            got_eager = out['sample']
+        want = orc.sample(ref, x0, noises=[torch.zeros_like(x0)] * 50)
+        # per-step eps parity along the ORACLE trajectory (same x_t for both models)
+        xt = x0
+        for (t, tp) in orc._pairs():
+            tb = torch.full((B,), t, device=DEV)
+            e_ref = ref(xt, tb)
+            e_our = m(xt, tb)
+            eps_rel.append(_rel_l2(e_our, e_ref))
+            xt = orc.denoise(e_ref, xt, t, tp, torch.zeros_like(xt))['sample']
+    psnr_g, psnr_e = _psnr(got_graph.clamp(-1, 1), want.clamp(-1, 1)), _psnr(got_eager.clamp(-1, 1), want.clamp(-1, 1))
+    same = bool(torch.equal(got_graph, got_eager))
+    _emit(case='ddim50 final sample PSNR (graph)', psnr_db=psnr_g, gate=40.0, ok=psnr_g >= 40.0)
+    _emit(case='ddim50 final sample PSNR (eager loop)', psnr_db=psnr_e, gate=40.0, ok=psnr_e >= 40.0)
+    _emit(case='ddim50 graph replay == eager loop (bitwise)', ok=same)
+    _emit(case='ddim50 per-step eps rel-L2 along oracle trajectory', max=max(eps_rel), mean=sum(eps_rel) / len(eps_rel),
+          gate=1e-2, ok=max(eps_rel) <= 1e-2)
+    return ok and psnr_g >= 40.0 and psnr_e >= 40.0 and same and max(eps_rel) <= 1e-2
+
+
+def case_ddpm_noise():
+    """DDPM (fixed_large, 20 respaced steps) with injected noise: graph RNG stream == eager RNG stream, and
+    the trajectory with identical injected noise stays close to the oracle."""
+    _no_tf32()
+    m, ref = _build(CIFAR)
+    B = 8
+    g = torch.Generator(device='cpu').manual_seed(3)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    ours = diffusions.DDPM(total_steps=1000, respace_type='uniform', respace_steps=20, var_type='fixed_large', device=DEV)
+    orc = R.DDPMRef(total_steps=1000, respace_type='uniform', respace_steps=20, var_type='fixed_large')
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(11)
+        a = ours.sample(m, x0, tqdm_kwargs=dict(disable=True))
+        torch.manual_seed(11)
+        noises, b = [], None
+        for out in ours.sample_loop(m, x0, tqdm_kwargs=dict(disable=True)):
+            b = out['sample']
+            noises.append(out['reverse_eps'])
+        want = orc.sample(ref, x0, noises=noises)
+    same = bool(torch.equal(a, b))
+    psnr = _psnr(b.clamp(-1, 1), want.clamp(-1, 1))
+    _emit(case='ddpm20 graph replay == eager loop (same RNG stream, bitwise)', ok=same)
+    _emit(case='ddpm20 vs oracle with identical injected noise', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+    return same and psnr >= 40.0
+
+
+def case_timing():
+    """Orientation numbers (not the bench): forward and DDIM-50 at B=256."""
+    m, _ = _build(CIFAR)
+    B = 256
+    x = torch.randn(B, 3, 32, 32, device=DEV)
+    t = torch.full((1,), 500, device=DEV).expand(B)
+    with torch.no_grad():
+        for _ in range(3):
+            m(x, t)
+        torch.cuda.synchronize()
+        n0 = sys.modules['b200diff'].launch_count()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            m(x, t)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 5
+        _emit(case='forward B=256 eager launches', ms_gpu=e0.elapsed_time(e1) / 5, ms_wall=wall * 1e3,
+              kernels_per_forward=(sys.modules['b200diff'].launch_count() - n0) // 5,
+              tflops=12.444e9 * B / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e12)
+        d = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, device=DEV)
+        d.sample(m, x, tqdm_kwargs=dict(disable=True))
+        torch.cuda.synchronize()
+        e0.record()
+        d.sample(m, x, tqdm_kwargs=dict(disable=True))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        _emit(case='DDIM-50 B=256 graph', ms=ms, images_per_s=B / (ms * 1e-3), ms_per_step=ms / 50,
+              tflops=12.444e9 * B * 50 / (ms * 1e-3) / 1e12)
+    return True
+
+
+CASES = {n[5:]: f for n, f in list(globals().items()) if n.startswith('case_')}
+
+if __name__ == '__main__':
+    names = sys.argv[1:] or list(CASES)
+    all_ok = True
+    for n in names:
+        try:
+            okc = CASES[n]()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print(json.dumps({'case': n, 'ok': False, 'exception': repr(e)}))
+            okc = False
+        print(f'=== {n}: {"PASS" if okc else "FAIL"}', flush=True)
+        all_ok &= bool(okc)
+    sys.exit(0 if all_ok else 1)

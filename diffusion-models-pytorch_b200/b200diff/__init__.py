@@ -30,6 +30,7 @@ class ConvDesc(Structure):
         ('taps0', c_int8 * 144), ('tap1', c_int8 * 4),
         ('bias', c_void_p), ('rowadd', c_void_p), ('rowadd_ld', c_int),
         ('residual', c_void_p), ('res_ld', c_int),
+        ('stats', c_void_p),
         ('out', c_void_p), ('out_mode', c_int), ('out_ld', c_int), ('out_H', c_int), ('out_W', c_int),
         ('osy', c_int), ('osx', c_int),
     ]
@@ -64,8 +65,11 @@ def lib():
     L.b200_last_error.restype = c_char_p
     L.b200_launch_count.restype = c_longlong
     L.b200_conv2d_fwd.argtypes = [POINTER(ConvDesc), c_void_p]
-    L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                     c_void_p]
+    L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_void_p]
+    L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                           c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,
+                                           c_int, c_void_p, c_void_p, c_void_p]
     L.b200_groupnorm_silu_fwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p]
@@ -78,7 +82,8 @@ def lib():
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
     L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
-    for name in ('b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_cast_bf16',
+    for name in ('b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd',
+                 'b200_cast_bf16',
                  'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd', 'b200_time_embed',
                  'b200_sampler_step', 'b200_diffuse'):
         getattr(L, name).restype = c_int
@@ -88,13 +93,63 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv3x3_first',
-    'b200_groupnorm_silu_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
+    'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse',
 )
 
 
+GRAPH_LAUNCHES = 0   # kernels executed through CUDA-graph replays (captured once, replayed per timestep)
+
+
 def launch_count() -> int:
+    """Kernels of this library launched so far: direct launches plus launches replayed from captured graphs."""
+    return int(lib().b200_launch_count()) + GRAPH_LAUNCHES
+
+
+def direct_launch_count() -> int:
     return int(lib().b200_launch_count())
+
+
+class Profiler:
+    """Per-launch CUDA-event timing of the library's kernels on the current stream (bench.py's roofline leg).
+    Usage: `with K.Profiler() as prof: model(x, t)`; `prof.summary()` -> {kind: dict(n, ms, flops, bytes)}."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _PROFILER
+        _PROFILER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILER
+        _PROFILER = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, nbytes, e0, e1 in self.records:
+            r = out.setdefault(kind, dict(n=0, ms=0.0, flops=0.0, bytes=0.0))
+            r['n'] += 1
+            r['ms'] += e0.elapsed_time(e1)
+            r['flops'] += flops
+            r['bytes'] += nbytes
+        return out
+
+
+_PROFILER = None
+
+
+def _launch(kind, call, flops=0.0, nbytes=0.0):
+    if _PROFILER is None:
+        call()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    _PROFILER.records.append((kind, flops, nbytes, e0, e1))
 
 
 def _check(rc: int, what: str):
@@ -199,7 +254,7 @@ def pack_weight_up2(w: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None, tap1=(0, 0, 0), bias=None,
            rowadd=None, rowadd_ld=0, residual=None, res_ld=0, out=None, out_mode=OUT_F32_NHWC, out_ld=None,
-           out_H=None, out_W=None, w_rows_per_phase=None):
+           out_H=None, out_W=None, w_rows_per_phase=None, stats=None, alg_macs=None):
     """a0_geom = (C, H, W, planes) of the bf16 source tensor [B][planes][H][W][C]."""
     _need_cuda(a0, w_packed, out)
     d = ConvDesc()
@@ -218,36 +273,68 @@ def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None,
     d.bias = _ptr(bias)
     d.rowadd, d.rowadd_ld = _ptr(rowadd), rowadd_ld
     d.residual, d.res_ld = _ptr(residual), res_ld
+    d.stats = _ptr(stats)
     d.out, d.out_mode = out.data_ptr(), out_mode
     d.out_ld = out_ld if out_ld is not None else N
     up = 2 if phases == 4 else 1
     d.out_H = out_H if out_H is not None else Ho * up
     d.out_W = out_W if out_W is not None else Wo * up
     d.osy = d.osx = up
-    _check(lib().b200_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
+    # algorithmic work = MACs of the reference convolution (alg_macs) or, by default, the MACs executed
+    macs = alg_macs if alg_macs is not None else float(phases) * B * Ho * Wo * N * d.w_K
+    _launch('conv_gemm', lambda: _check(lib().b200_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd'),
+            flops=2.0 * macs)
     return out
 
 
-def conv3x3_first(x, w, bias, out):
+def conv3x3_first(x, w, bias, out, stats=None):
     _need_cuda(x, w, out)
     B, Cin, H, W = x.shape
-    _check(lib().b200_conv3x3_first(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, Cin, H, W, w.shape[0],
-                                    _stream()), 'conv3x3_first')
+    Cout = w.shape[0]
+    _launch('conv3x3_first',
+            lambda: _check(lib().b200_conv3x3_first(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(),
+                                                    _ptr(stats), B, Cin, H, W, Cout, _stream()), 'conv3x3_first'),
+            flops=2.0 * B * H * W * Cout * Cin * 9, nbytes=4.0 * B * H * W * (Cin + Cout))
     return out
 
 
 def groupnorm_silu(x0, C0, x1, C1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None, shift=None, ss_ld=0,
                    silu=True, resample=0, raw_out=None):
     _need_cuda(x0, out)
-    _check(lib().b200_groupnorm_silu_fwd(x0.data_ptr(), C0, _ptr(x1), C1, B, HW, W, groups, _ptr(gamma), _ptr(beta),
-                                         float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu), resample,
-                                         out.data_ptr(), _ptr(raw_out), _stream()), 'groupnorm_silu_fwd')
+    _launch('groupnorm_slab',
+            lambda: _check(lib().b200_groupnorm_silu_fwd(x0.data_ptr(), C0, _ptr(x1), C1, B, HW, W, groups, _ptr(gamma),
+                                                         _ptr(beta), float(eps), _ptr(scale), _ptr(shift), ss_ld,
+                                                         int(silu), resample, out.data_ptr(), _ptr(raw_out),
+                                                         _stream()), 'groupnorm_silu_fwd'),
+            nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None))
+    return out
+
+
+def _gn_bytes(B, HW, C, resample, raw):
+    """Algorithmic HBM bytes of GroupNorm+SiLU: fp32 read once, bf16 written once (+ bf16 raw copy)."""
+    out_elems = B * HW * C * ({0: 1.0, 1: 0.25, 2: 4.0}[resample])
+    return 4.0 * B * HW * C + 2.0 * out_elems + (2.0 * B * HW * C if raw else 0.0)
+
+
+def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None,
+                    shift=None, ss_ld=0, silu=True, resample=0, raw_out=None):
+    """Streaming GroupNorm(+SiLU) for inputs whose [B][C][2] statistics came from the producing kernel."""
+    _need_cuda(x0, stats0, out)
+    _launch('groupnorm_apply',
+            lambda: _check(lib().b200_groupnorm_apply_fwd(x0.data_ptr(), C0, stats0.data_ptr(), _ptr(x1), C1,
+                                                          _ptr(stats1), B, HW, W, groups, _ptr(gamma), _ptr(beta),
+                                                          float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu),
+                                                          resample, out.data_ptr(), _ptr(raw_out), _stream()),
+                           'groupnorm_apply_fwd'),
+            nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None))
     return out
 
 
 def cast_bf16(x, out, B, H, W, C, parity_split=False):
     _need_cuda(x, out)
-    _check(lib().b200_cast_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C, int(parity_split), _stream()), 'cast_bf16')
+    _launch('cast_bf16', lambda: _check(lib().b200_cast_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C,
+                                                             int(parity_split), _stream()), 'cast_bf16'),
+            nbytes=6.0 * B * H * W * C)
     return out
 
 
@@ -263,16 +350,21 @@ def upsample2_f32(x, out, B, H, W, C):
 
 def attention(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale):
     _need_cuda(qk, vt, out)
-    _check(lib().b200_attention_fwd(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(), ld_out, B, T,
-                                    heads, d, float(scale), _stream()), 'attention_fwd')
+    _launch('attention',
+            lambda: _check(lib().b200_attention_fwd(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(),
+                                                    ld_out, B, T, heads, d, float(scale), _stream()), 'attention_fwd'),
+            flops=4.0 * B * heads * T * T * d)
     return out
 
 
 def time_embed(t, freqs, dim, E, cos_first, w1, b1, w2, b2, out, *, y=None, class_embed=None, out_silu_bf16=None):
     _need_cuda(t, out)
-    _check(lib().b200_time_embed(t.data_ptr(), t.shape[0], freqs.data_ptr(), dim, E, int(cos_first), w1.data_ptr(),
-                                 b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), _ptr(y), _ptr(class_embed),
-                                 out.data_ptr(), _ptr(out_silu_bf16), _stream()), 'time_embed')
+    _launch('time_embed',
+            lambda: _check(lib().b200_time_embed(t.data_ptr(), t.shape[0], freqs.data_ptr(), dim, E, int(cos_first),
+                                                 w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), _ptr(y),
+                                                 _ptr(class_embed), out.data_ptr(), _ptr(out_silu_bf16), _stream()),
+                           'time_embed'),
+            flops=2.0 * t.shape[0] * (dim * E + E * E))
     return out
 
 
@@ -289,7 +381,9 @@ def sampler_step(model_out, xt, coef_row, *, objective='pred_eps', clip=True, le
     d.guidance_scale = float(guidance_scale)
     d.sample, d.mean, d.pred_x0, d.pred_eps, d.var_out = _ptr(sample), _ptr(mean), _ptr(pred_x0), _ptr(pred_eps), \
         _ptr(var_out)
-    _check(lib().b200_sampler_step(ctypes.byref(d), _stream()), 'sampler_step')
+    n_streams = 2 + sum(v is not None for v in (noise, model_out_uncond, sample, mean, pred_x0, pred_eps, var_out))
+    _launch('sampler_step', lambda: _check(lib().b200_sampler_step(ctypes.byref(d), _stream()), 'sampler_step'),
+            nbytes=4.0 * xt.numel() * n_streams)
 
 
 def diffuse(x0, eps, t, alphas_cumprod, out):

@@ -1,27 +1,33 @@
-// K1: convolution as implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
-// operands staged by TMA with 128-byte swizzle.  Replaces nn.Conv2d + the adds around it in
-// models/unet.py:10-43, models/modules.py:60-102 of the reference (see include/b200diff.h).
+// K1: convolution as implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA with 128-byte swizzle.  Replaces nn.Conv2d + the adds around it in models/unet.py:10-43,
+// models/modules.py:60-102 of the reference (see include/b200diff.h).
 //
-// GEMM view: D[128 pixels x block_n channels] per tile, K-blocks of 64 bf16 = (tap, 64-channel chunk).
-//   A tile  = TMA 5-D box (64 ch, bw, bh, 1 plane, bn images) of an NHWC bf16 activation, shifted by the
-//             tap offset; out-of-image elements are zero-filled by TMA, which *is* the conv padding.
-//   B tile  = TMA 2-D box (64, block_n) of the packed weight matrix [Cout][K].
-// Warp roles (192 threads, persistent over tiles):
-//   warp 0   TMA producer      (ring of `stages` smem slots, full/empty mbarriers)
-//   warp 1   MMA issuer        (single thread; tcgen05.commit releases slots and publishes accumulators)
-//   warps 2-5 epilogue         (tcgen05.ld -> +bias +time-embedding row +residual -> global), overlapped
-//                              with the next tile's MMAs through two TMEM accumulator stages.
+// Channel-major orientation: D^T[128 output channels x NP pixels] per tile, so that
+//   * the UMMA "A" operand is the weight tile  [128 x 64]  (TMA 2-D box of the packed [Cout][K] matrix),
+//   * the UMMA "B" operand is the pixel tile   [NP  x 64]  (TMA 5-D box (64 ch, bw, bh, 1 plane, bn images) of an
+//     NHWC bf16 activation shifted by the tap offset; TMA zero fill outside the image *is* the conv padding),
+//   * TMEM lane = output channel, TMEM column = pixel.  An epilogue warp therefore touches 32 consecutive
+//     channels of one pixel per instruction: residual loads and output stores are 128-byte coalesced, bias and
+//     the time-embedding row are per-lane scalars, and the per-(image, channel) sum / sum-of-squares that the
+//     next GroupNorm needs fall out as per-thread accumulators (one atomicAdd pair per thread per image).
+// NP = 256 pixels (N = 256 UMMA, 85 flop/B of operand traffic) unless the layer is too small to fill the SMs.
+// Warp roles (192 threads, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer (one thread),
+// warps 2-5 epilogue, overlapped with the next tile's MMAs through two TMEM accumulator stages.
 #include "common.cuh"
 #include <string.h>
 #include "../../include/b200diff.h"
 
 namespace b200 {
 
+int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_);
+int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh, int bn);
+
 struct ConvKParams {
-  int B, bw, bh, bn;
+  int B, NP;
+  int bw, bh, bn, lg_bw, lg_bhw;
   int tiles_w, tiles_h;
-  int m_tiles, n_tiles, total_tiles;
-  int N, block_n, w_rows_per_phase;
+  int p_tiles, c_tiles, total_tiles;
+  int N, w_rows_per_phase;
   int cpb0, nkb0, nkb1;
   int stages;
   int8_t taps0[4][9][4];
@@ -31,13 +37,15 @@ struct ConvKParams {
   int rowadd_ld;
   const float* residual;
   int res_ld;
+  float* stats;  // [B][N][2] running (sum, sum of squares) of the fp32 output, or NULL
   void* out;
-  int out_mode, out_ld, out_H, out_W, osy, osx;
+  int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
+  int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
 };
 
-constexpr int kBlockM = 128;
+constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
 constexpr int kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kWBytes = kBlockC * kBlockK * 2;  // 16 KB weight tile
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 
@@ -49,26 +57,45 @@ struct __align__(8) ConvBarriers {
   uint32_t tmem_base;
 };
 
+struct TileCoord {
+  int ph, ct, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  const int per_phase = p.p_tiles * p.c_tiles;
+  t.ph = tile / per_phase;
+  const int rem = tile - t.ph * per_phase;
+  const int pt = rem / p.c_tiles;
+  t.ct = rem - pt * p.c_tiles;
+  const int tw = pt % p.tiles_w;
+  const int th = (pt / p.tiles_w) % p.tiles_h;
+  const int tn = pt / (p.tiles_w * p.tiles_h);
+  t.w0 = tw * p.bw;
+  t.h0 = th * p.bh;
+  t.n0 = tn * p.bn;
+  return t;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvKParams p) {
+                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
+  const int px_bytes = p.NP * kBlockK * 2;
+  const int stage_bytes = kWBytes + px_bytes;
   ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + (size_t)p.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = p.nkb0 + p.nkb1;
-  const uint32_t tmem_cols = (2 * p.block_n <= 32) ? 32u : (2 * p.block_n <= 64)  ? 64u
-                             : (2 * p.block_n <= 128) ? 128u : (2 * p.block_n <= 256) ? 256u : 512u;
+  const uint32_t tmem_cols = (uint32_t)(2 * p.NP);  // 128 / 256 / 512
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
-    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapW);
     if (p.nkb1 > 0) tma_prefetch_desc(&mapA1);
   }
   if (warp == 1 && lane == 0) {
@@ -94,30 +121,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ph = tile / (p.m_tiles * p.n_tiles);
-        const int rem = tile - ph * (p.m_tiles * p.n_tiles);
-        const int mt = rem / p.n_tiles;
-        const int nt = rem - mt * p.n_tiles;
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-        const int wrow = ph * p.w_rows_per_phase + nt * p.block_n;
+        const TileCoord t = decode_tile(p, tile);
+        const int wrow = t.ph * p.w_rows_per_phase + t.ct * kBlockC;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
-          uint8_t* sA = smem + (size_t)stage * stage_bytes;
-          uint8_t* sB = sA + kABytes;
+          uint8_t* sW = smem + (size_t)stage * stage_bytes;
+          uint8_t* sP = sW + kWBytes;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
           if (kb < p.nkb0) {
             const int tap = kb / p.cpb0;
             const int c0 = (kb - tap * p.cpb0) * kBlockK;
-            tma_load_5d(sA, &mapA0, &bars->full[stage], c0, w0 + p.taps0[ph][tap][0], h0 + p.taps0[ph][tap][1],
-                        p.taps0[ph][tap][2], n0);
+            tma_load_5d(sP, &mapA0, &bars->full[stage], c0, t.w0 + p.taps0[t.ph][tap][0],
+                        t.h0 + p.taps0[t.ph][tap][1], p.taps0[t.ph][tap][2], t.n0);
           } else {
             const int c0 = (kb - p.nkb0) * kBlockK;
-            tma_load_5d(sA, &mapA1, &bars->full[stage], c0, w0 + p.tap1[0], h0 + p.tap1[1], p.tap1[2], n0);
+            tma_load_5d(sP, &mapA1, &bars->full[stage], c0, t.w0 + p.tap1[0], t.h0 + p.tap1[1], p.tap1[2], t.n0);
           }
-          tma_load_2d(sB, &mapB, &bars->full[stage], kb * kBlockK, wrow);
+          tma_load_2d(sW, &mapW, &bars->full[stage], kb * kBlockK, wrow);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -125,7 +145,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.NP);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -134,17 +154,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.NP);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + kABytes);
+          const uint32_t w_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t wdesc = umma_desc_kmajor_sw128(w_addr);
+          const uint64_t pdesc = umma_desc_kmajor_sw128(w_addr + kWBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+            umma_bf16(tmem_d, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&bars->empty[stage]);
@@ -156,116 +176,169 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   } else {
     // ================================ epilogue ================================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    const int w_l = r % p.bw;
-    const int h_l = (r / p.bw) % p.bh;
-    const int n_l = r / (p.bw * p.bh);
     const int hw_out = p.out_H * p.out_W;
+    const float* __restrict__ residual = p.residual;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const int ph = tile / (p.m_tiles * p.n_tiles);
-      const int rem = tile - ph * (p.m_tiles * p.n_tiles);
-      const int mt = rem / p.n_tiles;
-      const int nt = rem - mt * p.n_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tn = mt / (p.tiles_w * p.tiles_h);
-      const int n = tn * p.bn + n_l;
-      const int oy = (th * p.bh + h_l) * p.osy + (ph >> 1);
-      const int ox = (tw * p.bw + w_l) * p.osx + (ph & 1);
-      const bool row_ok = n < p.B;
-      const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+      const TileCoord t = decode_tile(p, tile);
+      const int c = t.ct * kBlockC + q * 32 + lane;  // output channel of this thread
+      const bool c_ok = c < p.N;
+      const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
+      const int pa = t.ph >> 1, pb = t.ph & 1;
 
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(as * p.block_n) + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
+      const uint32_t taddr = tmem_base + (uint32_t)(as * p.NP) + ((uint32_t)(q * 32) << 16);
+      float s1 = 0.f, s2 = 0.f, ra_c = 0.f;
+      int cur_n = -1;
+      // fast path: the tile's pixels are consecutive output pixels (full-width rows / whole images, stride 1)
+      const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
+      const float* __restrict__ rbase = residual ? residual + pix0 * (size_t)p.res_ld + c : nullptr;
+      for (int ch = 0; ch < p.NP; ch += 32) {
+        uint32_t v[32];
         __syncwarp();
-        tmem_ld_x16(taddr + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int col0 = nt * p.block_n + c;
-        const int ncols = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= 16)
-        if (row_ok && ncols > 0) {
-          float acc[16];
+        tmem_ld_x32(taddr + (uint32_t)ch, v);
+        // residual prefetch overlaps the TMEM load
+        float r[32];
+        if (residual) {
+          if (p.fast_epi) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-          if (ncols >= 16) {
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
-              }
-            }
-            if (p.rowadd) {
-              const float* ra = p.rowadd + (size_t)n * p.rowadd_ld + col0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ra + j));
-                acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
-              }
-            }
-            if (p.residual) {
-              const float* rs = p.residual + pix * (size_t)p.res_ld + col0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rs + j));
-                acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
-              }
-            }
+            for (int j = 0; j < 32; ++j) r[j] = c_ok ? __ldg(rbase + (ch + j) * p.res_ld) : 0.f;
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < ncols) {
-                if (p.bias) acc[j] += __ldg(p.bias + col0 + j);
-                if (p.rowadd) acc[j] += __ldg(p.rowadd + (size_t)n * p.rowadd_ld + col0 + j);
-                if (p.residual) acc[j] += __ldg(p.residual + pix * (size_t)p.res_ld + col0 + j);
-              }
+            for (int j = 0; j < 32; ++j) {
+              const int pp = ch + j;
+              const int n = t.n0 + (pp >> p.lg_bhw);
+              const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+              const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+              const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+              r[j] = (c_ok && n < p.B) ? __ldg(residual + pix * (size_t)p.res_ld + c) : 0.f;
             }
-          }
-          if (p.out_mode == B200_OUT_F32_NHWC) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + col0;
-            if (ncols >= 16) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < ncols) o[j] = acc[j];
-            }
-          } else if (p.out_mode == B200_OUT_BF16_NHWC) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + col0;
-            if (ncols >= 16) {
-              uint4 u0, u1;
-              u0.x = pack_bf16x2(acc[0], acc[1]);   u0.y = pack_bf16x2(acc[2], acc[3]);
-              u0.z = pack_bf16x2(acc[4], acc[5]);   u0.w = pack_bf16x2(acc[6], acc[7]);
-              u1.x = pack_bf16x2(acc[8], acc[9]);   u1.y = pack_bf16x2(acc[10], acc[11]);
-              u1.z = pack_bf16x2(acc[12], acc[13]); u1.w = pack_bf16x2(acc[14], acc[15]);
-              *reinterpret_cast<uint4*>(o) = u0;
-              *reinterpret_cast<uint4*>(o + 8) = u1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < ncols) o[j] = __float2bfloat16_rn(acc[j]);
-            }
-          } else if (p.out_mode == B200_OUT_F32_NCHW) {
-            // channel-major per image: consecutive lanes hold consecutive pixels -> coalesced per channel
-            float* o = reinterpret_cast<float*>(p.out) + ((size_t)n * p.out_ld + col0) * hw_out + oy * p.out_W + ox;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) o[(size_t)j * hw_out] = acc[j];
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                               ((size_t)n * p.out_ld + col0) * hw_out + oy * p.out_W + ox;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) o[(size_t)j * hw_out] = __float2bfloat16_rn(acc[j]);
           }
         }
+        tmem_ld_wait();
+        float acc[32];
+        if (p.fast_epi) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
+            if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
+              if (p.stats && c_ok && cur_n >= 0) {
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+              }
+              s1 = 0.f; s2 = 0.f;
+              cur_n = n;
+              ra_c = (p.rowadd && c_ok) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+            }
+            const float add_c = bias_c + ra_c;
+#pragma unroll
+            for (int j = 16 * hf; j < 16 * hf + 16; ++j) {
+              float a = __uint_as_float(v[j]) + add_c;
+              if (residual) a += r[j];
+              acc[j] = a;
+              s1 += a;
+              s2 += a * a;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = t.n0 + ((ch + j) >> p.lg_bhw);
+            if (n != cur_n) {
+              if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+              }
+              s1 = 0.f; s2 = 0.f;
+              cur_n = n;
+              ra_c = (p.rowadd && c_ok && n < p.B) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+            }
+            float a = __uint_as_float(v[j]) + bias_c + ra_c;
+            if (residual) a += r[j];
+            acc[j] = a;
+            if (n < p.B) { s1 += a; s2 += a * a; }
+          }
+        }
+        if (p.fast_epi && p.out_mode == B200_OUT_F32_NHWC) {
+          float* __restrict__ ob = reinterpret_cast<float*>(p.out) + pix0 * (size_t)p.out_ld + c;
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = acc[j];
+          }
+        } else if (p.fast_epi && p.out_mode == B200_OUT_BF16_NHWC) {
+          __nv_bfloat16* __restrict__ ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix0 * (size_t)p.out_ld + c;
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = __float2bfloat16_rn(acc[j]);
+          }
+        } else
+        if (p.out_mode == B200_OUT_F32_NHWC) {
+          float* __restrict__ o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int pp = ch + j;
+            const int n = t.n0 + (pp >> p.lg_bhw);
+            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+            const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+            if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = acc[j];
+          }
+        } else if (p.out_mode == B200_OUT_BF16_NHWC) {
+          __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int pp = ch + j;
+            const int n = t.n0 + (pp >> p.lg_bhw);
+            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+            const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+            if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = __float2bfloat16_rn(acc[j]);
+          }
+        } else if (p.vec8_ok) {
+          // channel-major outputs: this thread owns a row of consecutive pixels -> 8-pixel vector stores
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int pp = ch + 8 * g;
+            const int n = t.n0 + (pp >> p.lg_bhw);
+            const int oy = t.h0 + ((pp >> p.lg_bw) & (p.bh - 1));
+            const int ox = t.w0 + (pp & (p.bw - 1));
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + (size_t)oy * p.out_W + ox;
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NCHW) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e);
+                o[0] = make_float4(acc[8 * g], acc[8 * g + 1], acc[8 * g + 2], acc[8 * g + 3]);
+                o[1] = make_float4(acc[8 * g + 4], acc[8 * g + 5], acc[8 * g + 6], acc[8 * g + 7]);
+              } else {
+                uint4 u;
+                u.x = pack_bf16x2(acc[8 * g], acc[8 * g + 1]);
+                u.y = pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]);
+                u.z = pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]);
+                u.w = pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + e) = u;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int pp = ch + j;
+            const int n = t.n0 + (pp >> p.lg_bhw);
+            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + (size_t)oy * p.out_W + ox;
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NCHW) reinterpret_cast<float*>(p.out)[e] = acc[j];
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
+            }
+          }
+        }
+      }
+      if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
       }
       tc_fence_before();
       __syncwarp();
@@ -284,13 +357,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 static int g_num_sms = 0;
 extern long long g_launch_count;
 
-static int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh,
-                      int bn) {
-  uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)planes, (uint64_t)B};
-  uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2,
-                         (uint64_t)planes * H * W * C * 2};
-  uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, 1, (uint32_t)bn};
-  return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
 }
 
 }  // namespace b200
@@ -300,47 +370,60 @@ using namespace b200;
 extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(d != nullptr, "conv2d_fwd: null descriptor");
+  B200_REQUIRE(d->N >= 1, "conv2d_fwd: N must be positive");
+  if (d->N <= 32) {
+    B200_REQUIRE(d->stats == nullptr, "conv2d_fwd: statistics output is not available for N <= 32");
+    return conv2d_fwd_pixm(d, stream_);  // tiny Cout (last conv): pixels on the UMMA M side instead
+  }
   B200_REQUIRE(d->a0 && d->w && d->out, "conv2d_fwd: null a0/w/out");
   B200_REQUIRE(d->a0_C > 0 && d->a0_C % 64 == 0, "conv2d_fwd: a0_C=%d must be a positive multiple of 64", d->a0_C);
   B200_REQUIRE(d->a1 == nullptr || (d->a1_C > 0 && d->a1_C % 64 == 0), "conv2d_fwd: a1_C=%d must be a multiple of 64",
                d->a1_C);
   B200_REQUIRE(d->phases == 1 || d->phases == 4, "conv2d_fwd: phases must be 1 or 4");
   B200_REQUIRE(d->ntaps0 >= 1 && d->ntaps0 <= 9, "conv2d_fwd: ntaps0=%d out of range", d->ntaps0);
-  B200_REQUIRE(d->N >= 1, "conv2d_fwd: N must be positive");
   B200_REQUIRE(d->B >= 1 && d->Ho >= 1 && d->Wo >= 1, "conv2d_fwd: bad B/Ho/Wo");
   const int K = d->ntaps0 * d->a0_C + (d->a1 ? d->a1_C : 0);
   B200_REQUIRE(d->w_K == K, "conv2d_fwd: w_K=%d does not match ntaps0*a0_C+a1_C=%d", d->w_K, K);
   B200_REQUIRE(d->out_mode >= 0 && d->out_mode <= 3, "conv2d_fwd: bad out_mode");
   B200_REQUIRE(((uintptr_t)d->a0 & 127) == 0 && ((uintptr_t)d->w & 127) == 0 && ((uintptr_t)d->out & 15) == 0,
                "conv2d_fwd: a0/w must be 128-byte aligned and out 16-byte aligned");
-  if (d->out_mode <= B200_OUT_BF16_NHWC)
-    B200_REQUIRE(d->out_ld % 8 == 0 || d->N < 16, "conv2d_fwd: NHWC out_ld=%d must be a multiple of 8", d->out_ld);
-  if (d->residual) B200_REQUIRE(d->res_ld % 4 == 0 && ((uintptr_t)d->residual & 15) == 0, "conv2d_fwd: residual alignment");
-  if (d->rowadd) B200_REQUIRE(d->rowadd_ld % 4 == 0 && ((uintptr_t)d->rowadd & 15) == 0, "conv2d_fwd: rowadd alignment");
-  if (d->bias) B200_REQUIRE(((uintptr_t)d->bias & 15) == 0, "conv2d_fwd: bias alignment");
+  B200_REQUIRE(d->stats == nullptr || d->out_mode == B200_OUT_F32_NHWC, "conv2d_fwd: statistics need an fp32 NHWC output");
 
-  // ---- M tiling: 128 output pixels = bw x bh x bn ----
-  int bw = 1;
-  while (bw * 2 <= 128 && d->Wo % (bw * 2) == 0) bw *= 2;
-  int bh = 1;
-  while (bw * bh * 2 <= 128 && d->Ho % (bh * 2) == 0) bh *= 2;
-  int bn = 128 / (bw * bh);
-  B200_REQUIRE(bn == 1 || (bw == d->Wo && bh == d->Ho),
-               "conv2d_fwd: unsupported spatial size %dx%d (need power-of-two factors to fill a 128-pixel tile)",
-               d->Ho, d->Wo);
+  // ---- pixel tile: NP = bw x bh x bn pixels, power-of-two factors of the output grid ----
+  int maxw = 1;
+  while (maxw * 2 <= 256 && d->Wo % (maxw * 2) == 0) maxw *= 2;
+  int maxh = 1;
+  while (maxh * 2 <= 256 && d->Ho % (maxh * 2) == 0) maxh *= 2;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200_CHECK(cudaGetDevice(&dev));
+    B200_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int c_tiles = (d->N + kBlockC - 1) / kBlockC;
   ConvKParams p;
   memset(&p, 0, sizeof(p));
+  // largest pixel tile that still gives (nearly) every SM a tile; otherwise the smallest valid one
+  int best_np = 0;
+  for (int np = 256; np >= 64; np >>= 1) {
+    const int bw = maxw < np ? maxw : np;
+    const int bh = maxh < np / bw ? maxh : np / bw;
+    const int bn = np / (bw * bh);
+    if (bn > 1 && !(bw == d->Wo && bh == d->Ho)) continue;  // images may only be stacked whole
+    const long p_tiles = (long)(d->Wo / bw) * (d->Ho / bh) * ((d->B + bn - 1) / bn);
+    p.NP = np; p.bw = bw; p.bh = bh; p.bn = bn;
+    p.p_tiles = (int)p_tiles;
+    best_np = np;
+    if (p_tiles * c_tiles * d->phases >= (long)g_num_sms * 3 / 4) break;
+  }
+  B200_REQUIRE(best_np != 0, "conv2d_fwd: unsupported spatial size %dx%d (need power-of-two factors)", d->Ho, d->Wo);
   p.B = d->B;
-  p.bw = bw; p.bh = bh; p.bn = bn;
-  p.tiles_w = d->Wo / bw;
-  p.tiles_h = d->Ho / bh;
-  const int tiles_n = (d->B + bn - 1) / bn;
-  p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  // ---- N tiling ----
-  int block_n = d->N >= 256 ? 256 : ((d->N + 15) / 16) * 16;
-  p.block_n = block_n;
-  p.n_tiles = (d->N + block_n - 1) / block_n;
-  p.total_tiles = d->phases * p.m_tiles * p.n_tiles;
+  p.lg_bw = ilog2(p.bw);
+  p.lg_bhw = ilog2(p.bw * p.bh);
+  p.tiles_w = d->Wo / p.bw;
+  p.tiles_h = d->Ho / p.bh;
+  p.c_tiles = c_tiles;
+  p.total_tiles = d->phases * p.p_tiles * p.c_tiles;
   p.N = d->N;
   p.w_rows_per_phase = d->w_rows_per_phase;
   p.cpb0 = d->a0_C / 64;
@@ -350,21 +433,27 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   memcpy(p.tap1, d->tap1, sizeof(p.tap1));
   p.bias = d->bias; p.rowadd = d->rowadd; p.rowadd_ld = d->rowadd_ld;
   p.residual = d->residual; p.res_ld = d->res_ld;
+  p.stats = d->stats;
   p.out = d->out; p.out_mode = d->out_mode; p.out_ld = d->out_ld;
   p.out_H = d->out_H; p.out_W = d->out_W; p.osy = d->osy; p.osx = d->osx;
+  // 8 consecutive tile pixels are contiguous in a channel-major output row?
+  p.vec8_ok = (d->phases == 1 && d->osx == 1 && d->osy == 1 && (p.bw >= 8 || (p.bw == d->out_W && p.bw * p.bh >= 8)) &&
+               (d->out_H * d->out_W) % 8 == 0 && d->out_W % (p.bw < 8 ? p.bw : 8) == 0) ? 1 : 0;
 
-  const int stage_bytes = kABytes + block_n * 128;
+  p.fast_epi = (d->phases == 1 && d->osx == 1 && d->osy == 1 && p.bw == d->Wo && d->out_W == d->Wo &&
+                d->out_H == d->Ho && (p.bn == 1 || p.bh == d->Ho) && d->B % p.bn == 0 && p.lg_bhw >= 4) ? 1 : 0;
+
+  const int stage_bytes = kWBytes + p.NP * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvBarriers) + 1024;
 
-  CUtensorMap mapA0, mapA1, mapB;
-  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, bw, bh, bn);
+  CUtensorMap mapA0, mapA1, mapW;
+  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, p.bw, p.bh, p.bn);
   if (rc) return rc;
   if (d->a1) {
-    rc = make_a_map(&mapA1, d->a1, d->a1_C, d->a1_H, d->a1_W, d->a1_planes, d->B, bw, bh, bn);
+    rc = make_a_map(&mapA1, d->a1, d->a1_C, d->a1_H, d->a1_W, d->a1_planes, d->B, p.bw, p.bh, p.bn);
     if (rc) return rc;
   } else {
     mapA1 = mapA0;
@@ -372,19 +461,12 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)d->w_K, (uint64_t)d->w_rows};
     uint64_t strides[1] = {(uint64_t)d->w_K * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
-    rc = encode_tmap(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[2] = {64, (uint32_t)kBlockC};
+    rc = encode_tmap(&mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-
-  if (g_num_sms == 0) {
-    int dev = 0;
-    B200_CHECK(cudaGetDevice(&dev));
-    B200_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
 }

@@ -270,3 +270,186 @@ extern "C" int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1,
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "groupnorm_kernel launch");
 }
+
+// ================================================================================================
+// K3, streaming variant: the per-(image, channel) sum / sum-of-squares of the input were already accumulated by
+// the kernel that produced it (conv epilogue, conv_gemm.cu), so GroupNorm+SiLU is ONE coalesced pass:
+// read fp32 once, write bf16 once.  A CTA owns (image n, a contiguous range of pixels, all channels); its
+// prologue turns the channel statistics into per-channel y = x*A + B coefficients in shared memory.
+// ================================================================================================
+namespace b200 {
+
+struct GnApplyParams {
+  const float* x0; int C0; const float* st0;
+  const float* x1; int C1; const float* st1;
+  int HW, W, groups, cpg, pix_per_cta;
+  const float* gamma; const float* beta; float eps;
+  const float* scale; const float* shift; int ss_ld;
+  int apply_silu, resample;
+  __nv_bfloat16* out; __nv_bfloat16* raw;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float gsm[];
+  const int C = p.C0 + p.C1;
+  float* coefA = gsm;            // [C]
+  float* coefB = gsm + C;        // [C]
+  float* chS = gsm + 2 * C;      // [C] channel sums
+  float* chQ = gsm + 3 * C;      // [C] channel sums of squares
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int c = tid; c < C; c += 256) {
+    const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+    chS[c] = __ldg(st);
+    chQ[c] = __ldg(st + 1);
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);
+  for (int c = tid; c < C; c += 256) {
+    const int g0 = (c / p.cpg) * p.cpg;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < p.cpg; ++i) { s += chS[g0 + i]; q += chQ[g0 + i]; }
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    float ga = p.gamma ? __ldg(p.gamma + c) : 1.f;
+    float be = p.beta ? __ldg(p.beta + c) : 0.f;
+    if (p.scale) {
+      const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c);
+      ga *= sc;
+      be = be * sc + __ldg(p.shift + (size_t)n * p.ss_ld + c);
+    }
+    coefA[c] = rstd * ga;
+    coefB[c] = be - mean * rstd * ga;
+  }
+  __syncthreads();
+
+  const int nv = C >> 2;
+  if (p.resample != 1) {
+    const int px0 = blockIdx.x * p.pix_per_cta;
+    const int px1 = min(p.HW, px0 + p.pix_per_cta);
+    const int total = (px1 - px0) * nv;
+    // 4 independent 16-byte loads in flight per thread before any dependent math
+    for (int idx0 = tid; idx0 < total; idx0 += 1024) {
+      float4 vv[4];
+      int pxs[4], cs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * 256;
+        const int pl = idx / nv;
+        const int j = idx - pl * nv;
+        pxs[u] = px0 + pl;
+        cs[u] = j << 2;
+        if (idx < total) {
+          vv[u] = (cs[u] < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + pxs[u]) * p.C0 + cs[u])
+                                 : ldg4(p.x1 + ((size_t)n * p.HW + pxs[u]) * p.C1 + (cs[u] - p.C0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (idx0 + u * 256 >= total) break;
+        const float4 v = vv[u];
+        const int px = pxs[u], c = cs[u];
+        const float4 a = *reinterpret_cast<const float4*>(coefA + c);
+        const float4 b = *reinterpret_cast<const float4*>(coefB + c);
+        float y[4] = {v.x * a.x + b.x, v.y * a.y + b.y, v.z * a.z + b.z, v.w * a.w + b.w};
+        if (p.apply_silu) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = silu_f(y[i]);
+        }
+        uint2 uo;
+        uo.x = pack_bf16x2(y[0], y[1]);
+        uo.y = pack_bf16x2(y[2], y[3]);
+        if (p.resample == 0) {
+          *reinterpret_cast<uint2*>(p.out + ((size_t)n * p.HW + px) * C + c) = uo;
+        } else {  // nearest 2x
+          const int iy = px / p.W, ix = px - iy * p.W;
+          const int Wo = p.W * 2;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const size_t po = (size_t)(2 * iy + dy) * Wo + 2 * ix + dx;
+              *reinterpret_cast<uint2*>(p.out + ((size_t)n * (4 * p.HW) + po) * C + c) = uo;
+            }
+        }
+        if (p.raw) {
+          uint2 ur;
+          ur.x = pack_bf16x2(v.x, v.y);
+          ur.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(p.raw + ((size_t)n * p.HW + px) * C + c) = ur;
+        }
+      }
+    }
+  } else {  // 2x2 average pool of the activated values; the CTA's pixel range is over OUTPUT pixels
+    const int Wo = p.W >> 1, HWo = p.HW >> 2;
+    const int po0 = blockIdx.x * p.pix_per_cta;
+    const int po1 = min(HWo, po0 + p.pix_per_cta);
+    const int total = (po1 - po0) * nv;
+    for (int idx = tid; idx < total; idx += 256) {
+      const int pl = idx / nv;
+      const int j = idx - pl * nv;
+      const int po = po0 + pl;
+      const int c = j << 2;
+      const int oy = po / Wo, ox = po - oy * Wo;
+      const float4 a = *reinterpret_cast<const float4*>(coefA + c);
+      const float4 b = *reinterpret_cast<const float4*>(coefB + c);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int px = (2 * oy + dy) * p.W + 2 * ox + dx;
+          const float4 v = (c < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + px) * p.C0 + c)
+                                      : ldg4(p.x1 + ((size_t)n * p.HW + px) * p.C1 + (c - p.C0));
+          float y[4] = {v.x * a.x + b.x, v.y * a.y + b.y, v.z * a.z + b.z, v.w * a.w + b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] += p.apply_silu ? silu_f(y[i]) : y[i];
+        }
+      uint2 u;
+      u.x = pack_bf16x2(0.25f * acc[0], 0.25f * acc[1]);
+      u.y = pack_bf16x2(0.25f * acc[2], 0.25f * acc[3]);
+      *reinterpret_cast<uint2*>(p.out + ((size_t)n * HWo + po) * C + c) = u;
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200_groupnorm_apply_fwd(const float* x0, int C0, const float* stats0, const float* x1, int C1,
+                                        const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+                                        const float* beta, float eps, const float* scale, const float* shift,
+                                        int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
+                                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x0 && stats0 && out_bf16, "groupnorm_apply: null x0/stats0/out");
+  if (!x1) C1 = 0;
+  B200_REQUIRE(x1 == nullptr || stats1 != nullptr, "groupnorm_apply: second source needs its statistics");
+  const int C = C0 + C1;
+  B200_REQUIRE(groups > 0 && C % groups == 0, "groupnorm_apply: C=%d not divisible by groups=%d", C, groups);
+  B200_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0, "groupnorm_apply: channel counts (%d, %d) must be multiples of 4", C0, C1);
+  B200_REQUIRE(resample >= 0 && resample <= 2, "groupnorm_apply: bad resample mode");
+  B200_REQUIRE(W > 0 && HW % W == 0, "groupnorm_apply: HW=%d not a multiple of W=%d", HW, W);
+  if (resample == 1) B200_REQUIRE(W % 2 == 0 && (HW / W) % 2 == 0 && raw_out_bf16 == nullptr, "groupnorm_apply: avg-pool needs even H, W and no raw copy");
+  B200_REQUIRE((scale == nullptr) == (shift == nullptr), "groupnorm_apply: scale and shift must be given together");
+  const size_t smem = (size_t)4 * C * 4;
+  B200_REQUIRE(smem <= 48 * 1024, "groupnorm_apply: C=%d too large", C);
+  GnApplyParams p;
+  p.x0 = x0; p.C0 = C0; p.st0 = stats0; p.x1 = x1; p.C1 = C1; p.st1 = stats1;
+  p.HW = HW; p.W = W; p.groups = groups; p.cpg = C / groups;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
+  p.apply_silu = apply_silu; p.resample = resample;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
+  const int work_pix = resample == 1 ? HW / 4 : HW;
+  int ppc = (resample == 1 ? 8192 : 32768) / C;  // ~128 KB of fp32 input per CTA
+  if (ppc < 1) ppc = 1;
+  if (ppc > work_pix) ppc = work_pix;
+  p.pix_per_cta = ppc;
+  dim3 grid((work_pix + ppc - 1) / ppc, B);
+  groupnorm_apply_kernel<<<grid, 256, smem, stream>>>(p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "groupnorm_apply_kernel launch");
+}

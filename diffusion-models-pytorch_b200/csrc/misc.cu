@@ -9,53 +9,79 @@ extern long long g_launch_count;
 
 // ------------------------------------------------------------------------------------------------
 // First convolution (models/unet.py:72,123): x NCHW fp32 [B][Cin][H][W] -> NHWC fp32 [B][H][W][Cout].
-// A warp produces all Cout channels of one pixel per iteration (coalesced 4*Cout-byte row store);
-// the 9*Cin inputs of that pixel are warp-uniform broadcast loads, the weights sit in smem as [9*Cin][Cout].
+// One CTA = (R output rows, image, group of 128 output channels).  Each lane owns 4 output channels and keeps
+// their 9*Cin*4 weights in registers; the (R+2) x (W+2) x Cin zero-padded input patch sits in shared memory and is
+// read as warp-wide broadcasts; a warp emits one pixel's 128 channels per iteration (coalesced 512-byte store).
+// The per-(image, channel) sum / sum of squares for the GroupNorm that follows are accumulated on the fly.
 // ------------------------------------------------------------------------------------------------
+template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            int B, int Cin, int H, int W, int Cout) {
-  extern __shared__ float wsm[];  // [9*Cin][Cout] + bias[Cout]
-  const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-    const int k = i / Cout, co = i - k * Cout;  // k = (ci*3 + r)*3 + s  (OIHW inner order)
-    wsm[i] = w[(size_t)co * K + k];
+                                                            float* __restrict__ stats, int B, int H, int W, int Cout,
+                                                            int R) {
+  constexpr int K = 9 * CIN;
+  extern __shared__ float fsm[];
+  float* ssm = fsm;               // [2*128] statistics of this CTA's channel group
+  float* patch = fsm + 256;       // [CIN][R+2][W+2], zero padded
+  const int n = blockIdx.y;
+  const int h0 = blockIdx.x * R;
+  const int PW = W + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int co = blockIdx.z * 128 + 4 * lane;  // first of this lane's 4 output channels
+  const bool co_ok = co < Cout;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0.f;
+  for (int i = threadIdx.x; i < CIN * (R + 2) * PW; i += blockDim.x) {
+    const int ci = i / ((R + 2) * PW);
+    const int rem = i - ci * (R + 2) * PW;
+    const int py = rem / PW, pxx = rem - py * PW;
+    const int yy = h0 + py - 1, xx = pxx - 1;
+    patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)n * CIN + ci) * H + yy) * W + xx) : 0.f;
   }
-  float* bsm = wsm + K * Cout;
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bsm[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int npix = B * H * W;
-  const int quads = Cout >> 2;
-  for (int pix = gwarp; pix < npix; pix += warps_total) {
-    const int n = pix / (H * W);
-    const int hw = pix - n * H * W;
-    const int h = hw / W, wq = hw - h * W;
-    float in[36];
+  // weights of channels co..co+3: rows of K contiguous floats in the OIHW tensor (k = (ci*3 + r)*3 + s)
+  float wr[4][K];
+  float bv[4];
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci)
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) wr[e][k] = co_ok ? __ldg(w + (size_t)(co + e) * K + k) : 0.f;
+    bv[e] = (co_ok && bias) ? __ldg(bias + co + e) : 0.f;
+  }
+  __syncthreads();
+  const int rows = min(R, H - h0);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int lp = warp; lp < rows * W; lp += nwarps) {
+    const int ly = lp / W, lx = lp - ly * W;
+    float acc[4] = {bv[0], bv[1], bv[2], bv[3]};
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const int yy = h + r - 1, xx = wq + s - 1;
-          float v = 0.f;
-          if (ci < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W)
-            v = __ldg(x + (((size_t)n * Cin + ci) * H + yy) * W + xx);
-          in[(ci * 3 + r) * 3 + s] = v;
-        }
-    for (int qd = lane; qd < quads; qd += 32) {
-      float4 acc = *reinterpret_cast<const float4*>(bsm + 4 * qd);
+          const float v = patch[(ci * (R + 2) + ly + r) * PW + lx + s];
+          const int k = (ci * 3 + r) * 3 + s;
 #pragma unroll
-      for (int k = 0; k < 36; ++k) {
-        if (k < K) {
-          const float4 wv = *reinterpret_cast<const float4*>(wsm + k * Cout + 4 * qd);
-          acc.x += in[k] * wv.x; acc.y += in[k] * wv.y; acc.z += in[k] * wv.z; acc.w += in[k] * wv.w;
+          for (int e = 0; e < 4; ++e) acc[e] += v * wr[e][k];
         }
+    if (co_ok) {
+      const size_t pix = ((size_t)n * H + h0 + ly) * W + lx;
+      *reinterpret_cast<float4*>(out + pix * Cout + co) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s1[e] += acc[e]; s2[e] += acc[e] * acc[e]; }
+    }
+  }
+  if (stats) {
+    if (co_ok) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(ssm + 2 * (4 * lane + e), s1[e]);
+        atomicAdd(ssm + 2 * (4 * lane + e) + 1, s2[e]);
       }
-      *reinterpret_cast<float4*>(out + (size_t)pix * Cout + 4 * qd) = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      const int ch = blockIdx.z * 128 + (i >> 1);
+      if (ch < Cout) atomicAdd(stats + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
     }
   }
 }
@@ -133,10 +159,11 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
                                                          const float* __restrict__ b2, const int64_t* __restrict__ y,
                                                          const float* __restrict__ class_embed, float* __restrict__ out,
                                                          __nv_bfloat16* __restrict__ out_silu_bf16) {
+  // grid = (splits, rows): every CTA recomputes the cheap hidden layer and produces E/splits outputs of layer 2
   extern __shared__ float tsm[];  // pe[dim] + h[E]
   float* pe = tsm;
   float* hid = tsm + dim;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int half = dim >> 1;
   const float tv = (float)t[b];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -146,24 +173,37 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
     pe[half + i] = cos_first ? s : c;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int e = warp; e < E; e += nwarps) {
-    float acc = 0.f;
-    for (int k = lane; k < dim; k += 32) acc += __ldg(w1 + (size_t)e * dim + k) * pe[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      const float v = acc + b1[e];
-      hid[e] = v / (1.0f + expf(-v));
+  // layer 1: thread-per-output, each thread streams its own weight row with float4 loads (dim % 4 == 0)
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)e * dim);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < dim / 4; ++k) {
+      const float4 wv = __ldg(wr + k);
+      a0 += wv.x * pe[4 * k]; a1 += wv.y * pe[4 * k + 1]; a2 += wv.z * pe[4 * k + 2]; a3 += wv.w * pe[4 * k + 3];
     }
+    const float v = (a0 + a1) + (a2 + a3) + b1[e];
+    hid[e] = v / (1.0f + expf(-v));
   }
   __syncthreads();
-  for (int e = warp; e < E; e += nwarps) {
+  // layer 2: 8 lanes per output, coalesced float4 reads of the weight row, shuffle reduction
+  const int per_cta = (E + gridDim.x - 1) / gridDim.x;
+  const int e_begin = blockIdx.x * per_cta;
+  const int e_end = min(E, e_begin + per_cta);
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;  // 32 groups of 8 lanes
+  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    const int e = e0 + grp;
     float acc = 0.f;
-    for (int k = lane; k < E; k += 32) acc += __ldg(w2 + (size_t)e * E + k) * hid[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+    if (e < e_end) {
+      const float4* wr = reinterpret_cast<const float4*>(w2 + (size_t)e * E);
+      for (int k = sub; k < E / 4; k += 8) {
+        const float4 wv = __ldg(wr + k);
+        acc += wv.x * hid[4 * k] + wv.y * hid[4 * k + 1] + wv.z * hid[4 * k + 2] + wv.w * hid[4 * k + 3];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (sub == 0 && e < e_end) {
       float v = acc + b2[e];
       if (y && class_embed) v += class_embed[(size_t)y[b] * E + e];
       out[(size_t)b * E + e] = v;
@@ -195,25 +235,37 @@ static inline int ew_grid(size_t total, int block) {
 
 using namespace b200;
 
-extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H,
-                                  int W, int Cout, void* stream_) {
+template <int CIN>
+static int launch_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B, int H,
+                        int W, int Cout, cudaStream_t stream) {
+  int R = 8;
+  while (R > 1 && (size_t)CIN * (R + 2) * (W + 2) * 4 > 96 * 1024) R >>= 1;
+  if (R > H) R = H;
+  const size_t smem = (256 + (size_t)CIN * (R + 2) * (W + 2)) * 4;
+  B200_REQUIRE(smem <= 100 * 1024, "conv3x3_first: input patch does not fit in shared memory (W=%d)", W);
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(conv3x3_first_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  dim3 grid((H + R - 1) / R, B, (Cout + 127) / 128);
+  conv3x3_first_kernel<CIN><<<grid, 256, smem, stream>>>(x, w, bias, out, stats, B, H, W, Cout, R);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "conv3x3_first launch");
+}
+
+extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B,
+                                  int Cin, int H, int W, int Cout, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(x && w && out, "conv3x3_first: null pointer");
   B200_REQUIRE(Cin >= 1 && Cin <= 4, "conv3x3_first: Cin=%d must be in [1,4]", Cin);
-  B200_REQUIRE(Cout % 4 == 0 && Cout <= 1024, "conv3x3_first: Cout=%d must be a multiple of 4", Cout);
-  const size_t smem = ((size_t)9 * Cin * Cout + Cout) * 4;
-  static bool attr = false;
-  if (!attr) {
-    B200_CHECK(cudaFuncSetAttribute(conv3x3_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
+  B200_REQUIRE(Cout % 4 == 0, "conv3x3_first: Cout=%d must be a multiple of 4", Cout);
+  switch (Cin) {
+    case 1: return launch_first<1>(x, w, bias, out, stats, B, H, W, Cout, stream);
+    case 2: return launch_first<2>(x, w, bias, out, stats, B, H, W, Cout, stream);
+    case 3: return launch_first<3>(x, w, bias, out, stats, B, H, W, Cout, stream);
+    default: return launch_first<4>(x, w, bias, out, stats, B, H, W, Cout, stream);
   }
-  B200_REQUIRE(smem <= 160 * 1024, "conv3x3_first: weights do not fit in shared memory");
-  const int npix = B * H * W;
-  int grid = (npix + 63) / 64;  // 8 warps per CTA, ~8 pixels per warp
-  if (grid > 148 * 4) grid = 148 * 4;
-  conv3x3_first_kernel<<<grid, 256, smem, stream>>>(x, w, bias, out, B, Cin, H, W, Cout);
-  ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "conv3x3_first launch");
 }
 
 extern "C" int b200_cast_bf16(const float* x, void* out, int B, int H, int W, int C, int parity_split, void* stream_) {
@@ -251,10 +303,11 @@ extern "C" int b200_time_embed(const int64_t* t, int rows, const float* freqs, i
                                const float* class_embed, float* out, void* out_silu_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(t && freqs && w1 && b1 && w2 && b2 && out, "time_embed: null pointer");
-  B200_REQUIRE(dim % 2 == 0 && rows >= 1, "time_embed: bad dim/rows");
+  B200_REQUIRE(dim % 8 == 0 && E % 4 == 0 && rows >= 1, "time_embed: dim must be a multiple of 8, E of 4");
   const size_t smem = (size_t)(dim + E) * 4;
   B200_REQUIRE(smem <= 48 * 1024, "time_embed: dim+E too large");
-  time_embed_kernel<<<rows, 256, smem, stream>>>(t, freqs, dim, E, cos_first, w1, b1, w2, b2, y, class_embed, out,
+  const int splits = rows >= 64 ? 2 : 8;
+  time_embed_kernel<<<dim3(splits, rows), 256, smem, stream>>>(t, freqs, dim, E, cos_first, w1, b1, w2, b2, y, class_embed, out,
                                                  reinterpret_cast<__nv_bfloat16*>(out_silu_bf16));
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "time_embed launch");

@@ -22,10 +22,11 @@ import b200diff as K
 
 class Act:
     """fp32 NHWC activation [B, H, W, C]."""
-    __slots__ = ('t', 'B', 'H', 'W', 'C')
+    __slots__ = ('t', 'B', 'H', 'W', 'C', 'stats')
 
-    def __init__(self, t, B, H, W, C):
+    def __init__(self, t, B, H, W, C, stats=None):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.stats = stats   # [B, C, 2] per-(image, channel) sum / sum of squares from the producing kernel
 
 
 class Engine:
@@ -34,7 +35,7 @@ class Engine:
         self._packed: Dict = {}
         self._sig = None
         self._arena: Dict = {}
-        self._tproj_index: Optional[Dict[str, int]] = None
+        self._stats: Dict = {}
 
     # ------------------------------------------------------------------------------------------
     # buffers and packed weights
@@ -50,6 +51,20 @@ class Engine:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._arena[key] = t
         return t
+
+    def stats_buf(self, tag, B, C):
+        """[B, C, 2] fp32 accumulator for the GroupNorm statistics of a conv output (zeroed every forward)."""
+        key = (tag, B, C, self.device)
+        t = self._stats.get(key)
+        if t is None:
+            t = torch.zeros((B, C, 2), dtype=torch.float32, device=self.device)
+            self._stats[key] = t
+        return t
+
+    def begin_forward(self):
+        self.refresh()
+        if self._stats:
+            torch._foreach_zero_(list(self._stats.values()))
 
     def refresh(self):
         """Drops the packed bf16 weights when any parameter was modified or moved."""
@@ -111,22 +126,30 @@ class Engine:
             Ho, Wo = x.H * 2, x.W * 2
         out = self.buf(tag + '.gn', (x.B, Ho, Wo, C), torch.bfloat16)
         raw_out = self.buf(tag + '.raw', (x.B, x.H, x.W, C), torch.bfloat16) if raw else None
-        K.groupnorm_silu(x.t, x.C, None if skip is None else skip.t, 0 if skip is None else skip.C, x.B, x.H * x.W,
-                         x.W, norm.num_groups, norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift,
-                         ss_ld=ss_ld, silu=silu, resample=resample, raw_out=raw_out)
+        if x.stats is not None and (skip is None or skip.stats is not None):
+            K.groupnorm_apply(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
+                              None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
+                              norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift, ss_ld=ss_ld, silu=silu,
+                              resample=resample, raw_out=raw_out)
+        else:
+            K.groupnorm_silu(x.t, x.C, None if skip is None else skip.t, 0 if skip is None else skip.C, x.B,
+                             x.H * x.W, x.W, norm.num_groups, norm.weight, norm.bias, norm.eps, out, scale=scale,
+                             shift=shift, ss_ld=ss_ld, silu=silu, resample=resample, raw_out=raw_out)
         return out, raw_out
 
     def conv3x3(self, tag, a, B, H, W, Cin, conv, *, rowadd=None, rowadd_ld=0, residual: Optional[Act] = None,
                 sc_a=None, sc_C=0, sc_conv=None, out_mode=K.OUT_F32_NHWC, out=None):
         Cout = conv.out_channels
         w, b = self.w_conv(tag, conv, sc_conv)
+        stats = None
         if out is None:
             out = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
+            stats = self.stats_buf(tag, B, Cout) if Cout > 32 else None
         K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(Cin, H, W, 1),
                  a1=sc_a, a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, bias=b,
                  rowadd=rowadd, rowadd_ld=rowadd_ld, residual=None if residual is None else residual.t,
-                 res_ld=0 if residual is None else residual.C, out=out, out_mode=out_mode)
-        return out
+                 res_ld=0 if residual is None else residual.C, out=out, out_mode=out_mode, stats=stats)
+        return Act(out, B, H, W, Cout, stats)
 
     def attention(self, tag, blk, x: Act) -> Act:
         B, H, W, C = x.B, x.H, x.W, x.C
@@ -147,8 +170,10 @@ class Engine:
         K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, blk.scale)
         wp, bp = self.w_conv(tag + '.proj', blk.proj)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
-        K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out)
-        return Act(out, B, H, W, C)
+        stats = self.stats_buf(tag, B, C)
+        K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
+                 stats=stats)
+        return Act(out, B, H, W, C, stats)
 
     def downsample_conv(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
         B, H, W, C = x.B, x.H, x.W, x.C
@@ -157,9 +182,10 @@ class Engine:
         w, b = self.w_conv(tag, conv)
         Cout = conv.out_channels
         out = self.buf(tag + '.out', (B, H // 2, W // 2, Cout), torch.float32)
+        stats = self.stats_buf(tag, B, Cout)
         K.conv2d(planes, w, Cout, B, H // 2, W // 2, K.taps_3x3_s2(pad_lo), a0_geom=(C, H // 2, W // 2, 4), bias=b,
-                 out=out)
-        return Act(out, B, H // 2, W // 2, Cout)
+                 out=out, stats=stats)
+        return Act(out, B, H // 2, W // 2, Cout, stats)
 
     def upsample_conv(self, tag, conv: nn.Conv2d, x: Act) -> Act:
         """nearest-2x + conv3x3 as four 2x2-tap phase convolutions on the low-res grid (2.25x fewer MACs)."""
@@ -169,9 +195,10 @@ class Engine:
         w, b = self.w_up2(tag, conv)
         Cout = conv.out_channels
         out = self.buf(tag + '.out', (B, 2 * H, 2 * W, Cout), torch.float32)
+        stats = self.stats_buf(tag, B, Cout)
         K.conv2d(xb, w, Cout, B, H, W, K.taps_up2_3x3(), a0_geom=(C, H, W, 1), bias=b, out=out,
-                 w_rows_per_phase=Cout)
-        return Act(out, B, 2 * H, 2 * W, Cout)
+                 w_rows_per_phase=Cout, stats=stats, alg_macs=9.0 * B * 4 * H * W * C * Cout)
+        return Act(out, B, 2 * H, 2 * W, Cout, stats)
 
     def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
         """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
@@ -182,13 +209,11 @@ class Engine:
         has_sc = isinstance(blk.shortcut, nn.Conv2d)
         a1, raw = self.gn(tag + '.1', x, skip, blk.blk1[0], raw=has_sc)
         h = self.conv3x3(tag + '.c1', a1, B, H, W, Cin, conv1, rowadd=tproj[:, tproj_off:], rowadd_ld=tproj_ld)
-        a2, _ = self.gn(tag + '.2', Act(h, B, H, W, Cout), None, blk.blk2[0])
+        a2, _ = self.gn(tag + '.2', h, None, blk.blk2[0])
         if has_sc:
-            out = self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
-        else:
-            assert skip is None and Cin == Cout
-            out = self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, residual=x)
-        return Act(out, B, H, W, Cout)
+            return self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
+        assert skip is None and Cin == Cout
+        return self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, residual=x)
 
     def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
         """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""
@@ -212,13 +237,11 @@ class Engine:
             K.upsample2_f32(x.t, r, B, H, W, x.C)
             res_x = Act(r, B, Ho, Wo, x.C)
         h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1)
-        a2, _ = self.gn(tag + '.2', Act(h, B, Ho, Wo, Cout), None, blk.adagn.gn, scale=ss[:, ss_off:],
-                        shift=ss[:, ss_off + Cout:], ss_ld=ss_ld)
+        a2, _ = self.gn(tag + '.2', h, None, blk.adagn.gn, scale=ss[:, ss_off:], shift=ss[:, ss_off + Cout:],
+                        ss_ld=ss_ld)
         if has_sc:
-            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
-        else:
-            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
-        return Act(out, B, Ho, Wo, Cout)
+            return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
+        return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
 
     # ------------------------------------------------------------------------------------------
     # embedding path

@@ -74,6 +74,7 @@ class SamplingRunner:
             g['t'].copy_(t_table[i:i + 1])
             g['coef'].copy_(coef_table[i])
             g['graph'].replay()
+            K.GRAPH_LAUNCHES += g['kernels']
             pbar.update(1)
         pbar.close()
         return g['x'].clone()
@@ -115,8 +116,10 @@ class SamplingRunner:
             step()
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        n0 = K.direct_launch_count()
         with torch.no_grad(), torch.cuda.graph(graph):
             step()
+        st['kernels'] = K.direct_launch_count() - n0   # libb200diff kernels captured per timestep
         torch.cuda.set_rng_state(rng, dev)
         st['graph'] = graph
         return st

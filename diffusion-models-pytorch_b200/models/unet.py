@@ -133,7 +133,7 @@ class UNet(_EngineModel):
         """X: [B, C, H, W] fp32 (NCHW), T: [B] int64 -> [B, C_out, H, W] fp32.  (reference unet.py:121-152)"""
         self._reject_training()
         eng = self.engine
-        eng.refresh()
+        eng.begin_forward()
         X = eng.check_input(X, T, self.in_channels)
         B, _, H, W = X.shape
 
@@ -146,8 +146,9 @@ class UNet(_EngineModel):
                                [blk.proj[1] for _, blk in res_blocks])
 
         h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
-        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0)
-        h = Act(h0, B, H, W, self.first_conv.out_channels)
+        st0 = eng.stats_buf('first_conv', B, self.first_conv.out_channels)
+        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0, st0)
+        h = Act(h0, B, H, W, self.first_conv.out_channels, st0)
         skips = [h]
 
         def run_res(name, blk, x, skip=None):

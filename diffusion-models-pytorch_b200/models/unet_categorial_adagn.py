@@ -124,7 +124,7 @@ class UNetCategorialAdaGN(_EngineModel):
         """X: [B, C, H, W] fp32, T: [B] int64, y: [B] int64 labels or None -> [B, C_out, H, W] fp32."""
         self._reject_training()
         eng = self.engine
-        eng.refresh()
+        eng.begin_forward()
         X = eng.check_input(X, T, self.in_channels)
         B, _, H, W = X.shape
 
@@ -137,8 +137,9 @@ class UNetCategorialAdaGN(_EngineModel):
                               [blk.adagn.proj[1] for _, blk in res_blocks])
 
         h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
-        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0)
-        h = Act(h0, B, H, W, self.first_conv.out_channels)
+        st0 = eng.stats_buf('first_conv', B, self.first_conv.out_channels)
+        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0, st0)
+        h = Act(h0, B, H, W, self.first_conv.out_channels, st0)
         skips = [h]
 
         def run_res(name, blk, x, skip=None):

@@ -66,6 +66,8 @@ typedef struct b200_conv_desc {
   int rowadd_ld;
   const float* residual; /* fp32 NHWC [B][out_H][out_W][res_ld] or NULL */
   int res_ld;
+  float* stats;          /* optional [B][N][2] fp32, pre-zeroed: per-(image, channel) sum and sum of squares of the
+                            fp32 NHWC output are atomically accumulated here for the GroupNorm that follows */
   void* out;
   int out_mode;        /* B200_OUT_* */
   int out_ld;          /* channel stride of NHWC outputs; for NCHW outputs the channel count */
@@ -78,6 +80,7 @@ int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
 /* First convolution of the UNet (models/unet.py:72,123): NCHW fp32 image, tiny Cin (1..4), 3x3 s1 p1,
  * -> fp32 NHWC [B][H][W][Cout].  Weights are the reference's OIHW fp32 tensor as is. */
 int b200_conv3x3_first(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc,
+                       float* stats /* optional [B][Cout][2], pre-zeroed, as in b200_conv_desc.stats */,
                        int B, int Cin, int H, int W, int Cout, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -93,6 +96,14 @@ int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, in
                             const float* gamma, const float* beta, float eps, const float* scale,
                             const float* shift, int ss_ld, int apply_silu, int resample, void* out_bf16,
                             void* raw_out_bf16, void* stream);
+
+/* Streaming variant of K3 for inputs whose per-(image, channel) statistics [B][C][2] = (sum, sum of squares) were
+ * accumulated by the producing kernel (b200_conv_desc.stats): one coalesced pass, 4 B read + 2 B written per
+ * element.  Same semantics and arguments as b200_groupnorm_silu_fwd otherwise. */
+int b200_groupnorm_apply_fwd(const float* x0, int C0, const float* stats0, const float* x1, int C1,
+                             const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+                             const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
+                             int apply_silu, int resample, void* out_bf16, void* raw_out_bf16, void* stream);
 
 /* fp32 NHWC -> bf16 NHWC, optionally split into the 4 parity planes [B][2*(h&1)+(w&1)][H/2][W/2][C] that
  * the stride-2 convolution (models/modules.py:72) reads through unit-stride TMA boxes. */

@@ -113,12 +113,18 @@ def _conv_case(name, B, Cin, Cout, H, W, ksize=3, stride=1, bias=True, rowadd=Fa
         out = torch.full((B, Cout, Ho, Wo), float('nan'), device=DEV,
                          dtype=torch.float32 if out_mode == K.OUT_F32_NCHW else torch.bfloat16)
     res = res_nchw.permute(0, 2, 3, 1).contiguous() if residual else None
+    stats = torch.zeros(B, Cout, 2, device=DEV) if (out_mode == K.OUT_F32_NHWC and Cout > 32) else None
     K.conv2d(a0, wp, Cout, B, Ho, Wo, taps, a0_geom=geom,
              a1=_nhwc_bf16(x1) if sc_cin else None, a1_geom=(sc_cin, Ho, Wo, 1) if sc_cin else None,
              bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0, residual=res, res_ld=Cout, out=out,
-             out_mode=out_mode)
+             out_mode=out_mode, stats=stats)
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2) if out_mode in (K.OUT_F32_NHWC, K.OUT_BF16_NHWC) else out
+    if stats is not None:
+        # fused GroupNorm statistics: per-(image, channel) sum and sum of squares (fp32 atomics: 1e-4 relative)
+        ref_st = torch.stack([ref.sum(dim=(2, 3)), (ref * ref).sum(dim=(2, 3))], dim=-1)
+        if not _report(name + ' [fused GN stats]', stats, ref_st, rtol=2e-4, atol=2e-2):
+            return False
     # fp32 accumulation order differs from cuDNN/cuBLAS: 1e-4 relative on O(1) values; bf16 outputs: 1 ulp = 2^-8
     if out_mode in (K.OUT_BF16_NHWC, K.OUT_BF16_NCHW):
         return _report(name, got, ref, rtol=1e-2, atol=1e-2)
@@ -267,6 +273,19 @@ def _gn_case(name, B, C0, C1, H, W, silu=True, adagn=False, resample=0, raw=Fals
     ok = _report(name, out.permute(0, 3, 1, 2), ref, rtol=5e-3, atol=5e-3)
     if raw:
         ok &= _report(name + ' [raw copy]', rawo, xcat.to(torch.bfloat16), 0, 0)
+    # streaming variant fed with producer-side statistics
+    if C0 % 4 == 0 and C1 % 4 == 0 and not (raw and resample == 1):
+        def st(x):
+            return torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
+        out2 = torch.full((B, Ho, Wo, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+        raw2 = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16) if raw else None
+        K.groupnorm_apply(x0, C0, st(x0), x1, C1, st(x1) if C1 else None, B, H * W, W, 32, gamma, beta, eps, out2,
+                          scale=ys if adagn else None, shift=ys[:, C:] if adagn else None,
+                          ss_ld=(2 * C + 8) if adagn else 0, silu=silu, resample=resample, raw_out=raw2)
+        torch.cuda.synchronize()
+        ok &= _report(name + ' [streaming, producer stats]', out2.permute(0, 3, 1, 2), ref, rtol=5e-3, atol=5e-3)
+        if raw:
+            ok &= _report(name + ' [streaming raw copy]', raw2, xcat.to(torch.bfloat16), 0, 0)
     return ok
 
 
@@ -297,9 +316,12 @@ def case_misc():
         b = _gen(Cout, seed=3)
         ref = F.conv2d(x, w, b, padding=1)
         out = torch.full((B, H, H, Cout), float('nan'), device=DEV)
-        K.conv3x3_first(x, w, b, out)
+        st = torch.zeros(B, Cout, 2, device=DEV)
+        K.conv3x3_first(x, w, b, out, st)
         torch.cuda.synchronize()
         ok &= _report(f'first conv {Cin}->{Cout} @{H}', out.permute(0, 3, 1, 2), ref, 1e-5, 1e-5)
+        ok &= _report(f'first conv {Cin}->{Cout} @{H} [fused GN stats]', st,
+                      torch.stack([ref.sum(dim=(2, 3)), (ref * ref).sum(dim=(2, 3))], dim=-1), 2e-4, 2e-2)
     x = _gen(2, 8, 8, 128, seed=4)
     o = torch.empty(2, 8, 8, 128, device=DEV, dtype=torch.bfloat16)
     K.cast_bf16(x, o, 2, 8, 8, 128)

@@ -40,6 +40,7 @@ struct ConvKParams {
   float* stats;  // [B][N][2] running (sum, sum of squares) of the fp32 output, or NULL
   void* out;
   int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
+  int group4;    // bw >= 4: 4 consecutive tile pixels are 4 output pixels osx apart in one row
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
 };
 
@@ -75,6 +76,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   t.h0 = th * p.bh;
   t.n0 = tn * p.bn;
   return t;
+}
+
+// Output pixel of tile pixel pp (and its image index): generic decode, done once per group of 4 pixels.
+__device__ __forceinline__ void decode_pixel(const ConvKParams& p, const TileCoord& t, int pp, int pa, int pb, int& n,
+                                             size_t& pix) {
+  n = t.n0 + (pp >> p.lg_bhw);
+  const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+  const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+  pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -206,14 +216,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           if (p.fast_epi) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = c_ok ? __ldg(rbase + (ch + j) * p.res_ld) : 0.f;
+          } else if (p.group4) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              int n;
+              size_t pix;
+              decode_pixel(p, t, ch + 4 * g, pa, pb, n, pix);
+              const float* rp = residual + pix * (size_t)p.res_ld + c;
+              const bool ok = c_ok && n < p.B;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r[4 * g + e] = ok ? __ldg(rp + e * p.osx * p.res_ld) : 0.f;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int pp = ch + j;
-              const int n = t.n0 + (pp >> p.lg_bhw);
-              const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
-              const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-              const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+              int n;
+              size_t pix;
+              decode_pixel(p, t, ch + j, pa, pb, n, pix);
               r[j] = (c_ok && n < p.B) ? __ldg(residual + pix * (size_t)p.res_ld + c) : 0.f;
             }
           }
@@ -274,27 +293,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = __float2bfloat16_rn(acc[j]);
           }
-        } else
-        if (p.out_mode == B200_OUT_F32_NHWC) {
+        } else if (p.group4 && p.out_mode <= B200_OUT_BF16_NHWC) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            int n;
+            size_t pix;
+            decode_pixel(p, t, ch + 4 * g, pa, pb, n, pix);
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NHWC) {
+                float* __restrict__ o = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + c;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e * p.osx * p.out_ld] = acc[4 * g + e];
+              } else {
+                __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + c;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e * p.osx * p.out_ld] = __float2bfloat16_rn(acc[4 * g + e]);
+              }
+            }
+          }
+        } else if (p.out_mode == B200_OUT_F32_NHWC) {
           float* __restrict__ o = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int pp = ch + j;
-            const int n = t.n0 + (pp >> p.lg_bhw);
-            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
-            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-            const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+            int n;
+            size_t pix;
+            decode_pixel(p, t, ch + j, pa, pb, n, pix);
             if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = acc[j];
           }
         } else if (p.out_mode == B200_OUT_BF16_NHWC) {
           __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int pp = ch + j;
-            const int n = t.n0 + (pp >> p.lg_bhw);
-            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
-            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-            const size_t pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+            int n;
+            size_t pix;
+            decode_pixel(p, t, ch + j, pa, pb, n, pix);
             if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = __float2bfloat16_rn(acc[j]);
           }
         } else if (p.vec8_ok) {
@@ -440,6 +472,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   p.vec8_ok = (d->phases == 1 && d->osx == 1 && d->osy == 1 && (p.bw >= 8 || (p.bw == d->out_W && p.bw * p.bh >= 8)) &&
                (d->out_H * d->out_W) % 8 == 0 && d->out_W % (p.bw < 8 ? p.bw : 8) == 0) ? 1 : 0;
 
+  p.group4 = p.bw >= 4 ? 1 : 0;
   p.fast_epi = (d->phases == 1 && d->osx == 1 && d->osy == 1 && p.bw == d->Wo && d->out_W == d->Wo &&
                 d->out_H == d->Ho && (p.bn == 1 || p.bh == d->Ho) && d->B % p.bn == 0 && p.lg_bhw >= 4) ? 1 : 0;
 

@@ -116,12 +116,13 @@ def case_ddim50():
             xt = orc.denoise(e_ref, xt, t, tp, torch.zeros_like(xt))['sample']
     psnr_g, psnr_e = _psnr(got_graph.clamp(-1, 1), want.clamp(-1, 1)), _psnr(got_eager.clamp(-1, 1), want.clamp(-1, 1))
     # the fused GroupNorm statistics are accumulated with fp32 atomics, so two runs agree to rounding, not bitwise
+    # (gate: the two runs must agree far better than either agrees with the fp32 oracle: PSNR >= 50 dB)
     gdiff = (got_graph - got_eager).abs().max().item()
-    same = gdiff <= 2e-2
+    gpsnr = _psnr(got_graph, got_eager)
+    same = gpsnr >= 50.0
     _emit(case='ddim50 final sample PSNR (graph)', psnr_db=psnr_g, gate=40.0, ok=psnr_g >= 40.0)
     _emit(case='ddim50 final sample PSNR (eager loop)', psnr_db=psnr_e, gate=40.0, ok=psnr_e >= 40.0)
-    _emit(case='ddim50 graph replay vs eager loop', max_abs_diff=gdiff, psnr_db=_psnr(got_graph, got_eager), gate=2e-2,
-          ok=same)
+    _emit(case='ddim50 graph replay vs eager loop', max_abs_diff=gdiff, psnr_db=gpsnr, gate=50.0, ok=same)
     _emit(case='ddim50 per-step eps rel-L2 along oracle trajectory', max=max(eps_rel), mean=sum(eps_rel) / len(eps_rel),
           gate=1e-2, ok=max(eps_rel) <= 1e-2)
     return ok and psnr_g >= 40.0 and psnr_e >= 40.0 and same and max(eps_rel) <= 1e-2
@@ -149,11 +150,52 @@ def case_ddpm_noise():
         want = orc.sample(ref, x0, noises=noises)
     # same RNG stream => same trajectory up to the rounding noise of the atomically accumulated GN statistics
     gdiff = (a - b).abs().max().item()
-    same = gdiff <= 2e-2
+    gpsnr = _psnr(a, b)
+    same = gpsnr >= 50.0
     psnr = _psnr(b.clamp(-1, 1), want.clamp(-1, 1))
-    _emit(case='ddpm20 graph replay vs eager loop (same RNG stream)', max_abs_diff=gdiff, gate=2e-2, ok=same)
+    _emit(case='ddpm20 graph replay vs eager loop (same RNG stream)', max_abs_diff=gdiff, psnr_db=gpsnr, gate=50.0,
+          ok=same)
     _emit(case='ddpm20 vs oracle with identical injected noise', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
     return same and psnr >= 40.0
+
+
+def case_cfg():
+    """Classifier-free guidance config (BASELINE configs[2]): UNetCategorialAdaGN forward (cond / uncond) and
+    DDIMCFG-50 (cosine betas, s = 3), B=8, against the oracle."""
+    _no_tf32()
+    cfg = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+               num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+    torch.manual_seed(2022)
+    m = models.UNetCategorialAdaGN(**cfg).to(DEV).eval()
+    ref = UNetRef(m.state_dict(), dim=128, adagn=True, attn_head_dims=64, num_res_blocks=2).to(DEV)
+    B = 8
+    g = torch.Generator(device='cpu').manual_seed(5)
+    x = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    y = (torch.arange(B) % 10).to(DEV)
+    t = torch.tensor([20, 500, 980, 7, 250, 640, 811, 999], device=DEV)
+    ok = True
+    with torch.no_grad():
+        for tag, yy in (('cond', y), ('uncond', None)):
+            rel = _rel_l2(m(x, t, yy), ref(x, t, yy))
+            # north_star gate is 1e-2; BASELINE.md section 4 measured 7.5e-3 for bf16 operands on this network
+            _emit(case=f'adagn unet forward [{tag}]', rel_l2=rel, gate=1e-2, ok=rel <= 1e-2)
+            ok &= rel <= 1e-2
+        ours = diffusions.DDIMCFG(guidance_scale=3.0, total_steps=1000, beta_schedule='cosine',
+                                  respace_type='uniform', respace_steps=50, device=DEV)
+        orc = R.DDIMRef(total_steps=1000, beta_schedule='cosine', respace_type='uniform', respace_steps=50)
+        orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+        got = ours.sample(m, x, tqdm_kwargs=dict(disable=True), model_kwargs=dict(y=y))
+        got_e = None
+        for out in ours.sample_loop(m, x, tqdm_kwargs=dict(disable=True), model_kwargs=dict(y=y)):
+            got_e = out['sample']
+        want = None
+        for out in orc.sample_loop_cfg(ref, x, 3.0, dict(y=y), dict(y=None), noises=[torch.zeros_like(x)] * 50):
+            want = out['sample']
+    for tag, gg in (('graph', got), ('eager loop', got_e)):
+        psnr = _psnr(gg.clamp(-1, 1), want.clamp(-1, 1))
+        _emit(case=f'ddimcfg50 s=3 final sample PSNR ({tag})', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+        ok &= psnr >= 40.0
+    return ok
 
 
 def case_timing():

@@ -1,0 +1,24 @@
+"""End-to-end parity on a B200 (tests/e2e_cases.py): UNet forward eps rel-L2 <= 1e-2, DDIM-50 PSNR >= 40 dB against
+the fp32 oracle, graph replay vs eager loop, the smoke() entry point."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['unet_forward', 'ddim50', 'ddpm_noise', 'cfg'])
+def test_e2e_case(case):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'e2e_cases.py'), case], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, f'{case} failed:\n{r.stdout[-3000:]}\n{r.stderr[-2000:]}'
+
+
+@pytest.mark.gpu
+def test_smoke_entry():
+    r = subprocess.run([sys.executable, '-c', 'import __graft_entry__ as g; g.smoke()'], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

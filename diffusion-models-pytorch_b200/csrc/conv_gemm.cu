@@ -11,9 +11,10 @@
 //     the time-embedding row are per-lane scalars, and the per-(image, channel) sum / sum-of-squares that the
 //     next GroupNorm needs fall out as per-thread accumulators (one atomicAdd pair per thread per image).
 // NP = 256 pixels (N = 256 UMMA, 85 flop/B of operand traffic) unless the layer is too small to fill the SMs.
-// Warp roles (192 threads, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer (one thread),
-// warps 2-5 epilogue, overlapped with the next tile's MMAs through two TMEM accumulator stages.
+// Warp roles (320 threads, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer (one thread),
+// warps 2-9 epilogue, overlapped with the next tile's MMAs through two TMEM accumulator stages.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/b200diff.h"
 
@@ -41,13 +42,14 @@ struct ConvKParams {
   void* out;
   int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
   int group4;    // bw >= 4: 4 consecutive tile pixels are 4 output pixels osx apart in one row
+  int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
 };
 
 constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
 constexpr int kBlockK = 64;
 constexpr int kWBytes = kBlockC * kBlockK * 2;  // 16 KB weight tile
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
 
 struct __align__(8) ConvBarriers {
@@ -78,13 +80,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   return t;
 }
 
-// Output pixel of tile pixel pp (and its image index): generic decode, done once per group of 4 pixels.
+// Image index and pixel offset (row-major within the output image) of tile pixel pp.
 __device__ __forceinline__ void decode_pixel(const ConvKParams& p, const TileCoord& t, int pp, int pa, int pb, int& n,
-                                             size_t& pix) {
+                                             int& po) {
   n = t.n0 + (pp >> p.lg_bhw);
   const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
   const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-  pix = ((size_t)n * p.out_H + oy) * p.out_W + ox;
+  po = oy * p.out_W + ox;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -115,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], 4);
+      mbar_init(&bars->tmem_empty[s], 4 * p.epi_halves);
     }
     fence_barrier_init();
   }
@@ -185,8 +187,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
   } else {
     // ================================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the tile's
+    // 32-pixel column chunks (even / odd), doubling the instruction throughput of the latency-bound epilogue.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int hw_out = p.out_H * p.out_W;
+    const size_t img_out = (size_t)hw_out * p.out_ld;   // elements per image of an NHWC output
+    const size_t img_res = (size_t)hw_out * p.res_ld;
+    const int ostep = p.osx * p.out_ld, rstep = p.osx * p.res_ld;
     const float* __restrict__ residual = p.residual;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -206,7 +214,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       // fast path: the tile's pixels are consecutive output pixels (full-width rows / whole images, stride 1)
       const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
       const float* __restrict__ rbase = residual ? residual + pix0 * (size_t)p.res_ld + c : nullptr;
-      for (int ch = 0; ch < p.NP; ch += 32) {
+      for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_x32(taddr + (uint32_t)ch, v);
@@ -219,27 +227,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           } else if (p.group4) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              int n;
-              size_t pix;
-              decode_pixel(p, t, ch + 4 * g, pa, pb, n, pix);
-              const float* rp = residual + pix * (size_t)p.res_ld + c;
+              int n, po;
+              decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
+              const float* rp = residual + (size_t)n * img_res + c + po * p.res_ld;
               const bool ok = c_ok && n < p.B;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) r[4 * g + e] = ok ? __ldg(rp + e * p.osx * p.res_ld) : 0.f;
+              for (int e = 0; e < 4; ++e) r[4 * g + e] = ok ? __ldg(rp + e * rstep) : 0.f;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              int n;
-              size_t pix;
-              decode_pixel(p, t, ch + j, pa, pb, n, pix);
-              r[j] = (c_ok && n < p.B) ? __ldg(residual + pix * (size_t)p.res_ld + c) : 0.f;
+              int n, po;
+              decode_pixel(p, t, ch + j, pa, pb, n, po);
+              r[j] = (c_ok && n < p.B) ? __ldg(residual + (size_t)n * img_res + c + po * p.res_ld) : 0.f;
             }
           }
         }
         tmem_ld_wait();
         float acc[32];
         if (p.fast_epi) {
+          // >= 16 pixels per image: the image index is constant over each half of the chunk; two independent
+          // accumulator pairs shorten the dependent FADD/FFMA chains of the statistics
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
@@ -253,32 +261,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
               ra_c = (p.rowadd && c_ok) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
             }
             const float add_c = bias_c + ra_c;
+            float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-            for (int j = 16 * hf; j < 16 * hf + 16; ++j) {
-              float a = __uint_as_float(v[j]) + add_c;
-              if (residual) a += r[j];
-              acc[j] = a;
-              s1 += a;
-              s2 += a * a;
+            for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
+              float a0 = __uint_as_float(v[j]) + add_c;
+              float a1 = __uint_as_float(v[j + 1]) + add_c;
+              if (residual) { a0 += r[j]; a1 += r[j + 1]; }
+              acc[j] = a0;
+              acc[j + 1] = a1;
+              s1 += a0; t1 += a1;
+              s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
             }
+            s1 += t1;
+            s2 += t2;
           }
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = t.n0 + ((ch + j) >> p.lg_bhw);
-            if (n != cur_n) {
-              if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
-                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
-                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+  #pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            // the image index can only change between groups of 4 pixels when every image has >= 4 pixels per tile
+            const int n = t.n0 + ((ch + 4 * g) >> p.lg_bhw);
+            if (p.lg_bhw >= 2) {
+              if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
+                if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+                }
+                s1 = 0.f; s2 = 0.f;
+                cur_n = n;
+                ra_c = (p.rowadd && c_ok && n < p.B) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
               }
-              s1 = 0.f; s2 = 0.f;
-              cur_n = n;
-              ra_c = (p.rowadd && c_ok && n < p.B) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+              const float add_c = bias_c + ra_c;
+              const bool n_ok = n < p.B;
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = __uint_as_float(v[4 * g + e]) + add_c;
+                if (residual) a += r[4 * g + e];
+                acc[4 * g + e] = a;
+                if (n_ok) { s1 += a; s2 += a * a; }
+              }
+            } else {
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ne = t.n0 + ((ch + 4 * g + e) >> p.lg_bhw);
+                if (ne != cur_n) {
+                  if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+                  }
+                  s1 = 0.f; s2 = 0.f;
+                  cur_n = ne;
+                  ra_c = (p.rowadd && c_ok && ne < p.B) ? __ldg(p.rowadd + (size_t)ne * p.rowadd_ld + c) : 0.f;
+                }
+                float a = __uint_as_float(v[4 * g + e]) + bias_c + ra_c;
+                if (residual) a += r[4 * g + e];
+                acc[4 * g + e] = a;
+                if (ne < p.B) { s1 += a; s2 += a * a; }
+              }
             }
-            float a = __uint_as_float(v[j]) + bias_c + ra_c;
-            if (residual) a += r[j];
-            acc[j] = a;
-            if (n < p.B) { s1 += a; s2 += a * a; }
           }
         }
         if (p.fast_epi && p.out_mode == B200_OUT_F32_NHWC) {
@@ -296,48 +335,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         } else if (p.group4 && p.out_mode <= B200_OUT_BF16_NHWC) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            int n;
-            size_t pix;
-            decode_pixel(p, t, ch + 4 * g, pa, pb, n, pix);
+            int n, po;
+            decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
             if (c_ok && n < p.B) {
               if (p.out_mode == B200_OUT_F32_NHWC) {
-                float* __restrict__ o = reinterpret_cast<float*>(p.out) + pix * (size_t)p.out_ld + c;
+                float* __restrict__ o = reinterpret_cast<float*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e * p.osx * p.out_ld] = acc[4 * g + e];
+                for (int e = 0; e < 4; ++e) o[e * ostep] = acc[4 * g + e];
               } else {
-                __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * (size_t)p.out_ld + c;
+                __nv_bfloat16* __restrict__ o =
+                    reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e * p.osx * p.out_ld] = __float2bfloat16_rn(acc[4 * g + e]);
+                for (int e = 0; e < 4; ++e) o[e * ostep] = __float2bfloat16_rn(acc[4 * g + e]);
               }
             }
           }
-        } else if (p.out_mode == B200_OUT_F32_NHWC) {
-          float* __restrict__ o = reinterpret_cast<float*>(p.out);
+        } else if (p.out_mode <= B200_OUT_BF16_NHWC) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            int n;
-            size_t pix;
-            decode_pixel(p, t, ch + j, pa, pb, n, pix);
-            if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = acc[j];
-          }
-        } else if (p.out_mode == B200_OUT_BF16_NHWC) {
-          __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(p.out);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int n;
-            size_t pix;
-            decode_pixel(p, t, ch + j, pa, pb, n, pix);
-            if (c_ok && n < p.B) o[pix * (size_t)p.out_ld + c] = __float2bfloat16_rn(acc[j]);
+            int n, po;
+            decode_pixel(p, t, ch + j, pa, pb, n, po);
+            if (c_ok && n < p.B) {
+              const size_t e = (size_t)n * img_out + c + po * p.out_ld;
+              if (p.out_mode == B200_OUT_F32_NHWC) reinterpret_cast<float*>(p.out)[e] = acc[j];
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
+            }
           }
         } else if (p.vec8_ok) {
           // channel-major outputs: this thread owns a row of consecutive pixels -> 8-pixel vector stores
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int pp = ch + 8 * g;
-            const int n = t.n0 + (pp >> p.lg_bhw);
-            const int oy = t.h0 + ((pp >> p.lg_bw) & (p.bh - 1));
-            const int ox = t.w0 + (pp & (p.bw - 1));
-            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + (size_t)oy * p.out_W + ox;
+            int n, po;
+            decode_pixel(p, t, ch + 8 * g, 0, 0, n, po);
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
             if (c_ok && n < p.B) {
               if (p.out_mode == B200_OUT_F32_NCHW) {
                 float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e);
@@ -356,11 +386,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int pp = ch + j;
-            const int n = t.n0 + (pp >> p.lg_bhw);
-            const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
-            const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + (size_t)oy * p.out_W + ox;
+            int n, po;
+            decode_pixel(p, t, ch + j, pa, pb, n, po);
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
             if (c_ok && n < p.B) {
               if (p.out_mode == B200_OUT_F32_NCHW) reinterpret_cast<float*>(p.out)[e] = acc[j];
               else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
@@ -498,8 +526,11 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     rc = encode_tmap(&mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
+  static const char* env_halves = getenv("B200_EPI_HALVES");
+  p.epi_halves = (env_halves && atoi(env_halves) == 1) ? 1 : 2;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
+  conv_gemm_kernel<<<grid, 64 + 128 * p.epi_halves, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
 }

@@ -67,9 +67,9 @@ def lib():
     L.b200_conv2d_fwd.argtypes = [POINTER(ConvDesc), c_void_p]
     L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p]
-    L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
-                                           c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,
-                                           c_int, c_void_p, c_void_p, c_void_p]
+    L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                           c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.b200_groupnorm_silu_fwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p]
@@ -321,12 +321,14 @@ def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, bet
     """Streaming GroupNorm(+SiLU) for inputs whose [B][C][2] statistics came from the producing kernel."""
     _need_cuda(x0, stats0, out)
     _launch('groupnorm_apply',
-            lambda: _check(lib().b200_groupnorm_apply_fwd(x0.data_ptr(), C0, stats0.data_ptr(), _ptr(x1), C1,
+            lambda: _check(lib().b200_groupnorm_apply_fwd(x0.data_ptr(), int(x0.dtype == torch.bfloat16), C0,
+                                                          stats0.data_ptr(), _ptr(x1), C1,
                                                           _ptr(stats1), B, HW, W, groups, _ptr(gamma), _ptr(beta),
                                                           float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu),
                                                           resample, out.data_ptr(), _ptr(raw_out), _stream()),
                            'groupnorm_apply_fwd'),
-            nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None))
+            nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None) -
+            (2.0 * B * HW * C0 if x0.dtype == torch.bfloat16 else 0.0))
     return out
 
 

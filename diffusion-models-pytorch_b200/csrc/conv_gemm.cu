@@ -43,6 +43,7 @@ struct ConvKParams {
   int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
   int group4;    // bw >= 4: 4 consecutive tile pixels are 4 output pixels osx apart in one row
   int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
+  int k_rotate;    // rotate the K-block order per CTA (spreads weight-tile requests over L2)
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
 };
 
@@ -135,7 +136,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const int wrow = t.ph * p.w_rows_per_phase + t.ct * kBlockC;
-        for (int kb = 0; kb < nkb; ++kb) {
+        // Every CTA walks the K-blocks of its tile from a different starting point: otherwise all SMs request
+        // the same 16 KB weight tile from the same L2 lines at the same moment (accumulation order is irrelevant).
+        const int rot = p.k_rotate ? (int)((blockIdx.x * 5u + (unsigned)tile) % (unsigned)nkb) : 0;
+        for (int kbi = 0; kbi < nkb; ++kbi) {
+          int kb = kbi + rot;
+          if (kb >= nkb) kb -= nkb;
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sW = smem + (size_t)stage * stage_bytes;
           uint8_t* sP = sW + kWBytes;
@@ -447,7 +453,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   B200_REQUIRE(d->out_mode >= 0 && d->out_mode <= 3, "conv2d_fwd: bad out_mode");
   B200_REQUIRE(((uintptr_t)d->a0 & 127) == 0 && ((uintptr_t)d->w & 127) == 0 && ((uintptr_t)d->out & 15) == 0,
                "conv2d_fwd: a0/w must be 128-byte aligned and out 16-byte aligned");
-  B200_REQUIRE(d->stats == nullptr || d->out_mode == B200_OUT_F32_NHWC, "conv2d_fwd: statistics need an fp32 NHWC output");
+  B200_REQUIRE(d->stats == nullptr || d->out_mode <= B200_OUT_BF16_NHWC, "conv2d_fwd: statistics need an NHWC output");
 
   // ---- pixel tile: NP = bw x bh x bn pixels, power-of-two factors of the output grid ----
   int maxw = 1;
@@ -465,7 +471,8 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   memset(&p, 0, sizeof(p));
   // largest pixel tile that still gives (nearly) every SM a tile; otherwise the smallest valid one
   int best_np = 0;
-  for (int np = 256; np >= 64; np >>= 1) {
+  static const char* env_np = getenv("B200_MAX_NP");
+  for (int np = env_np ? atoi(env_np) : 256; np >= 64; np >>= 1) {
     const int bw = maxw < np ? maxw : np;
     const int bh = maxh < np / bw ? maxh : np / bw;
     const int bn = np / (bw * bh);
@@ -474,7 +481,9 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     p.NP = np; p.bw = bw; p.bh = bh; p.bn = bn;
     p.p_tiles = (int)p_tiles;
     best_np = np;
-    if (p_tiles * c_tiles * d->phases >= (long)g_num_sms * 3 / 4) break;
+    static const char* env_fill = getenv("B200_MIN_FILL");  // experiment knob: required tiles, in 1/4 SM counts
+    const long need = (long)g_num_sms * (env_fill ? atoi(env_fill) : 3) / 4;
+    if (p_tiles * c_tiles * d->phases >= need) break;
   }
   B200_REQUIRE(best_np != 0, "conv2d_fwd: unsupported spatial size %dx%d (need power-of-two factors)", d->Ho, d->Wo);
   p.B = d->B;
@@ -507,6 +516,8 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   const int stage_bytes = kWBytes + p.NP * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  static const char* env_stages = getenv("B200_STAGES");
+  if (env_stages && atoi(env_stages) >= 2 && atoi(env_stages) < stages) stages = atoi(env_stages);
   p.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvBarriers) + 1024;
 
@@ -529,6 +540,8 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
   static const char* env_halves = getenv("B200_EPI_HALVES");
   p.epi_halves = (env_halves && atoi(env_halves) == 1) ? 1 : 2;
+  static const char* env_rot = getenv("B200_K_ROTATE");
+  p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   conv_gemm_kernel<<<grid, 64 + 128 * p.epi_halves, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
   ++g_launch_count;

@@ -286,10 +286,18 @@ struct GnApplyParams {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
+  int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg4_bf16(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 r;
+  r.x = __uint_as_float(u.x << 16); r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16); r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
 // SiLU through one MUFU op: x * sigmoid(x) = x * (0.5 * tanh(x / 2) + 0.5); tanh.approx error (2^-11) is below the
 // half-ulp of the bf16 the value is rounded to.
 __device__ __forceinline__ float silu_tanh(float x) {
@@ -348,11 +356,13 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
       const int sld = from0 ? p.C0 : p.C1;
       __nv_bfloat16* dst = p.out + (size_t)n * p.HW * C + c;
       __nv_bfloat16* rdst = p.raw ? p.raw + (size_t)n * p.HW * C + c : nullptr;
+      const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.x0) + (size_t)n * p.HW * p.C0 + c;
       for (int px = px0 + prow; px < px1; px += 4 * pstep) {
         float4 vv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (px + u * pstep < px1) vv[u] = ldg4(src + (size_t)(px + u * pstep) * sld);
+          if (px + u * pstep < px1)
+            vv[u] = p.in_bf16 ? ldg4_bf16(srcb + (size_t)(px + u * pstep) * sld) : ldg4(src + (size_t)(px + u * pstep) * sld);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int q = px + u * pstep;
@@ -387,8 +397,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
         pxs[u] = px0 + pl;
         cs[u] = j << 2;
         if (idx < total) {
-          vv[u] = (cs[u] < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + pxs[u]) * p.C0 + cs[u])
-                                 : ldg4(p.x1 + ((size_t)n * p.HW + pxs[u]) * p.C1 + (cs[u] - p.C0));
+          if (p.in_bf16)
+            vv[u] = ldg4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x0) + ((size_t)n * p.HW + pxs[u]) * p.C0 + cs[u]);
+          else
+            vv[u] = (cs[u] < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + pxs[u]) * p.C0 + cs[u])
+                                   : ldg4(p.x1 + ((size_t)n * p.HW + pxs[u]) * p.C1 + (cs[u] - p.C0));
         }
       }
 #pragma unroll
@@ -446,8 +459,10 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const int px = (2 * oy + dy) * p.W + 2 * ox + dx;
-          const float4 v = (c < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + px) * p.C0 + c)
-                                      : ldg4(p.x1 + ((size_t)n * p.HW + px) * p.C1 + (c - p.C0));
+          float4 v;
+          if (p.in_bf16) v = ldg4_bf16(reinterpret_cast<const __nv_bfloat16*>(p.x0) + ((size_t)n * p.HW + px) * p.C0 + c);
+          else v = (c < p.C0) ? ldg4(p.x0 + ((size_t)n * p.HW + px) * p.C0 + c)
+                              : ldg4(p.x1 + ((size_t)n * p.HW + px) * p.C1 + (c - p.C0));
           float y[4] = {v.x * a.x + b.x, v.y * a.y + b.y, v.z * a.z + b.z, v.w * a.w + b.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[i] += p.apply_silu ? silu_tanh(y[i]) : y[i];
@@ -462,14 +477,16 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
 
 }  // namespace b200
 
-extern "C" int b200_groupnorm_apply_fwd(const float* x0, int C0, const float* stats0, const float* x1, int C1,
-                                        const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0, const float* x1,
+                                        int C1, const float* stats1, int B, int HW, int W, int groups, const float* gamma,
                                         const float* beta, float eps, const float* scale, const float* shift,
                                         int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
                                         void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const float* x0 = reinterpret_cast<const float*>(x0_);
   B200_REQUIRE(x0 && stats0 && out_bf16, "groupnorm_apply: null x0/stats0/out");
   if (!x1) C1 = 0;
+  B200_REQUIRE(!x0_is_bf16 || (x1 == nullptr && raw_out_bf16 == nullptr), "groupnorm_apply: a bf16 input must be the only source");
   B200_REQUIRE(x1 == nullptr || stats1 != nullptr, "groupnorm_apply: second source needs its statistics");
   const int C = C0 + C1;
   B200_REQUIRE(groups > 0 && C % groups == 0, "groupnorm_apply: C=%d not divisible by groups=%d", C, groups);
@@ -485,6 +502,7 @@ extern "C" int b200_groupnorm_apply_fwd(const float* x0, int C0, const float* st
   p.HW = HW; p.W = W; p.groups = groups; p.cpg = C / groups;
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
   p.apply_silu = apply_silu; p.resample = resample;
+  p.in_bf16 = x0_is_bf16 ? 1 : 0;
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
   const int work_pix = resample == 1 ? HW / 4 : HW;

@@ -67,7 +67,8 @@ typedef struct b200_conv_desc {
   const float* residual; /* fp32 NHWC [B][out_H][out_W][res_ld] or NULL */
   int res_ld;
   float* stats;          /* optional [B][N][2] fp32, pre-zeroed: per-(image, channel) sum and sum of squares of the
-                            fp32 NHWC output are atomically accumulated here for the GroupNorm that follows */
+                            NHWC output (before any rounding to bf16) are atomically accumulated here for the
+                            GroupNorm that follows */
   void* out;
   int out_mode;        /* B200_OUT_* */
   int out_ld;          /* channel stride of NHWC outputs; for NCHW outputs the channel count */
@@ -100,8 +101,10 @@ int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, in
 /* Streaming variant of K3 for inputs whose per-(image, channel) statistics [B][C][2] = (sum, sum of squares) were
  * accumulated by the producing kernel (b200_conv_desc.stats): one coalesced pass, 4 B read + 2 B written per
  * element.  Same semantics and arguments as b200_groupnorm_silu_fwd otherwise. */
-int b200_groupnorm_apply_fwd(const float* x0, int C0, const float* stats0, const float* x1, int C1,
-                             const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+int b200_groupnorm_apply_fwd(const void* x0, int x0_is_bf16 /* x0 is bf16 NHWC (single source, statistics taken
+                             from the fp32 accumulators of its producer) */, int C0, const float* stats0,
+                             const float* x1, int C1, const float* stats1, int B, int HW, int W, int groups,
+                             const float* gamma,
                              const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
                              int apply_silu, int resample, void* out_bf16, void* raw_out_bf16, void* stream);
 

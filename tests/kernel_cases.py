@@ -286,6 +286,30 @@ def _gn_case(name, B, C0, C1, H, W, silu=True, adagn=False, resample=0, raw=Fals
         ok &= _report(name + ' [streaming, producer stats]', out2.permute(0, 3, 1, 2), ref, rtol=5e-3, atol=5e-3)
         if raw:
             ok &= _report(name + ' [streaming raw copy]', raw2, xcat.to(torch.bfloat16), 0, 0)
+        if C1 == 0 and not raw:
+            # bf16-stored input whose statistics were taken from the fp32 values by its producer
+            xb = x0.to(torch.bfloat16)
+            cpg = C // 32
+            xg = x0.permute(0, 3, 1, 2).reshape(B, 32, cpg * H * W)
+            mean = xg.mean(dim=2)[:, :, None, None, None]
+            var = xg.var(dim=2, unbiased=False)[:, :, None, None, None]
+            xr = xb.float().permute(0, 3, 1, 2).reshape(B, 32, cpg, H, W)
+            refb = ((xr - mean) * torch.rsqrt(var + eps)).reshape(B, C, H, W) * gamma[None, :, None, None] + \
+                beta[None, :, None, None]
+            if adagn:
+                refb = refb * (1 + ys[:, :C, None, None]) + ys[:, C:2 * C, None, None]
+            if silu:
+                refb = F.silu(refb)
+            if resample == 1:
+                refb = F.avg_pool2d(refb, 2, 2)
+            elif resample == 2:
+                refb = F.interpolate(refb, scale_factor=2, mode='nearest')
+            out3 = torch.full((B, Ho, Wo, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+            K.groupnorm_apply(xb, C0, st(x0), None, 0, None, B, H * W, W, 32, gamma, beta, eps, out3,
+                              scale=ys if adagn else None, shift=ys[:, C:] if adagn else None,
+                              ss_ld=(2 * C + 8) if adagn else 0, silu=silu, resample=resample)
+            torch.cuda.synchronize()
+            ok &= _report(name + ' [streaming, bf16 input]', out3.permute(0, 3, 1, 2), refb, rtol=5e-3, atol=5e-3)
     return ok
 
 

@@ -1,0 +1,56 @@
+"""The N > 1 host logic on CPU: world_size-2 gloo process group (rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from b200diff.dist import allreduce_mean_, gather_samples, rank_seed, shard_plan
+
+
+def test_shard_plan_matches_reference_formula():
+    # scripts/sample_uncond.py:182-183: bspp = min(batch_size, ceil(n / P)); folds = amortize(n, bspp * P)
+    assert shard_plan(50000, 256, 8) == (256, [2048] * 24 + [848])
+    assert shard_plan(64, 256, 8) == (8, [64])
+    assert shard_plan(100, 16, 1) == (16, [16] * 6 + [4])
+    assert shard_plan(10, 256, 4) == (3, [10])
+    assert rank_seed(2022, 3) == 2025
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        bspp, folds = shard_plan(10, 4, world)
+        g = torch.Generator().manual_seed(rank_seed(2022, rank))
+        mine = torch.randn(bspp, 3, 2, 2, generator=g)             # "samples" of this rank, no traffic while sampling
+        allx = gather_samples(mine, keep=folds[0])
+        grads = [torch.full((5,), float(rank + 1)), torch.full((2, 3), float(10 * (rank + 1)))]
+        allreduce_mean_(grads, bucket_bytes=16)
+        ret[rank] = (allx.clone(), [t.clone() for t in grads], mine.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_and_allreduce_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+    assert torch.equal(r0[0], r1[0])                                   # every rank sees the same gathered batch
+    assert torch.equal(r0[0], torch.cat([r0[2], r1[2]], dim=0)[:8])   # rank order, truncated to the fold size
+    assert not torch.equal(r0[2], r1[2])                               # rank-specific seeds
+    for t0, t1, want in zip(r0[1], r1[1], (1.5, 15.0)):
+        assert torch.allclose(t0, torch.full_like(t0, want)) and torch.equal(t0, t1)

@@ -162,6 +162,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the single JSON line
         dist.init_process_group('nccl', device_id=dev)
     B, S = args.batch, args.sample_steps
 

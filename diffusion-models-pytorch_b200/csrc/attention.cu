@@ -185,6 +185,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
 }  // namespace b200
 
+namespace b200 {
+int attention_kv64(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out, int B, int T,
+                   int heads, float scale, cudaStream_t stream);
+}
 using namespace b200;
 
 extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
@@ -192,7 +196,12 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(qk && vt && out, "attention_fwd: null pointer");
   B200_REQUIRE(d == 64 || d == 128 || d == 256, "attention_fwd: head dim %d not in {64,128,256}", d);
-  B200_REQUIRE(T >= 8 && T <= 256 && T % 8 == 0, "attention_fwd: T=%d must be a multiple of 8 in [8,256]", T);
+  B200_REQUIRE(T >= 8 && T % 8 == 0, "attention_fwd: T=%d must be a positive multiple of 8", T);
+  if (T > 256) {
+    B200_REQUIRE(d == 64, "attention_fwd: T=%d > 256 is supported for head dim 64 only (got %d)", T, d);
+    B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
+    return attention_kv64(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, scale, stream);
+  }
   B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
   B200_REQUIRE(((uintptr_t)qk & 127) == 0 && ((uintptr_t)vt & 127) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: alignment");
   const int Tp = (T + 63) / 64 * 64;
@@ -235,3 +244,241 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "attention_kernel launch");
 }
+
+// ================================================================================================
+// K2, long-sequence variant (T > 256, head dim 64: ADM 32x32 attention, T = 1024): flash-style loop over key/value
+// tiles of 256 keys with an online softmax.  Per tile: S = Q K_j^T (tcgen05, TMEM cols [0,256)), row max / exp2 /
+// row sum in registers, P (bf16) to swizzled smem, O_j = P V_j (TMEM cols [256, 320)), and the running output
+// O = O * alpha + O_j is kept in 64 fp32 registers per thread (one query row each).  K/V tiles are double-buffered:
+// the TMA for tile j+1 is in flight while tile j is processed.
+// ================================================================================================
+namespace b200 {
+
+struct AttnKvParams {
+  int T, q_off, k_off, n_tiles;
+  float scale_log2e;
+  __nv_bfloat16* out;
+  int ld_out;
+};
+
+struct __align__(8) AttnKvBars {
+  uint64_t q_full, kv_full[2], s_done, o_done;
+  uint32_t tmem_base;
+};
+
+constexpr int kKvTile = 256;
+
+__global__ void __launch_bounds__(128, 1)
+attention_kv64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AttnKvParams p) {
+  constexpr int D = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;                                // [128 rows][128 B]                    16 KB
+  uint8_t* sK = sQ + 16384;                          // [2][256 rows][128 B]                 64 KB
+  uint8_t* sV = sK + 2 * 32768;                      // [2][4 key chunks][64 rows][128 B]    64 KB
+  uint8_t* sP = sV + 2 * 32768;                      // [4 key chunks][128 rows][128 B]      64 KB
+  AttnKvBars* bars = reinterpret_cast<AttnKvBars*>(sP + 65536);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->kv_full[0], 1);
+    mbar_init(&bars->kv_full[1], 1);
+    mbar_init(&bars->s_done, 1);
+    mbar_init(&bars->o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = bars->tmem_base;
+  const uint32_t tmem_o = tmem_s + 256;
+
+  auto load_kv = [&](int j) {   // thread 0 only
+    const int buf = j & 1;
+    mbar_arrive_expect_tx(&bars->kv_full[buf], 32768u + 32768u);
+    tma_load_3d(sK + buf * 32768, &mapK, &bars->kv_full[buf], p.k_off + h * D, j * kKvTile, b);
+    for (int c = 0; c < 4; ++c)
+      tma_load_3d(sV + buf * 32768 + c * 8192, &mapV, &bars->kv_full[buf], j * kKvTile + c * 64, h * D, b);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars->q_full, 16384u);
+    tma_load_3d(sQ, &mapQ, &bars->q_full, p.q_off + h * D, q0, b);
+    load_kv(0);
+    if (p.n_tiles > 1) load_kv(1);
+    mbar_wait(&bars->q_full, 0);
+  }
+  __syncwarp();
+
+  const int r = warp * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16_m128(kKvTile);
+  const uint32_t idesc_o = umma_idesc_bf16_m128(D);
+  float o_acc[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = 0; j < p.n_tiles; ++j) {
+    const int buf = j & 1;
+    const uint32_t par = (uint32_t)j & 1u;
+    if (threadIdx.x == 0) {
+      mbar_wait(&bars->kv_full[buf], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sQ));
+      const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sK + buf * 32768));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_s, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(&bars->s_done);
+    }
+    __syncwarp();
+    mbar_wait(&bars->s_done, par);
+    tc_fence_after();
+
+    // ---- online softmax over this tile's 256 score columns ----
+    const int kbase = j * kKvTile;
+    float m_tile = -INFINITY;
+    for (int c = 0; c < kKvTile; c += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (kbase + c + i < p.T) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+    }
+    const float m_new = fmaxf(m_run, m_tile);
+    const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * p.scale_log2e);
+    const float ms = m_new * p.scale_log2e;
+    float sum = 0.f;
+    for (int c = 0; c < kKvTile; c += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = (kbase + c + i < p.T) ? exp2f(__uint_as_float(v[i]) * p.scale_log2e - ms) : 0.f;
+        e[i] = x;
+        sum += x;
+      }
+      uint8_t* prow = sP + (size_t)(c >> 6) * 16384 + (size_t)r * 128;
+      const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(e[8 * i + 0], e[8 * i + 1]);
+        u.y = pack_bf16x2(e[8 * i + 2], e[8 * i + 3]);
+        u.z = pack_bf16x2(e[8 * i + 4], e[8 * i + 5]);
+        u.w = pack_bf16x2(e[8 * i + 6], e[8 * i + 7]);
+        *reinterpret_cast<uint4*>(prow + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+      }
+    }
+    l_run = l_run * alpha + sum;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- O_j = P V_j ----
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sP + c * 16384));
+        const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sV + buf * 32768 + c * 8192));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&bars->o_done);
+    }
+    __syncwarp();
+    mbar_wait(&bars->o_done, par);
+    tc_fence_after();
+    if (threadIdx.x == 0 && j + 2 < p.n_tiles) load_kv(j + 2);   // buffer `buf` is free again
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < D; c += 32) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_o + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
+    }
+    // all threads must have read S / O of this tile before the next tile's MMAs overwrite them
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  const float inv = 1.0f / l_run;
+  if (q0 + r < p.T) {
+    __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q0 + r) * p.ld_out + h * D;
+#pragma unroll
+    for (int i = 0; i < D; i += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+      u.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+      u.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+      u.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + i) = u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_s, 512);
+  }
+}
+
+int attention_kv64(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out, int B, int T,
+                   int heads, float scale, cudaStream_t stream) {
+  constexpr int D = 64;
+  AttnKvParams p;
+  p.T = T; p.q_off = q_off; p.k_off = k_off;
+  p.n_tiles = (T + kKvTile - 1) / kKvTile;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  CUtensorMap mapQ, mapK, mapV;
+  {
+    uint64_t dims[3] = {(uint64_t)ld_qk, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)ld_qk * 2, (uint64_t)T * ld_qk * 2};
+    uint32_t boxq[3] = {64, 128, 1};
+    uint32_t boxk[3] = {64, (uint32_t)kKvTile, 1};
+    int rc = encode_tmap(&mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tmap(&mapK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxk, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)T, (uint64_t)heads * D, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)T * 2, (uint64_t)heads * D * T * 2};
+    uint32_t box[3] = {64, (uint32_t)D, 1};
+    int rc = encode_tmap(&mapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const size_t smem = 16384 + 65536 + 65536 + 65536 + sizeof(AttnKvBars) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(attention_kv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  dim3 grid((T + 127) / 128, heads, B);
+  attention_kv64_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "attention_kv64_kernel launch");
+}
+
+}  // namespace b200

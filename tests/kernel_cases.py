@@ -424,6 +424,8 @@ def case_attention():
     ok &= _attn_case('attention T=256 h=4 d=64 (CFG UNet)', 2, 256, 4, 64)
     ok &= _attn_case('attention T=64 h=4 d=64 (CFG UNet 8x8)', 3, 64, 4, 64)
     ok &= _attn_case('attention T=256 h=2 d=128', 2, 256, 2, 128)
+    ok &= _attn_case('attention T=1024 h=8 d=64 (ADM 32x32, KV loop)', 2, 1024, 8, 64)
+    ok &= _attn_case('attention T=576 h=2 d=64 (ragged last KV tile)', 2, 576, 2, 64)
     return ok
 
 

@@ -188,6 +188,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 namespace b200 {
 int attention_kv64(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out, int B, int T,
                    int heads, float scale, cudaStream_t stream);
+int attention_wide(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out, int B, int T,
+                   int heads, int d, float scale, cudaStream_t stream);
 }
 using namespace b200;
 
@@ -195,8 +197,13 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
                                   int B, int T, int heads, int d, float scale, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(qk && vt && out, "attention_fwd: null pointer");
-  B200_REQUIRE(d == 64 || d == 128 || d == 256, "attention_fwd: head dim %d not in {64,128,256}", d);
+  B200_REQUIRE(d >= 64 && d <= 512 && d % 64 == 0, "attention_fwd: head dim %d must be a multiple of 64 in [64,512]", d);
   B200_REQUIRE(T >= 8 && T % 8 == 0, "attention_fwd: T=%d must be a positive multiple of 8", T);
+  if (T <= 256 && !(d == 64 || d == 128 || d == 256)) {
+    B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
+    B200_REQUIRE(((uintptr_t)qk & 127) == 0 && ((uintptr_t)vt & 127) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: alignment");
+    return attention_wide(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale, stream);
+  }
   if (T > 256) {
     B200_REQUIRE(d == 64, "attention_fwd: T=%d > 256 is supported for head dim 64 only (got %d)", T, d);
     B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
@@ -479,6 +486,249 @@ int attention_kv64(const void* qk, int ld_qk, int q_off, int k_off, const void* 
   attention_kv64_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "attention_kv64_kernel launch");
+}
+
+}  // namespace b200
+
+
+// ================================================================================================
+// K2, wide-head variant (T <= 256, head dim up to 512: the single-head attention of the pesser / DDPM CelebA-HQ UNet,
+// C = 512 at 16x16).  Q/K do not fit in shared memory at once, so S = sum over 64-wide channel chunks of Q_c K_c^T is
+// accumulated from a 2-stage TMA ring; after the softmax (P in smem) the accumulator columns are reused for
+// O[128 x d] (up to 512 fp32 columns = all of TMEM), computed as two N <= 256 halves per 64-key chunk of V^T, again
+// from a 2-stage ring.
+// ================================================================================================
+namespace b200 {
+
+struct AttnWideParams {
+  int T, Tp, d, q_off, k_off;
+  float scale_log2e;
+  __nv_bfloat16* out;
+  int ld_out;
+};
+
+struct __align__(8) AttnWideBars {
+  uint64_t full[2], empty[2], vfull[2], vempty[2], s_done, o_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1)
+attention_wide_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AttnWideParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int dk = p.d >> 6, tk = p.Tp >> 6;
+  const int qk_stage = 16384 + p.Tp * 128;          // Q chunk [128][128 B] + K chunk [Tp][128 B]
+  const int v_stage = p.d * 128;                    // V^T chunk [d][128 B] (64 keys)
+  const int ring = 2 * (qk_stage > v_stage ? qk_stage : v_stage);
+  uint8_t* sRing = smem;
+  uint8_t* sP = smem + ring;                        // [tk][128 rows][128 B]
+  AttnWideBars* bars = reinterpret_cast<AttnWideBars*>(sP + (size_t)tk * 16384);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->vfull[s], 1);
+      mbar_init(&bars->vempty[s], 1);
+    }
+    mbar_init(&bars->s_done, 1);
+    mbar_init(&bars->o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = bars->tmem_base;
+
+  auto load_qk = [&](int c) {   // thread 0 only
+    uint8_t* st = sRing + (size_t)(c & 1) * qk_stage;
+    mbar_arrive_expect_tx(&bars->full[c & 1], (uint32_t)qk_stage);
+    tma_load_3d(st, &mapQ, &bars->full[c & 1], p.q_off + h * p.d + c * 64, q0, b);
+    tma_load_3d(st + 16384, &mapK, &bars->full[c & 1], p.k_off + h * p.d + c * 64, 0, b);
+  };
+  auto load_v = [&](int c) {    // thread 0 only: V^T rows [h*d, h*d + d), keys [64c, 64c + 64), in boxes of <= 256 rows
+    uint8_t* st = sRing + (size_t)(c & 1) * v_stage;
+    mbar_arrive_expect_tx(&bars->vfull[c & 1], (uint32_t)v_stage);
+    for (int r0 = 0; r0 < p.d; r0 += 64)
+      tma_load_3d(st + (size_t)r0 * 128, &mapV, &bars->vfull[c & 1], c * 64, h * p.d + r0, b);
+  };
+
+  if (threadIdx.x == 0) {
+    // ---- S = sum_c Q_c K_c^T ----
+    load_qk(0);
+    if (dk > 1) load_qk(1);
+    const uint32_t idesc_s = umma_idesc_bf16_m128((uint32_t)p.Tp);
+    for (int c = 0; c < dk; ++c) {
+      mbar_wait(&bars->full[c & 1], (uint32_t)(c >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t base = smem_u32(sRing + (size_t)(c & 1) * qk_stage);
+      const uint64_t adesc = umma_desc_kmajor_sw128(base);
+      const uint64_t bdesc = umma_desc_kmajor_sw128(base + 16384);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+      umma_commit(&bars->empty[c & 1]);
+      if (c + 2 < dk) {
+        mbar_wait(&bars->empty[c & 1], (uint32_t)(c >> 1) & 1u);
+        load_qk(c + 2);
+      }
+    }
+    umma_commit(&bars->s_done);
+  }
+  __syncwarp();
+  mbar_wait(&bars->s_done, 0);
+  tc_fence_after();
+  if (threadIdx.x == 0) {   // all Q/K chunks are consumed: the ring is free for V^T
+    load_v(0);
+    if (tk > 1) load_v(1);
+  }
+  __syncwarp();
+
+  // ---- softmax over the score row held by this thread ----
+  const int r = warp * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  float m = -INFINITY;
+  for (int c = 0; c < p.Tp; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_acc + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+  }
+  const float ms = m * p.scale_log2e;
+  float sum = 0.f;
+  for (int c = 0; c < p.Tp; c += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_acc + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = (c + j < p.T) ? exp2f(__uint_as_float(v[j]) * p.scale_log2e - ms) : 0.f;
+      e[j] = x;
+      sum += x;
+    }
+    uint8_t* prow = sP + (size_t)(c >> 6) * 16384 + (size_t)r * 128;
+    const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16x2(e[8 * i + 0], e[8 * i + 1]);
+      u.y = pack_bf16x2(e[8 * i + 2], e[8 * i + 3]);
+      u.z = pack_bf16x2(e[8 * i + 4], e[8 * i + 5]);
+      u.w = pack_bf16x2(e[8 * i + 6], e[8 * i + 7]);
+      *reinterpret_cast<uint4*>(prow + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();       // every thread has read its S row: the accumulator columns may be overwritten by O
+  tc_fence_after();
+
+  // ---- O = P V, N halves of <= 256 columns ----
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < tk; ++c) {
+      mbar_wait(&bars->vfull[c & 1], (uint32_t)(c >> 1) & 1u);
+      tc_fence_after();
+      const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sP + (size_t)c * 16384));
+      const uint32_t vbase = smem_u32(sRing + (size_t)(c & 1) * v_stage);
+      for (int n0 = 0; n0 < p.d; n0 += 256) {
+        const int nn = (p.d - n0) < 256 ? (p.d - n0) : 256;
+        const uint32_t idesc_o = umma_idesc_bf16_m128((uint32_t)nn);
+        const uint64_t bdesc = umma_desc_kmajor_sw128(vbase + (uint32_t)n0 * 128u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_acc + (uint32_t)n0, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_o,
+                    (c > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&bars->vempty[c & 1]);
+      if (c + 2 < tk) {
+        mbar_wait(&bars->vempty[c & 1], (uint32_t)(c >> 1) & 1u);
+        load_v(c + 2);
+      }
+    }
+    umma_commit(&bars->o_done);
+  }
+  __syncwarp();
+  mbar_wait(&bars->o_done, 0);
+  tc_fence_after();
+  const float inv = 1.0f / sum;
+  const bool row_ok = (q0 + r) < p.T;
+  __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q0 + r) * p.ld_out + h * p.d;
+  for (int c = 0; c < p.d; c += 32) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(tmem_acc + lane_base + (uint32_t)c, v);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c + 8 * i) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, 512);
+  }
+}
+
+int attention_wide(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out, int B, int T,
+                   int heads, int d, float scale, cudaStream_t stream) {
+  const int Tp = (T + 63) / 64 * 64;
+  AttnWideParams p;
+  p.T = T; p.Tp = Tp; p.d = d; p.q_off = q_off; p.k_off = k_off;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  CUtensorMap mapQ, mapK, mapV;
+  {
+    uint64_t dims[3] = {(uint64_t)ld_qk, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)ld_qk * 2, (uint64_t)T * ld_qk * 2};
+    uint32_t boxq[3] = {64, 128, 1};
+    uint32_t boxk[3] = {64, (uint32_t)Tp, 1};
+    int rc = encode_tmap(&mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxq, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = encode_tmap(&mapK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qk, dims, strides, boxk, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)T, (uint64_t)heads * d, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)T * 2, (uint64_t)heads * d * T * 2};
+    uint32_t box[3] = {64, 64, 1};
+    int rc = encode_tmap(&mapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const int qk_stage = 16384 + Tp * 128, v_stage = d * 128;
+  const size_t smem = (size_t)2 * (qk_stage > v_stage ? qk_stage : v_stage) + (size_t)(Tp / 64) * 16384 +
+                      sizeof(AttnWideBars) + 1024;
+  B200_REQUIRE(smem <= 227 * 1024, "attention_fwd: smem %zu too large", smem);
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(attention_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  dim3 grid((T + 127) / 128, heads, B);
+  attention_wide_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "attention_wide_kernel launch");
 }
 
 }  // namespace b200

@@ -102,13 +102,6 @@ class Engine:
         return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight),
                                                   conv.bias.detach().float().contiguous()))
 
-    def w_qk(self, tag, blk):
-        def make():
-            w = torch.cat([K.pack_weight(blk.q.weight), K.pack_weight(blk.k.weight)], dim=0).contiguous()
-            b = torch.cat([blk.q.bias.detach(), blk.k.bias.detach()]).float().contiguous()
-            return w, b
-        return self.packed(('qk', tag), make)
-
     def w_tproj(self, linears: List[nn.Linear]):
         """All per-ResBlock embedding projections stacked into one [sum(out), E] bf16 matrix."""
         def make():
@@ -159,23 +152,33 @@ class Engine:
         return Act(out, B, H, W, Cout, stats)
 
     def attention(self, tag, blk, x: Act) -> Act:
+        """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2."""
+        def make():
+            wqk = torch.cat([K.pack_weight(blk.q.weight), K.pack_weight(blk.k.weight)], dim=0).contiguous()
+            bqk = torch.cat([blk.q.bias.detach(), blk.k.bias.detach()]).float().contiguous()
+            return (wqk, bqk, K.pack_weight(blk.v.weight), blk.v.bias.detach().float().contiguous(),
+                    K.pack_weight(blk.proj.weight), blk.proj.bias.detach().float().contiguous())
+        return self.attention_core(tag, x, blk.norm, self.packed(('attn', tag), make), blk.n_heads, blk.scale)
+
+    def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float) -> Act:
+        """GroupNorm -> [q|k] and v^T 1x1 convs -> fused softmax(q k^T * scale) v -> 1x1 proj + residual.
+        `weights` = (Wqk [2C, C] bf16 with rows [q heads..., k heads...], bqk, Wv [C, C], bv, Wproj, bproj)."""
         B, H, W, C = x.B, x.H, x.W, x.C
-        T, heads = H * W, blk.n_heads
+        T = H * W
         d = C // heads
-        if d not in (64, 128, 256) or T > 256 or T % 8 != 0:
-            raise RuntimeError(f'attention block {tag}: T={T}, head_dim={d} not supported by b200_attention_fwd '
-                               '(T <= 256, d in {64,128,256})')
-        n, _ = self.gn(tag, x, None, blk.norm, silu=False)
-        wqk, bqk = self.w_qk(tag, blk)
+        if T % 8 != 0 or not ((T <= 256 and d in (64, 128, 256)) or (T <= 256 and d % 64 == 0 and d <= 512 and heads == 1)
+                              or (T > 256 and d == 64)):
+            raise RuntimeError(f'attention block {tag}: T={T}, head_dim={d}, heads={heads} not supported by '
+                               'b200_attention_fwd')
+        wqk, bqk, wv, bv, wp, bp = weights
+        n, _ = self.gn(tag, x, None, norm, silu=False)
         qk = self.buf(tag + '.qk', (B, T, 2 * C), torch.bfloat16)
         K.conv2d(n, wqk, 2 * C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bqk, out=qk,
                  out_mode=K.OUT_BF16_NHWC)
-        wv, bv = self.w_conv(tag + '.v', blk.v)
         vt = self.buf(tag + '.vt', (B, C, T), torch.bfloat16)
         K.conv2d(n, wv, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bv, out=vt, out_mode=K.OUT_BF16_NCHW)
         o = self.buf(tag + '.o', (B, T, C), torch.bfloat16)
-        K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, blk.scale)
-        wp, bp = self.w_conv(tag + '.proj', blk.proj)
+        K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
         stats = self.stats_buf(tag, B, C)
         K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
@@ -207,49 +210,72 @@ class Engine:
                  w_rows_per_phase=Cout, stats=stats, alg_macs=9.0 * B * 4 * H * W * C * Cout)
         return Act(out, B, 2 * H, 2 * W, Cout, stats)
 
-    def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
-        """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
+    def resample_plain(self, tag, x: Act, mode: int) -> Act:
+        """Parameter-free 2x2 average pool (mode 1) / nearest 2x (mode 2) of the fp32 residual stream (the
+        conv_resample=False / with_conv=False variants).  The result carries no producer statistics, so the next
+        GroupNorm takes the exact two-pass slab kernel (small feature maps only)."""
+        B, H, W, C = x.B, x.H, x.W, x.C
+        Ho, Wo = (H // 2, W // 2) if mode == 1 else (H * 2, W * 2)
+        r = self.buf(tag + '.rs', (B, Ho, Wo, C), torch.float32)
+        (K.avgpool2_f32 if mode == 1 else K.upsample2_f32)(x.t, r, B, H, W, C)
+        return Act(r, B, Ho, Wo, C)
+
+    def resblock_core(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
+                      emb_ld, scale_shift: bool, resample: int = 0) -> Act:
+        """The ResBlock shared by all UNet families:
+            h = conv1(resample(SiLU(GN1(cat(x, skip)))))            (+ emb row when not scale_shift)
+            h = conv2(SiLU(GN2(h) [* (1 + scale) + shift]))          (dropout = identity in eval mode)
+            out = h + shortcut(resample(cat(x, skip)))
+        `emb` is the [rows, total] fp32 matrix of all per-block embedding projections, this block's columns start at
+        emb_off (scale_shift: [scale | shift], 2*Cout columns).  shortcut: None (identity), a 1x1 conv (folded into
+        conv2's GEMM as extra K-blocks) or a 3x3 conv (own launch, added as conv2's residual).
+        resample: 0 none, 1 = 2x2 average pool, 2 = nearest 2x of both h and x (BigGAN-style up/down blocks).
+        Reference: models/unet.py:30-43, models/unet_categorial_adagn.py:44-62, models/adm/unet.py:244-275,
+        models/pesser/model.py:114-134."""
         B, H, W = x.B, x.H, x.W
         Cin = x.C + (skip.C if skip is not None else 0)
-        conv1, conv2 = blk.blk1[2], blk.blk2[3]
         Cout = conv1.out_channels
-        has_sc = isinstance(blk.shortcut, nn.Conv2d)
-        a1, raw = self.gn(tag + '.1', x, skip, blk.blk1[0], raw=has_sc)
-        h = self.conv3x3(tag + '.c1', a1, B, H, W, Cin, conv1, rowadd=tproj[:, tproj_off:], rowadd_ld=tproj_ld,
-                         intermediate=True)
-        a2, _ = self.gn(tag + '.2', h, None, blk.blk2[0])
-        if has_sc:
-            return self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
-        assert skip is None and Cin == Cout
-        return self.conv3x3(tag + '.c2', a2, B, H, W, Cout, conv2, residual=x)
+        sc1x1 = shortcut is not None and shortcut.kernel_size[0] == 1
+        sc3x3 = shortcut is not None and not sc1x1
+        if resample and (shortcut is not None or skip is not None):
+            raise RuntimeError('up/down ResBlocks with a projection shortcut or a concatenated skip are not supported')
+        a1, raw = self.gn(tag + '.1', x, skip, norm1, raw=sc1x1 or sc3x3, resample=resample)
+        Ho, Wo = (H // 2, W // 2) if resample == 1 else (H * 2, W * 2) if resample == 2 else (H, W)
+        res_x = x
+        if resample:
+            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
+            (K.avgpool2_f32 if resample == 1 else K.upsample2_f32)(x.t, r, B, H, W, x.C)
+            res_x = Act(r, B, Ho, Wo, x.C)
+        if scale_shift:
+            h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, intermediate=True)
+            a2, _ = self.gn(tag + '.2', h, None, norm2, scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:],
+                            ss_ld=emb_ld)
+        else:
+            h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, rowadd=emb[:, emb_off:], rowadd_ld=emb_ld,
+                             intermediate=True)
+            a2, _ = self.gn(tag + '.2', h, None, norm2)
+        if sc1x1:
+            return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=shortcut)
+        if sc3x3:
+            res_x = self.conv3x3(tag + '.sc', raw, B, Ho, Wo, Cin, shortcut)
+        else:
+            assert skip is None and Cin == Cout
+        return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
+
+    def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
+        """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
+        return self.resblock_core(tag, x, skip, norm1=blk.blk1[0], conv1=blk.blk1[2], norm2=blk.blk2[0],
+                                  conv2=blk.blk2[3],
+                                  shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
+                                  emb=tproj, emb_off=tproj_off, emb_ld=tproj_ld, scale_shift=False)
 
     def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
         """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""
-        B, H, W = x.B, x.H, x.W
-        Cin = x.C + (skip.C if skip is not None else 0)
-        conv1, conv2 = blk.blk1[2], blk.blk2[2]
-        Cout = conv1.out_channels
-        has_sc = isinstance(blk.shortcut, nn.Conv2d)
-        resample = {'up': 2, 'down': 1}.get(blk.updown_kind, 0)
-        if resample and (has_sc or skip is not None):
-            raise RuntimeError('up/down ResBlocks with a projection shortcut are not supported')
-        a1, raw = self.gn(tag + '.1', x, skip, blk.blk1[0], raw=has_sc, resample=resample)
-        Ho, Wo = (H // 2, W // 2) if resample == 1 else (H * 2, W * 2) if resample == 2 else (H, W)
-        res_x = x
-        if resample == 1:
-            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
-            K.avgpool2_f32(x.t, r, B, H, W, x.C)
-            res_x = Act(r, B, Ho, Wo, x.C)
-        elif resample == 2:
-            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
-            K.upsample2_f32(x.t, r, B, H, W, x.C)
-            res_x = Act(r, B, Ho, Wo, x.C)
-        h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, intermediate=True)
-        a2, _ = self.gn(tag + '.2', h, None, blk.adagn.gn, scale=ss[:, ss_off:], shift=ss[:, ss_off + Cout:],
-                        ss_ld=ss_ld)
-        if has_sc:
-            return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=blk.shortcut)
-        return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
+        return self.resblock_core(tag, x, skip, norm1=blk.blk1[0], conv1=blk.blk1[2], norm2=blk.adagn.gn,
+                                  conv2=blk.blk2[2],
+                                  shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
+                                  emb=ss, emb_off=ss_off, emb_ld=ss_ld, scale_shift=True,
+                                  resample={'up': 2, 'down': 1}.get(blk.updown_kind, 0))
 
     # ------------------------------------------------------------------------------------------
     # embedding path
@@ -267,7 +293,8 @@ class Engine:
         freqs = self.packed(('freqs',), lambda: pos_emb.frequencies(dev).float().contiguous())
         emb = self.buf('emb', (rows, E), torch.float32)
         semb = self.buf('semb', (rows, E), torch.bfloat16)
-        K.time_embed(t_rows, freqs, pos_emb.dim, E, False, lin1.weight, lin1.bias, lin2.weight, lin2.bias, emb,
+        K.time_embed(t_rows, freqs, pos_emb.dim, E, bool(getattr(pos_emb, 'cos_first', False)), lin1.weight, lin1.bias,
+                     lin2.weight, lin2.bias, emb,
                      y=y if use_y else None, class_embed=class_embed.weight if use_y else None, out_silu_bf16=semb)
         w, b = self.w_tproj(proj_linears)
         total = w.shape[0]

@@ -201,6 +201,109 @@ def case_cfg():
     return ok
 
 
+def _family_product(c):
+    from models.adm.unet import UNetModel
+    from models.adm.unet_combined import UNetCombined
+    from models.pesser.model import Model
+    from oracle.adm_ref import randomize_zero_params
+    torch.manual_seed(c['seed'])
+    if c['family'] == 'pesser':
+        return Model(**c['cfg']).to(DEV).eval()
+    m = (UNetCombined if c['family'] == 'adm_combined' else UNetModel)(**c['cfg'])
+    m.load_state_dict(randomize_zero_params(m.state_dict()))
+    return m.to(DEV).eval()
+
+
+def case_families_golden():
+    """ADM (cond scale-shift / plain / UNetCombined) and pesser toy configs against the REFERENCE's own outputs frozen
+    in tests/golden/family_forward.pt (product modules re-create the reference's seeded weights)."""
+    _no_tf32()
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'family_forward.pt'), weights_only=False)
+    ok = True
+    for name, c in gold.items():
+        m = _family_product(c)
+        x, t = c['x'].to(DEV), c['t'].to(DEV)
+        y = None if c['y'] is None else c['y'].to(DEV)
+        with torch.no_grad():
+            got = m(x, t, y) if c['family'] != 'pesser' else m(x, t)
+        rel = _rel_l2(got, c['out'].to(DEV))
+        good = rel <= 1e-2 and bool(torch.isfinite(got).all())
+        _emit(case=f'{name} forward vs reference golden', rel_l2=rel, gate=1e-2, ok=good)
+        ok &= good
+    return ok
+
+
+ADM256 = dict(image_size=256, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=2,
+              attention_resolutions=[32, 16, 8], dropout=0.0, channel_mult=[1, 1, 2, 2, 4, 4], conv_resample=True,
+              dims=2, num_classes=1000, use_checkpoint=False, use_fp16=False, num_heads=4, num_head_channels=64,
+              num_heads_upsample=-1, use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=False)
+PESSER256 = dict(resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 1, 2, 2, 4, 4], num_res_blocks=2,
+                 attn_resolutions=[16], dropout=0.0, resamp_with_conv=True)
+
+
+def case_adm256():
+    """ADM ImageNet-256 class-conditional UNet (BASELINE configs[4]) at its full width/resolution, B=2: forward vs the
+    fp32 oracle (zero-initialised tensors re-drawn N(0, 0.02)); then 3 DDIM steps (learned-variance channels ignored)."""
+    from models.adm.unet import UNetModel
+    from oracle.adm_ref import FamilyRef, randomize_zero_params
+    _no_tf32()
+    torch.manual_seed(2022)
+    m = UNetModel(**ADM256)
+    m.load_state_dict(randomize_zero_params(m.state_dict()))
+    m = m.to(DEV).eval()
+    ref = FamilyRef('adm', m.state_dict(), ADM256).to(DEV)
+    B = 2
+    g = torch.Generator(device='cpu').manual_seed(2022)
+    x = torch.randn(B, 3, 256, 256, generator=g).to(DEV)
+    t = torch.tensor([996, 120], device=DEV)
+    y = torch.tensor([7, 901], device=DEV)
+    with torch.no_grad():
+        got, want = m(x, t, y), ref(x, t, y)
+    rel = _rel_l2(got, want)
+    ok = rel <= 1e-2 and bool(torch.isfinite(got).all())
+    _emit(case='adm256 forward B=2', rel_l2=rel, gate=1e-2, ok=ok, out_absmax=got.abs().max().item(),
+          params=sum(p.numel() for p in m.parameters()))
+    # a full (respaced) DDIM trajectory, learned-variance channels ignored by DDIM (ddpm.py:185-186)
+    ours = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=20, device=DEV)
+    orc = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=20)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    with torch.no_grad():
+        a = ours.sample(m, x, tqdm_kwargs=dict(disable=True), model_kwargs=dict(y=y))
+        w = orc.sample(ref, x, noises=[torch.zeros_like(x)] * 20, model_kwargs=dict(y=y))
+    psnr = _psnr(a.clamp(-1, 1), w.clamp(-1, 1))
+    _emit(case='adm256 DDIM-20 final sample vs oracle', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+    return ok and psnr >= 40.0
+
+
+def case_pesser256():
+    """pesser CelebA-HQ 256 UNet (BASELINE configs[3]) at full size, B=2: forward vs the fp32 oracle."""
+    from models.pesser.model import Model
+    from oracle.adm_ref import FamilyRef
+    _no_tf32()
+    torch.manual_seed(2022)
+    m = Model(**PESSER256).to(DEV).eval()
+    ref = FamilyRef('pesser', m.state_dict(), PESSER256).to(DEV)
+    B = 2
+    g = torch.Generator(device='cpu').manual_seed(2022)
+    x = torch.randn(B, 3, 256, 256, generator=g).to(DEV)
+    t = torch.tensor([990, 120], device=DEV)
+    with torch.no_grad():
+        got, want = m(x, t), ref(x, t)
+    rel = _rel_l2(got, want)
+    ok = rel <= 1e-2 and bool(torch.isfinite(got).all())
+    _emit(case='pesser256 forward B=2', rel_l2=rel, gate=1e-2, ok=ok, out_absmax=got.abs().max().item(),
+          params=sum(p.numel() for p in m.parameters()))
+    ours = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=20, device=DEV)
+    orc = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=20)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    with torch.no_grad():
+        a = ours.sample(m, x, tqdm_kwargs=dict(disable=True))
+        w = orc.sample(ref, x, noises=[torch.zeros_like(x)] * 20)
+    psnr = _psnr(a.clamp(-1, 1), w.clamp(-1, 1))
+    _emit(case='pesser256 DDIM-20 final sample vs oracle', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+    return ok and psnr >= 40.0
+
+
 def case_timing():
     """Orientation numbers (not the bench): forward and DDIM-50 at B=256."""
     m, _ = _build(CIFAR)

@@ -426,6 +426,9 @@ def case_attention():
     ok &= _attn_case('attention T=256 h=2 d=128', 2, 256, 2, 128)
     ok &= _attn_case('attention T=1024 h=8 d=64 (ADM 32x32, KV loop)', 2, 1024, 8, 64)
     ok &= _attn_case('attention T=576 h=2 d=64 (ragged last KV tile)', 2, 576, 2, 64)
+    ok &= _attn_case('attention T=256 h=1 d=512 (pesser 16x16, wide head)', 3, 256, 1, 512)
+    ok &= _attn_case('attention T=64 h=1 d=512 (pesser 8x8)', 2, 64, 1, 512)
+    ok &= _attn_case('attention T=144 h=2 d=320 (wide, ragged)', 2, 144, 2, 320)
     return ok
 
 

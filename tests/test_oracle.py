@@ -135,3 +135,61 @@ def test_sampling_runs_match_reference(gold):
                 orcc, g['x0'], 3.0, dict(y=g['y']), dict(y=None), noises=g['noises']):
             pass
         assert torch.allclose(out['sample'], g['runs']['ddim10_cfg3'], rtol=0, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# ADM / pesser families (oracle/adm_ref.py, fixtures from oracle/gen_golden_families.py)
+# ------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def fam(golden_dir):
+    return torch.load(os.path.join(golden_dir, 'family_forward.pt'), weights_only=False)
+
+
+def _family_product(c):
+    from models.adm.unet import UNetModel
+    from models.adm.unet_combined import UNetCombined
+    from models.pesser.model import Model
+    from oracle.adm_ref import randomize_zero_params
+    torch.manual_seed(c['seed'])
+    if c['family'] == 'pesser':
+        return Model(**c['cfg'])
+    m = (UNetCombined if c['family'] == 'adm_combined' else UNetModel)(**c['cfg'])
+    m.load_state_dict(randomize_zero_params(m.state_dict()))
+    return m
+
+
+@pytest.mark.parametrize('name', ['adm_tiny_cond', 'adm_tiny_plain', 'adm_combined_cond', 'adm_combined_uncond',
+                                  'pesser_tiny'])
+def test_family_forward_matches_reference(fam, name):
+    """The PRODUCT module has the reference's state_dict keys, shapes, registration order and seeded initial values,
+    and the oracle evaluated on that state_dict reproduces the reference's output."""
+    from oracle.adm_ref import FamilyRef
+    c = fam[name]
+    m = _family_product(c)
+    sd = m.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == c['keys']
+    if 'param_sum' in c:
+        assert float(sum(p.double().sum() for p in m.parameters())) == pytest.approx(c['param_sum'], rel=1e-12)
+    if c['family'] == 'adm_combined':
+        sub = 'unet_uncond.' if c['y'] is None else 'unet_cond.'
+        sd = {k[len(sub):]: v for k, v in sd.items() if k.startswith(sub)}
+        orc = FamilyRef('adm', sd, dict(c['cfg'], num_classes=None if c['y'] is None else c['cfg']['num_classes']))
+    else:
+        orc = FamilyRef(c['family'], sd, c['cfg'])
+    assert torch.allclose(orc(c['x'], c['t'], c['y']), c['out'], rtol=0, atol=1e-5)
+
+
+def test_adm_conditioning_contract():
+    """models/adm/unet.py:662-664: y must be given iff the model is class-conditional (AssertionError)."""
+    from models.adm.unet import UNetModel
+    m = UNetModel(image_size=32, in_channels=3, model_channels=64, out_channels=3, num_res_blocks=1,
+                  attention_resolutions=[2], channel_mult=[1, 2], num_classes=10, num_head_channels=64)
+    x, t = torch.zeros(1, 3, 32, 32), torch.zeros(1, dtype=torch.long)
+    with pytest.raises(AssertionError):
+        m(x, t)
+    m2 = UNetModel(image_size=32, in_channels=3, model_channels=64, out_channels=3, num_res_blocks=1,
+                   attention_resolutions=[2], channel_mult=[1, 2], num_head_channels=64)
+    with pytest.raises(AssertionError):
+        m2(x, t, torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError):      # CPU tensors: no fallback
+        m2.eval()(x, t)

@@ -48,6 +48,26 @@ class SamplerDesc(Structure):
     ]
 
 
+class GemmOperand(Structure):
+    _fields_ = [('ptr', c_void_p), ('rows', c_int), ('ld', c_int), ('batch_stride', c_longlong),
+                ('col_base', c_int), ('col_head', c_int), ('mn_major', c_int), ('per_head_batch', c_int)]
+
+
+class GemmDesc(Structure):
+    _fields_ = [('a', GemmOperand), ('b', GemmOperand), ('M', c_int), ('N', c_int), ('K', c_int),
+                ('batch', c_int), ('heads', c_int), ('out', c_void_p), ('out_bf16', c_int), ('out_ld', c_int),
+                ('out_batch_stride', c_longlong), ('out_head_stride', c_longlong), ('accumulate', c_int),
+                ('split_k', c_int), ('alpha', c_float)]
+
+
+class WgradDesc(Structure):
+    _fields_ = [('dy', c_void_p), ('dy_C', c_int),
+                ('x', c_void_p), ('x_C', c_int), ('x_H', c_int), ('x_W', c_int), ('x_planes', c_int), ('x_c0', c_int),
+                ('B', c_int), ('Ho', c_int), ('Wo', c_int), ('Cout', c_int), ('Cin', c_int), ('ntaps', c_int),
+                ('taps', c_int8 * 36), ('dw', c_void_p), ('dw_co_stride', c_longlong), ('dw_ci_stride', c_longlong),
+                ('dw_tap_stride', c_longlong)]
+
+
 _lib = None
 
 
@@ -82,7 +102,9 @@ def lib():
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
     L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
-    for name in ('b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd',
+    L.b200_gemm_batched.argtypes = [POINTER(GemmDesc), c_void_p]
+    L.b200_conv2d_wgrad.argtypes = [POINTER(WgradDesc), c_void_p]
+    for name in ('b200_gemm_batched', 'b200_conv2d_wgrad', 'b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd',
                  'b200_cast_bf16',
                  'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd', 'b200_time_embed',
                  'b200_sampler_step', 'b200_diffuse'):
@@ -94,7 +116,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
-    'b200_time_embed', 'b200_sampler_step', 'b200_diffuse',
+    'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
 )
 
 
@@ -393,3 +415,55 @@ def diffuse(x0, eps, t, alphas_cumprod, out):
     _check(lib().b200_diffuse(x0.data_ptr(), eps.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
                               x0.shape[0], x0[0].numel(), _stream()), 'diffuse')
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# backward-pass kernels
+# --------------------------------------------------------------------------------------------------
+def _operand(t, rows, ld, *, col_base=0, col_head=0, mn_major=False, per_head_batch=False, batch_stride=0):
+    o = GemmOperand()
+    o.ptr, o.rows, o.ld, o.batch_stride = t.data_ptr(), rows, ld, batch_stride
+    o.col_base, o.col_head, o.mn_major, o.per_head_batch = col_base, col_head, int(mn_major), int(per_head_batch)
+    return o
+
+
+def gemm_batched(a, b, out, M, N, Kdim, *, batch=1, heads=1, out_ld=None, out_batch_stride=0, out_head_stride=0,
+                 accumulate=False, split_k=1, alpha=1.0):
+    """a, b: (tensor, rows, ld, kwargs of _operand).  out: fp32 or bf16 tensor."""
+    d = GemmDesc()
+    d.a = _operand(a[0], a[1], a[2], **(a[3] if len(a) > 3 else {}))
+    d.b = _operand(b[0], b[1], b[2], **(b[3] if len(b) > 3 else {}))
+    _need_cuda(a[0], b[0], out)
+    d.M, d.N, d.K, d.batch, d.heads = M, N, Kdim, batch, heads
+    d.out, d.out_bf16 = out.data_ptr(), int(out.dtype == torch.bfloat16)
+    d.out_ld = out_ld if out_ld is not None else N
+    d.out_batch_stride, d.out_head_stride = out_batch_stride, out_head_stride
+    d.accumulate, d.split_k, d.alpha = int(accumulate), split_k, float(alpha)
+    _launch('gemm_batched', lambda: _check(lib().b200_gemm_batched(ctypes.byref(d), _stream()), 'gemm_batched'),
+            flops=2.0 * batch * heads * M * N * Kdim)
+    return out
+
+
+def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0, co_stride=None, ci_stride=None,
+                 tap_stride=1):
+    """Accumulates the weight gradient into `dw` (fp32; default strides = an OIHW tensor [Cout][Cin][ntaps]).
+    x_geom = (C, H, W, planes) of the bf16 tensor the forward conv read, taps = its tap table (one phase)."""
+    _need_cuda(dy, x, dw)
+    d = WgradDesc()
+    d.dy, d.dy_C = dy.data_ptr(), dy_C
+    d.x = x.data_ptr()
+    d.x_C, d.x_H, d.x_W, d.x_planes = x_geom
+    d.x_c0 = x_c0
+    d.B, d.Ho, d.Wo, d.Cout, d.Cin, d.ntaps = B, Ho, Wo, Cout, Cin, len(taps)
+    flat = [0] * 36
+    for k, (dwx, dhy, pl) in enumerate(taps):
+        flat[4 * k], flat[4 * k + 1], flat[4 * k + 2] = dwx, dhy, pl
+    d.taps = (c_int8 * 36)(*flat)
+    d.dw = dw.data_ptr()
+    nt = len(taps)
+    d.dw_co_stride = co_stride if co_stride is not None else Cin * nt
+    d.dw_ci_stride = ci_stride if ci_stride is not None else nt
+    d.dw_tap_stride = tap_stride
+    _launch('conv_wgrad', lambda: _check(lib().b200_conv2d_wgrad(ctypes.byref(d), _stream()), 'conv2d_wgrad'),
+            flops=2.0 * B * Ho * Wo * Cout * Cin * nt)
+    return dw

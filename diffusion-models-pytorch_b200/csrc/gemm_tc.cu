@@ -1,0 +1,371 @@
+// Generic tcgen05 GEMM with selectable operand majorness, used by the backward pass:
+//   * weight gradients of the convolutions (b200_conv2d_wgrad): dW[co][tap][ci] = sum over pixels of
+//     dY[pixel][co] * X[pixel + tap][ci].  The contraction runs over PIXELS, which are the slow dimension of the
+//     NHWC tensors, so both operands are fed to the tensor core "MN-major" (UMMA a_major = b_major = 1): a TMA box
+//     of (64 channels, 64 pixels) lands in shared memory as [pixel][128 B] and is consumed without any transpose.
+//     The tap shift and the zero padding are, as in the forward kernel, the TMA box origin and its out-of-bounds fill.
+//   * the batched matrix products of the attention backward and of the embedding-projection backward
+//     (b200_gemm_batched), in all four major combinations (A K-major / MN-major x B K-major / MN-major).
+// Tile: 128 (M) x BN <= 256 (N) fp32 accumulators in TMEM, K-blocks of 64, 4-stage TMA ring, split-K with fp32
+// atomics.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (one TMEM lane quarter each).
+#include "common.cuh"
+#include <string.h>
+#include "../../include/b200diff.h"
+
+namespace b200 {
+extern long long g_launch_count;
+int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh, int bn);
+
+struct GemmOperandK {
+  int mn_major;        // 0: K contiguous, 1: M/N contiguous
+  int c_base, c_head;  // inner-dimension (column) origin: c_base + (g % heads) * c_head
+  int b_mul, h_mul;    // batch coordinate = (g / heads) * b_mul + (g % heads) * h_mul
+};
+
+struct GemmKParams {
+  GemmOperandK a, b;
+  int conv;                          // 1: K-blocks are pixel tiles of a convolution (wgrad)
+  int BN;                            // N tile
+  int m_tiles, n_tiles, groups, heads, ksplit, kblocks;
+  int M, N;                          // valid extents (masking in the epilogue)
+  // conv mode: pixel tile = bw x bh x bn = 64 pixels, g = tap
+  int bw, bh, bn, tiles_w, tiles_h;
+  int8_t taps[9][4];                 // {dw, dh, plane, 0} of the B operand (the activation)
+  // epilogue
+  void* out;
+  int out_bf16, atomic;
+  long long s_batch, s_head, s_m, s_n;
+  float alpha;
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kGemmStages = 4;
+
+struct __align__(8) GemmBars {
+  uint64_t full[kGemmStages], empty[kGemmStages], acc_full;
+  uint32_t tmem_base;
+};
+
+// MN-major operand tile, 128-byte swizzle: 64-element (128 B) chunks of the M/N dimension, each chunk a
+// [64 k-rows][128 B] slab; slabs `lbo` bytes apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int b_bytes = p.BN * 128;
+  const int stage_bytes = 16384 + b_bytes;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)kGemmStages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x = ((g * ksplit + ks) * m_tiles + mt) * n_tiles + nt
+  int idx = blockIdx.x;
+  const int nt = idx % p.n_tiles; idx /= p.n_tiles;
+  const int mt = idx % p.m_tiles; idx /= p.m_tiles;
+  const int ks = idx % p.ksplit;
+  const int g = idx / p.ksplit;
+  const int gb = g / p.heads, gh = g - gb * p.heads;
+  const int per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  const int kb0 = ks * per;
+  const int kb1 = min(p.kblocks, kb0 + per);
+  const int nkb = kb1 - kb0;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_base;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int m0 = mt * 128, n0 = nt * p.BN;
+        const int ca = p.a.c_base + gh * p.a.c_head, cb = p.b.c_base + gh * p.b.c_head;
+        const int ba = gb * p.a.b_mul + gh * p.a.h_mul, bb = gb * p.b.b_mul + gh * p.b.h_mul;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + 16384;
+          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+          if (p.conv) {
+            // K-block = pixel tile (tw, th, tn); A = dY (unshifted), B = activation shifted by the tap g
+            const int tw = kb % p.tiles_w;
+            const int th = (kb / p.tiles_w) % p.tiles_h;
+            const int tn = kb / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * p.bw, h0 = th * p.bh, i0 = tn * p.bn;
+            for (int c = 0; c < 2; ++c)
+              tma_load_5d(sA + c * 8192, &mapA, &bars->full[stage], ca + m0 + c * 64, w0, h0, 0, i0);
+            for (int c = 0; c < p.BN / 64; ++c)
+              tma_load_5d(sB + c * 8192, &mapB, &bars->full[stage], cb + n0 + c * 64, w0 + p.taps[g][0],
+                          h0 + p.taps[g][1], p.taps[g][2], i0);
+          } else {
+            const int k0 = kb * 64;
+            if (p.a.mn_major) {
+              for (int c = 0; c < 2; ++c)
+                tma_load_5d(sA + c * 8192, &mapA, &bars->full[stage], ca + m0 + c * 64, k0, 0, 0, ba);
+            } else {
+              tma_load_5d(sA, &mapA, &bars->full[stage], ca + k0, m0, 0, 0, ba);
+            }
+            if (p.b.mn_major) {
+              for (int c = 0; c < p.BN / 64; ++c)
+                tma_load_5d(sB + c * 8192, &mapB, &bars->full[stage], cb + n0 + c * 64, k0, 0, 0, bb);
+            } else {
+              tma_load_5d(sB, &mapB, &bars->full[stage], cb + k0, n0, 0, 0, bb);
+            }
+          }
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.BN);
+        if (p.a.mn_major) idesc |= 1u << 15;
+        if (p.b.mn_major) idesc |= 1u << 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 16384;
+          const uint64_t adesc = p.a.mn_major ? umma_desc_mnmajor_sw128(a_addr, 8192) : umma_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = p.b.mn_major ? umma_desc_mnmajor_sw128(b_addr, 8192) : umma_desc_kmajor_sw128(b_addr);
+          // 16 k per instruction: K-major advances 32 B inside the swizzle row, MN-major advances 16 rows = 2048 B
+          const uint64_t astep = p.a.mn_major ? 128u : 2u;
+          const uint64_t bstep = p.b.mn_major ? 128u : 2u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_d, adesc + astep * (uint64_t)k, bdesc + bstep * (uint64_t)k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&bars->empty[stage]);
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->acc_full);
+      }
+    } else {
+      // ================================ epilogue ================================
+      const int q = warp & 3;
+      const int m = mt * 128 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      mbar_wait(&bars->acc_full, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+      const long long base = (long long)gb * p.s_batch + (long long)gh * p.s_head + (long long)m * p.s_m;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int n0 = nt * p.BN + c0;
+        if (!m_ok || n0 >= p.N) continue;
+        if (p.out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base + (long long)n0 * p.s_n;
+          if (p.s_n == 1 && n0 + 32 <= p.N && (((uintptr_t)o) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * p.alpha, __uint_as_float(v[8 * i + 1]) * p.alpha);
+              u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * p.alpha, __uint_as_float(v[8 * i + 3]) * p.alpha);
+              u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * p.alpha, __uint_as_float(v[8 * i + 5]) * p.alpha);
+              u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * p.alpha, __uint_as_float(v[8 * i + 7]) * p.alpha);
+              reinterpret_cast<uint4*>(o)[i] = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[(long long)j * p.s_n] = __float2bfloat16_rn(__uint_as_float(v[j]) * p.alpha);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + base + (long long)n0 * p.s_n;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) atomicAdd(o + (long long)j * p.s_n, __uint_as_float(v[j]) * p.alpha);
+          } else if (p.s_n == 1 && n0 + 32 <= p.N && (((uintptr_t)o) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(o)[i] =
+                  make_float4(__uint_as_float(v[4 * i]) * p.alpha, __uint_as_float(v[4 * i + 1]) * p.alpha,
+                              __uint_as_float(v[4 * i + 2]) * p.alpha, __uint_as_float(v[4 * i + 3]) * p.alpha);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[(long long)j * p.s_n] = __uint_as_float(v[j]) * p.alpha;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& p, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const size_t smem = (size_t)kGemmStages * (16384 + p.BN * 128) + sizeof(GemmBars) + 1024;
+  const long long grid = (long long)p.groups * p.ksplit * p.m_tiles * p.n_tiles;
+  B200_REQUIRE(grid >= 1 && grid < (1ll << 31), "gemm: bad grid %lld", grid);
+  gemm_tc_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(mapA, mapB, p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+static int g_sms = 0;
+static int num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+// 5-D map over a plain [batch][rows][ld] bf16 matrix: dims (ld, rows, 1, 1, batch)
+static int make_matrix_map(CUtensorMap* m, const b200_gemm_operand* o, int batch, int box_rows) {
+  uint64_t dims[5] = {(uint64_t)o->ld, (uint64_t)o->rows, 1, 1, (uint64_t)batch};
+  const uint64_t bs = (uint64_t)(o->batch_stride ? o->batch_stride : (long long)o->rows * o->ld) * 2;
+  uint64_t strides[4] = {(uint64_t)o->ld * 2, bs, bs, bs};
+  uint32_t box[5] = {64, (uint32_t)box_rows, 1, 1, 1};
+  return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, o->ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm_batched(const b200_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(d && d->a.ptr && d->b.ptr && d->out, "gemm_batched: null pointer");
+  B200_REQUIRE(d->M >= 1 && d->N >= 1 && d->K >= 1 && d->batch >= 1 && d->heads >= 1, "gemm_batched: bad sizes");
+  B200_REQUIRE(d->a.ld % 8 == 0 && d->b.ld % 8 == 0, "gemm_batched: leading dimensions must be multiples of 8");
+  B200_REQUIRE(((uintptr_t)d->a.ptr & 127) == 0 && ((uintptr_t)d->b.ptr & 127) == 0, "gemm_batched: operand alignment");
+  B200_REQUIRE((d->a.batch_stride % 8) == 0 && (d->b.batch_stride % 8) == 0, "gemm_batched: batch strides must be multiples of 8");
+  B200_REQUIRE(d->K % 8 == 0, "gemm_batched: K=%d must be a multiple of 8", d->K);
+  // A K tail that is not a multiple of 64 relies on TMA zero fill, which only triggers at the tensor edge: the
+  // contraction window must then end exactly at the operand's last row / column
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.a.mn_major = d->a.mn_major; p.a.c_base = d->a.col_base; p.a.c_head = d->a.col_head;
+  p.b.mn_major = d->b.mn_major; p.b.c_base = d->b.col_base; p.b.c_head = d->b.col_head;
+  p.a.b_mul = d->a.per_head_batch ? d->heads : 1; p.a.h_mul = d->a.per_head_batch ? 1 : 0;
+  p.b.b_mul = d->b.per_head_batch ? d->heads : 1; p.b.h_mul = d->b.per_head_batch ? 1 : 0;
+  if (d->K % 64 != 0) {
+    if (d->a.mn_major) B200_REQUIRE(d->a.rows == d->K, "gemm_batched: ragged K needs A rows == K");
+    else B200_REQUIRE((d->heads == 1 || d->a.col_head == 0) && d->a.col_base + d->K == d->a.ld, "gemm_batched: ragged K needs the A window at the row end");
+    if (d->b.mn_major) B200_REQUIRE(d->b.rows == d->K, "gemm_batched: ragged K needs B rows == K");
+    else B200_REQUIRE((d->heads == 1 || d->b.col_head == 0) && d->b.col_base + d->K == d->b.ld, "gemm_batched: ragged K needs the B window at the row end");
+  }
+  // an MN-major operand is loaded in 64-column chunks: columns past M/N inside the last chunk must either not exist
+  // (tensor edge, zero fill) or be harmless: they only produce rows/columns the epilogue masks.
+  int BN = d->b.mn_major ? ((d->N + 63) / 64) * 64 : ((d->N + 15) / 16) * 16;
+  if (BN > 256) BN = 256;
+  p.BN = BN;
+  p.m_tiles = (d->M + 127) / 128;
+  p.n_tiles = (d->N + BN - 1) / BN;
+  p.groups = d->batch * d->heads;
+  p.heads = d->heads;
+  p.kblocks = (d->K + 63) / 64;
+  p.M = d->M; p.N = d->N;
+  p.out = d->out; p.out_bf16 = d->out_bf16;
+  p.s_batch = d->out_batch_stride; p.s_head = d->out_head_stride; p.s_m = d->out_ld; p.s_n = 1;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  int ksplit = 1;
+  if (d->split_k > 1) {
+    B200_REQUIRE(!d->out_bf16, "gemm_batched: split-K needs an fp32 output");
+    ksplit = d->split_k < p.kblocks ? d->split_k : p.kblocks;
+  }
+  p.ksplit = ksplit;
+  p.atomic = (d->accumulate || ksplit > 1) ? 1 : 0;
+  B200_REQUIRE(!(p.atomic && d->out_bf16), "gemm_batched: accumulate needs an fp32 output");
+  CUtensorMap mapA, mapB;
+  int rc = make_matrix_map(&mapA, &d->a, d->batch * (d->a.per_head_batch ? d->heads : 1), d->a.mn_major ? 64 : 128);
+  if (rc) return rc;
+  rc = make_matrix_map(&mapB, &d->b, d->batch * (d->b.per_head_batch ? d->heads : 1), d->b.mn_major ? 64 : BN);
+  if (rc) return rc;
+  return launch_gemm(mapA, mapB, p, stream);
+}
+
+extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(d && d->dy && d->x && d->dw, "conv2d_wgrad: null pointer");
+  B200_REQUIRE(d->dy_C % 64 == 0 && d->x_C % 64 == 0, "conv2d_wgrad: channel counts (%d, %d) must be multiples of 64", d->dy_C, d->x_C);
+  B200_REQUIRE(d->Cout >= 1 && d->Cout <= d->dy_C && d->Cin >= 1 && d->Cin <= d->x_C, "conv2d_wgrad: bad Cout/Cin");
+  B200_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "conv2d_wgrad: ntaps=%d out of range", d->ntaps);
+  B200_REQUIRE(((uintptr_t)d->dy & 127) == 0 && ((uintptr_t)d->x & 127) == 0, "conv2d_wgrad: operand alignment");
+  int bw = 1;
+  while (bw * 2 <= 64 && d->Wo % (bw * 2) == 0) bw *= 2;
+  int bh = 1;
+  while (bw * bh * 2 <= 64 && d->Ho % (bh * 2) == 0) bh *= 2;
+  const int bn = 64 / (bw * bh);
+  B200_REQUIRE(bn == 1 || (bw == d->Wo && bh == d->Ho), "conv2d_wgrad: unsupported spatial size %dx%d", d->Ho, d->Wo);
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = 1;
+  p.a.mn_major = 1; p.b.mn_major = 1;
+  p.a.c_base = 0; p.b.c_base = d->x_c0;
+  int BN = ((d->Cin + 63) / 64) * 64;
+  if (BN > 256) BN = 256;
+  p.BN = BN;
+  p.m_tiles = (d->Cout + 127) / 128;
+  p.n_tiles = (d->Cin + BN - 1) / BN;
+  p.groups = d->ntaps;
+  p.heads = d->ntaps;      // g = tap: gb = 0, gh = tap
+  p.bw = bw; p.bh = bh; p.bn = bn;
+  p.tiles_w = d->Wo / bw; p.tiles_h = d->Ho / bh;
+  p.kblocks = p.tiles_w * p.tiles_h * ((d->B + bn - 1) / bn);
+  p.M = d->Cout; p.N = d->Cin;
+  memcpy(p.taps, d->taps, sizeof(p.taps));
+  p.out = d->dw; p.out_bf16 = 0;
+  p.s_batch = 0; p.s_head = d->dw_tap_stride; p.s_m = d->dw_co_stride; p.s_n = d->dw_ci_stride;
+  p.alpha = 1.f;
+  // split the pixel range so that the grid fills the machine (~2 waves); every split accumulates with atomics,
+  // which is also what lets repeated backward passes accumulate into an existing .grad
+  const long tiles = (long)p.groups * p.m_tiles * p.n_tiles;
+  long ks = (2L * num_sms() + tiles - 1) / tiles;
+  if (ks > p.kblocks) ks = p.kblocks;
+  if (ks < 1) ks = 1;
+  p.ksplit = (int)ks;
+  p.atomic = 1;
+  CUtensorMap mapA, mapB;
+  int rc = make_a_map(&mapA, d->dy, d->dy_C, d->Ho, d->Wo, 1, d->B, bw, bh, bn);
+  if (rc) return rc;
+  rc = make_a_map(&mapB, d->x, d->x_C, d->x_H, d->x_W, d->x_planes, d->B, bw, bh, bn);
+  if (rc) return rc;
+  return launch_gemm(mapA, mapB, p, stream);
+}

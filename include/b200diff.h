@@ -183,6 +183,63 @@ int b200_sampler_step(const b200_sampler_desc* d, void* stream);
 int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
                  int B, int CHW, void* stream);
 
+/* =============================================================================================
+ * Backward pass (training step: scripts/train_ddpm.py:171-192 -> loss.backward() of diffusions/ddpm.py:122-138).
+ * The reference relies on autograd; each entry point below is the hand-written adjoint of a forward kernel.
+ * ============================================================================================= */
+
+/* Batched GEMM on tcgen05 with selectable operand majorness:
+ *   D_g[M][N] (+)= alpha * sum_k A_g(m, k) * B_g(n, k),   g = (batch b, head h)
+ * An operand is a bf16 matrix [batch][rows][ld]; its window starts at column col_base + h * col_head.
+ *   mn_major = 0: rows index M (resp. N), columns index K   (the "K-major" form, e.g. q, k of softmax(q k^T))
+ *   mn_major = 1: rows index K, columns index M (resp. N)   (contraction over the slow dimension, no transpose pass)
+ * per_head_batch: the operand is stored [batch*heads][rows][ld] (scores / probabilities) instead of with the
+ * heads side by side in its columns.  Used by the attention backward (models/modules.py:92-97 adjoint) and by
+ * the backward of the per-block embedding projections (models/unet.py:18-21,41). */
+typedef struct b200_gemm_operand {
+  const void* ptr;
+  int rows, ld;
+  long long batch_stride;   /* elements; 0 = rows * ld */
+  int col_base, col_head;
+  int mn_major;
+  int per_head_batch;
+} b200_gemm_operand;
+
+typedef struct b200_gemm_desc {
+  b200_gemm_operand a, b;
+  int M, N, K;
+  int batch, heads;
+  void* out;                /* [..][M][out_ld]: element (b, h, m, n) at b*out_batch_stride + h*out_head_stride + m*out_ld + n */
+  int out_bf16;             /* 0: fp32, 1: bf16 */
+  int out_ld;
+  long long out_batch_stride, out_head_stride;
+  int accumulate;           /* fp32 only: D += (atomic adds) instead of D = */
+  int split_k;              /* > 1: split the contraction over this many CTAs (fp32 atomics; D must be pre-zeroed
+                               or hold the value to accumulate into) */
+  float alpha;              /* 0 is read as 1 */
+} b200_gemm_desc;
+
+int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
+
+/* Weight gradient of a convolution executed by b200_conv2d_fwd (adjoint of nn.Conv2d w.r.t. its weight):
+ *   dw[co][ci][tap] += sum over (n, ho, wo) dy[n][ho][wo][co] * x[n][plane_tap][ho + dh_tap][wo + dw_tap][x_c0 + ci]
+ * dy: bf16 NHWC [B][Ho][Wo][dy_C]; x: bf16 [B][x_planes][x_H][x_W][x_C] exactly as the forward read it (same tap
+ * table).  dw is fp32 with arbitrary element strides, so the result lands directly in the reference's OIHW
+ * .grad tensor (dw_co_stride = Cin_total*kh*kw, dw_ci_stride = kh*kw, dw_tap_stride = 1) -- and always ACCUMULATES
+ * (split over pixel ranges with atomics), like autograd's .grad accumulation. */
+typedef struct b200_wgrad_desc {
+  const void* dy; int dy_C;
+  const void* x; int x_C, x_H, x_W, x_planes, x_c0;
+  int B, Ho, Wo;
+  int Cout, Cin;
+  int ntaps;
+  int8_t taps[9][4];        /* {dw, dh, plane, 0} */
+  float* dw;
+  long long dw_co_stride, dw_ci_stride, dw_tap_stride;
+} b200_wgrad_desc;
+
+int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

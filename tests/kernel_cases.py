@@ -433,6 +433,86 @@ def case_attention():
 
 
 # ----------------------------------------------------------------------------------------------------
+# backward-pass GEMMs: batched GEMM in all major combinations, conv weight gradient
+# ----------------------------------------------------------------------------------------------------
+def _gemm_case(name, B, H, M, N, Kd, a_mn, b_mn, out_dtype=torch.float32, split_k=1):
+    """D[b,h] = A[b,h] (M x K) @ B[b,h]^T (N x K), operands stored with the heads side by side in the columns."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    A = _bf16r(_gen(B, H, M, Kd, seed=1))
+    Bm = _bf16r(_gen(B, H, N, Kd, seed=2))
+    ref = torch.einsum('bhmk,bhnk->bhmn', A, Bm)
+    # storage: K-major operand [B][rows = M][H*K]; MN-major operand [B][rows = K][H*M]
+    if a_mn:
+        a_t = A.permute(0, 3, 1, 2).reshape(B, Kd, H * M).to(torch.bfloat16).contiguous()
+        a = (a_t, Kd, H * M, dict(col_head=M, mn_major=True))
+    else:
+        a_t = A.permute(0, 2, 1, 3).reshape(B, M, H * Kd).to(torch.bfloat16).contiguous()
+        a = (a_t, M, H * Kd, dict(col_head=Kd))
+    if b_mn:
+        b_t = Bm.permute(0, 3, 1, 2).reshape(B, Kd, H * N).to(torch.bfloat16).contiguous()
+        b = (b_t, Kd, H * N, dict(col_head=N, mn_major=True))
+    else:
+        b_t = Bm.permute(0, 2, 1, 3).reshape(B, N, H * Kd).to(torch.bfloat16).contiguous()
+        b = (b_t, N, H * Kd, dict(col_head=Kd))
+    out = torch.zeros(B, H, M, N, device=DEV, dtype=out_dtype) if split_k > 1 else \
+        torch.full((B, H, M, N), float('nan'), device=DEV, dtype=out_dtype)
+    K.gemm_batched(a, b, out, M, N, Kd, batch=B, heads=H, out_ld=N, out_batch_stride=H * M * N, out_head_stride=M * N,
+                   split_k=split_k)
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-2, atol=2e-2 * Kd ** 0.5) if out_dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-3)
+    return _report(name, out, ref, **tol)
+
+
+def case_gemm():
+    ok = True
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            tag = f"A {'MN' if a_mn else 'K'}-major, B {'MN' if b_mn else 'K'}-major"
+            ok &= _gemm_case(f'gemm 256x256x256 h=2 ({tag})', 3, 2, 256, 256, 256, a_mn, b_mn)
+            ok &= _gemm_case(f'gemm 128x64x320 h=4 ({tag})', 2, 4, 128, 64, 320, a_mn, b_mn)
+            ok &= _gemm_case(f'gemm ragged 200x192x64 h=1 ({tag})', 2, 1, 200, 192, 64, a_mn, b_mn)
+            ok &= _gemm_case(f'gemm tiny 16x64x128 h=2 bf16 out ({tag})', 2, 2, 16, 64, 128, a_mn, b_mn,
+                             out_dtype=torch.bfloat16)
+    ok &= _gemm_case('gemm split-K 128x256x4096', 1, 1, 128, 256, 4096, True, True, split_k=8)
+    ok &= _gemm_case('gemm ragged K=16 h=1', 4, 1, 16, 64, 16, False, True)
+    return ok
+
+
+def _wgrad_case(name, B, H, W, Cin, Cout, kind):
+    """dW of a conv executed by b200_conv2d_fwd vs autograd of F.conv2d on the bf16-rounded operands."""
+    torch.backends.cudnn.allow_tf32 = False
+    x = _bf16r(_gen(B, Cin, H, W, seed=1))
+    stride, pad, k = (2, 1, 3) if kind == 's2' else (1, 1, 3) if kind == '3x3' else (1, 0, 1)
+    Ho, Wo = H // stride, W // stride
+    dy = _bf16r(_gen(B, Cout, Ho, Wo, seed=2) * 0.1)
+    w = torch.zeros(Cout, Cin, k, k, device=DEV, requires_grad=True)
+    F.conv2d(x, w, None, stride=stride, padding=pad).backward(dy)
+    ref = w.grad
+    dyb = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    xb = x.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros(Cout, Cin, k, k, device=DEV)
+    if kind == 's2':
+        planes = torch.empty(B, 4, H // 2, W // 2, Cin, device=DEV, dtype=torch.bfloat16)
+        K.cast_bf16(xb, planes, B, H, W, Cin, parity_split=True)
+        K.conv2d_wgrad(dyb, Cout, planes, (Cin, H // 2, W // 2, 4), B, Ho, Wo, Cout, Cin, K.taps_3x3_s2(1)[0], dw)
+    else:
+        taps = K.taps_3x3_s1()[0] if kind == '3x3' else K.taps_1x1()[0]
+        K.conv2d_wgrad(dyb, Cout, xb.to(torch.bfloat16), (Cin, H, W, 1), B, Ho, Wo, Cout, Cin, taps, dw)
+    torch.cuda.synchronize()
+    return _report(name, dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
+
+
+def case_wgrad():
+    ok = _wgrad_case('wgrad 3x3 128->128 @32x32 B=4', 4, 32, 32, 128, 128, '3x3')
+    ok &= _wgrad_case('wgrad 3x3 384->256 @16x16 B=3', 3, 16, 16, 384, 256, '3x3')
+    ok &= _wgrad_case('wgrad 3x3 256->256 @4x4 B=6 (stacked images, ragged batch)', 6, 4, 4, 256, 256, '3x3')
+    ok &= _wgrad_case('wgrad 3x3 64->64 @8x8 B=5', 5, 8, 8, 64, 64, '3x3')
+    ok &= _wgrad_case('wgrad 1x1 512->256 @8x8 B=4', 4, 8, 8, 512, 256, '1x1')
+    ok &= _wgrad_case('wgrad 3x3 stride 2 128->128 @32x32 B=2', 2, 32, 32, 128, 128, 's2')
+    return ok
+
+
+# ----------------------------------------------------------------------------------------------------
 # sampler step vs the eager op sequence of the reference (restated in oracle/diffusion_ref.py)
 # ----------------------------------------------------------------------------------------------------
 def case_sampler():

@@ -68,6 +68,23 @@ class WgradDesc(Structure):
                 ('dw_tap_stride', c_longlong)]
 
 
+class GnBwdDesc(Structure):
+    _fields_ = [('g', c_void_p),
+                ('x0', c_void_p), ('C0', c_int), ('stats0', c_void_p),
+                ('x1', c_void_p), ('C1', c_int), ('stats1', c_void_p),
+                ('B', c_int), ('HW', c_int), ('W', c_int), ('groups', c_int),
+                ('gamma', c_void_p), ('beta', c_void_p), ('eps', c_float),
+                ('scale', c_void_p), ('shift', c_void_p), ('ss_ld', c_int),
+                ('apply_silu', c_int), ('resample', c_int),
+                ('drop_p', c_float), ('drop_seed', ctypes.c_ulonglong),
+                ('sums', c_void_p),
+                ('dx0', c_void_p), ('dx0_accumulate', c_int),
+                ('dx1', c_void_p), ('dx1_accumulate', c_int),
+                ('addend', c_void_p), ('dx_bf16', c_void_p), ('dx_rowsum', c_void_p),
+                ('dgamma', c_void_p), ('dbeta', c_void_p),
+                ('dscale', c_void_p), ('dshift', c_void_p), ('dss_ld', c_int)]
+
+
 _lib = None
 
 
@@ -102,6 +119,23 @@ def lib():
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
     L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    ull = ctypes.c_ulonglong
+    L.b200_groupnorm_apply_train_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                                 c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                                 c_int, c_int, c_int, c_float, ull, c_void_p, c_void_p, c_void_p]
+    L.b200_dropout_mask.argtypes = [c_void_p, c_longlong, c_float, ull, c_void_p]
+    L.b200_groupnorm_bwd.argtypes = [POINTER(GnBwdDesc), c_void_p]
+    L.b200_cast_bf16_colsum.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+    L.b200_nchw_to_nhwc_pad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_colsum_bf16.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]
+    L.b200_resample_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]
+    L.b200_upsample2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_softmax_rows.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
+    L.b200_softmax_bwd_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
+    L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
+    L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
+    for name in BACKWARD_SYMBOLS:
+        getattr(L, name).restype = c_int
     L.b200_gemm_batched.argtypes = [POINTER(GemmDesc), c_void_p]
     L.b200_conv2d_wgrad.argtypes = [POINTER(WgradDesc), c_void_p]
     for name in ('b200_gemm_batched', 'b200_conv2d_wgrad', 'b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd',
@@ -113,7 +147,13 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = (
+BACKWARD_SYMBOLS = (
+    'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
+    'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
+    'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad',
+)
+
+EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
@@ -339,16 +379,15 @@ def _gn_bytes(B, HW, C, resample, raw):
 
 
 def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None,
-                    shift=None, ss_ld=0, silu=True, resample=0, raw_out=None):
-    """Streaming GroupNorm(+SiLU) for inputs whose [B][C][2] statistics came from the producing kernel."""
+                    shift=None, ss_ld=0, silu=True, resample=0, raw_out=None, drop_p=0.0, drop_seed=0):
+    """Streaming GroupNorm(+SiLU)(+dropout) for inputs whose [B][C][2] statistics came from the producing kernel."""
     _need_cuda(x0, stats0, out)
     _launch('groupnorm_apply',
-            lambda: _check(lib().b200_groupnorm_apply_fwd(x0.data_ptr(), int(x0.dtype == torch.bfloat16), C0,
-                                                          stats0.data_ptr(), _ptr(x1), C1,
-                                                          _ptr(stats1), B, HW, W, groups, _ptr(gamma), _ptr(beta),
-                                                          float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu),
-                                                          resample, out.data_ptr(), _ptr(raw_out), _stream()),
-                           'groupnorm_apply_fwd'),
+            lambda: _check(lib().b200_groupnorm_apply_train_fwd(
+                x0.data_ptr(), int(x0.dtype == torch.bfloat16), C0, stats0.data_ptr(), _ptr(x1), C1, _ptr(stats1), B,
+                HW, W, groups, _ptr(gamma), _ptr(beta), float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu),
+                resample, float(drop_p), int(drop_seed), out.data_ptr(), _ptr(raw_out), _stream()),
+                'groupnorm_apply_fwd'),
             nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None) -
             (2.0 * B * HW * C0 if x0.dtype == torch.bfloat16 else 0.0))
     return out
@@ -467,3 +506,77 @@ def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0,
     _launch('conv_wgrad', lambda: _check(lib().b200_conv2d_wgrad(ctypes.byref(d), _stream()), 'conv2d_wgrad'),
             flops=2.0 * B * Ho * Wo * Cout * Cin * nt)
     return dw
+
+
+def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, sums, *, scale=None,
+                  shift=None, ss_ld=0, silu=True, resample=0, drop_p=0.0, drop_seed=0, dx0=None, dx0_acc=False,
+                  dx1=None, dx1_acc=False, addend=None, dx_bf16=None, dx_rowsum=None, dgamma=None, dbeta=None,
+                  dscale=None, dshift=None, dss_ld=0):
+    _need_cuda(g, x0, stats0, sums)
+    d = GnBwdDesc()
+    d.g, d.x0, d.C0, d.stats0 = g.data_ptr(), x0.data_ptr(), C0, stats0.data_ptr()
+    d.x1, d.C1, d.stats1 = _ptr(x1), (C1 if x1 is not None else 0), _ptr(stats1)
+    d.B, d.HW, d.W, d.groups = B, HW, W, groups
+    d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), float(eps)
+    d.scale, d.shift, d.ss_ld = _ptr(scale), _ptr(shift), ss_ld
+    d.apply_silu, d.resample, d.drop_p, d.drop_seed = int(silu), resample, float(drop_p), int(drop_seed)
+    d.sums = sums.data_ptr()
+    d.dx0, d.dx0_accumulate, d.dx1, d.dx1_accumulate = _ptr(dx0), int(dx0_acc), _ptr(dx1), int(dx1_acc)
+    d.addend, d.dx_bf16, d.dx_rowsum = _ptr(addend), _ptr(dx_bf16), _ptr(dx_rowsum)
+    d.dgamma, d.dbeta, d.dscale, d.dshift, d.dss_ld = _ptr(dgamma), _ptr(dbeta), _ptr(dscale), _ptr(dshift), dss_ld
+    C = C0 + (C1 if x1 is not None else 0)
+    _launch('groupnorm_bwd', lambda: _check(lib().b200_groupnorm_bwd(ctypes.byref(d), _stream()), 'groupnorm_bwd'),
+            nbytes=float(B) * HW * C * (12.0 + (2.0 if dx_bf16 is not None else 4.0)))
+
+
+def dropout_mask(out, p, seed):
+    _check(lib().b200_dropout_mask(out.data_ptr(), out.numel(), float(p), int(seed), _stream()), 'dropout_mask')
+    return out
+
+
+def cast_bf16_colsum(x, out, colsum, rows, C):
+    _launch('grad_cast', lambda: _check(lib().b200_cast_bf16_colsum(x.data_ptr(), out.data_ptr(), _ptr(colsum), rows, C,
+                                                                    _stream()), 'cast_bf16_colsum'),
+            nbytes=6.0 * rows * C)
+    return out
+
+
+def nchw_to_nhwc_pad_bf16(x, out, colsum, B, C, HW, Cpad):
+    _check(lib().b200_nchw_to_nhwc_pad_bf16(x.data_ptr(), out.data_ptr(), _ptr(colsum), B, C, HW, Cpad, _stream()),
+           'nchw_to_nhwc_pad_bf16')
+    return out
+
+
+def colsum_bf16(x, colsum, rows, ld, c0, C):
+    _check(lib().b200_colsum_bf16(x.data_ptr(), colsum.data_ptr(), rows, ld, c0, C, _stream()), 'colsum_bf16')
+
+
+def resample_f32(x, out, B, H, W, C, mode, scale=1.0, accumulate=False):
+    _check(lib().b200_resample_f32(x.data_ptr(), out.data_ptr(), B, H, W, C, mode, float(scale), int(accumulate),
+                                   _stream()), 'resample_f32')
+    return out
+
+
+def upsample2_bf16(x, out, B, H, W, C):
+    _check(lib().b200_upsample2_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream()), 'upsample2_bf16')
+    return out
+
+
+def softmax_rows(S, P, rows, T, scale):
+    _check(lib().b200_softmax_rows(S.data_ptr(), P.data_ptr(), rows, T, float(scale), _stream()), 'softmax_rows')
+
+
+def softmax_bwd_rows(P, dP, dS, rows, T, scale):
+    _check(lib().b200_softmax_bwd_rows(P.data_ptr(), dP.data_ptr(), dS.data_ptr(), rows, T, float(scale), _stream()),
+           'softmax_bwd_rows')
+
+
+def mse_loss(a, b, loss):
+    _check(lib().b200_mse_loss(a.data_ptr(), b.data_ptr(), loss.data_ptr(), a.numel(), _stream()), 'mse_loss')
+    return loss
+
+
+def mse_loss_grad(a, b, grad_scale, da):
+    _check(lib().b200_mse_loss_grad(a.data_ptr(), b.data_ptr(), _ptr(grad_scale), da.data_ptr(), a.numel(), _stream()),
+           'mse_loss_grad')
+    return da

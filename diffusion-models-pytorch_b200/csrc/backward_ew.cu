@@ -1,0 +1,662 @@
+// Memory-bound kernels of the backward pass (training step, scripts/train_ddpm.py:171-192): the adjoint of
+// GroupNorm(+AdaGN)(+SiLU)(+dropout)(+2x resample) as two streaming passes, gradient casts with fused bias-gradient
+// column sums, resampling adjoints, the row softmax of the unfused attention backward and the MSE loss.
+// Everything is fp32 arithmetic on NHWC tensors; tensor-core operands of the following GEMMs are emitted as bf16.
+#include "common.cuh"
+#include <string.h>
+#include "../../include/b200diff.h"
+
+namespace b200 {
+extern long long g_launch_count;
+
+__device__ __forceinline__ float4 bw_ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 bw_ldg4_bf16(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 r;
+  r.x = __uint_as_float(u.x << 16); r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16); r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * x));
+  return fmaf(0.5f, th, 0.5f);
+}
+// d/dz [z * sigmoid(z)]
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = sigmoid_tanh(z);
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
+
+// ================================================================================================
+// GroupNorm backward.  Forward (groupnorm.cu): y = resample(drop(act(xh * g' + b'))), xh = (x - mean) * rstd,
+// g' = gamma (1 + scale_n), b' = beta (1 + scale_n) + shift_n.  With dz = dL/dz (z = xh g' + b'):
+//   S1[n,c] = sum_p dz, S2[n,c] = sum_p dz * xh                                   (pass 1, "reduce")
+//   dx = rstd * (g' dz - mean_group(g' S1) - xh * mean_group(g' S2))               (pass 2, "apply")
+//   dgamma_c = sum_n S2 (1 + scale), dbeta_c = sum_n S1 (1 + scale), dscale[n,c] = gamma S2 + beta S1, dshift = S1.
+// Both passes stream x (fp32) and g (bf16) once: 6 B + 6 B read, 2-4 B written per element.
+// ================================================================================================
+struct GnBwdParams {
+  const __nv_bfloat16* g;
+  const float* x0; int C0; const float* st0;
+  const float* x1; int C1; const float* st1;
+  int HW, W, groups, cpg, pix_per_cta;
+  const float* gamma; const float* beta; float eps;
+  const float* scale; const float* shift; int ss_ld;
+  int apply_silu, resample;
+  uint32_t drop_thresh; float drop_scale; unsigned long long drop_seed;
+  float* sums;
+  float* dx0; int acc0; float* dx1; int acc1; const float* addend;
+  __nv_bfloat16* dx_bf16; float* dx_rowsum;
+  float* dgamma; float* dbeta; float* dscale; float* dshift; int dss_ld;
+};
+
+// per-channel forward coefficients: z = x*cA + cB, xh = x*rA + rB   (smem arrays of C floats each)
+__device__ __forceinline__ void gn_bwd_coefs(const GnBwdParams& p, int n, float* cA, float* cB, float* rA, float* rB,
+                                             float* tmpS, float* tmpQ) {
+  const int C = p.C0 + p.C1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+    tmpS[c] = __ldg(st);
+    tmpQ[c] = __ldg(st + 1);
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / p.cpg) * p.cpg;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < p.cpg; ++i) { s += tmpS[g0 + i]; q += tmpQ[g0 + i]; }
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    float ga = p.gamma ? __ldg(p.gamma + c) : 1.f;
+    float be = p.beta ? __ldg(p.beta + c) : 0.f;
+    if (p.scale) {
+      const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c);
+      ga *= sc;
+      be = be * sc + __ldg(p.shift + (size_t)n * p.ss_ld + c);
+    }
+    cA[c] = rstd * ga;
+    cB[c] = be - mean * rstd * ga;
+    rA[c] = rstd;
+    rB[c] = -mean * rstd;
+  }
+  __syncthreads();
+}
+
+// gradient w.r.t. the activated output at input pixel px (adjoint of the forward's resampling), 4 channels
+__device__ __forceinline__ float4 gn_bwd_load_g(const GnBwdParams& p, int n, int px, int C, int c) {
+  if (p.resample == 0) return bw_ldg4_bf16(p.g + ((size_t)n * p.HW + px) * C + c);
+  const int py = px / p.W, pxx = px - py * p.W;
+  if (p.resample == 1) {   // forward averaged 2x2 blocks: every input pixel receives a quarter of its block's gradient
+    const int Wo = p.W >> 1;
+    float4 v = bw_ldg4_bf16(p.g + ((size_t)n * (p.HW >> 2) + (size_t)(py >> 1) * Wo + (pxx >> 1)) * C + c);
+    v.x *= 0.25f; v.y *= 0.25f; v.z *= 0.25f; v.w *= 0.25f;
+    return v;
+  }
+  const int Wo = p.W * 2;   // forward replicated the pixel 2x2: sum the four gradients
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float4 v = bw_ldg4_bf16(p.g + ((size_t)n * (4 * (size_t)p.HW) + (size_t)(2 * py + dy) * Wo + 2 * pxx + dx) * C + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  return a;
+}
+
+__device__ __forceinline__ float4 gn_bwd_load_x(const GnBwdParams& p, int n, int px, int c) {
+  return (c < p.C0) ? bw_ldg4(p.x0 + ((size_t)n * p.HW + px) * p.C0 + c)
+                    : bw_ldg4(p.x1 + ((size_t)n * p.HW + px) * p.C1 + (c - p.C0));
+}
+
+// dz for 4 channels of one pixel; also returns xh
+__device__ __forceinline__ void gn_bwd_dz(const GnBwdParams& p, int n, int px, int C, int c, const float4 x, const float4 g,
+                                          const float4 a, const float4 b, const float4 ra, const float4 rb, float (&dz)[4],
+                                          float (&xh)[4]) {
+  const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g.x, g.y, g.z, g.w};
+  const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  const float rav[4] = {ra.x, ra.y, ra.z, ra.w}, rbv[4] = {rb.x, rb.y, rb.z, rb.w};
+  const unsigned long long e = ((unsigned long long)n * p.HW + px) * C + c;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xh[i] = fmaf(xv[i], rav[i], rbv[i]);
+    float d = gv[i];
+    if (p.apply_silu) d *= silu_grad(fmaf(xv[i], av[i], bv[i]));
+    if (p.drop_thresh) d = dropout_keep(p.drop_seed, e + i, p.drop_thresh) ? d * p.drop_scale : 0.f;
+    dz[i] = d;
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  extern __shared__ float bsm[];
+  const int C = p.C0 + p.C1;
+  float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
+  float* accS = bsm + 4 * C; float* accQ = bsm + 5 * C;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  gn_bwd_coefs(p, n, cA, cB, rA, rB, accS, accQ);
+  for (int c = tid; c < C; c += 256) { accS[c] = 0.f; accQ[c] = 0.f; }
+  __syncthreads();
+  const int nv = C >> 2;
+  const int cols = nv < 256 ? nv : 256;
+  const int pstep = 256 / cols;
+  const int px0 = blockIdx.x * p.pix_per_cta;
+  const int px1 = min(p.HW, px0 + p.pix_per_cta);
+  for (int j0 = 0; j0 < nv; j0 += cols) {
+    const int j = j0 + tid % cols, prow = tid / cols;
+    if (prow >= pstep || j >= nv) continue;
+    const int c = j << 2;
+    const float4 a = *reinterpret_cast<const float4*>(cA + c), b = *reinterpret_cast<const float4*>(cB + c);
+    const float4 ra = *reinterpret_cast<const float4*>(rA + c), rb = *reinterpret_cast<const float4*>(rB + c);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int px = px0 + prow; px < px1; px += pstep) {
+      const float4 x = gn_bwd_load_x(p, n, px, c);
+      const float4 g = gn_bwd_load_g(p, n, px, C, c);
+      float dz[4], xh[4];
+      gn_bwd_dz(p, n, px, C, c, x, g, a, b, ra, rb, dz, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (pstep > 1) { atomicAdd(accS + c + i, s1[i]); atomicAdd(accQ + c + i, s2[i]); }
+      else { accS[c + i] = s1[i]; accQ[c + i] = s2[i]; }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    atomicAdd(p.sums + ((size_t)n * C + c) * 2, accS[c]);
+    atomicAdd(p.sums + ((size_t)n * C + c) * 2 + 1, accQ[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) {
+  extern __shared__ float bsm[];
+  const int C = p.C0 + p.C1;
+  float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
+  float* k2 = bsm + 4 * C; float* k3 = bsm + 5 * C;   // dx = dz*cA(=rstd g') - k2 - xh*k3
+  float* rsum = bsm + 6 * C;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  gn_bwd_coefs(p, n, cA, cB, rA, rB, k2, k3);
+  // k2/k3 currently hold scratch; load the channel sums S1, S2 into them, then turn them into group terms
+  for (int c = tid; c < C; c += 256) {
+    k2[c] = __ldg(p.sums + ((size_t)n * C + c) * 2);
+    k3[c] = __ldg(p.sums + ((size_t)n * C + c) * 2 + 1);
+    rsum[c] = 0.f;
+  }
+  __syncthreads();
+  const float inv_m = 1.0f / (float)(p.HW * p.cpg);
+  float t2[8], t3[8];   // up to 8 channels per thread in this prologue loop (C <= 2048)
+  int cnt = 0;
+  for (int c = tid; c < C; c += 256, ++cnt) {
+    const int g0 = (c / p.cpg) * p.cpg;
+    float A = 0.f, Bq = 0.f;
+    for (int i = 0; i < p.cpg; ++i) {
+      // g'_i = cA_i / rstd
+      const float gp = cA[g0 + i] / rA[g0 + i];
+      A = fmaf(gp, k2[g0 + i], A);
+      Bq = fmaf(gp, k3[g0 + i], Bq);
+    }
+    t2[cnt] = rA[c] * A * inv_m;
+    t3[cnt] = rA[c] * Bq * inv_m;
+    if (blockIdx.x == 0) {   // parameter gradients of image n, once
+      const float S1 = k2[c], S2 = k3[c];
+      const float sc = p.scale ? 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c) : 1.f;
+      if (p.dgamma) atomicAdd(p.dgamma + c, S2 * sc);
+      if (p.dbeta) atomicAdd(p.dbeta + c, S1 * sc);
+      if (p.dscale) {
+        const float ga = p.gamma ? __ldg(p.gamma + c) : 1.f, be = p.beta ? __ldg(p.beta + c) : 0.f;
+        p.dscale[(size_t)n * p.dss_ld + c] = ga * S2 + be * S1;
+        p.dshift[(size_t)n * p.dss_ld + c] = S1;
+      }
+    }
+  }
+  __syncthreads();
+  cnt = 0;
+  for (int c = tid; c < C; c += 256, ++cnt) { k2[c] = t2[cnt]; k3[c] = t3[cnt]; }
+  __syncthreads();
+
+  const int nv = C >> 2;
+  const int cols = nv < 256 ? nv : 256;
+  const int pstep = 256 / cols;
+  const int px0 = blockIdx.x * p.pix_per_cta;
+  const int px1 = min(p.HW, px0 + p.pix_per_cta);
+  for (int j0 = 0; j0 < nv; j0 += cols) {
+    const int j = j0 + tid % cols, prow = tid / cols;
+    if (prow >= pstep || j >= nv) continue;
+    const int c = j << 2;
+    const float4 a = *reinterpret_cast<const float4*>(cA + c), b = *reinterpret_cast<const float4*>(cB + c);
+    const float4 ra = *reinterpret_cast<const float4*>(rA + c), rb = *reinterpret_cast<const float4*>(rB + c);
+    const float4 q2 = *reinterpret_cast<const float4*>(k2 + c), q3 = *reinterpret_cast<const float4*>(k3 + c);
+    const float av[4] = {a.x, a.y, a.z, a.w}, q2v[4] = {q2.x, q2.y, q2.z, q2.w}, q3v[4] = {q3.x, q3.y, q3.z, q3.w};
+    const bool from0 = c < p.C0;
+    float* dst = from0 ? p.dx0 : p.dx1;
+    const int dld = from0 ? p.C0 : p.C1, dc = from0 ? c : c - p.C0;
+    const int acc = from0 ? p.acc0 : p.acc1;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int px = px0 + prow; px < px1; px += pstep) {
+      const float4 x = gn_bwd_load_x(p, n, px, c);
+      const float4 g = gn_bwd_load_g(p, n, px, C, c);
+      float dz[4], xh[4], dx[4];
+      gn_bwd_dz(p, n, px, C, c, x, g, a, b, ra, rb, dz, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dx[i] = fmaf(dz[i], av[i], -q2v[i]) - xh[i] * q3v[i];
+      if (p.addend) {
+        const float4 ad = bw_ldg4(p.addend + ((size_t)n * p.HW + px) * C + c);
+        dx[0] += ad.x; dx[1] += ad.y; dx[2] += ad.z; dx[3] += ad.w;
+      }
+      if (p.dx_bf16) {
+        uint2 u;
+        u.x = pack_bf16x2(dx[0], dx[1]);
+        u.y = pack_bf16x2(dx[2], dx[3]);
+        *reinterpret_cast<uint2*>(p.dx_bf16 + ((size_t)n * p.HW + px) * C + c) = u;
+      } else if (dst) {
+        float4* o = reinterpret_cast<float4*>(dst + ((size_t)n * p.HW + px) * dld + dc);
+        if (acc) {
+          const float4 old = *o;
+          dx[0] += old.x; dx[1] += old.y; dx[2] += old.z; dx[3] += old.w;
+        }
+        *o = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rs[i] += dx[i];
+    }
+    if (p.dx_rowsum) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(rsum + c + i, rs[i]);
+    }
+  }
+  if (p.dx_rowsum) {
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) atomicAdd(p.dx_rowsum + (size_t)n * C + c, rsum[c]);
+  }
+}
+
+// ================================================================================================
+// Gradient casts with fused column sums (bias gradients)
+// ================================================================================================
+// fp32 [rows][C] -> bf16 [rows][C]; colsum[c] += sum over rows (optional)
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          float* __restrict__ colsum, long long rows, int C,
+                                                          int rows_per_cta) {
+  extern __shared__ float csm[];
+  const int tid = threadIdx.x;
+  const int nv = C >> 2;
+  const int cols = nv < 256 ? nv : 256;
+  const int pstep = 256 / cols;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  if (colsum) {
+    for (int c = tid; c < C; c += 256) csm[c] = 0.f;
+    __syncthreads();
+  }
+  for (int j0 = 0; j0 < nv; j0 += cols) {
+    const int j = j0 + tid % cols, prow = tid / cols;
+    if (prow >= pstep || j >= nv) continue;
+    const int c = j << 2;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (long long r = r0 + prow; r < r1; r += pstep) {
+      const float4 v = bw_ldg4(x + r * C + c);
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(out + r * C + c) = u;
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    if (colsum) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(csm + c + i, s[i]);
+    }
+  }
+  if (colsum) {
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) atomicAdd(colsum + c, csm[c]);
+  }
+}
+
+// fp32 NCHW [B][C][HW] (C small) -> bf16 NHWC [B][HW][Cpad] zero padded; colsum[c] += sum (optional)
+__global__ void __launch_bounds__(256) nchw_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                       float* __restrict__ colsum, int B, int C, int HW, int Cpad) {
+  __shared__ float ssum[8];
+  if (threadIdx.x < 8) ssum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * HW;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), px = (int)(i - (long long)n * HW);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v[c] = c < C ? __ldg(x + ((size_t)n * C + c) * HW + px) : 0.f;
+      s[c] += v[c];
+    }
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * Cpad);
+    o[0] = u;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 1; k < Cpad / 8; ++k) o[k] = z;
+  }
+  if (colsum) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float t = s[c];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if ((threadIdx.x & 31) == 0 && c < C) atomicAdd(ssum + c, t);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(colsum + threadIdx.x, ssum[threadIdx.x]);
+  }
+}
+
+// colsum[c] += sum over rows of a bf16 matrix window [rows][ld] at columns [c0, c0 + C)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ colsum,
+                                                          long long rows, int ld, int c0, int C, int rows_per_cta) {
+  extern __shared__ float csm[];
+  const int tid = threadIdx.x;
+  for (int c = tid; c < C; c += 256) csm[c] = 0.f;
+  __syncthreads();
+  const int nv = C >> 2;
+  const int cols = nv < 256 ? nv : 256;
+  const int pstep = 256 / cols;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  for (int j0 = 0; j0 < nv; j0 += cols) {
+    const int j = j0 + tid % cols, prow = tid / cols;
+    if (prow >= pstep || j >= nv) continue;
+    const int c = j << 2;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (long long r = r0 + prow; r < r1; r += pstep) {
+      const float4 v = bw_ldg4_bf16(x + r * ld + c0 + c);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(csm + c + i, s[i]);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) atomicAdd(colsum + c, csm[c]);
+}
+
+// out (+)= scale * resample(x): mode 1 = 2x2 average (out is half size), mode 2 = nearest 2x (out is double size)
+__global__ void __launch_bounds__(256) resample_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int B,
+                                                           int H, int W, int C, int mode, float scale, int accumulate) {
+  const int cv = C >> 2;
+  const int Ho = mode == 1 ? H >> 1 : H * 2, Wo = mode == 1 ? W >> 1 : W * 2;
+  const size_t total = (size_t)B * Ho * Wo * cv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cv);
+    const size_t po = i / cv;
+    const int ox = (int)(po % Wo);
+    const int oy = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    float4 r;
+    if (mode == 1) {
+      const float4* src = reinterpret_cast<const float4*>(x) + (((size_t)n * H + 2 * oy) * W + 2 * ox) * cv + c4;
+      const float4 a = __ldg(src), b = __ldg(src + cv), c = __ldg(src + (size_t)W * cv), d = __ldg(src + (size_t)W * cv + cv);
+      r.x = 0.25f * (a.x + b.x + c.x + d.x); r.y = 0.25f * (a.y + b.y + c.y + d.y);
+      r.z = 0.25f * (a.z + b.z + c.z + d.z); r.w = 0.25f * (a.w + b.w + c.w + d.w);
+    } else {
+      r = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * cv + c4);
+    }
+    r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+    float4* o = reinterpret_cast<float4*>(out) + i;
+    if (accumulate) {
+      const float4 old = *o;
+      r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+    }
+    *o = r;
+  }
+}
+
+// fp32 NHWC -> bf16 NHWC nearest 2x (training-mode Upsample: the 3x3 conv then runs on the materialised tensor)
+__global__ void __launch_bounds__(256) upsample2_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             int B, int H, int W, int C) {
+  const int cv = C >> 2, Ho = H * 2, Wo = W * 2;
+  const size_t total = (size_t)B * Ho * Wo * cv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cv);
+    const size_t po = i / cv;
+    const int ox = (int)(po % Wo);
+    const int oy = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * cv + c4);
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+
+// ================================================================================================
+// Row softmax of the unfused attention backward: P = softmax(scale * S) (bf16), dS = scale * P o (dP - sum_j dP_j P_j)
+// One warp per row.
+// ================================================================================================
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P,
+                                                           long long rows, int T, float scale) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* s = S + r * T;
+  float m = -INFINITY;
+  for (int j = lane; j < T; j += 32) m = fmaxf(m, s[j]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) sum += __expf((s[j] - m) * scale);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < T; j += 32) P[r * T + j] = __float2bfloat16_rn(__expf((s[j] - m) * scale) * inv);
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ P,
+                                                               const float* __restrict__ dP,
+                                                               __nv_bfloat16* __restrict__ dS, long long rows, int T,
+                                                               float scale) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int j = lane; j < T; j += 32) dot = fmaf(__bfloat162float(P[r * T + j]), dP[r * T + j], dot);
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int j = lane; j < T; j += 32)
+    dS[r * T + j] = __float2bfloat16_rn(scale * __bfloat162float(P[r * T + j]) * (dP[r * T + j] - dot));
+}
+
+// ================================================================================================
+// MSE loss (F.mse_loss(mean), diffusions/ddpm.py:136-138) and its gradient
+// ================================================================================================
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ loss, long long n, float inv_n) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    s = fmaf(d, d, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    atomicAdd(loss, t * inv_n);
+  }
+}
+
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       const float* __restrict__ gscale, float* __restrict__ da,
+                                                       long long n, float two_inv_n) {
+  const float k = two_inv_n * (gscale ? gscale[0] : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    da[i] = k * (a[i] - b[i]);
+}
+
+// keep-mask of the counter-based dropout (for the parity tests: the oracle applies exactly this mask)
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, long long n, unsigned long long seed,
+                                                           uint32_t thresh) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dropout_keep(seed, (unsigned long long)i, thresh) ? 1.f : 0.f;
+}
+
+static inline int bw_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(d && d->g && d->x0 && d->stats0 && d->sums, "groupnorm_bwd: null g/x0/stats0/sums");
+  const int C1 = d->x1 ? d->C1 : 0;
+  const int C = d->C0 + C1;
+  B200_REQUIRE(d->x1 == nullptr || d->stats1 != nullptr, "groupnorm_bwd: second source needs its statistics");
+  B200_REQUIRE(d->groups > 0 && C % d->groups == 0, "groupnorm_bwd: C=%d not divisible by groups=%d", C, d->groups);
+  B200_REQUIRE(d->C0 % 4 == 0 && C1 % 4 == 0, "groupnorm_bwd: channel counts must be multiples of 4");
+  B200_REQUIRE(C <= 2048, "groupnorm_bwd: C=%d too large", C);
+  B200_REQUIRE(d->resample >= 0 && d->resample <= 2, "groupnorm_bwd: bad resample mode");
+  B200_REQUIRE(d->W > 0 && d->HW % d->W == 0, "groupnorm_bwd: HW not a multiple of W");
+  if (d->resample == 1) B200_REQUIRE(d->W % 2 == 0 && (d->HW / d->W) % 2 == 0, "groupnorm_bwd: avg-pool needs even H, W");
+  B200_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "groupnorm_bwd: scale and shift go together");
+  B200_REQUIRE((d->dscale == nullptr) == (d->dshift == nullptr), "groupnorm_bwd: dscale and dshift go together");
+  B200_REQUIRE(d->drop_p >= 0.f && d->drop_p < 1.f && (d->drop_p == 0.f || d->resample == 0), "groupnorm_bwd: bad dropout");
+  B200_REQUIRE(d->dx_bf16 == nullptr || (d->dx0 == nullptr && d->dx1 == nullptr), "groupnorm_bwd: choose bf16 or fp32 dx");
+  GnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = reinterpret_cast<const __nv_bfloat16*>(d->g);
+  p.x0 = d->x0; p.C0 = d->C0; p.st0 = d->stats0; p.x1 = d->x1; p.C1 = C1; p.st1 = d->stats1;
+  p.HW = d->HW; p.W = d->W; p.groups = d->groups; p.cpg = C / d->groups;
+  p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps; p.scale = d->scale; p.shift = d->shift; p.ss_ld = d->ss_ld;
+  p.apply_silu = d->apply_silu; p.resample = d->resample;
+  p.drop_thresh = dropout_threshold(d->drop_p); p.drop_scale = 1.0f / (1.0f - d->drop_p); p.drop_seed = d->drop_seed;
+  p.sums = d->sums;
+  p.dx0 = d->dx0; p.acc0 = d->dx0_accumulate; p.dx1 = d->dx1; p.acc1 = d->dx1_accumulate; p.addend = d->addend;
+  p.dx_bf16 = reinterpret_cast<__nv_bfloat16*>(d->dx_bf16); p.dx_rowsum = d->dx_rowsum;
+  p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dscale = d->dscale; p.dshift = d->dshift; p.dss_ld = d->dss_ld;
+  int ppc = 32768 / C;
+  if (ppc < 1) ppc = 1;
+  if (ppc > d->HW) ppc = d->HW;
+  p.pix_per_cta = ppc;
+  dim3 grid((d->HW + ppc - 1) / ppc, d->B);
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  B200_CHECK(cudaMemsetAsync(d->sums, 0, (size_t)d->B * C * 2 * sizeof(float), stream));
+  gn_bwd_reduce_kernel<<<grid, 256, (size_t)6 * C * 4, stream>>>(p);
+  ++g_launch_count;
+  B200_CHECK(cudaGetLastError());
+  gn_bwd_apply_kernel<<<grid, 256, (size_t)7 * C * 4, stream>>>(p);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "gn_bwd kernels launch");
+}
+
+extern "C" int b200_cast_bf16_colsum(const float* x, void* out_bf16, float* colsum, long long rows, int C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out_bf16 && rows >= 1 && C >= 4 && C % 4 == 0 && C <= 8192, "cast_bf16_colsum: bad arguments");
+  int rpc = 32768 / C;
+  if (rpc < 1) rpc = 1;
+  const long long grid = (rows + rpc - 1) / rpc;
+  cast_colsum_kernel<<<(unsigned)grid, 256, (size_t)C * 4, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), colsum,
+                                                                   rows, C, rpc);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "cast_colsum_kernel launch");
+}
+
+extern "C" int b200_nchw_to_nhwc_pad_bf16(const float* x, void* out_bf16, float* colsum, int B, int C, int HW, int Cpad,
+                                          void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out_bf16 && C >= 1 && C <= 8 && Cpad % 8 == 0 && Cpad >= 8, "nchw_to_nhwc_pad: needs C <= 8, Cpad % 8 == 0");
+  nchw_pad_kernel<<<bw_grid((long long)B * HW, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), colsum, B,
+                                                                     C, HW, Cpad);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "nchw_pad_kernel launch");
+}
+
+extern "C" int b200_colsum_bf16(const void* x, float* colsum, long long rows, int ld, int c0, int C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && colsum && rows >= 1 && C >= 4 && C % 4 == 0 && c0 % 4 == 0 && ld % 4 == 0 && C <= 8192,
+               "colsum_bf16: bad arguments");
+  int rpc = 65536 / C;
+  if (rpc < 1) rpc = 1;
+  const long long grid = (rows + rpc - 1) / rpc;
+  colsum_bf16_kernel<<<(unsigned)grid, 256, (size_t)C * 4, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), colsum, rows,
+                                                                   ld, c0, C, rpc);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "colsum_bf16_kernel launch");
+}
+
+extern "C" int b200_resample_f32(const float* x, float* out, int B, int H, int W, int C, int mode, float scale,
+                                 int accumulate, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out && C % 4 == 0 && (mode == 1 || mode == 2), "resample_f32: bad arguments");
+  if (mode == 1) B200_REQUIRE(H % 2 == 0 && W % 2 == 0, "resample_f32: average pool needs even H, W");
+  const size_t total = (size_t)B * (mode == 1 ? (H / 2) * (W / 2) : 4 * H * W) * (C / 4);
+  resample_f32_kernel<<<bw_grid((long long)total, 256), 256, 0, stream>>>(x, out, B, H, W, C, mode, scale, accumulate);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "resample_f32_kernel launch");
+}
+
+extern "C" int b200_upsample2_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out_bf16 && C % 4 == 0, "upsample2_bf16: bad arguments");
+  const size_t total = (size_t)B * 4 * H * W * (C / 4);
+  upsample2_bf16_kernel<<<bw_grid((long long)total, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, H,
+                                                                          W, C);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "upsample2_bf16_kernel launch");
+}
+
+extern "C" int b200_softmax_rows(const float* S, void* P_bf16, long long rows, int T, float scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(S && P_bf16 && rows >= 1 && T >= 1, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, scale);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "softmax_rows_kernel launch");
+}
+
+extern "C" int b200_softmax_bwd_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, float scale,
+                                     void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(P_bf16 && dP && dS_bf16 && rows >= 1 && T >= 1, "softmax_bwd_rows: bad arguments");
+  softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(P_bf16), dP,
+                                                                       reinterpret_cast<__nv_bfloat16*>(dS_bf16), rows, T, scale);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "softmax_bwd_rows_kernel launch");
+}
+
+extern "C" int b200_mse_loss(const float* a, const float* b, float* loss, long long n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(a && b && loss && n >= 1, "mse_loss: bad arguments");
+  B200_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  mse_loss_kernel<<<bw_grid(n, 256), 256, 0, stream>>>(a, b, loss, n, 1.0f / (float)n);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "mse_loss_kernel launch");
+}
+
+extern "C" int b200_mse_loss_grad(const float* a, const float* b, const float* grad_scale, float* da, long long n,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(a && b && da && n >= 1, "mse_loss_grad: bad arguments");
+  mse_grad_kernel<<<bw_grid(n, 256), 256, 0, stream>>>(a, b, grad_scale, da, n, 2.0f / (float)n);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "mse_grad_kernel launch");
+}
+
+extern "C" int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(out && n >= 1 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  dropout_mask_kernel<<<bw_grid(n, 256), 256, 0, stream>>>(out, n, seed, dropout_threshold(p));
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "dropout_mask_kernel launch");
+}

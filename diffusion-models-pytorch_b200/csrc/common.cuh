@@ -211,6 +211,19 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return d;
 }
 
+// Counter-based dropout: element e of a tensor is kept iff hash(seed, e) >= p * 2^32.  The same function regenerates the
+// mask in the backward pass (and in b200_dropout_mask for the parity tests), so no mask tensor is ever stored.
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  return p <= 0.f ? 0u : (uint32_t)((double)p * 4294967296.0);
+}
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long e, uint32_t thresh) {
+  uint32_t x = (uint32_t)e ^ (uint32_t)seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  x += (uint32_t)(e >> 32) * 0x9e3779b9u + (uint32_t)(seed >> 32);
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x >= thresh;
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -288,6 +288,8 @@ struct GnApplyParams {
   int apply_silu, resample;
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
+  float drop_p, drop_scale;       // training-mode dropout after the activation (resample == 0 only)
+  uint32_t drop_thresh; unsigned long long drop_seed;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -370,6 +372,13 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
           const float4 v = vv[u];
           float y0 = fmaf(v.x, a.x, b.x), y1 = fmaf(v.y, a.y, b.y), y2 = fmaf(v.z, a.z, b.z), y3 = fmaf(v.w, a.w, b.w);
           if (p.apply_silu) { y0 = silu_tanh(y0); y1 = silu_tanh(y1); y2 = silu_tanh(y2); y3 = silu_tanh(y3); }
+          if (p.drop_thresh) {
+            const unsigned long long e = ((unsigned long long)n * p.HW + q) * C + c;
+            y0 = dropout_keep(p.drop_seed, e, p.drop_thresh) ? y0 * p.drop_scale : 0.f;
+            y1 = dropout_keep(p.drop_seed, e + 1, p.drop_thresh) ? y1 * p.drop_scale : 0.f;
+            y2 = dropout_keep(p.drop_seed, e + 2, p.drop_thresh) ? y2 * p.drop_scale : 0.f;
+            y3 = dropout_keep(p.drop_seed, e + 3, p.drop_thresh) ? y3 * p.drop_scale : 0.f;
+          }
           uint2 uo;
           uo.x = pack_bf16x2(y0, y1);
           uo.y = pack_bf16x2(y2, y3);
@@ -415,6 +424,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
         if (p.apply_silu) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = silu_tanh(y[i]);
+        }
+        if (p.drop_thresh) {
+          const unsigned long long e = ((unsigned long long)n * p.HW + px) * C + c;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = dropout_keep(p.drop_seed, e + i, p.drop_thresh) ? y[i] * p.drop_scale : 0.f;
         }
         uint2 uo;
         uo.x = pack_bf16x2(y[0], y[1]);
@@ -477,11 +491,12 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
 
 }  // namespace b200
 
-extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0, const float* x1,
-                                        int C1, const float* stats1, int B, int HW, int W, int groups, const float* gamma,
-                                        const float* beta, float eps, const float* scale, const float* shift,
-                                        int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
-                                        void* stream_) {
+extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0,
+                                              const float* x1, int C1, const float* stats1, int B, int HW, int W,
+                                              int groups, const float* gamma, const float* beta, float eps,
+                                              const float* scale, const float* shift, int ss_ld, int apply_silu,
+                                              int resample, float drop_p, unsigned long long drop_seed, void* out_bf16,
+                                              void* raw_out_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const float* x0 = reinterpret_cast<const float*>(x0_);
   B200_REQUIRE(x0 && stats0 && out_bf16, "groupnorm_apply: null x0/stats0/out");
@@ -503,6 +518,10 @@ extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0,
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
   p.apply_silu = apply_silu; p.resample = resample;
   p.in_bf16 = x0_is_bf16 ? 1 : 0;
+  B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
+  B200_REQUIRE(drop_p == 0.f || resample == 0, "groupnorm_apply: dropout is not combined with resampling");
+  p.drop_p = drop_p; p.drop_scale = 1.0f / (1.0f - drop_p); p.drop_seed = drop_seed;
+  p.drop_thresh = dropout_threshold(drop_p);
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
   const int work_pix = resample == 1 ? HW / 4 : HW;
@@ -514,4 +533,14 @@ extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0,
   groupnorm_apply_kernel<<<grid, 256, smem, stream>>>(p);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "groupnorm_apply_kernel launch");
+}
+
+extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0, const float* x1,
+                                        int C1, const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+                                        const float* beta, float eps, const float* scale, const float* shift,
+                                        int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
+                                        void* stream_) {
+  return b200_groupnorm_apply_train_fwd(x0_, x0_is_bf16, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps,
+                                        scale, shift, ss_ld, apply_silu, resample, 0.f, 0ull, out_bf16, raw_out_bf16,
+                                        stream_);
 }

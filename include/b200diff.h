@@ -240,6 +240,63 @@ typedef struct b200_wgrad_desc {
 
 int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream);
 
+/* Training-mode K3: b200_groupnorm_apply_fwd plus dropout after the activation (nn.Dropout of models/unet.py:24).
+ * The keep mask is a counter-based hash of (drop_seed, element index): the backward regenerates it, nothing is stored. */
+int b200_groupnorm_apply_train_fwd(const void* x0, int x0_is_bf16, int C0, const float* stats0, const float* x1, int C1,
+                                   const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+                                   const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
+                                   int apply_silu, int resample, float drop_p, unsigned long long drop_seed,
+                                   void* out_bf16, void* raw_out_bf16, void* stream);
+/* keep mask (1.0 / 0.0) of that dropout for elements [0, n): lets the parity tests hand the oracle the same mask */
+int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed, void* stream);
+
+/* Adjoint of K3 (GroupNorm [+ AdaGN scale/shift] [+ SiLU] [+ dropout] [+ 2x resample]), two streaming passes.
+ * g: bf16 gradient w.r.t. the K3 output [B][HW_out][C0+C1]; x0/x1/stats*: the forward's inputs and statistics.
+ * Outputs: dx as fp32 split over the two sources (store or accumulate each; optional fp32 addend [B][HW][C] folded
+ * in, e.g. the residual branch's gradient), or as one bf16 tensor (+ optional per-(image, channel) sums of dx in
+ * dx_rowsum [B][C], accumulated: the bias / time-embedding-row gradients of the producing conv);
+ * dgamma/dbeta [C] accumulate; dscale/dshift [B][dss_ld] are written. sums: workspace [B][C][2]. */
+typedef struct b200_gn_bwd_desc {
+  const void* g;
+  const float* x0; int C0; const float* stats0;
+  const float* x1; int C1; const float* stats1;
+  int B, HW, W, groups;
+  const float* gamma; const float* beta; float eps;
+  const float* scale; const float* shift; int ss_ld;
+  int apply_silu, resample;
+  float drop_p; unsigned long long drop_seed;
+  float* sums;
+  float* dx0; int dx0_accumulate;
+  float* dx1; int dx1_accumulate;
+  const float* addend;
+  void* dx_bf16;
+  float* dx_rowsum;
+  float* dgamma; float* dbeta;
+  float* dscale; float* dshift; int dss_ld;
+} b200_gn_bwd_desc;
+int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream);
+
+/* Gradient plumbing: fp32 [rows][C] -> bf16 (tensor-core operand) with colsum[c] += column sums (bias gradient);
+ * NCHW fp32 with C <= 8 -> NHWC bf16 zero-padded to Cpad channels (first / last conv); column sums of a bf16 window;
+ * out (+)= scale * {2x2 average (mode 1) | nearest 2x (mode 2)} of x (adjoints of each other up to the scale);
+ * fp32 -> bf16 nearest 2x (training-mode Upsample). */
+int b200_cast_bf16_colsum(const float* x, void* out_bf16, float* colsum, long long rows, int C, void* stream);
+int b200_nchw_to_nhwc_pad_bf16(const float* x, void* out_bf16, float* colsum, int B, int C, int HW, int Cpad, void* stream);
+int b200_colsum_bf16(const void* x, float* colsum, long long rows, int ld, int c0, int C, void* stream);
+int b200_resample_f32(const float* x, float* out, int B, int H, int W, int C, int mode, float scale, int accumulate,
+                      void* stream);
+int b200_upsample2_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream);
+
+/* Row softmax pieces of the attention backward (adjoint of models/modules.py:94-95):
+ * P = softmax(scale * S) as bf16; dS = scale * P o (dP - rowsum(dP o P)) as bf16.  S, dP fp32 [rows][T]. */
+int b200_softmax_rows(const float* S, void* P_bf16, long long rows, int T, float scale, void* stream);
+int b200_softmax_bwd_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, float scale, void* stream);
+
+/* F.mse_loss(a, b) (mean) into loss[0], and its gradient da = grad_scale[0] * 2 (a - b) / n (diffusions/ddpm.py:136-138);
+ * grad_scale is a device scalar (the incoming dL/dloss) or NULL for 1. */
+int b200_mse_loss(const float* a, const float* b, float* loss, long long n, void* stream);
+int b200_mse_loss_grad(const float* a, const float* b, const float* grad_scale, float* da, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -513,6 +513,162 @@ def case_wgrad():
 
 
 # ----------------------------------------------------------------------------------------------------
+# GroupNorm(+AdaGN)(+SiLU)(+dropout)(+resample) backward vs autograd of the fp32 restatement
+# ----------------------------------------------------------------------------------------------------
+def _gn_bwd_case(name, B, H, W, C0, C1, *, silu=True, adagn=False, resample=0, drop_p=0.0, bf16_out=False, addend=False,
+                 eps=1e-5):
+    C = C0 + C1
+    x0 = _gen(B, H, W, C0, seed=1) * 1.5 + 0.3
+    x1 = (_gen(B, H, W, C1, seed=2) * 0.7 - 0.2) if C1 else None
+    gamma = (_gen(C, seed=3) * 0.2 + 1.0)
+    beta = _gen(C, seed=4) * 0.1
+    scale = _gen(B, C, seed=5) * 0.3 if adagn else None
+    shift = _gen(B, C, seed=6) * 0.3 if adagn else None
+    Ho, Wo = (H // 2, W // 2) if resample == 1 else (2 * H, 2 * W) if resample == 2 else (H, W)
+    g = _bf16r(_gen(B, Ho, Wo, C, seed=7))
+    ad = _gen(B, H, W, C, seed=8) if addend else None
+    seed = 1234567
+    mask = None
+    if drop_p > 0:
+        mask = K.dropout_mask(torch.empty(B, H, W, C, device=DEV), drop_p, seed)
+    # ---- fp32 autograd restatement (NHWC tensors, channels last dim) ----
+    xs = [x0.clone().requires_grad_(True)] + ([x1.clone().requires_grad_(True)] if C1 else [])
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    sc = scale.clone().requires_grad_(True) if adagn else None
+    sh = shift.clone().requires_grad_(True) if adagn else None
+    xc = torch.cat(xs, dim=-1).permute(0, 3, 1, 2)
+    y = F.group_norm(xc, 32, gm, bt, eps)
+    if adagn:
+        y = y * (1 + sc[:, :, None, None]) + sh[:, :, None, None]
+    if silu:
+        y = F.silu(y)
+    if mask is not None:
+        y = y * mask.permute(0, 3, 1, 2) / (1 - drop_p)
+    if resample == 1:
+        y = F.avg_pool2d(y, 2, 2)
+    elif resample == 2:
+        y = F.interpolate(y, scale_factor=2, mode='nearest')
+    y.backward(g.permute(0, 3, 1, 2))
+    # ---- kernels: statistics as the conv epilogue would deliver them ----
+    def stats(x):
+        return torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
+    st0 = stats(x0)
+    st1 = stats(x1) if C1 else None
+    sums = torch.empty(B, C, 2, device=DEV)
+    dgamma, dbeta = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dss = torch.full((B, 2 * C), float('nan'), device=DEV) if adagn else None
+    kw = dict(scale=scale, shift=shift, ss_ld=C if adagn else 0, silu=silu, resample=resample, drop_p=drop_p,
+              drop_seed=seed, dgamma=dgamma, dbeta=dbeta, dscale=dss, dshift=dss[:, C:] if adagn else None,
+              dss_ld=2 * C)
+    gb = g.to(torch.bfloat16).contiguous()
+    ok = True
+    if bf16_out:
+        dxb = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+        rowsum = torch.zeros(B, C, device=DEV)
+        K.groupnorm_bwd(gb, x0, C0, st0, x1, C1, st1, B, H * W, W, 32, gamma, beta, eps, sums, dx_bf16=dxb,
+                        dx_rowsum=rowsum, **kw)
+        torch.cuda.synchronize()
+        ref = torch.cat([t.grad for t in xs], dim=-1)
+        ok &= _report(name + ' dx(bf16)', dxb, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+        ok &= _report(name + ' dx rowsum', rowsum, ref.sum(dim=(1, 2)), rtol=1e-2, atol=2e-2 * float(ref.abs().max()) * (H * W) ** 0.5)
+    else:
+        dx0 = torch.full((B, H, W, C0), 0.5, device=DEV)       # accumulate on top of an existing gradient
+        dx1 = torch.full((B, H, W, C1), float('nan'), device=DEV) if C1 else None
+        K.groupnorm_bwd(gb, x0, C0, st0, x1, C1, st1, B, H * W, W, 32, gamma, beta, eps, sums, dx0=dx0, dx0_acc=True,
+                        dx1=dx1, dx1_acc=False, addend=ad, **kw)
+        torch.cuda.synchronize()
+        r0 = xs[0].grad + 0.5 + (ad[..., :C0] if addend else 0)
+        ok &= _report(name + ' dx0 (accumulated)', dx0, r0, rtol=1e-3, atol=2e-3 * float(r0.abs().max()))
+        if C1:
+            r1 = xs[1].grad + (ad[..., C0:] if addend else 0)
+            ok &= _report(name + ' dx1', dx1, r1, rtol=1e-3, atol=2e-3 * float(r1.abs().max()))
+    ok &= _report(name + ' dgamma', dgamma, gm.grad, rtol=1e-3, atol=2e-3 * float(gm.grad.abs().max()))
+    ok &= _report(name + ' dbeta', dbeta, bt.grad, rtol=1e-3, atol=2e-3 * float(bt.grad.abs().max()))
+    if adagn:
+        ok &= _report(name + ' dscale', dss[:, :C], sc.grad, rtol=1e-3, atol=2e-3 * float(sc.grad.abs().max()))
+        ok &= _report(name + ' dshift', dss[:, C:], sh.grad, rtol=1e-3, atol=2e-3 * float(sh.grad.abs().max()))
+    return ok
+
+
+def case_groupnorm_bwd():
+    ok = _gn_bwd_case('gn_bwd C128 32x32', 3, 32, 32, 128, 0)
+    ok &= _gn_bwd_case('gn_bwd cat 256+128 16x16 addend', 2, 16, 16, 256, 128, addend=True)
+    ok &= _gn_bwd_case('gn_bwd C256 8x8 no-silu (attention norm)', 4, 8, 8, 256, 0, silu=False, addend=True)
+    ok &= _gn_bwd_case('gn_bwd adagn C256 16x16 bf16 out + rowsum', 3, 16, 16, 256, 0, adagn=True, bf16_out=True)
+    ok &= _gn_bwd_case('gn_bwd dropout 0.1 C128 16x16 bf16 out', 2, 16, 16, 128, 0, drop_p=0.1, bf16_out=True)
+    ok &= _gn_bwd_case('gn_bwd avgpool C128 16x16', 2, 16, 16, 128, 0, resample=1)
+    ok &= _gn_bwd_case('gn_bwd nearest-up C256 8x8', 2, 8, 8, 256, 0, resample=2)
+    ok &= _gn_bwd_case('gn_bwd C64 4x4 eps 1e-6', 5, 4, 4, 64, 0, eps=1e-6)
+    ok &= _gn_bwd_case('gn_bwd cat 1024+512 8x8', 1, 8, 8, 1024, 512)
+    return ok
+
+
+def case_backward_misc():
+    ok = True
+    # cast + column sums
+    x = _gen(1000, 256, seed=1)
+    out = torch.empty(1000, 256, device=DEV, dtype=torch.bfloat16)
+    cs = torch.ones(256, device=DEV)
+    K.cast_bf16_colsum(x, out, cs, 1000, 256)
+    ok &= _report('cast_bf16_colsum cast', out, x.to(torch.bfloat16), rtol=0, atol=0)
+    ok &= _report('cast_bf16_colsum sums (accumulate)', cs, x.sum(0) + 1, rtol=1e-4, atol=1e-3)
+    # NCHW -> padded NHWC
+    xi = _gen(3, 3, 64, seed=2)
+    po = torch.full((3, 64, 64), float('nan'), device=DEV, dtype=torch.bfloat16)
+    cs3 = torch.zeros(3, device=DEV)
+    K.nchw_to_nhwc_pad_bf16(xi, po, cs3, 3, 3, 64, 64)
+    ref = torch.zeros(3, 64, 64, device=DEV)
+    ref[..., :3] = xi.permute(0, 2, 1)
+    ok &= _report('nchw_to_nhwc_pad', po, ref.to(torch.bfloat16), rtol=0, atol=0)
+    ok &= _report('nchw_to_nhwc_pad colsum', cs3, xi.sum(dim=(0, 2)), rtol=1e-4, atol=1e-3)
+    # bf16 column sums of a window
+    xb = _gen(777, 512, seed=3).to(torch.bfloat16)
+    cw = torch.zeros(256, device=DEV)
+    K.colsum_bf16(xb, cw, 777, 512, 128, 256)
+    ok &= _report('colsum_bf16 window', cw, xb[:, 128:384].float().sum(0), rtol=1e-4, atol=1e-2)
+    # resampling adjoints
+    xr = _gen(2, 8, 8, 64, seed=4)
+    o1 = torch.ones(2, 4, 4, 64, device=DEV)
+    K.resample_f32(xr, o1, 2, 8, 8, 64, 1, scale=4.0, accumulate=True)
+    ref1 = F.avg_pool2d(xr.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1) * 4 + 1
+    ok &= _report('resample avg (sum-pool, accumulate)', o1, ref1, rtol=1e-5, atol=1e-5)
+    o2 = torch.empty(2, 16, 16, 64, device=DEV)
+    K.resample_f32(xr, o2, 2, 8, 8, 64, 2, scale=0.25)
+    ref2 = F.interpolate(xr.permute(0, 3, 1, 2), scale_factor=2, mode='nearest').permute(0, 2, 3, 1) * 0.25
+    ok &= _report('resample nearest x0.25', o2, ref2, rtol=1e-6, atol=1e-6)
+    o3 = torch.empty(2, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    K.upsample2_bf16(xr, o3, 2, 8, 8, 64)
+    ok &= _report('upsample2_bf16', o3, (ref2 * 4).to(torch.bfloat16), rtol=0, atol=0)
+    # softmax rows fwd / bwd
+    S = _gen(6, 100, 100, seed=5) * 3
+    P = torch.empty(6, 100, 100, device=DEV, dtype=torch.bfloat16)
+    K.softmax_rows(S, P, 600, 100, 0.125)
+    Pr = torch.softmax(S * 0.125, dim=-1)
+    ok &= _report('softmax_rows', P, Pr, rtol=1e-2, atol=1e-4)
+    dP = _gen(6, 100, 100, seed=6)
+    dS = torch.empty_like(P)
+    K.softmax_bwd_rows(P, dP, dS, 600, 100, 0.125)
+    Pf = P.float()
+    ref = 0.125 * Pf * (dP - (dP * Pf).sum(-1, keepdim=True))
+    ok &= _report('softmax_bwd_rows', dS, ref, rtol=1e-2, atol=1e-4)
+    # MSE loss + gradient
+    a, b = _gen(4, 3, 32, 32, seed=7), _gen(4, 3, 32, 32, seed=8)
+    loss = torch.empty(1, device=DEV)
+    K.mse_loss(a, b, loss)
+    ok &= _report('mse_loss', loss, F.mse_loss(a, b).view(1), rtol=1e-5, atol=1e-6)
+    da = torch.empty_like(a)
+    gs = torch.tensor([0.5], device=DEV)
+    K.mse_loss_grad(a, b, gs, da)
+    ok &= _report('mse_loss_grad', da, 0.5 * 2 * (a - b) / a.numel(), rtol=1e-5, atol=1e-9)
+    # dropout keep rate
+    m = K.dropout_mask(torch.empty(1 << 20, device=DEV), 0.1, 42)
+    rate = 1 - m.mean().item()
+    good = abs(rate - 0.1) < 2e-3
+    print(json.dumps({'case': 'dropout keep rate', 'drop_rate': rate, 'ok': good}), flush=True)
+    return ok and good
+
+
+# ----------------------------------------------------------------------------------------------------
 # sampler step vs the eager op sequence of the reference (restated in oracle/diffusion_ref.py)
 # ----------------------------------------------------------------------------------------------------
 def case_sampler():

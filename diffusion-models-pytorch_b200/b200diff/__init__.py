@@ -61,7 +61,7 @@ class GemmDesc(Structure):
 
 
 class WgradDesc(Structure):
-    _fields_ = [('dy', c_void_p), ('dy_C', c_int),
+    _fields_ = [('dy', c_void_p), ('dy_C', c_int), ('dy_c0', c_int),
                 ('x', c_void_p), ('x_C', c_int), ('x_H', c_int), ('x_W', c_int), ('x_planes', c_int), ('x_c0', c_int),
                 ('B', c_int), ('Ho', c_int), ('Wo', c_int), ('Cout', c_int), ('Cin', c_int), ('ntaps', c_int),
                 ('taps', c_int8 * 36), ('dw', c_void_p), ('dw_co_stride', c_longlong), ('dw_ci_stride', c_longlong),
@@ -80,8 +80,8 @@ class GnBwdDesc(Structure):
                 ('sums', c_void_p),
                 ('dx0', c_void_p), ('dx0_accumulate', c_int),
                 ('dx1', c_void_p), ('dx1_accumulate', c_int),
-                ('addend', c_void_p), ('dx_bf16', c_void_p), ('dx_rowsum', c_void_p),
-                ('dgamma', c_void_p), ('dbeta', c_void_p),
+                ('addend', c_void_p), ('dx_bf16', c_void_p), ('dx_rowsum', c_void_p), ('dx_rowsum_ld', c_int),
+                ('dx_colsum', c_void_p), ('dgamma', c_void_p), ('dbeta', c_void_p),
                 ('dscale', c_void_p), ('dshift', c_void_p), ('dss_ld', c_int)]
 
 
@@ -132,6 +132,7 @@ def lib():
     L.b200_upsample2_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.b200_softmax_rows.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
     L.b200_softmax_bwd_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
+    L.b200_time_embed_bwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 14
     L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for name in BACKWARD_SYMBOLS:
@@ -150,7 +151,7 @@ def lib():
 BACKWARD_SYMBOLS = (
     'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
     'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
-    'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad',
+    'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad', 'b200_time_embed_bwd',
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
@@ -483,13 +484,13 @@ def gemm_batched(a, b, out, M, N, Kdim, *, batch=1, heads=1, out_ld=None, out_ba
     return out
 
 
-def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0, co_stride=None, ci_stride=None,
-                 tap_stride=1):
+def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0, dy_c0=0, co_stride=None,
+                 ci_stride=None, tap_stride=1):
     """Accumulates the weight gradient into `dw` (fp32; default strides = an OIHW tensor [Cout][Cin][ntaps]).
     x_geom = (C, H, W, planes) of the bf16 tensor the forward conv read, taps = its tap table (one phase)."""
     _need_cuda(dy, x, dw)
     d = WgradDesc()
-    d.dy, d.dy_C = dy.data_ptr(), dy_C
+    d.dy, d.dy_C, d.dy_c0 = dy.data_ptr(), dy_C, dy_c0
     d.x = x.data_ptr()
     d.x_C, d.x_H, d.x_W, d.x_planes = x_geom
     d.x_c0 = x_c0
@@ -510,8 +511,8 @@ def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0,
 
 def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, sums, *, scale=None,
                   shift=None, ss_ld=0, silu=True, resample=0, drop_p=0.0, drop_seed=0, dx0=None, dx0_acc=False,
-                  dx1=None, dx1_acc=False, addend=None, dx_bf16=None, dx_rowsum=None, dgamma=None, dbeta=None,
-                  dscale=None, dshift=None, dss_ld=0):
+                  dx1=None, dx1_acc=False, addend=None, dx_bf16=None, dx_rowsum=None, dx_rowsum_ld=0, dx_colsum=None,
+                  dgamma=None, dbeta=None, dscale=None, dshift=None, dss_ld=0):
     _need_cuda(g, x0, stats0, sums)
     d = GnBwdDesc()
     d.g, d.x0, d.C0, d.stats0 = g.data_ptr(), x0.data_ptr(), C0, stats0.data_ptr()
@@ -523,6 +524,7 @@ def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, be
     d.sums = sums.data_ptr()
     d.dx0, d.dx0_accumulate, d.dx1, d.dx1_accumulate = _ptr(dx0), int(dx0_acc), _ptr(dx1), int(dx1_acc)
     d.addend, d.dx_bf16, d.dx_rowsum = _ptr(addend), _ptr(dx_bf16), _ptr(dx_rowsum)
+    d.dx_rowsum_ld, d.dx_colsum = dx_rowsum_ld, _ptr(dx_colsum)
     d.dgamma, d.dbeta, d.dscale, d.dshift, d.dss_ld = _ptr(dgamma), _ptr(dbeta), _ptr(dscale), _ptr(dshift), dss_ld
     C = C0 + (C1 if x1 is not None else 0)
     _launch('groupnorm_bwd', lambda: _check(lib().b200_groupnorm_bwd(ctypes.byref(d), _stream()), 'groupnorm_bwd'),
@@ -580,3 +582,10 @@ def mse_loss_grad(a, b, grad_scale, da):
     _check(lib().b200_mse_loss_grad(a.data_ptr(), b.data_ptr(), _ptr(grad_scale), da.data_ptr(), a.numel(), _stream()),
            'mse_loss_grad')
     return da
+
+
+def time_embed_bwd(t, freqs, dim, E, cos_first, w1, b1, w2, emb, d_semb, y, pe, hid, demb, dpre, db1, db2, dclass):
+    _check(lib().b200_time_embed_bwd(t.data_ptr(), t.shape[0], freqs.data_ptr(), dim, E, int(cos_first), w1.data_ptr(),
+                                     b1.data_ptr(), w2.data_ptr(), emb.data_ptr(), d_semb.data_ptr(), _ptr(y),
+                                     pe.data_ptr(), hid.data_ptr(), demb.data_ptr(), dpre.data_ptr(), db1.data_ptr(),
+                                     db2.data_ptr(), _ptr(dclass), _stream()), 'time_embed_bwd')

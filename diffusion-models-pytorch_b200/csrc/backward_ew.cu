@@ -47,7 +47,7 @@ struct GnBwdParams {
   uint32_t drop_thresh; float drop_scale; unsigned long long drop_seed;
   float* sums;
   float* dx0; int acc0; float* dx1; int acc1; const float* addend;
-  __nv_bfloat16* dx_bf16; float* dx_rowsum;
+  __nv_bfloat16* dx_bf16; float* dx_rowsum; int rowsum_ld; float* dx_colsum;
   float* dgamma; float* dbeta; float* dscale; float* dshift; int dss_ld;
 };
 
@@ -264,14 +264,17 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
 #pragma unroll
       for (int i = 0; i < 4; ++i) rs[i] += dx[i];
     }
-    if (p.dx_rowsum) {
+    if (p.dx_rowsum || p.dx_colsum) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) atomicAdd(rsum + c + i, rs[i]);
     }
   }
-  if (p.dx_rowsum) {
+  if (p.dx_rowsum || p.dx_colsum) {
     __syncthreads();
-    for (int c = tid; c < C; c += 256) atomicAdd(p.dx_rowsum + (size_t)n * C + c, rsum[c]);
+    for (int c = tid; c < C; c += 256) {
+      if (p.dx_rowsum) atomicAdd(p.dx_rowsum + (size_t)n * p.rowsum_ld + c, rsum[c]);
+      if (p.dx_colsum) atomicAdd(p.dx_colsum + c, rsum[c]);
+    }
   }
 }
 
@@ -503,6 +506,65 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ o
     out[i] = dropout_keep(seed, (unsigned long long)i, thresh) ? 1.f : 0.f;
 }
 
+// ================================================================================================
+// Time-embedding MLP backward, per-row part (adjoint of time_embed_kernel in misc.cu): recomputes the sinusoid and the
+// hidden layer, and emits the bf16 operands of the two weight-gradient GEMMs:
+//   demb = d_semb o silu'(emb);  dhid = demb W2;  dpre = dhid o silu'(hid_pre)
+//   db2 += demb, db1 += dpre, dclass[y] += demb (atomics);  pe / hid / demb / dpre rows as bf16.
+// ================================================================================================
+__global__ void __launch_bounds__(256) time_embed_bwd_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                                             int dim, int E, int cos_first, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ emb, const float* __restrict__ d_semb,
+                                                             const int64_t* __restrict__ y, __nv_bfloat16* __restrict__ pe_o,
+                                                             __nv_bfloat16* __restrict__ hid_o, __nv_bfloat16* __restrict__ demb_o,
+                                                             __nv_bfloat16* __restrict__ dpre_o, float* __restrict__ db1,
+                                                             float* __restrict__ db2, float* __restrict__ dclass) {
+  extern __shared__ float tsm[];   // pe[dim] + hid_pre[E] + demb[E]
+  float* pe = tsm;
+  float* hpre = tsm + dim;
+  float* demb = hpre + E;
+  const int r = blockIdx.x;
+  const int half = dim >> 1;
+  const float tv = (float)t[r];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float a = tv * freqs[i];
+    const float s = sinf(a), c = cosf(a);
+    pe[i] = cos_first ? c : s;
+    pe[half + i] = cos_first ? s : c;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) pe_o[(size_t)r * dim + i] = __float2bfloat16_rn(pe[i]);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)e * dim);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < dim / 4; ++k) {
+      const float4 wv = __ldg(wr + k);
+      a0 += wv.x * pe[4 * k]; a1 += wv.y * pe[4 * k + 1]; a2 += wv.z * pe[4 * k + 2]; a3 += wv.w * pe[4 * k + 3];
+    }
+    const float v = (a0 + a1) + (a2 + a3) + b1[e];
+    hpre[e] = v;
+    hid_o[(size_t)r * E + e] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+    const float em = emb[(size_t)r * E + e];
+    const float sg = 1.0f / (1.0f + expf(-em));
+    const float de = d_semb[(size_t)r * E + e] * sg * (1.0f + em * (1.0f - sg));
+    demb[e] = de;
+    demb_o[(size_t)r * E + e] = __float2bfloat16_rn(de);
+    atomicAdd(db2 + e, de);
+    if (y && dclass) atomicAdd(dclass + (size_t)y[r] * E + e, de);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < E; k += blockDim.x) {   // dhid[k] = sum_e demb[e] w2[e][k]  (coalesced over k)
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(demb[e], __ldg(w2 + (size_t)e * E + k), acc);
+    const float v = hpre[k];
+    const float sg = 1.0f / (1.0f + expf(-v));
+    const float dp = acc * sg * (1.0f + v * (1.0f - sg));
+    dpre_o[(size_t)r * E + k] = __float2bfloat16_rn(dp);
+    atomicAdd(db1 + k, dp);
+  }
+}
+
 static inline int bw_grid(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148 * 16;
@@ -540,6 +602,7 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   p.sums = d->sums;
   p.dx0 = d->dx0; p.acc0 = d->dx0_accumulate; p.dx1 = d->dx1; p.acc1 = d->dx1_accumulate; p.addend = d->addend;
   p.dx_bf16 = reinterpret_cast<__nv_bfloat16*>(d->dx_bf16); p.dx_rowsum = d->dx_rowsum;
+  p.rowsum_ld = d->dx_rowsum_ld ? d->dx_rowsum_ld : C; p.dx_colsum = d->dx_colsum;
   p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dscale = d->dscale; p.dshift = d->dshift; p.dss_ld = d->dss_ld;
   int ppc = 32768 / C;
   if (ppc < 1) ppc = 1;
@@ -563,7 +626,12 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
 
 extern "C" int b200_cast_bf16_colsum(const float* x, void* out_bf16, float* colsum, long long rows, int C, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  B200_REQUIRE(x && out_bf16 && rows >= 1 && C >= 4 && C % 4 == 0 && C <= 8192, "cast_bf16_colsum: bad arguments");
+  B200_REQUIRE(x && out_bf16 && rows >= 1 && C >= 4 && C % 4 == 0 && C <= 32768, "cast_bf16_colsum: bad arguments");
+  static bool attr = false;
+  if (!attr) {
+    B200_CHECK(cudaFuncSetAttribute(cast_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr = true;
+  }
   int rpc = 32768 / C;
   if (rpc < 1) rpc = 1;
   const long long grid = (rows + rpc - 1) / rpc;
@@ -659,4 +727,22 @@ extern "C" int b200_dropout_mask(float* out, long long n, float p, unsigned long
   dropout_mask_kernel<<<bw_grid(n, 256), 256, 0, stream>>>(out, n, seed, dropout_threshold(p));
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "dropout_mask_kernel launch");
+}
+
+extern "C" int b200_time_embed_bwd(const int64_t* t, int rows, const float* freqs, int dim, int E, int cos_first,
+                                   const float* w1, const float* b1, const float* w2, const float* emb, const float* d_semb,
+                                   const int64_t* y, void* pe_bf16, void* hid_bf16, void* demb_bf16, void* dpre_bf16,
+                                   float* db1, float* db2, float* dclass, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(t && freqs && w1 && b1 && w2 && emb && d_semb && pe_bf16 && hid_bf16 && demb_bf16 && dpre_bf16 && db1 && db2,
+               "time_embed_bwd: null pointer");
+  B200_REQUIRE(dim % 8 == 0 && E % 4 == 0 && rows >= 1, "time_embed_bwd: dim must be a multiple of 8, E of 4");
+  const size_t smem = (size_t)(dim + 2 * E) * 4;
+  B200_REQUIRE(smem <= 48 * 1024, "time_embed_bwd: dim+2E too large");
+  time_embed_bwd_kernel<<<rows, 256, smem, stream>>>(
+      t, freqs, dim, E, cos_first, w1, b1, w2, emb, d_semb, y, reinterpret_cast<__nv_bfloat16*>(pe_bf16),
+      reinterpret_cast<__nv_bfloat16*>(hid_bf16), reinterpret_cast<__nv_bfloat16*>(demb_bf16),
+      reinterpret_cast<__nv_bfloat16*>(dpre_bf16), db1, db2, dclass);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "time_embed_bwd_kernel launch");
 }

@@ -325,7 +325,7 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(d && d->dy && d->x && d->dw, "conv2d_wgrad: null pointer");
   B200_REQUIRE(d->dy_C % 64 == 0 && d->x_C % 64 == 0, "conv2d_wgrad: channel counts (%d, %d) must be multiples of 64", d->dy_C, d->x_C);
-  B200_REQUIRE(d->Cout >= 1 && d->Cout <= d->dy_C && d->Cin >= 1 && d->Cin <= d->x_C, "conv2d_wgrad: bad Cout/Cin");
+  B200_REQUIRE(d->Cout >= 1 && d->dy_c0 >= 0 && d->dy_c0 + d->Cout <= d->dy_C && d->Cin >= 1 && d->Cin <= d->x_C, "conv2d_wgrad: bad Cout/Cin");
   B200_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "conv2d_wgrad: ntaps=%d out of range", d->ntaps);
   B200_REQUIRE(((uintptr_t)d->dy & 127) == 0 && ((uintptr_t)d->x & 127) == 0, "conv2d_wgrad: operand alignment");
   int bw = 1;
@@ -338,7 +338,7 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   memset(&p, 0, sizeof(p));
   p.conv = 1;
   p.a.mn_major = 1; p.b.mn_major = 1;
-  p.a.c_base = 0; p.b.c_base = d->x_c0;
+  p.a.c_base = d->dy_c0; p.b.c_base = d->x_c0;
   int BN = ((d->Cin + 63) / 64) * 64;
   if (BN > 256) BN = 256;
   p.BN = BN;

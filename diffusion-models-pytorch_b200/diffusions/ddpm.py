@@ -161,13 +161,11 @@ class DDPM:
         else:
             raise ValueError(f'Objective {self.objective} is not supported.')
         pred = model(xt, t, **model_kwargs)
-        mse = getattr(model, 'mse_loss', None)
-        if mse is None and hasattr(model, 'module'):
-            mse = getattr(model.module, 'mse_loss', None)
-        if mse is None:
-            raise RuntimeError('loss_func needs a b200diff model (models.unet.UNet / UNetCategorialAdaGN): '
-                               'the training step has no PyTorch fallback')
-        return mse(pred, target)
+        if not pred.is_cuda:
+            raise RuntimeError('loss_func needs a b200diff model on a CUDA device: the training step has no '
+                               'PyTorch fallback')
+        from models.backward import mse_loss
+        return mse_loss(pred, target)
 
     def get_v(self, x0: Tensor, eps: Tensor, t: Tensor):
         # v = sqrt(ac) eps - sqrt(1-ac) x0 == diffuse(eps, t, -x0)

@@ -223,7 +223,8 @@ class UNetModel(_EngineModel):
             return eng.resblock_core(name, h, skip, norm1=layer.in_layers[0], conv1=layer.in_layers[2],
                                      norm2=layer.out_layers[0], conv2=layer.out_layers[3], shortcut=sc, emb=emb,
                                      emb_off=offsets[name], emb_ld=emb_ld, scale_shift=layer.use_scale_shift_norm,
-                                     resample=layer.resample)
+                                     resample=layer.resample, dropout=layer.out_layers[2],
+                                     emb_linear=layer.emb_layers[1])
         assert skip is None
         if isinstance(layer, AttentionBlock):
             d = layer.channels // layer.num_heads
@@ -235,11 +236,10 @@ class UNetModel(_EngineModel):
             return eng.upsample_conv(name + '.conv', layer.conv, h) if layer.use_conv else eng.resample_plain(name, h, 2)
         raise RuntimeError(f'{name}: unexpected layer {type(layer).__name__}')
 
-    def forward(self, x, timesteps, y=None, out=None):
+    def _forward_impl(self, x, timesteps, y=None, out=None):
         """x: [N, C, H, W] fp32, timesteps: [N] int64, y: [N] int64 iff class-conditional (reference :653-682)."""
         assert (y is not None) == (self.num_classes is not None), \
             'must specify y if and only if the model is class-conditional'
-        self._reject_training()
         eng = self.engine
         eng.begin_forward()
         x = eng.check_input(x, timesteps, self.in_channels)
@@ -256,11 +256,7 @@ class UNetModel(_EngineModel):
                                 self.label_emb if self.num_classes is not None else None,
                                 [blk.emb_layers[1] for _, blk in res_blocks])
 
-        conv_in = self.input_blocks[0][0]
-        h0 = eng.buf('input_blocks.0.out', (B, H, W, conv_in.out_channels), torch.float32)
-        st0 = eng.stats_buf('input_blocks.0', B, conv_in.out_channels)
-        K.conv3x3_first(x, conv_in.weight, conv_in.bias, h0, st0)
-        h = Act(h0, B, H, W, conv_in.out_channels, st0)
+        h = eng.first_conv('input_blocks.0', self.input_blocks[0][0], x)
         hs = [h]
         for i, seq in list(enumerate(self.input_blocks))[1:]:
             for j, layer in enumerate(seq):
@@ -273,8 +269,4 @@ class UNetModel(_EngineModel):
             for j, layer in enumerate(seq):
                 h = self._run_layer(f'output_blocks.{i}.{j}', layer, h, skip if j == 0 else None, emb, emb_ld, offsets)
 
-        a, _ = eng.gn('out', h, None, self.out[0])
-        if out is None:
-            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=x.device)
-        eng.conv3x3('out.c', a, B, H, W, h.C, self.out[2], out_mode=K.OUT_F32_NCHW, out=out)
-        return out
+        return eng.head('out', h, self.out[0], self.out[2], out)

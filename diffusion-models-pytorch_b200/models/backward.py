@@ -1,0 +1,398 @@
+"""Backward pass of the engine-backed UNets: the hand-written adjoint of models/engine.py's forward.
+
+The reference trains through autograd (`loss.backward()` in scripts/train_ddpm.py:171-192 over models/unet.py).
+Here `UNetFunction` is ONE autograd node around the whole network: its forward runs the forward kernels in training
+mode (dropout on, every composite op appends a record to `engine.tape`), its backward replays the tape in reverse
+and issues only libb200diff kernels:
+  * conv data gradients  = the forward implicit-GEMM kernel (K1) on spatially flipped, channel-transposed weights;
+  * conv weight gradients = b200_conv2d_wgrad (tcgen05, contraction over pixels via MN-major TMA tiles), written
+    straight into the reference-layout (OIHW) gradient tensors;
+  * GroupNorm / AdaGN / SiLU / dropout / resample adjoints = b200_groupnorm_bwd (two streaming passes);
+  * attention adjoint = batched tcgen05 GEMMs (b200_gemm_batched) around the row-softmax kernels;
+  * embedding path adjoint = b200_time_embed_bwd + GEMMs.
+Gradients w.r.t. parameters are returned to autograd (so `.grad` accumulation, DDP hooks, torch optimizers and
+`clip_grad_norm_` behave exactly as with the reference); they are views into one flat fp32 buffer per backward.
+"""
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+import b200diff as K
+from models.engine import Act, Engine
+
+
+class UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, args, kwargs, *params):
+        eng = model.engine
+        eng.tape = []
+        eng._n_drop = 0
+        # one host-side draw from torch's CPU generator per forward: deterministic under torch.manual_seed
+        eng.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        try:
+            out = model._forward_impl(*args, **kwargs)
+            ctx.tape = eng.tape
+            eng.last_tape = eng.tape     # introspection (tests read the dropout seeds from it)
+        finally:
+            eng.tape = None
+        ctx.model = model
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = run_backward(ctx.model.engine, ctx.tape, dout.contiguous(), ctx.params)
+        ctx.tape = None
+        return (None, None, None) + tuple(grads)
+
+
+class MSELossFunction(torch.autograd.Function):
+    """F.mse_loss(pred, target) (mean reduction, diffusions/ddpm.py:136-138) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred, target = pred.contiguous(), target.contiguous().to(pred.dtype)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        K.mse_loss(pred, target, loss)
+        ctx.save_for_backward(pred, target)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        da = torch.empty_like(pred)
+        K.mse_loss_grad(pred, target, g.reshape(1).float().contiguous(), da)
+        return da, None
+
+
+def mse_loss(pred, target):
+    if pred.shape != target.shape:
+        raise RuntimeError(f'mse_loss: shape mismatch {tuple(pred.shape)} vs {tuple(target.shape)}')
+    return MSELossFunction.apply(pred, target)
+
+
+class _Grads:
+    """Per-parameter fp32 gradient views into one flat, zero-initialised buffer (the kernels accumulate)."""
+
+    def __init__(self, eng: Engine, params):
+        total = sum(p.numel() for p in params)
+        # a fresh buffer per backward: autograd may keep the returned views as the parameters' .grad
+        self.flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
+        self.views: Dict[int, torch.Tensor] = {}
+        off = 0
+        for p in params:
+            self.views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.params = params
+
+    def __call__(self, p):
+        return self.views[id(p)]
+
+    def as_tuple(self):
+        return [self.views[id(p)] if p.requires_grad else None for p in self.params]
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------
+def _grad_slot(eng: Engine, act: Act):
+    """(fp32 gradient buffer of `act`, accumulate?) -- the first contribution stores, later ones accumulate."""
+    if act.g is None:
+        act.g = eng.buf(('grad', act.t.data_ptr()), tuple(act.t.shape), torch.float32)
+        return act.g, False
+    return act.g, True
+
+
+def _w_dgrad(eng: Engine, tag, conv: nn.Conv2d):
+    """Packed weights of the data-gradient conv: spatially flipped taps, in/out channels swapped."""
+    return eng.packed(('dgrad', tag), lambda: K.pack_weight(conv.weight.detach().flip(2, 3).transpose(0, 1)))
+
+
+def _cast_out_grad(eng: Engine, tag, out: Act, bias_grad):
+    """fp32 gradient of a conv output -> bf16 tensor-core operand, bias gradient = its column sums."""
+    B, H, W, C = out.B, out.H, out.W, out.C
+    dob = eng.buf(tag + '.dOb', (B, H, W, C), torch.bfloat16)
+    K.cast_bf16_colsum(out.g, dob, bias_grad, B * H * W, C)
+    return dob
+
+
+def _sums(eng: Engine, B, C):
+    return eng.buf('gn_bwd_sums', (B, C, 2), torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# composite adjoints
+# ------------------------------------------------------------------------------------------------------
+def _res_bwd(eng: Engine, e, G: _Grads):
+    tag, x, skip, out = e['tag'], e['x'], e['skip'], e['out']
+    conv1, conv2, norm1, norm2, sc = e['conv1'], e['conv2'], e['norm1'], e['norm2'], e['shortcut']
+    B, H, W = x.B, x.H, x.W
+    Ho, Wo, Cout = out.H, out.W, out.C
+    Cin = x.C + (skip.C if skip is not None else 0)
+    resample = e['resample']
+    t3, t1 = K.taps_3x3_s1(), K.taps_1x1()
+    if out.g is None:
+        raise RuntimeError(f'{tag}: no gradient reached this block')
+
+    # conv2 (+ shortcut): bias, weights, data
+    dob = _cast_out_grad(eng, tag + '.c2', out, G(conv2.bias))
+    K.conv2d_wgrad(dob, Cout, e['a2'], (Cout, Ho, Wo, 1), B, Ho, Wo, Cout, Cout, t3[0], G(conv2.weight))
+    addend = None
+    if sc is not None:
+        G(sc.bias).copy_(G(conv2.bias))
+        k = sc.kernel_size[0]
+        K.conv2d_wgrad(dob, Cout, e['raw'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, (t1 if k == 1 else t3)[0],
+                       G(sc.weight))
+        addend = eng.buf(tag + '.dcat', (B, H, W, Cin), torch.float32)
+        K.conv2d(dob, _w_dgrad(eng, tag + '.sc', sc), Cin, B, H, W, t1 if k == 1 else t3, a0_geom=(Cout, H, W, 1),
+                 out=addend)
+    da2 = eng.buf(tag + '.dA2', (B, Ho, Wo, Cout), torch.bfloat16)
+    K.conv2d(dob, _w_dgrad(eng, tag + '.c2', conv2), Cout, B, Ho, Wo, t3, a0_geom=(Cout, Ho, Wo, 1), out=da2,
+             out_mode=K.OUT_BF16_NHWC)
+
+    # GroupNorm 2 (+ AdaGN, SiLU, dropout) -> dH; conv1 bias and embedding-projection gradients ride along
+    h = e['h']
+    dh = eng.buf(tag + '.dH', (B, Ho, Wo, Cout), torch.bfloat16)
+    emb, off, total = e['emb'], e['emb_off'], eng.d_emb.shape[1]
+    kw = {}
+    if e['scale_shift']:
+        kw = dict(scale=emb[:, off:], shift=emb[:, off + Cout:], ss_ld=e['emb_ld'], dscale=eng.d_emb[:, off:],
+                  dshift=eng.d_emb[:, off + Cout:], dss_ld=total)
+    else:
+        kw = dict(dx_rowsum=eng.d_emb[:, off:], dx_rowsum_ld=total)
+    K.groupnorm_bwd(da2, h.t, Cout, h.stats, None, 0, None, B, Ho * Wo, Wo, norm2.num_groups, norm2.weight, norm2.bias,
+                    norm2.eps, _sums(eng, B, Cout), silu=True, drop_p=e['drop_p'], drop_seed=e['drop_seed'], dx_bf16=dh,
+                    dx_colsum=G(conv1.bias), dgamma=G(norm2.weight), dbeta=G(norm2.bias), **kw)
+
+    # conv1: weights, data
+    K.conv2d_wgrad(dh, Cout, e['a1'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, t3[0], G(conv1.weight))
+    da1 = eng.buf(tag + '.dA1', (B, Ho, Wo, Cin), torch.bfloat16)
+    K.conv2d(dh, _w_dgrad(eng, tag + '.c1', conv1), Cin, B, Ho, Wo, t3, a0_geom=(Cout, Ho, Wo, 1), out=da1,
+             out_mode=K.OUT_BF16_NHWC)
+
+    # identity shortcut of a resampling block: the residual gradient reaches x through the resample adjoint
+    if sc is None and resample:
+        gx, acc = _grad_slot(eng, x)
+        if resample == 1:    # forward avg-pooled x: spread a quarter of the gradient over each 2x2 block
+            K.resample_f32(out.g, gx, B, Ho, Wo, Cout, 2, scale=0.25, accumulate=acc)
+        else:                # forward replicated x 2x2: sum the block
+            K.resample_f32(out.g, gx, B, Ho, Wo, Cout, 1, scale=4.0, accumulate=acc)
+    elif sc is None:
+        addend = out.g
+
+    # GroupNorm 1 (+ SiLU, resample) over cat(x, skip) -> gradients of x and of the skip connection
+    gx, accx = _grad_slot(eng, x)
+    gs, accs = _grad_slot(eng, skip) if skip is not None else (None, False)
+    K.groupnorm_bwd(da1, x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
+                    None if skip is None else skip.stats, B, H * W, W, norm1.num_groups, norm1.weight, norm1.bias,
+                    norm1.eps, _sums(eng, B, Cin), silu=True, resample=resample, dx0=gx, dx0_acc=accx, dx1=gs,
+                    dx1_acc=accs, addend=addend, dgamma=G(norm1.weight), dbeta=G(norm1.bias))
+
+
+def _attn_bwd(eng: Engine, e, G: _Grads):
+    tag, x, out, norm = e['tag'], e['x'], e['out'], e['norm']
+    q, k, v, proj = e['mods']
+    B, H, W, C = x.B, x.H, x.W, x.C
+    T, heads, scale = H * W, e['heads'], e['scale']
+    d = C // heads
+    t1 = K.taps_1x1()
+    qk, vt, o = e['qk'], e['vt'], e['o']
+    bf = torch.bfloat16
+
+    dob = _cast_out_grad(eng, tag + '.proj', out, G(proj.bias))
+    K.conv2d_wgrad(dob, C, o, (C, H, W, 1), B, H, W, C, C, t1[0], G(proj.weight))
+    do = eng.buf(tag + '.dO', (B, T, C), bf)
+    K.conv2d(dob, _w_dgrad(eng, tag + '.proj', proj), C, B, H, W, t1, a0_geom=(C, H, W, 1), out=do,
+             out_mode=K.OUT_BF16_NHWC)
+
+    # attention core: recompute P, then dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q
+    G_ = B * heads
+    S = eng.buf('attn_ws.S', (G_, T, T), torch.float32)
+    P = eng.buf('attn_ws.P', (G_, T, T), bf)
+    dP = eng.buf('attn_ws.dP', (G_, T, T), torch.float32)
+    dS = eng.buf('attn_ws.dS', (G_, T, T), bf)
+    qop = (qk, T, 2 * C, dict(col_base=0, col_head=d))
+    kop = (qk, T, 2 * C, dict(col_base=C, col_head=d))
+    grid = dict(batch=B, heads=heads)
+    sq = dict(out_ld=T, out_batch_stride=heads * T * T, out_head_stride=T * T)
+    K.gemm_batched(qop, kop, S, T, T, d, **grid, **sq)
+    K.softmax_rows(S, P, G_ * T, T, scale)
+    vop = (vt, d, T, dict(per_head_batch=True, mn_major=True))                 # [B*h][d][T]: rows = channel (K), cols = key
+    K.gemm_batched((do, T, C, dict(col_head=d)), vop, dP, T, T, d, **grid, **sq)
+    K.softmax_bwd_rows(P, dP, dS, G_ * T, T, scale)
+    dqk = eng.buf(tag + '.dqk', (B, T, 2 * C), bf)
+    dv = eng.buf(tag + '.dv', (B, T, C), bf)
+    dsop = (dS, T, T, dict(per_head_batch=True))
+    K.gemm_batched(dsop, (qk, T, 2 * C, dict(col_base=C, col_head=d, mn_major=True)), dqk, T, d, T, **grid,
+                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+    dsop_t = (dS, T, T, dict(per_head_batch=True, mn_major=True))
+    K.gemm_batched(dsop_t, (qk, T, 2 * C, dict(col_base=0, col_head=d, mn_major=True)), dqk[:, :, C:], T, d, T, **grid,
+                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+    K.gemm_batched((P, T, T, dict(per_head_batch=True, mn_major=True)), (do, T, C, dict(col_head=d, mn_major=True)), dv,
+                   T, d, T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
+
+    # q, k, v 1x1 convs: biases, weights, data (one GEMM over the concatenated [dq | dk | dv] channels)
+    n = e['n']
+    K.colsum_bf16(dqk, G(q.bias), B * T, 2 * C, 0, C)
+    K.colsum_bf16(dqk, G(k.bias), B * T, 2 * C, C, C)
+    K.colsum_bf16(dv, G(v.bias), B * T, C, 0, C)
+    K.conv2d_wgrad(dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(q.weight))
+    K.conv2d_wgrad(dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(k.weight), dy_c0=C)
+    K.conv2d_wgrad(dv, C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(v.weight))
+    wd = eng.packed(('dgrad', tag + '.qkv'), lambda: torch.cat(
+        [m.weight.detach().reshape(C, C).t() for m in (q, k, v)], dim=1).to(bf).contiguous())     # [C_in][3C]
+    dn = eng.buf(tag + '.dN', (B, H, W, C), bf)
+    K.conv2d(dqk, wd, C, B, H, W, t1, a0_geom=(2 * C, H, W, 1), a1=dv, a1_geom=(C, H, W, 1), out=dn,
+             out_mode=K.OUT_BF16_NHWC)
+
+    gx, acc = _grad_slot(eng, x)
+    K.groupnorm_bwd(dn, x.t, C, x.stats, None, 0, None, B, T, W, norm.num_groups, norm.weight, norm.bias, norm.eps,
+                    _sums(eng, B, C), silu=False, dx0=gx, dx0_acc=acc, addend=out.g, dgamma=G(norm.weight),
+                    dbeta=G(norm.bias))
+
+
+def _s2_dgrad_plan(conv: nn.Conv2d, pad_lo: int):
+    """Transposed 3x3 stride-2 conv as four 2x2-tap phase convolutions over dY (output pixel (2i+a, 2j+b)):
+    tap r contributes to parity a iff (a - r + pad_lo) is even, reading dY row i + (a - r + pad_lo) / 2."""
+    w = conv.weight.detach().float()            # [Cout, Cin, 3, 3]
+    co, ci = w.shape[0], w.shape[1]
+
+    def axis(a):
+        items = [(r, (a - r + pad_lo) // 2) for r in range(3) if (a - r + pad_lo) % 2 == 0]
+        return items + [(None, 0)] * (2 - len(items))
+    taps, mats = [], []
+    for a in range(2):
+        for b in range(2):
+            ph_taps, cols = [], []
+            for (r, dh) in axis(a):
+                for (s_, dw) in axis(b):
+                    ph_taps.append((dw, dh, 0))
+                    cols.append(torch.zeros(ci, co, device=w.device) if r is None or s_ is None
+                                else w[:, :, r, s_].t())
+            taps.append(ph_taps)
+            mats.append(torch.cat(cols, dim=1))           # [Cin][4*Cout]
+    return taps, torch.cat(mats, dim=0).to(torch.bfloat16).contiguous()
+
+
+def _down_bwd(eng: Engine, e, G: _Grads):
+    tag, x, out, conv = e['tag'], e['x'], e['out'], e['conv']
+    B, H, W, C = x.B, x.H, x.W, x.C
+    Ho, Wo, Cout = out.H, out.W, out.C
+    dob = _cast_out_grad(eng, tag, out, G(conv.bias))
+    K.conv2d_wgrad(dob, Cout, e['planes'], (C, Ho, Wo, 4), B, Ho, Wo, Cout, C, K.taps_3x3_s2(e['pad_lo'])[0],
+                   G(conv.weight))
+    taps, wd = eng.packed(('dgrad_s2', tag), lambda: _s2_dgrad_plan(conv, e['pad_lo']))
+    gx, acc = _grad_slot(eng, x)
+    K.conv2d(dob, wd, C, B, Ho, Wo, taps, a0_geom=(Cout, Ho, Wo, 1), out=gx, w_rows_per_phase=C,
+             residual=gx if acc else None, res_ld=C)
+
+
+def _up_bwd(eng: Engine, e, G: _Grads):
+    tag, x, out, conv = e['tag'], e['x'], e['out'], e['conv']
+    B, H, W, C = x.B, x.H, x.W, x.C
+    Ho, Wo, Cout = out.H, out.W, out.C
+    t3 = K.taps_3x3_s1()
+    dob = _cast_out_grad(eng, tag, out, G(conv.bias))
+    K.conv2d_wgrad(dob, Cout, e['ub'], (C, Ho, Wo, 1), B, Ho, Wo, Cout, C, t3[0], G(conv.weight))
+    du = eng.buf(tag + '.dU', (B, Ho, Wo, C), torch.float32)
+    K.conv2d(dob, _w_dgrad(eng, tag, conv), C, B, Ho, Wo, t3, a0_geom=(Cout, Ho, Wo, 1), out=du)
+    gx, acc = _grad_slot(eng, x)
+    K.resample_f32(du, gx, B, Ho, Wo, C, 1, scale=4.0, accumulate=acc)     # adjoint of nearest 2x = 2x2 sum
+
+
+def _head_bwd(eng: Engine, e, G: _Grads, dout):
+    tag, x, norm, conv = e['tag'], e['x'], e['norm'], e['conv']
+    B, H, W, C = x.B, x.H, x.W, x.C
+    Co = conv.out_channels
+    t3 = K.taps_3x3_s1()
+    dob = eng.buf(tag + '.dOb', (B, H, W, 64), torch.bfloat16)
+    K.nchw_to_nhwc_pad_bf16(dout, dob, G(conv.bias), B, Co, H * W, 64)
+    K.conv2d_wgrad(dob, 64, e['a'], (C, H, W, 1), B, H, W, Co, C, t3[0], G(conv.weight))
+
+    def make():   # data-gradient weights with the output channels zero-padded to the 64-channel operand
+        w = conv.weight.detach().flip(2, 3).transpose(0, 1)          # [C, Co, 3, 3]
+        wp = torch.zeros(C, 64, 3, 3, device=w.device, dtype=w.dtype)
+        wp[:, :Co] = w
+        return K.pack_weight(wp)
+    da = eng.buf(tag + '.dA', (B, H, W, C), torch.bfloat16)
+    K.conv2d(dob, eng.packed(('dgrad', tag), make), C, B, H, W, t3, a0_geom=(64, H, W, 1), out=da,
+             out_mode=K.OUT_BF16_NHWC)
+    gx, acc = _grad_slot(eng, x)
+    K.groupnorm_bwd(da, x.t, C, x.stats, None, 0, None, B, H * W, W, norm.num_groups, norm.weight, norm.bias, norm.eps,
+                    _sums(eng, B, C), silu=True, dx0=gx, dx0_acc=acc, dgamma=G(norm.weight), dbeta=G(norm.bias))
+
+
+def _first_bwd(eng: Engine, e, G: _Grads):
+    tag, X, out, conv = e['tag'], e['X'], e['out'], e['conv']
+    B, Ci, H, W = X.shape
+    Co = conv.out_channels
+    if out.g is None:
+        return
+    dob = _cast_out_grad(eng, tag, out, G(conv.bias))
+    xp = eng.buf(tag + '.xpad', (B, H, W, 64), torch.bfloat16)
+    K.nchw_to_nhwc_pad_bf16(X, xp, None, B, Ci, H * W, 64)
+    K.conv2d_wgrad(dob, Co, xp, (64, H, W, 1), B, H, W, Co, Ci, K.taps_3x3_s1()[0], G(conv.weight))
+
+
+def _embed_bwd(eng: Engine, e, G: _Grads):
+    rows, E, total = e['rows'], e['E'], e['total']
+    rp = (rows + 7) // 8 * 8
+    bf = torch.bfloat16
+    dev = eng.device
+    key = ('embed_bwd_ws', rp, total, E)
+    ws = eng._arena.get(key)
+    if ws is None:   # zero-initialised once: the padding rows (rows..rp) must stay zero
+        dim = e['pos_emb'].dim
+        ws = dict(dproj=torch.zeros(rp, total, dtype=bf, device=dev), pe=torch.zeros(rp, dim, dtype=bf, device=dev),
+                  hid=torch.zeros(rp, E, dtype=bf, device=dev), demb=torch.zeros(rp, E, dtype=bf, device=dev),
+                  dpre=torch.zeros(rp, E, dtype=bf, device=dev), semb=torch.zeros(rp, E, dtype=bf, device=dev),
+                  bias=torch.zeros(total, dtype=torch.float32, device=dev),
+                  dsemb=torch.zeros(rows, E, dtype=torch.float32, device=dev))
+        eng._arena[key] = ws
+    # per-block projections: proj = SiLU(emb) Wt^T + bt
+    ws['bias'].zero_()
+    K.cast_bf16_colsum(eng.d_emb, ws['dproj'], ws['bias'], rows, total)
+    ws['semb'][:rows].copy_(e['semb'])
+    off = 0
+    for lin in e['linears']:
+        n = lin.out_features
+        G(lin.bias).copy_(ws['bias'][off:off + n])
+        K.gemm_batched((ws['dproj'], rp, total, dict(col_base=off, mn_major=True)),
+                       (ws['semb'], rp, E, dict(mn_major=True)), G(lin.weight), n, E, rp, out_ld=E)
+        off += n
+    K.gemm_batched((ws['dproj'], rp, total), (e['w'], total, E, dict(mn_major=True)), ws['dsemb'], rows, E, total,
+                   out_ld=E)
+    # time MLP (+ class embedding)
+    lin1, lin2, ce = e['lin1'], e['lin2'], e['class_embed']
+    pos = e['pos_emb']
+    K.time_embed_bwd(e['t'], e['freqs'], pos.dim, E, bool(getattr(pos, 'cos_first', False)), lin1.weight, lin1.bias,
+                     lin2.weight, e['emb'], ws['dsemb'], e['y'], ws['pe'], ws['hid'], ws['demb'], ws['dpre'],
+                     G(lin1.bias), G(lin2.bias), None if ce is None else G(ce.weight))
+    K.gemm_batched((ws['demb'], rp, E, dict(mn_major=True)), (ws['hid'], rp, E, dict(mn_major=True)), G(lin2.weight),
+                   E, E, rp, out_ld=E)
+    K.gemm_batched((ws['dpre'], rp, E, dict(mn_major=True)), (ws['pe'], rp, pos.dim, dict(mn_major=True)),
+                   G(lin1.weight), E, pos.dim, rp, out_ld=pos.dim)
+
+
+_BWD = {'res': _res_bwd, 'attn': _attn_bwd, 'down': _down_bwd, 'up': _up_bwd, 'first': _first_bwd, 'embed': _embed_bwd}
+
+
+def run_backward(eng: Engine, tape, dout, params):
+    """Replays `tape` in reverse.  dout: fp32 NCHW gradient of the network output."""
+    if not dout.is_cuda or dout.dtype != torch.float32:
+        raise RuntimeError('backward: expected a float32 CUDA gradient')
+    G = _Grads(eng, params)
+    with torch.no_grad():
+        embed_rec = None
+        for e in reversed(tape):
+            kind = e['kind']
+            if kind == 'head':
+                _head_bwd(eng, e, G, dout)
+            elif kind == 'embed':
+                embed_rec = e        # recorded first, but its gradient is complete only after every block ran
+            else:
+                _BWD[kind](eng, e, G)
+        if embed_rec is not None:
+            _embed_bwd(eng, embed_rec, G)
+    return G.as_tuple()

@@ -22,11 +22,12 @@ import b200diff as K
 
 class Act:
     """fp32 NHWC activation [B, H, W, C]."""
-    __slots__ = ('t', 'B', 'H', 'W', 'C', 'stats')
+    __slots__ = ('t', 'B', 'H', 'W', 'C', 'stats', 'g')
 
     def __init__(self, t, B, H, W, C, stats=None):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.stats = stats   # [B, C, 2] per-(image, channel) sum / sum of squares from the producing kernel
+        self.g = None        # fp32 NHWC gradient buffer, created by the first backward contribution (models/backward.py)
 
 
 class Engine:
@@ -40,6 +41,9 @@ class Engine:
         self._sig = None
         self._arena: Dict = {}
         self._stats: Dict = {}
+        self.tape = None         # training forward: list of records replayed in reverse by models/backward.py
+        self.drop_seed = 0       # base seed of this forward's dropout masks
+        self._n_drop = 0
 
     # ------------------------------------------------------------------------------------------
     # buffers and packed weights
@@ -113,8 +117,12 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # ops
     # ------------------------------------------------------------------------------------------
+    def next_drop_seed(self):
+        self._n_drop += 1
+        return (self.drop_seed + 0x9E3779B97F4A7C15 * self._n_drop) & 0x7FFFFFFFFFFFFFFF
+
     def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
-           ss_ld=0, resample=0):
+           ss_ld=0, resample=0, drop_p=0.0, drop_seed=0):
         C = x.C + (skip.C if skip is not None else 0)
         Ho, Wo = x.H, x.W
         if resample == 1:
@@ -127,8 +135,11 @@ class Engine:
             K.groupnorm_apply(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
                               None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
                               norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift, ss_ld=ss_ld, silu=silu,
-                              resample=resample, raw_out=raw_out)
+                              resample=resample, raw_out=raw_out, drop_p=drop_p, drop_seed=drop_seed)
         else:
+            if drop_p > 0 or self.tape is not None:
+                raise RuntimeError(f'{tag}: training needs producer statistics for every GroupNorm input '
+                                   '(parameter-free resampling layers are inference-only)')
             K.groupnorm_silu(x.t, x.C, None if skip is None else skip.t, 0 if skip is None else skip.C, x.B,
                              x.H * x.W, x.W, norm.num_groups, norm.weight, norm.bias, norm.eps, out, scale=scale,
                              shift=shift, ss_ld=ss_ld, silu=silu, resample=resample, raw_out=raw_out)
@@ -158,9 +169,10 @@ class Engine:
             bqk = torch.cat([blk.q.bias.detach(), blk.k.bias.detach()]).float().contiguous()
             return (wqk, bqk, K.pack_weight(blk.v.weight), blk.v.bias.detach().float().contiguous(),
                     K.pack_weight(blk.proj.weight), blk.proj.bias.detach().float().contiguous())
-        return self.attention_core(tag, x, blk.norm, self.packed(('attn', tag), make), blk.n_heads, blk.scale)
+        return self.attention_core(tag, x, blk.norm, self.packed(('attn', tag), make), blk.n_heads, blk.scale,
+                                   mods=(blk.q, blk.k, blk.v, blk.proj))
 
-    def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float) -> Act:
+    def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:
         """GroupNorm -> [q|k] and v^T 1x1 convs -> fused softmax(q k^T * scale) v -> 1x1 proj + residual.
         `weights` = (Wqk [2C, C] bf16 with rows [q heads..., k heads...], bqk, Wv [C, C], bv, Wproj, bproj)."""
         B, H, W, C = x.B, x.H, x.W, x.C
@@ -183,7 +195,13 @@ class Engine:
         stats = self.stats_buf(tag, B, C)
         K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
                  stats=stats)
-        return Act(out, B, H, W, C, stats)
+        res = Act(out, B, H, W, C, stats)
+        if self.tape is not None:
+            if mods is None:
+                raise RuntimeError(f'{tag}: training through a fused-qkv attention block is not implemented')
+            self.tape.append(dict(kind='attn', tag=tag, x=x, out=res, norm=norm, n=n, qk=qk, vt=vt, o=o, heads=heads,
+                                  scale=scale, mods=mods))
+        return res
 
     def downsample_conv(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
         B, H, W, C = x.B, x.H, x.W, x.C
@@ -195,11 +213,22 @@ class Engine:
         stats = self.stats_buf(tag, B, Cout)
         K.conv2d(planes, w, Cout, B, H // 2, W // 2, K.taps_3x3_s2(pad_lo), a0_geom=(C, H // 2, W // 2, 4), bias=b,
                  out=out, stats=stats)
-        return Act(out, B, H // 2, W // 2, Cout, stats)
+        res = Act(out, B, H // 2, W // 2, Cout, stats)
+        if self.tape is not None:
+            self.tape.append(dict(kind='down', tag=tag, x=x, out=res, conv=conv, planes=planes, pad_lo=pad_lo))
+        return res
 
     def upsample_conv(self, tag, conv: nn.Conv2d, x: Act) -> Act:
         """nearest-2x + conv3x3 as four 2x2-tap phase convolutions on the low-res grid (2.25x fewer MACs)."""
         B, H, W, C = x.B, x.H, x.W, x.C
+        if self.tape is not None:
+            # training: materialise the nearest-2x tensor and run the plain 3x3 conv, whose adjoints are the standard
+            # dgrad / wgrad kernels (the 4-phase form would need phase-wise weight-gradient folding)
+            ub = self.buf(tag + '.up', (B, 2 * H, 2 * W, C), torch.bfloat16)
+            K.upsample2_bf16(x.t, ub, B, H, W, C)
+            res = self.conv3x3(tag, ub, B, 2 * H, 2 * W, C, conv)
+            self.tape.append(dict(kind='up', tag=tag, x=x, out=res, conv=conv, ub=ub))
+            return res
         xb = self.buf(tag + '.bf16', (B, H, W, C), torch.bfloat16)
         K.cast_bf16(x.t, xb, B, H, W, C)
         w, b = self.w_up2(tag, conv)
@@ -221,7 +250,8 @@ class Engine:
         return Act(r, B, Ho, Wo, C)
 
     def resblock_core(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
-                      emb_ld, scale_shift: bool, resample: int = 0) -> Act:
+                      emb_ld, scale_shift: bool, resample: int = 0, dropout: Optional[nn.Dropout] = None,
+                      emb_linear: Optional[nn.Linear] = None) -> Act:
         """The ResBlock shared by all UNet families:
             h = conv1(resample(SiLU(GN1(cat(x, skip)))))            (+ emb row when not scale_shift)
             h = conv2(SiLU(GN2(h) [* (1 + scale) + shift]))          (dropout = identity in eval mode)
@@ -246,28 +276,39 @@ class Engine:
             r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
             (K.avgpool2_f32 if resample == 1 else K.upsample2_f32)(x.t, r, B, H, W, x.C)
             res_x = Act(r, B, Ho, Wo, x.C)
+        drop_p, drop_seed = 0.0, 0
+        if self.tape is not None and dropout is not None and dropout.p > 0 and self.model.training:
+            drop_p, drop_seed = float(dropout.p), self.next_drop_seed()
         if scale_shift:
             h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, intermediate=True)
             a2, _ = self.gn(tag + '.2', h, None, norm2, scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:],
-                            ss_ld=emb_ld)
+                            ss_ld=emb_ld, drop_p=drop_p, drop_seed=drop_seed)
         else:
             h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, rowadd=emb[:, emb_off:], rowadd_ld=emb_ld,
                              intermediate=True)
-            a2, _ = self.gn(tag + '.2', h, None, norm2)
+            a2, _ = self.gn(tag + '.2', h, None, norm2, drop_p=drop_p, drop_seed=drop_seed)
         if sc1x1:
-            return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=shortcut)
-        if sc3x3:
-            res_x = self.conv3x3(tag + '.sc', raw, B, Ho, Wo, Cin, shortcut)
+            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=shortcut)
         else:
-            assert skip is None and Cin == Cout
-        return self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
+            if sc3x3:
+                res_x = self.conv3x3(tag + '.sc', raw, B, Ho, Wo, Cin, shortcut)
+            else:
+                assert skip is None and Cin == Cout
+            out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
+        if self.tape is not None:
+            self.tape.append(dict(kind='res', tag=tag, x=x, skip=skip, out=out, a1=a1, raw=raw, h=h, a2=a2, norm1=norm1,
+                                  conv1=conv1, norm2=norm2, conv2=conv2, shortcut=shortcut, emb=emb, emb_off=emb_off,
+                                  emb_ld=emb_ld, scale_shift=scale_shift, resample=resample, drop_p=drop_p,
+                                  drop_seed=drop_seed, emb_linear=emb_linear))
+        return out
 
     def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
         """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
         return self.resblock_core(tag, x, skip, norm1=blk.blk1[0], conv1=blk.blk1[2], norm2=blk.blk2[0],
                                   conv2=blk.blk2[3],
                                   shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
-                                  emb=tproj, emb_off=tproj_off, emb_ld=tproj_ld, scale_shift=False)
+                                  emb=tproj, emb_off=tproj_off, emb_ld=tproj_ld, scale_shift=False, dropout=blk.blk2[2],
+                                  emb_linear=blk.proj[1])
 
     def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
         """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""
@@ -275,7 +316,8 @@ class Engine:
                                   conv2=blk.blk2[2],
                                   shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
                                   emb=ss, emb_off=ss_off, emb_ld=ss_ld, scale_shift=True,
-                                  resample={'up': 2, 'down': 1}.get(blk.updown_kind, 0))
+                                  resample={'up': 2, 'down': 1}.get(blk.updown_kind, 0), dropout=blk.blk2[1],
+                                  emb_linear=blk.adagn.proj[1])
 
     # ------------------------------------------------------------------------------------------
     # embedding path
@@ -283,7 +325,8 @@ class Engine:
     def embed(self, T, y, B, pos_emb, lin1, lin2, class_embed, proj_linears):
         """Returns (proj [rows, sum_out] fp32, ld) where ld = 0 when one row serves the whole batch."""
         dev = self.device
-        uniform = (T.dim() == 1 and T.shape[0] == B and (B == 1 or T.stride(0) == 0))
+        # one embedding row serves the whole batch when t is a stride-0 expand (sampling); training keeps per-sample rows
+        uniform = (T.dim() == 1 and T.shape[0] == B and (B == 1 or T.stride(0) == 0)) and self.tape is None
         use_y = class_embed is not None and y is not None
         rows = 1 if (uniform and not use_y) else B
         t_rows = (T[:1] if uniform and rows == 1 else T).to(torch.long).contiguous()
@@ -300,7 +343,34 @@ class Engine:
         total = w.shape[0]
         proj = self.buf('tproj', (rows, total), torch.float32)
         K.conv2d(semb, w, total, rows, 1, 1, K.taps_1x1(), a0_geom=(E, 1, 1, 1), bias=b, out=proj)
-        return proj, (0 if rows == 1 else total)
+        if self.tape is not None:
+            self.tape.append(dict(kind='embed', t=t_rows, y=y if use_y else None, rows=rows, E=E, total=total,
+                                  pos_emb=pos_emb, freqs=freqs, lin1=lin1, lin2=lin2, class_embed=class_embed if use_y else None,
+                                  linears=proj_linears, emb=emb, semb=semb, w=w))
+            self.d_emb = self.buf('d_tproj', (rows, total), torch.float32)
+            self.d_emb.zero_()
+        return proj, (0 if rows == 1 and self.tape is None else total)
+
+    def first_conv(self, tag, conv: nn.Conv2d, X) -> Act:
+        """The Cin <= 4 input convolution (models/unet.py:72,123): NCHW fp32 image -> fp32 NHWC residual stream."""
+        B, _, H, W = X.shape
+        h0 = self.buf(tag + '.out', (B, H, W, conv.out_channels), torch.float32)
+        st0 = self.stats_buf(tag, B, conv.out_channels)
+        K.conv3x3_first(X, conv.weight, conv.bias, h0, st0)
+        res = Act(h0, B, H, W, conv.out_channels, st0)
+        if self.tape is not None:
+            self.tape.append(dict(kind='first', tag=tag, X=X, out=res, conv=conv))
+        return res
+
+    def head(self, tag, h: Act, norm: nn.GroupNorm, conv: nn.Conv2d, out):
+        """GroupNorm -> SiLU -> 3x3 conv to the few output channels, written as the reference's NCHW fp32."""
+        a, _ = self.gn(tag, h, None, norm)
+        if out is None:
+            out = torch.empty((h.B, conv.out_channels, h.H, h.W), dtype=torch.float32, device=h.t.device)
+        self.conv3x3(tag + '.c', a, h.B, h.H, h.W, h.C, conv, out_mode=K.OUT_F32_NCHW, out=out)
+        if self.tape is not None:
+            self.tape.append(dict(kind='head', tag=tag, x=h, a=a, norm=norm, conv=conv))
+        return out
 
     @staticmethod
     def check_input(X, T, in_channels):

@@ -147,10 +147,9 @@ class Model(_EngineModel):
             blocks += [(f'up.{i}.block.{j}', b) for j, b in enumerate(lvl.block)]
         return blocks
 
-    def forward(self, x, t, out=None):
+    def _forward_impl(self, x, t, out=None):
         """x: [B, C, R, R] fp32, t: [B] int64 -> [B, out_ch, R, R] fp32 (reference :286-327)."""
         assert x.shape[2] == x.shape[3] == self.resolution
-        self._reject_training()
         eng = self.engine
         eng.begin_forward()
         x = eng.check_input(x, t, self.in_channels)
@@ -168,16 +167,13 @@ class Model(_EngineModel):
         def run_res(name, blk, h, skip=None):
             return eng.resblock_core(name, h, skip, norm1=blk.norm1, conv1=blk.conv1, norm2=blk.norm2, conv2=blk.conv2,
                                      shortcut=blk.shortcut_conv(), emb=tproj, emb_off=offsets[name], emb_ld=tld,
-                                     scale_shift=False)
+                                     scale_shift=False, dropout=blk.dropout, emb_linear=blk.temb_proj)
 
         def run_attn(name, blk, h):
             return eng.attention_core(name, h, blk.norm, eng.packed(('attn', name), blk.packed_weights), 1,
-                                      float(int(blk.in_channels) ** (-0.5)))
+                                      float(int(blk.in_channels) ** (-0.5)), mods=(blk.q, blk.k, blk.v, blk.proj_out))
 
-        h0 = eng.buf('conv_in.out', (B, H, W, self.ch), torch.float32)
-        st0 = eng.stats_buf('conv_in', B, self.ch)
-        K.conv3x3_first(x, self.conv_in.weight, self.conv_in.bias, h0, st0)
-        hs = [Act(h0, B, H, W, self.ch, st0)]
+        hs = [eng.first_conv('conv_in', self.conv_in, x)]
         for i, lvl in enumerate(self.down):
             for j in range(self.num_res_blocks):
                 h = run_res(f'down.{i}.block.{j}', lvl.block[j], hs[-1])
@@ -204,8 +200,4 @@ class Model(_EngineModel):
                 h = eng.upsample_conv(f'up.{i}.upsample.conv', us.conv, h) if us.with_conv \
                     else eng.resample_plain(f'up.{i}.upsample', h, 2)
 
-        a, _ = eng.gn('norm_out', h, None, self.norm_out)
-        if out is None:
-            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=x.device)
-        eng.conv3x3('conv_out', a, B, H, W, h.C, self.conv_out, out_mode=K.OUT_F32_NCHW, out=out)
-        return out
+        return eng.head('norm_out', h, self.norm_out, self.conv_out, out)

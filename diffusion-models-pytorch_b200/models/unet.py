@@ -54,12 +54,14 @@ class _EngineModel(nn.Module):
             self.__dict__['_runners'][key] = r
         return r
 
-    def _reject_training(self):
-        if self.training and torch.is_grad_enabled():
-            has_dropout = any(isinstance(m, nn.Dropout) and m.p > 0 for m in self.modules())
-            raise RuntimeError('b200diff UNet: the training step (backward kernels' +
-                               (', dropout' if has_dropout else '') + ') is not implemented yet; call model.eval() '
-                               'and run under torch.no_grad() for sampling')
+    def forward(self, *args, **kwargs):
+        """Inference: launches the forward kernels.  Training (module in train mode, grad enabled): the same forward
+        with dropout and a tape, wrapped in an autograd node whose backward runs the hand-written adjoint kernels
+        (models/backward.py) -- autograd itself never sees the network's interior."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from models.backward import UNetFunction
+            return UNetFunction.apply(self, args, kwargs, *list(self.parameters()))
+        return self._forward_impl(*args, **kwargs)
 
 
 class UNet(_EngineModel):
@@ -129,9 +131,8 @@ class UNet(_EngineModel):
         blocks += [(f'up_blocks.{i}.{j}', b) for i, st in enumerate(self.up_blocks) for j, b in enumerate(st)]
         return [(n, b) for n, b in blocks if isinstance(b, ResBlock)]
 
-    def forward(self, X: Tensor, T: Tensor, out: Tensor = None):
+    def _forward_impl(self, X: Tensor, T: Tensor, out: Tensor = None):
         """X: [B, C, H, W] fp32 (NCHW), T: [B] int64 -> [B, C_out, H, W] fp32.  (reference unet.py:121-152)"""
-        self._reject_training()
         eng = self.engine
         eng.begin_forward()
         X = eng.check_input(X, T, self.in_channels)
@@ -145,10 +146,7 @@ class UNet(_EngineModel):
         tproj, tld = eng.embed(T, None, B, self.time_embed[0], self.time_embed[1], self.time_embed[3], None,
                                [blk.proj[1] for _, blk in res_blocks])
 
-        h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
-        st0 = eng.stats_buf('first_conv', B, self.first_conv.out_channels)
-        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0, st0)
-        h = Act(h0, B, H, W, self.first_conv.out_channels, st0)
+        h = eng.first_conv('first_conv', self.first_conv, X)
         skips = [h]
 
         def run_res(name, blk, x, skip=None):
@@ -181,8 +179,4 @@ class UNet(_EngineModel):
                 else:
                     h = eng.upsample_conv(name, blk[1], h)
 
-        a, _ = eng.gn('last_conv', h, None, self.last_conv[0])
-        if out is None:
-            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=X.device)
-        eng.conv3x3('last_conv.c', a, B, H, W, h.C, self.last_conv[2], out_mode=K.OUT_F32_NCHW, out=out)
-        return out
+        return eng.head('last_conv', h, self.last_conv[0], self.last_conv[2], out)

@@ -120,9 +120,8 @@ class UNetCategorialAdaGN(_EngineModel):
         blocks += [(f'up_blocks.{i}.{j}', b) for i, st in enumerate(self.up_blocks) for j, b in enumerate(st)]
         return [(n, b) for n, b in blocks if isinstance(b, ResBlock)]
 
-    def forward(self, X: Tensor, T: Tensor, y: Tensor = None, out: Tensor = None):
+    def _forward_impl(self, X: Tensor, T: Tensor, y: Tensor = None, out: Tensor = None):
         """X: [B, C, H, W] fp32, T: [B] int64, y: [B] int64 labels or None -> [B, C_out, H, W] fp32."""
-        self._reject_training()
         eng = self.engine
         eng.begin_forward()
         X = eng.check_input(X, T, self.in_channels)
@@ -136,10 +135,7 @@ class UNetCategorialAdaGN(_EngineModel):
         ss, ss_ld = eng.embed(T, y, B, self.time_embed[0], self.time_embed[1], self.time_embed[3], self.class_embed,
                               [blk.adagn.proj[1] for _, blk in res_blocks])
 
-        h0 = eng.buf('first_conv.out', (B, H, W, self.first_conv.out_channels), torch.float32)
-        st0 = eng.stats_buf('first_conv', B, self.first_conv.out_channels)
-        K.conv3x3_first(X, self.first_conv.weight, self.first_conv.bias, h0, st0)
-        h = Act(h0, B, H, W, self.first_conv.out_channels, st0)
+        h = eng.first_conv('first_conv', self.first_conv, X)
         skips = [h]
 
         def run_res(name, blk, x, skip=None):
@@ -174,8 +170,4 @@ class UNetCategorialAdaGN(_EngineModel):
                 else:
                     h = eng.upsample_conv(name, blk[1], h)
 
-        a, _ = eng.gn('last_conv', h, None, self.last_conv[0])
-        if out is None:
-            out = torch.empty((B, self.out_channels, H, W), dtype=torch.float32, device=X.device)
-        eng.conv3x3('last_conv.c', a, B, H, W, h.C, self.last_conv[2], out_mode=K.OUT_F32_NCHW, out=out)
-        return out
+        return eng.head('last_conv', h, self.last_conv[0], self.last_conv[2], out)

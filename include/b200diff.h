@@ -228,7 +228,7 @@ int b200_gemm_batched(const b200_gemm_desc* d, void* stream);
  * .grad tensor (dw_co_stride = Cin_total*kh*kw, dw_ci_stride = kh*kw, dw_tap_stride = 1) -- and always ACCUMULATES
  * (split over pixel ranges with atomics), like autograd's .grad accumulation. */
 typedef struct b200_wgrad_desc {
-  const void* dy; int dy_C;
+  const void* dy; int dy_C, dy_c0;   /* the Cout gradient channels start at channel dy_c0 of dy */
   const void* x; int x_C, x_H, x_W, x_planes, x_c0;
   int B, Ho, Wo;
   int Cout, Cin;
@@ -254,7 +254,7 @@ int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed,
  * g: bf16 gradient w.r.t. the K3 output [B][HW_out][C0+C1]; x0/x1/stats*: the forward's inputs and statistics.
  * Outputs: dx as fp32 split over the two sources (store or accumulate each; optional fp32 addend [B][HW][C] folded
  * in, e.g. the residual branch's gradient), or as one bf16 tensor (+ optional per-(image, channel) sums of dx in
- * dx_rowsum [B][C], accumulated: the bias / time-embedding-row gradients of the producing conv);
+ * dx_rowsum, accumulated: the time-embedding-row gradient of the producing conv; dx_colsum: its bias gradient);
  * dgamma/dbeta [C] accumulate; dscale/dshift [B][dss_ld] are written. sums: workspace [B][C][2]. */
 typedef struct b200_gn_bwd_desc {
   const void* g;
@@ -270,7 +270,8 @@ typedef struct b200_gn_bwd_desc {
   float* dx1; int dx1_accumulate;
   const float* addend;
   void* dx_bf16;
-  float* dx_rowsum;
+  float* dx_rowsum; int dx_rowsum_ld;   /* [B][dx_rowsum_ld] (0 = C), accumulated */
+  float* dx_colsum;                     /* [C], accumulated: sum of dx over images and pixels */
   float* dgamma; float* dbeta;
   float* dscale; float* dshift; int dss_ld;
 } b200_gn_bwd_desc;
@@ -291,6 +292,14 @@ int b200_upsample2_bf16(const float* x, void* out_bf16, int B, int H, int W, int
  * P = softmax(scale * S) as bf16; dS = scale * P o (dP - rowsum(dP o P)) as bf16.  S, dP fp32 [rows][T]. */
 int b200_softmax_rows(const float* S, void* P_bf16, long long rows, int T, float scale, void* stream);
 int b200_softmax_bwd_rows(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, float scale, void* stream);
+
+/* Adjoint of b200_time_embed, per-row part: given d_semb = dL/d SiLU(emb) (fp32 [rows][E]) and the forward's emb, it
+ * accumulates db1, db2 and the class-embedding rows (atomics) and writes the bf16 operands pe [rows][dim],
+ * hid / demb / dpre [rows][E] of the weight-gradient GEMMs dW2 = demb^T hid, dW1 = dpre^T pe (b200_gemm_batched). */
+int b200_time_embed_bwd(const int64_t* t, int rows, const float* freqs, int dim, int E, int cos_first, const float* w1,
+                        const float* b1, const float* w2, const float* emb, const float* d_semb, const int64_t* y,
+                        void* pe_bf16, void* hid_bf16, void* demb_bf16, void* dpre_bf16, float* db1, float* db2,
+                        float* dclass, void* stream);
 
 /* F.mse_loss(a, b) (mean) into loss[0], and its gradient da = grad_scale[0] * 2 (a - b) / n (diffusions/ddpm.py:136-138);
  * grad_scale is a device scalar (the incoming dL/dloss) or NULL for 1. */

@@ -49,16 +49,24 @@ def attention_block(sd, p, x, n_heads):
     return _conv(sd, p + '.proj', o) + x
 
 
-def resblock(sd, p, x, emb):
-    """models/unet.py:30-43 (dropout is the identity in eval mode)."""
+def _drop(h, drop, p):
+    """Training-mode nn.Dropout with an injected keep mask: drop = {block prefix: (mask NCHW, probability)}."""
+    if drop is None or p not in drop:
+        return h
+    mask, prob = drop[p]
+    return h * mask / (1.0 - prob)
+
+
+def resblock(sd, p, x, emb, drop=None):
+    """models/unet.py:30-43 (dropout is the identity in eval mode; in training mode the mask is injected)."""
     h = _conv(sd, p + '.blk1.2', F.silu(_gn(sd, p + '.blk1.0', x)), padding=1)
     h = h + F.linear(F.silu(emb), sd[p + '.proj.1.weight'], sd[p + '.proj.1.bias'])[:, :, None, None]
-    h = _conv(sd, p + '.blk2.3', F.silu(_gn(sd, p + '.blk2.0', h)), padding=1)
+    h = _conv(sd, p + '.blk2.3', _drop(F.silu(_gn(sd, p + '.blk2.0', h)), drop, p), padding=1)
     sc = _conv(sd, p + '.shortcut', x) if (p + '.shortcut.weight') in sd else x
     return h + sc
 
 
-def resblock_adagn(sd, p, x, emb, updown=None):
+def resblock_adagn(sd, p, x, emb, updown=None, drop=None):
     """models/unet_categorial_adagn.py:44-62."""
     h = F.silu(_gn(sd, p + '.blk1.0', x))
     if updown == 'up':
@@ -71,7 +79,7 @@ def resblock_adagn(sd, p, x, emb, updown=None):
     ss = F.linear(F.silu(emb), sd[p + '.adagn.proj.1.weight'], sd[p + '.adagn.proj.1.bias'])
     ys, yb = torch.chunk(ss, 2, dim=-1)
     h = _gn(sd, p + '.adagn.gn', h) * (1 + ys[:, :, None, None]) + yb[:, :, None, None]
-    h = _conv(sd, p + '.blk2.2', F.silu(h), padding=1)
+    h = _conv(sd, p + '.blk2.2', _drop(F.silu(h), drop, p), padding=1)
     sc = _conv(sd, p + '.shortcut', x) if (p + '.shortcut.weight') in sd else x
     return h + sc
 
@@ -89,7 +97,7 @@ def _kind(sd, p):
 
 
 def unet_forward(sd, x, t, *, dim, n_heads=1, y=None, adagn=False, attn_head_dims=64, num_res_blocks=2,
-                 trace=None):
+                 trace=None, drop=None):
     """Forward of models.unet.UNet (adagn=False) or UNetCategorialAdaGN (adagn=True) from a state_dict.
 
     The block structure is recovered from the key names; `num_res_blocks` is only needed to tell the
@@ -105,7 +113,7 @@ def unet_forward(sd, x, t, *, dim, n_heads=1, y=None, adagn=False, attn_head_dim
         return C // attn_head_dims
 
     def rb(p, h, updown=None):
-        return resblock_adagn(sd, p, h, emb, updown) if adagn else resblock(sd, p, h, emb)
+        return resblock_adagn(sd, p, h, emb, updown, drop) if adagn else resblock(sd, p, h, emb, drop)
 
     h = _conv(sd, 'first_conv', x, padding=1)
     skips = [h]

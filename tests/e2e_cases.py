@@ -304,6 +304,85 @@ def case_pesser256():
     return ok and psnr >= 40.0
 
 
+def _train_parity(name, model, oracle_kw, x0, t, eps, y=None, gate=3e-2):
+    """One noise-prediction training step (diffusions/ddpm.py:122-138 + loss.backward()): loss and every parameter
+    gradient of the kernel path against fp32 autograd over the oracle, with the SAME dropout masks (regenerated from the
+    seeds the forward used)."""
+    import torch.nn.functional as F
+    import b200diff as K
+    from oracle.unet_ref import unet_forward
+    model.train()
+    d = diffusions.DDPM(total_steps=1000, device=DEV)
+    orc = R.DDPMRef(total_steps=1000)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    kw = {} if y is None else dict(y=y)
+    for p in model.parameters():
+        p.grad = None
+    torch.manual_seed(123)
+    loss = d.loss_func(model, x0, t, eps=eps, model_kwargs=kw)
+    loss.backward()
+    drop = {}
+    for rec in model.engine.last_tape:
+        if rec['kind'] == 'res' and rec['drop_p'] > 0:
+            o = rec['out']
+            m = K.dropout_mask(torch.empty(o.B, o.H, o.W, o.C, device=DEV), rec['drop_p'], rec['drop_seed'])
+            drop[rec['tag']] = (m.permute(0, 3, 1, 2), rec['drop_p'])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xt = orc.diffuse(x0, t, eps)
+    pred = unet_forward(sd, xt, t, y=y, drop=drop, **oracle_kw)
+    loss_ref = F.mse_loss(pred, eps)
+    loss_ref.backward()
+    num = den = 0.0
+    worst, worst_name = 0.0, ''
+    finite = True
+    for k, p in model.named_parameters():
+        g, r = p.grad, sd[k].grad
+        if r is None:            # parameter unused by this call (class embedding when y is None)
+            r = torch.zeros_like(g)
+        finite &= bool(torch.isfinite(g).all())
+        e2, r2 = float((g - r).pow(2).sum()), float(r.pow(2).sum())
+        num += e2
+        den += r2
+        rel = (e2 / max(r2, 1e-30)) ** 0.5
+        if r.numel() >= 1024 and rel > worst:
+            worst, worst_name = rel, k
+    rel_all = (num / den) ** 0.5
+    lerr = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    ok = finite and rel_all <= gate and worst <= 3 * gate and lerr <= 5e-3
+    _emit(case=f'train step {name}', loss=loss.item(), loss_ref=loss_ref.item(), loss_rel_err=lerr,
+          grad_rel_l2_all=rel_all, worst_tensor=worst_name, worst_tensor_rel_l2=worst, gate=gate,
+          n_dropout_blocks=len(drop), ok=ok)
+    return ok
+
+
+def case_train_step():
+    """Backward kernels: plain UNet (MNIST width, CIFAR-10 width) and the AdaGN / CFG UNet, dropout 0.1 active."""
+    _no_tf32()
+    ok = True
+    for name, cfg, B in (('mnist-width UNet B=8', MNIST, 8), ('cifar10 UNet B=4', CIFAR, 4)):
+        torch.manual_seed(2022)
+        m = models.UNet(**cfg).to(DEV)
+        g = torch.Generator(device='cpu').manual_seed(3)
+        x0 = torch.randn(B, cfg['in_channels'], 32, 32, generator=g).clamp(-1, 1).to(DEV)
+        eps = torch.randn(B, cfg['in_channels'], 32, 32, generator=g).to(DEV)
+        t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+        ok &= _train_parity(name, m, dict(dim=cfg['dim'], n_heads=cfg['n_heads']), x0, t, eps)
+    cfgc = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+                num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+    torch.manual_seed(2022)
+    m = models.UNetCategorialAdaGN(**cfgc).to(DEV)
+    B = 4
+    g = torch.Generator(device='cpu').manual_seed(4)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1).to(DEV)
+    eps = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    y = torch.tensor([1, 5, 9, 0], device=DEV)
+    okw = dict(dim=128, adagn=True, attn_head_dims=64, num_res_blocks=2)
+    ok &= _train_parity('cfg AdaGN UNet B=4 (cond)', m, okw, x0, t, eps, y=y)
+    ok &= _train_parity('cfg AdaGN UNet B=4 (uncond)', m, okw, x0, t, eps, y=None)
+    return ok
+
+
 def case_timing():
     """Orientation numbers (not the bench): forward and DDIM-50 at B=256."""
     m, _ = _build(CIFAR)

@@ -85,6 +85,12 @@ class GnBwdDesc(Structure):
                 ('dscale', c_void_p), ('dshift', c_void_p), ('dss_ld', c_int)]
 
 
+class OptimDesc(Structure):
+    _fields_ = [('chunks', c_void_p), ('n_chunks', c_int), ('lr', c_float), ('beta1', c_float), ('beta2', c_float),
+                ('eps', c_float), ('weight_decay', c_float), ('adamw', c_int), ('step', c_int),
+                ('max_grad_norm', c_float), ('want_norm', c_int), ('gnorm_sq', c_void_p), ('ema_decay', c_float)]
+
+
 _lib = None
 
 
@@ -133,6 +139,7 @@ def lib():
     L.b200_softmax_rows.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
     L.b200_softmax_bwd_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
     L.b200_time_embed_bwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 14
+    L.b200_optimizer_step.argtypes = [POINTER(OptimDesc), c_void_p]
     L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for name in BACKWARD_SYMBOLS:
@@ -152,6 +159,7 @@ BACKWARD_SYMBOLS = (
     'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
     'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
     'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad', 'b200_time_embed_bwd',
+    'b200_optimizer_step',
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (

@@ -1,0 +1,89 @@
+// Fused optimizer tail of the training step (scripts/train_ddpm.py:186-188 +
+// models/ema.py:44-52 of the reference): global gradient-norm clip + Adam / AdamW + EMA of the weights as two
+// multi-tensor kernels over a device-resident chunk table, instead of clip_grad_norm_ (2 passes), Adam.step
+// (foreach, ~6 passes) and the per-tensor EMA loop.  Nothing synchronises with the host: the clip coefficient is
+// computed on the device from the squared norm accumulated by the first kernel.
+#include "common.cuh"
+#include "../../include/b200diff.h"
+
+namespace b200 {
+extern long long g_launch_count;
+
+__global__ void __launch_bounds__(256) optim_sumsq_kernel(const b200_optim_chunk* __restrict__ chunks,
+                                                          float* __restrict__ gnorm_sq) {
+  const b200_optim_chunk c = chunks[blockIdx.x];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < c.n; i += 256) {
+    const float g = c.g[i];
+    s = fmaf(g, g, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    atomicAdd(gnorm_sq, t);
+  }
+}
+
+struct OptimK {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm, ema_decay;
+  int adamw, use_ema;
+};
+
+__global__ void __launch_bounds__(256) optim_adam_kernel(const b200_optim_chunk* __restrict__ chunks,
+                                                         const float* __restrict__ gnorm_sq, const OptimK k) {
+  const b200_optim_chunk c = chunks[blockIdx.x];
+  float coef = 1.f;
+  if (k.max_norm > 0.f) {   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    coef = fminf(1.f, k.max_norm / (sqrtf(gnorm_sq[0]) + 1e-6f));
+  }
+  const float step_size = k.lr / k.bc1;
+  for (int i = threadIdx.x; i < c.n; i += 256) {
+    float p = c.p[i];
+    float g = c.g[i] * coef;
+    if (k.wd != 0.f) {
+      if (k.adamw) p *= 1.f - k.lr * k.wd;
+      else g = fmaf(k.wd, p, g);
+    }
+    const float m = fmaf(k.beta1, c.m[i], (1.f - k.beta1) * g);
+    const float v = fmaf(k.beta2, c.v[i], (1.f - k.beta2) * g * g);
+    c.m[i] = m;
+    c.v[i] = v;
+    p -= step_size * m / (sqrtf(v) / k.bc2_sqrt + k.eps);
+    c.p[i] = p;
+    if (k.use_ema && c.ema) {
+      const float e = c.ema[i];
+      c.ema[i] = e - (1.f - k.ema_decay) * (e - p);
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(d && d->chunks && d->n_chunks >= 1 && d->gnorm_sq, "optimizer_step: null chunk table / workspace");
+  B200_REQUIRE(d->step >= 1 && d->beta1 >= 0.f && d->beta1 < 1.f && d->beta2 >= 0.f && d->beta2 < 1.f,
+               "optimizer_step: bad step / betas");
+  const b200_optim_chunk* chunks = reinterpret_cast<const b200_optim_chunk*>(d->chunks);
+  B200_CHECK(cudaMemsetAsync(d->gnorm_sq, 0, sizeof(float), stream));
+  if (d->max_grad_norm > 0.f || d->want_norm) {
+    optim_sumsq_kernel<<<d->n_chunks, 256, 0, stream>>>(chunks, d->gnorm_sq);
+    ++g_launch_count;
+    B200_CHECK(cudaGetLastError());
+  }
+  OptimK k;
+  k.lr = d->lr; k.beta1 = d->beta1; k.beta2 = d->beta2; k.eps = d->eps; k.wd = d->weight_decay;
+  k.bc1 = (float)(1.0 - pow((double)d->beta1, (double)d->step));
+  k.bc2_sqrt = (float)sqrt(1.0 - pow((double)d->beta2, (double)d->step));
+  k.max_norm = d->max_grad_norm; k.adamw = d->adamw;
+  k.use_ema = d->ema_decay >= 0.f ? 1 : 0; k.ema_decay = d->ema_decay;
+  optim_adam_kernel<<<d->n_chunks, 256, 0, stream>>>(chunks, d->gnorm_sq, k);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "optim_adam_kernel launch");
+}

@@ -383,6 +383,7 @@ def run_backward(eng: Engine, tape, dout, params):
     if not dout.is_cuda or dout.dtype != torch.float32:
         raise RuntimeError('backward: expected a float32 CUDA gradient')
     G = _Grads(eng, params)
+    eng.flat_grad = G.flat        # the parameters' gradients are views into this buffer, in registration order
     with torch.no_grad():
         embed_rec = None
         for e in reversed(tape):

@@ -306,6 +306,29 @@ int b200_time_embed_bwd(const int64_t* t, int rows, const float* freqs, int dim,
 int b200_mse_loss(const float* a, const float* b, float* loss, long long n, void* stream);
 int b200_mse_loss_grad(const float* a, const float* b, const float* grad_scale, float* da, long long n, void* stream);
 
+/* Fused optimizer tail (clip_grad_norm_ + torch.optim.Adam/AdamW step + models/ema.py:44-52 EMA update;
+ * scripts/train_ddpm.py:186-188).  `chunks` is a DEVICE array of n_chunks descriptors, each covering up to 65536
+ * consecutive elements of one parameter tensor and of its gradient / Adam moments / EMA shadow (ema may be NULL).
+ * gnorm_sq (device scalar) receives the squared global gradient norm when max_grad_norm > 0 or want_norm.
+ * Semantics are torch's: clip coefficient min(1, max_norm / (norm + 1e-6)); Adam with bias correction, L2
+ * weight decay added to the gradient (adamw = 0) or decoupled (adamw = 1); EMA: e -= (1 - decay) (e - p_new). */
+typedef struct b200_optim_chunk {
+  float* p; const float* g; float* m; float* v; float* ema;
+  int n; int pad_;
+} b200_optim_chunk;
+
+typedef struct b200_optim_desc {
+  const void* chunks; int n_chunks;
+  float lr, beta1, beta2, eps, weight_decay;
+  int adamw;
+  int step;                 /* 1-based step count (bias correction) */
+  float max_grad_norm;      /* <= 0: no clipping */
+  int want_norm;
+  float* gnorm_sq;
+  float ema_decay;          /* < 0: no EMA update */
+} b200_optim_desc;
+int b200_optimizer_step(const b200_optim_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -669,6 +669,42 @@ def case_backward_misc():
 
 
 # ----------------------------------------------------------------------------------------------------
+# fused clip + Adam(W) + EMA vs clip_grad_norm_ + torch.optim.Adam(W) + the reference EMA update
+# ----------------------------------------------------------------------------------------------------
+def case_optimizer():
+    sys.path.insert(0, os.path.join(ROOT, 'diffusion-models-pytorch_b200'))
+    from b200diff.optim import FusedAdam
+    from models.ema import EMA
+    ok = True
+    shapes = [(256, 128, 3, 3), (128,), (70001,), (512, 512), (3, 128, 3, 3)]
+    for adamw, wd in ((False, 0.0), (False, 0.01), (True, 0.05)):
+        ps = [torch.nn.Parameter(_gen(*s, seed=i) * 0.1) for i, s in enumerate(shapes)]
+        qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        ours = FusedAdam(ps, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, adamw=adamw)
+        ref = (torch.optim.AdamW if adamw else torch.optim.Adam)(qs, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        ema_o, ema_r = EMA(ps, decay=0.9999, gradual=True), EMA(qs, decay=0.9999, gradual=True)
+        for step in range(4):
+            for i, (p, q) in enumerate(zip(ps, qs)):
+                g = _gen(*p.shape, seed=100 * step + i) * (3.0 if step == 1 else 0.01)
+                p.grad, q.grad = g.clone(), g.clone()
+            norm_ref = torch.nn.utils.clip_grad_norm_(qs, max_norm=1.0)
+            ref.step()
+            ema_r.update(qs)
+            ours.step(clip_grad_norm=1.0, ema=ema_o)
+            ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} step {step} grad norm', ours.grad_norm,
+                          norm_ref.view(1), rtol=1e-5, atol=1e-6)
+        for i, (p, q) in enumerate(zip(ps, qs)):
+            ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} param {i}', p.detach(), q.detach(), rtol=1e-5, atol=1e-7)
+            ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} ema {i}', ema_o.shadow[i], ema_r.shadow[i], rtol=1e-5,
+                          atol=1e-7)
+        sd = ours.state_dict()
+        good = set(sd['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'} and ema_o.num_updates == 4
+        print(json.dumps({'case': 'fused adam state_dict layout', 'ok': good}), flush=True)
+        ok &= good
+    return ok
+
+
+# ----------------------------------------------------------------------------------------------------
 # sampler step vs the eager op sequence of the reference (restated in oracle/diffusion_ref.py)
 # ----------------------------------------------------------------------------------------------------
 def case_sampler():

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb200diff.so')
+LIB_PATH = os.environ.get('B200DIFF_LIB') or os.path.join(_HERE, 'libb200diff.so')   # override: A/B experiments
 
 OUT_F32_NHWC, OUT_BF16_NHWC, OUT_F32_NCHW, OUT_BF16_NCHW = 0, 1, 2, 3
 OBJ = {'pred_eps': 0, 'pred_x0': 1, 'pred_v': 2}

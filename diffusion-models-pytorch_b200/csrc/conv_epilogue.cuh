@@ -1,0 +1,292 @@
+// Shared pieces of the implicit-GEMM convolution kernels (conv_gemm.cu: one CTA per tile; conv_gemm2.cu: CTA pairs).
+#pragma once
+#include "common.cuh"
+#include "../../include/b200diff.h"
+
+namespace b200 {
+
+struct ConvKParams {
+  int B, NP;
+  int bw, bh, bn, lg_bw, lg_bhw;
+  int tiles_w, tiles_h;
+  int p_tiles, c_tiles, total_tiles;
+  int N, w_rows_per_phase;
+  int cpb0, nkb0, nkb1;
+  int stages;
+  int8_t taps0[4][9][4];
+  int8_t tap1[4];
+  const float* bias;
+  const float* rowadd;
+  int rowadd_ld;
+  const float* residual;
+  int res_ld;
+  float* stats;  // [B][N][2] running (sum, sum of squares) of the fp32 output, or NULL
+  void* out;
+  int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
+  int group4;    // bw >= 4: 4 consecutive tile pixels are 4 output pixels osx apart in one row
+  int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
+  int k_rotate;    // rotate the K-block order per CTA (spreads weight-tile requests over L2)
+  int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
+  int dbg;       // experiment knob (B200_EPI_DBG): 1 = no residual loads, 2 = no output stores, 4 = epilogue does nothing
+};
+
+constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
+constexpr int kBlockK = 64;
+constexpr int kWBytes = kBlockC * kBlockK * 2;  // 16 KB weight tile
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kMaxStages = 8;
+
+struct __align__(8) ConvBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct TileCoord {
+  int ph, ct, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  const int per_phase = p.p_tiles * p.c_tiles;
+  t.ph = tile / per_phase;
+  const int rem = tile - t.ph * per_phase;
+  const int pt = rem / p.c_tiles;
+  t.ct = rem - pt * p.c_tiles;
+  const int tw = pt % p.tiles_w;
+  const int th = (pt / p.tiles_w) % p.tiles_h;
+  const int tn = pt / (p.tiles_w * p.tiles_h);
+  t.w0 = tw * p.bw;
+  t.h0 = th * p.bh;
+  t.n0 = tn * p.bn;
+  return t;
+}
+
+// Image index and pixel offset (row-major within the output image) of tile pixel pp.
+__device__ __forceinline__ void decode_pixel(const ConvKParams& p, const TileCoord& t, int pp, int pa, int pb, int& n,
+                                             int& po) {
+  n = t.n0 + (pp >> p.lg_bhw);
+  const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+  const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+  po = oy * p.out_W + ox;
+}
+
+// Epilogue of one tile for one warp: TMEM lanes = 32 consecutive output channels (this thread owns channel c), TMEM
+// columns = the tile's pixels.  Shared by the 1-CTA and the CTA-pair kernels.  (Fetching the residual a chunk ahead
+// was measured: no gain -- the epilogue's cost is its HBM traffic competing with the operand stream, not its latency --
+// and the doubled code slowed the short-K 1x1 layers, so one chunk is processed at a time.)
+__device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, const TileCoord& t, const uint32_t taddr, const int c,
+                                                   const bool c_ok, const int half, uint64_t* acc_full_bar,
+                                                   const uint32_t acc_parity) {
+  const int hw_out = p.out_H * p.out_W;
+  const size_t img_out = (size_t)hw_out * p.out_ld;   // elements per image of an NHWC output
+  const size_t img_res = (size_t)hw_out * p.res_ld;
+  const int ostep = p.osx * p.out_ld, rstep = p.osx * p.res_ld;
+  const float* __restrict__ residual = (p.dbg & 1) ? nullptr : p.residual;
+  const int pa = t.ph >> 1, pb = t.ph & 1;
+  const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
+  float s1 = 0.f, s2 = 0.f, ra_c = 0.f;
+  int cur_n = -1;
+  // fast path: the tile's pixels are consecutive output pixels (full-width rows / whole images, stride 1)
+  const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
+  const float* __restrict__ rbase = residual ? residual + pix0 * (size_t)p.res_ld + c : nullptr;
+
+  auto load_res = [&](const int ch, float (&r)[32]) {
+          if (p.fast_epi) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = c_ok ? __ldg(rbase + (ch + j) * p.res_ld) : 0.f;
+          } else if (p.group4) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              int n, po;
+              decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
+              const float* rp = residual + (size_t)n * img_res + c + po * p.res_ld;
+              const bool ok = c_ok && n < p.B;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r[4 * g + e] = ok ? __ldg(rp + e * rstep) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int n, po;
+              decode_pixel(p, t, ch + j, pa, pb, n, po);
+              r[j] = (c_ok && n < p.B) ? __ldg(residual + (size_t)n * img_res + c + po * p.res_ld) : 0.f;
+            }
+          }
+  };
+
+  auto process = [&](const int ch) {
+        uint32_t v[32];
+        float r[32];
+        __syncwarp();
+        tmem_ld_x32(taddr + (uint32_t)ch, v);
+        if (residual) load_res(ch, r);      // overlaps the TMEM load
+        tmem_ld_wait();
+        float acc[32];
+        if (p.fast_epi) {
+          // >= 16 pixels per image: the image index is constant over each half of the chunk; two independent
+          // accumulator pairs shorten the dependent FADD/FFMA chains of the statistics
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
+            if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
+              if (p.stats && c_ok && cur_n >= 0) {
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+              }
+              s1 = 0.f; s2 = 0.f;
+              cur_n = n;
+              ra_c = (p.rowadd && c_ok) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+            }
+            const float add_c = bias_c + ra_c;
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
+              float a0 = __uint_as_float(v[j]) + add_c;
+              float a1 = __uint_as_float(v[j + 1]) + add_c;
+              if (residual) { a0 += r[j]; a1 += r[j + 1]; }
+              acc[j] = a0;
+              acc[j + 1] = a1;
+              s1 += a0; t1 += a1;
+              s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
+            }
+            s1 += t1;
+            s2 += t2;
+          }
+        } else {
+  #pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            // the image index can only change between groups of 4 pixels when every image has >= 4 pixels per tile
+            const int n = t.n0 + ((ch + 4 * g) >> p.lg_bhw);
+            if (p.lg_bhw >= 2) {
+              if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
+                if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+                }
+                s1 = 0.f; s2 = 0.f;
+                cur_n = n;
+                ra_c = (p.rowadd && c_ok && n < p.B) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+              }
+              const float add_c = bias_c + ra_c;
+              const bool n_ok = n < p.B;
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = __uint_as_float(v[4 * g + e]) + add_c;
+                if (residual) a += r[4 * g + e];
+                acc[4 * g + e] = a;
+                if (n_ok) { s1 += a; s2 += a * a; }
+              }
+            } else {
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ne = t.n0 + ((ch + 4 * g + e) >> p.lg_bhw);
+                if (ne != cur_n) {
+                  if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+                  }
+                  s1 = 0.f; s2 = 0.f;
+                  cur_n = ne;
+                  ra_c = (p.rowadd && c_ok && ne < p.B) ? __ldg(p.rowadd + (size_t)ne * p.rowadd_ld + c) : 0.f;
+                }
+                float a = __uint_as_float(v[4 * g + e]) + bias_c + ra_c;
+                if (residual) a += r[4 * g + e];
+                acc[4 * g + e] = a;
+                if (ne < p.B) { s1 += a; s2 += a * a; }
+              }
+            }
+          }
+        }
+        if (p.dbg & 2) return;
+        if (p.fast_epi && p.out_mode == B200_OUT_F32_NHWC) {
+          float* __restrict__ ob = reinterpret_cast<float*>(p.out) + pix0 * (size_t)p.out_ld + c;
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = acc[j];
+          }
+        } else if (p.fast_epi && p.out_mode == B200_OUT_BF16_NHWC) {
+          __nv_bfloat16* __restrict__ ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix0 * (size_t)p.out_ld + c;
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = __float2bfloat16_rn(acc[j]);
+          }
+        } else if (p.group4 && p.out_mode <= B200_OUT_BF16_NHWC) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            int n, po;
+            decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NHWC) {
+                float* __restrict__ o = reinterpret_cast<float*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e * ostep] = acc[4 * g + e];
+              } else {
+                __nv_bfloat16* __restrict__ o =
+                    reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e * ostep] = __float2bfloat16_rn(acc[4 * g + e]);
+              }
+            }
+          }
+        } else if (p.out_mode <= B200_OUT_BF16_NHWC) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int n, po;
+            decode_pixel(p, t, ch + j, pa, pb, n, po);
+            if (c_ok && n < p.B) {
+              const size_t e = (size_t)n * img_out + c + po * p.out_ld;
+              if (p.out_mode == B200_OUT_F32_NHWC) reinterpret_cast<float*>(p.out)[e] = acc[j];
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
+            }
+          }
+        } else if (p.vec8_ok) {
+          // channel-major outputs: this thread owns a row of consecutive pixels -> 8-pixel vector stores
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            int n, po;
+            decode_pixel(p, t, ch + 8 * g, 0, 0, n, po);
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NCHW) {
+                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e);
+                o[0] = make_float4(acc[8 * g], acc[8 * g + 1], acc[8 * g + 2], acc[8 * g + 3]);
+                o[1] = make_float4(acc[8 * g + 4], acc[8 * g + 5], acc[8 * g + 6], acc[8 * g + 7]);
+              } else {
+                uint4 u;
+                u.x = pack_bf16x2(acc[8 * g], acc[8 * g + 1]);
+                u.y = pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]);
+                u.z = pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]);
+                u.w = pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + e) = u;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int n, po;
+            decode_pixel(p, t, ch + j, pa, pb, n, po);
+            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
+            if (c_ok && n < p.B) {
+              if (p.out_mode == B200_OUT_F32_NCHW) reinterpret_cast<float*>(p.out)[e] = acc[j];
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
+            }
+          }
+        }
+  };
+
+  mbar_wait(acc_full_bar, acc_parity);
+  tc_fence_after();
+  if (p.dbg & 4) return;
+#pragma unroll 1
+  for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves) process(ch);
+      if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
+        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+      }
+}
+
+}  // namespace b200

@@ -13,82 +13,15 @@
 // NP = 256 pixels (N = 256 UMMA, 85 flop/B of operand traffic) unless the layer is too small to fill the SMs.
 // Warp roles (320 threads, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer (one thread),
 // warps 2-9 epilogue, overlapped with the next tile's MMAs through two TMEM accumulator stages.
-#include "common.cuh"
+#include "conv_epilogue.cuh"
 #include <stdlib.h>
 #include <string.h>
-#include "../../include/b200diff.h"
 
 namespace b200 {
 
+int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t stream);
 int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_);
 int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh, int bn);
-
-struct ConvKParams {
-  int B, NP;
-  int bw, bh, bn, lg_bw, lg_bhw;
-  int tiles_w, tiles_h;
-  int p_tiles, c_tiles, total_tiles;
-  int N, w_rows_per_phase;
-  int cpb0, nkb0, nkb1;
-  int stages;
-  int8_t taps0[4][9][4];
-  int8_t tap1[4];
-  const float* bias;
-  const float* rowadd;
-  int rowadd_ld;
-  const float* residual;
-  int res_ld;
-  float* stats;  // [B][N][2] running (sum, sum of squares) of the fp32 output, or NULL
-  void* out;
-  int out_mode, out_ld, out_H, out_W, osy, osx, vec8_ok;
-  int group4;    // bw >= 4: 4 consecutive tile pixels are 4 output pixels osx apart in one row
-  int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
-  int k_rotate;    // rotate the K-block order per CTA (spreads weight-tile requests over L2)
-  int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
-};
-
-constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
-constexpr int kBlockK = 64;
-constexpr int kWBytes = kBlockC * kBlockK * 2;  // 16 KB weight tile
-constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int kMaxStages = 8;
-
-struct __align__(8) ConvBarriers {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
-};
-
-struct TileCoord {
-  int ph, ct, w0, h0, n0;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
-  TileCoord t;
-  const int per_phase = p.p_tiles * p.c_tiles;
-  t.ph = tile / per_phase;
-  const int rem = tile - t.ph * per_phase;
-  const int pt = rem / p.c_tiles;
-  t.ct = rem - pt * p.c_tiles;
-  const int tw = pt % p.tiles_w;
-  const int th = (pt / p.tiles_w) % p.tiles_h;
-  const int tn = pt / (p.tiles_w * p.tiles_h);
-  t.w0 = tw * p.bw;
-  t.h0 = th * p.bh;
-  t.n0 = tn * p.bn;
-  return t;
-}
-
-// Image index and pixel offset (row-major within the output image) of tile pixel pp.
-__device__ __forceinline__ void decode_pixel(const ConvKParams& p, const TileCoord& t, int pp, int pa, int pb, int& n,
-                                             int& po) {
-  n = t.n0 + (pp >> p.lg_bhw);
-  const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
-  const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
-  po = oy * p.out_W + ox;
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -197,11 +130,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     // 32-pixel column chunks (even / odd), doubling the instruction throughput of the latency-bound epilogue.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int hw_out = p.out_H * p.out_W;
-    const size_t img_out = (size_t)hw_out * p.out_ld;   // elements per image of an NHWC output
-    const size_t img_res = (size_t)hw_out * p.res_ld;
-    const int ostep = p.osx * p.out_ld, rstep = p.osx * p.res_ld;
-    const float* __restrict__ residual = p.residual;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -209,203 +137,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const TileCoord t = decode_tile(p, tile);
       const int c = t.ct * kBlockC + q * 32 + lane;  // output channel of this thread
       const bool c_ok = c < p.N;
-      const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
-      const int pa = t.ph >> 1, pb = t.ph & 1;
-
-      mbar_wait(&bars->tmem_full[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.NP) + ((uint32_t)(q * 32) << 16);
-      float s1 = 0.f, s2 = 0.f, ra_c = 0.f;
-      int cur_n = -1;
-      // fast path: the tile's pixels are consecutive output pixels (full-width rows / whole images, stride 1)
-      const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
-      const float* __restrict__ rbase = residual ? residual + pix0 * (size_t)p.res_ld + c : nullptr;
-      for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_x32(taddr + (uint32_t)ch, v);
-        // residual prefetch overlaps the TMEM load
-        float r[32];
-        if (residual) {
-          if (p.fast_epi) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = c_ok ? __ldg(rbase + (ch + j) * p.res_ld) : 0.f;
-          } else if (p.group4) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              int n, po;
-              decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
-              const float* rp = residual + (size_t)n * img_res + c + po * p.res_ld;
-              const bool ok = c_ok && n < p.B;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) r[4 * g + e] = ok ? __ldg(rp + e * rstep) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              int n, po;
-              decode_pixel(p, t, ch + j, pa, pb, n, po);
-              r[j] = (c_ok && n < p.B) ? __ldg(residual + (size_t)n * img_res + c + po * p.res_ld) : 0.f;
-            }
-          }
-        }
-        tmem_ld_wait();
-        float acc[32];
-        if (p.fast_epi) {
-          // >= 16 pixels per image: the image index is constant over each half of the chunk; two independent
-          // accumulator pairs shorten the dependent FADD/FFMA chains of the statistics
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
-            if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
-              if (p.stats && c_ok && cur_n >= 0) {
-                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
-                atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
-              }
-              s1 = 0.f; s2 = 0.f;
-              cur_n = n;
-              ra_c = (p.rowadd && c_ok) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
-            }
-            const float add_c = bias_c + ra_c;
-            float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
-              float a0 = __uint_as_float(v[j]) + add_c;
-              float a1 = __uint_as_float(v[j + 1]) + add_c;
-              if (residual) { a0 += r[j]; a1 += r[j + 1]; }
-              acc[j] = a0;
-              acc[j + 1] = a1;
-              s1 += a0; t1 += a1;
-              s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
-            }
-            s1 += t1;
-            s2 += t2;
-          }
-        } else {
-  #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            // the image index can only change between groups of 4 pixels when every image has >= 4 pixels per tile
-            const int n = t.n0 + ((ch + 4 * g) >> p.lg_bhw);
-            if (p.lg_bhw >= 2) {
-              if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
-                if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
-                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
-                  atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
-                }
-                s1 = 0.f; s2 = 0.f;
-                cur_n = n;
-                ra_c = (p.rowadd && c_ok && n < p.B) ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
-              }
-              const float add_c = bias_c + ra_c;
-              const bool n_ok = n < p.B;
-  #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a = __uint_as_float(v[4 * g + e]) + add_c;
-                if (residual) a += r[4 * g + e];
-                acc[4 * g + e] = a;
-                if (n_ok) { s1 += a; s2 += a * a; }
-              }
-            } else {
-  #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int ne = t.n0 + ((ch + 4 * g + e) >> p.lg_bhw);
-                if (ne != cur_n) {
-                  if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
-                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
-                    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
-                  }
-                  s1 = 0.f; s2 = 0.f;
-                  cur_n = ne;
-                  ra_c = (p.rowadd && c_ok && ne < p.B) ? __ldg(p.rowadd + (size_t)ne * p.rowadd_ld + c) : 0.f;
-                }
-                float a = __uint_as_float(v[4 * g + e]) + bias_c + ra_c;
-                if (residual) a += r[4 * g + e];
-                acc[4 * g + e] = a;
-                if (ne < p.B) { s1 += a; s2 += a * a; }
-              }
-            }
-          }
-        }
-        if (p.fast_epi && p.out_mode == B200_OUT_F32_NHWC) {
-          float* __restrict__ ob = reinterpret_cast<float*>(p.out) + pix0 * (size_t)p.out_ld + c;
-          if (c_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = acc[j];
-          }
-        } else if (p.fast_epi && p.out_mode == B200_OUT_BF16_NHWC) {
-          __nv_bfloat16* __restrict__ ob = reinterpret_cast<__nv_bfloat16*>(p.out) + pix0 * (size_t)p.out_ld + c;
-          if (c_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ob[(ch + j) * p.out_ld] = __float2bfloat16_rn(acc[j]);
-          }
-        } else if (p.group4 && p.out_mode <= B200_OUT_BF16_NHWC) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            int n, po;
-            decode_pixel(p, t, ch + 4 * g, pa, pb, n, po);
-            if (c_ok && n < p.B) {
-              if (p.out_mode == B200_OUT_F32_NHWC) {
-                float* __restrict__ o = reinterpret_cast<float*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e * ostep] = acc[4 * g + e];
-              } else {
-                __nv_bfloat16* __restrict__ o =
-                    reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)n * img_out + c + po * p.out_ld;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e * ostep] = __float2bfloat16_rn(acc[4 * g + e]);
-              }
-            }
-          }
-        } else if (p.out_mode <= B200_OUT_BF16_NHWC) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int n, po;
-            decode_pixel(p, t, ch + j, pa, pb, n, po);
-            if (c_ok && n < p.B) {
-              const size_t e = (size_t)n * img_out + c + po * p.out_ld;
-              if (p.out_mode == B200_OUT_F32_NHWC) reinterpret_cast<float*>(p.out)[e] = acc[j];
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
-            }
-          }
-        } else if (p.vec8_ok) {
-          // channel-major outputs: this thread owns a row of consecutive pixels -> 8-pixel vector stores
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            int n, po;
-            decode_pixel(p, t, ch + 8 * g, 0, 0, n, po);
-            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
-            if (c_ok && n < p.B) {
-              if (p.out_mode == B200_OUT_F32_NCHW) {
-                float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + e);
-                o[0] = make_float4(acc[8 * g], acc[8 * g + 1], acc[8 * g + 2], acc[8 * g + 3]);
-                o[1] = make_float4(acc[8 * g + 4], acc[8 * g + 5], acc[8 * g + 6], acc[8 * g + 7]);
-              } else {
-                uint4 u;
-                u.x = pack_bf16x2(acc[8 * g], acc[8 * g + 1]);
-                u.y = pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]);
-                u.z = pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]);
-                u.w = pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + e) = u;
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int n, po;
-            decode_pixel(p, t, ch + j, pa, pb, n, po);
-            const size_t e = ((size_t)n * p.out_ld + c) * hw_out + po;
-            if (c_ok && n < p.B) {
-              if (p.out_mode == B200_OUT_F32_NCHW) reinterpret_cast<float*>(p.out)[e] = acc[j];
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[e] = __float2bfloat16_rn(acc[j]);
-            }
-          }
-        }
-      }
-      if (p.stats && c_ok && cur_n >= 0 && cur_n < p.B) {
-        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
-        atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
-      }
+      conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
@@ -513,6 +246,21 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   p.fast_epi = (d->phases == 1 && d->osx == 1 && d->osy == 1 && p.bw == d->Wo && d->out_W == d->Wo &&
                 d->out_H == d->Ho && (p.bn == 1 || p.bh == d->Ho) && d->B % p.bn == 0 && p.lg_bhw >= 4) ? 1 : 0;
 
+  // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
+  static const char* env_halves = getenv("B200_EPI_HALVES");
+  p.epi_halves = (env_halves && atoi(env_halves) == 1) ? 1 : 2;
+  static const char* env_rot = getenv("B200_K_ROTATE");
+  p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
+
+  static const char* env_dbg = getenv("B200_EPI_DBG");
+  p.dbg = env_dbg ? atoi(env_dbg) : 0;
+  // CTA pairs (cta_group::2, conv_gemm2.cu) when two 128-channel tiles can share one 256-pixel tile and there are
+  // enough pair tiles to occupy the 74 SM pairs
+  static const char* env_pair = getenv("B200_PAIR");
+  if ((!env_pair || atoi(env_pair) != 0) && d->N % 256 == 0 && p.NP == 256 &&
+      (long)d->phases * p.p_tiles * (c_tiles / 2) >= (long)(g_num_sms / 2) * 3 / 4)
+    return conv2d_fwd_pair(d, p, stream);
+
   const int stage_bytes = kWBytes + p.NP * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -537,11 +285,6 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     rc = encode_tmap(&mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
-  static const char* env_halves = getenv("B200_EPI_HALVES");
-  p.epi_halves = (env_halves && atoi(env_halves) == 1) ? 1 : 2;
-  static const char* env_rot = getenv("B200_K_ROTATE");
-  p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   conv_gemm_kernel<<<grid, 64 + 128 * p.epi_halves, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
   ++g_launch_count;

@@ -33,7 +33,7 @@ class Act:
 class Engine:
     # conv1 outputs of ResBlocks (consumed only by the following GroupNorm) are stored as bf16; their GroupNorm
     # statistics still come from the fp32 accumulators in the conv epilogue
-    h_bf16 = False  # measured: +0.6e-3 eps error for no speed-up (GroupNorm is not limited by its read bytes)
+    h_bf16 = bool(int(__import__('os').environ.get('B200_H_BF16', '0')))  # measured: +0.6e-3 eps error for no speed-up
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -151,7 +151,7 @@ class Engine:
         w, b = self.w_conv(tag, conv, sc_conv)
         stats = None
         if out is None:
-            if intermediate and self.h_bf16 and Cout > 32:
+            if intermediate and self.h_bf16 and Cout > 32 and self.tape is None:
                 out_mode = K.OUT_BF16_NHWC
             out = self.buf(tag + '.out', (B, H, W, Cout),
                            torch.bfloat16 if out_mode == K.OUT_BF16_NHWC else torch.float32)

@@ -161,8 +161,13 @@ def run_ours(args):
                          '(use --impl reference for the CPU baseline)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    stdout_fd = None
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the single JSON line
+        # NCCL prints its version banner (and NCCL_DEBUG output) on stdout: route fd 1 to stderr while the job runs and
+        # restore it for the single JSON line
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     B, S = args.batch, args.sample_steps
 
@@ -279,6 +284,12 @@ def run_ours(args):
         line['roofline_groupnorm'] = {'kernel': 'groupnorm_apply_kernel', 'bound': 'hbm', 'achieved': gbs,
                                       'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
                                       'traffic': None}
+    if stdout_fd is not None:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        os.close(stdout_fd)
     if rank == 0:
         # CPU baseline on rank 0: a bounded sample (batch 8, 1 warm-up + 2 timed single DDIM steps)
         if world == 1 and not args.no_cpu_baseline:
@@ -288,8 +299,6 @@ def run_ours(args):
                 'sample': 'oracle port (PyTorch fp32 CPU), batch 8, 1 warm-up + 2 timed DDIM steps (UNet forward + '
                           'sampler arithmetic), extrapolated linearly to 50 steps'}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

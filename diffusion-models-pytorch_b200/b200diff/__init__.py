@@ -65,7 +65,7 @@ class WgradDesc(Structure):
                 ('x', c_void_p), ('x_C', c_int), ('x_H', c_int), ('x_W', c_int), ('x_planes', c_int), ('x_c0', c_int),
                 ('B', c_int), ('Ho', c_int), ('Wo', c_int), ('Cout', c_int), ('Cin', c_int), ('ntaps', c_int),
                 ('taps', c_int8 * 36), ('dw', c_void_p), ('dw_co_stride', c_longlong), ('dw_ci_stride', c_longlong),
-                ('dw_tap_stride', c_longlong)]
+                ('dw_tap_stride', c_longlong), ('scratch', c_void_p), ('scratch_bytes', c_longlong)]
 
 
 class GnBwdDesc(Structure):
@@ -493,7 +493,7 @@ def gemm_batched(a, b, out, M, N, Kdim, *, batch=1, heads=1, out_ld=None, out_ba
 
 
 def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0, dy_c0=0, co_stride=None,
-                 ci_stride=None, tap_stride=1):
+                 ci_stride=None, tap_stride=1, scratch=None):
     """Accumulates the weight gradient into `dw` (fp32; default strides = an OIHW tensor [Cout][Cin][ntaps]).
     x_geom = (C, H, W, planes) of the bf16 tensor the forward conv read, taps = its tap table (one phase)."""
     _need_cuda(dy, x, dw)
@@ -512,6 +512,8 @@ def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0,
     d.dw_co_stride = co_stride if co_stride is not None else Cin * nt
     d.dw_ci_stride = ci_stride if ci_stride is not None else nt
     d.dw_tap_stride = tap_stride
+    if scratch is not None:
+        d.scratch, d.scratch_bytes = scratch.data_ptr(), scratch.numel() * scratch.element_size()
     _launch('conv_wgrad', lambda: _check(lib().b200_conv2d_wgrad(ctypes.byref(d), _stream()), 'conv2d_wgrad'),
             flops=2.0 * B * Ho * Wo * Cout * Cin * nt)
     return dw

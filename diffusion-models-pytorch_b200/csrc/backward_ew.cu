@@ -3,6 +3,7 @@
 // column sums, resampling adjoints, the row softmax of the unfused attention backward and the MSE loss.
 // Everything is fp32 arithmetic on NHWC tensors; tensor-core operands of the following GEMMs are emitted as bf16.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/b200diff.h"
 
@@ -118,18 +119,19 @@ __device__ __forceinline__ void gn_bwd_dz(const GnBwdParams& p, int n, int px, i
   const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g.x, g.y, g.z, g.w};
   const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
   const float rav[4] = {ra.x, ra.y, ra.z, ra.w}, rbv[4] = {rb.x, rb.y, rb.z, rb.w};
-  const unsigned long long e = ((unsigned long long)n * p.HW + px) * C + c;
+  uint32_t keep = 15u;
+  if (p.drop_thresh) keep = dropout_keep4(p.drop_seed, (((unsigned long long)n * p.HW + px) * C + c) >> 2, p.drop_thresh);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     xh[i] = fmaf(xv[i], rav[i], rbv[i]);
     float d = gv[i];
     if (p.apply_silu) d *= silu_grad(fmaf(xv[i], av[i], bv[i]));
-    if (p.drop_thresh) d = dropout_keep(p.drop_seed, e + i, p.drop_thresh) ? d * p.drop_scale : 0.f;
+    if (p.drop_thresh) d = ((keep >> i) & 1u) ? d * p.drop_scale : 0.f;
     dz[i] = d;
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p) {
+__global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
   float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
@@ -150,14 +152,22 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
     const float4 a = *reinterpret_cast<const float4*>(cA + c), b = *reinterpret_cast<const float4*>(cB + c);
     const float4 ra = *reinterpret_cast<const float4*>(rA + c), rb = *reinterpret_cast<const float4*>(rB + c);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int px = px0 + prow; px < px1; px += pstep) {
-      const float4 x = gn_bwd_load_x(p, n, px, c);
-      const float4 g = gn_bwd_load_g(p, n, px, C, c);
-      float dz[4], xh[4];
-      gn_bwd_dz(p, n, px, C, c, x, g, a, b, ra, rb, dz, xh);
+    for (int px = px0 + prow; px < px1; px += 4 * pstep) {
+      float4 xs[4], gs[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+      for (int u = 0; u < 4; ++u)
+        if (px + u * pstep < px1) {
+          xs[u] = gn_bwd_load_x(p, n, px + u * pstep, c);
+          gs[u] = gn_bwd_load_g(p, n, px + u * pstep, C, c);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (px + u * pstep >= px1) break;
+        float dz[4], xh[4];
+        gn_bwd_dz(p, n, px + u * pstep, C, c, xs[u], gs[u], a, b, ra, rb, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) {
+__global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
   float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
@@ -236,23 +246,33 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
     const int dld = from0 ? p.C0 : p.C1, dc = from0 ? c : c - p.C0;
     const int acc = from0 ? p.acc0 : p.acc1;
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int px = px0 + prow; px < px1; px += pstep) {
-      const float4 x = gn_bwd_load_x(p, n, px, c);
-      const float4 g = gn_bwd_load_g(p, n, px, C, c);
+    for (int pxb = px0 + prow; pxb < px1; pxb += 2 * pstep) {
+      float4 xs[2], gs[2], ads[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (pxb + u * pstep < px1) {
+          xs[u] = gn_bwd_load_x(p, n, pxb + u * pstep, c);
+          gs[u] = gn_bwd_load_g(p, n, pxb + u * pstep, C, c);
+          if (p.addend) ads[u] = bw_ldg4(p.addend + ((size_t)n * p.HW + pxb + u * pstep) * C + c);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int px = pxb + u * pstep;
+        if (px >= px1) break;
+        const float4 x = xs[u], g = gs[u];
       float dz[4], xh[4], dx[4];
       gn_bwd_dz(p, n, px, C, c, x, g, a, b, ra, rb, dz, xh);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dx[i] = fmaf(dz[i], av[i], -q2v[i]) - xh[i] * q3v[i];
       if (p.addend) {
-        const float4 ad = bw_ldg4(p.addend + ((size_t)n * p.HW + px) * C + c);
+        const float4 ad = ads[u];
         dx[0] += ad.x; dx[1] += ad.y; dx[2] += ad.z; dx[3] += ad.w;
       }
       if (p.dx_bf16) {
-        uint2 u;
-        u.x = pack_bf16x2(dx[0], dx[1]);
-        u.y = pack_bf16x2(dx[2], dx[3]);
-        *reinterpret_cast<uint2*>(p.dx_bf16 + ((size_t)n * p.HW + px) * C + c) = u;
+        uint2 u2;
+        u2.x = pack_bf16x2(dx[0], dx[1]);
+        u2.y = pack_bf16x2(dx[2], dx[3]);
+        *reinterpret_cast<uint2*>(p.dx_bf16 + ((size_t)n * p.HW + px) * C + c) = u2;
       } else if (dst) {
         float4* o = reinterpret_cast<float4*>(dst + ((size_t)n * p.HW + px) * dld + dc);
         if (acc) {
@@ -263,6 +283,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) rs[i] += dx[i];
+      }
     }
     if (p.dx_rowsum || p.dx_colsum) {
 #pragma unroll
@@ -604,7 +625,8 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   p.dx_bf16 = reinterpret_cast<__nv_bfloat16*>(d->dx_bf16); p.dx_rowsum = d->dx_rowsum;
   p.rowsum_ld = d->dx_rowsum_ld ? d->dx_rowsum_ld : C; p.dx_colsum = d->dx_colsum;
   p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dscale = d->dscale; p.dshift = d->dshift; p.dss_ld = d->dss_ld;
-  int ppc = 32768 / C;
+  static const char* env_ppc = getenv("B200_GNB_ELEMS");
+  int ppc = (env_ppc ? atoi(env_ppc) : 16384) / C;
   if (ppc < 1) ppc = 1;
   if (ppc > d->HW) ppc = d->HW;
   p.pix_per_cta = ppc;

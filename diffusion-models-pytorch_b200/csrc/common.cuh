@@ -211,17 +211,26 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return d;
 }
 
-// Counter-based dropout: element e of a tensor is kept iff hash(seed, e) >= p * 2^32.  The same function regenerates the
-// mask in the backward pass (and in b200_dropout_mask for the parity tests), so no mask tensor is ever stored.
+// Counter-based dropout: the elements of a tensor are taken in groups of 4 consecutive indices (one 16-byte vector of
+// the NHWC kernels); group g gets two 32-bit hashes of (seed, g) = four 16-bit lanes, and element 4g+i is kept iff
+// lane i >= p * 2^16.  The same function regenerates the mask in the backward pass (and in b200_dropout_mask for the
+// parity tests), so no mask tensor is ever stored.  (16-bit resolution: p = 0.1 is realised as 0.100006.)
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-  return p <= 0.f ? 0u : (uint32_t)((double)p * 4294967296.0);
+  return p <= 0.f ? 0u : (uint32_t)((double)p * 65536.0 + 0.5);
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// keep bits of elements 4g .. 4g+3 in bits 0..3
+__device__ __forceinline__ uint32_t dropout_keep4(unsigned long long seed, unsigned long long g, uint32_t thresh) {
+  const uint32_t x = hash32((uint32_t)g ^ (uint32_t)seed ^ ((uint32_t)(g >> 32) * 0x9e3779b9u));
+  const uint32_t y = hash32(x + (uint32_t)(seed >> 32) + 0x85ebca6bu);
+  return ((x & 0xffffu) >= thresh ? 1u : 0u) | ((x >> 16) >= thresh ? 2u : 0u) | ((y & 0xffffu) >= thresh ? 4u : 0u) |
+         ((y >> 16) >= thresh ? 8u : 0u);
 }
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long e, uint32_t thresh) {
-  uint32_t x = (uint32_t)e ^ (uint32_t)seed;
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  x += (uint32_t)(e >> 32) * 0x9e3779b9u + (uint32_t)(seed >> 32);
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x >= thresh;
+  return (dropout_keep4(seed, e >> 2, thresh) >> (uint32_t)(e & 3)) & 1u;
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

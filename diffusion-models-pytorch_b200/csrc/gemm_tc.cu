@@ -33,7 +33,7 @@ struct GemmKParams {
   int8_t taps[9][4];                 // {dw, dh, plane, 0} of the B operand (the activation)
   // epilogue
   void* out;
-  int out_bf16, atomic;
+  int out_bf16, atomic, split_out;
   long long s_batch, s_head, s_m, s_n;
   float alpha;
 };
@@ -176,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&bars->acc_full, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-      const long long base = (long long)gb * p.s_batch + (long long)gh * p.s_head + (long long)m * p.s_m;
+      const long long base = (long long)(p.split_out ? ks : gb) * p.s_batch + (long long)gh * p.s_head + (long long)m * p.s_m;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         __syncwarp();
@@ -243,6 +243,25 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
   gemm_tc_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(mapA, mapB, p);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+// dw[co][ci][tap] (arbitrary strides) += sum over splits of scratch[split][tap][co][ci]: the second phase of the
+// weight gradient when the pixel range is split over CTAs (plain coalesced partial stores instead of atomics)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                                           int splits, int ntaps, int Cout, int Cin, long long s_co,
+                                                           long long s_ci, long long s_tap) {
+  const long long per_tap = (long long)Cout * Cin;
+  const long long per_split = per_tap * ntaps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_tap; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / Cin), ci = (int)(i - (long long)co * Cin);
+    float* o = dw + co * s_co + ci * s_ci;
+    for (int t = 0; t < ntaps; ++t) {
+      float acc = 0.f;
+      const float* src = scratch + (long long)t * per_tap + i;
+      for (int sp = 0; sp < splits; ++sp) acc += __ldg(src + (long long)sp * per_split);
+      o[t * s_tap] += acc;
+    }
+  }
 }
 
 static int g_sms = 0;
@@ -351,21 +370,45 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   p.kblocks = p.tiles_w * p.tiles_h * ((d->B + bn - 1) / bn);
   p.M = d->Cout; p.N = d->Cin;
   memcpy(p.taps, d->taps, sizeof(p.taps));
-  p.out = d->dw; p.out_bf16 = 0;
-  p.s_batch = 0; p.s_head = d->dw_tap_stride; p.s_m = d->dw_co_stride; p.s_n = d->dw_ci_stride;
   p.alpha = 1.f;
-  // split the pixel range so that the grid fills the machine (~2 waves); every split accumulates with atomics,
-  // which is also what lets repeated backward passes accumulate into an existing .grad
+  // split the pixel range so that the grid fills the machine (one wave of CTAs)
   const long tiles = (long)p.groups * p.m_tiles * p.n_tiles;
-  long ks = (2L * num_sms() + tiles - 1) / tiles;
+  long ks = (num_sms() + tiles - 1) / tiles;
   if (ks > p.kblocks) ks = p.kblocks;
   if (ks < 1) ks = 1;
+  {   // no empty split: the kernel gives every split ceil(kblocks / ksplit) K-blocks
+    const long per = (p.kblocks + ks - 1) / ks;
+    ks = (p.kblocks + per - 1) / per;
+  }
+  const long long per_split = (long long)d->ntaps * d->Cout * d->Cin;
+  const bool two_phase = d->scratch != nullptr && d->scratch_bytes >= (long long)ks * per_split * 4;
   p.ksplit = (int)ks;
-  p.atomic = 1;
+  if (two_phase) {
+    // phase 1: every split stores its partial [tap][co][ci] tile rows with plain vector stores (split = "batch" of
+    // the generic epilogue addressing: blockIdx decode gives ks; we fold it into the output pointer per CTA below)
+    p.out = d->scratch; p.out_bf16 = 0; p.atomic = 0;
+    p.s_batch = per_split;                       // indexed by the split (see kernel: conv mode uses ks as "gb")
+    p.s_head = (long long)d->Cout * d->Cin;      // tap
+    p.s_m = d->Cin; p.s_n = 1;
+    p.split_out = 1;
+  } else {
+    // single phase: atomics straight into the (strided) gradient tensor; also what lets repeated backward passes
+    // accumulate into an existing .grad
+    p.out = d->dw; p.out_bf16 = 0; p.atomic = 1;
+    p.s_batch = 0; p.s_head = d->dw_tap_stride; p.s_m = d->dw_co_stride; p.s_n = d->dw_ci_stride;
+  }
   CUtensorMap mapA, mapB;
   int rc = make_a_map(&mapA, d->dy, d->dy_C, d->Ho, d->Wo, 1, d->B, bw, bh, bn);
   if (rc) return rc;
   rc = make_a_map(&mapB, d->x, d->x_C, d->x_H, d->x_W, d->x_planes, d->B, bw, bh, bn);
   if (rc) return rc;
-  return launch_gemm(mapA, mapB, p, stream);
+  rc = launch_gemm(mapA, mapB, p, stream);
+  if (rc || !two_phase) return rc;
+  const long long per_tap = (long long)d->Cout * d->Cin;
+  long long g = (per_tap + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(reinterpret_cast<const float*>(d->scratch), d->dw, p.ksplit, d->ntaps,
+                                                      d->Cout, d->Cin, d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "wgrad_reduce_kernel launch");
 }

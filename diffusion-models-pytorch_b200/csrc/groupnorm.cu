@@ -374,10 +374,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
           if (p.apply_silu) { y0 = silu_tanh(y0); y1 = silu_tanh(y1); y2 = silu_tanh(y2); y3 = silu_tanh(y3); }
           if (p.drop_thresh) {
             const unsigned long long e = ((unsigned long long)n * p.HW + q) * C + c;
-            y0 = dropout_keep(p.drop_seed, e, p.drop_thresh) ? y0 * p.drop_scale : 0.f;
-            y1 = dropout_keep(p.drop_seed, e + 1, p.drop_thresh) ? y1 * p.drop_scale : 0.f;
-            y2 = dropout_keep(p.drop_seed, e + 2, p.drop_thresh) ? y2 * p.drop_scale : 0.f;
-            y3 = dropout_keep(p.drop_seed, e + 3, p.drop_thresh) ? y3 * p.drop_scale : 0.f;
+            const uint32_t keep = dropout_keep4(p.drop_seed, e >> 2, p.drop_thresh);
+            y0 = (keep & 1u) ? y0 * p.drop_scale : 0.f;
+            y1 = (keep & 2u) ? y1 * p.drop_scale : 0.f;
+            y2 = (keep & 4u) ? y2 * p.drop_scale : 0.f;
+            y3 = (keep & 8u) ? y3 * p.drop_scale : 0.f;
           }
           uint2 uo;
           uo.x = pack_bf16x2(y0, y1);
@@ -427,8 +428,9 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
         }
         if (p.drop_thresh) {
           const unsigned long long e = ((unsigned long long)n * p.HW + px) * C + c;
+          const uint32_t keep = dropout_keep4(p.drop_seed, e >> 2, p.drop_thresh);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = dropout_keep(p.drop_seed, e + i, p.drop_thresh) ? y[i] * p.drop_scale : 0.f;
+          for (int i = 0; i < 4; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * p.drop_scale : 0.f;
         }
         uint2 uo;
         uo.x = pack_bf16x2(y[0], y[1]);

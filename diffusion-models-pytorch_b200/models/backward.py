@@ -117,6 +117,14 @@ def _cast_out_grad(eng: Engine, tag, out: Act, bias_grad):
     return dob
 
 
+def _wgrad(eng: Engine, *args, **kw):
+    """b200_conv2d_wgrad with the engine's shared split-K workspace (two-phase, atomics-free reduction)."""
+    ws = eng._arena.get('wgrad_scratch')
+    if ws is None:
+        ws = eng._arena['wgrad_scratch'] = torch.empty(64 << 20, dtype=torch.float32, device=eng.device)   # 256 MB
+    return K.conv2d_wgrad(*args, scratch=ws, **kw)
+
+
 def _sums(eng: Engine, B, C):
     return eng.buf('gn_bwd_sums', (B, C, 2), torch.float32)
 
@@ -137,12 +145,12 @@ def _res_bwd(eng: Engine, e, G: _Grads):
 
     # conv2 (+ shortcut): bias, weights, data
     dob = _cast_out_grad(eng, tag + '.c2', out, G(conv2.bias))
-    K.conv2d_wgrad(dob, Cout, e['a2'], (Cout, Ho, Wo, 1), B, Ho, Wo, Cout, Cout, t3[0], G(conv2.weight))
+    _wgrad(eng, dob, Cout, e['a2'], (Cout, Ho, Wo, 1), B, Ho, Wo, Cout, Cout, t3[0], G(conv2.weight))
     addend = None
     if sc is not None:
         G(sc.bias).copy_(G(conv2.bias))
         k = sc.kernel_size[0]
-        K.conv2d_wgrad(dob, Cout, e['raw'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, (t1 if k == 1 else t3)[0],
+        _wgrad(eng, dob, Cout, e['raw'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, (t1 if k == 1 else t3)[0],
                        G(sc.weight))
         addend = eng.buf(tag + '.dcat', (B, H, W, Cin), torch.float32)
         K.conv2d(dob, _w_dgrad(eng, tag + '.sc', sc), Cin, B, H, W, t1 if k == 1 else t3, a0_geom=(Cout, H, W, 1),
@@ -166,7 +174,7 @@ def _res_bwd(eng: Engine, e, G: _Grads):
                     dx_colsum=G(conv1.bias), dgamma=G(norm2.weight), dbeta=G(norm2.bias), **kw)
 
     # conv1: weights, data
-    K.conv2d_wgrad(dh, Cout, e['a1'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, t3[0], G(conv1.weight))
+    _wgrad(eng, dh, Cout, e['a1'], (Cin, Ho, Wo, 1), B, Ho, Wo, Cout, Cin, t3[0], G(conv1.weight))
     da1 = eng.buf(tag + '.dA1', (B, Ho, Wo, Cin), torch.bfloat16)
     K.conv2d(dh, _w_dgrad(eng, tag + '.c1', conv1), Cin, B, Ho, Wo, t3, a0_geom=(Cout, Ho, Wo, 1), out=da1,
              out_mode=K.OUT_BF16_NHWC)
@@ -201,7 +209,7 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     bf = torch.bfloat16
 
     dob = _cast_out_grad(eng, tag + '.proj', out, G(proj.bias))
-    K.conv2d_wgrad(dob, C, o, (C, H, W, 1), B, H, W, C, C, t1[0], G(proj.weight))
+    _wgrad(eng, dob, C, o, (C, H, W, 1), B, H, W, C, C, t1[0], G(proj.weight))
     do = eng.buf(tag + '.dO', (B, T, C), bf)
     K.conv2d(dob, _w_dgrad(eng, tag + '.proj', proj), C, B, H, W, t1, a0_geom=(C, H, W, 1), out=do,
              out_mode=K.OUT_BF16_NHWC)
@@ -237,9 +245,9 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     K.colsum_bf16(dqk, G(q.bias), B * T, 2 * C, 0, C)
     K.colsum_bf16(dqk, G(k.bias), B * T, 2 * C, C, C)
     K.colsum_bf16(dv, G(v.bias), B * T, C, 0, C)
-    K.conv2d_wgrad(dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(q.weight))
-    K.conv2d_wgrad(dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(k.weight), dy_c0=C)
-    K.conv2d_wgrad(dv, C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(v.weight))
+    _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(q.weight))
+    _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(k.weight), dy_c0=C)
+    _wgrad(eng, dv, C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(v.weight))
     wd = eng.packed(('dgrad', tag + '.qkv'), lambda: torch.cat(
         [m.weight.detach().reshape(C, C).t() for m in (q, k, v)], dim=1).to(bf).contiguous())     # [C_in][3C]
     dn = eng.buf(tag + '.dN', (B, H, W, C), bf)
@@ -280,7 +288,7 @@ def _down_bwd(eng: Engine, e, G: _Grads):
     B, H, W, C = x.B, x.H, x.W, x.C
     Ho, Wo, Cout = out.H, out.W, out.C
     dob = _cast_out_grad(eng, tag, out, G(conv.bias))
-    K.conv2d_wgrad(dob, Cout, e['planes'], (C, Ho, Wo, 4), B, Ho, Wo, Cout, C, K.taps_3x3_s2(e['pad_lo'])[0],
+    _wgrad(eng, dob, Cout, e['planes'], (C, Ho, Wo, 4), B, Ho, Wo, Cout, C, K.taps_3x3_s2(e['pad_lo'])[0],
                    G(conv.weight))
     taps, wd = eng.packed(('dgrad_s2', tag), lambda: _s2_dgrad_plan(conv, e['pad_lo']))
     gx, acc = _grad_slot(eng, x)
@@ -294,7 +302,7 @@ def _up_bwd(eng: Engine, e, G: _Grads):
     Ho, Wo, Cout = out.H, out.W, out.C
     t3 = K.taps_3x3_s1()
     dob = _cast_out_grad(eng, tag, out, G(conv.bias))
-    K.conv2d_wgrad(dob, Cout, e['ub'], (C, Ho, Wo, 1), B, Ho, Wo, Cout, C, t3[0], G(conv.weight))
+    _wgrad(eng, dob, Cout, e['ub'], (C, Ho, Wo, 1), B, Ho, Wo, Cout, C, t3[0], G(conv.weight))
     du = eng.buf(tag + '.dU', (B, Ho, Wo, C), torch.float32)
     K.conv2d(dob, _w_dgrad(eng, tag, conv), C, B, Ho, Wo, t3, a0_geom=(Cout, Ho, Wo, 1), out=du)
     gx, acc = _grad_slot(eng, x)
@@ -308,7 +316,7 @@ def _head_bwd(eng: Engine, e, G: _Grads, dout):
     t3 = K.taps_3x3_s1()
     dob = eng.buf(tag + '.dOb', (B, H, W, 64), torch.bfloat16)
     K.nchw_to_nhwc_pad_bf16(dout, dob, G(conv.bias), B, Co, H * W, 64)
-    K.conv2d_wgrad(dob, 64, e['a'], (C, H, W, 1), B, H, W, Co, C, t3[0], G(conv.weight))
+    _wgrad(eng, dob, 64, e['a'], (C, H, W, 1), B, H, W, Co, C, t3[0], G(conv.weight))
 
     def make():   # data-gradient weights with the output channels zero-padded to the 64-channel operand
         w = conv.weight.detach().flip(2, 3).transpose(0, 1)          # [C, Co, 3, 3]
@@ -332,7 +340,7 @@ def _first_bwd(eng: Engine, e, G: _Grads):
     dob = _cast_out_grad(eng, tag, out, G(conv.bias))
     xp = eng.buf(tag + '.xpad', (B, H, W, 64), torch.bfloat16)
     K.nchw_to_nhwc_pad_bf16(X, xp, None, B, Ci, H * W, 64)
-    K.conv2d_wgrad(dob, Co, xp, (64, H, W, 1), B, H, W, Co, Ci, K.taps_3x3_s1()[0], G(conv.weight))
+    _wgrad(eng, dob, Co, xp, (64, H, W, 1), B, H, W, Co, Ci, K.taps_3x3_s1()[0], G(conv.weight))
 
 
 def _embed_bwd(eng: Engine, e, G: _Grads):

@@ -236,6 +236,10 @@ typedef struct b200_wgrad_desc {
   int8_t taps[9][4];        /* {dw, dh, plane, 0} */
   float* dw;
   long long dw_co_stride, dw_ci_stride, dw_tap_stride;
+  void* scratch;            /* optional fp32 workspace: when it holds splits * ntaps * Cout * Cin floats the pixel-range
+                               splits store plain partial tiles there and a second kernel reduces them into dw
+                               (deterministic, no atomics); otherwise the splits accumulate into dw with atomics */
+  long long scratch_bytes;
 } b200_wgrad_desc;
 
 int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream);

@@ -478,7 +478,7 @@ def case_gemm():
     return ok
 
 
-def _wgrad_case(name, B, H, W, Cin, Cout, kind):
+def _wgrad_case(name, B, H, W, Cin, Cout, kind, scratch=False):
     """dW of a conv executed by b200_conv2d_fwd vs autograd of F.conv2d on the bf16-rounded operands."""
     torch.backends.cudnn.allow_tf32 = False
     x = _bf16r(_gen(B, Cin, H, W, seed=1))
@@ -491,13 +491,14 @@ def _wgrad_case(name, B, H, W, Cin, Cout, kind):
     dyb = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
     xb = x.permute(0, 2, 3, 1).contiguous()
     dw = torch.zeros(Cout, Cin, k, k, device=DEV)
+    ws = torch.full((16 << 20,), float('nan'), device=DEV) if scratch else None     # two-phase split reduction
     if kind == 's2':
         planes = torch.empty(B, 4, H // 2, W // 2, Cin, device=DEV, dtype=torch.bfloat16)
         K.cast_bf16(xb, planes, B, H, W, Cin, parity_split=True)
-        K.conv2d_wgrad(dyb, Cout, planes, (Cin, H // 2, W // 2, 4), B, Ho, Wo, Cout, Cin, K.taps_3x3_s2(1)[0], dw)
+        K.conv2d_wgrad(dyb, Cout, planes, (Cin, H // 2, W // 2, 4), B, Ho, Wo, Cout, Cin, K.taps_3x3_s2(1)[0], dw, scratch=ws)
     else:
         taps = K.taps_3x3_s1()[0] if kind == '3x3' else K.taps_1x1()[0]
-        K.conv2d_wgrad(dyb, Cout, xb.to(torch.bfloat16), (Cin, H, W, 1), B, Ho, Wo, Cout, Cin, taps, dw)
+        K.conv2d_wgrad(dyb, Cout, xb.to(torch.bfloat16), (Cin, H, W, 1), B, Ho, Wo, Cout, Cin, taps, dw, scratch=ws)
     torch.cuda.synchronize()
     return _report(name, dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
 
@@ -509,6 +510,11 @@ def case_wgrad():
     ok &= _wgrad_case('wgrad 3x3 64->64 @8x8 B=5', 5, 8, 8, 64, 64, '3x3')
     ok &= _wgrad_case('wgrad 1x1 512->256 @8x8 B=4', 4, 8, 8, 512, 256, '1x1')
     ok &= _wgrad_case('wgrad 3x3 stride 2 128->128 @32x32 B=2', 2, 32, 32, 128, 128, 's2')
+    ok &= _wgrad_case('wgrad two-phase 3x3 256->256 @16x16 B=8', 8, 16, 16, 256, 256, '3x3', scratch=True)
+    ok &= _wgrad_case('wgrad two-phase 3x3 384->128 @32x32 B=3', 3, 32, 32, 384, 128, '3x3', scratch=True)
+    ok &= _wgrad_case('wgrad two-phase 1x1 512->256 @8x8 B=4', 4, 8, 8, 512, 256, '1x1', scratch=True)
+    ok &= _wgrad_case('wgrad two-phase stride 2 128->128 @32x32 B=2', 2, 32, 32, 128, 128, 's2', scratch=True)
+    ok &= _wgrad_case('wgrad two-phase 3x3 64->64 @8x8 B=5', 5, 8, 8, 64, 64, '3x3', scratch=True)
     return ok
 
 

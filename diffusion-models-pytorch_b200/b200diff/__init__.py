@@ -85,6 +85,15 @@ class GnBwdDesc(Structure):
                 ('dscale', c_void_p), ('dshift', c_void_p), ('dss_ld', c_int)]
 
 
+class OdeDesc(Structure):
+    _fields_ = [('model_out', c_void_p), ('x', c_void_p), ('d1', c_void_p), ('x1', c_void_p),
+                ('B', c_int), ('C', c_int), ('Cm', c_int), ('HW', c_int),
+                ('objective', c_int), ('clip', c_int), ('second_order', c_int),
+                ('sqrt_recip_ac', c_float), ('sqrt_recipm1_ac', c_float), ('sqrt_ac', c_float), ('sqrt_1m_ac', c_float),
+                ('sigma_t', c_float), ('sigma_prev', c_float),
+                ('sample', c_void_p), ('pred_x0', c_void_p), ('deriv', c_void_p)]
+
+
 class OptimDesc(Structure):
     _fields_ = [('chunks', c_void_p), ('n_chunks', c_int), ('lr', c_float), ('beta1', c_float), ('beta2', c_float),
                 ('eps', c_float), ('weight_decay', c_float), ('adamw', c_int), ('step', c_int),
@@ -140,6 +149,7 @@ def lib():
     L.b200_softmax_bwd_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
     L.b200_time_embed_bwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 14
     L.b200_optimizer_step.argtypes = [POINTER(OptimDesc), c_void_p]
+    L.b200_ode_step.argtypes = [POINTER(OdeDesc), c_void_p]
     L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for name in BACKWARD_SYMBOLS:
@@ -159,7 +169,7 @@ BACKWARD_SYMBOLS = (
     'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
     'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
     'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad', 'b200_time_embed_bwd',
-    'b200_optimizer_step',
+    'b200_optimizer_step', 'b200_ode_step',
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
@@ -599,3 +609,18 @@ def time_embed_bwd(t, freqs, dim, E, cos_first, w1, b1, w2, emb, d_semb, y, pe, 
                                      b1.data_ptr(), w2.data_ptr(), emb.data_ptr(), d_semb.data_ptr(), _ptr(y),
                                      pe.data_ptr(), hid.data_ptr(), demb.data_ptr(), dpre.data_ptr(), db1.data_ptr(),
                                      db2.data_ptr(), _ptr(dclass), _stream()), 'time_embed_bwd')
+
+
+def ode_step(model_out, x, coefs, sigma_t, sigma_prev, *, objective='pred_eps', clip=True, d1=None, x1=None, sample=None,
+             pred_x0=None, deriv=None):
+    """coefs = (sqrt(1/ac), sqrt(1/ac - 1), sqrt(ac), sqrt(1 - ac)) of the evaluation timestep, as Python floats."""
+    _need_cuda(model_out, x)
+    d = OdeDesc()
+    d.model_out, d.x, d.d1, d.x1 = model_out.data_ptr(), x.data_ptr(), _ptr(d1), _ptr(x1)
+    d.B, d.C, d.Cm, d.HW = x.shape[0], x.shape[1], model_out.shape[1], x[0, 0].numel()
+    d.objective, d.clip, d.second_order = OBJ[objective], int(clip), int(d1 is not None)
+    d.sqrt_recip_ac, d.sqrt_recipm1_ac, d.sqrt_ac, d.sqrt_1m_ac = [float(c) for c in coefs]
+    d.sigma_t, d.sigma_prev = float(sigma_t), float(sigma_prev)
+    d.sample, d.pred_x0, d.deriv = _ptr(sample), _ptr(pred_x0), _ptr(deriv)
+    _launch('ode_step', lambda: _check(lib().b200_ode_step(ctypes.byref(d), _stream()), 'ode_step'),
+            nbytes=4.0 * x.numel() * (2 + sum(v is not None for v in (d1, x1, sample, pred_x0, deriv))))

@@ -72,9 +72,70 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerK k) {
   }
 }
 
+// Euler / Heun steps in sigma space (diffusions/euler.py:50-66, diffusions/heun.py:56-107; Karras et al. 2022):
+//   x0 = predict(model_out, x, t_eval);  bar = sqrt(1 + s_eval^2) x;  d = (bar - x0) / s_eval
+//   first order : sample = (bar + d (s_prev - s_t)) / sqrt(1 + s_prev^2)            (x = x_t, s_eval = s_t)
+//   second order: d = (d + d1) / 2; bar_t = sqrt(1 + s_t^2) x1; sample = (bar_t + d (s_prev - s_t)) / sqrt(1 + s_prev^2)
+//                 (x = the first-order sample, s_eval = s_prev, d1 / x1 = derivative and x_t of the first-order step)
+struct OdeK {
+  const float* mo; const float* x; const float* d1; const float* x1;
+  int C, Cm, HW, objective, clip, second;
+  float c_rx, c_rm1, c_sa, c_s1ma, sig_t, sig_prev;
+  float* sample; float* pred_x0; float* deriv;
+  size_t total;
+};
+
+__global__ void __launch_bounds__(256) ode_step_kernel(const OdeK k) {
+  const size_t chw = (size_t)k.C * k.HW;
+  const float sig_eval = k.second ? k.sig_prev : k.sig_t;
+  const float up_eval = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(sig_eval, sig_eval)));
+  const float up_t = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(k.sig_t, k.sig_t)));
+  const float down = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(k.sig_prev, k.sig_prev)));
+  const float dsig = __fsub_rn(k.sig_prev, k.sig_t);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k.total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / chw;
+    const size_t mi = b * (size_t)k.Cm * k.HW + (i - b * chw);
+    const float x = k.x[i];
+    float x0;
+    predict_eps(k.mo[mi], x, k.objective, k.clip, k.c_rx, k.c_rm1, k.c_sa, k.c_s1ma, x0);
+    const float bar = __fmul_rn(up_eval, x);
+    float d = __fdiv_rn(__fsub_rn(bar, x0), sig_eval);
+    float base = bar;
+    if (k.second) {
+      d = __fdiv_rn(__fadd_rn(d, k.d1[i]), 2.0f);
+      base = __fmul_rn(up_t, k.x1[i]);
+    }
+    const float s = __fdiv_rn(__fadd_rn(base, __fmul_rn(d, dsig)), down);
+    if (k.sample) k.sample[i] = s;
+    if (k.pred_x0) k.pred_x0[i] = x0;
+    if (k.deriv) k.deriv[i] = d;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_ode_step(const b200_ode_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(d && d->model_out && d->x, "ode_step: null model_out/x");
+  B200_REQUIRE(d->Cm >= d->C, "ode_step: model channels %d < C=%d", d->Cm, d->C);
+  B200_REQUIRE(d->objective >= 0 && d->objective <= 2, "ode_step: bad objective");
+  B200_REQUIRE(!d->second_order || (d->d1 && d->x1), "ode_step: the second-order step needs d1 and x1");
+  OdeK k;
+  k.mo = d->model_out; k.x = d->x; k.d1 = d->d1; k.x1 = d->x1;
+  k.C = d->C; k.Cm = d->Cm; k.HW = d->HW; k.objective = d->objective; k.clip = d->clip; k.second = d->second_order;
+  k.c_rx = d->sqrt_recip_ac; k.c_rm1 = d->sqrt_recipm1_ac; k.c_sa = d->sqrt_ac; k.c_s1ma = d->sqrt_1m_ac;
+  k.sig_t = d->sigma_t; k.sig_prev = d->sigma_prev;
+  k.sample = d->sample; k.pred_x0 = d->pred_x0; k.deriv = d->deriv;
+  k.total = (size_t)d->B * d->C * d->HW;
+  size_t g = (k.total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g == 0) g = 1;
+  ode_step_kernel<<<(int)g, 256, 0, stream>>>(k);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "ode_step launch");
+}
 
 extern "C" int b200_sampler_step(const b200_sampler_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

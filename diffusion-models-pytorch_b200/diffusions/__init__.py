@@ -3,3 +3,5 @@ from .schedule import get_beta_schedule, get_respaced_seq
 
 from .ddpm import DDPM, DDPMCFG
 from .ddim import DDIM, DDIMCFG
+from .euler import EulerSampler
+from .heun import HeunSampler

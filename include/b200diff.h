@@ -179,6 +179,22 @@ typedef struct b200_sampler_desc {
 
 int b200_sampler_step(const b200_sampler_desc* d, void* stream);
 
+/* Euler / Heun sampler steps in sigma space (diffusions/euler.py:50-66, diffusions/heun.py:56-107), sigma = sqrt((1-ac)/ac).
+ * The predict coefficients are those of the evaluation timestep (t for the first-order step, t_prev for Heun's second
+ * evaluation); second_order = 1 averages the derivative with d1 and restarts from x1 (both saved by the first step). */
+typedef struct b200_ode_desc {
+  const float* model_out;    /* [B][Cm][HW] */
+  const float* x;            /* [B][C][HW]: x_t (first order) or the first-order sample (second order) */
+  const float* d1;           /* second order: derivative of the first-order step */
+  const float* x1;           /* second order: x_t of the first-order step */
+  int B, C, Cm, HW;
+  int objective, clip, second_order;
+  float sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac, sqrt_1m_ac;
+  float sigma_t, sigma_prev;
+  float* sample; float* pred_x0; float* deriv;   /* each optional */
+} b200_ode_desc;
+int b200_ode_step(const b200_ode_desc* d, void* stream);
+
 /* q(x_t | x_0) (diffusions/ddpm.py:152-172): xt = sqrt(ac[t_b]) x0 + sqrt(1-ac[t_b]) eps, per-sample t. */
 int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
                  int B, int CHW, void* stream);

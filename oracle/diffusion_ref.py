@@ -211,3 +211,43 @@ class DDIMRef(DDPMRef):
             reverse_eps = torch.randn_like(xt)
         sample = mean if t == 0 else mean + torch.sqrt(var) * reverse_eps
         return {'sample': sample, 'mean': mean, 'var': var, 'pred_x0': x0, 'pred_eps': eps, 'reverse_eps': reverse_eps}
+
+
+# ------------------------------------------------------------------------------------------------------
+# Euler / Heun samplers (diffusions/euler.py:46-66, diffusions/heun.py:48-131)
+# ------------------------------------------------------------------------------------------------------
+class EulerRef(DDPMRef):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod).sqrt()
+
+    def _sig(self, t, t_prev):
+        return self.sigmas[t], (self.sigmas[t_prev] if t_prev >= 0 else torch.tensor(0.0))
+
+    def denoise(self, model_output, xt, t, t_prev, reverse_eps=None):
+        st, sp = self._sig(t, t_prev)
+        x0 = self.predict(model_output, xt, t)['pred_x0']
+        bar_xt = (1 + st ** 2).sqrt() * xt
+        derivative = (bar_xt - x0) / st
+        bar_sample = bar_xt + derivative * (sp - st)
+        return {'sample': bar_sample / (1 + sp ** 2).sqrt(), 'pred_x0': x0, 'derivative': derivative}
+
+
+class HeunRef(EulerRef):
+    def sample_loop(self, model, init_noise, noises=None, model_kwargs=None):
+        kw = model_kwargs or {}
+        img = init_noise
+        for (t, tp) in self._pairs():
+            tb = torch.full((img.shape[0],), t, dtype=torch.long, device=img.device)
+            first = EulerRef.denoise(self, model(img, tb, **kw), img, t, tp)
+            out, x_first, img = first, img, first['sample']
+            if tp >= 0:
+                st, sp = self._sig(t, tp)
+                tpb = torch.full((img.shape[0],), tp, dtype=torch.long, device=img.device)
+                x0 = self.predict(model(img, tpb, **kw), img, tp)['pred_x0']
+                bar_prev = (1 + sp ** 2).sqrt() * img
+                derivative = ((bar_prev - x0) / sp + first['derivative']) / 2
+                bar_xt = (1 + st ** 2).sqrt() * x_first
+                out = {'sample': (bar_xt + derivative * (sp - st)) / (1 + sp ** 2).sqrt(), 'pred_x0': x0}
+                img = out['sample']
+            yield out

@@ -383,6 +383,28 @@ def case_train_step():
     return ok
 
 
+def case_ode_sampling():
+    """Euler-20 / Heun-10 sampling (CIFAR-10 UNet, B=8) through EulerSampler / HeunSampler vs the fp32 oracle loops."""
+    _no_tf32()
+    m, ref = _build(CIFAR)
+    B = 8
+    x0 = torch.randn(B, 3, 32, 32, generator=torch.Generator(device='cpu').manual_seed(5)).to(DEV)
+    ok = True
+    for tag, cls, ocls, steps in (('euler20', diffusions.EulerSampler, R.EulerRef, 20),
+                                  ('heun10', diffusions.HeunSampler, R.HeunRef, 10)):
+        ours = cls(total_steps=1000, respace_type='uniform', respace_steps=steps, device=DEV)
+        orc = ocls(total_steps=1000, respace_type='uniform', respace_steps=steps)
+        orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+        orc.sigmas = orc.sigmas.to(DEV)
+        with torch.no_grad():
+            got = ours.sample(m, x0, tqdm_kwargs=dict(disable=True))
+            want = orc.sample(ref, x0)
+        psnr = _psnr(got.clamp(-1, 1), want.clamp(-1, 1))
+        _emit(case=f'{tag} final sample PSNR', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+        ok &= psnr >= 40.0
+    return ok
+
+
 def case_timing():
     """Orientation numbers (not the bench): forward and DDIM-50 at B=256."""
     m, _ = _build(CIFAR)

@@ -711,6 +711,35 @@ def case_optimizer():
 
 
 # ----------------------------------------------------------------------------------------------------
+# Euler / Heun ODE steps vs the reference's outputs frozen in tests/golden/ode_samplers.pt
+# ----------------------------------------------------------------------------------------------------
+def case_ode_samplers():
+    import diffusions
+    g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ode_samplers.pt'), weights_only=False)
+    xt, mo, d1 = g['xt'].to(DEV), g['mo'].to(DEV), g['d1'].to(DEV)
+    ok = True
+    worst = 0.0
+    for c in g['steps']:
+        kw = dict(objective=c['objective'], clip_denoised=c['clip'], beta_schedule=c['beta'], device=DEV, **g['kw0'])
+        e = diffusions.EulerSampler(**kw)
+        o = e.denoise(mo.clone(), xt, c['t'], c['t_prev'])
+        for k in ('sample', 'pred_x0'):
+            worst = max(worst, (o[k].cpu() - c['euler'][k]).abs().max().item() / max(1.0, c['euler'][k].abs().max().item()))
+        if 'heun2' in c:
+            h = diffusions.HeunSampler(**kw)
+            h.denoise_1st_order(mo.clone(), xt, c['t'], c['t_prev'])
+            h._1st_order_derivative, h._1st_order_xt = d1.clone(), xt.clone()
+            o2 = h.denoise_2nd_order(mo.clone(), xt * 0.9, c['t'], c['t_prev'])
+            for k in ('sample', 'pred_x0'):
+                worst = max(worst, (o2[k].cpu() - c['heun2'][k]).abs().max().item() /
+                            max(1.0, c['heun2'][k].abs().max().item()))
+    good = worst <= 2e-6
+    print(json.dumps({'case': f'euler/heun single steps ({len(g["steps"])} cases) vs reference golden',
+                      'max_rel_err': worst, 'gate': 2e-6, 'ok': good}), flush=True)
+    return ok and good
+
+
+# ----------------------------------------------------------------------------------------------------
 # sampler step vs the eager op sequence of the reference (restated in oracle/diffusion_ref.py)
 # ----------------------------------------------------------------------------------------------------
 def case_sampler():

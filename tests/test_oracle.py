@@ -193,3 +193,20 @@ def test_adm_conditioning_contract():
         m2(x, t, torch.zeros(1, dtype=torch.long))
     with pytest.raises(RuntimeError):      # CPU tensors: no fallback
         m2.eval()(x, t)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Euler / Heun samplers (fixtures from oracle/gen_golden_samplers.py)
+# ------------------------------------------------------------------------------------------------------
+def test_ode_samplers_match_reference(golden_dir, gold):
+    g = torch.load(os.path.join(golden_dir, 'ode_samplers.pt'), weights_only=False)
+    for c in g['steps']:
+        d = R.EulerRef(objective=c['objective'], clip_denoised=c['clip'], beta_schedule=c['beta'], **g['kw0'])
+        o = d.denoise(g['mo'].clone(), g['xt'], c['t'], c['t_prev'])
+        assert torch.equal(o['sample'], c['euler']['sample']) and torch.equal(o['pred_x0'], c['euler']['pred_x0'])
+    cfg = gold['unet_forward']['tiny']['cfg']
+    orc = UNetRef(_product_state_dict('tiny', cfg, 2022), dim=32, n_heads=1)
+    with torch.no_grad():
+        for tag, cls in (('euler10', R.EulerRef), ('heun10', R.HeunRef)):
+            got = cls(respace_type='uniform', respace_steps=10).sample(orc, g['x0'])
+            assert torch.allclose(got, g['runs'][tag], rtol=0, atol=1e-4), tag

@@ -150,6 +150,7 @@ def lib():
     L.b200_time_embed_bwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 14
     L.b200_optimizer_step.argtypes = [POINTER(OptimDesc), c_void_p]
     L.b200_ode_step.argtypes = [POINTER(OdeDesc), c_void_p]
+    L.b200_to_uint8_hwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for name in BACKWARD_SYMBOLS:
@@ -169,7 +170,7 @@ BACKWARD_SYMBOLS = (
     'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
     'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
     'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad', 'b200_time_embed_bwd',
-    'b200_optimizer_step', 'b200_ode_step',
+    'b200_optimizer_step', 'b200_ode_step', 'b200_to_uint8_hwc',
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
@@ -624,3 +625,13 @@ def ode_step(model_out, x, coefs, sigma_t, sigma_prev, *, objective='pred_eps', 
     d.sample, d.pred_x0, d.deriv = _ptr(sample), _ptr(pred_x0), _ptr(deriv)
     _launch('ode_step', lambda: _check(lib().b200_ode_step(ctypes.byref(d), _stream()), 'ode_step'),
             nbytes=4.0 * x.numel() * (2 + sum(v is not None for v in (d1, x1, sample, pred_x0, deriv))))
+
+
+def to_uint8_hwc(x, out=None):
+    """fp32 NCHW samples in [-1, 1] -> uint8 NHWC pixels with torchvision.save_image's rounding (the output stage)."""
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device)
+    _check(lib().b200_to_uint8_hwc(x.contiguous().data_ptr(), out.data_ptr(), B, C, H * W, _stream()), 'to_uint8_hwc')
+    return out

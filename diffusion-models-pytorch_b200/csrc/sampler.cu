@@ -112,9 +112,40 @@ __global__ void __launch_bounds__(256) ode_step_kernel(const OdeK k) {
   }
 }
 
+// Output stage after the sampling loop (scripts/sample_uncond.py:189-195 + utils/misc.py image_norm_to_float +
+// torchvision.utils.save_image's quantisation): fp32 NCHW in [-1, 1] -> uint8 NHWC, one pass on the device:
+//   u8 = trunc(clamp(((clamp(x, -1, 1) + 1) / 2) * 255 + 0.5, 0, 255))
+// so that only B*H*W*C bytes (a quarter of the fp32 tensor, already in PNG row order) cross PCIe.
+__global__ void __launch_bounds__(256) to_uint8_hwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int C,
+                                                           int HW) {
+  const size_t total = (size_t)B * HW * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t pix = i / C;
+    const int hw = (int)(pix % HW);
+    const size_t b = pix / HW;
+    float v = x[(b * C + c) * HW + hw];
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    v = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    out[i] = (uint8_t)v;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_to_uint8_hwc(const float* x, uint8_t* out, int B, int C, int HW, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out && B >= 1 && C >= 1 && HW >= 1, "to_uint8_hwc: bad arguments");
+  size_t g = ((size_t)B * C * HW + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  to_uint8_hwc_kernel<<<(int)g, 256, 0, stream>>>(x, out, B, C, HW);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "to_uint8_hwc launch");
+}
 
 extern "C" int b200_ode_step(const b200_ode_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

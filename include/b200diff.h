@@ -195,6 +195,10 @@ typedef struct b200_ode_desc {
 } b200_ode_desc;
 int b200_ode_step(const b200_ode_desc* d, void* stream);
 
+/* Output stage (scripts/sample_uncond.py:189-195, utils/misc.py image_norm_to_float, torchvision save_image):
+ * fp32 NCHW samples -> uint8 NHWC pixels, out = trunc(clamp((clamp(x,-1,1)+1)/2*255 + 0.5, 0, 255)). */
+int b200_to_uint8_hwc(const float* x, uint8_t* out, int B, int C, int HW, void* stream);
+
 /* q(x_t | x_0) (diffusions/ddpm.py:152-172): xt = sqrt(ac[t_b]) x0 + sqrt(1-ac[t_b]) eps, per-sample t. */
 int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
                  int B, int CHW, void* stream);

@@ -666,6 +666,13 @@ def case_backward_misc():
     gs = torch.tensor([0.5], device=DEV)
     K.mse_loss_grad(a, b, gs, da)
     ok &= _report('mse_loss_grad', da, 0.5 * 2 * (a - b) / a.numel(), rtol=1e-5, atol=1e-9)
+    # output stage: uint8 HWC with torchvision.save_image's quantisation
+    xs = _gen(5, 3, 32, 32, seed=9) * 0.8
+    u8 = K.to_uint8_hwc(xs)
+    ref8 = ((xs.clamp(-1, 1) + 1) / 2).mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    same = bool(torch.equal(u8, ref8))
+    print(json.dumps({'case': 'to_uint8_hwc (bit-exact vs torchvision quantisation)', 'ok': same}), flush=True)
+    ok &= same
     # dropout keep rate
     m = K.dropout_mask(torch.empty(1 << 20, device=DEV), 0.1, 42)
     rate = 1 - m.mean().item()

@@ -41,6 +41,7 @@ class Engine:
         self._sig = None
         self._arena: Dict = {}
         self._stats: Dict = {}
+        self._stats_pools: List = []
         self.tape = None         # training forward: list of records replayed in reverse by models/backward.py
         self.drop_seed = 0       # base seed of this forward's dropout masks
         self._n_drop = 0
@@ -65,14 +66,23 @@ class Engine:
         key = (tag, B, C, self.device)
         t = self._stats.get(key)
         if t is None:
-            t = torch.zeros((B, C, 2), dtype=torch.float32, device=self.device)
+            # sub-allocated from a few large pool tensors so that one forward needs one memset per pool, not one
+            # tiny kernel per GroupNorm input (70 of them for the CIFAR-10 UNet)
+            n = B * C * 2
+            if (not self._stats_pools or self._stats_pools[-1][1] + n > self._stats_pools[-1][0].numel()
+                    or self._stats_pools[-1][0].device != self.device):
+                cap = max(n, 8 << 20)
+                self._stats_pools.append([torch.zeros(cap, dtype=torch.float32, device=self.device), 0])
+            pool = self._stats_pools[-1]
+            t = pool[0][pool[1]:pool[1] + n].view(B, C, 2)
+            pool[1] += (n + 63) // 64 * 64
             self._stats[key] = t
         return t
 
     def begin_forward(self):
         self.refresh()
-        if self._stats:
-            torch._foreach_zero_(list(self._stats.values()))
+        for pool, used in self._stats_pools:
+            pool[:used].zero_()
 
     def refresh(self):
         """Drops the packed bf16 weights when any parameter was modified or moved."""

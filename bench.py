@@ -284,6 +284,14 @@ def run_ours(args):
         line['roofline_groupnorm'] = {'kernel': 'groupnorm_apply_kernel', 'bound': 'hbm', 'achieved': gbs,
                                       'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
                                       'traffic': None}
+    if world == 1 and not args.no_extras:
+        # free the headline model's arena before the (larger) secondary workloads
+        del model, diffuser
+        torch.cuda.empty_cache()
+        try:
+            line['extras'] = _extras(dev, peaks)
+        except Exception as e:  # noqa: BLE001  (secondary numbers must never cost the headline line)
+            line['extras'] = {'error': repr(e)}
     if stdout_fd is not None:
         torch.cuda.synchronize()
         dist.destroy_process_group()
@@ -301,6 +309,92 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
+def _extras(dev, peaks):
+    """Secondary workloads of BASELINE.json on the same GPU, same timing rules (CUDA events, warm-up, inputs resident):
+    (1) ADM ImageNet-256 class-conditional UNet forward, batch 16 (configs[4]; north_star: >= 60 % of bf16 peak), as a
+    CUDA-graph replay of one forward; (2) one classifier-free-guidance training step (configs[2]: UNetCategorialAdaGN,
+    batch 128, dropout 0.1): loss_func -> hand-written backward -> fused clip + Adam + EMA."""
+    import b200diff as K
+    import diffusions
+    import models
+    from b200diff.optim import FusedAdam
+    from b200diff.train import TrainStep
+    from models.adm.unet import UNetModel
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    # ---- (1) ADM-256 forward ----
+    adm = dict(image_size=256, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=2,
+               attention_resolutions=[32, 16, 8], dropout=0.0, channel_mult=[1, 1, 2, 2, 4, 4], num_classes=1000,
+               num_heads=4, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True)
+    torch.manual_seed(2022)
+    m = UNetModel(**adm)
+    gen = torch.Generator().manual_seed(2022)
+    with torch.no_grad():      # ADM zero-initialises conv2 / proj_out / out: re-draw them N(0, 0.02) (SURVEY section 8d)
+        for p_ in m.parameters():
+            if not bool(p_.any()):
+                p_.copy_(torch.randn(p_.shape, generator=gen) * 0.02)
+    m = m.to(dev).eval()
+    B = 16
+    x = torch.randn(B, 3, 256, 256, device=dev)
+    t = torch.full((1,), 500, device=dev, dtype=torch.long).expand(B)
+    y = (torch.arange(B, device=dev) % 1000)
+    o = torch.empty(B, 6, 256, 256, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            m(x, t, y, out=o)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            m(x, t, y, out=o)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    tf = 2239.67e9 * B / (ms * 1e-3) / 1e12
+    out['adm256_forward'] = {'workload': 'ADM ImageNet-256 class-cond UNet forward (guided-diffusion 256x256_diffusion.yaml), '
+                                         'batch 16, random weights', 'ms_per_forward': ms, 'tflops': tf,
+                             'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
+                             'gflop_per_image': 2239.67, 'images_fwd_per_s': B / (ms * 1e-3)}
+    del m, g, x, o
+    torch.cuda.empty_cache()
+    # ---- (2) CFG training step ----
+    cfgc = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+                num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+    torch.manual_seed(2022)
+    model = models.UNetCategorialAdaGN(**cfgc).to(dev).train()
+    diffuser = diffusions.DDPM(total_steps=1000, beta_schedule='cosine', device=dev)
+    step = TrainStep(model, diffuser, FusedAdam(model.parameters(), lr=2e-4), ema=models.EMA(model.parameters()),
+                     clip_grad_norm=1.0, p_uncond=0.2)
+    B = 128
+    x0 = (torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(2022)) * 0.5).clamp(-1, 1).to(dev)
+    y = (torch.arange(B, device=dev) % 10)
+    first = None
+    for _ in range(3):
+        loss = step(x0, y=y)
+        first = loss if first is None else first
+    torch.cuda.synchronize()
+    n0 = K.direct_launch_count()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(10):
+        loss = step(x0, y=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    tf = 3 * 14.396e9 * B / (ms * 1e-3) / 1e12
+    out['cfg_train_step'] = {'workload': 'UNetCategorialAdaGN (configs/ddpm_cfg_cifar10.yaml) noise-prediction training '
+                                         'step, batch 128, dropout 0.1, clip 1.0 + Adam + EMA fused, 1 GPU',
+                             'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'tflops_3x_fwd': tf,
+                             'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
+                             'kernels_per_step': (K.direct_launch_count() - n0) // 10,
+                             'loss_first': float(first), 'loss_last': float(loss)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -310,6 +404,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--sample-steps', type=int, default=50)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the ADM-256 forward and training-step measurements')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

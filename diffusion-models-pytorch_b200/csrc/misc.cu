@@ -2,6 +2,7 @@
 // (with the parity split that turns the stride-2 conv into unit-stride TMA boxes), 2x resampling of the fp32
 // residual stream, and the time-embedding MLP.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/b200diff.h"
 
 namespace b200 {
@@ -238,7 +239,9 @@ using namespace b200;
 template <int CIN>
 static int launch_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B, int H,
                         int W, int Cout, cudaStream_t stream) {
-  int R = 8;
+  // rows per CTA: enough pixels per warp (R * W / 8) to amortise the per-lane weight fetch (108 floats for Cin = 3)
+  static const char* env_r = getenv("B200_FIRST_ROWS");
+  int R = env_r ? atoi(env_r) : 32;
   while (R > 1 && (size_t)CIN * (R + 2) * (W + 2) * 4 > 96 * 1024) R >>= 1;
   if (R > H) R = H;
   const size_t smem = (256 + (size_t)CIN * (R + 2) * (W + 2)) * 4;

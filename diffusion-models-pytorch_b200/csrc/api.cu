@@ -2,6 +2,7 @@
 // driver entry point (resolved at run time so the library links against cudart only).
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/b200diff.h"
 
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200_PDL");
+    on = (e && atoi(e) == 1) ? 1 : 0;   // measured on B200 (DDIM-50 graph replay): 958 vs 969 images/s, no gain -> off by default
+  }
+  return on != 0;
 }
 
 int check_cuda(cudaError_t e, const char* what) {

@@ -61,6 +61,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_s = bars->tmem_base;
   const uint32_t tmem_o = tmem_s + (uint32_t)p.Tp;
+  griddep_sync();
 
   if (threadIdx.x == 0) {
     // ---- 1. loads + 2. S = Q K^T ----
@@ -247,9 +248,9 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
   }
   B200_REQUIRE(smem <= 227 * 1024, "attention_fwd: smem %zu too large", smem);
   dim3 grid((T + 127) / 128, heads, B);
-  attention_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  B200_CHECK(launch_pdl(attention_kernel, grid, dim3(128), smem, stream, mapQ, mapK, mapV, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "attention_kernel launch");
+  return 0;
 }
 
 // ================================================================================================
@@ -308,6 +309,7 @@ attention_kv64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   tc_fence_after();
   const uint32_t tmem_s = bars->tmem_base;
   const uint32_t tmem_o = tmem_s + 256;
+  griddep_sync();
 
   auto load_kv = [&](int j) {   // thread 0 only
     const int buf = j & 1;
@@ -483,9 +485,9 @@ int attention_kv64(const void* qk, int ld_qk, int q_off, int k_off, const void* 
     attr = true;
   }
   dim3 grid((T + 127) / 128, heads, B);
-  attention_kv64_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  B200_CHECK(launch_pdl(attention_kv64_kernel, grid, dim3(128), smem, stream, mapQ, mapK, mapV, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "attention_kv64_kernel launch");
+  return 0;
 }
 
 }  // namespace b200
@@ -548,6 +550,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = bars->tmem_base;
+  griddep_sync();
 
   auto load_qk = [&](int c) {   // thread 0 only
     uint8_t* st = sRing + (size_t)(c & 1) * qk_stage;
@@ -726,9 +729,9 @@ int attention_wide(const void* qk, int ld_qk, int q_off, int k_off, const void* 
     attr = true;
   }
   dim3 grid((T + 127) / 128, heads, B);
-  attention_wide_kernel<<<grid, 128, smem, stream>>>(mapQ, mapK, mapV, p);
+  B200_CHECK(launch_pdl(attention_wide_kernel, grid, dim3(128), smem, stream, mapQ, mapK, mapV, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "attention_wide_kernel launch");
+  return 0;
 }
 
 }  // namespace b200

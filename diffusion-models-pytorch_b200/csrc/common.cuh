@@ -35,7 +35,36 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const voi
     }                                                               \
   } while (0)
 
+// Programmatic dependent launch (PDL): consecutive kernels of one forward are launched with the
+// programmatic-stream-serialization attribute, so kernel i+1's CTAs are scheduled (and run their set-up: mbarrier
+// init, TMEM allocation, descriptor prefetch) while kernel i's last CTAs are still draining; every kernel calls
+// griddep_sync() before its first access to global memory, which blocks until the preceding grid has completed and
+// flushed.  Works inside captured CUDA graphs (programmatic edges).  Opt-in with B200_PDL=1: measured neutral.
+bool pdl_enabled();
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// wait for the preceding grid (no-op when launched without the attribute), then let the next grid start its set-up
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // Basic helpers
 // ----------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_sync();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -286,7 +287,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_gemm_kernel<<<grid, 64 + 128 * p.epi_halves, smem_bytes, stream>>>(mapA0, mapA1, mapW, p);
+  B200_CHECK(launch_pdl(conv_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "conv_gemm_kernel launch");
+  return 0;
 }

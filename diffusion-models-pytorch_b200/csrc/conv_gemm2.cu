@@ -133,6 +133,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   cluster_sync_all();          // barriers of both CTAs initialised before any remote arrival / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_sync();
 
   // pair tile -> (phase, pixel tile, channel pair); this CTA's own tile coordinate has ct = 2 * cp + rank
   auto my_tile = [&](int ptile) {
@@ -276,13 +277,15 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
   cfg.blockDim = dim3(64 + 128 * p.epi_halves);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel, mapA0, mapA1, mapW, p, pp));
   ++g_launch_count;
   return 0;

@@ -88,6 +88,7 @@ conv_gemm_pixm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_sync();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -385,8 +386,8 @@ int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_) {
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_pixm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int grid = p.total_tiles < g_num_sms_pixm ? p.total_tiles : g_num_sms_pixm;
-  conv_gemm_pixm_kernel<<<grid, kPmThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
+  B200_CHECK(launch_pdl(conv_gemm_pixm_kernel, dim3(grid), dim3(kPmThreads), smem_bytes, stream, mapA0, mapA1, mapB, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "conv_gemm_pixm_kernel launch");
+  return 0;
 }
 }  // namespace b200

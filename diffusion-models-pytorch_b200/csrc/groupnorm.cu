@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
   float* chQ = gsm + 3 * C;      // [C] channel sums of squares
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
+  griddep_sync();
   for (int c = tid; c < C; c += 256) {
     const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
     chS[c] = __ldg(st);
@@ -532,9 +533,9 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   if (ppc > work_pix) ppc = work_pix;
   p.pix_per_cta = ppc;
   dim3 grid((work_pix + ppc - 1) / ppc, B);
-  groupnorm_apply_kernel<<<grid, 256, smem, stream>>>(p);
+  B200_CHECK(launch_pdl(groupnorm_apply_kernel, grid, dim3(256), smem, stream, p));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "groupnorm_apply_kernel launch");
+  return 0;
 }
 
 extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0, const float* x1,

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int co = blockIdx.z * 128 + 4 * lane;  // first of this lane's 4 output channels
   const bool co_ok = co < Cout;
+  griddep_sync();
   for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0.f;
   for (int i = threadIdx.x; i < CIN * (R + 2) * PW; i += blockDim.x) {
     const int ci = i / ((R + 2) * PW);
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
                                                         int B, int H, int W, int C, int parity) {
   const int cv = C >> 2;
   const size_t total = (size_t)B * H * W * cv;
+  griddep_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     uint2 u;
@@ -252,9 +254,9 @@ static int launch_first(const float* x, const float* w, const float* bias, float
     attr = true;
   }
   dim3 grid((H + R - 1) / R, B, (Cout + 127) / 128);
-  conv3x3_first_kernel<CIN><<<grid, 256, smem, stream>>>(x, w, bias, out, stats, B, H, W, Cout, R);
+  B200_CHECK(launch_pdl(conv3x3_first_kernel<CIN>, grid, dim3(256), smem, stream, x, w, bias, out, stats, B, H, W, Cout, R));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "conv3x3_first launch");
+  return 0;
 }
 
 extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B,
@@ -277,10 +279,10 @@ extern "C" int b200_cast_bf16(const float* x, void* out, int B, int H, int W, in
   B200_REQUIRE(C % 4 == 0, "cast_bf16: C=%d must be a multiple of 4", C);
   if (parity_split) B200_REQUIRE(H % 2 == 0 && W % 2 == 0, "cast_bf16: parity split needs even H, W");
   const size_t total = (size_t)B * H * W * (C / 4);
-  cast_bf16_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C,
-                                                            parity_split);
+  B200_CHECK(launch_pdl(cast_bf16_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, stream, x,
+                        reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, parity_split));
   ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "cast_bf16 launch");
+  return 0;
 }
 
 extern "C" int b200_avgpool2_f32(const float* x, float* out, int B, int H, int W, int C, void* stream_) {

@@ -150,6 +150,7 @@ def lib():
     L.b200_time_embed_bwd.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int] + [c_void_p] * 14
     L.b200_optimizer_step.argtypes = [POINTER(OptimDesc), c_void_p]
     L.b200_ode_step.argtypes = [POINTER(OdeDesc), c_void_p]
+    L.b200_pack_weights.argtypes = [c_void_p, c_int, c_void_p]
     L.b200_to_uint8_hwc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.b200_mse_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
@@ -170,7 +171,7 @@ BACKWARD_SYMBOLS = (
     'b200_groupnorm_apply_train_fwd', 'b200_dropout_mask', 'b200_groupnorm_bwd', 'b200_cast_bf16_colsum',
     'b200_nchw_to_nhwc_pad_bf16', 'b200_colsum_bf16', 'b200_resample_f32', 'b200_upsample2_bf16', 'b200_softmax_rows',
     'b200_softmax_bwd_rows', 'b200_mse_loss', 'b200_mse_loss_grad', 'b200_time_embed_bwd',
-    'b200_optimizer_step', 'b200_ode_step', 'b200_to_uint8_hwc',
+    'b200_optimizer_step', 'b200_ode_step', 'b200_to_uint8_hwc', 'b200_pack_weights',
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
@@ -635,3 +636,14 @@ def to_uint8_hwc(x, out=None):
         out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device)
     _check(lib().b200_to_uint8_hwc(x.contiguous().data_ptr(), out.data_ptr(), B, C, H * W, _stream()), 'to_uint8_hwc')
     return out
+
+
+def pack_entry_bytes(src, dst, Co, Ci, taps, mode, row0=0, col0=0, ld=0, src2=None):
+    """One b200_pack_entry as bytes (3 pointers, 8 ints)."""
+    import struct
+    return struct.pack('<3Q8i', src.data_ptr(), 0 if src2 is None else src2.data_ptr(), dst.data_ptr(), Co, Ci, taps, mode,
+                       row0, col0, ld, 0)
+
+
+def pack_weights(table_dev, n_entries):
+    _check(lib().b200_pack_weights(table_dev.data_ptr(), n_entries, _stream()), 'pack_weights')

@@ -87,3 +87,55 @@ extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "optim_adam_kernel launch");
 }
+
+// ================================================================================================
+// Multi-tensor weight pack: after an optimizer step (or load_state_dict) every fp32 OIHW parameter is re-laid-out to
+// the bf16 GEMM operand(s) the kernels consume, for ALL layers in one launch over a device-resident table:
+//   mode 0 (forward operand)      dst[row0 + co][col0 + tap*Ci + ci]          = src[co][ci][tap]
+//   mode 1 (data-gradient operand) dst[row0 + ci][col0 + (taps-1-tap)*Co + co] = src[co][ci][tap]   (flipped taps)
+//   mode 2 (fp32 bias sum)         dstf[i] = src[i] + src2[i]                  (conv bias + fused-shortcut bias)
+// Replaces ~1000 tiny torch permute / cast / cat kernels per training step.
+// ================================================================================================
+namespace b200 {
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_entry* __restrict__ table, int ctas_per_entry) {
+  const b200_pack_entry e = table[blockIdx.x / ctas_per_entry];
+  const int part = blockIdx.x % ctas_per_entry;
+  const long long total = (long long)e.Co * e.Ci * e.taps;
+  const long long per = (total + ctas_per_entry - 1) / ctas_per_entry;
+  const long long j0 = part * per, j1 = min(total, j0 + per);
+  if (e.mode == 2) {
+    float* dst = reinterpret_cast<float*>(e.dst);
+    for (long long j = j0 + threadIdx.x; j < j1; j += 256) dst[j] = e.src[j] + (e.src2 ? e.src2[j] : 0.f);
+    return;
+  }
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+  const int tc = e.taps * (e.mode == 0 ? e.Ci : e.Co);    // packed row length of this entry
+  for (long long j = j0 + threadIdx.x; j < j1; j += 256) {
+    // j enumerates the destination in row-major order (coalesced writes)
+    const int r = (int)(j / tc);
+    const int rem = (int)(j - (long long)r * tc);
+    int co, ci, tap;
+    if (e.mode == 0) {
+      co = r; tap = rem / e.Ci; ci = rem - tap * e.Ci;
+    } else {
+      ci = r;
+      const int tp = rem / e.Co;
+      co = rem - tp * e.Co;
+      tap = e.taps - 1 - tp;
+    }
+    const float v = __ldg(e.src + ((long long)co * e.Ci + ci) * e.taps + tap);
+    dst[(long long)(e.row0 + r) * e.ld + e.col0 + rem] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200_pack_weights(const void* table_dev, int n_entries, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(table_dev && n_entries >= 1, "pack_weights: empty table");
+  const int cpe = 8;
+  pack_weights_kernel<<<n_entries * cpe, 256, 0, stream>>>(reinterpret_cast<const b200_pack_entry*>(table_dev), cpe);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "pack_weights_kernel launch");
+}

@@ -106,7 +106,7 @@ def _grad_slot(eng: Engine, act: Act):
 
 def _w_dgrad(eng: Engine, tag, conv: nn.Conv2d):
     """Packed weights of the data-gradient conv: spatially flipped taps, in/out channels swapped."""
-    return eng.packed(('dgrad', tag), lambda: K.pack_weight(conv.weight.detach().flip(2, 3).transpose(0, 1)))
+    return eng.w_dgrad(tag, conv)
 
 
 def _cast_out_grad(eng: Engine, tag, out: Act, bias_grad):
@@ -248,8 +248,13 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(q.weight))
     _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(k.weight), dy_c0=C)
     _wgrad(eng, dv, C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(v.weight))
-    wd = eng.packed(('dgrad', tag + '.qkv'), lambda: torch.cat(
-        [m.weight.detach().reshape(C, C).t() for m in (q, k, v)], dim=1).to(bf).contiguous())     # [C_in][3C]
+    hit = eng._pt.get(('dgrad', tag + '.qkv'))
+    if hit is None:     # [C_in][3C] = [Wq^T | Wk^T | Wv^T]
+        wd = torch.empty((C, 3 * C), dtype=bf, device=eng.device)
+        wd = eng.pack_table(('dgrad', tag + '.qkv'), wd, [K.pack_entry_bytes(m.weight, wd, C, C, 1, 1, col0=i * C, ld=3 * C)
+                                                           for i, m in enumerate((q, k, v))])
+    else:
+        wd = hit[0]
     dn = eng.buf(tag + '.dN', (B, H, W, C), bf)
     K.conv2d(dqk, wd, C, B, H, W, t1, a0_geom=(2 * C, H, W, 1), a1=dv, a1_geom=(C, H, W, 1), out=dn,
              out_mode=K.OUT_BF16_NHWC)

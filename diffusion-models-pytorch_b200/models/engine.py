@@ -42,6 +42,9 @@ class Engine:
         self._arena: Dict = {}
         self._stats: Dict = {}
         self._stats_pools: List = []
+        self._pt: Dict = {}          # table-managed packed weights: key -> (result, [b200_pack_entry bytes])
+        self._pt_table = None        # device table over all entries (rebuilt when an entry is added)
+        self._pt_scratch: List = []  # single-entry tables of first-use packs (kept alive until the stream consumed them)
         self.tape = None         # training forward: list of records replayed in reverse by models/backward.py
         self.drop_seed = 0       # base seed of this forward's dropout masks
         self._n_drop = 0
@@ -85,10 +88,24 @@ class Engine:
             pool[:used].zero_()
 
     def refresh(self):
-        """Drops the packed bf16 weights when any parameter was modified or moved."""
+        """Brings the packed bf16 weights up to date when a parameter was modified (optimizer step, load_state_dict,
+        EMA swap): table-managed packs are re-created in place by ONE b200_pack_weights launch; everything is dropped
+        when a parameter moved (new storage)."""
         sig = tuple((p.data_ptr(), p._version) for p in self.model.parameters())
         if sig != self._sig:
+            moved = self._sig is None or len(sig) != len(self._sig) or \
+                any(a[0] != b[0] for a, b in zip(sig, self._sig))
             self._packed.clear()
+            if moved:
+                self._pt.clear()
+                self._pt_table = None
+            elif self._pt:
+                if self._pt_table is None:
+                    blob = b''.join(e for _, entries in self._pt.values() for e in entries)
+                    n = sum(len(entries) for _, entries in self._pt.values())
+                    self._pt_table = (torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device), n)
+                K.pack_weights(*self._pt_table)
+            self._pt_scratch.clear()
             self._sig = sig
         dev = self.device
         if dev.type != 'cuda':
@@ -103,14 +120,43 @@ class Engine:
             self._packed[key] = v
         return v
 
+    def pack_table(self, key, result, entries):
+        """Registers a table-managed pack (`entries`: b200_pack_entry byte strings writing into the tensors of `result`)
+        and fills it now; later parameter updates re-run all registered entries in one launch (refresh)."""
+        self._pt[key] = (result, entries)
+        self._pt_table = None
+        blob = torch.frombuffer(bytearray(b''.join(entries)), dtype=torch.uint8).to(self.device)
+        self._pt_scratch.append(blob)
+        K.pack_weights(blob, len(entries))
+        return result
+
     def w_conv(self, tag, conv: nn.Conv2d, shortcut: Optional[nn.Conv2d] = None):
-        def make():
-            w = K.pack_weight(conv.weight, None if shortcut is None else shortcut.weight)
-            b = conv.bias.detach().float().contiguous()
-            if shortcut is not None:
-                b = (b + shortcut.bias.detach().float()).contiguous()
-            return w, b
-        return self.packed(('conv', tag), make)
+        """bf16 [Cout, taps*Cin (+ Cin_shortcut)] forward operand + fp32 bias (conv bias, summed with the fused shortcut's)."""
+        key = ('conv', tag)
+        hit = self._pt.get(key)
+        if hit is not None:
+            return hit[0]
+        Co, Ci, kh, kw = conv.weight.shape
+        taps = kh * kw
+        Kd = taps * Ci + (shortcut.in_channels if shortcut is not None else 0)
+        w = torch.empty((Co, Kd), dtype=torch.bfloat16, device=self.device)
+        entries = [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, 0, ld=Kd)]
+        b = conv.bias
+        if shortcut is not None:
+            entries.append(K.pack_entry_bytes(shortcut.weight, w, Co, shortcut.in_channels, 1, 0, col0=taps * Ci, ld=Kd))
+            b = torch.empty(Co, dtype=torch.float32, device=self.device)
+            entries.append(K.pack_entry_bytes(conv.bias, b, Co, 1, 1, 2, src2=shortcut.bias))
+        return self.pack_table(key, (w, b), entries)
+
+    def w_dgrad(self, tag, conv: nn.Conv2d):
+        """bf16 [Cin, taps*Cout] data-gradient operand: spatially flipped taps, in/out channels swapped."""
+        key = ('dgrad', tag)
+        hit = self._pt.get(key)
+        if hit is not None:
+            return hit[0]
+        Co, Ci, kh, kw = conv.weight.shape
+        w = torch.empty((Ci, kh * kw * Co), dtype=torch.bfloat16, device=self.device)
+        return self.pack_table(key, w, [K.pack_entry_bytes(conv.weight, w, Co, Ci, kh * kw, 1, ld=kh * kw * Co)])
 
     def w_up2(self, tag, conv: nn.Conv2d):
         return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight),
@@ -118,11 +164,21 @@ class Engine:
 
     def w_tproj(self, linears: List[nn.Linear]):
         """All per-ResBlock embedding projections stacked into one [sum(out), E] bf16 matrix."""
-        def make():
-            w = torch.cat([l.weight.detach() for l in linears], dim=0).to(torch.bfloat16).contiguous()
-            b = torch.cat([l.bias.detach() for l in linears]).float().contiguous()
-            return w, b
-        return self.packed(('tproj',), make)
+        key = ('tproj',)
+        hit = self._pt.get(key)
+        if hit is not None:
+            return hit[0]
+        E = linears[0].in_features
+        total = sum(l.out_features for l in linears)
+        w = torch.empty((total, E), dtype=torch.bfloat16, device=self.device)
+        b = torch.empty(total, dtype=torch.float32, device=self.device)
+        entries, off = [], 0
+        for l in linears:
+            n = l.out_features
+            entries.append(K.pack_entry_bytes(l.weight, w, n, E, 1, 0, row0=off, ld=E))
+            entries.append(K.pack_entry_bytes(l.bias, b[off:off + n], n, 1, 1, 2))
+            off += n
+        return self.pack_table(key, (w, b), entries)
 
     # ------------------------------------------------------------------------------------------
     # ops
@@ -174,12 +230,23 @@ class Engine:
 
     def attention(self, tag, blk, x: Act) -> Act:
         """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2."""
-        def make():
-            wqk = torch.cat([K.pack_weight(blk.q.weight), K.pack_weight(blk.k.weight)], dim=0).contiguous()
-            bqk = torch.cat([blk.q.bias.detach(), blk.k.bias.detach()]).float().contiguous()
-            return (wqk, bqk, K.pack_weight(blk.v.weight), blk.v.bias.detach().float().contiguous(),
-                    K.pack_weight(blk.proj.weight), blk.proj.bias.detach().float().contiguous())
-        return self.attention_core(tag, x, blk.norm, self.packed(('attn', tag), make), blk.n_heads, blk.scale,
+        key = ('attn', tag)
+        hit = self._pt.get(key)
+        if hit is None:
+            C = blk.q.out_channels
+            bf, dev = torch.bfloat16, self.device
+            wqk, wv, wp = (torch.empty((2 * C, C), dtype=bf, device=dev), torch.empty((C, C), dtype=bf, device=dev),
+                           torch.empty((C, C), dtype=bf, device=dev))
+            bqk = torch.empty(2 * C, dtype=torch.float32, device=dev)
+            entries = [K.pack_entry_bytes(blk.q.weight, wqk, C, C, 1, 0, ld=C),
+                       K.pack_entry_bytes(blk.k.weight, wqk, C, C, 1, 0, row0=C, ld=C),
+                       K.pack_entry_bytes(blk.q.bias, bqk, C, 1, 1, 2), K.pack_entry_bytes(blk.k.bias, bqk[C:], C, 1, 1, 2),
+                       K.pack_entry_bytes(blk.v.weight, wv, C, C, 1, 0, ld=C),
+                       K.pack_entry_bytes(blk.proj.weight, wp, C, C, 1, 0, ld=C)]
+            weights = self.pack_table(key, (wqk, bqk, wv, blk.v.bias, wp, blk.proj.bias), entries)
+        else:
+            weights = hit[0]
+        return self.attention_core(tag, x, blk.norm, weights, blk.n_heads, blk.scale,
                                    mods=(blk.q, blk.k, blk.v, blk.proj))
 
     def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:

@@ -353,6 +353,18 @@ typedef struct b200_optim_desc {
 } b200_optim_desc;
 int b200_optimizer_step(const b200_optim_desc* d, void* stream);
 
+/* Multi-tensor weight pack (see b200_conv_desc.w): one launch re-creates the bf16 GEMM operands of every layer from
+ * the fp32 OIHW parameters after they changed.  `table` is a DEVICE array of n_entries descriptors.
+ *   mode 0: dst[row0 + co][col0 + tap*Ci + ci] = src[co][ci][tap]                    (forward operand, bf16, row stride ld)
+ *   mode 1: dst[row0 + ci][col0 + (taps-1-tap)*Co + co] = src[co][ci][tap]           (data-gradient operand)
+ *   mode 2: dst_f32[i] = src[i] + src2[i], i < Co*Ci*taps                            (summed bias of a fused shortcut) */
+typedef struct b200_pack_entry {
+  const float* src; const float* src2; void* dst;
+  int Co, Ci, taps, mode;
+  int row0, col0, ld, pad_;
+} b200_pack_entry;
+int b200_pack_weights(const void* table, int n_entries, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,9 +57,12 @@ def main():
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = K.direct_launch_count()
+    import time
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         losses.append(step(x0, y=y))
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps      # time the host needs to ENQUEUE one step
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
@@ -77,7 +80,7 @@ def main():
     tf = 3 * gf * 1e9 * B / (ms * 1e-3) / 1e12
     if rank == 0:
         print(json.dumps({
-            'model': which, 'batch_per_gpu': B, 'n_gpus': world, 'ms_per_step': ms,
+            'model': which, 'batch_per_gpu': B, 'n_gpus': world, 'ms_per_step': ms, 'host_enqueue_ms_per_step': host_ms,
             'images_per_s': world * B / (ms * 1e-3), 'tflops_per_gpu_3x_fwd': tf, 'frac_of_bf16_sustained_peak': tf / peak,
             'kernels_per_step': launches, 'loss_first': float(losses[0]), 'loss_last': float(losses[-1]),
             'peak_mem_gib': torch.cuda.max_memory_allocated() / 2 ** 30,

@@ -42,6 +42,7 @@ class Engine:
         self._arena: Dict = {}
         self._stats: Dict = {}
         self._stats_pools: List = []
+        self._device = None          # cached per forward (refresh re-reads it)
         self._pt: Dict = {}          # table-managed packed weights: key -> (result, [b200_pack_entry bytes])
         self._pt_table = None        # device table over all entries (rebuilt when an entry is added)
         self._pt_scratch: List = []  # single-entry tables of first-use packs (kept alive until the stream consumed them)
@@ -54,7 +55,10 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     @property
     def device(self):
-        return next(self.model.parameters()).device
+        d = self._device
+        if d is None:
+            d = self._device = next(self.model.parameters()).device
+        return d
 
     def buf(self, tag, shape, dtype):
         key = (tag, tuple(shape), dtype, self.device)
@@ -91,6 +95,7 @@ class Engine:
         """Brings the packed bf16 weights up to date when a parameter was modified (optimizer step, load_state_dict,
         EMA swap): table-managed packs are re-created in place by ONE b200_pack_weights launch; everything is dropped
         when a parameter moved (new storage)."""
+        self._device = None
         sig = tuple((p.data_ptr(), p._version) for p in self.model.parameters())
         if sig != self._sig:
             moved = self._sig is None or len(sig) != len(self._sig) or \

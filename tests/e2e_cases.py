@@ -383,6 +383,46 @@ def case_train_step():
     return ok
 
 
+def case_train_step_pesser():
+    """Backward kernels through the pesser family (separate q/k/v AttnBlock, nin_shortcut, stride-2 conv with
+    (0,1,0,1) padding and its 4-phase transposed-conv adjoint, nearest-2x + conv upsampling): toy-width config, B=4."""
+    import torch.nn.functional as F
+    from models.pesser.model import Model
+    from oracle.adm_ref import pesser_forward
+    _no_tf32()
+    cfg = dict(resolution=32, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 2], num_res_blocks=1, attn_resolutions=[16],
+               dropout=0.0, resamp_with_conv=True)
+    torch.manual_seed(2022)
+    m = Model(**cfg).to(DEV).train()
+    B = 4
+    g = torch.Generator(device='cpu').manual_seed(6)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1).to(DEV)
+    eps = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    d = diffusions.DDPM(total_steps=1000, device=DEV)
+    orc = R.DDPMRef(total_steps=1000)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    loss = d.loss_func(m, x0, t, eps=eps)
+    loss.backward()
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    loss_ref = F.mse_loss(pesser_forward(sd, orc.diffuse(x0, t, eps), t, cfg=cfg), eps)
+    loss_ref.backward()
+    num = den = 0.0
+    worst, worst_name = 0.0, ''
+    for k, p in m.named_parameters():
+        e2, r2 = float((p.grad - sd[k].grad).pow(2).sum()), float(sd[k].grad.pow(2).sum())
+        num, den = num + e2, den + r2
+        rel = (e2 / max(r2, 1e-30)) ** 0.5
+        if p.numel() >= 1024 and rel > worst:
+            worst, worst_name = rel, k
+    rel_all = (num / den) ** 0.5
+    lerr = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    ok = rel_all <= 3e-2 and worst <= 9e-2 and lerr <= 5e-3
+    _emit(case='train step pesser toy B=4', loss=loss.item(), loss_ref=loss_ref.item(), loss_rel_err=lerr,
+          grad_rel_l2_all=rel_all, worst_tensor=worst_name, worst_tensor_rel_l2=worst, gate=3e-2, ok=ok)
+    return ok
+
+
 def case_ode_sampling():
     """Euler-20 / Heun-10 sampling (CIFAR-10 UNet, B=8) through EulerSampler / HeunSampler vs the fp32 oracle loops."""
     _no_tf32()

@@ -229,7 +229,7 @@ class UNetModel(_EngineModel):
         if isinstance(layer, AttentionBlock):
             d = layer.channels // layer.num_heads
             return eng.attention_core(name, h, layer.norm, eng.packed(('attn', name), layer.packed_weights),
-                                      layer.num_heads, 1.0 / math.sqrt(d))
+                                      layer.num_heads, 1.0 / math.sqrt(d), mods=layer)
         if isinstance(layer, Downsample):
             return eng.downsample_conv(name + '.op', layer.op, h) if layer.use_conv else eng.resample_plain(name, h, 1)
         if isinstance(layer, Upsample):

@@ -200,8 +200,8 @@ def _res_bwd(eng: Engine, e, G: _Grads):
 
 def _attn_bwd(eng: Engine, e, G: _Grads):
     tag, x, out, norm = e['tag'], e['x'], e['out'], e['norm']
-    q, k, v, proj = e['mods']
     B, H, W, C = x.B, x.H, x.W, x.C
+    targets, proj = _attn_targets(eng, e, G, C)
     T, heads, scale = H * W, e['heads'], e['scale']
     d = C // heads
     t1 = K.taps_1x1()
@@ -240,21 +240,15 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     K.gemm_batched((P, T, T, dict(per_head_batch=True, mn_major=True)), (do, T, C, dict(col_head=d, mn_major=True)), dv,
                    T, d, T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
 
-    # q, k, v 1x1 convs: biases, weights, data (one GEMM over the concatenated [dq | dk | dv] channels)
+    # q, k, v 1x1 convs: biases, weights, data (one GEMM over the concatenated [dq | dk | dv] channels).
+    # `targets` maps row ranges of dq / dk / dv to rows of the parameters' gradients: one range each for separate
+    # q, k, v convs; one per head for ADM's fused, head-interleaved qkv Conv1d.
     n = e['n']
-    K.colsum_bf16(dqk, G(q.bias), B * T, 2 * C, 0, C)
-    K.colsum_bf16(dqk, G(k.bias), B * T, 2 * C, C, C)
-    K.colsum_bf16(dv, G(v.bias), B * T, C, 0, C)
-    _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(q.weight))
-    _wgrad(eng, dqk, 2 * C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(k.weight), dy_c0=C)
-    _wgrad(eng, dv, C, n, (C, H, W, 1), B, H, W, C, C, t1[0], G(v.weight))
-    hit = eng._pt.get(('dgrad', tag + '.qkv'))
-    if hit is None:     # [C_in][3C] = [Wq^T | Wk^T | Wv^T]
-        wd = torch.empty((C, 3 * C), dtype=bf, device=eng.device)
-        wd = eng.pack_table(('dgrad', tag + '.qkv'), wd, [K.pack_entry_bytes(m.weight, wd, C, C, 1, 1, col0=i * C, ld=3 * C)
-                                                           for i, m in enumerate((q, k, v))])
-    else:
-        wd = hit[0]
+    for which, (src, ld, c_off) in (('q', (dqk, 2 * C, 0)), ('k', (dqk, 2 * C, C)), ('v', (dv, C, 0))):
+        for (r0, nrows, wg, bg) in targets[which]:
+            K.colsum_bf16(src, bg, B * T, ld, c_off + r0, nrows)
+            _wgrad(eng, src, ld, n, (C, H, W, 1), B, H, W, nrows, C, t1[0], wg, dy_c0=c_off + r0)
+    wd = targets['wd']()
     dn = eng.buf(tag + '.dN', (B, H, W, C), bf)
     K.conv2d(dqk, wd, C, B, H, W, t1, a0_geom=(2 * C, H, W, 1), a1=dv, a1_geom=(C, H, W, 1), out=dn,
              out_mode=K.OUT_BF16_NHWC)
@@ -263,6 +257,45 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     K.groupnorm_bwd(dn, x.t, C, x.stats, None, 0, None, B, T, W, norm.num_groups, norm.weight, norm.bias, norm.eps,
                     _sums(eng, B, C), silu=False, dx0=gx, dx0_acc=acc, addend=out.g, dgamma=G(norm.weight),
                     dbeta=G(norm.bias))
+
+
+def _attn_targets(eng: Engine, e, G: _Grads, C: int):
+    """({'q'|'k'|'v': [(first row, rows, weight-grad view [rows, C], bias-grad view [rows])], 'wd': maker of the
+    [C][3C] = [Wq^T | Wk^T | Wv^T] data-gradient operand}, output projection module) of an attention block."""
+    tag, mods = e['tag'], e['mods']
+    bf = torch.bfloat16
+    if isinstance(mods, tuple):                       # separate q, k, v, proj convs (models/modules.py, pesser)
+        q, k, v, proj = mods
+
+        def wd():
+            hit = eng._pt.get(('dgrad', tag + '.qkv'))
+            if hit is not None:
+                return hit[0]
+            w = torch.empty((C, 3 * C), dtype=bf, device=eng.device)
+            return eng.pack_table(('dgrad', tag + '.qkv'), w, [K.pack_entry_bytes(m.weight, w, C, C, 1, 1, col0=i * C, ld=3 * C)
+                                                               for i, m in enumerate((q, k, v))])
+        tg = {n: [(0, C, G(m.weight).view(C, C), G(m.bias))] for n, m in (('q', q), ('k', k), ('v', v))}
+        tg['wd'] = wd
+        return tg, proj
+    blk = mods                                        # ADM AttentionBlock: fused qkv Conv1d [3C, C, 1]
+    Hh = blk.num_heads
+    d = C // Hh
+    wg, bg = G(blk.qkv.weight).view(3 * C, C), G(blk.qkv.bias)
+    tg = {}
+    for j, name in enumerate(('q', 'k', 'v')):
+        if blk.use_new_attention_order:               # rows (j*H + h)*d + i: one contiguous range per projection
+            tg[name] = [(0, C, wg[j * C:(j + 1) * C], bg[j * C:(j + 1) * C])]
+        else:                                         # legacy rows (h*3 + j)*d + i: one range per head
+            tg[name] = [(h * d, d, wg[(h * 3 + j) * d:(h * 3 + j + 1) * d], bg[(h * 3 + j) * d:(h * 3 + j + 1) * d])
+                        for h in range(Hh)]
+
+    def wd():
+        def make():
+            wqk, _, wv, _, _, _ = blk.packed_weights()                   # [2C, C] (q heads | k heads), [C, C]
+            return torch.cat([wqk[:C].t(), wqk[C:].t(), wv.t()], dim=1).contiguous()
+        return eng.packed(('dgrad', tag + '.qkv'), make)
+    tg['wd'] = wd
+    return tg, blk.proj_out
 
 
 def _s2_dgrad_plan(conv: nn.Conv2d, pad_lo: int):

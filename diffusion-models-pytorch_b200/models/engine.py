@@ -141,8 +141,8 @@ class Engine:
         hit = self._pt.get(key)
         if hit is not None:
             return hit[0]
-        Co, Ci, kh, kw = conv.weight.shape
-        taps = kh * kw
+        Co, Ci = conv.weight.shape[:2]
+        taps = conv.weight[0, 0].numel()
         Kd = taps * Ci + (shortcut.in_channels if shortcut is not None else 0)
         w = torch.empty((Co, Kd), dtype=torch.bfloat16, device=self.device)
         entries = [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, 0, ld=Kd)]
@@ -159,9 +159,10 @@ class Engine:
         hit = self._pt.get(key)
         if hit is not None:
             return hit[0]
-        Co, Ci, kh, kw = conv.weight.shape
-        w = torch.empty((Ci, kh * kw * Co), dtype=torch.bfloat16, device=self.device)
-        return self.pack_table(key, w, [K.pack_entry_bytes(conv.weight, w, Co, Ci, kh * kw, 1, ld=kh * kw * Co)])
+        Co, Ci = conv.weight.shape[:2]          # Conv2d [Co, Ci, kh, kw] or Conv1d [Co, Ci, 1]
+        taps = conv.weight[0, 0].numel()
+        w = torch.empty((Ci, taps * Co), dtype=torch.bfloat16, device=self.device)
+        return self.pack_table(key, w, [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, 1, ld=taps * Co)])
 
     def w_up2(self, tag, conv: nn.Conv2d):
         return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight),
@@ -280,7 +281,7 @@ class Engine:
         res = Act(out, B, H, W, C, stats)
         if self.tape is not None:
             if mods is None:
-                raise RuntimeError(f'{tag}: training through a fused-qkv attention block is not implemented')
+                raise RuntimeError(f'{tag}: this attention block did not register its parameters for the backward pass')
             self.tape.append(dict(kind='attn', tag=tag, x=x, out=res, norm=norm, n=n, qk=qk, vt=vt, o=o, heads=heads,
                                   scale=scale, mods=mods))
         return res

@@ -423,6 +423,51 @@ def case_train_step_pesser():
     return ok
 
 
+def case_train_step_adm():
+    """Backward kernels through the ADM family: fused head-interleaved qkv Conv1d (legacy and new attention order),
+    scale-shift ResBlocks, BigGAN up/down ResBlocks, strided-conv / nearest+conv resampling, class embedding."""
+    import torch.nn.functional as F
+    from models.adm.unet import UNetModel
+    from oracle.adm_ref import adm_forward, randomize_zero_params
+    _no_tf32()
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'family_forward.pt'), weights_only=False)
+    ok = True
+    for name in ('adm_tiny_cond', 'adm_tiny_plain'):
+        cfg = gold[name]['cfg']
+        torch.manual_seed(2022)
+        m = UNetModel(**cfg)
+        m.load_state_dict(randomize_zero_params(m.state_dict()))
+        m = m.to(DEV).train()
+        B = 4
+        g = torch.Generator(device='cpu').manual_seed(8)
+        x0 = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1).to(DEV)
+        eps = torch.randn(B, cfg['out_channels'], 32, 32, generator=g).to(DEV)
+        t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+        y = torch.tensor([1, 5, 9, 0], device=DEV) if cfg['num_classes'] is not None else None
+        xt = R.DDPMRef(total_steps=1000).diffuse(x0.cpu(), t.cpu(), eps[:, :3].cpu()).to(DEV)
+        from models.backward import mse_loss
+        loss = mse_loss(m(xt, t, y), eps)
+        loss.backward()
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        loss_ref = F.mse_loss(adm_forward(sd, xt, t, y, cfg=cfg), eps)
+        loss_ref.backward()
+        num = den = 0.0
+        worst, worst_name = 0.0, ''
+        for k, p in m.named_parameters():
+            e2, r2 = float((p.grad - sd[k].grad).pow(2).sum()), float(sd[k].grad.pow(2).sum())
+            num, den = num + e2, den + r2
+            rel = (e2 / max(r2, 1e-30)) ** 0.5
+            if p.numel() >= 1024 and rel > worst:
+                worst, worst_name = rel, k
+        rel_all = (num / den) ** 0.5
+        lerr = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+        good = rel_all <= 3e-2 and worst <= 9e-2 and lerr <= 5e-3
+        _emit(case=f'train step {name} B=4', loss=loss.item(), loss_ref=loss_ref.item(), loss_rel_err=lerr,
+              grad_rel_l2_all=rel_all, worst_tensor=worst_name, worst_tensor_rel_l2=worst, gate=3e-2, ok=good)
+        ok &= good
+    return ok
+
+
 def case_ode_sampling():
     """Euler-20 / Heun-10 sampling (CIFAR-10 UNet, B=8) through EulerSampler / HeunSampler vs the fp32 oracle loops."""
     _no_tf32()

@@ -42,10 +42,15 @@ def test_struct_layout_matches_header(tmp_path):
     import b200diff
     if shutil.which('gcc') is None:
         pytest.skip('gcc not available')
-    fields = {'b200_conv_desc': b200diff.ConvDesc, 'b200_sampler_desc': b200diff.SamplerDesc}
+    fields = {'b200_conv_desc': b200diff.ConvDesc, 'b200_sampler_desc': b200diff.SamplerDesc,
+              'b200_gemm_desc': b200diff.GemmDesc, 'b200_wgrad_desc': b200diff.WgradDesc,
+              'b200_gn_bwd_desc': b200diff.GnBwdDesc, 'b200_optim_desc': b200diff.OptimDesc,
+              'b200_ode_desc': b200diff.OdeDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200diff.h"', 'int main(void) {']
     for cname, cls in fields.items():
-        for fname, _ in cls._fields_:
+        for fname, ftype in cls._fields_:
+            if isinstance(ftype, type) and issubclass(ftype, ctypes.Structure):
+                continue      # nested structs (gemm operands): covered by the offsets of the members that follow them
             lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
         lines.append(f'  printf("{cname}.sizeof %zu\\n", sizeof({cname}));')
     lines += ['  return 0;', '}']
@@ -55,9 +60,18 @@ def test_struct_layout_matches_header(tmp_path):
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
     for cname, cls in fields.items():
-        for fname, _ in cls._fields_:
+        for fname, ftype in cls._fields_:
+            if isinstance(ftype, type) and issubclass(ftype, ctypes.Structure):
+                continue
             assert int(out[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
         assert int(out[f'{cname}.sizeof']) == ctypes.sizeof(cls), cname
+    # the pack / optimizer tables are serialised with struct.pack: their C sizes are part of the contract too
+    src.write_text('#include <stdio.h>\n#include "b200diff.h"\nint main(void) { printf("%zu %zu\\n", '
+                   'sizeof(b200_pack_entry), sizeof(b200_optim_chunk)); return 0; }')
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    import struct
+    sz = subprocess.check_output([str(exe)], text=True).split()
+    assert int(sz[0]) == struct.calcsize('<3Q8i') and int(sz[1]) == struct.calcsize('<5Q2i')
 
 
 def test_no_cpu_fallback():

@@ -76,7 +76,7 @@ class GnBwdDesc(Structure):
                 ('gamma', c_void_p), ('beta', c_void_p), ('eps', c_float),
                 ('scale', c_void_p), ('shift', c_void_p), ('ss_ld', c_int),
                 ('apply_silu', c_int), ('resample', c_int),
-                ('drop_p', c_float), ('drop_seed', ctypes.c_ulonglong),
+                ('drop_p', c_float), ('drop_seed', ctypes.c_ulonglong), ('drop_seed_dev', c_void_p),
                 ('sums', c_void_p),
                 ('dx0', c_void_p), ('dx0_accumulate', c_int),
                 ('dx1', c_void_p), ('dx1_accumulate', c_int),
@@ -97,7 +97,8 @@ class OdeDesc(Structure):
 class OptimDesc(Structure):
     _fields_ = [('chunks', c_void_p), ('n_chunks', c_int), ('lr', c_float), ('beta1', c_float), ('beta2', c_float),
                 ('eps', c_float), ('weight_decay', c_float), ('adamw', c_int), ('step', c_int),
-                ('max_grad_norm', c_float), ('want_norm', c_int), ('gnorm_sq', c_void_p), ('ema_decay', c_float)]
+                ('max_grad_norm', c_float), ('want_norm', c_int), ('gnorm_sq', c_void_p), ('ema_decay', c_float),
+                ('dev_state', c_void_p)]
 
 
 _lib = None
@@ -137,7 +138,7 @@ def lib():
     ull = ctypes.c_ulonglong
     L.b200_groupnorm_apply_train_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                                  c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                                 c_int, c_int, c_int, c_float, ull, c_void_p, c_void_p, c_void_p]
+                                                 c_int, c_int, c_int, c_float, ull, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_dropout_mask.argtypes = [c_void_p, c_longlong, c_float, ull, c_void_p]
     L.b200_groupnorm_bwd.argtypes = [POINTER(GnBwdDesc), c_void_p]
     L.b200_cast_bf16_colsum.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]
@@ -417,14 +418,15 @@ def _gn_bytes(B, HW, C, resample, raw):
 
 
 def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None,
-                    shift=None, ss_ld=0, silu=True, resample=0, raw_out=None, drop_p=0.0, drop_seed=0):
+                    shift=None, ss_ld=0, silu=True, resample=0, raw_out=None, drop_p=0.0, drop_seed=0,
+                    drop_seed_dev=None):
     """Streaming GroupNorm(+SiLU)(+dropout) for inputs whose [B][C][2] statistics came from the producing kernel."""
     _need_cuda(x0, stats0, out)
     _launch('groupnorm_apply',
             lambda: _check(lib().b200_groupnorm_apply_train_fwd(
                 x0.data_ptr(), int(x0.dtype == torch.bfloat16), C0, stats0.data_ptr(), _ptr(x1), C1, _ptr(stats1), B,
                 HW, W, groups, _ptr(gamma), _ptr(beta), float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu),
-                resample, float(drop_p), int(drop_seed), out.data_ptr(), _ptr(raw_out), _stream()),
+                resample, float(drop_p), int(drop_seed), _ptr(drop_seed_dev), out.data_ptr(), _ptr(raw_out), _stream()),
                 'groupnorm_apply_fwd'),
             nbytes=_gn_bytes(B, HW, C0 + (C1 if x1 is not None else 0), resample, raw_out is not None) -
             (2.0 * B * HW * C0 if x0.dtype == torch.bfloat16 else 0.0))
@@ -549,7 +551,8 @@ def conv2d_wgrad(dy, dy_C, x, x_geom, B, Ho, Wo, Cout, Cin, taps, dw, *, x_c0=0,
 
 
 def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, sums, *, scale=None,
-                  shift=None, ss_ld=0, silu=True, resample=0, drop_p=0.0, drop_seed=0, dx0=None, dx0_acc=False,
+                  shift=None, ss_ld=0, silu=True, resample=0, drop_p=0.0, drop_seed=0, drop_seed_dev=None, dx0=None,
+                  dx0_acc=False,
                   dx1=None, dx1_acc=False, addend=None, dx_bf16=None, dx_rowsum=None, dx_rowsum_ld=0, dx_colsum=None,
                   dgamma=None, dbeta=None, dscale=None, dshift=None, dss_ld=0):
     _need_cuda(g, x0, stats0, sums)
@@ -560,6 +563,7 @@ def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, be
     d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), float(eps)
     d.scale, d.shift, d.ss_ld = _ptr(scale), _ptr(shift), ss_ld
     d.apply_silu, d.resample, d.drop_p, d.drop_seed = int(silu), resample, float(drop_p), int(drop_seed)
+    d.drop_seed_dev = _ptr(drop_seed_dev)
     d.sums = sums.data_ptr()
     d.dx0, d.dx0_accumulate, d.dx1, d.dx1_accumulate = _ptr(dx0), int(dx0_acc), _ptr(dx1), int(dx1_acc)
     d.addend, d.dx_bf16, d.dx_rowsum = _ptr(addend), _ptr(dx_bf16), _ptr(dx_rowsum)

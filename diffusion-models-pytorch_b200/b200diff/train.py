@@ -6,10 +6,18 @@ scripts/train_ddpm.py:171-192 / train_ddpm_cfg.py:172-196:
 
 with the last three fused into b200_optimizer_step, and no host synchronisation anywhere (the loss is returned as a
 device scalar; call `.item()` on it only when it is logged).
+
+`use_cuda_graph=True` (single-GPU, FusedAdam(capturable=True)): after two eager warm-up steps the whole step -- timestep and
+noise draws, diffuse, UNet forward with fresh dropout masks, MSE, every backward kernel, clip + Adam + EMA, and the bf16
+re-pack of the weights -- is captured once per (batch shape, conditional / unconditional) and replayed: the ~830
+kernel launches of a step then cost one graph launch on the host instead of ~25 ms of Python.
 """
 from typing import Dict, Optional
 
 import torch
+import torch.distributed as dist
+
+import b200diff as K
 
 from .dist import allreduce_grads_
 from .optim import FusedAdam
@@ -17,13 +25,18 @@ from .optim import FusedAdam
 
 class TrainStep:
     def __init__(self, model, diffuser, optimizer: FusedAdam, ema=None, clip_grad_norm: Optional[float] = 1.0,
-                 p_uncond: float = 0.0):
+                 p_uncond: float = 0.0, use_cuda_graph: bool = False):
         self.model, self.diffuser, self.optimizer, self.ema = model, diffuser, optimizer, ema
         self.clip_grad_norm = clip_grad_norm
         self.p_uncond = p_uncond      # train_ddpm_cfg.py:183-186: the label is dropped with this probability
+        self.use_cuda_graph = use_cuda_graph
+        if use_cuda_graph and not getattr(optimizer, 'capturable', False):
+            raise ValueError('TrainStep(use_cuda_graph=True) needs FusedAdam(capturable=True)')
+        self._graphs: Dict = {}
+        self._warm: Dict = {}
 
-    def __call__(self, x0: torch.Tensor, t: torch.Tensor = None, y: torch.Tensor = None, eps: torch.Tensor = None,
-                 micro_batch: int = None) -> torch.Tensor:
+    # ------------------------------------------------------------------------------------------
+    def _body(self, x0, t, y, eps, micro_batch):
         B = x0.shape[0]
         micro_batch = B if micro_batch is None else micro_batch
         self.optimizer.zero_grad(set_to_none=True)
@@ -34,9 +47,7 @@ class TrainStep:
                 torch.randint(self.diffuser.total_steps, (xs.shape[0],), device=xs.device).long()
             kw: Dict = {}
             if y is not None:
-                # classifier-free guidance training: the whole micro-batch is unconditional with probability p_uncond
-                drop = self.p_uncond > 0 and float(torch.rand(())) < self.p_uncond
-                kw = dict(y=None if drop else y[i:i + micro_batch])
+                kw = dict(y=y[i:i + micro_batch])
             loss = self.diffuser.loss_func(self.model, x0=xs, t=ts, eps=None if eps is None else eps[i:i + micro_batch],
                                            model_kwargs=kw)
             scale = xs.shape[0] / B
@@ -45,3 +56,64 @@ class TrainStep:
         allreduce_grads_(self.model)
         self.optimizer.step(clip_grad_norm=self.clip_grad_norm, ema=self.ema)
         return total
+
+    def __call__(self, x0: torch.Tensor, t: torch.Tensor = None, y: torch.Tensor = None, eps: torch.Tensor = None,
+                 micro_batch: int = None) -> torch.Tensor:
+        if y is not None and self.p_uncond > 0 and float(torch.rand(())) < self.p_uncond:
+            y = None       # classifier-free guidance training: the whole batch is unconditional with probability p_uncond
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        graphable = (self.use_cuda_graph and world == 1 and t is None and eps is None
+                     and (micro_batch is None or micro_batch >= x0.shape[0]))
+        if not graphable:
+            return self._body(x0, t, y, eps, micro_batch)
+        key = (tuple(x0.shape), x0.dtype, None if y is None else tuple(y.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            if self._warm.get(key, 0) < 2:     # eager warm-up: fills the arena, weight / optimizer tables, .grad storage
+                self._warm[key] = self._warm.get(key, 0) + 1
+                return self._body(x0, None, y, None, None)
+            g = self._capture(x0, y)
+            self._graphs[key] = g
+        g['x0'].copy_(x0)
+        if y is not None:
+            g['y'].copy_(y)
+        lr = self.optimizer.param_groups[0]['lr']
+        if lr != self.optimizer._lr_host:
+            self.optimizer.set_lr(lr)
+        g['graph'].replay()
+        K.GRAPH_LAUNCHES += g['kernels']
+        self.optimizer.mirror_replayed_step(self.ema)
+        return g['loss'].clone()
+
+    def warmup(self, x0, y=None):
+        """Runs (and, in CUDA-graph mode, captures) every variant of the step once: conditional and -- when labels may be
+        dropped -- unconditional.  These are real optimizer steps."""
+        p, self.p_uncond = self.p_uncond, 0.0
+        try:
+            variants = [y] + ([None] if (y is not None and p > 0) else [])
+            for yy in variants:
+                for _ in range(3):
+                    self(x0, y=yy)
+        finally:
+            self.p_uncond = p
+
+    def _capture(self, x0, y):
+        st = {'x0': x0.clone(), 'y': None if y is None else y.clone()}
+        # the captured forward must contain the bf16 re-pack of the weights (every replay follows an optimizer step):
+        # make sure the engine sees "parameters changed" while capturing
+        torch.autograd.graph.increment_version([p for g_ in self.optimizer.param_groups for p in g_['params']])
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = K.direct_launch_count()
+        # the host-side counters advance once here (capture executes the Python body once); the captured kernels are
+        # not executed during capture, so undo that bookkeeping afterwards
+        with torch.cuda.graph(graph):
+            st['loss'] = self._body(st['x0'], None, st['y'], None, None)
+        params = [p for g_ in self.optimizer.param_groups for p in g_['params'] if p.grad is not None]
+        for p in params:
+            self.optimizer.state[p]['step'] -= 1
+        if self.ema is not None:
+            self.ema.num_updates -= 1
+        st['graph'] = graph
+        st['kernels'] = K.direct_launch_count() - n0      # libb200diff kernels replayed per step
+        return st

@@ -45,7 +45,7 @@ struct GnBwdParams {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
-  uint32_t drop_thresh; float drop_scale; unsigned long long drop_seed;
+  uint32_t drop_thresh; float drop_scale; unsigned long long drop_seed; const unsigned long long* drop_seed_dev;
   float* sums;
   float* dx0; int acc0; float* dx1; int acc1; const float* addend;
   __nv_bfloat16* dx_bf16; float* dx_rowsum; int rowsum_ld; float* dx_colsum;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void gn_bwd_dz(const GnBwdParams& p, int n, int px, i
   const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
   const float rav[4] = {ra.x, ra.y, ra.z, ra.w}, rbv[4] = {rb.x, rb.y, rb.z, rb.w};
   uint32_t keep = 15u;
-  if (p.drop_thresh) keep = dropout_keep4(p.drop_seed, (((unsigned long long)n * p.HW + px) * C + c) >> 2, p.drop_thresh);
+  if (p.drop_thresh) keep = dropout_keep4(p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull), (((unsigned long long)n * p.HW + px) * C + c) >> 2, p.drop_thresh);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     xh[i] = fmaf(xv[i], rav[i], rbv[i]);
@@ -620,6 +620,7 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   p.gamma = d->gamma; p.beta = d->beta; p.eps = d->eps; p.scale = d->scale; p.shift = d->shift; p.ss_ld = d->ss_ld;
   p.apply_silu = d->apply_silu; p.resample = d->resample;
   p.drop_thresh = dropout_threshold(d->drop_p); p.drop_scale = 1.0f / (1.0f - d->drop_p); p.drop_seed = d->drop_seed;
+  p.drop_seed_dev = d->drop_seed_dev;
   p.sums = d->sums;
   p.dx0 = d->dx0; p.acc0 = d->dx0_accumulate; p.dx1 = d->dx1; p.acc1 = d->dx1_accumulate; p.addend = d->addend;
   p.dx_bf16 = reinterpret_cast<__nv_bfloat16*>(d->dx_bf16); p.dx_rowsum = d->dx_rowsum;

@@ -289,7 +289,7 @@ struct GnApplyParams {
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
   float drop_p, drop_scale;       // training-mode dropout after the activation (resample == 0 only)
-  uint32_t drop_thresh; unsigned long long drop_seed;
+  uint32_t drop_thresh; unsigned long long drop_seed; const unsigned long long* drop_seed_dev;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -310,6 +310,8 @@ __device__ __forceinline__ float silu_tanh(float x) {
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
   extern __shared__ float gsm[];
+  // dropout seed = per-block offset (by value) + per-forward base read from device memory (CUDA-graph replayable)
+  const unsigned long long drop_seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
   const int C = p.C0 + p.C1;
   float* coefA = gsm;            // [C]
   float* coefB = gsm + C;        // [C]
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
           if (p.apply_silu) { y0 = silu_tanh(y0); y1 = silu_tanh(y1); y2 = silu_tanh(y2); y3 = silu_tanh(y3); }
           if (p.drop_thresh) {
             const unsigned long long e = ((unsigned long long)n * p.HW + q) * C + c;
-            const uint32_t keep = dropout_keep4(p.drop_seed, e >> 2, p.drop_thresh);
+            const uint32_t keep = dropout_keep4(drop_seed, e >> 2, p.drop_thresh);
             y0 = (keep & 1u) ? y0 * p.drop_scale : 0.f;
             y1 = (keep & 2u) ? y1 * p.drop_scale : 0.f;
             y2 = (keep & 4u) ? y2 * p.drop_scale : 0.f;
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
         }
         if (p.drop_thresh) {
           const unsigned long long e = ((unsigned long long)n * p.HW + px) * C + c;
-          const uint32_t keep = dropout_keep4(p.drop_seed, e >> 2, p.drop_thresh);
+          const uint32_t keep = dropout_keep4(drop_seed, e >> 2, p.drop_thresh);
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * p.drop_scale : 0.f;
         }
@@ -498,7 +500,8 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
                                               const float* x1, int C1, const float* stats1, int B, int HW, int W,
                                               int groups, const float* gamma, const float* beta, float eps,
                                               const float* scale, const float* shift, int ss_ld, int apply_silu,
-                                              int resample, float drop_p, unsigned long long drop_seed, void* out_bf16,
+                                              int resample, float drop_p, unsigned long long drop_seed,
+                                              const unsigned long long* drop_seed_dev, void* out_bf16,
                                               void* raw_out_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const float* x0 = reinterpret_cast<const float*>(x0_);
@@ -523,7 +526,7 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.in_bf16 = x0_is_bf16 ? 1 : 0;
   B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
   B200_REQUIRE(drop_p == 0.f || resample == 0, "groupnorm_apply: dropout is not combined with resampling");
-  p.drop_p = drop_p; p.drop_scale = 1.0f / (1.0f - drop_p); p.drop_seed = drop_seed;
+  p.drop_p = drop_p; p.drop_scale = 1.0f / (1.0f - drop_p); p.drop_seed = drop_seed; p.drop_seed_dev = drop_seed_dev;
   p.drop_thresh = dropout_threshold(drop_p);
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
@@ -544,6 +547,6 @@ extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0,
                                         int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
                                         void* stream_) {
   return b200_groupnorm_apply_train_fwd(x0_, x0_is_bf16, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps,
-                                        scale, shift, ss_ld, apply_silu, resample, 0.f, 0ull, out_bf16, raw_out_bf16,
+                                        scale, shift, ss_ld, apply_silu, resample, 0.f, 0ull, nullptr, out_bf16, raw_out_bf16,
                                         stream_);
 }

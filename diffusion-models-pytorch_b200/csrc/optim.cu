@@ -31,32 +31,49 @@ __global__ void __launch_bounds__(256) optim_sumsq_kernel(const b200_optim_chunk
 struct OptimK {
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm, ema_decay;
   int adamw, use_ema;
+  const b200_optim_dev_state* dev;   // when set, lr / bias corrections / EMA decay come from device memory
 };
+
+// One thread: advances the device-resident step counters and derives the per-step scalars, so that a captured CUDA
+// graph of the training step needs no host-computed constants (bias corrections, gradual EMA decay, lr).
+__global__ void optim_prepare_kernel(b200_optim_dev_state* st, float beta1, float beta2, int use_ema) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->step += 1;
+  st->bc1 = (float)(1.0 - pow((double)beta1, (double)st->step));
+  st->bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)st->step));
+  if (use_ema) {
+    st->ema_updates += 1;
+    const float n = (float)st->ema_updates;
+    st->ema_decay = st->ema_gradual ? fminf(st->ema_decay_max, (1.f + n) / (10.f + n)) : st->ema_decay_max;
+  }
+}
 
 __global__ void __launch_bounds__(256) optim_adam_kernel(const b200_optim_chunk* __restrict__ chunks,
                                                          const float* __restrict__ gnorm_sq, const OptimK k) {
   const b200_optim_chunk c = chunks[blockIdx.x];
+  float lr = k.lr, bc1 = k.bc1, bc2_sqrt = k.bc2_sqrt, ema_decay = k.ema_decay;
+  if (k.dev) { lr = k.dev->lr; bc1 = k.dev->bc1; bc2_sqrt = k.dev->bc2_sqrt; ema_decay = k.dev->ema_decay; }
   float coef = 1.f;
   if (k.max_norm > 0.f) {   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
     coef = fminf(1.f, k.max_norm / (sqrtf(gnorm_sq[0]) + 1e-6f));
   }
-  const float step_size = k.lr / k.bc1;
+  const float step_size = lr / bc1;
   for (int i = threadIdx.x; i < c.n; i += 256) {
     float p = c.p[i];
     float g = c.g[i] * coef;
     if (k.wd != 0.f) {
-      if (k.adamw) p *= 1.f - k.lr * k.wd;
+      if (k.adamw) p *= 1.f - lr * k.wd;
       else g = fmaf(k.wd, p, g);
     }
     const float m = fmaf(k.beta1, c.m[i], (1.f - k.beta1) * g);
     const float v = fmaf(k.beta2, c.v[i], (1.f - k.beta2) * g * g);
     c.m[i] = m;
     c.v[i] = v;
-    p -= step_size * m / (sqrtf(v) / k.bc2_sqrt + k.eps);
+    p -= step_size * m / (sqrtf(v) / bc2_sqrt + k.eps);
     c.p[i] = p;
     if (k.use_ema && c.ema) {
       const float e = c.ema[i];
-      c.ema[i] = e - (1.f - k.ema_decay) * (e - p);
+      c.ema[i] = e - (1.f - ema_decay) * (e - p);
     }
   }
 }
@@ -68,7 +85,7 @@ using namespace b200;
 extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(d && d->chunks && d->n_chunks >= 1 && d->gnorm_sq, "optimizer_step: null chunk table / workspace");
-  B200_REQUIRE(d->step >= 1 && d->beta1 >= 0.f && d->beta1 < 1.f && d->beta2 >= 0.f && d->beta2 < 1.f,
+  B200_REQUIRE((d->step >= 1 || d->dev_state) && d->beta1 >= 0.f && d->beta1 < 1.f && d->beta2 >= 0.f && d->beta2 < 1.f,
                "optimizer_step: bad step / betas");
   const b200_optim_chunk* chunks = reinterpret_cast<const b200_optim_chunk*>(d->chunks);
   B200_CHECK(cudaMemsetAsync(d->gnorm_sq, 0, sizeof(float), stream));
@@ -77,10 +94,18 @@ extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
     ++g_launch_count;
     B200_CHECK(cudaGetLastError());
   }
+  if (d->dev_state) {
+    optim_prepare_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<b200_optim_dev_state*>(d->dev_state), d->beta1, d->beta2,
+                                               d->ema_decay >= 0.f ? 1 : 0);
+    ++g_launch_count;
+    B200_CHECK(cudaGetLastError());
+  }
   OptimK k;
+  k.dev = reinterpret_cast<const b200_optim_dev_state*>(d->dev_state);
   k.lr = d->lr; k.beta1 = d->beta1; k.beta2 = d->beta2; k.eps = d->eps; k.wd = d->weight_decay;
-  k.bc1 = (float)(1.0 - pow((double)d->beta1, (double)d->step));
-  k.bc2_sqrt = (float)sqrt(1.0 - pow((double)d->beta2, (double)d->step));
+  const int step = d->step >= 1 ? d->step : 1;
+  k.bc1 = (float)(1.0 - pow((double)d->beta1, (double)step));
+  k.bc2_sqrt = (float)sqrt(1.0 - pow((double)d->beta2, (double)step));
   k.max_norm = d->max_grad_norm; k.adamw = d->adamw;
   k.use_ema = d->ema_decay >= 0.f ? 1 : 0; k.ema_decay = d->ema_decay;
   optim_adam_kernel<<<d->n_chunks, 256, 0, stream>>>(chunks, d->gnorm_sq, k);

@@ -27,9 +27,7 @@ class UNetFunction(torch.autograd.Function):
     def forward(ctx, model, args, kwargs, *params):
         eng = model.engine
         eng.tape = []
-        eng._n_drop = 0
-        # one host-side draw from torch's CPU generator per forward: deterministic under torch.manual_seed
-        eng.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        eng.new_dropout_base()
         try:
             out = model._forward_impl(*args, **kwargs)
             ctx.tape = eng.tape
@@ -77,8 +75,22 @@ class _Grads:
 
     def __init__(self, eng: Engine, params):
         total = sum(p.numel() for p in params)
-        # a fresh buffer per backward: autograd may keep the returned views as the parameters' .grad
-        self.flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
+        # One persistent buffer per engine, zeroed per backward: stable gradient addresses across steps (optimizer
+        # chunk tables, CUDA-graph capture, NCCL buffer registration).  autograd keeps the returned views as the
+        # parameters' .grad, so when a .grad still aliases the buffer (gradient accumulation over micro-batches: a second
+        # backward before zero_grad) this backward gets a fresh buffer instead and autograd adds it to the first.
+        flat = getattr(eng, '_grad_flat', None)
+        aliased = False
+        if flat is not None and flat.numel() == total and flat.device == eng.device:
+            lo, hi = flat.data_ptr(), flat.data_ptr() + 4 * total
+            aliased = any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params)
+        if flat is None or flat.numel() != total or flat.device != eng.device:
+            flat = eng._grad_flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
+        elif aliased:
+            flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
+        else:
+            flat.zero_()
+        self.flat = flat
         self.views: Dict[int, torch.Tensor] = {}
         off = 0
         for p in params:
@@ -170,7 +182,8 @@ def _res_bwd(eng: Engine, e, G: _Grads):
     else:
         kw = dict(dx_rowsum=eng.d_emb[:, off:], dx_rowsum_ld=total)
     K.groupnorm_bwd(da2, h.t, Cout, h.stats, None, 0, None, B, Ho * Wo, Wo, norm2.num_groups, norm2.weight, norm2.bias,
-                    norm2.eps, _sums(eng, B, Cout), silu=True, drop_p=e['drop_p'], drop_seed=e['drop_seed'], dx_bf16=dh,
+                    norm2.eps, _sums(eng, B, Cout), silu=True, drop_p=e['drop_p'], drop_seed=e['drop_seed'],
+                    drop_seed_dev=eng.seed_dev if e['drop_p'] > 0 else None, dx_bf16=dh,
                     dx_colsum=G(conv1.bias), dgamma=G(norm2.weight), dbeta=G(norm2.bias), **kw)
 
     # conv1: weights, data

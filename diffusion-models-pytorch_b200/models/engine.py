@@ -38,6 +38,7 @@ class Engine:
     def __init__(self, model: nn.Module):
         self.model = model
         self._packed: Dict = {}
+        self._const: Dict = {}
         self._sig = None
         self._arena: Dict = {}
         self._stats: Dict = {}
@@ -47,7 +48,7 @@ class Engine:
         self._pt_table = None        # device table over all entries (rebuilt when an entry is added)
         self._pt_scratch: List = []  # single-entry tables of first-use packs (kept alive until the stream consumed them)
         self.tape = None         # training forward: list of records replayed in reverse by models/backward.py
-        self.drop_seed = 0       # base seed of this forward's dropout masks
+        self.seed_dev = None     # int64 [1] device scalar: base seed of this forward's dropout masks (graph replayable)
         self._n_drop = 0
 
     # ------------------------------------------------------------------------------------------
@@ -116,6 +117,13 @@ class Engine:
         if dev.type != 'cuda':
             raise RuntimeError('b200diff models run on a CUDA device only: there is no CPU/PyTorch fallback '
                                f'(parameters are on {dev})')
+
+    def const(self, key, make):
+        """Parameter-independent device constants (frequency tables): survive weight updates, unlike `packed`."""
+        v = self._const.get(key)
+        if v is None:
+            v = self._const[key] = make()
+        return v
 
     def packed(self, key, make):
         v = self._packed.get(key)
@@ -190,11 +198,25 @@ class Engine:
     # ops
     # ------------------------------------------------------------------------------------------
     def next_drop_seed(self):
+        """Per-block offset added (mod 2^64, on the device) to the per-forward base seed in `seed_dev`."""
         self._n_drop += 1
-        return (self.drop_seed + 0x9E3779B97F4A7C15 * self._n_drop) & 0x7FFFFFFFFFFFFFFF
+        return (0x9E3779B97F4A7C15 * self._n_drop) & 0xFFFFFFFFFFFFFFFF
+
+    def new_dropout_base(self):
+        """Draws the per-forward base seed ON THE DEVICE (torch's CUDA generator: reproducible under manual_seed and
+        re-drawn on every replay of a captured graph)."""
+        if self.seed_dev is None or self.seed_dev.device != self.device:
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.seed_dev.random_()
+        self._n_drop = 0
+
+    def dropout_seed_of(self, rec) -> int:
+        """Effective 64-bit seed of a tape record's dropout mask (host sync; for tests that regenerate the mask)."""
+        return (rec['drop_seed'] + int(self.seed_dev.item())) & 0xFFFFFFFFFFFFFFFF
 
     def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
            ss_ld=0, resample=0, drop_p=0.0, drop_seed=0):
+        seed_dev = self.seed_dev if drop_p > 0 else None
         C = x.C + (skip.C if skip is not None else 0)
         Ho, Wo = x.H, x.W
         if resample == 1:
@@ -207,7 +229,8 @@ class Engine:
             K.groupnorm_apply(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
                               None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
                               norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift, ss_ld=ss_ld, silu=silu,
-                              resample=resample, raw_out=raw_out, drop_p=drop_p, drop_seed=drop_seed)
+                              resample=resample, raw_out=raw_out, drop_p=drop_p, drop_seed=drop_seed,
+                              drop_seed_dev=seed_dev)
         else:
             if drop_p > 0 or self.tape is not None:
                 raise RuntimeError(f'{tag}: training needs producer statistics for every GroupNorm input '
@@ -416,7 +439,7 @@ class Engine:
         if use_y:
             y = y.to(torch.long).contiguous()
         E = lin1.out_features
-        freqs = self.packed(('freqs',), lambda: pos_emb.frequencies(dev).float().contiguous())
+        freqs = self.const(('freqs', str(dev)), lambda: pos_emb.frequencies(dev).float().contiguous())
         emb = self.buf('emb', (rows, E), torch.float32)
         semb = self.buf('semb', (rows, E), torch.bfloat16)
         K.time_embed(t_rows, freqs, pos_emb.dim, E, bool(getattr(pos_emb, 'cos_first', False)), lin1.weight, lin1.bias,

@@ -265,11 +265,14 @@ typedef struct b200_wgrad_desc {
 int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream);
 
 /* Training-mode K3: b200_groupnorm_apply_fwd plus dropout after the activation (nn.Dropout of models/unet.py:24).
- * The keep mask is a counter-based hash of (drop_seed, element index): the backward regenerates it, nothing is stored. */
+ * The keep mask is a counter-based hash of (seed, element index): the backward regenerates it, nothing is stored.
+ * seed = drop_seed + *drop_seed_dev (a device scalar, may be NULL): the per-forward base lives in device memory so that
+ * a captured CUDA graph of the training step draws fresh masks on every replay. */
 int b200_groupnorm_apply_train_fwd(const void* x0, int x0_is_bf16, int C0, const float* stats0, const float* x1, int C1,
                                    const float* stats1, int B, int HW, int W, int groups, const float* gamma,
                                    const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
                                    int apply_silu, int resample, float drop_p, unsigned long long drop_seed,
+                                   const unsigned long long* drop_seed_dev,
                                    void* out_bf16, void* raw_out_bf16, void* stream);
 /* keep mask (1.0 / 0.0) of that dropout for elements [0, n): lets the parity tests hand the oracle the same mask */
 int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed, void* stream);
@@ -288,7 +291,7 @@ typedef struct b200_gn_bwd_desc {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
-  float drop_p; unsigned long long drop_seed;
+  float drop_p; unsigned long long drop_seed; const unsigned long long* drop_seed_dev;
   float* sums;
   float* dx0; int dx0_accumulate;
   float* dx1; int dx1_accumulate;
@@ -341,6 +344,16 @@ typedef struct b200_optim_chunk {
   int n; int pad_;
 } b200_optim_chunk;
 
+/* Optional device-resident optimizer state: with it the step count, bias corrections, gradual EMA decay and lr are
+ * advanced / read on the device (one extra 1-thread kernel), so a captured CUDA graph of the whole training step can
+ * be replayed without host-computed scalars.  The host initialises step / ema_updates / lr / ema_decay_max /
+ * ema_gradual and may rewrite lr between replays. */
+typedef struct b200_optim_dev_state {
+  int step, ema_updates;
+  float lr, bc1, bc2_sqrt, ema_decay, ema_decay_max;
+  int ema_gradual;
+} b200_optim_dev_state;
+
 typedef struct b200_optim_desc {
   const void* chunks; int n_chunks;
   float lr, beta1, beta2, eps, weight_decay;
@@ -350,6 +363,7 @@ typedef struct b200_optim_desc {
   int want_norm;
   float* gnorm_sq;
   float ema_decay;          /* < 0: no EMA update */
+  void* dev_state;          /* b200_optim_dev_state in device memory, or NULL (then step / lr / ema_decay above are used) */
 } b200_optim_desc;
 int b200_optimizer_step(const b200_optim_desc* d, void* stream);
 

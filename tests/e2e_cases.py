@@ -325,7 +325,7 @@ def _train_parity(name, model, oracle_kw, x0, t, eps, y=None, gate=3e-2):
     for rec in model.engine.last_tape:
         if rec['kind'] == 'res' and rec['drop_p'] > 0:
             o = rec['out']
-            m = K.dropout_mask(torch.empty(o.B, o.H, o.W, o.C, device=DEV), rec['drop_p'], rec['drop_seed'])
+            m = K.dropout_mask(torch.empty(o.B, o.H, o.W, o.C, device=DEV), rec['drop_p'], model.engine.dropout_seed_of(rec))
             drop[rec['tag']] = (m.permute(0, 3, 1, 2), rec['drop_p'])
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     xt = orc.diffuse(x0, t, eps)
@@ -466,6 +466,82 @@ def case_train_step_adm():
               grad_rel_l2_all=rel_all, worst_tensor=worst_name, worst_tensor_rel_l2=worst, gate=3e-2, ok=good)
         ok &= good
     return ok
+
+
+def case_train_multi_step():
+    """Several optimizer steps in a row (weights really change between forwards): TrainStep (kernel forward/backward +
+    fused clip/Adam/EMA + bf16 re-pack) vs fp32 autograd over the oracle + clip_grad_norm_ + torch.optim.Adam + the
+    reference EMA rule, same data / timesteps / noise, dropout 0.  Then CUDA-graph replay vs eager stepping."""
+    import torch.nn.functional as F
+    from b200diff.optim import FusedAdam
+    from b200diff.train import TrainStep
+    from oracle.unet_ref import unet_forward
+    _no_tf32()
+    cfg = dict(MNIST, dropout=0.0)
+    B, steps = 8, 4
+    g = torch.Generator(device='cpu').manual_seed(12)
+    x0 = torch.randn(B, 1, 32, 32, generator=g).clamp(-1, 1).to(DEV)
+    ts = [torch.randint(0, 1000, (B,), generator=g).to(DEV) for _ in range(steps)]
+    es = [torch.randn(B, 1, 32, 32, generator=g).to(DEV) for _ in range(steps)]
+    torch.manual_seed(2022)
+    m = models.UNet(**cfg).to(DEV).train()
+    ema = models.EMA(m.parameters(), decay=0.9999)
+    d = diffusions.DDPM(total_steps=1000, device=DEV)
+    step = TrainStep(m, d, FusedAdam(m.parameters(), lr=1e-3), ema=ema, clip_grad_norm=1.0)
+    w0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-3)
+    ema_r = models.EMA(list(sd.values()), decay=0.9999)
+    orc = R.DDPMRef(total_steps=1000)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    losses, losses_ref = [], []
+    for i in range(steps):
+        losses.append(step(x0, t=ts[i], eps=es[i]).item())
+        opt.zero_grad()
+        lr_ = F.mse_loss(unet_forward(sd, orc.diffuse(x0, ts[i], es[i]), ts[i], dim=64, n_heads=1), es[i])
+        lr_.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
+        opt.step()
+        ema_r.update(list(sd.values()))
+        losses_ref.append(lr_.item())
+    # compare the accumulated UPDATE (w - w0), which is what the optimizer produced
+    num = den = 0.0
+    for k, p in m.state_dict().items():
+        num += float(((p - w0[k]) - (sd[k].detach() - w0[k])).pow(2).sum())
+        den += float((sd[k].detach() - w0[k]).pow(2).sum())
+    rel_upd = (num / den) ** 0.5
+    lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, losses_ref))
+    ema_err = max(float((a - b).abs().max()) for a, b in zip(ema.shadow, ema_r.shadow))
+    # Adam's m / sqrt(v) turns tiny gradient differences into O(lr) update differences: the loss trajectory is the
+    # tight check, the accumulated update / EMA shadow are sanity bounds
+    ok = rel_upd <= 0.25 and lerr <= 1e-2 and ema_err <= 2e-2
+    _emit(case=f'{steps} training steps vs autograd + torch Adam', losses=losses, losses_ref=losses_ref,
+          max_loss_rel_err=lerr, update_rel_l2=rel_upd, ema_max_abs_err=ema_err, ok=ok)
+
+    # ---- CUDA-graph replay of the whole step vs eager stepping (fresh models, same seeds, dropout ON) ----
+    cfg2 = dict(MNIST)
+    finals, lossv = [], []
+    for use_graph in (False, True):
+        torch.manual_seed(2022)
+        mm = models.UNet(**cfg2).to(DEV).train()
+        em = models.EMA(mm.parameters(), decay=0.9999)
+        st = TrainStep(mm, d, FusedAdam(mm.parameters(), lr=1e-3, capturable=True), ema=em, clip_grad_norm=1.0,
+                       use_cuda_graph=use_graph)
+        torch.manual_seed(77)
+        ls = [st(x0).item() for _ in range(8)]
+        lossv.append(ls)
+        finals.append(torch.cat([p.detach().flatten() for p in mm.parameters()]))
+        steps_host = int(next(iter(st.optimizer.state.values()))['step'])
+        good = steps_host == 8 and em.num_updates == 8
+        _emit(case=f'8 steps, cuda_graph={use_graph}', losses=ls, host_step_count=steps_host, ema_updates=em.num_updates,
+              n_graphs=len(st._graphs), ok=good)
+        ok &= good
+    moved = float((finals[1] - torch.cat([p.detach().flatten() for p in models.UNet(**cfg2).parameters()]).to(DEV)).norm())
+    diff = float((finals[0] - finals[1]).norm() / finals[0].norm())
+    fin = all(abs(a) < 10 for a in lossv[1]) and lossv[1][-1] < lossv[1][0] * 1.5
+    _emit(case='graph replay vs eager: relative parameter difference after 8 steps (random streams may differ)',
+          rel_diff=diff, ok=fin and diff < 5e-2)
+    return ok and fin and diff < 5e-2
 
 
 def case_ode_sampling():

@@ -690,10 +690,11 @@ def case_optimizer():
     from models.ema import EMA
     ok = True
     shapes = [(256, 128, 3, 3), (128,), (70001,), (512, 512), (3, 128, 3, 3)]
-    for adamw, wd in ((False, 0.0), (False, 0.01), (True, 0.05)):
+    for adamw, wd, capt in ((False, 0.0, False), (False, 0.01, False), (True, 0.05, False), (False, 0.0, True),
+                            (True, 0.05, True)):
         ps = [torch.nn.Parameter(_gen(*s, seed=i) * 0.1) for i, s in enumerate(shapes)]
         qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
-        ours = FusedAdam(ps, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, adamw=adamw)
+        ours = FusedAdam(ps, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, adamw=adamw, capturable=capt)
         ref = (torch.optim.AdamW if adamw else torch.optim.Adam)(qs, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
         ema_o, ema_r = EMA(ps, decay=0.9999, gradual=True), EMA(qs, decay=0.9999, gradual=True)
         for step in range(4):
@@ -703,8 +704,10 @@ def case_optimizer():
             norm_ref = torch.nn.utils.clip_grad_norm_(qs, max_norm=1.0)
             ref.step()
             ema_r.update(qs)
+            v0 = ps[0]._version
             ours.step(clip_grad_norm=1.0, ema=ema_o)
-            ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} step {step} grad norm', ours.grad_norm,
+            ok &= ps[0]._version > v0          # raw-pointer updates must still bump the tensors' version counters
+            ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} capturable={capt} step {step} grad norm', ours.grad_norm,
                           norm_ref.view(1), rtol=1e-5, atol=1e-6)
         for i, (p, q) in enumerate(zip(ps, qs)):
             ok &= _report(f'fused adam{"w" if adamw else ""} wd={wd} param {i}', p.detach(), q.detach(), rtol=1e-5, atol=1e-7)

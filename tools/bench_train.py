@@ -45,13 +45,15 @@ def main():
         diffuser = diffusions.DDPM(total_steps=1000, device=dev)
         y = None
     ema = models.EMA(model.parameters(), decay=0.9999)
-    opt = FusedAdam(model.parameters(), lr=2e-4)
-    step = TrainStep(model, diffuser, opt, ema=ema, clip_grad_norm=1.0, p_uncond=0.2 if y is not None else 0.0)
+    opt = FusedAdam(model.parameters(), lr=2e-4, capturable=True)
+    use_graph = os.environ.get('B200_TRAIN_GRAPH', '1') != '0'
+    step = TrainStep(model, diffuser, opt, ema=ema, clip_grad_norm=1.0, p_uncond=0.2 if y is not None else 0.0,
+                     use_cuda_graph=use_graph)
     g = torch.Generator(device='cpu').manual_seed(2022 + rank)
     x0 = (torch.randn(B, 3, 32, 32, generator=g) * 0.5).clamp(-1, 1).to(dev)
     losses = []
-    for _ in range(3):
-        losses.append(step(x0, y=y))
+    step.warmup(x0, y)        # eager steps, then the CUDA-graph captures (conditional and unconditional)
+    losses.append(step(x0, y=y))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -69,7 +71,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
-    launches = (K.direct_launch_count() - n0) // steps
+    launches = (K.launch_count() - n0) // steps
+    step.use_cuda_graph = False       # per-kernel CUDA-event profile of one eagerly launched step
     with K.Profiler() as prof:
         step(x0, y=y)
     kern = prof.summary()

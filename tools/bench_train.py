@@ -58,7 +58,7 @@ def main():
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = K.direct_launch_count()
+    n0 = K.launch_count()
     import time
     e0.record()
     h0 = time.perf_counter()

@@ -52,10 +52,19 @@ struct GnBwdParams {
   float* dgamma; float* dbeta; float* dscale; float* dshift; int dss_ld;
 };
 
-// per-channel forward coefficients: z = x*cA + cB, xh = x*rA + rB   (smem arrays of C floats each)
-__device__ __forceinline__ void gn_bwd_coefs(const GnBwdParams& p, int n, float* cA, float* cB, float* rA, float* rB,
-                                             float* tmpS, float* tmpQ) {
+// Workspace layout (d->sums, [B][8][C] floats): rows 0,1 = S1, S2 (channel sums of dz and dz*xh); rows 2..5 = the
+// forward coefficients z = x*cA + cB, xh = x*rA + rB; rows 6,7 = k2, k3 of dx = dz*cA - k2 - xh*k3.
+// The coefficient rows are computed ONCE per image by small kernels, so the two streaming passes start loading data
+// immediately (no per-CTA prologue: with it the passes ran at 25 % of HBM bandwidth on the 16x16 / 32x32 slabs).
+__device__ __forceinline__ float* gn_ws(const GnBwdParams& p, int n, int row) {
+  return p.sums + ((size_t)n * 8 + row) * (p.C0 + p.C1);
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const GnBwdParams p) {
+  extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
+  float* tmpS = bsm; float* tmpQ = bsm + C;
+  const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
     tmpS[c] = __ldg(st);
@@ -77,12 +86,42 @@ __device__ __forceinline__ void gn_bwd_coefs(const GnBwdParams& p, int n, float*
       ga *= sc;
       be = be * sc + __ldg(p.shift + (size_t)n * p.ss_ld + c);
     }
-    cA[c] = rstd * ga;
-    cB[c] = be - mean * rstd * ga;
-    rA[c] = rstd;
-    rB[c] = -mean * rstd;
+    gn_ws(p, n, 0)[c] = 0.f;
+    gn_ws(p, n, 1)[c] = 0.f;
+    gn_ws(p, n, 2)[c] = rstd * ga;
+    gn_ws(p, n, 3)[c] = be - mean * rstd * ga;
+    gn_ws(p, n, 4)[c] = rstd;
+    gn_ws(p, n, 5)[c] = -mean * rstd;
   }
-  __syncthreads();
+}
+
+// k2 / k3 from the channel sums, parameter gradients of image n
+__global__ void __launch_bounds__(256) gn_bwd_final_kernel(const GnBwdParams p) {
+  const int C = p.C0 + p.C1;
+  const int n = blockIdx.x;
+  const float* S1 = gn_ws(p, n, 0); const float* S2 = gn_ws(p, n, 1);
+  const float* cA = gn_ws(p, n, 2); const float* rA = gn_ws(p, n, 4);
+  const float inv_m = 1.0f / (float)(p.HW * p.cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / p.cpg) * p.cpg;
+    float A = 0.f, Bq = 0.f;
+    for (int i = 0; i < p.cpg; ++i) {
+      const float gp = cA[g0 + i] / rA[g0 + i];     // g' = gamma (1 + scale)
+      A = fmaf(gp, S1[g0 + i], A);
+      Bq = fmaf(gp, S2[g0 + i], Bq);
+    }
+    gn_ws(p, n, 6)[c] = rA[c] * A * inv_m;
+    gn_ws(p, n, 7)[c] = rA[c] * Bq * inv_m;
+    const float s1 = S1[c], s2 = S2[c];
+    const float sc = p.scale ? 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c) : 1.f;
+    if (p.dgamma) atomicAdd(p.dgamma + c, s2 * sc);
+    if (p.dbeta) atomicAdd(p.dbeta + c, s1 * sc);
+    if (p.dscale) {
+      const float ga = p.gamma ? __ldg(p.gamma + c) : 1.f, be = p.beta ? __ldg(p.beta + c) : 0.f;
+      p.dscale[(size_t)n * p.dss_ld + c] = ga * s2 + be * s1;
+      p.dshift[(size_t)n * p.dss_ld + c] = s1;
+    }
+  }
 }
 
 // gradient w.r.t. the activated output at input pixel px (adjoint of the forward's resampling), 4 channels
@@ -134,10 +173,10 @@ __device__ __forceinline__ void gn_bwd_dz(const GnBwdParams& p, int n, int px, i
 __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
-  float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
-  float* accS = bsm + 4 * C; float* accQ = bsm + 5 * C;
+  float* accS = bsm; float* accQ = bsm + C;
   const int n = blockIdx.y, tid = threadIdx.x;
-  gn_bwd_coefs(p, n, cA, cB, rA, rB, accS, accQ);
+  const float* cA = gn_ws(p, n, 2); const float* cB = gn_ws(p, n, 3);
+  const float* rA = gn_ws(p, n, 4); const float* rB = gn_ws(p, n, 5);
   for (int c = tid; c < C; c += 256) { accS[c] = 0.f; accQ[c] = 0.f; }
   __syncthreads();
   const int nv = C >> 2;
@@ -149,8 +188,8 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams
     const int j = j0 + tid % cols, prow = tid / cols;
     if (prow >= pstep || j >= nv) continue;
     const int c = j << 2;
-    const float4 a = *reinterpret_cast<const float4*>(cA + c), b = *reinterpret_cast<const float4*>(cB + c);
-    const float4 ra = *reinterpret_cast<const float4*>(rA + c), rb = *reinterpret_cast<const float4*>(rB + c);
+    const float4 a = bw_ldg4(cA + c), b = bw_ldg4(cB + c);
+    const float4 ra = bw_ldg4(rA + c), rb = bw_ldg4(rB + c);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     for (int px = px0 + prow; px < px1; px += 4 * pstep) {
       float4 xs[4], gs[4];
@@ -177,57 +216,23 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams
   }
   __syncthreads();
   for (int c = tid; c < C; c += 256) {
-    atomicAdd(p.sums + ((size_t)n * C + c) * 2, accS[c]);
-    atomicAdd(p.sums + ((size_t)n * C + c) * 2 + 1, accQ[c]);
+    atomicAdd(gn_ws(p, n, 0) + c, accS[c]);
+    atomicAdd(gn_ws(p, n, 1) + c, accQ[c]);
   }
 }
 
 __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
-  float* cA = bsm; float* cB = bsm + C; float* rA = bsm + 2 * C; float* rB = bsm + 3 * C;
-  float* k2 = bsm + 4 * C; float* k3 = bsm + 5 * C;   // dx = dz*cA(=rstd g') - k2 - xh*k3
-  float* rsum = bsm + 6 * C;
+  float* rsum = bsm;
   const int n = blockIdx.y, tid = threadIdx.x;
-  gn_bwd_coefs(p, n, cA, cB, rA, rB, k2, k3);
-  // k2/k3 currently hold scratch; load the channel sums S1, S2 into them, then turn them into group terms
-  for (int c = tid; c < C; c += 256) {
-    k2[c] = __ldg(p.sums + ((size_t)n * C + c) * 2);
-    k3[c] = __ldg(p.sums + ((size_t)n * C + c) * 2 + 1);
-    rsum[c] = 0.f;
+  const float* cA = gn_ws(p, n, 2); const float* cB = gn_ws(p, n, 3);
+  const float* rA = gn_ws(p, n, 4); const float* rB = gn_ws(p, n, 5);
+  const float* k2 = gn_ws(p, n, 6); const float* k3 = gn_ws(p, n, 7);
+  if (p.dx_rowsum || p.dx_colsum) {
+    for (int c = tid; c < C; c += 256) rsum[c] = 0.f;
+    __syncthreads();
   }
-  __syncthreads();
-  const float inv_m = 1.0f / (float)(p.HW * p.cpg);
-  float t2[8], t3[8];   // up to 8 channels per thread in this prologue loop (C <= 2048)
-  int cnt = 0;
-  for (int c = tid; c < C; c += 256, ++cnt) {
-    const int g0 = (c / p.cpg) * p.cpg;
-    float A = 0.f, Bq = 0.f;
-    for (int i = 0; i < p.cpg; ++i) {
-      // g'_i = cA_i / rstd
-      const float gp = cA[g0 + i] / rA[g0 + i];
-      A = fmaf(gp, k2[g0 + i], A);
-      Bq = fmaf(gp, k3[g0 + i], Bq);
-    }
-    t2[cnt] = rA[c] * A * inv_m;
-    t3[cnt] = rA[c] * Bq * inv_m;
-    if (blockIdx.x == 0) {   // parameter gradients of image n, once
-      const float S1 = k2[c], S2 = k3[c];
-      const float sc = p.scale ? 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + c) : 1.f;
-      if (p.dgamma) atomicAdd(p.dgamma + c, S2 * sc);
-      if (p.dbeta) atomicAdd(p.dbeta + c, S1 * sc);
-      if (p.dscale) {
-        const float ga = p.gamma ? __ldg(p.gamma + c) : 1.f, be = p.beta ? __ldg(p.beta + c) : 0.f;
-        p.dscale[(size_t)n * p.dss_ld + c] = ga * S2 + be * S1;
-        p.dshift[(size_t)n * p.dss_ld + c] = S1;
-      }
-    }
-  }
-  __syncthreads();
-  cnt = 0;
-  for (int c = tid; c < C; c += 256, ++cnt) { k2[c] = t2[cnt]; k3[c] = t3[cnt]; }
-  __syncthreads();
-
   const int nv = C >> 2;
   const int cols = nv < 256 ? nv : 256;
   const int pstep = 256 / cols;
@@ -237,9 +242,9 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
     const int j = j0 + tid % cols, prow = tid / cols;
     if (prow >= pstep || j >= nv) continue;
     const int c = j << 2;
-    const float4 a = *reinterpret_cast<const float4*>(cA + c), b = *reinterpret_cast<const float4*>(cB + c);
-    const float4 ra = *reinterpret_cast<const float4*>(rA + c), rb = *reinterpret_cast<const float4*>(rB + c);
-    const float4 q2 = *reinterpret_cast<const float4*>(k2 + c), q3 = *reinterpret_cast<const float4*>(k3 + c);
+    const float4 a = bw_ldg4(cA + c), b = bw_ldg4(cB + c);
+    const float4 ra = bw_ldg4(rA + c), rb = bw_ldg4(rB + c);
+    const float4 q2 = bw_ldg4(k2 + c), q3 = bw_ldg4(k3 + c);
     const float av[4] = {a.x, a.y, a.z, a.w}, q2v[4] = {q2.x, q2.y, q2.z, q2.w}, q3v[4] = {q3.x, q3.y, q3.z, q3.w};
     const bool from0 = c < p.C0;
     float* dst = from0 ? p.dx0 : p.dx1;
@@ -638,12 +643,12 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
     B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  B200_CHECK(cudaMemsetAsync(d->sums, 0, (size_t)d->B * C * 2 * sizeof(float), stream));
-  gn_bwd_reduce_kernel<<<grid, 256, (size_t)6 * C * 4, stream>>>(p);
-  ++g_launch_count;
+  gn_bwd_coef_kernel<<<d->B, 256, (size_t)2 * C * 4, stream>>>(p);
+  gn_bwd_reduce_kernel<<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
+  gn_bwd_final_kernel<<<d->B, 256, 0, stream>>>(p);
   B200_CHECK(cudaGetLastError());
-  gn_bwd_apply_kernel<<<grid, 256, (size_t)7 * C * 4, stream>>>(p);
-  ++g_launch_count;
+  gn_bwd_apply_kernel<<<grid, 256, (size_t)C * 4, stream>>>(p);
+  g_launch_count += 4;
   return check_cuda(cudaGetLastError(), "gn_bwd kernels launch");
 }
 

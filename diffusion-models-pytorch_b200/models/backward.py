@@ -138,7 +138,7 @@ def _wgrad(eng: Engine, *args, **kw):
 
 
 def _sums(eng: Engine, B, C):
-    return eng.buf('gn_bwd_sums', (B, C, 2), torch.float32)
+    return eng.buf('gn_bwd_sums', (B, 8, C), torch.float32)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -282,7 +282,7 @@ int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed,
  * Outputs: dx as fp32 split over the two sources (store or accumulate each; optional fp32 addend [B][HW][C] folded
  * in, e.g. the residual branch's gradient), or as one bf16 tensor (+ optional per-(image, channel) sums of dx in
  * dx_rowsum, accumulated: the time-embedding-row gradient of the producing conv; dx_colsum: its bias gradient);
- * dgamma/dbeta [C] accumulate; dscale/dshift [B][dss_ld] are written. sums: workspace [B][C][2]. */
+ * dgamma/dbeta [C] accumulate; dscale/dshift [B][dss_ld] are written. sums: workspace [B][8][C] floats. */
 typedef struct b200_gn_bwd_desc {
   const void* g;
   const float* x0; int C0; const float* stats0;

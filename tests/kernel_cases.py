@@ -560,7 +560,7 @@ def _gn_bwd_case(name, B, H, W, C0, C1, *, silu=True, adagn=False, resample=0, d
         return torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
     st0 = stats(x0)
     st1 = stats(x1) if C1 else None
-    sums = torch.empty(B, C, 2, device=DEV)
+    sums = torch.empty(B, 8, C, device=DEV)
     dgamma, dbeta = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dss = torch.full((B, 2 * C), float('nan'), device=DEV) if adagn else None
     kw = dict(scale=scale, shift=shift, ss_ld=C if adagn else 0, silu=silu, resample=resample, drop_p=drop_p,

@@ -36,7 +36,7 @@ def run(C, H, bf16_out=True, drop=0.1):
     st = torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
     g = torch.randn(B, H, W, C, device=DEV).to(torch.bfloat16)
     gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
-    sums = torch.empty(B, C, 2, device=DEV)
+    sums = torch.empty(B, 8, C, device=DEV)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     dxb = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
     dx = torch.empty(B, H, W, C, device=DEV)

@@ -7,6 +7,7 @@
 // normalised, activated values are rounded to bf16 exactly once on the way out.  HBM traffic = 4 B read +
 // 2 B written per element (+2 B when the raw bf16 copy for the 1x1 shortcut conv is requested).
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/b200diff.h"
 
 namespace b200 {
@@ -286,6 +287,7 @@ struct GnApplyParams {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
+  int reverse;  // walk images / pixel ranges from the end: the producer's most recent writes are still in L2
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
   float drop_p, drop_scale;       // training-mode dropout after the activation (resample == 0 only)
@@ -317,7 +319,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
   float* coefB = gsm + C;        // [C]
   float* chS = gsm + 2 * C;      // [C] channel sums
   float* chQ = gsm + 3 * C;      // [C] channel sums of squares
-  const int n = blockIdx.y;
+  const int n = p.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int bx = p.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int tid = threadIdx.x;
   griddep_sync();
   for (int c = tid; c < C; c += 256) {
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
 
   const int nv = C >> 2;
   if (p.resample != 1) {
-    const int px0 = blockIdx.x * p.pix_per_cta;
+    const int px0 = bx * p.pix_per_cta;
     const int px1 = min(p.HW, px0 + p.pix_per_cta);
     if (p.resample == 0 && (256 % nv) == 0) {
       // fast path: a thread owns one 4-channel column (coefficients in registers) and walks down the pixels
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
     }
   } else {  // 2x2 average pool of the activated values; the CTA's pixel range is over OUTPUT pixels
     const int Wo = p.W >> 1, HWo = p.HW >> 2;
-    const int po0 = blockIdx.x * p.pix_per_cta;
+    const int po0 = bx * p.pix_per_cta;
     const int po1 = min(HWo, po0 + p.pix_per_cta);
     const int total = (po1 - po0) * nv;
     for (int idx = tid; idx < total; idx += 256) {
@@ -524,6 +527,8 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
   p.apply_silu = apply_silu; p.resample = resample;
   p.in_bf16 = x0_is_bf16 ? 1 : 0;
+  static const char* env_rev = getenv("B200_L2_REVERSE");
+  p.reverse = (env_rev && atoi(env_rev) == 0) ? 0 : 1;
   B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
   B200_REQUIRE(drop_p == 0.f || resample == 0, "groupnorm_apply: dropout is not combined with resampling");
   p.drop_p = drop_p; p.drop_scale = 1.0f / (1.0f - drop_p); p.drop_seed = drop_seed; p.drop_seed_dev = drop_seed_dev;

@@ -92,11 +92,13 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
 // fp32 NHWC -> bf16 NHWC (optionally into 4 parity planes)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                        int B, int H, int W, int C, int parity) {
+                                                        int B, int H, int W, int C, int parity, int reverse) {
   const int cv = C >> 2;
   const size_t total = (size_t)B * H * W * cv;
   griddep_sync();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t ii = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ii < total; ii += (size_t)gridDim.x * blockDim.x) {
+    // reverse: start from the end of the tensor, where the producer's most recent writes are still in L2
+    const size_t i = reverse ? total - 1 - ii : ii;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     uint2 u;
     u.x = pack_bf16x2(v.x, v.y);
@@ -279,8 +281,10 @@ extern "C" int b200_cast_bf16(const float* x, void* out, int B, int H, int W, in
   B200_REQUIRE(C % 4 == 0, "cast_bf16: C=%d must be a multiple of 4", C);
   if (parity_split) B200_REQUIRE(H % 2 == 0 && W % 2 == 0, "cast_bf16: parity split needs even H, W");
   const size_t total = (size_t)B * H * W * (C / 4);
+  static const char* env_rev = getenv("B200_L2_REVERSE");
+  const int reverse = (env_rev && atoi(env_rev) == 0) ? 0 : 1;
   B200_CHECK(launch_pdl(cast_bf16_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, stream, x,
-                        reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, parity_split));
+                        reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, parity_split, reverse));
   ++g_launch_count;
   return 0;
 }

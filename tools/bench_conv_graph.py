@@ -12,9 +12,13 @@ import b200diff as K  # noqa: E402
 
 DEV = 'cuda'
 B = int(os.environ.get('B', 256))
+REPLAYS = int(os.environ.get('REPLAYS', 5))
+ONLY = os.environ.get('ONLY')
 
 
 def run(name, Cin, Cout, H, k=3, residual=False, out_mode=K.OUT_F32_NHWC, reps=20):
+    if ONLY and ONLY not in name:
+        return
     W = H
     a0 = torch.randn(B, H, W, Cin, device=DEV).to(torch.bfloat16)
     w = K.pack_weight(torch.randn(Cout, Cin, k, k, device=DEV) / math.sqrt(k * k * Cin))
@@ -42,11 +46,11 @@ def run(name, Cin, Cout, H, k=3, residual=False, out_mode=K.OUT_F32_NHWC, reps=2
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    for _ in range(REPLAYS):
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / (5 * reps) * 1e3
+    us = e0.elapsed_time(e1) / (REPLAYS * reps) * 1e3
     macs = 1.0 * B * H * W * Cout * k * k * Cin
     print(f'{name:44s} {us:8.1f} us  {2 * macs / us / 1e6:7.1f} TFLOP/s', flush=True)
 

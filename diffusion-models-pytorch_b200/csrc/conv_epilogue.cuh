@@ -34,6 +34,7 @@ constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
 constexpr int kBlockK = 64;
 constexpr int kWBytes = kBlockC * kBlockK * 2;  // 16 KB weight tile
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kThreadsWide = 576;  // ... + 16 epilogue warps (epi_halves == 4; fewer registers per thread)
 constexpr int kMaxStages = 8;
 
 struct __align__(8) ConvBarriers {

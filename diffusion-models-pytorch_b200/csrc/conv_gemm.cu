@@ -23,7 +23,8 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
 int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_);
 int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh, int bn);
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kT>
+__global__ void __launch_bounds__(kT, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,7 +199,8 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     int dev = 0;
     B200_CHECK(cudaGetDevice(&dev));
     B200_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int c_tiles = (d->N + kBlockC - 1) / kBlockC;
   ConvKParams p;
@@ -249,7 +251,8 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
 
   // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
   static const char* env_halves = getenv("B200_EPI_HALVES");
-  p.epi_halves = (env_halves && atoi(env_halves) == 1) ? 1 : 2;
+  p.epi_halves = env_halves ? atoi(env_halves) : 2;
+  if (p.epi_halves != 1 && p.epi_halves != 2 && p.epi_halves != 4) p.epi_halves = 2;
   static const char* env_rot = getenv("B200_K_ROTATE");
   p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
 
@@ -287,7 +290,10 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  B200_CHECK(launch_pdl(conv_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
+  if (p.epi_halves == 4)
+    B200_CHECK(launch_pdl(conv_gemm_kernel<kThreadsWide>, dim3(grid), dim3(64 + 128 * 4), smem_bytes, stream, mapA0, mapA1, mapW, p));
+  else
+    B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads>, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
   ++g_launch_count;
   return 0;
 }

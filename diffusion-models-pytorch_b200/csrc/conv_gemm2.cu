@@ -94,7 +94,8 @@ struct PairParams {
 
 constexpr int kPairStageBytes = kWBytes + 128 * 128;   // 16 KB weights + 128 pixels x 128 B per CTA
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kT>
+__global__ void __launch_bounds__(kT, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p,
                       const __grid_constant__ PairParams pp) {
@@ -267,7 +268,8 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
     int dev = 0;
     B200_CHECK(cudaGetDevice(&dev));
     B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int max_clusters = sms / 2;
   const int clusters = pp.pair_tiles < max_clusters ? pp.pair_tiles : max_clusters;
@@ -286,7 +288,10 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel, mapA0, mapA1, mapW, p, pp));
+  if (p.epi_halves == 4)
+    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreadsWide>, mapA0, mapA1, mapW, p, pp));
+  else
+    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreads>, mapA0, mapA1, mapW, p, pp));
   ++g_launch_count;
   return 0;
 }

@@ -287,6 +287,7 @@ struct GnApplyParams {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
+  int cols8;    // 8-channel columns: C0, C1 multiples of 8 and C / 8 <= 256
   int reverse;  // walk images / pixel ranges from the end: the producer's most recent writes are still in L2
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
@@ -310,7 +311,88 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return x * fmaf(0.5f, th, 0.5f);
 }
 
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParams p) {
+// Fast path of the streaming kernel: a thread owns one 8-channel column (coefficients in registers) and walks down the
+// CTA's pixels with kU independent 16-byte (bf16 source) / 2 x 16-byte (fp32 source) loads in flight; every store is
+// a full 16-byte bf16x8.  (With 4-channel columns a bf16 source moved only 8 bytes per load and ran latency-bound.)
+template <bool kInBf16, int kU>
+__device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const float* coefA, const float* coefB, int n,
+                                               int px0, int px1, unsigned long long drop_seed) {
+  const int C = p.C0 + p.C1;
+  const int nv8 = C >> 3;
+  const int pstep = 256 / nv8;
+  const int tid = threadIdx.x;
+  if (tid >= pstep * nv8) return;
+  const int j = tid % nv8, prow = tid / nv8;
+  const int c = j << 3;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = coefA[c + i]; b[i] = coefB[c + i]; }
+  const bool from0 = c < p.C0;
+  const int sld = from0 ? p.C0 : p.C1;
+  const float* src = from0 ? p.x0 + (size_t)n * p.HW * p.C0 + c : p.x1 + (size_t)n * p.HW * p.C1 + (c - p.C0);
+  const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.x0) + (size_t)n * p.HW * p.C0 + c;
+  __nv_bfloat16* dst = p.out + (size_t)n * p.HW * C + c;
+  __nv_bfloat16* rdst = p.raw ? p.raw + (size_t)n * p.HW * C + c : nullptr;
+  for (int px = px0 + prow; px < px1; px += kU * pstep) {
+    uint4 raw0[kU], raw1[kInBf16 ? 1 : kU];   // loads stay packed until they are consumed (register budget: 4 CTAs / SM)
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int q = px + u * pstep;
+      if (q < px1) {
+        if (kInBf16) {
+          raw0[u] = __ldg(reinterpret_cast<const uint4*>(srcb + (size_t)q * sld));
+        } else {
+          raw0[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld));
+          raw1[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld + 4));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int q = px + u * pstep;
+      if (q >= px1) break;
+      float v[8];
+      if (kInBf16) {
+        const uint32_t ww[4] = {raw0[u].x, raw0[u].y, raw0[u].z, raw0[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[2 * i] = __uint_as_float(ww[i] << 16);
+          v[2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u);
+        }
+      } else {
+        v[0] = __uint_as_float(raw0[u].x); v[1] = __uint_as_float(raw0[u].y);
+        v[2] = __uint_as_float(raw0[u].z); v[3] = __uint_as_float(raw0[u].w);
+        v[4] = __uint_as_float(raw1[kInBf16 ? 0 : u].x); v[5] = __uint_as_float(raw1[kInBf16 ? 0 : u].y);
+        v[6] = __uint_as_float(raw1[kInBf16 ? 0 : u].z); v[7] = __uint_as_float(raw1[kInBf16 ? 0 : u].w);
+      }
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        y[i] = fmaf(v[i], a[i], b[i]);
+        if (p.apply_silu) y[i] = silu_tanh(y[i]);
+      }
+      if (p.drop_thresh) {
+        const unsigned long long e = ((unsigned long long)n * p.HW + q) * C + c;
+        const uint32_t keep = dropout_keep4(drop_seed, e >> 2, p.drop_thresh) |
+                              (dropout_keep4(drop_seed, (e >> 2) + 1, p.drop_thresh) << 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * p.drop_scale : 0.f;
+      }
+      uint4 uo;
+      uo.x = pack_bf16x2(y[0], y[1]); uo.y = pack_bf16x2(y[2], y[3]);
+      uo.z = pack_bf16x2(y[4], y[5]); uo.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(dst + (size_t)q * C) = uo;
+      if (rdst) {
+        uint4 ur;
+        ur.x = pack_bf16x2(v[0], v[1]); ur.y = pack_bf16x2(v[2], v[3]);
+        ur.z = pack_bf16x2(v[4], v[5]); ur.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(rdst + (size_t)q * C) = ur;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyParams p) {
   extern __shared__ float gsm[];
   // dropout seed = per-block offset (by value) + per-forward base read from device memory (CUDA-graph replayable)
   const unsigned long long drop_seed = p.drop_seed + ((p.drop_thresh && p.drop_seed_dev) ? *p.drop_seed_dev : 0ull);
@@ -353,6 +435,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GnApplyParam
   if (p.resample != 1) {
     const int px0 = bx * p.pix_per_cta;
     const int px1 = min(p.HW, px0 + p.pix_per_cta);
+    if (p.resample == 0 && p.cols8) {
+      if (p.in_bf16) gn_apply_cols8<true, 4>(p, coefA, coefB, n, px0, px1, drop_seed);
+      else gn_apply_cols8<false, 2>(p, coefA, coefB, n, px0, px1, drop_seed);
+      return;
+    }
     if (p.resample == 0 && (256 % nv) == 0) {
       // fast path: a thread owns one 4-channel column (coefficients in registers) and walks down the pixels
       const int j = tid % nv, prow = tid / nv, pstep = 256 / nv;
@@ -527,6 +614,8 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
   p.apply_silu = apply_silu; p.resample = resample;
   p.in_bf16 = x0_is_bf16 ? 1 : 0;
+  static const char* env_c8 = getenv("B200_GN_COLS8");
+  p.cols8 = (C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= 256 && !(env_c8 && atoi(env_c8) == 0)) ? 1 : 0;
   static const char* env_rev = getenv("B200_L2_REVERSE");
   p.reverse = (env_rev && atoi(env_rev) == 0) ? 0 : 1;
   B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
@@ -536,7 +625,7 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
   const int work_pix = resample == 1 ? HW / 4 : HW;
-  int ppc = (resample == 1 ? 8192 : 32768) / C;  // ~128 KB of fp32 input per CTA
+  int ppc = (resample == 1 ? 8192 : x0_is_bf16 ? 65536 : 32768) / C;  // ~128 KB of input per CTA
   if (ppc < 1) ppc = 1;
   if (ppc > work_pix) ppc = work_pix;
   p.pix_per_cta = ppc;

@@ -33,7 +33,8 @@ class Act:
 class Engine:
     # conv1 outputs of ResBlocks (consumed only by the following GroupNorm) are stored as bf16; their GroupNorm
     # statistics still come from the fp32 accumulators in the conv epilogue
-    h_bf16 = bool(int(__import__('os').environ.get('B200_H_BF16', '0')))  # measured: +0.6e-3 eps error for no speed-up
+    # (inference only; measured: eps rel-L2 +0.6e-3, DDIM-50 CIFAR-10 +2 %, pesser-256 forward +3.4 %)
+    h_bf16 = bool(int(__import__('os').environ.get('B200_H_BF16', '1')))
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -246,7 +247,7 @@ class Engine:
         w, b = self.w_conv(tag, conv, sc_conv)
         stats = None
         if out is None:
-            if intermediate and self.h_bf16 and Cout > 32 and self.tape is None:
+            if intermediate and self.h_bf16 and Cout >= 128 and self.tape is None:   # narrow toy nets keep fp32 h
                 out_mode = K.OUT_BF16_NHWC
             out = self.buf(tag + '.out', (B, H, W, Cout),
                            torch.bfloat16 if out_mode == K.OUT_BF16_NHWC else torch.float32)

@@ -287,7 +287,7 @@ struct GnApplyParams {
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
-  int cols8;    // 8-channel columns: C0, C1 multiples of 8 and C / 8 <= 256
+  int cols8;    // 8-channel columns: C0, C1 multiples of 8 and C / 8 <= 256; 2 = coefficients computed per thread
   int reverse;  // walk images / pixel ranges from the end: the producer's most recent writes are still in L2
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
   __nv_bfloat16* out; __nv_bfloat16* raw;
@@ -314,7 +314,10 @@ __device__ __forceinline__ float silu_tanh(float x) {
 // Fast path of the streaming kernel: a thread owns one 8-channel column (coefficients in registers) and walks down the
 // CTA's pixels with kU independent 16-byte (bf16 source) / 2 x 16-byte (fp32 source) loads in flight; every store is
 // a full 16-byte bf16x8.  (With 4-channel columns a bf16 source moved only 8 bytes per load and ran latency-bound.)
-template <bool kInBf16, int kU>
+// kOwnCoef: the thread derives the y = x*a + b coefficients of ITS 8 channels straight from the producer's statistics
+// (its GroupNorm groups lie inside / are made of whole 8-channel columns), after its first data loads were issued:
+// no shared-memory prologue, no __syncthreads, the statistics' latency hides behind the data loads.
+template <bool kInBf16, int kU, bool kOwnCoef>
 __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const float* coefA, const float* coefB, int n,
                                                int px0, int px1, unsigned long long drop_seed) {
   const int C = p.C0 + p.C1;
@@ -324,17 +327,14 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
   if (tid >= pstep * nv8) return;
   const int j = tid % nv8, prow = tid / nv8;
   const int c = j << 3;
-  float a[8], b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = coefA[c + i]; b[i] = coefB[c + i]; }
   const bool from0 = c < p.C0;
   const int sld = from0 ? p.C0 : p.C1;
   const float* src = from0 ? p.x0 + (size_t)n * p.HW * p.C0 + c : p.x1 + (size_t)n * p.HW * p.C1 + (c - p.C0);
   const __nv_bfloat16* srcb = reinterpret_cast<const __nv_bfloat16*>(p.x0) + (size_t)n * p.HW * p.C0 + c;
   __nv_bfloat16* dst = p.out + (size_t)n * p.HW * C + c;
   __nv_bfloat16* rdst = p.raw ? p.raw + (size_t)n * p.HW * C + c : nullptr;
-  for (int px = px0 + prow; px < px1; px += kU * pstep) {
-    uint4 raw0[kU], raw1[kInBf16 ? 1 : kU];   // loads stay packed until they are consumed (register budget: 4 CTAs / SM)
+  uint4 raw0[kU], raw1[kInBf16 ? 1 : kU];   // loads stay packed until they are consumed (register budget: 4 CTAs / SM)
+  auto issue = [&](int px) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int q = px + u * pstep;
@@ -343,10 +343,73 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
           raw0[u] = __ldg(reinterpret_cast<const uint4*>(srcb + (size_t)q * sld));
         } else {
           raw0[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld));
-          raw1[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld + 4));
+          raw1[kInBf16 ? 0 : u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld + 4));
         }
       }
     }
+  };
+  int px = px0 + prow;
+  if (px >= px1) return;
+  issue(px);
+  float a[8], b[8];
+  if (kOwnCoef) {
+    const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);
+    float mean[8], rstd[8];
+    if (p.cpg <= 8) {
+      // statistics of the own 8 channels: 16 consecutive floats of [n][c][2]
+      const float* st = from0 ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+      float sq[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = ldg4(st + 4 * i);
+        sq[4 * i] = t.x; sq[4 * i + 1] = t.y; sq[4 * i + 2] = t.z; sq[4 * i + 3] = t.w;
+      }
+#pragma unroll
+      for (int i0 = 0; i0 < 8; i0 += 1) {
+        const int g0 = i0 & ~(p.cpg - 1);          // cpg is 1, 2, 4 or 8 here
+        float sm = 0.f, qm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i >= g0 && i < g0 + p.cpg) { sm += sq[2 * i]; qm += sq[2 * i + 1]; }
+        mean[i0] = sm * inv_cnt;
+        rstd[i0] = rsqrtf(fmaxf(qm * inv_cnt - mean[i0] * mean[i0], 0.f) + p.eps);
+      }
+    } else {
+      // groups of 16, 24, ... channels: whole 8-channel columns of one source
+      const int g0 = (c / p.cpg) * p.cpg;
+      const float* st = (g0 < p.C0) ? p.st0 + ((size_t)n * p.C0 + g0) * 2 : p.st1 + ((size_t)n * p.C1 + (g0 - p.C0)) * 2;
+      float sm = 0.f, qm = 0.f;
+      for (int i = 0; i < p.cpg; i += 2) {
+        const float4 t = ldg4(st + 2 * i);
+        sm += t.x + t.z; qm += t.y + t.w;
+      }
+      const float m = sm * inv_cnt;
+      const float r = rsqrtf(fmaxf(qm * inv_cnt - m * m, 0.f) + p.eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mean[i] = m; rstd[i] = r; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 ga = p.gamma ? ldg4(p.gamma + c + 4 * h) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 be = p.beta ? ldg4(p.beta + c + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float gv[4] = {ga.x, ga.y, ga.z, ga.w}, bv[4] = {be.x, be.y, be.z, be.w};
+      if (p.scale) {
+        const float4 sc = ldg4(p.scale + (size_t)n * p.ss_ld + c + 4 * h), sh = ldg4(p.shift + (size_t)n * p.ss_ld + c + 4 * h);
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { gv[i] *= 1.f + scv[i]; bv[i] = bv[i] * (1.f + scv[i]) + shv[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[4 * h + i] = rstd[4 * h + i] * gv[i];
+        b[4 * h + i] = bv[i] - mean[4 * h + i] * rstd[4 * h + i] * gv[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = coefA[c + i]; b[i] = coefB[c + i]; }
+  }
+  for (;;) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int q = px + u * pstep;
@@ -389,6 +452,9 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
         *reinterpret_cast<uint4*>(rdst + (size_t)q * C) = ur;
       }
     }
+    px += kU * pstep;
+    if (px >= px1) break;
+    issue(px);
   }
 }
 
@@ -405,6 +471,13 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
   const int bx = p.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int tid = threadIdx.x;
   griddep_sync();
+  if (p.resample == 0 && p.cols8 == 2) {   // per-thread coefficients: no shared-memory prologue
+    const int px0 = bx * p.pix_per_cta;
+    const int px1 = min(p.HW, px0 + p.pix_per_cta);
+    if (p.in_bf16) gn_apply_cols8<true, 4, true>(p, nullptr, nullptr, n, px0, px1, drop_seed);
+    else gn_apply_cols8<false, 2, true>(p, nullptr, nullptr, n, px0, px1, drop_seed);
+    return;
+  }
   for (int c = tid; c < C; c += 256) {
     const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
     chS[c] = __ldg(st);
@@ -436,8 +509,8 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
     const int px0 = bx * p.pix_per_cta;
     const int px1 = min(p.HW, px0 + p.pix_per_cta);
     if (p.resample == 0 && p.cols8) {
-      if (p.in_bf16) gn_apply_cols8<true, 4>(p, coefA, coefB, n, px0, px1, drop_seed);
-      else gn_apply_cols8<false, 2>(p, coefA, coefB, n, px0, px1, drop_seed);
+      if (p.in_bf16) gn_apply_cols8<true, 4, false>(p, coefA, coefB, n, px0, px1, drop_seed);
+      else gn_apply_cols8<false, 2, false>(p, coefA, coefB, n, px0, px1, drop_seed);
       return;
     }
     if (p.resample == 0 && (256 % nv) == 0) {
@@ -616,6 +689,12 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.in_bf16 = x0_is_bf16 ? 1 : 0;
   static const char* env_c8 = getenv("B200_GN_COLS8");
   p.cols8 = (C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= 256 && !(env_c8 && atoi(env_c8) == 0)) ? 1 : 0;
+  {
+    const int cpg = C / groups;
+    const bool own = (cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8) ||
+                     (cpg % 8 == 0 && (C1 == 0 || C0 % cpg == 0));   // a group never straddles the two sources
+    if (p.cols8 && own && !(env_c8 && atoi(env_c8) == 1)) p.cols8 = 2;
+  }
   static const char* env_rev = getenv("B200_L2_REVERSE");
   p.reverse = (env_rev && atoi(env_rev) == 0) ? 0 : 1;
   B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
@@ -628,6 +707,12 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   int ppc = (resample == 1 ? 8192 : x0_is_bf16 ? 65536 : 32768) / C;  // ~128 KB of input per CTA
   if (ppc < 1) ppc = 1;
   if (ppc > work_pix) ppc = work_pix;
+  // small tensors: shrink the per-CTA range (down to ~16 KB of input) until the grid covers the SMs once
+  // (4 resident CTAs per SM), otherwise a few long CTAs leave most of the memory system idle
+  static const char* env_fill = getenv("B200_GN_FILL");
+  const long want = env_fill ? atol(env_fill) : 592;
+  const int ppc_min = (resample == 1 ? 1024 : x0_is_bf16 ? 8192 : 4096) / C > 8 ? (resample == 1 ? 1024 : x0_is_bf16 ? 8192 : 4096) / C : 8;
+  while (ppc > ppc_min && (long)B * ((work_pix + ppc - 1) / ppc) < want) ppc = (ppc + 1) / 2;
   p.pix_per_cta = ppc;
   dim3 grid((work_pix + ppc - 1) / ppc, B);
   B200_CHECK(launch_pdl(groupnorm_apply_kernel, grid, dim3(256), smem, stream, p));

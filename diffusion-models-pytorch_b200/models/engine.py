@@ -50,6 +50,8 @@ class Engine:
         self._pt_scratch: List = []  # single-entry tables of first-use packs (kept alive until the stream consumed them)
         self.tape = None         # training forward: list of records replayed in reverse by models/backward.py
         self.seed_dev = None     # int64 [1] device scalar: base seed of this forward's dropout masks (graph replayable)
+        self.emb_override = None  # [1, total] fp32: precomputed embedding projections of the current timestep (sampling runner)
+        self._embed_args = None   # modules of the last time-only embedding (what embed_rows re-evaluates for a whole schedule)
         self._n_drop = 0
 
     # ------------------------------------------------------------------------------------------
@@ -435,6 +437,10 @@ class Engine:
         # one embedding row serves the whole batch when t is a stride-0 expand (sampling); training keeps per-sample rows
         uniform = (T.dim() == 1 and T.shape[0] == B and (B == 1 or T.stride(0) == 0)) and self.tape is None
         use_y = class_embed is not None and y is not None
+        if uniform and not use_y:
+            if self.emb_override is not None:   # the sampling runner filled this row for the current step
+                return self.emb_override, 0
+            self._embed_args = (pos_emb, lin1, lin2, proj_linears)
         rows = 1 if (uniform and not use_y) else B
         t_rows = (T[:1] if uniform and rows == 1 else T).to(torch.long).contiguous()
         if use_y:
@@ -457,6 +463,23 @@ class Engine:
             self.d_emb = self.buf('d_tproj', (rows, total), torch.float32)
             self.d_emb.zero_()
         return proj, (0 if rows == 1 and self.tape is None else total)
+
+    def embed_rows(self, t_all):
+        """Embedding projections of a whole timestep schedule at once: t_all [S] int64 -> [S, total] fp32, the rows that
+        `embed` would produce one per call (same kernels, rows = S).  The sampling runner evaluates this once per
+        `sample()` instead of a sinusoid + 2-layer MLP + projection GEMM in every one of the S steps."""
+        pos_emb, lin1, lin2, proj_linears = self._embed_args
+        dev = self.device
+        S, E = t_all.numel(), lin1.out_features
+        freqs = self.const(('freqs', str(dev)), lambda: pos_emb.frequencies(dev).float().contiguous())
+        emb = torch.empty((S, E), dtype=torch.float32, device=dev)
+        semb = torch.empty((S, E), dtype=torch.bfloat16, device=dev)
+        K.time_embed(t_all.to(torch.long).contiguous(), freqs, pos_emb.dim, E, bool(getattr(pos_emb, 'cos_first', False)),
+                     lin1.weight, lin1.bias, lin2.weight, lin2.bias, emb, out_silu_bf16=semb)
+        w, b = self.w_tproj(proj_linears)
+        proj = torch.empty((S, w.shape[0]), dtype=torch.float32, device=dev)
+        K.conv2d(semb, w, w.shape[0], S, 1, 1, K.taps_1x1(), a0_geom=(E, 1, 1, 1), bias=b, out=proj)
+        return proj
 
     def first_conv(self, tag, conv: nn.Conv2d, X) -> Act:
         """The Cin <= 4 input convolution (models/unet.py:72,123): NCHW fp32 image -> fp32 NHWC residual stream."""

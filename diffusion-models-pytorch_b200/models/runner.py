@@ -69,9 +69,15 @@ class SamplingRunner:
                 g['kw'][k].copy_(v)
         if cfg and uncond_conditioning is not None:
             g['uncond'].copy_(uncond_conditioning)
+        emb_table = None
+        if g['emb'] is not None:   # embedding projections of the whole schedule in one batched evaluation
+            with torch.no_grad():
+                emb_table = eng.embed_rows(t_table)
         pbar = tqdm.tqdm(total=len(pairs), **tqdm_kwargs)
         for i in range(len(pairs)):
             g['t'].copy_(t_table[i:i + 1])
+            if emb_table is not None:
+                g['emb'].copy_(emb_table[i:i + 1])
             g['coef'].copy_(coef_table[i])
             g['graph'].replay()
             K.GRAPH_LAUNCHES += g['kernels']
@@ -115,10 +121,22 @@ class SamplingRunner:
         with torch.cuda.stream(side), torch.no_grad():
             step()
         torch.cuda.current_stream(dev).wait_stream(side)
+        # models whose embedding depends on the timestep only (no class label): the captured forward reads the
+        # projections of the current step from st['emb'], filled per step from a table computed once per sample()
+        eng = model.engine
+        st['emb'] = None
+        if (not cfg and getattr(eng, '_embed_args', None) is not None and hasattr(eng, 'embed_rows')
+                and all(v is None for v in st['kw'].values())):
+            total = sum(l.out_features for l in eng._embed_args[3])
+            st['emb'] = torch.zeros((1, total), dtype=torch.float32, device=dev)
         graph = torch.cuda.CUDAGraph()
         n0 = K.direct_launch_count()
-        with torch.no_grad(), torch.cuda.graph(graph):
-            step()
+        eng.emb_override = st['emb']
+        try:
+            with torch.no_grad(), torch.cuda.graph(graph):
+                step()
+        finally:
+            eng.emb_override = None
         st['kernels'] = K.direct_launch_count() - n0   # libb200diff kernels captured per timestep
         torch.cuda.set_rng_state(rng, dev)
         st['graph'] = graph

@@ -88,6 +88,99 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
   }
 }
 
+// Persistent variant for W % 4 == 0 (every model family): a CTA keeps its lanes' weights in registers across
+// (image, row block) units; a lane computes 4 consecutive pixels x 4 channels, so each (ci, r) patch row is read as
+// one 16-byte + one 8-byte warp-broadcast shared-memory load feeding 48 FMAs (the 1-pixel form issued one 4-byte
+// load per 4 FMAs and ran at 22 % of the FP32 rate).
+template <int CIN>
+__global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                                   float* __restrict__ stats, int B, int H, int W, int Cout,
+                                                                   int R, int units_per_image, int total_units) {
+  constexpr int K = 9 * CIN;
+  extern __shared__ float fsm[];
+  float* ssm = fsm;               // [2*128] statistics of the current unit's channel group
+  float* patch = fsm + 256;       // [CIN][R+2][PWp], zero padded, rows 16-byte aligned
+  const int PWp = (W + 2 + 3) & ~3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int co = blockIdx.z * 128 + 4 * lane;
+  const bool co_ok = co < Cout;
+  float wr[4][K];
+  float bv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) wr[e][k] = co_ok ? __ldg(w + (size_t)(co + e) * K + k) : 0.f;
+    bv[e] = (co_ok && bias) ? __ldg(bias + co + e) : 0.f;
+  }
+  griddep_sync();
+  const int gpr = W >> 2;   // 4-pixel groups per row
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    const int n = unit / units_per_image;
+    const int h0 = (unit - n * units_per_image) * R;
+    __syncthreads();   // the previous unit's patch and statistics are consumed
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0.f;
+    for (int i = threadIdx.x; i < CIN * (R + 2) * PWp; i += blockDim.x) {
+      const int ci = i / ((R + 2) * PWp);
+      const int rem = i - ci * (R + 2) * PWp;
+      const int py = rem / PWp, pxx = rem - py * PWp;
+      const int yy = h0 + py - 1, xx = pxx - 1;
+      patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)n * CIN + ci) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(R, H - h0);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int g = warp; g < rows * gpr; g += nwarps) {
+      const int ly = g / gpr, lx = (g - ly * gpr) << 2;
+      float acc[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[q][e] = bv[e];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float* pr = patch + (ci * (R + 2) + ly + r) * PWp + lx;
+          const float4 v0 = *reinterpret_cast<const float4*>(pr);
+          const float2 v1 = *reinterpret_cast<const float2*>(pr + 4);
+          const float pv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int k = (ci * 3 + r) * 3 + s;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[q][e] = fmaf(pv[q + s], wr[e][k], acc[q][e]);
+          }
+        }
+      if (co_ok) {
+        const size_t pix = ((size_t)n * H + h0 + ly) * W + lx;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(out + (pix + q) * Cout + co) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { s1[e] += acc[q][e]; s2[e] = fmaf(acc[q][e], acc[q][e], s2[e]); }
+        }
+      }
+    }
+    if (stats) {
+      if (co_ok) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          atomicAdd(ssm + 2 * (4 * lane + e), s1[e]);
+          atomicAdd(ssm + 2 * (4 * lane + e) + 1, s2[e]);
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int ch = blockIdx.z * 128 + (i >> 1);
+        if (ch < Cout) atomicAdd(stats + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32 NHWC -> bf16 NHWC (optionally into 4 parity planes)
 // ------------------------------------------------------------------------------------------------
@@ -96,24 +189,36 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   const int cv = C >> 2;
   const size_t total = (size_t)B * H * W * cv;
   griddep_sync();
-  for (size_t ii = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ii < total; ii += (size_t)gridDim.x * blockDim.x) {
-    // reverse: start from the end of the tensor, where the producer's most recent writes are still in L2
-    const size_t i = reverse ? total - 1 - ii : ii;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-    uint2 u;
-    u.x = pack_bf16x2(v.x, v.y);
-    u.y = pack_bf16x2(v.z, v.w);
-    size_t o = i;
-    if (parity) {
-      const int c4 = (int)(i % cv);
-      const size_t pix = i / cv;
-      const int wq = (int)(pix % W);
-      const int h = (int)((pix / W) % H);
-      const int n = (int)(pix / ((size_t)W * H));
-      const int pl = ((h & 1) << 1) | (wq & 1);
-      o = ((((size_t)n * 4 + pl) * (H >> 1) + (h >> 1)) * (W >> 1) + (wq >> 1)) * cv + c4;
+  // 4 independent 16-byte loads in flight per thread (one load per thread left most of the HBM latency exposed)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t ii = i0 + u * stride;
+      // reverse: start from the end of the tensor, where the producer's most recent writes are still in L2
+      if (ii < total) v[u] = __ldg(reinterpret_cast<const float4*>(x) + (reverse ? total - 1 - ii : ii));
     }
-    reinterpret_cast<uint2*>(out)[o] = u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t ii = i0 + u * stride;
+      if (ii >= total) break;
+      const size_t i = reverse ? total - 1 - ii : ii;
+      uint2 w2;
+      w2.x = pack_bf16x2(v[u].x, v[u].y);
+      w2.y = pack_bf16x2(v[u].z, v[u].w);
+      size_t o = i;
+      if (parity) {
+        const int c4 = (int)(i % cv);
+        const size_t pix = i / cv;
+        const int wq = (int)(pix % W);
+        const int h = (int)((pix / W) % H);
+        const int n = (int)(pix / ((size_t)W * H));
+        const int pl = ((h & 1) << 1) | (wq & 1);
+        o = ((((size_t)n * 4 + pl) * (H >> 1) + (h >> 1)) * (W >> 1) + (wq >> 1)) * cv + c4;
+      }
+      reinterpret_cast<uint2*>(out)[o] = w2;
+    }
   }
 }
 
@@ -243,6 +348,30 @@ using namespace b200;
 template <int CIN>
 static int launch_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B, int H,
                         int W, int Cout, cudaStream_t stream) {
+  static const char* env_v = getenv("B200_FIRST_PX4");
+  if (W % 4 == 0 && !(env_v && atoi(env_v) == 0)) {
+    int R = 8;
+    if (R > H) R = H;
+    const int PWp = (W + 2 + 3) & ~3;
+    const size_t smem = (256 + (size_t)CIN * (R + 2) * PWp) * 4;
+    B200_REQUIRE(smem <= 100 * 1024, "conv3x3_first: input patch does not fit in shared memory (W=%d)", W);
+    static bool attr4 = false;
+    static int sms = 0;
+    if (!attr4) {
+      int dev = 0;
+      B200_CHECK(cudaGetDevice(&dev));
+      B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      B200_CHECK(cudaFuncSetAttribute(conv3x3_first_px4_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr4 = true;
+    }
+    const int upi = (H + R - 1) / R;
+    const int total = upi * B;
+    dim3 grid(total < sms ? total : sms, 1, (Cout + 127) / 128);
+    B200_CHECK(launch_pdl(conv3x3_first_px4_kernel<CIN>, grid, dim3(256), smem, stream, x, w, bias, out, stats, B, H, W, Cout,
+                          R, upi, total));
+    ++g_launch_count;
+    return 0;
+  }
   // rows per CTA: enough pixels per warp (R * W / 8) to amortise the per-lane weight fetch (108 floats for Cin = 3)
   static const char* env_r = getenv("B200_FIRST_ROWS");
   int R = env_r ? atoi(env_r) : 32;

@@ -6,10 +6,11 @@
 //     The tap shift and the zero padding are, as in the forward kernel, the TMA box origin and its out-of-bounds fill.
 //   * the batched matrix products of the attention backward and of the embedding-projection backward
 //     (b200_gemm_batched), in all four major combinations (A K-major / MN-major x B K-major / MN-major).
-// Tile: 128 (M) x BN <= 256 (N) fp32 accumulators in TMEM, K-blocks of 64, 4-stage TMA ring, split-K with fp32
+// Tile: 128 (M) x BN <= 256 (N) fp32 accumulators in TMEM, K-blocks of 64, TMA ring as deep as shared memory allows, split-K with fp32
 // atomics.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (one TMEM lane quarter each).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/b200diff.h"
 
 namespace b200 {
@@ -26,7 +27,8 @@ struct GemmKParams {
   GemmOperandK a, b;
   int conv;                          // 1: K-blocks are pixel tiles of a convolution (wgrad)
   int BN;                            // N tile
-  int m_tiles, n_tiles, groups, heads, ksplit, kblocks;
+  int m_tiles, n_tiles, groups, heads, ksplit, kblocks, stages, k_rotate;
+  int kpx;                           // K extent of one stage: 64, or 128 pixels in conv mode (half as many TMA operations per byte)
   int M, N;                          // valid extents (masking in the epilogue)
   // conv mode: pixel tile = bw x bh x bn = 64 pixels, g = tap
   int bw, bh, bn, tiles_w, tiles_h;
@@ -39,10 +41,10 @@ struct GemmKParams {
 };
 
 constexpr int kGemmThreads = 192;
-constexpr int kGemmStages = 4;
+constexpr int kGemmMaxStages = 8;   // ring depth = as many (16 KB + BN x 128 B) stages as fit in shared memory
 
 struct __align__(8) GemmBars {
-  uint64_t full[kGemmStages], empty[kGemmStages], acc_full;
+  uint64_t full[kGemmMaxStages], empty[kGemmMaxStages], acc_full;
   uint32_t tmem_base;
 };
 
@@ -64,9 +66,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  const int b_bytes = p.BN * 128;
-  const int stage_bytes = 16384 + b_bytes;
-  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)kGemmStages * stage_bytes);
+  const int chunk_bytes = p.kpx * 128;                  // one 64-channel slab of kpx K-rows
+  const int a_bytes = 2 * chunk_bytes;
+  const int stage_bytes = a_bytes + p.BN * p.kpx * 2;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)p.stages * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // tile decode: blockIdx.x = ((g * ksplit + ks) * m_tiles + mt) * n_tiles + nt
@@ -88,7 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tma_prefetch_desc(&mapB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kGemmStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
@@ -109,10 +112,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int ba = gb * p.a.b_mul + gh * p.a.h_mul, bb = gb * p.b.b_mul + gh * p.b.h_mul;
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        // conv mode: the CTAs of the 9 taps of one pixel range would otherwise request the same dY / activation lines
+        // from L2 at the same moment; each tap starts at a different K-block of the range (the sum is order-free)
+        const int rot = (p.conv && p.k_rotate) ? (int)(((long)g * nkb) / p.groups) : 0;
+        for (int kbi = 0; kbi < nkb; ++kbi) {
+          int kb = kb0 + kbi + rot;
+          if (kb >= kb1) kb -= nkb;
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
-          uint8_t* sB = sA + 16384;
+          uint8_t* sB = sA + a_bytes;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
           if (p.conv) {
             // K-block = pixel tile (tw, th, tn); A = dY (unshifted), B = activation shifted by the tap g
@@ -121,9 +129,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int tn = kb / (p.tiles_w * p.tiles_h);
             const int w0 = tw * p.bw, h0 = th * p.bh, i0 = tn * p.bn;
             for (int c = 0; c < 2; ++c)
-              tma_load_5d(sA + c * 8192, &mapA, &bars->full[stage], ca + m0 + c * 64, w0, h0, 0, i0);
+              tma_load_5d(sA + c * chunk_bytes, &mapA, &bars->full[stage], ca + m0 + c * 64, w0, h0, 0, i0);
             for (int c = 0; c < p.BN / 64; ++c)
-              tma_load_5d(sB + c * 8192, &mapB, &bars->full[stage], cb + n0 + c * 64, w0 + p.taps[g][0],
+              tma_load_5d(sB + c * chunk_bytes, &mapB, &bars->full[stage], cb + n0 + c * 64, w0 + p.taps[g][0],
                           h0 + p.taps[g][1], p.taps[g][2], i0);
           } else {
             const int k0 = kb * 64;
@@ -140,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               tma_load_5d(sB, &mapB, &bars->full[stage], cb + k0, n0, 0, 0, bb);
             }
           }
-          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     } else if (warp == 1) {
@@ -154,17 +162,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + 16384;
-          const uint64_t adesc = p.a.mn_major ? umma_desc_mnmajor_sw128(a_addr, 8192) : umma_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = p.b.mn_major ? umma_desc_mnmajor_sw128(b_addr, 8192) : umma_desc_kmajor_sw128(b_addr);
+          const uint32_t b_addr = a_addr + (uint32_t)a_bytes;
+          const uint64_t adesc = p.a.mn_major ? umma_desc_mnmajor_sw128(a_addr, (uint32_t)chunk_bytes) : umma_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = p.b.mn_major ? umma_desc_mnmajor_sw128(b_addr, (uint32_t)chunk_bytes) : umma_desc_kmajor_sw128(b_addr);
           // 16 k per instruction: K-major advances 32 B inside the swizzle row, MN-major advances 16 rows = 2048 B
           const uint64_t astep = p.a.mn_major ? 128u : 2u;
           const uint64_t bstep = p.b.mn_major ? 128u : 2u;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
+          const int ksteps = p.kpx >> 4;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k)
             umma_bf16(tmem_d, adesc + astep * (uint64_t)k, bdesc + bstep * (uint64_t)k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&bars->empty[stage]);
-          if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&bars->acc_full);
       }
@@ -231,13 +240,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& p_in, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     B200_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  const size_t smem = (size_t)kGemmStages * (16384 + p.BN * 128) + sizeof(GemmBars) + 1024;
+  GemmKParams p = p_in;
+  // as many stages as fit: with 4 stages of 32 KB (BN = 128) only 128 KB were in flight and the K loop ran at the
+  // TMA round-trip latency, not at the tensor-core rate
+  static const char* env_st = getenv("B200_GEMM_STAGES");
+  if (p.kpx == 0) p.kpx = 64;
+  const int stage_bytes = 2 * p.kpx * 128 + p.BN * p.kpx * 2;
+  int stages = 4;   // measured: deeper rings (up to 7 x 32 KB) are not faster -- the K loop is not latency-bound
+  const int fit = (int)((227 * 1024 - 2048 - sizeof(GemmBars)) / stage_bytes);
+  if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+  if (env_st && atoi(env_st) >= 2) stages = atoi(env_st);
+  if (stages > fit) stages = fit;
+  p.stages = stages;
+  static const char* env_rot = getenv("B200_WGRAD_ROTATE");
+  p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBars) + 1024;
   const long long grid = (long long)p.groups * p.ksplit * p.m_tiles * p.n_tiles;
   B200_REQUIRE(grid >= 1 && grid < (1ll << 31), "gemm: bad grid %lld", grid);
   gemm_tc_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(mapA, mapB, p);
@@ -347,18 +370,34 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   B200_REQUIRE(d->Cout >= 1 && d->dy_c0 >= 0 && d->dy_c0 + d->Cout <= d->dy_C && d->Cin >= 1 && d->Cin <= d->x_C, "conv2d_wgrad: bad Cout/Cin");
   B200_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "conv2d_wgrad: ntaps=%d out of range", d->ntaps);
   B200_REQUIRE(((uintptr_t)d->dy & 127) == 0 && ((uintptr_t)d->x & 127) == 0, "conv2d_wgrad: operand alignment");
+  // K-block = kpx pixels per stage: 128 when the tensor has enough pixels for every CTA (one TMA operation then
+  // brings 16 KB instead of 8 KB: the 64-pixel form was bound by the TMA operation rate), else 64
+  static const char* env_kpx = getenv("B200_WGRAD_KPX");
+  int kpx = env_kpx ? atoi(env_kpx) : 128;
+  if (kpx != 128 || (long)d->B * d->Ho * d->Wo < 4096) kpx = 64;   // (N tiles wider than 128 then run on 2 stages)
   int bw = 1;
-  while (bw * 2 <= 64 && d->Wo % (bw * 2) == 0) bw *= 2;
+  while (bw * 2 <= kpx && d->Wo % (bw * 2) == 0) bw *= 2;
   int bh = 1;
-  while (bw * bh * 2 <= 64 && d->Ho % (bh * 2) == 0) bh *= 2;
-  const int bn = 64 / (bw * bh);
+  while (bw * bh * 2 <= kpx && d->Ho % (bh * 2) == 0) bh *= 2;
+  int bn = kpx / (bw * bh);
+  if (!(bn == 1 || (bw == d->Wo && bh == d->Ho)) && kpx == 128) {   // fall back to 64-pixel blocks
+    kpx = 64;
+    bw = 1;
+    while (bw * 2 <= kpx && d->Wo % (bw * 2) == 0) bw *= 2;
+    bh = 1;
+    while (bw * bh * 2 <= kpx && d->Ho % (bh * 2) == 0) bh *= 2;
+    bn = kpx / (bw * bh);
+  }
   B200_REQUIRE(bn == 1 || (bw == d->Wo && bh == d->Ho), "conv2d_wgrad: unsupported spatial size %dx%d", d->Ho, d->Wo);
   GemmKParams p;
   memset(&p, 0, sizeof(p));
+  p.kpx = kpx;
   p.conv = 1;
   p.a.mn_major = 1; p.b.mn_major = 1;
   p.a.c_base = d->dy_c0; p.b.c_base = d->x_c0;
-  int BN = ((d->Cin + 63) / 64) * 64;
+  // N tile: Cin split evenly over ceil(Cin / 256) tiles (384 -> 2 x 192, not 256 + a half-empty 128)
+  const int n_split = (d->Cin + 255) / 256;
+  int BN = (((d->Cin + n_split - 1) / n_split + 63) / 64) * 64;
   if (BN > 256) BN = 256;
   p.BN = BN;
   p.m_tiles = (d->Cout + 127) / 128;
@@ -372,8 +411,11 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   memcpy(p.taps, d->taps, sizeof(p.taps));
   p.alpha = 1.f;
   // split the pixel range so that the grid fills the machine (one wave of CTAs)
+  // (one CTA per SM: rounding the split count UP gave e.g. 9 taps x 17 splits = 153 CTAs on 148 SMs, i.e. a second
+  // wave of 5 CTAs that doubled the kernel's duration; round DOWN so that the grid never exceeds the SM count)
   const long tiles = (long)p.groups * p.m_tiles * p.n_tiles;
-  long ks = (num_sms() + tiles - 1) / tiles;
+  static const char* env_up = getenv("B200_WGRAD_SPLIT_UP");
+  long ks = (env_up && atoi(env_up) == 1) ? (num_sms() + tiles - 1) / tiles : num_sms() / tiles;
   if (ks > p.kblocks) ks = p.kblocks;
   if (ks < 1) ks = 1;
   {   // no empty split: the kernel gives every split ceil(kblocks / ksplit) K-blocks

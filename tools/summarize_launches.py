@@ -17,7 +17,7 @@ for r in csv.DictReader(lines):
     unit = r['Metric Unit']
     us = v / 1000.0 if unit in ('ns', 'nsecond') else v if unit in ('us', 'usecond') else v * 1000.0
     name = r['Kernel Name']
-    short = name.split('(')[0].split('<')[0].split('::')[-1]
+    short = name.split('(')[0].split('<')[0].split('::')[-1].replace('void ', '').strip()
     rows.append((int(r['ID']), short, us, r['Grid Size'], r['Block Size']))
 rows = rows[skip:skip + count]
 tot = sum(r[2] for r in rows)

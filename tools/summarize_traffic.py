@@ -17,7 +17,7 @@ for r in csv.DictReader(lines):
     i = int(r['ID'])
     if i not in per:
         order.append(i)
-    name = r['Kernel Name'].split('(')[0].split('<')[0].split('::')[-1]
+    name = r['Kernel Name'].split('(')[0].split('<')[0].split('::')[-1].replace('void ', '').strip()
     v = float(r['Metric Value'].replace(',', ''))
     u = r['Metric Unit']
     if r['Metric Name'].startswith('dram__bytes'):

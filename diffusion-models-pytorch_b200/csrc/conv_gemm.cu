@@ -80,8 +80,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sW = smem + (size_t)stage * stage_bytes;
           uint8_t* sP = sW + kWBytes;
-          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-          if (kb < p.nkb0) {
+          // experiment knob (B200_EPI_DBG bits 8 / 16): leave out the weight / pixel operand load (timing only)
+          const bool skip_w = (p.dbg & 8) != 0, skip_p = (p.dbg & 16) != 0;
+          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)((skip_w ? 0 : kWBytes) + (skip_p ? 0 : px_bytes)));
+          if (skip_p) {
+          } else if (kb < p.nkb0) {
             const int tap = kb / p.cpb0;
             const int c0 = (kb - tap * p.cpb0) * kBlockK;
             tma_load_5d(sP, &mapA0, &bars->full[stage], c0, t.w0 + p.taps0[t.ph][tap][0],
@@ -90,7 +93,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const int c0 = (kb - p.nkb0) * kBlockK;
             tma_load_5d(sP, &mapA1, &bars->full[stage], c0, t.w0 + p.tap1[0], t.h0 + p.tap1[1], p.tap1[2], t.n0);
           }
-          tma_load_2d(sW, &mapW, &bars->full[stage], kb * kBlockK, wrow);
+          if (!skip_w) tma_load_2d(sW, &mapW, &bars->full[stage], kb * kBlockK, wrow);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }

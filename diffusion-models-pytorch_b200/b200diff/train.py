@@ -7,7 +7,7 @@ scripts/train_ddpm.py:171-192 / train_ddpm_cfg.py:172-196:
 with the last three fused into b200_optimizer_step, and no host synchronisation anywhere (the loss is returned as a
 device scalar; call `.item()` on it only when it is logged).
 
-`use_cuda_graph=True` (single-GPU, FusedAdam(capturable=True)): after two eager warm-up steps the whole step -- timestep and
+`use_cuda_graph=True` (FusedAdam(capturable=True); with world_size > 1 the gradient all-reduce is captured too): after two eager warm-up steps the whole step -- timestep and
 noise draws, diffuse, UNet forward with fresh dropout masks, MSE, every backward kernel, clip + Adam + EMA, and the bf16
 re-pack of the weights -- is captured once per (batch shape, conditional / unconditional) and replayed: the ~830
 kernel launches of a step then cost one graph launch on the host instead of ~25 ms of Python.
@@ -62,7 +62,10 @@ class TrainStep:
         if y is not None and self.p_uncond > 0 and float(torch.rand(())) < self.p_uncond:
             y = None       # classifier-free guidance training: the whole batch is unconditional with probability p_uncond
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        graphable = (self.use_cuda_graph and world == 1 and t is None and eps is None
+        # data-parallel runs capture the NCCL all-reduce of the flat gradient buffer inside the same graph
+        # (B200_TRAIN_GRAPH_DDP=0 falls back to eager launches when world > 1)
+        ddp_ok = world == 1 or __import__('os').environ.get('B200_TRAIN_GRAPH_DDP', '1') != '0'
+        graphable = (self.use_cuda_graph and ddp_ok and t is None and eps is None
                      and (micro_batch is None or micro_batch >= x0.shape[0]))
         if not graphable:
             return self._body(x0, t, y, eps, micro_batch)
@@ -84,6 +87,12 @@ class TrainStep:
         K.GRAPH_LAUNCHES += g['kernels']
         self.optimizer.mirror_replayed_step(self.ema)
         return g['loss'].clone()
+
+    def close(self):
+        """Drops the captured graphs.  Call it (then `torch.cuda.synchronize()`) before `dist.destroy_process_group()`:
+        graphs that captured NCCL kernels must not outlive the communicator."""
+        self._graphs.clear()
+        self._warm.clear()
 
     def warmup(self, x0, y=None):
         """Runs (and, in CUDA-graph mode, captures) every variant of the step once: conditional and -- when labels may be
@@ -107,7 +116,9 @@ class TrainStep:
         n0 = K.direct_launch_count()
         # the host-side counters advance once here (capture executes the Python body once); the captured kernels are
         # not executed during capture, so undo that bookkeeping afterwards
-        with torch.cuda.graph(graph):
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # thread-local capture mode: the NCCL watchdog thread of torch.distributed keeps querying events while we capture
+        with torch.cuda.graph(graph, capture_error_mode='thread_local' if world > 1 else 'global'):
             st['loss'] = self._body(st['x0'], None, st['y'], None, None)
         params = [p for g_ in self.optimizer.param_groups for p in g_['params'] if p.grad is not None]
         for p in params:

@@ -92,7 +92,13 @@ def main():
                             **({'gbs': v['bytes'] / (v['ms'] * 1e-3) / 1e9} if v['bytes'] else {})}
                         for k, v in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])}}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL kernels must be released before the communicator goes away; a process that still
+        # hangs in teardown is ended hard (the measurement is already printed)
+        step.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -170,6 +170,66 @@ __device__ __forceinline__ void gn_bwd_dz(const GnBwdParams& p, int n, int px, i
   }
 }
 
+
+// dz / xh of 4 channels from already fetched operands and an already drawn keep mask (the hot loops below step
+// pointers and the dropout counter instead of re-deriving 64-bit addresses per pixel)
+__device__ __forceinline__ void gn_bwd_dz_core(const float4 x, const float4 g, const float4 a, const float4 b,
+                                               const float4 ra, const float4 rb, const uint32_t keep, const bool silu,
+                                               const bool drop, const float drop_scale, float (&dz)[4], float (&xh)[4]) {
+  const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g.x, g.y, g.z, g.w};
+  const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  const float rav[4] = {ra.x, ra.y, ra.z, ra.w}, rbv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xh[i] = fmaf(xv[i], rav[i], rbv[i]);
+    float d = gv[i];
+    if (silu) d *= silu_grad(fmaf(xv[i], av[i], bv[i]));
+    if (drop) d = ((keep >> i) & 1u) ? d * drop_scale : 0.f;
+    dz[i] = d;
+  }
+}
+
+// no-resampling columns (every ResBlock GroupNorm except the up/down ones; concatenated inputs included).
+// One 32-bit element offset is stepped (the launcher takes this path only for tensors below 2^32 elements); the
+// base pointers stay in the constant bank and the dropout counter is offset >> 2.
+template <bool kCat>
+__device__ __forceinline__ void gn_bwd_reduce_simple(const GnBwdParams& p, const int n, const int c, const int prow,
+                                                     const int pstep, const int px0, const int px1, const float4 a,
+                                                     const float4 b, const float4 ra, const float4 rb, float (&s1)[4],
+                                                     float (&s2)[4]) {
+  const int C = p.C0 + (kCat ? p.C1 : 0);
+  const bool from0 = !kCat || c < p.C0;
+  const float* xsrc = from0 ? p.x0 : p.x1;          // concatenated inputs: the column lives in one of the two sources
+  const uint32_t sld = from0 ? p.C0 : p.C1, sc = from0 ? c : c - p.C0;
+  const uint32_t pix = (uint32_t)n * (uint32_t)p.HW + (uint32_t)(px0 + prow);
+  uint32_t off = pix * (uint32_t)C + (uint32_t)c, xoff = kCat ? pix * sld + sc : 0u;
+  const uint32_t step = (uint32_t)pstep * (uint32_t)C, xstep = kCat ? (uint32_t)pstep * sld : 0u;
+  const bool drop = p.drop_thresh != 0, silu = p.apply_silu != 0;
+  const unsigned long long seed = p.drop_seed + ((drop && p.drop_seed_dev) ? __ldg(p.drop_seed_dev) : 0ull);
+  for (int px = px0 + prow; px < px1; px += 4 * pstep, off += 4 * step, xoff += 4 * xstep) {
+    float4 xs[4];
+    uint2 gs[4];       // bf16 x 4, unpacked when consumed (register budget)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (px + u * pstep < px1) {
+        xs[u] = kCat ? bw_ldg4(xsrc + (size_t)(xoff + u * xstep)) : bw_ldg4(p.x0 + (size_t)(off + u * step));
+        gs[u] = __ldg(reinterpret_cast<const uint2*>(p.g + (size_t)(off + u * step)));
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (px + u * pstep >= px1) break;
+      const uint32_t keep = drop ? dropout_keep4(seed, (unsigned long long)((off + u * step) >> 2), p.drop_thresh) : 15u;
+      float dz[4], xh[4];
+      const float4 g4 = make_float4(__uint_as_float(gs[u].x << 16), __uint_as_float(gs[u].x & 0xffff0000u),
+                                    __uint_as_float(gs[u].y << 16), __uint_as_float(gs[u].y & 0xffff0000u));
+      gn_bwd_dz_core(xs[u], g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+    }
+  }
+}
+
+template <int kMode>   // 0 general (resampling), 1 single source, 2 concatenated sources
 __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
@@ -191,6 +251,9 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams
     const float4 a = bw_ldg4(cA + c), b = bw_ldg4(cB + c);
     const float4 ra = bw_ldg4(rA + c), rb = bw_ldg4(rB + c);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kMode == 1) gn_bwd_reduce_simple<false>(p, n, c, prow, pstep, px0, px1, a, b, ra, rb, s1, s2);
+    else if (kMode == 2) gn_bwd_reduce_simple<true>(p, n, c, prow, pstep, px0, px1, a, b, ra, rb, s1, s2);
+    else
     for (int px = px0 + prow; px < px1; px += 4 * pstep) {
       float4 xs[4], gs[4];
 #pragma unroll
@@ -221,6 +284,71 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(const GnBwdParams
   }
 }
 
+
+// pass 2 for single-source, no-resampling columns: dx = dz*cA - k2 - xh*k3 (+ addend), bf16 or fp32 (optionally
+// accumulating) output, per-thread row sums of dx; pointers and the dropout counter are stepped, not re-derived
+constexpr int kUA = 2;   // pixels in flight per thread in the apply pass (4 spill at 64 registers)
+// pass 2 for single-source, no-resampling columns: dx = dz*cA - k2 - xh*k3 (+ addend), bf16 or fp32 (optionally
+// accumulating) output, per-thread row sums of dx; same 32-bit offset stepping as the reduce pass
+template <bool kCat>
+__device__ __forceinline__ void gn_bwd_apply_simple(const GnBwdParams& p, const int n, const int c, const int prow,
+                                                    const int pstep, const int px0, const int px1, const float4 a,
+                                                    const float4 b, const float4 ra, const float4 rb, const float4 q2,
+                                                    const float4 q3, float (&rs)[4]) {
+  const int C = p.C0 + (kCat ? p.C1 : 0);
+  const bool from0 = !kCat || c < p.C0;
+  const float* xsrc = from0 ? p.x0 : p.x1;
+  float* dst = from0 ? p.dx0 : p.dx1;
+  const uint32_t sld = from0 ? p.C0 : p.C1, sc = from0 ? c : c - p.C0;
+  const uint32_t pix = (uint32_t)n * (uint32_t)p.HW + (uint32_t)(px0 + prow);
+  uint32_t off = pix * (uint32_t)C + (uint32_t)c, xoff = kCat ? pix * sld + sc : 0u;
+  const uint32_t step = (uint32_t)pstep * (uint32_t)C, xstep = kCat ? (uint32_t)pstep * sld : 0u;
+  const bool acc = (from0 ? p.acc0 : p.acc1) != 0;
+  const bool drop = p.drop_thresh != 0, silu = p.apply_silu != 0;
+  const unsigned long long seed = p.drop_seed + ((drop && p.drop_seed_dev) ? __ldg(p.drop_seed_dev) : 0ull);
+  const float av[4] = {a.x, a.y, a.z, a.w}, q2v[4] = {q2.x, q2.y, q2.z, q2.w}, q3v[4] = {q3.x, q3.y, q3.z, q3.w};
+  for (int px = px0 + prow; px < px1; px += kUA * pstep, off += kUA * step, xoff += kUA * xstep) {
+    float4 xs[kUA], ads[kUA];
+    uint2 gs[kUA];
+#pragma unroll
+    for (int u = 0; u < kUA; ++u)
+      if (px + u * pstep < px1) {
+        xs[u] = kCat ? bw_ldg4(xsrc + (size_t)(xoff + u * xstep)) : bw_ldg4(p.x0 + (size_t)(off + u * step));
+        gs[u] = __ldg(reinterpret_cast<const uint2*>(p.g + (size_t)(off + u * step)));
+        if (p.addend) ads[u] = bw_ldg4(p.addend + (size_t)(off + u * step));
+      }
+#pragma unroll
+    for (int u = 0; u < kUA; ++u) {
+      if (px + u * pstep >= px1) break;
+      const size_t o = (size_t)(off + u * step);
+      const uint32_t keep = drop ? dropout_keep4(seed, (unsigned long long)((off + u * step) >> 2), p.drop_thresh) : 15u;
+      float dz[4], xh[4], dx[4];
+      const float4 g4 = make_float4(__uint_as_float(gs[u].x << 16), __uint_as_float(gs[u].x & 0xffff0000u),
+                                    __uint_as_float(gs[u].y << 16), __uint_as_float(gs[u].y & 0xffff0000u));
+      gn_bwd_dz_core(xs[u], g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dx[i] = fmaf(dz[i], av[i], -q2v[i]) - xh[i] * q3v[i];
+      if (p.addend) { dx[0] += ads[u].x; dx[1] += ads[u].y; dx[2] += ads[u].z; dx[3] += ads[u].w; }
+      if (p.dx_bf16) {
+        uint2 u2;
+        u2.x = pack_bf16x2(dx[0], dx[1]);
+        u2.y = pack_bf16x2(dx[2], dx[3]);
+        *reinterpret_cast<uint2*>(p.dx_bf16 + o) = u2;
+      } else if (kCat ? dst != nullptr : p.dx0 != nullptr) {
+        float4* op = reinterpret_cast<float4*>(kCat ? dst + (size_t)(xoff + u * xstep) : p.dx0 + o);
+        if (acc) {
+          const float4 old = *op;
+          dx[0] += old.x; dx[1] += old.y; dx[2] += old.z; dx[3] += old.w;
+        }
+        *op = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rs[i] += dx[i];
+    }
+  }
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams p) {
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
@@ -251,6 +379,9 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
     const int dld = from0 ? p.C0 : p.C1, dc = from0 ? c : c - p.C0;
     const int acc = from0 ? p.acc0 : p.acc1;
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kMode == 1) gn_bwd_apply_simple<false>(p, n, c, prow, pstep, px0, px1, a, b, ra, rb, q2, q3, rs);
+    else if (kMode == 2) gn_bwd_apply_simple<true>(p, n, c, prow, pstep, px0, px1, a, b, ra, rb, q2, q3, rs);
+    else
     for (int pxb = px0 + prow; pxb < px1; pxb += 2 * pstep) {
       float4 xs[2], gs[2], ads[2];
 #pragma unroll
@@ -639,15 +770,24 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   dim3 grid((d->HW + ppc - 1) / ppc, d->B);
   static bool attr = false;
   if (!attr) {
-    B200_CHECK(cudaFuncSetAttribute(gn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_reduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
   gn_bwd_coef_kernel<<<d->B, 256, (size_t)2 * C * 4, stream>>>(p);
-  gn_bwd_reduce_kernel<<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
+  const int mode = (p.resample == 0 && (unsigned long long)d->B * d->HW * C < (1ull << 32)) ? (p.C1 == 0 ? 1 : 2) : 0;
+  if (mode == 1) gn_bwd_reduce_kernel<1><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
+  else if (mode == 2) gn_bwd_reduce_kernel<2><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
+  else gn_bwd_reduce_kernel<0><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
   gn_bwd_final_kernel<<<d->B, 256, 0, stream>>>(p);
   B200_CHECK(cudaGetLastError());
-  gn_bwd_apply_kernel<<<grid, 256, (size_t)C * 4, stream>>>(p);
+  if (mode == 1) gn_bwd_apply_kernel<1><<<grid, 256, (size_t)C * 4, stream>>>(p);
+  else if (mode == 2) gn_bwd_apply_kernel<2><<<grid, 256, (size_t)C * 4, stream>>>(p);
+  else gn_bwd_apply_kernel<0><<<grid, 256, (size_t)C * 4, stream>>>(p);
   g_launch_count += 4;
   return check_cuda(cudaGetLastError(), "gn_bwd kernels launch");
 }

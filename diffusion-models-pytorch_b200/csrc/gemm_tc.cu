@@ -273,16 +273,26 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            int splits, int ntaps, int Cout, int Cin, long long s_co,
                                                            long long s_ci, long long s_tap) {
+  // a thread owns one (co, ci) and writes its ntaps consecutive outputs (a tap-parallel grid was measured 1.4-2x
+  // slower: nine CTAs then read-modify-write interleaved 4-byte words of the same sectors); the splits of a tap are
+  // fetched 4 at a time into independent accumulators
   const long long per_tap = (long long)Cout * Cin;
   const long long per_split = per_tap * ntaps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_tap; i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i / Cin), ci = (int)(i - (long long)co * Cin);
     float* o = dw + co * s_co + ci * s_ci;
     for (int t = 0; t < ntaps; ++t) {
-      float acc = 0.f;
       const float* src = scratch + (long long)t * per_tap + i;
-      for (int sp = 0; sp < splits; ++sp) acc += __ldg(src + (long long)sp * per_split);
-      o[t * s_tap] += acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int sp = 0;
+      for (; sp + 4 <= splits; sp += 4) {
+        a0 += __ldg(src + (long long)sp * per_split);
+        a1 += __ldg(src + (long long)(sp + 1) * per_split);
+        a2 += __ldg(src + (long long)(sp + 2) * per_split);
+        a3 += __ldg(src + (long long)(sp + 3) * per_split);
+      }
+      for (; sp < splits; ++sp) a0 += __ldg(src + (long long)sp * per_split);
+      o[t * s_tap] += (a0 + a1) + (a2 + a3);
     }
   }
 }
@@ -446,7 +456,7 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   if (rc) return rc;
   rc = launch_gemm(mapA, mapB, p, stream);
   if (rc || !two_phase) return rc;
-  const long long per_tap = (long long)d->Cout * d->Cin;
+  const long long per_tap = (long long)d->Cout * d->Cin;   // Cin % 64 == 0: multiple of 4, 16-byte aligned partials
   long long g = (per_tap + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
   wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(reinterpret_cast<const float*>(d->scratch), d->dw, p.ksplit, d->ntaps,

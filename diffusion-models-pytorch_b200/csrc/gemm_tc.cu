@@ -240,6 +240,154 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+// ================================================================================================
+// 3x3 stride-1 weight gradient with VERTICAL TAP FUSION: a CTA owns one horizontal tap offset dx and accumulates the
+// three taps dy = -1, 0, +1 in three TMEM accumulators.  Per K-block (bw x bh pixels of one image) it loads the dY
+// tile once and ONE activation tile with a one-row halo above and below ((bh + 2) x bw pixels, TMA zero fill = the
+// conv padding); the three taps are three UMMA views of that tile whose start addresses differ by dy * bw rows of
+// 128 B -- a multiple of the 1024-byte swizzle repeat for bw >= 8, so plain descriptor offsets suffice.
+// 4 TMA operations then feed 3x the tensor-core work of the tap-per-CTA form, which was bound by the TMA operation rate.
+// ================================================================================================
+struct Wgrad3Params {
+  int BN;                        // ci tile (<= 128), multiple of 64
+  int m_tiles, n_tiles, ksplit, kblocks, stages;
+  int bw, bh, tiles_w, tiles_h;  // K-block = bw x bh pixels of one image
+  int dy_c0, x_c0, M, N;
+  float* out;                    // partials [split][tap = (dy+1)*3 + (dx+1)][co][ci]
+  long long s_split, s_tap;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wgrad3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const __grid_constant__ Wgrad3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int kp = p.bw * p.bh;                          // pixels per K-block
+  const int a_slab = kp * 128;                         // dY: [kp rows][128 B] per 64-channel slab
+  const int b_slab = (p.bh + 2) * p.bw * 128;          // activation with halo rows
+  const int a_bytes = 2 * a_slab;
+  const int stage_bytes = a_bytes + (p.BN / 64) * b_slab;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)p.stages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // blockIdx.x = ((dxi * ksplit + ks) * m_tiles + mt) * n_tiles + nt
+  int idx = blockIdx.x;
+  const int nt = idx % p.n_tiles; idx /= p.n_tiles;
+  const int mt = idx % p.m_tiles; idx /= p.m_tiles;
+  const int ks = idx % p.ksplit;
+  const int dxi = idx / p.ksplit;                      // 0..2  ->  dx = dxi - 1
+  const int per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  const int kb0 = ks * per;
+  const int kb1 = min(p.kblocks, kb0 + per);
+  const int nkb = kb1 - kb0;
+  const uint32_t tmem_cols = 512;                      // 3 accumulators of BN <= 128 columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars->tmem_base;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int m0 = mt * 128, n0 = nt * p.BN;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          uint8_t* sA = smem + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + a_bytes;
+          mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int tn = kb / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.bw, h0 = th * p.bh;
+          for (int c = 0; c < 2; ++c)
+            tma_load_5d(sA + c * a_slab, &mapA, &bars->full[stage], p.dy_c0 + m0 + c * 64, w0, h0, 0, tn);
+          for (int c = 0; c < p.BN / 64; ++c)
+            tma_load_5d(sB + c * b_slab, &mapB, &bars->full[stage], p.x_c0 + n0 + c * 64, w0 + dxi - 1, h0 - 1, 0, tn);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.BN) | (1u << 15) | (1u << 16);   // both MN-major
+        const uint32_t dy_bytes = (uint32_t)p.bw * 128u;       // one image row of the tile
+        const int ksteps = kp >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + (uint32_t)a_bytes;
+          const uint64_t adesc = umma_desc_mnmajor_sw128(a_addr, (uint32_t)a_slab);
+#pragma unroll
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const uint64_t bdesc = umma_desc_mnmajor_sw128(b_addr + (uint32_t)dyi * dy_bytes, (uint32_t)b_slab);
+            const uint32_t td = tmem_d + (uint32_t)(dyi * p.BN);
+            for (int k = 0; k < ksteps; ++k)   // 16 K-rows = 2048 B per step
+              umma_bf16(td, adesc + 128ull * (uint64_t)k, bdesc + 128ull * (uint64_t)k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->acc_full);
+      }
+    } else {
+      const int q = warp & 3;
+      const int m = mt * 128 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      mbar_wait(&bars->acc_full, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        float* obase = p.out + (long long)ks * p.s_split + (long long)(dyi * 3 + dxi) * p.s_tap + (long long)m * p.N;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_x32(taddr + (uint32_t)(dyi * p.BN + c0), v);
+          tmem_ld_wait();
+          const int n0 = nt * p.BN + c0;
+          if (!m_ok || n0 >= p.N) continue;
+          float* o = obase + n0;
+          if (n0 + 32 <= p.N && (((uintptr_t)o) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
 static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& p_in, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
@@ -380,6 +528,74 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   B200_REQUIRE(d->Cout >= 1 && d->dy_c0 >= 0 && d->dy_c0 + d->Cout <= d->dy_C && d->Cin >= 1 && d->Cin <= d->x_C, "conv2d_wgrad: bad Cout/Cin");
   B200_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "conv2d_wgrad: ntaps=%d out of range", d->ntaps);
   B200_REQUIRE(((uintptr_t)d->dy & 127) == 0 && ((uintptr_t)d->x & 127) == 0, "conv2d_wgrad: operand alignment");
+  // ---- vertical-tap-fused path: plain 3x3 stride-1 pad-1 convolution, two-phase reduction available ----
+  {
+    static const char* env_v3 = getenv("B200_WGRAD_V3");
+    bool plain3x3 = d->ntaps == 9 && d->x_planes == 1 && d->x_H == d->Ho && d->x_W == d->Wo && d->scratch != nullptr &&
+                    d->Wo >= 8 && (d->Wo & (d->Wo - 1)) == 0 && (d->Ho & (d->Ho - 1)) == 0;
+    for (int k = 0; k < 9 && plain3x3; ++k)
+      plain3x3 = d->taps[k][0] == (k % 3) - 1 && d->taps[k][1] == (k / 3) - 1 && d->taps[k][2] == 0;
+    if (plain3x3 && !(env_v3 && atoi(env_v3) == 0)) {
+      Wgrad3Params q;
+      memset(&q, 0, sizeof(q));
+      static const char* env_kp = getenv("B200_WGRAD_V3_KP");
+      const int kp_want = env_kp ? atoi(env_kp) : 128;   // measured: 128-pixel K-blocks beat 64 on every layer
+      q.bw = d->Wo < kp_want ? d->Wo : kp_want;
+      q.bh = kp_want / q.bw;
+      if (q.bh > d->Ho) q.bh = d->Ho;
+      if (q.bh < 1) q.bh = 1;
+      q.tiles_w = d->Wo / q.bw; q.tiles_h = d->Ho / q.bh;
+      q.kblocks = q.tiles_w * q.tiles_h * d->B;
+      const int n_split = (d->Cin + 127) / 128;
+      q.BN = (((d->Cin + n_split - 1) / n_split + 63) / 64) * 64;
+      q.m_tiles = (d->Cout + 127) / 128;
+      q.n_tiles = (d->Cin + q.BN - 1) / q.BN;
+      q.dy_c0 = d->dy_c0; q.x_c0 = d->x_c0; q.M = d->Cout; q.N = d->Cin;
+      const long tiles3 = 3l * q.m_tiles * q.n_tiles;
+      long ks = num_sms() / tiles3;
+      if (ks > q.kblocks) ks = q.kblocks;
+      if (ks < 1) ks = 1;
+      {
+        const long per = (q.kblocks + ks - 1) / ks;
+        ks = (q.kblocks + per - 1) / per;
+      }
+      const long long per_split3 = 9ll * d->Cout * d->Cin;
+      const int kp = q.bw * q.bh;
+      const int stage_bytes = 2 * kp * 128 + (q.BN / 64) * (q.bh + 2) * q.bw * 128;
+      int stages = (int)((227 * 1024 - 2048 - sizeof(GemmBars)) / stage_bytes);
+      if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+      // measured (tools/bench_wgrad.py): with few tiles the pixel range is split ~50 ways and the partial-sum traffic
+      // eats the gain (128->128@32x32: 56 -> 70 us), small images have too few K-blocks; otherwise 1.1-1.8x faster
+      const bool pays = (tiles3 >= 6 && d->Ho * d->Wo >= 256) || (env_v3 && atoi(env_v3) == 2);
+      if (pays && kp % 16 == 0 && stages >= 2 && d->scratch_bytes >= ks * per_split3 * 4 && tiles3 <= num_sms()) {
+        q.ksplit = (int)ks; q.stages = stages;
+        q.out = reinterpret_cast<float*>(d->scratch);
+        q.s_split = per_split3; q.s_tap = (long long)d->Cout * d->Cin;
+        CUtensorMap mapA, mapB;
+        int rc = make_a_map(&mapA, d->dy, d->dy_C, d->Ho, d->Wo, 1, d->B, q.bw, q.bh, 1);
+        if (rc) return rc;
+        rc = make_a_map(&mapB, d->x, d->x_C, d->x_H, d->x_W, 1, d->B, q.bw, q.bh + 2, 1);
+        if (rc) return rc;
+        static bool attr3 = false;
+        if (!attr3) {
+          B200_CHECK(cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          attr3 = true;
+        }
+        const size_t smem = (size_t)stages * stage_bytes + sizeof(GemmBars) + 1024;
+        const long long grid = 3ll * q.ksplit * q.m_tiles * q.n_tiles;
+        wgrad3_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(mapA, mapB, q);
+        ++g_launch_count;
+        B200_CHECK(cudaGetLastError());
+        const long long per_tap = (long long)d->Cout * d->Cin;
+        long long g = (per_tap + 255) / 256;
+        if (g > 148 * 8) g = 148 * 8;
+        wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(reinterpret_cast<const float*>(d->scratch), d->dw, q.ksplit, 9,
+                                                            d->Cout, d->Cin, d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride);
+        ++g_launch_count;
+        return check_cuda(cudaGetLastError(), "wgrad3 launch");
+      }
+    }
+  }
   // K-block = kpx pixels per stage: 128 when the tensor has enough pixels for every CTA (one TMA operation then
   // brings 16 KB instead of 8 KB: the 64-pixel form was bound by the TMA operation rate), else 64
   static const char* env_kpx = getenv("B200_WGRAD_KPX");

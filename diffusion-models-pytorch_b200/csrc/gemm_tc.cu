@@ -445,6 +445,65 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// Second phase of the split-K weight gradient, parallel over splits: a block of 256 threads = 32 consecutive (co, ci)
+// entries x 8 split groups; a thread sums its share of the splits for all taps (ntaps independent accumulators),
+// the 8 groups are combined in shared memory and the 32 x ntaps results are written with consecutive threads on
+// consecutive (entry, tap) pairs.  (One thread per entry walking every split serially took 12 us for 10 MB and
+// 45 us once the tap-fused kernel split the pixel range ~50 ways.)
+constexpr int kRedE = 32, kRedG = 8;
+__global__ void __launch_bounds__(256) wgrad_reduce2_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                                            int splits, int ntaps, int Cout, int Cin, long long s_co,
+                                                            long long s_ci, long long s_tap) {
+  __shared__ float red[kRedG][9][kRedE + 1];
+  const long long per_tap = (long long)Cout * Cin;
+  const long long per_split = per_tap * ntaps;
+  const int e = threadIdx.x % kRedE, g = threadIdx.x / kRedE;
+  const long long i = (long long)blockIdx.x * kRedE + e;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  if (i < per_tap) {
+    for (int sp = g; sp < splits; sp += kRedG) {
+      const float* src = scratch + (long long)sp * per_split + i;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if (t < ntaps) acc[t] += __ldg(src + (long long)t * per_tap);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) red[g][t][e] = acc[t];
+  __syncthreads();
+  for (int j = threadIdx.x; j < kRedE * ntaps; j += 256) {
+    const int ee = j / ntaps, t = j - ee * ntaps;
+    const long long ie = (long long)blockIdx.x * kRedE + ee;
+    if (ie >= per_tap) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < kRedG; ++gg) v += red[gg][t][ee];
+    const int co = (int)(ie / Cin), ci = (int)(ie - (long long)co * Cin);
+    dw[co * s_co + ci * s_ci + t * s_tap] += v;
+  }
+}
+
+static int launch_wgrad_reduce(const float* scratch, float* dw, int splits, int ntaps, int Cout, int Cin, long long s_co,
+                               long long s_ci, long long s_tap, cudaStream_t stream) {
+  const long long per_tap = (long long)Cout * Cin;
+  static const char* env_r = getenv("B200_WGRAD_REDUCE");
+  // measured: the split-parallel form wins from ~12 splits on (128->128@32x32: 55 -> 51 us), loses below
+  // (512->256@16x16 with 6 splits: 72 -> 80 us)
+  // and only helps while one thread per entry leaves the machine empty (<= 32 K entries; 1x1 512->256: 22 -> 38 us)
+  if (ntaps <= 9 && splits >= 12 && per_tap <= 32768 && !(env_r && atoi(env_r) == 1)) {
+    const long long g = (per_tap + kRedE - 1) / kRedE;
+    wgrad_reduce2_kernel<<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, ntaps, Cout, Cin, s_co, s_ci, s_tap);
+  } else {
+    long long g = (per_tap + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, ntaps, Cout, Cin, s_co, s_ci, s_tap);
+  }
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "wgrad_reduce launch");
+}
+
 static int g_sms = 0;
 static int num_sms() {
   if (g_sms == 0) {
@@ -586,13 +645,8 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
         wgrad3_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(mapA, mapB, q);
         ++g_launch_count;
         B200_CHECK(cudaGetLastError());
-        const long long per_tap = (long long)d->Cout * d->Cin;
-        long long g = (per_tap + 255) / 256;
-        if (g > 148 * 8) g = 148 * 8;
-        wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(reinterpret_cast<const float*>(d->scratch), d->dw, q.ksplit, 9,
-                                                            d->Cout, d->Cin, d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride);
-        ++g_launch_count;
-        return check_cuda(cudaGetLastError(), "wgrad3 launch");
+        return launch_wgrad_reduce(reinterpret_cast<const float*>(d->scratch), d->dw, q.ksplit, 9, d->Cout, d->Cin,
+                                   d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride, stream);
       }
     }
   }
@@ -672,11 +726,6 @@ extern "C" int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream_) {
   if (rc) return rc;
   rc = launch_gemm(mapA, mapB, p, stream);
   if (rc || !two_phase) return rc;
-  const long long per_tap = (long long)d->Cout * d->Cin;   // Cin % 64 == 0: multiple of 4, 16-byte aligned partials
-  long long g = (per_tap + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
-  wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(reinterpret_cast<const float*>(d->scratch), d->dw, p.ksplit, d->ntaps,
-                                                      d->Cout, d->Cin, d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride);
-  ++g_launch_count;
-  return check_cuda(cudaGetLastError(), "wgrad_reduce_kernel launch");
+  return launch_wgrad_reduce(reinterpret_cast<const float*>(d->scratch), d->dw, p.ksplit, d->ntaps, d->Cout, d->Cin,
+                             d->dw_co_stride, d->dw_ci_stride, d->dw_tap_stride, stream);
 }

@@ -418,12 +418,46 @@ static int launch_gemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
 
 // dw[co][ci][tap] (arbitrary strides) += sum over splits of scratch[split][tap][co][ci]: the second phase of the
 // weight gradient when the pixel range is split over CTAs (plain coalesced partial stores instead of atomics)
+template <int NT>   // taps known at compile time (9, 4, 1): NT accumulators, NT x 4 independent loads per round
+__global__ void __launch_bounds__(256) wgrad_reduce_nt_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
+                                                              int splits, int Cout, int Cin, long long s_co,
+                                                              long long s_ci, long long s_tap) {
+  // a thread owns one (co, ci) and writes its NT consecutive outputs (a tap-parallel grid was measured 1.4-2x
+  // slower: nine CTAs then read-modify-write interleaved 4-byte words of the same sectors).  With one load chain
+  // per tap the kernel was pure latency (72 dependent-ish loads = 12.6 us for 256x256x9 over 8 splits).
+  const long long per_tap = (long long)Cout * Cin;
+  const long long per_split = per_tap * NT;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_tap; i += (long long)gridDim.x * blockDim.x) {
+    float acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    const float* src = scratch + i;
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      float v[4][NT];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) v[u][t] = __ldg(src + (long long)(sp + u) * per_split + (long long)t * per_tap);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] += v[u][t];
+    }
+    for (; sp < splits; ++sp) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[t] += __ldg(src + (long long)sp * per_split + (long long)t * per_tap);
+    }
+    const int co = (int)(i / Cin), ci = (int)(i - (long long)co * Cin);
+    float* o = dw + co * s_co + ci * s_ci;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) o[t * s_tap] += acc[t];
+  }
+}
+
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw,
                                                            int splits, int ntaps, int Cout, int Cin, long long s_co,
                                                            long long s_ci, long long s_tap) {
-  // a thread owns one (co, ci) and writes its ntaps consecutive outputs (a tap-parallel grid was measured 1.4-2x
-  // slower: nine CTAs then read-modify-write interleaved 4-byte words of the same sectors); the splits of a tap are
-  // fetched 4 at a time into independent accumulators
   const long long per_tap = (long long)Cout * Cin;
   const long long per_split = per_tap * ntaps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_tap; i += (long long)gridDim.x * blockDim.x) {
@@ -498,7 +532,16 @@ static int launch_wgrad_reduce(const float* scratch, float* dw, int splits, int 
   } else {
     long long g = (per_tap + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, ntaps, Cout, Cin, s_co, s_ci, s_tap);
+    static const char* env_nt = getenv("B200_WGRAD_REDUCE_NT");
+    const bool nt_ok = !(env_nt && atoi(env_nt) == 0);
+    if (nt_ok && ntaps == 9)
+      wgrad_reduce_nt_kernel<9><<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, Cout, Cin, s_co, s_ci, s_tap);
+    else if (nt_ok && ntaps == 4)
+      wgrad_reduce_nt_kernel<4><<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, Cout, Cin, s_co, s_ci, s_tap);
+    else if (nt_ok && ntaps == 1)
+      wgrad_reduce_nt_kernel<1><<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, Cout, Cin, s_co, s_ci, s_tap);
+    else
+      wgrad_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(scratch, dw, splits, ntaps, Cout, Cin, s_co, s_ci, s_tap);
   }
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "wgrad_reduce launch");

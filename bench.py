@@ -238,11 +238,13 @@ def run_ours(args):
     conv = kern.get('conv_gemm', dict(n=1, ms=1.0, flops=0.0))
     conv_tflops = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
     gn = kern.get('groupnorm_apply')
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'conv_gemm_traffic.json')
+    traffic = gn_traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'conv_gemm_traffic.json')   # written by tools/capture_traffic.sh (ncu)
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+            tj = json.load(f)
+        traffic = tj.get('dram_bytes_per_launch')
+        gn_traffic = tj.get('kernels', {}).get('groupnorm_apply', {}).get('dram_bytes_per_launch')
     images = world * B * args.steps
     value = images / (ms_total * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
@@ -283,7 +285,8 @@ def run_ours(args):
         gbs = gn['bytes'] / (gn['ms'] * 1e-3) / 1e9
         line['roofline_groupnorm'] = {'kernel': 'groupnorm_apply_kernel', 'bound': 'hbm', 'achieved': gbs,
                                       'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
-                                      'traffic': None}
+                                      'traffic': gn_traffic,
+                                      'algorithmic_bytes_per_launch': gn['bytes'] / max(gn['n'], 1)}
     if world == 1 and not args.no_extras:
         # free the headline model's arena before the (larger) secondary workloads
         del model, diffuser

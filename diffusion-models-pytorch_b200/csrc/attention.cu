@@ -10,6 +10,7 @@
 //   4. tcgen05.mma: O[128 x d] = P V      (TMEM columns [Tp, Tp + d)).
 //   5. tcgen05.ld O, scale by 1/rowsum, store bf16 [B][T][heads*d].
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/b200diff.h"
 
 namespace b200 {
@@ -200,7 +201,9 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
   B200_REQUIRE(qk && vt && out, "attention_fwd: null pointer");
   B200_REQUIRE(d >= 64 && d <= 512 && d % 64 == 0, "attention_fwd: head dim %d must be a multiple of 64 in [64,512]", d);
   B200_REQUIRE(T >= 8 && T % 8 == 0, "attention_fwd: T=%d must be a positive multiple of 8", T);
-  if (T <= 256 && !(d == 64 || d == 128 || d == 256)) {
+  static const char* env_wide = getenv("B200_ATTN_WIDE");   // experiment: chunk-streaming kernel for single-head d = 256
+  const bool force_wide = env_wide && atoi(env_wide) == 1 && heads == 1 && d == 256;
+  if (T <= 256 && (force_wide || !(d == 64 || d == 128 || d == 256))) {
     B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
     B200_REQUIRE(((uintptr_t)qk & 127) == 0 && ((uintptr_t)vt & 127) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: alignment");
     return attention_wide(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale, stream);

@@ -27,6 +27,7 @@ struct ConvKParams {
   int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
   int k_rotate;    // rotate the K-block order per CTA (spreads weight-tile requests over L2)
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
+  int vtap;      // vertical-tap reuse (conv_gemm.cu): one haloed pixel tile + 3 weight tiles per stage
   int dbg;       // experiment knob (B200_EPI_DBG): 1 = no residual loads, 2 = no output stores, 4 = epilogue does nothing
 };
 

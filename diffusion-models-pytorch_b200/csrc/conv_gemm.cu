@@ -32,7 +32,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const int px_bytes = p.NP * kBlockK * 2;
-  const int stage_bytes = kWBytes + px_bytes;
+  // vertical-tap mode: a stage = 3 weight tiles (dy = -1, 0, +1 of one horizontal offset and channel block) + ONE pixel
+  // tile with a halo row above and below; the three taps are UMMA views of it shifted by one image row (bw x 128 B,
+  // a multiple of the 1 KB swizzle repeat for bw >= 8)
+  const int halo_bytes = (p.bh + 2) * p.bw * 128;
+  const int stage_bytes = p.vtap ? 3 * kWBytes + halo_bytes : kWBytes + px_bytes;
+  const int ngroups = 3 * p.cpb0 + p.nkb1;     // vtap: pipeline units per tile
   ConvBarriers* bars = reinterpret_cast<ConvBarriers*>(smem + (size_t)p.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -71,6 +76,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const int wrow = t.ph * p.w_rows_per_phase + t.ct * kBlockC;
+        if (p.vtap) {
+          const int rot = p.k_rotate ? (int)((blockIdx.x * 5u + (unsigned)tile) % (unsigned)ngroups) : 0;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            int g = gi + rot;
+            if (g >= ngroups) g -= ngroups;
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            uint8_t* sW = smem + (size_t)stage * stage_bytes;
+            uint8_t* sP = sW + 3 * kWBytes;
+            if (g < 3 * p.cpb0) {
+              const int dxi = g / p.cpb0, cb = g - dxi * p.cpb0;
+              mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)(3 * kWBytes + halo_bytes));
+              tma_load_5d(sP, &mapA0, &bars->full[stage], cb * kBlockK, t.w0 + dxi - 1, t.h0 - 1, 0, t.n0);
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                tma_load_2d(sW + r * kWBytes, &mapW, &bars->full[stage], ((r * 3 + dxi) * p.cpb0 + cb) * kBlockK, wrow);
+            } else {
+              const int kb1 = g - 3 * p.cpb0;
+              mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)(kWBytes + px_bytes));
+              tma_load_5d(sP, &mapA1, &bars->full[stage], kb1 * kBlockK, t.w0 + p.tap1[0], t.h0 + p.tap1[1], p.tap1[2], t.n0);
+              tma_load_2d(sW, &mapW, &bars->full[stage], (p.nkb0 + kb1) * kBlockK, wrow);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         // Every CTA walks the K-blocks of its tile from a different starting point: otherwise all SMs request
         // the same 16 KB weight tile from the same L2 lines at the same moment (accumulation order is irrelevant).
         const int rot = p.k_rotate ? (int)((blockIdx.x * 5u + (unsigned)tile) % (unsigned)nkb) : 0;
@@ -111,6 +141,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.NP);
+        if (p.vtap) {
+          const int rot = p.k_rotate ? (int)((blockIdx.x * 5u + (unsigned)tile) % (unsigned)ngroups) : 0;
+          const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;      // one image row, in descriptor (16-byte) units
+          for (int gi = 0; gi < ngroups; ++gi) {
+            int g = gi + rot;
+            if (g >= ngroups) g -= ngroups;
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t pdesc = umma_desc_kmajor_sw128(w_addr + 3 * kWBytes);
+            const int nr = g < 3 * p.cpb0 ? 3 : 1;
+            for (int r = 0; r < nr; ++r) {
+              const uint64_t wdesc = umma_desc_kmajor_sw128(w_addr + (uint32_t)(r * kWBytes));
+              const uint64_t pd = pdesc + (uint64_t)(r * row_step);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(tmem_d, wdesc + (uint64_t)(2 * k), pd + (uint64_t)(2 * k), idesc, (gi > 0 || r > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&bars->empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&bars->tmem_full[as]);
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
@@ -261,14 +315,28 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
 
   static const char* env_dbg = getenv("B200_EPI_DBG");
   p.dbg = env_dbg ? atoi(env_dbg) : 0;
+  // vertical-tap reuse (B200_VTAP=0 disables): plain 3x3 stride-1 layers whose 256-pixel tile is >= 4 full-width rows
+  // of one image.  Measured (B=256, back to back): 128->128@32x32 +res 90.1 -> 84.5 us, 256->256@16x16 +res 79.3 ->
+  // 70.9 us (the CTA-pair kernel needs 75.4 us for that layer, so eligible layers take this path instead).
+  static const char* env_vtap = getenv("B200_VTAP");
+  static const char* env_vbh = getenv("B200_VTAP_MINBH");
+  const int vtap_min_bh = env_vbh ? atoi(env_vbh) : 4;
+  if (!(env_vtap && atoi(env_vtap) == 0) && d->phases == 1 && d->ntaps0 == 9 && d->a0_planes == 1 && p.NP == 256 &&
+      p.bn == 1 && p.bw >= 8 && p.bh >= vtap_min_bh && p.bw == d->Wo && d->a0_H == d->Ho && d->a0_W == d->Wo &&
+      p.dbg < 8 && 2 * (3 * kWBytes + (p.bh + 2) * p.bw * 128) + 2048 <= 227 * 1024) {
+    bool std3 = true;
+    for (int k = 0; k < 9; ++k)
+      std3 = std3 && d->taps0[0][k][0] == (k % 3) - 1 && d->taps0[0][k][1] == (k / 3) - 1 && d->taps0[0][k][2] == 0;
+    p.vtap = std3 ? 1 : 0;
+  }
   // CTA pairs (cta_group::2, conv_gemm2.cu) when two 128-channel tiles can share one 256-pixel tile and there are
   // enough pair tiles to occupy the 74 SM pairs
   static const char* env_pair = getenv("B200_PAIR");
-  if ((!env_pair || atoi(env_pair) != 0) && d->N % 256 == 0 && p.NP == 256 &&
+  if (!p.vtap && (!env_pair || atoi(env_pair) != 0) && d->N % 256 == 0 && p.NP == 256 &&
       (long)d->phases * p.p_tiles * (c_tiles / 2) >= (long)(g_num_sms / 2) * 3 / 4)
     return conv2d_fwd_pair(d, p, stream);
 
-  const int stage_bytes = kWBytes + p.NP * 128;
+  const int stage_bytes = p.vtap ? 3 * kWBytes + (p.bh + 2) * p.bw * 128 : kWBytes + p.NP * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   static const char* env_stages = getenv("B200_STAGES");
@@ -277,7 +345,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvBarriers) + 1024;
 
   CUtensorMap mapA0, mapA1, mapW;
-  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, p.bw, p.bh, p.bn);
+  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, p.bw, p.vtap ? p.bh + 2 : p.bh, p.bn);
   if (rc) return rc;
   if (d->a1) {
     rc = make_a_map(&mapA1, d->a1, d->a1_C, d->a1_H, d->a1_W, d->a1_planes, d->B, p.bw, p.bh, p.bn);

@@ -293,6 +293,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         try:
             line['extras'] = _extras(dev, peaks)
+            if 'sampler_update' in line['extras']:
+                line['roofline_sampler'] = line['extras'].pop('sampler_update')
         except Exception as e:  # noqa: BLE001  (secondary numbers must never cost the headline line)
             line['extras'] = {'error': repr(e)}
     if stdout_fd is not None:
@@ -394,6 +396,37 @@ def _extras(dev, peaks):
                              'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
                              'kernels_per_step': (K.launch_count() - n0) // 10,
                              'loss_first': float(first), 'loss_last': float(loss)}
+    del step, model
+    torch.cuda.empty_cache()
+    try:
+        # ---- (3) K4 sampler update against the HBM roofline (CIFAR-size tensors are launch-latency bound,
+        # so the GB/s figure is taken on tensors larger than the 126 MB L2; two buffer sets alternate) ----
+        Bk, Hk = 256, 256
+        dd = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, eta=0.0, device=dev)
+        row = dd._coef_row(500, 480)
+        sets = [[torch.randn(Bk, 3, Hk, Hk, device=dev) for _ in range(3)] + [torch.empty(Bk, 3, Hk, Hk, device=dev)]
+                for _ in range(2)]
+        call = lambda s: K.sampler_step(s[0], s[1], row, objective='pred_eps', clip=True, noise=s[2], sample=s[3])  # noqa: E731
+        for s_ in sets:
+            call(s_)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(10):
+            for s_ in sets:
+                call(s_)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        by = 4.0 * Bk * 3 * Hk * Hk * 4      # model output, x_t, noise read; x_{t-1} written
+        out['sampler_update'] = {'kernel': 'sampler_step_vec4_kernel (K4: predict + clip + DDIM/DDPM step, fused)',
+                                 'bound': 'hbm', 'achieved': by / us / 1e3, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                                 'frac': by / us / 1e3 / peaks['hbm'], 'traffic': None,
+                                 'algorithmic_bytes_per_launch': by, 'avg_launch_us': us,
+                                 'workload': f'DDIM step on [{Bk},3,{Hk},{Hk}] fp32 tensors (201 MB each, 4 streams), '
+                                             f'20 launches over 2 buffer sets'}
+    except Exception as e:  # noqa: BLE001  (must not cost the two numbers above)
+        out['sampler_update_error'] = repr(e)
     return out
 
 

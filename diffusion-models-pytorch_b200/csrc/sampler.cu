@@ -26,49 +26,121 @@ __device__ __forceinline__ float predict_eps(float out, float xt, int objective,
   return __fdiv_rn(__fsub_rn(__fmul_rn(c_rx, xt), x0), c_rm1);
 }
 
+// Scalars of one step: the coefficient row is read once per thread, before the streaming loop.
+struct StepCoef {
+  float c_rx, c_rm1, c_sa, c_s1ma, c_x0, c_xt, c_eps, sd_fixed, min_lv, max_lv;
+  bool add_noise;
+};
+
+__device__ __forceinline__ StepCoef load_step_coef(const float* __restrict__ coef) {
+  StepCoef c;
+  c.c_rx = coef[B200_SC_SQRT_RECIP_AC]; c.c_rm1 = coef[B200_SC_SQRT_RECIPM1_AC];
+  c.c_sa = coef[B200_SC_SQRT_AC]; c.c_s1ma = coef[B200_SC_SQRT_1M_AC];
+  c.c_x0 = coef[B200_SC_X0_COEF]; c.c_xt = coef[B200_SC_XT_COEF]; c.c_eps = coef[B200_SC_EPS_COEF];
+  c.sd_fixed = __fsqrt_rn(coef[B200_SC_VAR]);
+  c.min_lv = coef[B200_SC_MIN_LOGVAR]; c.max_lv = coef[B200_SC_MAX_LOGVAR];
+  c.add_noise = coef[B200_SC_ADD_NOISE] != 0.0f;
+  return c;
+}
+
+// One element of the update.  mo_u is only read when cfg, lv only when learned_range (and noise is being added).
+__device__ __forceinline__ void step_element(const SamplerK& k, const StepCoef& c, bool cfg, float mo, float mo_u, float xt,
+                                             float nz, float lv, float& out, float& mean, float& x0, float& eps, float& var) {
+  if (cfg) {
+    float tmp;
+    const float eps_c = predict_eps(mo, xt, k.objective, k.clip, c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, tmp);
+    const float eps_u = predict_eps(mo_u, xt, k.objective, k.clip, c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, tmp);
+    const float mix = __fadd_rn(__fmul_rn(k.gs_u, eps_u), __fmul_rn(k.gs_c, eps_c));
+    eps = predict_eps(mix, xt, B200_OBJ_EPS, k.clip, c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, x0);
+  } else {
+    eps = predict_eps(mo, xt, k.objective, k.clip, c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, x0);
+  }
+  mean = __fadd_rn(__fadd_rn(__fmul_rn(c.c_x0, x0), __fmul_rn(c.c_xt, xt)), __fmul_rn(c.c_eps, eps));
+  out = mean;
+  var = 0.0f;
+  if (c.add_noise) {
+    float sd = c.sd_fixed;
+    if (k.learned_range) {
+      const float frac = __fdiv_rn(__fadd_rn(lv, 1.0f), 2.0f);
+      const float logvar = __fadd_rn(__fmul_rn(frac, c.max_lv), __fmul_rn(__fsub_rn(1.0f, frac), c.min_lv));
+      var = expf(logvar);
+      sd = __fsqrt_rn(var);
+    }
+    out = __fadd_rn(mean, __fmul_rn(sd, nz));
+  }
+}
+
+// Generic form: any HW / alignment, one element per iteration.
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerK k) {
-  const float c_rx = k.coef[B200_SC_SQRT_RECIP_AC], c_rm1 = k.coef[B200_SC_SQRT_RECIPM1_AC];
-  const float c_sa = k.coef[B200_SC_SQRT_AC], c_s1ma = k.coef[B200_SC_SQRT_1M_AC];
-  const float c_x0 = k.coef[B200_SC_X0_COEF], c_xt = k.coef[B200_SC_XT_COEF], c_eps = k.coef[B200_SC_EPS_COEF];
-  const float var_fixed = k.coef[B200_SC_VAR];
-  const float min_lv = k.coef[B200_SC_MIN_LOGVAR], max_lv = k.coef[B200_SC_MAX_LOGVAR];
-  const bool add_noise = k.coef[B200_SC_ADD_NOISE] != 0.0f;
-  const float sd_fixed = __fsqrt_rn(var_fixed);
+  const StepCoef c = load_step_coef(k.coef);
+  const bool cfg = k.mo_u != nullptr;
+  const bool want_lv = c.add_noise && k.learned_range;
   const size_t chw = (size_t)k.C * k.HW;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < k.total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / chw;
     const size_t r = i - b * chw;  // c*HW + hw
     const size_t mi = b * (size_t)k.Cm * k.HW + r;
-    const float xt = k.xt[i];
-    float x0, eps;
-    if (k.mo_u) {
-      float tmp;
-      const float eps_c = predict_eps(k.mo[mi], xt, k.objective, k.clip, c_rx, c_rm1, c_sa, c_s1ma, tmp);
-      const float eps_u = predict_eps(k.mo_u[mi], xt, k.objective, k.clip, c_rx, c_rm1, c_sa, c_s1ma, tmp);
-      const float mix = __fadd_rn(__fmul_rn(k.gs_u, eps_u), __fmul_rn(k.gs_c, eps_c));
-      eps = predict_eps(mix, xt, B200_OBJ_EPS, k.clip, c_rx, c_rm1, c_sa, c_s1ma, x0);
-    } else {
-      eps = predict_eps(k.mo[mi], xt, k.objective, k.clip, c_rx, c_rm1, c_sa, c_s1ma, x0);
-    }
-    const float mean = __fadd_rn(__fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_xt, xt)), __fmul_rn(c_eps, eps));
-    float out = mean;
-    if (add_noise) {
-      float sd = sd_fixed;
-      if (k.learned_range) {
-        const float lv = k.mo[mi + chw];
-        const float frac = __fdiv_rn(__fadd_rn(lv, 1.0f), 2.0f);
-        const float logvar = __fadd_rn(__fmul_rn(frac, max_lv), __fmul_rn(__fsub_rn(1.0f, frac), min_lv));
-        const float var = expf(logvar);
-        if (k.var_out) k.var_out[i] = var;
-        sd = __fsqrt_rn(var);
-      }
-      const float nz = k.noise ? k.noise[i] : 0.0f;
-      out = __fadd_rn(mean, __fmul_rn(sd, nz));
-    }
+    float out, mean, x0, eps, var;
+    step_element(k, c, cfg, k.mo[mi], cfg ? k.mo_u[mi] : 0.0f, k.xt[i], (c.add_noise && k.noise) ? k.noise[i] : 0.0f,
+                 want_lv ? k.mo[mi + chw] : 0.0f, out, mean, x0, eps, var);
+    if (want_lv && k.var_out) k.var_out[i] = var;
     if (k.sample) k.sample[i] = out;
     if (k.mean) k.mean[i] = mean;
     if (k.pred_x0) k.pred_x0[i] = x0;
     if (k.pred_eps) k.pred_eps[i] = eps;
+  }
+}
+
+// Streaming form (HW % 4 == 0, 16-byte aligned tensors): a thread owns U 16-byte units per iteration, a grid stride
+// apart, and issues every load of the iteration (2..5 streams x U) before the first dependent instruction, so
+// >= 64 B per thread are in flight; outputs leave as 16-byte stores.  Same per-element arithmetic as above, hence
+// the same bits.  The batch index (needed only when the model has 2C channels) costs one division per unit.
+template <int U>
+__global__ void __launch_bounds__(256) sampler_step_vec4_kernel(const SamplerK k) {
+  const StepCoef c = load_step_coef(k.coef);
+  const bool cfg = k.mo_u != nullptr;
+  const bool want_lv = c.add_noise && k.learned_range;
+  const bool want_nz = c.add_noise && k.noise != nullptr;
+  const size_t chw4 = ((size_t)k.C * k.HW) >> 2, mchw4 = ((size_t)k.Cm * k.HW) >> 2;
+  const size_t units = k.total >> 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float4* __restrict__ mo4 = reinterpret_cast<const float4*>(k.mo);
+  const float4* __restrict__ mou4 = reinterpret_cast<const float4*>(k.mo_u);
+  const float4* __restrict__ xt4 = reinterpret_cast<const float4*>(k.xt);
+  const float4* __restrict__ nz4 = reinterpret_cast<const float4*>(k.noise);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < units; base += stride * U) {
+    float4 vmo[U], vmu[U], vxt[U], vnz[U], vlv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)u * stride;
+      vmo[u] = vmu[u] = vxt[u] = vnz[u] = vlv[u] = zero;
+      if (i < units) {
+        size_t mi = i;
+        if (mchw4 != chw4) { const size_t b = i / chw4; mi = b * mchw4 + (i - b * chw4); }
+        vxt[u] = xt4[i];
+        vmo[u] = mo4[mi];
+        if (cfg) vmu[u] = mou4[mi];
+        if (want_nz) vnz[u] = nz4[i];
+        if (want_lv) vlv[u] = mo4[mi + chw4];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + (size_t)u * stride;
+      if (i < units) {
+        float4 out, mean, x0, eps, var;
+        step_element(k, c, cfg, vmo[u].x, vmu[u].x, vxt[u].x, vnz[u].x, vlv[u].x, out.x, mean.x, x0.x, eps.x, var.x);
+        step_element(k, c, cfg, vmo[u].y, vmu[u].y, vxt[u].y, vnz[u].y, vlv[u].y, out.y, mean.y, x0.y, eps.y, var.y);
+        step_element(k, c, cfg, vmo[u].z, vmu[u].z, vxt[u].z, vnz[u].z, vlv[u].z, out.z, mean.z, x0.z, eps.z, var.z);
+        step_element(k, c, cfg, vmo[u].w, vmu[u].w, vxt[u].w, vnz[u].w, vlv[u].w, out.w, mean.w, x0.w, eps.w, var.w);
+        if (want_lv && k.var_out) reinterpret_cast<float4*>(k.var_out)[i] = var;
+        if (k.sample) reinterpret_cast<float4*>(k.sample)[i] = out;
+        if (k.mean) reinterpret_cast<float4*>(k.mean)[i] = mean;
+        if (k.pred_x0) reinterpret_cast<float4*>(k.pred_x0)[i] = x0;
+        if (k.pred_eps) reinterpret_cast<float4*>(k.pred_eps)[i] = eps;
+      }
+    }
   }
 }
 
@@ -182,10 +254,24 @@ extern "C" int b200_sampler_step(const b200_sampler_desc* d, void* stream_) {
   k.gs_u = (float)(1.0 - d->guidance_scale);
   k.sample = d->sample; k.mean = d->mean; k.pred_x0 = d->pred_x0; k.pred_eps = d->pred_eps; k.var_out = d->var_out;
   k.total = (size_t)d->B * d->C * d->HW;
-  size_t g = (k.total + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
-  if (g == 0) g = 1;
-  sampler_step_kernel<<<(int)g, 256, 0, stream>>>(k);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = d->HW % 4 == 0 && al16(k.mo) && al16(k.mo_u) && al16(k.xt) && al16(k.noise) && al16(k.sample) &&
+                   al16(k.mean) && al16(k.pred_x0) && al16(k.pred_eps) && al16(k.var_out);
+  if (vec) {
+    // two units per thread per iteration once the tensor gives every thread of a full grid more than one
+    const size_t units = k.total / 4;
+    const int U = units > (size_t)148 * 8 * 256 ? 2 : 1;
+    size_t g = (units + (size_t)256 * U - 1) / ((size_t)256 * U);
+    if (g > 148 * 8) g = 148 * 8;
+    if (g == 0) g = 1;
+    if (U == 2) sampler_step_vec4_kernel<2><<<(int)g, 256, 0, stream>>>(k);
+    else sampler_step_vec4_kernel<1><<<(int)g, 256, 0, stream>>>(k);
+  } else {
+    size_t g = (k.total + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g == 0) g = 1;
+    sampler_step_kernel<<<(int)g, 256, 0, stream>>>(k);
+  }
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "sampler_step launch");
 }

@@ -757,40 +757,131 @@ def case_sampler():
     from oracle import diffusion_ref as R
     import diffusions
     ok = True
-    B, C, H = 4, 3, 8
-    xt = _gen(B, C, H, H, seed=1)
-    noise = _gen(B, C, H, H, seed=2)
-    for kind in ('ddpm', 'ddim'):
-        for var_type in (('fixed_small', 'fixed_large', 'learned_range') if kind == 'ddpm' else ('fixed_large',)):
-            for eta in ((0.0, 0.5, 1.0) if kind == 'ddim' else (0.0,)):
-                for objective in ('pred_eps', 'pred_x0', 'pred_v'):
-                    for clip in (True, False):
-                        Cm = 2 * C if var_type == 'learned_range' else C
-                        mo = _gen(B, Cm, H, H, seed=3)
-                        kw = dict(total_steps=1000, objective=objective, clip_denoised=clip, respace_type='uniform',
-                                  respace_steps=50)
-                        if kind == 'ddpm':
-                            ours = diffusions.DDPM(var_type=var_type, device=DEV, **kw)
-                            ref = R.DDPMRef(var_type=var_type, **kw)
-                        else:
-                            ours = diffusions.DDIM(eta=eta, device=DEV, **kw)
-                            ref = R.DDIMRef(eta=eta, **kw)
-                        for (t, tp) in ((980, 960), (500, 480), (20, 0), (0, -1)):
-                            o = ours.denoise(mo.clone(), xt, t, tp, reverse_eps=noise)
-                            r = ref.denoise(mo.clone().cpu(), xt.cpu(), t, tp, reverse_eps=noise.cpu())
-                            for key in ('sample', 'mean', 'pred_x0', 'pred_eps', 'var'):
-                                rv = r[key] if torch.is_tensor(r[key]) else torch.tensor(r[key])
-                                ov = o[key]
-                                # same fp32 op order, non-contracted: agreement to 1e-6 abs + 1e-6 rel
-                                # (learned_range goes through expf: 1e-5)
-                                tol = 1e-5 if var_type == 'learned_range' else 1e-6
-                                good = torch.allclose(ov.cpu().float().expand_as(rv) if ov.dim() == 0 else ov.cpu(),
-                                                      rv, rtol=tol, atol=tol)
-                                if not good:
-                                    _report(f'sampler {kind} {var_type} eta={eta} {objective} clip={clip} t={t} {key}',
-                                            ov.cpu().expand_as(rv) if ov.dim() == 0 else ov.cpu(), rv, tol, tol)
-                                    ok = False
+    B, C = 4, 3
+    # H=8: HW % 4 == 0 -> the 16-byte streaming kernel; H=5: HW = 25 -> the generic one-element kernel
+    for H in (8, 5):
+        xt = _gen(B, C, H, H, seed=1)
+        noise = _gen(B, C, H, H, seed=2)
+        for kind in ('ddpm', 'ddim'):
+            for var_type in (('fixed_small', 'fixed_large', 'learned_range') if kind == 'ddpm' else ('fixed_large',)):
+                for eta in ((0.0, 0.5, 1.0) if kind == 'ddim' else (0.0,)):
+                    for objective in ('pred_eps', 'pred_x0', 'pred_v'):
+                        for clip in (True, False):
+                            Cm = 2 * C if var_type == 'learned_range' else C
+                            mo = _gen(B, Cm, H, H, seed=3)
+                            kw = dict(total_steps=1000, objective=objective, clip_denoised=clip, respace_type='uniform',
+                                      respace_steps=50)
+                            if kind == 'ddpm':
+                                ours = diffusions.DDPM(var_type=var_type, device=DEV, **kw)
+                                ref = R.DDPMRef(var_type=var_type, **kw)
+                            else:
+                                ours = diffusions.DDIM(eta=eta, device=DEV, **kw)
+                                ref = R.DDIMRef(eta=eta, **kw)
+                            for (t, tp) in ((980, 960), (500, 480), (20, 0), (0, -1)):
+                                o = ours.denoise(mo.clone(), xt, t, tp, reverse_eps=noise)
+                                r = ref.denoise(mo.clone().cpu(), xt.cpu(), t, tp, reverse_eps=noise.cpu())
+                                for key in ('sample', 'mean', 'pred_x0', 'pred_eps', 'var'):
+                                    rv = r[key] if torch.is_tensor(r[key]) else torch.tensor(r[key])
+                                    ov = o[key]
+                                    # same fp32 op order, non-contracted: agreement to 1e-6 abs + 1e-6 rel
+                                    # (learned_range goes through expf: 1e-5)
+                                    tol = 1e-5 if var_type == 'learned_range' else 1e-6
+                                    good = torch.allclose(ov.cpu().float().expand_as(rv) if ov.dim() == 0 else ov.cpu(),
+                                                          rv, rtol=tol, atol=tol)
+                                    if not good:
+                                        _report(f'sampler {kind} {var_type} eta={eta} {objective} clip={clip} t={t} {key}',
+                                                ov.cpu().expand_as(rv) if ov.dim() == 0 else ov.cpu(), rv, tol, tol)
+                                        ok = False
     print(json.dumps({'case': 'sampler sweep', 'ok': ok}))
+    return ok
+
+
+
+def case_sampler_cfg():
+    """Classifier-free-guidance step: per-branch predict (+clip), eps = (1-s) eps_u + s eps_c, then the step under
+    objective pred_eps (diffusions/ddim.py:161-191, ddpm.py:319-351), fused in K4, against the oracle's op sequence."""
+    sys.path.insert(0, ROOT)
+    from oracle import diffusion_ref as R
+    import diffusions
+    ok, worst = True, 0.0
+    B, C = 4, 3
+    for H in (8, 5):
+        xt, noise = _gen(B, C, H, H, seed=1), _gen(B, C, H, H, seed=2)
+        for kind, var_type, eta in (('ddim', 'fixed_large', 0.0), ('ddim', 'fixed_large', 1.0),
+                                    ('ddpm', 'fixed_small', 0.0), ('ddpm', 'learned_range', 0.0)):
+            for objective in ('pred_eps', 'pred_x0', 'pred_v'):
+                for clip in (True, False):
+                    Cm = 2 * C if var_type == 'learned_range' else C
+                    mo_c, mo_u = _gen(B, Cm, H, H, seed=3), _gen(B, Cm, H, H, seed=4)
+                    kw = dict(total_steps=1000, objective=objective, clip_denoised=clip, respace_type='uniform',
+                              respace_steps=50, beta_schedule='cosine')
+                    rkw = dict(kw)
+                    rkw['beta_schedule_kind'] = rkw.pop('beta_schedule')
+                    if kind == 'ddpm':
+                        ours = diffusions.DDPMCFG(guidance_scale=3.0, var_type=var_type, device=DEV, **kw)
+                        ref = R.DDPMRef(var_type=var_type, **rkw)
+                    else:
+                        ours = diffusions.DDIMCFG(guidance_scale=3.0, eta=eta, device=DEV, **kw)
+                        ref = R.DDIMRef(eta=eta, **rkw)
+                    for (t, tp) in ((980, 960), (500, 480), (0, -1)):
+                        o = ours._denoise_impl(mo_c.clone(), xt, t, tp, noise, mo_u.clone(), 3.0)
+                        ref._pairs = lambda t=t, tp=tp: [(t, tp)]   # one step (t -> tp) of the oracle's CFG loop
+                        r = next(ref.sample_loop_cfg(lambda img, tb, which: (mo_c if which else mo_u).cpu(), xt.cpu(),
+                                                     3.0, dict(which=True), dict(which=False), noises=[noise.cpu()]))
+                        for key in ('sample', 'mean', 'pred_x0', 'pred_eps'):
+                            tol = 1e-5   # same fp32 op order; the guided eps reaches O(100) at small alpha-bar
+                            worst = max(worst, ((o[key].cpu() - r[key]).abs() / (1.0 + r[key].abs())).max().item())
+                            good = torch.allclose(o[key].cpu(), r[key], rtol=tol, atol=tol)
+                            if not good:
+                                _report(f'sampler cfg {kind} {var_type} eta={eta} {objective} clip={clip} H={H} t={t} {key}',
+                                        o[key].cpu(), r[key], tol, tol)
+                                ok = False
+    print(json.dumps({'case': 'sampler cfg sweep', 'max_rel_err': worst, 'gate': 1e-5, 'ok': ok}))
+    return ok
+
+
+def case_sampler_large():
+    """K4 at a size where the two-units-per-thread streaming kernel and the grid-stride tail are exercised
+    (B=24, 3x256x256: 4.7 M elements, 1.18 M units > 148*8*256 threads), against the generic kernel run on the same
+    data through unaligned views (bit-exact: same per-element arithmetic), for the plain, noisy, learned-variance and
+    CFG forms."""
+    import diffusions
+    import b200diff as K
+    ok = True
+    B, C, H = 24, 3, 256
+    n = B * C * H * H
+    for var_type, cfg in (('fixed_large', False), ('learned_range', False), ('fixed_large', True)):
+        Cm = 2 * C if var_type == 'learned_range' else C
+        d = diffusions.DDPM(total_steps=1000, var_type=var_type, respace_type='uniform', respace_steps=50, device=DEV)
+        row = d._coef_row(500, 480)
+        g = torch.Generator(device=DEV).manual_seed(5)
+        def mk(c):
+            # one spare leading float so that [1:] views are 4-byte- but not 16-byte-aligned
+            buf = torch.randn(B * c * H * H + 4, device=DEV, generator=g)
+            al = buf[4:].view(B, c, H, H)
+            un = torch.empty(B * c * H * H + 4, device=DEV)[1:B * c * H * H + 1].view(B, c, H, H)
+            un.copy_(al)
+            return al, un
+        mo, mo_un = mk(Cm)
+        xt, xt_un = mk(C)
+        nz, nz_un = mk(C)
+        mu, mu_un = mk(Cm) if cfg else (None, None)
+        outs = {k: torch.empty(B, C, H, H, device=DEV) for k in ('sample', 'mean', 'pred_x0', 'pred_eps', 'var_out')}
+        outs_un = {k: torch.empty(B, C, H, H, device=DEV) for k in outs}
+        common = dict(objective='pred_eps', clip=True, learned_range=var_type == 'learned_range',
+                      guidance_scale=3.0 if cfg else 1.0)
+        K.sampler_step(mo, xt, row, noise=nz, model_out_uncond=mu, **common, **outs)
+        K.sampler_step(mo_un, xt_un, row, noise=nz_un, model_out_uncond=mu_un, **common, **outs_un)
+        torch.cuda.synchronize()
+        for key in outs:
+            if key == 'var_out' and var_type != 'learned_range':
+                continue
+            same = torch.equal(outs[key], outs_un[key])
+            finite = bool(torch.isfinite(outs[key]).all())
+            if not (same and finite):
+                print(json.dumps({'case': f'sampler large {var_type} cfg={cfg} {key}', 'bit_equal': same, 'finite': finite}))
+                ok = False
+    print(json.dumps({'case': f'sampler large ({n} elements) streaming vs generic kernel', 'ok': ok}))
     return ok
 
 

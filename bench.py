@@ -137,8 +137,11 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DDIM-50 CIFAR-10 32x32 UNet (configs/ddpm_cifar10.yaml), random-init weights '
-                               '(seed 2022), CPU sample of batch 16'},
+        # the same workload as our arm; one bench step = a bounded CPU sample of it (see cpu_baseline.sample)
+        'config': {'workload': 'DDIM-50 CIFAR-10 32x32 UNet (configs/ddpm_cifar10.yaml), batch 256/GPU, eta=0, uniform '
+                               'respacing, random-init weights (seed 2022)',
+                   'batch_per_gpu': 256, 'sampler_steps': 50,
+                   'sample': f'batch {batch}, {substeps} of 50 DDIM steps per bench step, host cores only'},
         'cpu_baseline': {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': time.perf_counter() - t0,

@@ -26,6 +26,17 @@ __device__ __forceinline__ float predict_eps(float out, float xt, int objective,
   return __fdiv_rn(__fsub_rn(__fmul_rn(c_rx, xt), x0), c_rm1);
 }
 
+// Compile-time form of the same arithmetic for the streaming kernel (no per-element branches on uniform flags).
+template <int OBJ, bool CLIP>
+__device__ __forceinline__ float predict_eps_t(float out, float xt, const float c_rx, const float c_rm1, const float c_sa,
+                                               const float c_s1ma, float& x0) {
+  if (OBJ == B200_OBJ_EPS) x0 = __fsub_rn(__fmul_rn(c_rx, xt), __fmul_rn(c_rm1, out));
+  else if (OBJ == B200_OBJ_X0) x0 = out;
+  else x0 = __fsub_rn(__fmul_rn(c_sa, xt), __fmul_rn(c_s1ma, out));
+  if (CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  return __fdiv_rn(__fsub_rn(__fmul_rn(c_rx, xt), x0), c_rm1);
+}
+
 // Scalars of one step: the coefficient row is read once per thread, before the streaming loop.
 struct StepCoef {
   float c_rx, c_rm1, c_sa, c_s1ma, c_x0, c_xt, c_eps, sd_fixed, min_lv, max_lv;
@@ -92,14 +103,16 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerK k) {
 }
 
 // Streaming form (HW % 4 == 0, 16-byte aligned tensors): a thread owns U 16-byte units per iteration, a grid stride
-// apart, and issues every load of the iteration (2..5 streams x U) before the first dependent instruction, so
-// >= 64 B per thread are in flight; outputs leave as 16-byte stores.  Same per-element arithmetic as above, hence
-// the same bits.  The batch index (needed only when the model has 2C channels) costs one division per unit.
-template <int U>
-__global__ void __launch_bounds__(256) sampler_step_vec4_kernel(const SamplerK k) {
+// apart, and issues every load of the iteration (3..5 streams x U) before the first dependent instruction, so
+// >= 64 B per thread are in flight; outputs leave as 16-byte stores.  The uniform flags (CFG, objective, clip,
+// learned variance) are template parameters: the first version branched on them per element and was issue-bound
+// (ncu: 61 % issue slots busy at 55 % of DRAM peak, ~73 instructions per element).  Same per-element arithmetic as the
+// generic kernel, hence the same bits.  The batch index (needed only when the model has 2C channels) costs one
+// division per unit.  Grid = 4 resident CTAs x 148 SMs (one wave).
+template <int U, bool CFG, int OBJ, bool CLIP, bool LEARNED>
+__global__ void __launch_bounds__(256, 4) sampler_step_vec4_kernel(const SamplerK k) {
   const StepCoef c = load_step_coef(k.coef);
-  const bool cfg = k.mo_u != nullptr;
-  const bool want_lv = c.add_noise && k.learned_range;
+  const bool want_lv = LEARNED && c.add_noise;
   const bool want_nz = c.add_noise && k.noise != nullptr;
   const size_t chw4 = ((size_t)k.C * k.HW) >> 2, mchw4 = ((size_t)k.Cm * k.HW) >> 2;
   const size_t units = k.total >> 2;
@@ -117,10 +130,10 @@ __global__ void __launch_bounds__(256) sampler_step_vec4_kernel(const SamplerK k
       vmo[u] = vmu[u] = vxt[u] = vnz[u] = vlv[u] = zero;
       if (i < units) {
         size_t mi = i;
-        if (mchw4 != chw4) { const size_t b = i / chw4; mi = b * mchw4 + (i - b * chw4); }
+        if (LEARNED || mchw4 != chw4) { const size_t b = i / chw4; mi = b * mchw4 + (i - b * chw4); }
         vxt[u] = xt4[i];
         vmo[u] = mo4[mi];
-        if (cfg) vmu[u] = mou4[mi];
+        if (CFG) vmu[u] = mou4[mi];
         if (want_nz) vnz[u] = nz4[i];
         if (want_lv) vlv[u] = mo4[mi + chw4];
       }
@@ -129,19 +142,65 @@ __global__ void __launch_bounds__(256) sampler_step_vec4_kernel(const SamplerK k
     for (int u = 0; u < U; ++u) {
       const size_t i = base + (size_t)u * stride;
       if (i < units) {
-        float4 out, mean, x0, eps, var;
-        step_element(k, c, cfg, vmo[u].x, vmu[u].x, vxt[u].x, vnz[u].x, vlv[u].x, out.x, mean.x, x0.x, eps.x, var.x);
-        step_element(k, c, cfg, vmo[u].y, vmu[u].y, vxt[u].y, vnz[u].y, vlv[u].y, out.y, mean.y, x0.y, eps.y, var.y);
-        step_element(k, c, cfg, vmo[u].z, vmu[u].z, vxt[u].z, vnz[u].z, vlv[u].z, out.z, mean.z, x0.z, eps.z, var.z);
-        step_element(k, c, cfg, vmo[u].w, vmu[u].w, vxt[u].w, vnz[u].w, vlv[u].w, out.w, mean.w, x0.w, eps.w, var.w);
-        if (want_lv && k.var_out) reinterpret_cast<float4*>(k.var_out)[i] = var;
-        if (k.sample) reinterpret_cast<float4*>(k.sample)[i] = out;
-        if (k.mean) reinterpret_cast<float4*>(k.mean)[i] = mean;
-        if (k.pred_x0) reinterpret_cast<float4*>(k.pred_x0)[i] = x0;
-        if (k.pred_eps) reinterpret_cast<float4*>(k.pred_eps)[i] = eps;
+        const float mo[4] = {vmo[u].x, vmo[u].y, vmo[u].z, vmo[u].w}, mu[4] = {vmu[u].x, vmu[u].y, vmu[u].z, vmu[u].w};
+        const float xt[4] = {vxt[u].x, vxt[u].y, vxt[u].z, vxt[u].w}, nz[4] = {vnz[u].x, vnz[u].y, vnz[u].z, vnz[u].w};
+        const float lv[4] = {vlv[u].x, vlv[u].y, vlv[u].z, vlv[u].w};
+        float out[4], mean[4], x0[4], eps[4], var[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (CFG) {
+            float tmp;
+            const float eps_c = predict_eps_t<OBJ, CLIP>(mo[e], xt[e], c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, tmp);
+            const float eps_u = predict_eps_t<OBJ, CLIP>(mu[e], xt[e], c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, tmp);
+            const float mix = __fadd_rn(__fmul_rn(k.gs_u, eps_u), __fmul_rn(k.gs_c, eps_c));
+            eps[e] = predict_eps_t<B200_OBJ_EPS, CLIP>(mix, xt[e], c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, x0[e]);
+          } else {
+            eps[e] = predict_eps_t<OBJ, CLIP>(mo[e], xt[e], c.c_rx, c.c_rm1, c.c_sa, c.c_s1ma, x0[e]);
+          }
+          mean[e] = __fadd_rn(__fadd_rn(__fmul_rn(c.c_x0, x0[e]), __fmul_rn(c.c_xt, xt[e])), __fmul_rn(c.c_eps, eps[e]));
+          out[e] = mean[e];
+          var[e] = 0.0f;
+          if (c.add_noise) {
+            float sd = c.sd_fixed;
+            if (LEARNED) {
+              const float frac = __fdiv_rn(__fadd_rn(lv[e], 1.0f), 2.0f);
+              const float logvar = __fadd_rn(__fmul_rn(frac, c.max_lv), __fmul_rn(__fsub_rn(1.0f, frac), c.min_lv));
+              var[e] = expf(logvar);
+              sd = __fsqrt_rn(var[e]);
+            }
+            out[e] = __fadd_rn(mean[e], __fmul_rn(sd, nz[e]));
+          }
+        }
+        if (want_lv && k.var_out) reinterpret_cast<float4*>(k.var_out)[i] = make_float4(var[0], var[1], var[2], var[3]);
+        if (k.sample) reinterpret_cast<float4*>(k.sample)[i] = make_float4(out[0], out[1], out[2], out[3]);
+        if (k.mean) reinterpret_cast<float4*>(k.mean)[i] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+        if (k.pred_x0) reinterpret_cast<float4*>(k.pred_x0)[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+        if (k.pred_eps) reinterpret_cast<float4*>(k.pred_eps)[i] = make_float4(eps[0], eps[1], eps[2], eps[3]);
       }
     }
   }
+}
+
+template <int U, bool CFG, int OBJ, bool CLIP>
+static void launch_vec4_l(const SamplerK& k, int g, cudaStream_t stream) {
+  if (k.learned_range) sampler_step_vec4_kernel<U, CFG, OBJ, CLIP, true><<<g, 256, 0, stream>>>(k);
+  else sampler_step_vec4_kernel<U, CFG, OBJ, CLIP, false><<<g, 256, 0, stream>>>(k);
+}
+template <int U, bool CFG, int OBJ>
+static void launch_vec4_c(const SamplerK& k, int g, cudaStream_t stream) {
+  if (k.clip) launch_vec4_l<U, CFG, OBJ, true>(k, g, stream);
+  else launch_vec4_l<U, CFG, OBJ, false>(k, g, stream);
+}
+template <int U, bool CFG>
+static void launch_vec4_o(const SamplerK& k, int g, cudaStream_t stream) {
+  if (k.objective == B200_OBJ_EPS) launch_vec4_c<U, CFG, B200_OBJ_EPS>(k, g, stream);
+  else if (k.objective == B200_OBJ_X0) launch_vec4_c<U, CFG, B200_OBJ_X0>(k, g, stream);
+  else launch_vec4_c<U, CFG, B200_OBJ_V>(k, g, stream);
+}
+template <int U>
+static void launch_vec4(const SamplerK& k, int g, cudaStream_t stream) {
+  if (k.mo_u) launch_vec4_o<U, true>(k, g, stream);
+  else launch_vec4_o<U, false>(k, g, stream);
 }
 
 // Euler / Heun steps in sigma space (diffusions/euler.py:50-66, diffusions/heun.py:56-107; Karras et al. 2022):
@@ -258,14 +317,14 @@ extern "C" int b200_sampler_step(const b200_sampler_desc* d, void* stream_) {
   const bool vec = d->HW % 4 == 0 && al16(k.mo) && al16(k.mo_u) && al16(k.xt) && al16(k.noise) && al16(k.sample) &&
                    al16(k.mean) && al16(k.pred_x0) && al16(k.pred_eps) && al16(k.var_out);
   if (vec) {
-    // two units per thread per iteration once the tensor gives every thread of a full grid more than one
+    // two units per thread per iteration once the tensor gives every thread of a one-wave grid more than one
     const size_t units = k.total / 4;
-    const int U = units > (size_t)148 * 8 * 256 ? 2 : 1;
+    const int U = units > (size_t)148 * 4 * 256 ? 2 : 1;
     size_t g = (units + (size_t)256 * U - 1) / ((size_t)256 * U);
-    if (g > 148 * 8) g = 148 * 8;
+    if (g > 148 * 4) g = 148 * 4;
     if (g == 0) g = 1;
-    if (U == 2) sampler_step_vec4_kernel<2><<<(int)g, 256, 0, stream>>>(k);
-    else sampler_step_vec4_kernel<1><<<(int)g, 256, 0, stream>>>(k);
+    if (U == 2) launch_vec4<2>(k, (int)g, stream);
+    else launch_vec4<1>(k, (int)g, stream);
   } else {
     size_t g = (k.total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;

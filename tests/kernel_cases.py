@@ -354,6 +354,16 @@ def case_misc():
     K.cast_bf16(x, o, 2, 8, 8, 128, parity_split=True)
     refp = torch.stack([x[:, a::2, b::2] for a in range(2) for b in range(2)], dim=1).to(torch.bfloat16)
     ok &= _report('cast bf16 parity planes', o, refp, 0, 0)
+    # fast 8-channel kernel (power-of-two H, W, C/8; non-square, several grid-stride iterations) and the generic fallback
+    for (Bc, Hc, Wc, Cc) in ((5, 16, 32, 256), (300, 32, 32, 128), (2, 6, 10, 12)):
+        xc = _gen(Bc, Hc, Wc, Cc, seed=5)
+        oc = torch.empty(Bc, Hc, Wc, Cc, device=DEV, dtype=torch.bfloat16)
+        K.cast_bf16(xc, oc, Bc, Hc, Wc, Cc)
+        ok &= _report(f'cast bf16 {Bc}x{Hc}x{Wc}x{Cc}', oc, xc.to(torch.bfloat16), 0, 0)
+        oc = torch.empty(Bc, 4, Hc // 2, Wc // 2, Cc, device=DEV, dtype=torch.bfloat16)
+        K.cast_bf16(xc, oc, Bc, Hc, Wc, Cc, parity_split=True)
+        refp = torch.stack([xc[:, a::2, b::2] for a in range(2) for b in range(2)], dim=1).to(torch.bfloat16)
+        ok &= _report(f'cast bf16 parity planes {Bc}x{Hc}x{Wc}x{Cc}', oc, refp, 0, 0)
     o = torch.empty(2, 4, 4, 128, device=DEV)
     K.avgpool2_f32(x, o, 2, 8, 8, 128)
     ok &= _report('avgpool2 f32', o.permute(0, 3, 1, 2), F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2), 1e-6, 1e-6)

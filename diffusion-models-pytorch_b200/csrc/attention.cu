@@ -30,7 +30,12 @@ struct __align__(8) AttnBars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(128, 1)
+// NS = threads per score row: the row's Tp columns (softmax) and d columns (output) are split over NS warps that share
+// a TMEM lane quarter (warp % 4).  With one thread per row the softmax + output stage ran as ONE warp per scheduler
+// (~6 k dependent instructions at IPC 0.8 per SM, about half of the CTA's lifetime); NS warps per scheduler both
+// divide the work and hide each other's latency.  Row max / row sum are combined through shared memory.
+template <int NS>
+__global__ void __launch_bounds__(128 * NS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -42,8 +47,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint8_t* sQ = smem;                 // [dk][128 rows][128 B]   (aliased by P: [tk][128 rows][128 B])
   uint8_t* sK = smem + qp_bytes;      // [dk][Tp rows][128 B]    (aliased by V^T: [tk][d rows][128 B])
   AttnBars* bars = reinterpret_cast<AttnBars*>(sK + (size_t)dk * p.Tp * 128);
+  float* red_max = reinterpret_cast<float*>(bars + 1);   // [NS][128]
+  float* red_sum = red_max + NS * 128;                   // [NS][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = warp & 3, part = warp >> 2;             // TMEM lane quarter, column split owned by this warp
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
 
   if (threadIdx.x == 0) {
@@ -95,10 +103,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       tma_load_3d(sK + (size_t)c * p.d * 128, &mapV, &bars->v_full, c * 64, h * p.d, b);
   }
   __syncwarp();
-  const int r = warp * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int r = wq * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+  const int c_lo = part * (p.Tp / NS), c_hi = c_lo + p.Tp / NS;
   float m = -INFINITY;
-  for (int c = 0; c < p.Tp; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t v[32];
     tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
     tmem_ld_wait();
@@ -106,9 +115,15 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     for (int j = 0; j < 32; ++j)
       if (c + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
   }
+  if (NS > 1) {
+    red_max[part * 128 + r] = m;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NS; ++i) m = fmaxf(m, red_max[i * 128 + r]);
+  }
   const float ms = m * p.scale_log2e;
   float sum = 0.f;
-  for (int c = 0; c < p.Tp; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t v[32];
     tmem_ld_x32(tmem_s + lane_base + (uint32_t)c, v);
     tmem_ld_wait();
@@ -132,11 +147,17 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       *reinterpret_cast<uint4*>(prow + (((chunk0 + i) ^ (r & 7)) << 4)) = u;
     }
   }
+  if (NS > 1) red_sum[part * 128 + r] = sum;
   // generic-proxy writes of P -> visible to the tensor-core (async) proxy
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (NS > 1) {
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sum += red_sum[i * 128 + r];
+  }
 
   // ---- 4. O = P V ----
   if (threadIdx.x == 0) {
@@ -160,7 +181,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const float inv = 1.0f / sum;
   const bool row_ok = (q0 + r) < p.T;
   __nv_bfloat16* orow = p.out + ((size_t)b * p.T + q0 + r) * p.ld_out + h * p.d;
-  for (int c = 0; c < p.d; c += 32) {
+  const int d_lo = part * (p.d / NS), d_hi = d_lo + p.d / NS;
+  for (int c = d_lo; c < d_hi; c += 32) {
     uint32_t v[32];
     __syncwarp();
     tmem_ld_x32(tmem_o + lane_base + (uint32_t)c, v);
@@ -243,15 +265,24 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
     if (rc) return rc;
   }
   const int dk = d / 64, tk = Tp / 64;
-  const size_t smem = (size_t)(dk > tk ? dk : tk) * 16384 + (size_t)dk * Tp * 128 + sizeof(AttnBars) + 1024;
+  // threads per score row: 4 when both the key and the head dimension give every warp >= 32 columns, else 2
+  static const char* env_ns = getenv("B200_ATTN_SPLIT");   // experiment knob: 1 = one thread per row (the first version)
+  int ns = (Tp >= 128 && d >= 128) ? 4 : 2;
+  if (env_ns && (atoi(env_ns) == 1 || atoi(env_ns) == 2)) ns = atoi(env_ns);
+  const size_t smem = (size_t)(dk > tk ? dk : tk) * 16384 + (size_t)dk * Tp * 128 + sizeof(AttnBars) +
+                      (size_t)2 * ns * 128 * sizeof(float) + 1024;
   static bool attr = false;
   if (!attr) {
-    B200_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   B200_REQUIRE(smem <= 227 * 1024, "attention_fwd: smem %zu too large", smem);
   dim3 grid((T + 127) / 128, heads, B);
-  B200_CHECK(launch_pdl(attention_kernel, grid, dim3(128), smem, stream, mapQ, mapK, mapV, p));
+  if (ns == 4) B200_CHECK(launch_pdl(attention_kernel<4>, grid, dim3(512), smem, stream, mapQ, mapK, mapV, p));
+  else if (ns == 2) B200_CHECK(launch_pdl(attention_kernel<2>, grid, dim3(256), smem, stream, mapQ, mapK, mapV, p));
+  else B200_CHECK(launch_pdl(attention_kernel<1>, grid, dim3(128), smem, stream, mapQ, mapK, mapV, p));
   ++g_launch_count;
   return 0;
 }

@@ -123,34 +123,79 @@ extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
 // ================================================================================================
 namespace b200 {
 
+// Tiled form (taps <= 9): a CTA walks 32 (co) x 32 (ci) x taps tiles of its entry through shared memory.  Loads are
+// whole 32*taps-float row segments of the OIHW source (coalesced), stores are 32 consecutive bf16 of a packed row; the
+// thread mapping is (32 x 8), so no per-element division is needed.  The first version gathered single floats at a
+// stride of taps (mode 0) or Ci*taps (mode 1) elements with two integer divisions each: 448 us per training step for
+// 354 MB of traffic.
+constexpr int PW_T = 32;
+constexpr int PW_MAX_TAPS = 9;
+constexpr int PW_LD = PW_T * PW_MAX_TAPS + 1;   // odd row stride: conflict-free column reads in mode 1
+
 __global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_entry* __restrict__ table, int ctas_per_entry) {
+  __shared__ float tile[PW_T * PW_LD];
   const b200_pack_entry e = table[blockIdx.x / ctas_per_entry];
   const int part = blockIdx.x % ctas_per_entry;
   const long long total = (long long)e.Co * e.Ci * e.taps;
-  const long long per = (total + ctas_per_entry - 1) / ctas_per_entry;
-  const long long j0 = part * per, j1 = min(total, j0 + per);
   if (e.mode == 2) {
+    const long long per = (total + ctas_per_entry - 1) / ctas_per_entry;
+    const long long j0 = part * per, j1 = min(total, j0 + per);
     float* dst = reinterpret_cast<float*>(e.dst);
     for (long long j = j0 + threadIdx.x; j < j1; j += 256) dst[j] = e.src[j] + (e.src2 ? e.src2[j] : 0.f);
     return;
   }
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
-  const int tc = e.taps * (e.mode == 0 ? e.Ci : e.Co);    // packed row length of this entry
-  for (long long j = j0 + threadIdx.x; j < j1; j += 256) {
-    // j enumerates the destination in row-major order (coalesced writes)
-    const int r = (int)(j / tc);
-    const int rem = (int)(j - (long long)r * tc);
-    int co, ci, tap;
-    if (e.mode == 0) {
-      co = r; tap = rem / e.Ci; ci = rem - tap * e.Ci;
-    } else {
-      ci = r;
-      const int tp = rem / e.Co;
-      co = rem - tp * e.Co;
-      tap = e.taps - 1 - tp;
+  if (e.taps > PW_MAX_TAPS) {   // generic gather (no layer of the supported families takes it)
+    const long long per = (total + ctas_per_entry - 1) / ctas_per_entry;
+    const long long j0 = part * per, j1 = min(total, j0 + per);
+    const int tc = e.taps * (e.mode == 0 ? e.Ci : e.Co);    // packed row length of this entry
+    for (long long j = j0 + threadIdx.x; j < j1; j += 256) {
+      const int r = (int)(j / tc);
+      const int rem = (int)(j - (long long)r * tc);
+      int co, ci, tap;
+      if (e.mode == 0) {
+        co = r; tap = rem / e.Ci; ci = rem - tap * e.Ci;
+      } else {
+        ci = r;
+        const int tp = rem / e.Co;
+        co = rem - tp * e.Co;
+        tap = e.taps - 1 - tp;
+      }
+      const float v = __ldg(e.src + ((long long)co * e.Ci + ci) * e.taps + tap);
+      dst[(long long)(e.row0 + r) * e.ld + e.col0 + rem] = __float2bfloat16_rn(v);
     }
-    const float v = __ldg(e.src + ((long long)co * e.Ci + ci) * e.taps + tap);
-    dst[(long long)(e.row0 + r) * e.ld + e.col0 + rem] = __float2bfloat16_rn(v);
+    return;
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int taps = e.taps;
+  const int tiles_ci = (e.Ci + PW_T - 1) / PW_T, tiles_co = (e.Co + PW_T - 1) / PW_T;
+  for (int t = part; t < tiles_co * tiles_ci; t += ctas_per_entry) {
+    const int co0 = (t / tiles_ci) * PW_T, ci0 = (t % tiles_ci) * PW_T;
+    const int nco = min(PW_T, e.Co - co0), nci = min(PW_T, e.Ci - ci0);
+    const int seg = nci * taps;   // contiguous floats of one co row inside this tile
+    for (int r = ty; r < nco; r += 8) {
+      const float* srow = e.src + ((long long)(co0 + r) * e.Ci + ci0) * taps;
+      for (int c = tx; c < seg; c += 32) tile[r * PW_LD + c] = __ldg(srow + c);
+    }
+    __syncthreads();
+    if (e.mode == 0) {
+      // dst[row0 + co][col0 + tap*Ci + ci]
+      for (int r = ty; r < nco; r += 8) {
+        __nv_bfloat16* drow = dst + (long long)(e.row0 + co0 + r) * e.ld + e.col0 + ci0;
+        if (tx < nci)
+          for (int tap = 0; tap < taps; ++tap)
+            drow[(long long)tap * e.Ci + tx] = __float2bfloat16_rn(tile[r * PW_LD + tx * taps + tap]);
+      }
+    } else {
+      // dst[row0 + ci][col0 + (taps-1-tap)*Co + co]
+      for (int q = ty; q < nci; q += 8) {
+        __nv_bfloat16* drow = dst + (long long)(e.row0 + ci0 + q) * e.ld + e.col0 + co0;
+        if (tx < nco)
+          for (int tp = 0; tp < taps; ++tp)
+            drow[(long long)tp * e.Co + tx] = __float2bfloat16_rn(tile[tx * PW_LD + q * taps + (taps - 1 - tp)]);
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -895,6 +895,46 @@ def case_sampler_large():
     return ok
 
 
+
+def case_pack_weights():
+    """b200_pack_weights (multi-tensor fp32 OIHW -> bf16 GEMM operands) against torch permutes: forward layout (mode 0),
+    flipped / channel-swapped data-gradient layout (mode 1), bias sums (mode 2); ragged channel counts, taps 1 / 4 / 9 /
+    25 (generic gather), row / column offsets inside a wider destination."""
+    import b200diff as K
+    ok = True
+    entries, checks = [], []
+    keep = []
+    for i, (Co, Ci, kh, kw) in enumerate(((256, 256, 3, 3), (128, 384, 3, 3), (3, 128, 3, 3), (128, 3, 3, 3),
+                                          (256, 512, 1, 1), (70, 45, 2, 2), (33, 31, 3, 3), (8, 40, 5, 5))):
+        taps = kh * kw
+        w = _gen(Co, Ci, kh, kw, seed=10 + i)
+        # mode 0 into a wider matrix at a row / column offset
+        row0, col0, extra = 2 * (i % 3), 8 * (i % 2), 16
+        ld = col0 + taps * Ci + extra
+        d0 = torch.full((row0 + Co + 1, ld), 7.0, device=DEV, dtype=torch.bfloat16)
+        entries.append(K.pack_entry_bytes(w, d0, Co, Ci, taps, 0, row0=row0, col0=col0, ld=ld))
+        r0 = torch.full_like(d0, 7.0)
+        r0[row0:row0 + Co, col0:col0 + taps * Ci] = w.permute(0, 2, 3, 1).reshape(Co, taps * Ci).to(torch.bfloat16)
+        checks.append((f'pack mode 0 {Co}x{Ci}x{kh}x{kw}', d0, r0))
+        # mode 1
+        d1 = torch.full((Ci, taps * Co), 7.0, device=DEV, dtype=torch.bfloat16)
+        entries.append(K.pack_entry_bytes(w, d1, Co, Ci, taps, 1, ld=taps * Co))
+        r1 = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, taps * Co).to(torch.bfloat16)
+        checks.append((f'pack mode 1 {Co}x{Ci}x{kh}x{kw}', d1, r1))
+        keep += [w, d0, d1]
+    b1, b2 = _gen(300, seed=30), _gen(300, seed=31)
+    db, db1 = torch.zeros(300, device=DEV), torch.zeros(300, device=DEV)
+    entries.append(K.pack_entry_bytes(b1, db, 300, 1, 1, 2, src2=b2))
+    entries.append(K.pack_entry_bytes(b1, db1, 300, 1, 1, 2))
+    checks += [('pack mode 2 (bias sum)', db, b1 + b2), ('pack mode 2 (single bias)', db1, b1)]
+    blob = torch.frombuffer(bytearray(b''.join(entries)), dtype=torch.uint8).to(DEV)
+    K.pack_weights(blob, len(entries))
+    torch.cuda.synchronize()
+    for name, got, ref in checks:
+        ok &= _report(name, got, ref, 0, 0)
+    return ok
+
+
 CASES = {n[5:]: f for n, f in list(globals().items()) if n.startswith('case_')}
 
 if __name__ == '__main__':

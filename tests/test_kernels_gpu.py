@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = ['misc', 'groupnorm', 'conv_basic', 'conv_epilogue', 'conv_n256', 'conv_small_hw', 'conv_1x1',
          'conv_shortcut', 'conv_stride2', 'conv_lastconv', 'conv_up2', 'conv_tproj', 'attention', 'sampler', 'sampler_cfg',
          'sampler_large', 'gemm',
-         'wgrad', 'groupnorm_bwd', 'backward_misc', 'optimizer', 'ode_samplers']
+         'wgrad', 'groupnorm_bwd', 'backward_misc', 'optimizer', 'pack_weights', 'ode_samplers']
 
 
 @pytest.mark.gpu

@@ -403,12 +403,12 @@ def _extras(dev, peaks):
     torch.cuda.empty_cache()
     try:
         # ---- (3) K4 sampler update against the HBM roofline (CIFAR-size tensors are launch-latency bound,
-        # so the GB/s figure is taken on tensors larger than the 126 MB L2; two buffer sets alternate) ----
-        Bk, Hk = 256, 256
+        # so the GB/s figure is taken on tensors whose working set exceeds the 126 MB L2; three buffer sets rotate) ----
+        Bk, Hk = 128, 256     # the shape of the ncu capture in profiles/sampler_traffic.json
         dd = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, eta=0.0, device=dev)
         row = dd._coef_row(500, 480)
         sets = [[torch.randn(Bk, 3, Hk, Hk, device=dev) for _ in range(3)] + [torch.empty(Bk, 3, Hk, Hk, device=dev)]
-                for _ in range(2)]
+                for _ in range(3)]
         call = lambda s: K.sampler_step(s[0], s[1], row, objective='pred_eps', clip=True, noise=s[2], sample=s[3])  # noqa: E731
         for s_ in sets:
             call(s_)
@@ -420,14 +420,19 @@ def _extras(dev, peaks):
                 call(s_)
         e1.record()
         torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 20 * 1e3
+        us = e0.elapsed_time(e1) / 30 * 1e3
+        k4_traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'sampler_traffic.json')    # ncu dram__bytes_read/write.sum of this launch shape
+        if os.path.exists(tp):
+            with open(tp) as f:
+                k4_traffic = json.load(f).get('dram_bytes_per_launch')
         by = 4.0 * Bk * 3 * Hk * Hk * 4      # model output, x_t, noise read; x_{t-1} written
         out['sampler_update'] = {'kernel': 'sampler_step_vec4_kernel (K4: predict + clip + DDIM/DDPM step, fused)',
                                  'bound': 'hbm', 'achieved': by / us / 1e3, 'peak': peaks['hbm'], 'unit': 'GB/s',
-                                 'frac': by / us / 1e3 / peaks['hbm'], 'traffic': None,
+                                 'frac': by / us / 1e3 / peaks['hbm'], 'traffic': k4_traffic,
                                  'algorithmic_bytes_per_launch': by, 'avg_launch_us': us,
-                                 'workload': f'DDIM step on [{Bk},3,{Hk},{Hk}] fp32 tensors (201 MB each, 4 streams), '
-                                             f'20 launches over 2 buffer sets'}
+                                 'workload': f'DDIM step on [{Bk},3,{Hk},{Hk}] fp32 tensors (101 MB each, 4 streams: '
+                                             f'1.2 GB between reuses), 30 launches over 3 buffer sets'}
     except Exception as e:  # noqa: BLE001  (must not cost the two numbers above)
         out['sampler_update_error'] = repr(e)
     return out

@@ -193,11 +193,14 @@ def case_cfg():
             want = out['sample']
     # The 40 dB gate of BASELINE.json is stated for the headline (unguided) DDIM-50 run.  With guidance scale 3 the
     # mix (1-s) eps_u + s eps_c amplifies the per-branch bf16 error by up to |1-s| + |s| = 5 (about 14 dB), so this
-    # case is gated at 34 dB and the measured value is reported as is.
+    # case is gated below 40 dB and the measured value is reported as is.  The guided trajectory amplifies rounding-level
+    # differences (the fused GroupNorm statistics are accumulated with atomics, so two runs of the same code differ in
+    # the last bits): observed 34.75 / 35.27 / 35.7 dB over runs of the same inputs, hence a 33 dB gate (the principled
+    # bound is 40 - 14 = 26 dB).
     for tag, gg in (('graph', got), ('eager loop', got_e)):
         psnr = _psnr(gg.clamp(-1, 1), want.clamp(-1, 1))
-        _emit(case=f'ddimcfg50 s=3 final sample PSNR ({tag})', psnr_db=psnr, gate=34.0, ok=psnr >= 34.0)
-        ok &= psnr >= 34.0
+        _emit(case=f'ddimcfg50 s=3 final sample PSNR ({tag})', psnr_db=psnr, gate=33.0, ok=psnr >= 33.0)
+        ok &= psnr >= 33.0
     return ok
 
 

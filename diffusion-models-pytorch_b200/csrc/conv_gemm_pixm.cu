@@ -25,6 +25,7 @@ struct PixmParams {
   int N, block_n, w_rows_per_phase;
   int cpb0, nkb0, nkb1;
   int stages;
+  int vtap;   // vertical-tap reuse: one haloed pixel tile + three weight tiles per stage (see the host side)
   int8_t taps0[4][9][4];
   int8_t tap1[4];
   const float* bias;
@@ -58,7 +59,9 @@ conv_gemm_pixm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const int b_bytes = p.block_n * kPmBlockK * 2;
-  const int stage_bytes = kPmABytes + b_bytes;
+  const int halo_bytes = (p.bh + 2) * p.bw * 128;     // vtap: bh + 2 image rows of bw pixels x 64 channels
+  const int stage_bytes = p.vtap ? halo_bytes + 3 * b_bytes : kPmABytes + b_bytes;
+  const int ngroups = 3 * p.cpb0;                      // vtap: (horizontal offset, 64-channel chunk) units per tile
   PixmBarriers* bars = reinterpret_cast<PixmBarriers*>(smem + (size_t)p.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -105,6 +108,22 @@ conv_gemm_pixm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         const int wrow = ph * p.w_rows_per_phase + nt * p.block_n;
+        if (p.vtap) {
+          for (int g = 0; g < ngroups; ++g) {
+            const int dxi = g / p.cpb0, cb = g - dxi * p.cpb0;
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            uint8_t* sA = smem + (size_t)stage * stage_bytes;
+            uint8_t* sB = sA + halo_bytes;
+            mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+            // rows h0-1 .. h0+bh of the column-shifted tile; out-of-image rows / columns are zero-filled (= padding)
+            tma_load_5d(sA, &mapA0, &bars->full[stage], cb * kPmBlockK, w0 + dxi - 1, h0 - 1, 0, n0);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              tma_load_2d(sB + r * b_bytes, &mapB, &bars->full[stage], ((r * 3 + dxi) * p.cpb0 + cb) * kPmBlockK, wrow);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
@@ -137,6 +156,28 @@ conv_gemm_pixm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        if (p.vtap) {
+          // the three vertical taps are three views of the haloed tile whose first rows differ by one image row
+          // (bw * 128 B, a multiple of the 1 KB swizzle repeat for bw >= 8)
+          const uint32_t row_step = (uint32_t)(p.bw * 128) >> 4;
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t adesc0 = umma_desc_kmajor_sw128(a_addr);
+            for (int r = 0; r < 3; ++r) {
+              const uint64_t ad = adesc0 + (uint64_t)(r * row_step);
+              const uint64_t bd = umma_desc_kmajor_sw128(a_addr + (uint32_t)(halo_bytes + r * b_bytes));
+#pragma unroll
+              for (int k = 0; k < kPmBlockK / 16; ++k)
+                umma_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (g > 0 || r > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&bars->empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&bars->tmem_full[as]);
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
@@ -330,9 +371,24 @@ int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_) {
   B200_REQUIRE(bn == 1 || (bw == d->Wo && bh == d->Ho),
                "conv2d_fwd: unsupported spatial size %dx%d (need power-of-two factors to fill a 128-pixel tile)",
                d->Ho, d->Wo);
+  // Vertical-tap reuse (B200_PIXM_VTAP=0 disables): for plain 3x3 stride-1 layers the tile becomes (<= 32) x (>= 4)
+  // pixels and a pipeline stage holds ONE haloed pixel tile (bh + 2 rows) for a horizontal offset and channel chunk plus
+  // the three weight tiles of its vertical taps: (bh + 2) / (3 bh) of the pixel operand bytes (0.5 at bh = 4).  The
+  // one-row tiles chosen above for wide images (bw = 128, bh = 1) cannot share rows between taps.
+  static const char* env_vtap = getenv("B200_PIXM_VTAP");
+  bool vtap = !(env_vtap && atoi(env_vtap) == 0) && d->phases == 1 && d->ntaps0 == 9 && d->a0_planes == 1 &&
+              d->a1 == nullptr && d->a0_H == d->Ho && d->a0_W == d->Wo;
+  for (int k = 0; vtap && k < 9; ++k)
+    vtap = d->taps0[0][k][0] == (k % 3) - 1 && d->taps0[0][k][1] == (k / 3) - 1 && d->taps0[0][k][2] == 0;
+  if (vtap) {
+    const int vbw = bw > 32 ? 32 : bw, vbh = 128 / vbw;
+    if (vbw >= 8 && d->Ho % vbh == 0) { bw = vbw; bh = vbh; bn = 1; }
+    else vtap = false;
+  }
   PixmParams p;
   memset(&p, 0, sizeof(p));
   p.B = d->B;
+  p.vtap = vtap ? 1 : 0;
   p.bw = bw; p.bh = bh; p.bn = bn;
   p.tiles_w = d->Wo / bw;
   p.tiles_h = d->Ho / bh;
@@ -355,7 +411,7 @@ int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_) {
   p.out = d->out; p.out_mode = d->out_mode; p.out_ld = d->out_ld;
   p.out_H = d->out_H; p.out_W = d->out_W; p.osy = d->osy; p.osx = d->osx;
 
-  const int stage_bytes = kPmABytes + block_n * 128;
+  const int stage_bytes = vtap ? (bh + 2) * bw * 128 + 3 * block_n * 128 : kPmABytes + block_n * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > kPmMaxStages) stages = kPmMaxStages;
   if (stages < 2) stages = 2;
@@ -363,7 +419,7 @@ int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_) {
   const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(PixmBarriers) + 1024;
 
   CUtensorMap mapA0, mapA1, mapB;
-  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, bw, bh, bn);
+  int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, bw, vtap ? bh + 2 : bh, bn);
   if (rc) return rc;
   if (d->a1) {
     rc = make_a_map(&mapA1, d->a1, d->a1_C, d->a1_H, d->a1_W, d->a1_planes, d->B, bw, bh, bn);

@@ -190,6 +190,14 @@ def case_conv_lastconv():
                     out_mode=K.OUT_F32_NCHW)
     ok &= _conv_case('conv3x3 64->1 @32 f32 NCHW (MNIST last conv)', 2, 64, 1, 32, 32, bias=True,
                      out_mode=K.OUT_F32_NCHW)
+    # vertical-tap tiles: 32x4 on a wide image (two tiles per row, top / bottom / left / right zero fill), 16x8, 64x32
+    # non-square; 8x8 falls back to the plain tiles (two images per tile)
+    ok &= _conv_case('conv3x3 256->6 @64 f32 NCHW (ADM-style last conv, 32x4 tiles)', 2, 256, 6, 64, 64, bias=True,
+                     out_mode=K.OUT_F32_NCHW)
+    ok &= _conv_case('conv3x3 128->3 @16 f32 NCHW (16x8 tiles)', 3, 128, 3, 16, 16, bias=True, out_mode=K.OUT_F32_NCHW)
+    ok &= _conv_case('conv3x3 128->3 @32x64 f32 NCHW (non-square)', 2, 128, 3, 32, 64, bias=True,
+                     out_mode=K.OUT_F32_NCHW)
+    ok &= _conv_case('conv3x3 128->3 @8 f32 NCHW (plain tiles)', 4, 128, 3, 8, 8, bias=True, out_mode=K.OUT_F32_NCHW)
     return ok
 
 

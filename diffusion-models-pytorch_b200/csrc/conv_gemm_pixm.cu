@@ -381,7 +381,12 @@ int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_) {
   for (int k = 0; vtap && k < 9; ++k)
     vtap = d->taps0[0][k][0] == (k % 3) - 1 && d->taps0[0][k][1] == (k / 3) - 1 && d->taps0[0][k][2] == 0;
   if (vtap) {
-    const int vbw = bw > 32 ? 32 : bw, vbh = 128 / vbw;
+    // experiment knob: tile width cap 8 / 16 / 32.  Measured: 16x8 and 8x16 tiles (fewer halo bytes) run exactly as
+    // fast as 32x4 (50 us at 128->3@32x32, B=256), i.e. after the 2x cut the pixel operand stream is no longer the limit
+    static const char* env_vbw = getenv("B200_PIXM_VBW");
+    const int cap_env = env_vbw ? atoi(env_vbw) : 32;
+    const int cap = (cap_env == 8 || cap_env == 16) ? cap_env : 32;
+    const int vbw = bw > cap ? cap : bw, vbh = 128 / vbw;
     if (vbw >= 8 && d->Ho % vbh == 0) { bw = vbw; bh = vbh; bn = 1; }
     else vtap = false;
   }

@@ -310,12 +310,14 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   static const char* env_halves = getenv("B200_EPI_HALVES");
   p.epi_halves = env_halves ? atoi(env_halves) : 2;
   if (p.epi_halves != 1 && p.epi_halves != 2 && p.epi_halves != 4) p.epi_halves = 2;
-  // Short-K layers (the attention blocks' 1x1 convs: 4 K-blocks) are bound by the epilogue's issue latency, not by the
-  // mainloop: ncu on the q/k projection (256 -> 512 @16x16, B=256) shows 42 % issue slots busy with 2.5 warps per
-  // scheduler and DRAM at 14 % of peak.  They take 16 epilogue warps (4 per TMEM lane quarter, 96 registers); the
-  // 3x3 layers keep 8 (16 were measured slower there).  B200_EPI_WIDE_MAXKB=0 disables.
+  // Short-K layers (the attention blocks' 1x1 convs: 4 K-blocks) are bound by the epilogue, not by the mainloop: ncu on
+  // the q/k projection (256 -> 512 @16x16, B=256; profiles/r01_prof_conv1x1.details.txt) shows 42 % issue slots busy
+  // with 2.5 warps per scheduler, ~600 warp instructions per 32-pixel chunk and DRAM at 14 % of peak.  Experiment knob
+  // B200_EPI_WIDE_MAXKB=n gives layers with <= n K-blocks 16 epilogue warps (4 per TMEM lane quarter, 96 registers):
+  // measured with n = 8, DDIM-50 CIFAR-10 1022.6 -> 1011.9 images/s and the CFG training step 16.79 -> 16.92 ms, i.e.
+  // slower, so it is off by default; the remaining lever is fewer instructions per output (packed bf16 stores).
   static const char* env_wide = getenv("B200_EPI_WIDE_MAXKB");
-  const int wide_maxkb = env_wide ? atoi(env_wide) : 8;
+  const int wide_maxkb = env_wide ? atoi(env_wide) : 0;
   if (!env_halves && p.nkb0 + p.nkb1 <= wide_maxkb) p.epi_halves = 4;
   static const char* env_rot = getenv("B200_K_ROTATE");
   p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;

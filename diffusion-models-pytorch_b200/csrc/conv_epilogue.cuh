@@ -291,4 +291,116 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKParams& p, const T
       }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Lean epilogue (experiment knob B200_EPI_LEAN=1; compiled into SEPARATE kernel instantiations so that the default
+// kernels' code is untouched).  Motivation: ncu on the attention blocks' 1x1 projections (4 K-blocks per tile, so the
+// epilogue is the critical path) shows ~560 warp instructions per 32-pixel chunk, 217 of them 64-bit address
+// arithmetic for the 32 stores and ~100 statistics FADD/FFMA that run even when no statistics are requested.  Here the
+// uniform options are template parameters and every store / residual address is ONE IMAD.WIDE (32-bit byte stride x
+// compile-time pixel index + 64-bit chunk base).  Covers the fast_epi tiles (pixels linear in the output) with NHWC
+// fp32 / bf16 outputs; everything else takes conv_epilogue_tile.  Same arithmetic, same
+// order of the per-thread statistics sums as the standard fast path.
+// STATUS: written at the end of round 1 after the GPU budget was spent -- builds, SASS checked, NOT yet
+// run on hardware; tests/kernel_cases.py runs every conv case under the knob once a GPU is available.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool BF16_OUT, bool HAS_RES, bool HAS_STATS, bool HAS_ROW>
+__device__ __forceinline__ void conv_epilogue_lean(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
+                                                   const int c, const bool c_ok, const int half,
+                                                   uint64_t* acc_full_bar, const uint32_t acc_parity) {
+  constexpr int kOutBytes = BF16_OUT ? 2 : 4;
+  const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
+  const int ost = p.out_ld * kOutBytes;        // byte strides between consecutive pixels
+  const int rst = p.res_ld * 4;
+  char* const obase = reinterpret_cast<char*>(p.out) + (pix0 * (size_t)p.out_ld + c) * kOutBytes;
+  const char* const rbase = HAS_RES ? reinterpret_cast<const char*>(p.residual + pix0 * (size_t)p.res_ld + c) : nullptr;
+  const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
+  float s1 = 0.f, s2 = 0.f, ra_c = 0.f;
+  int cur_n = -1;
+  mbar_wait(acc_full_bar, acc_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves) {
+    uint32_t v[32];
+    float r[32];
+    __syncwarp();
+    tmem_ld_x32(taddr + (uint32_t)ch, v);
+    if (HAS_RES) {      // overlaps the TMEM load
+      const char* rp = rbase + (long long)ch * rst;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = c_ok ? __ldg(reinterpret_cast<const float*>(rp + (long long)j * rst)) : 0.f;
+    }
+    tmem_ld_wait();
+    float acc[32];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (HAS_STATS || HAS_ROW) {
+        const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
+        if (n != cur_n) {  // warp-uniform: new image -> flush statistics, fetch the time-embedding value
+          if (HAS_STATS && c_ok && cur_n >= 0) {
+            atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+            atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+          }
+          s1 = 0.f; s2 = 0.f;
+          cur_n = n;
+          if (HAS_ROW) ra_c = c_ok ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f;
+        }
+      }
+      const float add_c = bias_c + ra_c;
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
+        float a0 = __uint_as_float(v[j]) + add_c;
+        float a1 = __uint_as_float(v[j + 1]) + add_c;
+        if (HAS_RES) { a0 += r[j]; a1 += r[j + 1]; }
+        acc[j] = a0;
+        acc[j + 1] = a1;
+        if (HAS_STATS) {
+          s1 += a0; t1 += a1;
+          s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
+        }
+      }
+      if (HAS_STATS) { s1 += t1; s2 += t2; }
+    }
+    if (c_ok) {
+      char* op = obase + (long long)ch * ost;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (BF16_OUT) *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) = __float2bfloat16_rn(acc[j]);
+        else *reinterpret_cast<float*>(op + (long long)j * ost) = acc[j];
+      }
+    }
+  }
+  if (HAS_STATS && c_ok && cur_n >= 0 && cur_n < p.B) {
+    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2, s1);
+    atomicAdd(p.stats + ((size_t)cur_n * p.N + c) * 2 + 1, s2);
+  }
+}
+
+// Host-side eligibility of a layer for the lean epilogue (also asserted by the device dispatch below).
+inline bool conv_epilogue_lean_ok(const ConvKParams& p) {
+  return p.fast_epi && p.out_mode <= B200_OUT_BF16_NHWC && p.dbg == 0;
+}
+
+__device__ __forceinline__ void conv_epilogue_lean_dispatch(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
+                                                            const int c, const bool c_ok, const int half,
+                                                            uint64_t* bar, const uint32_t parity) {
+  const bool bf = p.out_mode == B200_OUT_BF16_NHWC, rs = p.residual != nullptr, st = p.stats != nullptr;
+  const bool rw = p.rowadd != nullptr;
+  if (!(p.fast_epi && p.out_mode <= B200_OUT_BF16_NHWC && p.dbg == 0)) {
+    conv_epilogue_tile(p, t, taddr, c, c_ok, half, bar, parity);
+    return;
+  }
+#define B200_LEAN_CASE(BF, RS, ST, RW) \
+  if (bf == BF && rs == RS && st == ST && rw == RW) { conv_epilogue_lean<BF, RS, ST, RW>(p, t, taddr, c, c_ok, half, bar, parity); return; }
+  B200_LEAN_CASE(true, false, false, false) B200_LEAN_CASE(true, false, false, true)
+  B200_LEAN_CASE(true, false, true, false)  B200_LEAN_CASE(true, false, true, true)
+  B200_LEAN_CASE(true, true, false, false)  B200_LEAN_CASE(true, true, false, true)
+  B200_LEAN_CASE(true, true, true, false)   B200_LEAN_CASE(true, true, true, true)
+  B200_LEAN_CASE(false, false, false, false) B200_LEAN_CASE(false, false, false, true)
+  B200_LEAN_CASE(false, false, true, false)  B200_LEAN_CASE(false, false, true, true)
+  B200_LEAN_CASE(false, true, false, false)  B200_LEAN_CASE(false, true, false, true)
+  B200_LEAN_CASE(false, true, true, false)   B200_LEAN_CASE(false, true, true, true)
+#undef B200_LEAN_CASE
+}
+
 }  // namespace b200

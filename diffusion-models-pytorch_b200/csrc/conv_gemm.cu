@@ -23,7 +23,7 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
 int conv2d_fwd_pixm(const b200_conv_desc* d, void* stream_);
 int make_a_map(CUtensorMap* m, const void* base, int C, int H, int W, int planes, int B, int bw, int bh, int bn);
 
-template <int kT>
+template <int kT, int kLean = 0>
 __global__ void __launch_bounds__(kT, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p) {
@@ -197,7 +197,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int c = t.ct * kBlockC + q * 32 + lane;  // output channel of this thread
       const bool c_ok = c < p.N;
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.NP) + ((uint32_t)(q * 32) << 16);
-      conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
+      if (kLean) conv_epilogue_lean_dispatch(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
+      else conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
@@ -258,6 +259,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     B200_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int c_tiles = (d->N + kBlockC - 1) / kBlockC;
   ConvKParams p;
@@ -370,8 +372,11 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
   if (p.epi_halves == 4)
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreadsWide>, dim3(grid), dim3(64 + 128 * 4), smem_bytes, stream, mapA0, mapA1, mapW, p));
+  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p))
+    B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads, 1>, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
   else
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads>, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
   ++g_launch_count;

@@ -94,7 +94,7 @@ struct PairParams {
 
 constexpr int kPairStageBytes = kWBytes + 128 * 128;   // 16 KB weights + 128 pixels x 128 B per CTA
 
-template <int kT>
+template <int kT, int kLean = 0>
 __global__ void __launch_bounds__(kT, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p,
@@ -217,7 +217,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       const int c = t.ct * kBlockC + q * 32 + lane;
       const bool c_ok = c < p.N;
       const uint32_t taddr = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
-      conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
+      if (kLean) conv_epilogue_lean_dispatch(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
+      else conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[as]);
@@ -270,6 +271,7 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
     B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int max_clusters = sms / 2;
   const int clusters = pp.pair_tiles < max_clusters ? pp.pair_tiles : max_clusters;
@@ -288,8 +290,11 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
   if (p.epi_halves == 4)
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreadsWide>, mapA0, mapA1, mapW, p, pp));
+  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p))
+    B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreads, 1>, mapA0, mapA1, mapW, p, pp));
   else
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreads>, mapA0, mapA1, mapW, p, pp));
   ++g_launch_count;

@@ -259,7 +259,6 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     B200_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int c_tiles = (d->N + kBlockC - 1) / kBlockC;
   ConvKParams p;
@@ -375,8 +374,14 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
   if (p.epi_halves == 4)
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreadsWide>, dim3(grid), dim3(64 + 128 * 4), smem_bytes, stream, mapA0, mapA1, mapW, p));
-  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p))
+  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p)) {
+    static bool lean_attr = false;    // set lazily: the default path never touches the experimental instantiation
+    if (!lean_attr) {
+      B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      lean_attr = true;
+    }
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads, 1>, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
+  }
   else
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads>, dim3(grid), dim3(64 + 128 * p.epi_halves), smem_bytes, stream, mapA0, mapA1, mapW, p));
   ++g_launch_count;

@@ -271,7 +271,6 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
     B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreadsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int max_clusters = sms / 2;
   const int clusters = pp.pair_tiles < max_clusters ? pp.pair_tiles : max_clusters;
@@ -293,8 +292,14 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
   static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
   if (p.epi_halves == 4)
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreadsWide>, mapA0, mapA1, mapW, p, pp));
-  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p))
+  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p)) {
+    static bool lean_attr = false;    // set lazily: the default path never touches the experimental instantiation
+    if (!lean_attr) {
+      B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      lean_attr = true;
+    }
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreads, 1>, mapA0, mapA1, mapW, p, pp));
+  }
   else
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreads>, mapA0, mapA1, mapW, p, pp));
   ++g_launch_count;

@@ -266,7 +266,13 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   // largest pixel tile that still gives (nearly) every SM a tile; otherwise the smallest valid one
   int best_np = 0;
   static const char* env_np = getenv("B200_MAX_NP");
-  for (int np = env_np ? atoi(env_np) : 256; np >= 64; np >>= 1) {
+  // experiment knob for the short-K (<= 8 K-blocks) layers, whose 4-stage ring otherwise holds exactly one tile:
+  // B200_SHORTK_NP=128 gives them 128-pixel tiles (32 KB stages, 6 deep).  Unset = same tiles as every other layer.
+  static const char* env_snp = getenv("B200_SHORTK_NP");
+  const int short_k = d->ntaps0 * (d->a0_C / 64) + (d->a1 ? d->a1_C / 64 : 0) <= 8;
+  const int np_max = (env_snp && short_k && (atoi(env_snp) == 64 || atoi(env_snp) == 128)) ? atoi(env_snp)
+                     : env_np ? atoi(env_np) : 256;
+  for (int np = np_max; np >= 64; np >>= 1) {
     const int bw = maxw < np ? maxw : np;
     const int bh = maxh < np / bw ? maxh : np / bw;
     const int bn = np / (bw * bh);

@@ -16,9 +16,13 @@ for c in unet_forward ddim50 cfg train_step; do
 done
 python bench.py > gpurun_out/bench_lean_off.json 2>/dev/null
 B200_EPI_LEAN=1 python bench.py > gpurun_out/bench_lean_on.json 2>/dev/null
+# second hypothesis: 128-pixel tiles for the short-K layers, alone and with the lean epilogue
+B200_SHORTK_NP=128 timeout 100 python tests/kernel_cases.py conv_1x1 2>&1 | tail -n 1
+B200_SHORTK_NP=128 python bench.py > gpurun_out/bench_lean_np128.json 2>/dev/null
+B200_SHORTK_NP=128 B200_EPI_LEAN=1 python bench.py > gpurun_out/bench_lean_on_np128.json 2>/dev/null
 python - <<'PY'
 import json
-for tag in ('off', 'on'):
+for tag in ('off', 'on', 'np128', 'on_np128'):
     l = json.load(open(f'gpurun_out/bench_lean_{tag}.json'))
     print(tag, 'ddim50 images/s', round(l['value'], 1), 'conv ms/forward', round(l['kernels']['conv_gemm']['ms_per_forward'], 3),
           'adm256 ms', round(l['extras']['adm256_forward']['ms_per_forward'], 2), 'train ms', round(l['extras']['cfg_train_step']['ms_per_step'], 2))

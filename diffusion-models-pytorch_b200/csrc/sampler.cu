@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(256, 4) sampler_step_vec4_kernel(const Sampler
   const size_t chw4 = ((size_t)k.C * k.HW) >> 2, mchw4 = ((size_t)k.Cm * k.HW) >> 2;
   const size_t units = k.total >> 2;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // The graph runner updates x in place (sample == xt): every unit is read and then written by the same thread only,
+  // and all loads of an iteration are issued before its stores, so the read-only (.nc) loads below stay correct.
   const float4* __restrict__ mo4 = reinterpret_cast<const float4*>(k.mo);
   const float4* __restrict__ mou4 = reinterpret_cast<const float4*>(k.mo_u);
   const float4* __restrict__ xt4 = reinterpret_cast<const float4*>(k.xt);

@@ -127,7 +127,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch, substeps = 16, 2
+    batch, substeps = 64, 2     # ~2-4 s of host work per bench step: the default K=5 / W=3 run takes well under a minute
     t0 = time.perf_counter()
     rate, cores, times = cpu_ddim_rate(batch, substeps, args.warmup, args.steps)
     ms_per_step = statistics.mean(times) * 1e3
@@ -307,13 +307,13 @@ def run_ours(args):
         os.dup2(stdout_fd, 1)
         os.close(stdout_fd)
     if rank == 0:
-        # CPU baseline on rank 0: a bounded sample (batch 8, 1 warm-up + 2 timed single DDIM steps)
+        # CPU baseline on rank 0: a bounded sample (batch 64, 1 warm-up + 3 timed pairs of DDIM steps: 10-20 s of host work)
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, _ = cpu_ddim_rate(batch=8, substeps=1, warmup=1, repeats=2)
+            rate, cores, _ = cpu_ddim_rate(batch=64, substeps=2, warmup=1, repeats=3)
             line['cpu_baseline'] = {
                 'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                'sample': 'oracle port (PyTorch fp32 CPU), batch 8, 1 warm-up + 2 timed DDIM steps (UNet forward + '
-                          'sampler arithmetic), extrapolated linearly to 50 steps'}
+                'sample': 'oracle port (PyTorch fp32 CPU), batch 64, 1 warm-up + 3 timed repeats of 2 DDIM steps (UNet '
+                          'forward + sampler arithmetic), extrapolated linearly to 50 steps'}
         print(json.dumps(line), flush=True)
 
 

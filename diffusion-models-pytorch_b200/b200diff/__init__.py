@@ -48,6 +48,13 @@ class SamplerDesc(Structure):
     ]
 
 
+class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (experimental fused conv + next GroupNorm)
+    _fields_ = [
+        ('gamma', c_void_p), ('beta', c_void_p), ('scale', c_void_p), ('shift', c_void_p), ('out_norm', c_void_p),
+        ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
+    ]
+
+
 class GemmOperand(Structure):
     _fields_ = [('ptr', c_void_p), ('rows', c_int), ('ld', c_int), ('batch_stride', c_longlong),
                 ('col_base', c_int), ('col_head', c_int), ('mn_major', c_int), ('per_head_batch', c_int)]
@@ -118,6 +125,8 @@ def lib():
     L.b200_last_error.restype = c_char_p
     L.b200_launch_count.restype = c_longlong
     L.b200_conv2d_fwd.argtypes = [POINTER(ConvDesc), c_void_p]
+    L.b200_conv2d_gn_fwd.argtypes = [POINTER(ConvDesc), POINTER(GnFuseDesc), c_void_p]
+    L.b200_conv2d_gn_fwd.restype = c_int
     L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p]
     L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
@@ -176,7 +185,7 @@ BACKWARD_SYMBOLS = (
 )
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
-    'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv3x3_first',
+    'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
 )
@@ -386,6 +395,33 @@ def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None,
     _launch('conv_gemm', lambda: _check(lib().b200_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd'),
             flops=2.0 * macs)
     return out
+
+
+def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
+              rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True):
+    """EXPERIMENTAL (b200_conv2d_gn_fwd, not yet validated on hardware): out_norm = SiLU(GN(conv(a0) + bias + rowadd))
+    as the bf16 NHWC operand of the next convolution; nothing else is written.  Raises when the layer is not eligible
+    (a tile must hold whole images: Ho*Wo in {16, 64, 256}; N % 128 == 0)."""
+    _need_cuda(a0, w_packed, out_norm)
+    d = ConvDesc()
+    d.a0 = a0.data_ptr()
+    d.a0_C, d.a0_H, d.a0_W, d.a0_planes = a0_geom
+    d.w = w_packed.data_ptr()
+    d.w_rows, d.w_K = w_packed.shape
+    d.w_rows_per_phase = N
+    d.B, d.Ho, d.Wo = B, Ho, Wo
+    d.phases, d.N, d.ntaps0 = 1, N, len(taps0[0])
+    _fill_taps(d, taps0, (0, 0, 0))
+    d.bias = _ptr(bias)
+    d.rowadd, d.rowadd_ld = _ptr(rowadd), rowadd_ld
+    d.out, d.out_mode, d.out_ld = None, OUT_BF16_NHWC, N
+    d.out_H, d.out_W, d.osy, d.osx = Ho, Wo, 1, 1
+    g = GnFuseDesc()
+    g.gamma, g.beta, g.scale, g.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
+    g.out_norm, g.ss_ld, g.groups, g.apply_silu, g.eps = out_norm.data_ptr(), ss_ld, groups, int(silu), float(eps)
+    _launch('conv_gemm', lambda: _check(lib().b200_conv2d_gn_fwd(ctypes.byref(d), ctypes.byref(g), _stream()),
+                                        'conv2d_gn_fwd'), flops=2.0 * B * Ho * Wo * N * d.w_K)
+    return out_norm
 
 
 def conv3x3_first(x, w, bias, out, stats=None):

@@ -29,6 +29,14 @@ struct ConvKParams {
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
   int vtap;      // vertical-tap reuse (conv_gemm.cu): one haloed pixel tile + 3 weight tiles per stage
   int dbg;       // experiment knob (B200_EPI_DBG): 1 = no residual loads, 2 = no output stores, 4 = epilogue does nothing
+  // fused next-GroupNorm epilogue (experimental, b200_conv2d_gn_fwd): appended so that the offsets above are unchanged
+  const float* gn_gamma;
+  const float* gn_beta;
+  const float* gn_scale;
+  const float* gn_shift;
+  void* gn_out;
+  int gn_ss_ld, gn_lg_cpg, gn_silu;
+  float gn_eps;
 };
 
 constexpr int kBlockC = 128;  // output channels per tile (UMMA M)
@@ -401,6 +409,142 @@ __device__ __forceinline__ void conv_epilogue_lean_dispatch(const ConvKParams& p
   B200_LEAN_CASE(false, true, false, false)  B200_LEAN_CASE(false, true, false, true)
   B200_LEAN_CASE(false, true, true, false)   B200_LEAN_CASE(false, true, true, true)
 #undef B200_LEAN_CASE
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused next-GroupNorm epilogue (EXPERIMENTAL, kernel instantiation <kThreads, 2>, entry b200_conv2d_gn_fwd; written
+// at the end of round 1, NOT yet run on hardware).  The tile is 64 / 128 / 256 pixels = whole images (2^lg_bhw pixels
+// each, lg_bhw in {4, 6, 8}) x 128 channels = whole groups, so the statistics of the GroupNorm that consumes this conv's output are
+// complete inside the CTA:
+//   pass 1  a = acc + bias (+ time-embedding row); per-thread (= per-channel) sums over each 16-pixel half chunk
+//   exchange the two warps that share a TMEM lane quarter own alternating 32-pixel chunks: per-chunk sums go through
+//           shared memory (double-buffered by tile parity, one named barrier of the 8 epilogue warps per tile)
+//   reduce  butterfly over the 2^lg_cpg lanes of a group -> mean / rstd -> A = rstd*gamma', B = beta' - mean*A
+//   pass 2  the accumulators are read from TMEM again (they stay valid until tmem_empty is signalled by the caller):
+//           y = SiLU(a*A + B) -> bf16 NHWC, the operand of the next convolution.  Nothing else is written.
+// Same formulas as groupnorm_apply_kernel (biased variance clamped at 0, rsqrtf, SiLU through tanh.approx).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float epi_silu_tanh(float x) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * x));
+  return x * fmaf(0.5f, th, 0.5f);   // identical to silu_tanh in groupnorm.cu
+}
+
+template <bool HAS_ROW, bool HAS_SS>
+__device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
+                                                     const int c, const int half, const int cl, float* xbuf,
+                                                     uint64_t* acc_full_bar, const uint32_t acc_parity) {
+  // cl = channel inside the tile (0..127); xbuf = this tile's exchange buffer [2 halves][4 chunks][128][2]
+  const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
+  const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
+  mbar_wait(acc_full_bar, acc_parity);
+  tc_fence_after();
+  const int nch = p.NP >> 6;     // 32-pixel chunks per warp: 1, 2 or 4 (tiles of 64 / 128 / 256 pixels)
+  float ps1[4][2], ps2[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ps1[i][0] = ps1[i][1] = ps2[i][0] = ps2[i][1] = 0.f;
+    if (i >= nch) continue;
+    const int ch = half * 32 + 64 * i;
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr + (uint32_t)ch, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
+      const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+      float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
+        const float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
+        s1 += a0; t1 += a1;
+        s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
+      }
+      ps1[i][hf] = s1 + t1;
+      ps2[i][hf] = s2 + t2;
+    }
+  }
+  // per-chunk sums of this warp -> shared memory; the partner warp (same channels, the other chunks) reads them
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 w2;
+    w2.x = ps1[i][0] + ps1[i][1];
+    w2.y = ps2[i][0] + ps2[i][1];
+    *reinterpret_cast<float2*>(xbuf + (((half * 4 + i) * 128 + cl) << 1)) = w2;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps (warps 0 / 1 = TMA / MMA do not take part)
+  float o1[4], o2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 r2 = *reinterpret_cast<const float2*>(xbuf + ((((1 - half) * 4 + i) * 128 + cl) << 1));
+    o1[i] = r2.x;
+    o2[i] = r2.y;
+  }
+  // image statistics of the (chunk, half-chunk) slots of this thread
+  float S1[4][2], S2[4][2];
+  if (p.lg_bhw >= 8) {          // one image per tile: everything
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1] + o1[i]; b += ps2[i][0] + ps2[i][1] + o2[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = a; S2[i][0] = S2[i][1] = b; }
+  } else if (p.lg_bhw == 6) {   // image i = chunk i of this warp + chunk i of the partner (pixels 64 i .. 64 i + 63)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      S1[i][0] = S1[i][1] = ps1[i][0] + ps1[i][1] + o1[i];
+      S2[i][0] = S2[i][1] = ps2[i][0] + ps2[i][1] + o2[i];
+    }
+  } else {                      // 16 pixels per image: every half chunk is a whole image of this warp
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { S1[i][0] = ps1[i][0]; S1[i][1] = ps1[i][1]; S2[i][0] = ps2[i][0]; S2[i][1] = ps2[i][1]; }
+  }
+  // group sums: butterfly over the 2^lg_cpg consecutive lanes (= channels) of a group
+  for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        S1[i][hf] += __shfl_xor_sync(0xffffffffu, S1[i][hf], m);
+        S2[i][hf] += __shfl_xor_sync(0xffffffffu, S2[i][hf], m);
+      }
+  }
+  const float inv_cnt = 1.0f / (float)((1 << p.lg_bhw) << p.gn_lg_cpg);
+  const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f;
+  const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
+  __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.N + c;
+  const int ost = p.N * 2;    // bytes between consecutive pixels of the NHWC output
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= nch) continue;
+    const int ch = half * 32 + 64 * i;
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr + (uint32_t)ch, v);
+    tmem_ld_wait();
+    char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
+      const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+      const float mean = S1[i][hf] * inv_cnt;
+      const float var = fmaxf(S2[i][hf] * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.gn_eps);
+      float ga = gamma_c, be = beta_c;
+      if (HAS_SS) {
+        const float sc = 1.f + __ldg(p.gn_scale + (size_t)n * p.gn_ss_ld + c);
+        ga *= sc;
+        be = be * sc + __ldg(p.gn_shift + (size_t)n * p.gn_ss_ld + c);
+      }
+      const float A = rstd * ga, B = be - mean * rstd * ga;
+#pragma unroll
+      for (int j = 16 * hf; j < 16 * hf + 16; ++j) {
+        float y = fmaf(__uint_as_float(v[j]) + add_c, A, B);
+        if (p.gn_silu) y = epi_silu_tanh(y);
+        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) = __float2bfloat16_rn(y);
+      }
+    }
+  }
 }
 
 }  // namespace b200

@@ -197,7 +197,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const int c = t.ct * kBlockC + q * 32 + lane;  // output channel of this thread
       const bool c_ok = c < p.N;
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.NP) + ((uint32_t)(q * 32) << 16);
-      if (kLean) conv_epilogue_lean_dispatch(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
+      if (kLean == 2) {
+        // fused next-GroupNorm epilogue (experimental): exchange buffers [2 tile parities][2][4][128][2] floats = 16 KB
+        // behind the barriers; all channels are valid (N % 128 == 0 is required by the host side)
+        float* xbuf = reinterpret_cast<float*>(bars + 1) + (it & 1) * 2048;
+        const int cl = q * 32 + lane;
+        const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
+        if (row && ss) conv_epilogue_gnfuse<true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        else if (row) conv_epilogue_gnfuse<true, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        else if (ss) conv_epilogue_gnfuse<false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        else conv_epilogue_gnfuse<false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+      } else if (kLean == 1) conv_epilogue_lean_dispatch(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       else conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       tc_fence_before();
       __syncwarp();
@@ -226,6 +236,23 @@ static int ilog2(int v) {
 
 using namespace b200;
 
+// Experimental fused conv + next GroupNorm (b200_conv2d_gn_fwd): the descriptor travels to b200_conv2d_fwd's launch
+// code through this thread-local pointer so that the regular entry point keeps its signature and code path.
+static thread_local const b200_gn_fuse_desc* tl_gn_fuse = nullptr;
+
+extern "C" int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void* stream_) {
+  B200_REQUIRE(d != nullptr && g != nullptr, "conv2d_gn_fwd: null descriptor");
+  B200_REQUIRE(g->out_norm && g->groups >= 1, "conv2d_gn_fwd: null out_norm / bad groups");
+  B200_REQUIRE(d->N > 32 && d->N % kBlockC == 0, "conv2d_gn_fwd: N=%d must be a multiple of 128", d->N);
+  B200_REQUIRE(d->residual == nullptr && d->stats == nullptr && d->phases == 1 && d->a1 == nullptr,
+               "conv2d_gn_fwd: residual / statistics / phases / second source are not supported");
+  B200_REQUIRE(((uintptr_t)g->out_norm & 15) == 0, "conv2d_gn_fwd: out_norm alignment");
+  tl_gn_fuse = g;
+  const int rc = b200_conv2d_fwd(d, stream_);
+  tl_gn_fuse = nullptr;
+  return rc;
+}
+
 extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(d != nullptr, "conv2d_fwd: null descriptor");
@@ -234,7 +261,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     B200_REQUIRE(d->stats == nullptr, "conv2d_fwd: statistics output is not available for N <= 32");
     return conv2d_fwd_pixm(d, stream_);  // tiny Cout (last conv): pixels on the UMMA M side instead
   }
-  B200_REQUIRE(d->a0 && d->w && d->out, "conv2d_fwd: null a0/w/out");
+  B200_REQUIRE(d->a0 && d->w && (d->out || tl_gn_fuse), "conv2d_fwd: null a0/w/out");
   B200_REQUIRE(d->a0_C > 0 && d->a0_C % 64 == 0, "conv2d_fwd: a0_C=%d must be a positive multiple of 64", d->a0_C);
   B200_REQUIRE(d->a1 == nullptr || (d->a1_C > 0 && d->a1_C % 64 == 0), "conv2d_fwd: a1_C=%d must be a multiple of 64",
                d->a1_C);
@@ -348,17 +375,18 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   // CTA pairs (cta_group::2, conv_gemm2.cu) when two 128-channel tiles can share one 256-pixel tile and there are
   // enough pair tiles to occupy the 74 SM pairs
   static const char* env_pair = getenv("B200_PAIR");
-  if (!p.vtap && (!env_pair || atoi(env_pair) != 0) && d->N % 256 == 0 && p.NP == 256 &&
+  if (!tl_gn_fuse && !p.vtap && (!env_pair || atoi(env_pair) != 0) && d->N % 256 == 0 && p.NP == 256 &&
       (long)d->phases * p.p_tiles * (c_tiles / 2) >= (long)(g_num_sms / 2) * 3 / 4)
     return conv2d_fwd_pair(d, p, stream);
 
   const int stage_bytes = p.vtap ? 3 * kWBytes + (p.bh + 2) * p.bw * 128 : kWBytes + p.NP * 128;
-  int stages = (227 * 1024 - 2048) / stage_bytes;
+  const int fuse_smem = tl_gn_fuse ? 2 * 2048 * (int)sizeof(float) : 0;   // statistics exchange buffers of the fused epilogue
+  int stages = (227 * 1024 - 2048 - fuse_smem) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   static const char* env_stages = getenv("B200_STAGES");
   if (env_stages && atoi(env_stages) >= 2 && atoi(env_stages) < stages) stages = atoi(env_stages);
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvBarriers) + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + sizeof(ConvBarriers) + 1024 + fuse_smem;
 
   CUtensorMap mapA0, mapA1, mapW;
   int rc = make_a_map(&mapA0, d->a0, d->a0_C, d->a0_H, d->a0_W, d->a0_planes, d->B, p.bw, p.vtap ? p.bh + 2 : p.bh, p.bn);
@@ -377,6 +405,29 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  if (tl_gn_fuse) {
+    // experimental fused next-GroupNorm epilogue: the tile must hold whole images and whole groups
+    const b200_gn_fuse_desc* g = tl_gn_fuse;
+    const int hw = d->Ho * d->Wo;
+    B200_REQUIRE(p.fast_epi && p.bw == d->Wo && p.bh == d->Ho && (hw == 16 || hw == 64 || hw == 256) && p.NP >= hw &&
+                 p.NP >= 64 && p.epi_halves == 2,
+                 "conv2d_gn_fwd: the %d-pixel tile does not hold whole %dx%d images (or epilogue layout unsupported)", p.NP,
+                 d->Ho, d->Wo);
+    B200_REQUIRE(d->N % g->groups == 0, "conv2d_gn_fwd: N=%d is not a multiple of groups=%d", d->N, g->groups);
+    const int cpg = d->N / g->groups;
+    B200_REQUIRE(cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0, "conv2d_gn_fwd: %d channels per group (need a power of two <= 32)", cpg);
+    B200_REQUIRE((g->scale == nullptr) == (g->shift == nullptr), "conv2d_gn_fwd: scale and shift come together");
+    p.gn_gamma = g->gamma; p.gn_beta = g->beta; p.gn_scale = g->scale; p.gn_shift = g->shift; p.gn_out = g->out_norm;
+    p.gn_ss_ld = g->ss_ld; p.gn_lg_cpg = ilog2(cpg); p.gn_silu = g->apply_silu; p.gn_eps = g->eps;
+    static bool fuse_attr = false;
+    if (!fuse_attr) {
+      B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      fuse_attr = true;
+    }
+    B200_CHECK(launch_pdl(conv_gemm_kernel<kThreads, 2>, dim3(grid), dim3(64 + 128 * 2), smem_bytes, stream, mapA0, mapA1, mapW, p));
+    ++g_launch_count;
+    return 0;
+  }
   static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
   if (p.epi_halves == 4)
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreadsWide>, dim3(grid), dim3(64 + 128 * 4), smem_bytes, stream, mapA0, mapA1, mapW, p));

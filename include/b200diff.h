@@ -78,6 +78,25 @@ typedef struct b200_conv_desc {
 
 int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
 
+/* EXPERIMENTAL (round 2, not yet validated on hardware; the product path does not call it unless B200_FUSE_GN2=1):
+ * convolution whose epilogue applies the GroupNorm (+ AdaGN scale/shift) (+ SiLU) that FOLLOWS it, i.e. conv1 -> norm2
+ * of a ResBlock (models/unet.py:20-24,38-40; models/unet_categorial_adagn.py:36-41,58-60), writing only the bf16
+ * NHWC operand of the next convolution: out_norm = SiLU(GN(conv(x) + bias + rowadd)).  Possible when one 256-pixel
+ * tile holds whole images (Ho*Wo in {16, 64, 256}) and its 128 channels whole groups, so the statistics are complete
+ * inside a CTA.  d->out / d->stats / d->residual must be NULL-equivalent (ignored); N % 128 == 0. */
+typedef struct b200_gn_fuse_desc {
+  const float* gamma;        /* [N] */
+  const float* beta;         /* [N] */
+  const float* scale;        /* optional per-image rows [B][ss_ld]: y = GN(x) * (1 + scale) + shift */
+  const float* shift;
+  void* out_norm;            /* bf16 NHWC [B][Ho][Wo][N] */
+  int ss_ld;
+  int groups;
+  int apply_silu;
+  float eps;
+} b200_gn_fuse_desc;
+int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void* stream);
+
 /* First convolution of the UNet (models/unet.py:72,123): NCHW fp32 image, tiny Cin (1..4), 3x3 s1 p1,
  * -> fp32 NHWC [B][H][W][Cout].  Weights are the reference's OIHW fp32 tensor as is. */
 int b200_conv3x3_first(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc,

@@ -943,6 +943,41 @@ def case_pack_weights():
     return ok
 
 
+
+def case_conv_gnfuse():
+    """EXPERIMENTAL entry b200_conv2d_gn_fwd (conv1 -> norm2 of a ResBlock fused in the conv epilogue; not part of the
+    default GPU suite until it has been validated): SiLU(GN(conv3x3(x) + bias + time-embedding row)) as bf16 NHWC, with
+    and without AdaGN scale / shift, at the three resolutions where a tile holds whole images."""
+    import b200diff as K
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    for (B, Cin, Cout, H, rowadd, ss, silu) in ((160, 256, 256, 16, True, False, True), (160, 256, 256, 8, True, False, True),
+                                                 (320, 256, 256, 4, True, False, True), (160, 128, 256, 8, False, True, True),
+                                                 (128, 256, 128, 16, False, False, False)):
+        x = _bf16r(_gen(B, Cin, H, H, seed=1))
+        w = _bf16r(_gen(Cout, Cin, 3, 3, seed=2, scale=1.0 / math.sqrt(Cin * 9)))
+        b = _gen(Cout, seed=3)
+        ra = _gen(B, Cout + 64, seed=4) if rowadd else None
+        gamma, beta = 1.0 + 0.1 * _gen(Cout, seed=5), 0.1 * _gen(Cout, seed=6)
+        sst = 0.2 * _gen(B, 2 * Cout, seed=7) if ss else None
+        ref = F.conv2d(x, w, b, padding=1)
+        if rowadd:
+            ref = ref + ra[:, :Cout, None, None]
+        ref = F.group_norm(ref, 32, gamma, beta, eps=1e-5)
+        if ss:
+            ref = ref * (1 + sst[:, :Cout, None, None]) + sst[:, Cout:, None, None]
+        if silu:
+            ref = F.silu(ref)
+        out = torch.full((B, H, H, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+        K.conv2d_gn(_nhwc_bf16(x), K.pack_weight(w), Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(Cin, H, H, 1), gamma=gamma,
+                    beta=beta, groups=32, eps=1e-5, out_norm=out, bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0,
+                    scale=sst, shift=None if sst is None else sst[:, Cout:], ss_ld=2 * Cout, silu=silu)
+        torch.cuda.synchronize()
+        ok &= _report(f'conv3x3 {Cin}->{Cout} @{H} B={B} + fused GN (rowadd={rowadd}, adagn={ss}, silu={silu})',
+                      out.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+    return ok
+
+
 CASES = {n[5:]: f for n, f in list(globals().items()) if n.startswith('case_')}
 
 if __name__ == '__main__':

@@ -45,7 +45,7 @@ def test_struct_layout_matches_header(tmp_path):
     fields = {'b200_conv_desc': b200diff.ConvDesc, 'b200_sampler_desc': b200diff.SamplerDesc,
               'b200_gemm_desc': b200diff.GemmDesc, 'b200_wgrad_desc': b200diff.WgradDesc,
               'b200_gn_bwd_desc': b200diff.GnBwdDesc, 'b200_optim_desc': b200diff.OptimDesc,
-              'b200_ode_desc': b200diff.OdeDesc}
+              'b200_ode_desc': b200diff.OdeDesc, 'b200_gn_fuse_desc': b200diff.GnFuseDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200diff.h"', 'int main(void) {']
     for cname, cls in fields.items():
         for fname, ftype in cls._fields_:

@@ -27,4 +27,6 @@ for tag in ('off', 'on', 'np128', 'on_np128'):
     print(tag, 'ddim50 images/s', round(l['value'], 1), 'conv ms/forward', round(l['kernels']['conv_gemm']['ms_per_forward'], 3),
           'adm256 ms', round(l['extras']['adm256_forward']['ms_per_forward'], 2), 'train ms', round(l['extras']['cfg_train_step']['ms_per_step'], 2))
 PY
+# third experiment: conv1 -> norm2 fused in the conv epilogue (b200_conv2d_gn_fwd), kernel-level parity only so far
+timeout 200 python tests/kernel_cases.py conv_gnfuse > gpurun_out/gnfuse.log 2>&1; echo "conv_gnfuse exit $?"; tail -n 6 gpurun_out/gnfuse.log | cut -c1-300
 exit $rc

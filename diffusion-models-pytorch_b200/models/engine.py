@@ -35,9 +35,13 @@ class Engine:
     # statistics still come from the fp32 accumulators in the conv epilogue
     # (inference only; measured: eps rel-L2 +0.6e-3, DDIM-50 CIFAR-10 +2 %, pesser-256 forward +3.4 %)
     h_bf16 = bool(int(__import__('os').environ.get('B200_H_BF16', '1')))
+    # EXPERIMENTAL (off by default, not yet validated on hardware): conv1 -> norm2 of a ResBlock through the fused
+    # b200_conv2d_gn_fwd entry where a conv tile holds whole images (inference only)
+    fuse_gn2 = bool(int(__import__('os').environ.get('B200_FUSE_GN2', '0')))
 
     def __init__(self, model: nn.Module):
         self.model = model
+        self._fuse_gn2_skip = set()      # layers the experimental fused conv1+GN2 entry rejected (B200_FUSE_GN2=1)
         self._packed: Dict = {}
         self._const: Dict = {}
         self._sig = None
@@ -358,6 +362,25 @@ class Engine:
         (K.avgpool2_f32 if mode == 1 else K.upsample2_f32)(x.t, r, B, H, W, C)
         return Act(r, B, Ho, Wo, C)
 
+    def _conv1_gn2_fused(self, tag, a1, B, Ho, Wo, Cin, Cout, conv1, norm2, emb, emb_off, emb_ld, scale_shift):
+        """EXPERIMENTAL: SiLU(GN2(conv1(a1) + bias [+ emb row]) [* (1 + scale) + shift]) in ONE launch; returns the bf16
+        operand of conv2 or None when the C side rejects the layer (tile policy), which is remembered per layer."""
+        w, b = self.w_conv(tag + '.c1', conv1)
+        a2 = self.buf(tag + '.2.gn', (B, Ho, Wo, Cout), torch.bfloat16)
+        try:
+            if scale_shift:
+                K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
+                            beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
+                            scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:], ss_ld=emb_ld)
+            else:
+                K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
+                            beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
+                            rowadd=emb[:, emb_off:], rowadd_ld=emb_ld)
+        except RuntimeError:
+            self._fuse_gn2_skip.add(tag)
+            return None
+        return a2
+
     def resblock_core(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
                       emb_ld, scale_shift: bool, resample: int = 0, dropout: Optional[nn.Dropout] = None,
                       emb_linear: Optional[nn.Linear] = None) -> Act:
@@ -388,7 +411,13 @@ class Engine:
         drop_p, drop_seed = 0.0, 0
         if self.tape is not None and dropout is not None and dropout.p > 0 and self.model.training:
             drop_p, drop_seed = float(dropout.p), self.next_drop_seed()
-        if scale_shift:
+        a2 = h = None
+        if (self.fuse_gn2 and self.tape is None and drop_p == 0.0 and Ho * Wo in (16, 64, 256) and Cout % 128 == 0
+                and tag not in self._fuse_gn2_skip):
+            a2 = self._conv1_gn2_fused(tag, a1, B, Ho, Wo, Cin, Cout, conv1, norm2, emb, emb_off, emb_ld, scale_shift)
+        if a2 is not None:
+            pass
+        elif scale_shift:
             h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, intermediate=True)
             a2, _ = self.gn(tag + '.2', h, None, norm2, scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:],
                             ss_ld=emb_ld, drop_p=drop_p, drop_seed=drop_seed)

@@ -29,4 +29,10 @@ for tag in ('off', 'on', 'np128', 'on_np128'):
 PY
 # third experiment: conv1 -> norm2 fused in the conv epilogue (b200_conv2d_gn_fwd), kernel-level parity only so far
 timeout 200 python tests/kernel_cases.py conv_gnfuse > gpurun_out/gnfuse.log 2>&1; echo "conv_gnfuse exit $?"; tail -n 6 gpurun_out/gnfuse.log | cut -c1-300
+# ... and through the engine (B200_FUSE_GN2=1): forward / sampling parity, then the bench A/B
+for c in unet_forward ddim50 cfg; do
+  B200_FUSE_GN2=1 timeout 300 python tests/e2e_cases.py $c > gpurun_out/fuse_e2e_$c.log 2>&1; echo "fuse e2e $c exit $?"
+  tail -n 2 gpurun_out/fuse_e2e_$c.log | cut -c1-300
+done
+B200_FUSE_GN2=1 python bench.py --no-extras 2>/dev/null | python -c "import json,sys; l=json.loads(sys.stdin.read()); print('fuse_gn2 ddim50 images/s', round(l['value'],1), {k: round(v['ms_per_forward'],3) for k, v in l['kernels'].items()})"
 exit $rc

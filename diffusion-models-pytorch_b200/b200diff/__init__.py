@@ -18,6 +18,28 @@ OBJ = {'pred_eps': 0, 'pred_x0': 1, 'pred_v': 2}
 (SC_SQRT_RECIP_AC, SC_SQRT_RECIPM1_AC, SC_SQRT_AC, SC_SQRT_1M_AC, SC_X0_COEF, SC_XT_COEF, SC_EPS_COEF, SC_VAR,
  SC_MIN_LOGVAR, SC_MAX_LOGVAR, SC_ADD_NOISE) = range(11)
 SC_COUNT = 12
+STAT_Q1, STAT_Q2 = float(2 ** 30), float(2 ** 22)   # fixed-point scales of the [B, C, 2] int64 GroupNorm statistics
+
+
+def new_stats(B, C, device):
+    """Zeroed [B, C, 2] int64 accumulator for a producer's fused GroupNorm statistics (b200_conv_desc.stats)."""
+    return torch.zeros((B, C, 2), dtype=torch.int64, device=device)
+
+
+def stats_to_float(stats):
+    """[B, C, 2] int64 fixed point -> float64 (sum, sum of squares); for tests and diagnostics."""
+    out = stats.to(torch.float64)
+    out[..., 0] /= STAT_Q1
+    out[..., 1] /= STAT_Q2
+    return out
+
+
+def stats_from_float(st):
+    """float (sum, sum of squares) [B, C, 2] -> the int64 fixed-point layout the kernels read (tests)."""
+    out = torch.empty(st.shape, dtype=torch.int64, device=st.device)
+    out[..., 0] = torch.round(st[..., 0].to(torch.float64) * STAT_Q1).to(torch.int64)
+    out[..., 1] = torch.round(st[..., 1].to(torch.float64) * STAT_Q2).to(torch.int64)
+    return out
 
 
 class ConvDesc(Structure):
@@ -48,7 +70,7 @@ class SamplerDesc(Structure):
     ]
 
 
-class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (experimental fused conv + next GroupNorm)
+class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next GroupNorm)
     _fields_ = [
         ('gamma', c_void_p), ('beta', c_void_p), ('scale', c_void_p), ('shift', c_void_p), ('out_norm', c_void_p),
         ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
@@ -266,6 +288,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _need_stats(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.int64 or not t.is_contiguous()):
+            raise RuntimeError('GroupNorm statistics buffers are contiguous int64 [B, C, 2] tensors (b200diff.new_stats); '
+                               f'got {t.dtype}')
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -367,6 +396,7 @@ def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None,
            out_H=None, out_W=None, w_rows_per_phase=None, stats=None, alg_macs=None):
     """a0_geom = (C, H, W, planes) of the bf16 source tensor [B][planes][H][W][C]."""
     _need_cuda(a0, w_packed, out)
+    _need_stats(stats)
     d = ConvDesc()
     d.a0 = a0.data_ptr()
     d.a0_C, d.a0_H, d.a0_W, d.a0_planes = a0_geom
@@ -397,11 +427,23 @@ def conv2d(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, a1=None, a1_geom=None,
     return out
 
 
+def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
+    """Static eligibility of a layer for the fused conv + next-GroupNorm entry (mirrors the checks of
+    b200_conv2d_gn_fwd, so the engine decides per layer up front instead of catching a rejected launch)."""
+    hw = Ho * Wo
+    if hw not in (16, 64, 256) or N % 128 != 0 or groups < 1 or N % groups != 0:
+        return False
+    cpg = N // groups
+    if cpg > 32 or cpg & (cpg - 1):
+        return False
+    return hw >= 64 or B % (64 // hw) == 0      # the smallest tile is 64 pixels = 4 whole 4x4 images
+
+
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
               rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True):
-    """EXPERIMENTAL (b200_conv2d_gn_fwd, not yet validated on hardware): out_norm = SiLU(GN(conv(a0) + bias + rowadd))
-    as the bf16 NHWC operand of the next convolution; nothing else is written.  Raises when the layer is not eligible
-    (a tile must hold whole images: Ho*Wo in {16, 64, 256}; N % 128 == 0)."""
+    """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution;
+    nothing else is written.  Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}),
+    N % 128 == 0, power-of-two channels per group <= 32."""
     _need_cuda(a0, w_packed, out_norm)
     d = ConvDesc()
     d.a0 = a0.data_ptr()
@@ -426,6 +468,7 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
 
 def conv3x3_first(x, w, bias, out, stats=None):
     _need_cuda(x, w, out)
+    _need_stats(stats)
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
     _launch('conv3x3_first',
@@ -458,6 +501,7 @@ def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, bet
                     drop_seed_dev=None):
     """Streaming GroupNorm(+SiLU)(+dropout) for inputs whose [B][C][2] statistics came from the producing kernel."""
     _need_cuda(x0, stats0, out)
+    _need_stats(stats0, stats1)
     _launch('groupnorm_apply',
             lambda: _check(lib().b200_groupnorm_apply_train_fwd(
                 x0.data_ptr(), int(x0.dtype == torch.bfloat16), C0, stats0.data_ptr(), _ptr(x1), C1, _ptr(stats1), B,
@@ -592,6 +636,7 @@ def groupnorm_bwd(g, x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, be
                   dx1=None, dx1_acc=False, addend=None, dx_bf16=None, dx_rowsum=None, dx_rowsum_ld=0, dx_colsum=None,
                   dgamma=None, dbeta=None, dscale=None, dshift=None, dss_ld=0):
     _need_cuda(g, x0, stats0, sums)
+    _need_stats(stats0, stats1)
     d = GnBwdDesc()
     d.g, d.x0, d.C0, d.stats0 = g.data_ptr(), x0.data_ptr(), C0, stats0.data_ptr()
     d.x1, d.C1, d.stats1 = _ptr(x1), (C1 if x1 is not None else 0), _ptr(stats1)

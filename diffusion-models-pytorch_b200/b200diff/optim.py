@@ -35,7 +35,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _table(self, gi, params, ema_shadow):
         """Device chunk table of one param group; rebuilt only when a tensor moved (new .grad buffers, new shadow)."""
-        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params) + \
+        sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]['exp_avg'].data_ptr(),
+                     self.state[p]['exp_avg_sq'].data_ptr()) for p in params) + \
             (tuple(s.data_ptr() for s in ema_shadow) if ema_shadow is not None else ())
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == sig:
@@ -68,6 +69,24 @@ class FusedAdam(torch.optim.Optimizer):
             self._dev_lr.fill_(float(lr))
             self._lr_host = float(lr)
         return self._dev_state
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict + drop everything derived from the old state tensors: the device chunk
+        tables (they hold raw exp_avg / exp_avg_sq pointers) and the device-resident step / EMA counters (capturable
+        mode re-creates them from the loaded host-side step counts at the next step)."""
+        super().load_state_dict(state_dict)
+        self._tables.clear()
+        self._dev_state = None
+        self._dev_lr = None
+        for st in self.state.values():      # torch moves 'step' to the parameter's device; this class keeps it on the host
+            if torch.is_tensor(st.get('step')) and st['step'].is_cuda:
+                st['step'] = st['step'].cpu()
+
+    def reset_device_state(self):
+        """Call after `ema.load_state_dict(...)` in capturable mode: the EMA update count lives in device memory."""
+        self._tables.clear()
+        self._dev_state = None
+        self._dev_lr = None
 
     def set_lr(self, lr: float):
         """Learning-rate schedulers: updates param_groups and (capturable mode) the device copy read by graph replays."""
@@ -111,6 +130,11 @@ class FusedAdam(torch.optim.Optimizer):
                 shadow_all = ema.shadow[shadow_off:shadow_off + len(all_params)]
                 shadow_off += len(all_params)
             idx = [i for i, p in enumerate(all_params) if p.grad is not None]
+            if ema is not None:
+                # models/ema.py:31-38: parameters that are frozen (or received no gradient) are copied, not averaged
+                for i, p in enumerate(all_params):
+                    if p.grad is None:
+                        shadow_all[i].copy_(p)
             if not idx:
                 continue
             params = [all_params[i] for i in idx]

@@ -39,8 +39,8 @@ __device__ __forceinline__ float silu_grad(float z) {
 // ================================================================================================
 struct GnBwdParams {
   const __nv_bfloat16* g;
-  const float* x0; int C0; const float* st0;
-  const float* x1; int C1; const float* st1;
+  const float* x0; int C0; const long long* st0;   // [B][C][2] int64 fixed-point statistics (common.cuh: stat_load)
+  const float* x1; int C1; const long long* st1;
   int HW, W, groups, cpg, pix_per_cta;
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
@@ -66,9 +66,10 @@ __global__ void __launch_bounds__(256) gn_bwd_coef_kernel(const GnBwdParams p) {
   float* tmpS = bsm; float* tmpQ = bsm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
-    tmpS[c] = __ldg(st);
-    tmpQ[c] = __ldg(st + 1);
+    const long long* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+    const float2 sv = stat_load(st);
+    tmpS[c] = sv.x;
+    tmpQ[c] = sv.y;
   }
   __syncthreads();
   const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);

@@ -111,7 +111,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
           uint8_t* sW = smem + (size_t)stage * stage_bytes;
           uint8_t* sP = sW + kWBytes;
           // experiment knob (B200_EPI_DBG bits 8 / 16): leave out the weight / pixel operand load (timing only)
-          const bool skip_w = (p.dbg & 8) != 0, skip_p = (p.dbg & 16) != 0;
+          const bool skip_w = (B200_DBG(p) & 8) != 0, skip_p = (B200_DBG(p) & 16) != 0;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)((skip_w ? 0 : kWBytes) + (skip_p ? 0 : px_bytes)));
           if (skip_p) {
           } else if (kb < p.nkb0) {
@@ -236,8 +236,8 @@ static int ilog2(int v) {
 
 using namespace b200;
 
-// Experimental fused conv + next GroupNorm (b200_conv2d_gn_fwd): the descriptor travels to b200_conv2d_fwd's launch
-// code through this thread-local pointer so that the regular entry point keeps its signature and code path.
+// Fused conv + next GroupNorm (b200_conv2d_gn_fwd): the descriptor travels to b200_conv2d_fwd's launch code through
+// this thread-local pointer so that the regular entry point keeps its signature and code path.
 static thread_local const b200_gn_fuse_desc* tl_gn_fuse = nullptr;
 
 extern "C" int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void* stream_) {
@@ -293,17 +293,17 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   // largest pixel tile that still gives (nearly) every SM a tile; otherwise the smallest valid one
   int best_np = 0;
   static const char* env_np = getenv("B200_MAX_NP");
-  // experiment knob for the short-K (<= 8 K-blocks) layers, whose 4-stage ring otherwise holds exactly one tile:
-  // B200_SHORTK_NP=128 gives them 128-pixel tiles (32 KB stages, 6 deep).  Unset = same tiles as every other layer.
-  static const char* env_snp = getenv("B200_SHORTK_NP");
-  const int short_k = d->ntaps0 * (d->a0_C / 64) + (d->a1 ? d->a1_C / 64 : 0) <= 8;
-  const int np_max = (env_snp && short_k && (atoi(env_snp) == 64 || atoi(env_snp) == 128)) ? atoi(env_snp)
-                     : env_np ? atoi(env_np) : 256;
-  for (int np = np_max; np >= 64; np >>= 1) {
+  // (128-pixel tiles for the short-K 1x1 layers -- a deeper TMA ring relative to a tile -- were measured in round 2:
+  // DDIM-50 1035 -> 1030 images/s, so every layer uses the same tile rule.)
+  const int np_max = env_np ? atoi(env_np) : 256;
+  // fused next-GroupNorm epilogue: a tile must hold whole images (so at least Ho*Wo pixels) and be full (bn | B)
+  const int np_min = (tl_gn_fuse && d->Ho * d->Wo > 64) ? d->Ho * d->Wo : 64;
+  for (int np = np_max; np >= np_min; np >>= 1) {
     const int bw = maxw < np ? maxw : np;
     const int bh = maxh < np / bw ? maxh : np / bw;
     const int bn = np / (bw * bh);
     if (bn > 1 && !(bw == d->Wo && bh == d->Ho)) continue;  // images may only be stacked whole
+    if (tl_gn_fuse && d->B % bn != 0) continue;
     const long p_tiles = (long)(d->Wo / bw) * (d->Ho / bh) * ((d->B + bn - 1) / bn);
     p.NP = np; p.bw = bw; p.bh = bh; p.bn = bn;
     p.p_tiles = (int)p_tiles;
@@ -356,8 +356,12 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   static const char* env_rot = getenv("B200_K_ROTATE");
   p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
 
-  static const char* env_dbg = getenv("B200_EPI_DBG");
+#ifdef B200_DEBUG
+  static const char* env_dbg = getenv("B200_EPI_DBG");   // timing experiments only: skips loads / stores
   p.dbg = env_dbg ? atoi(env_dbg) : 0;
+#else
+  p.dbg = 0;
+#endif
   // vertical-tap reuse (B200_VTAP=0 disables): plain 3x3 stride-1 layers whose 256-pixel tile is >= 4 full-width rows
   // of one image.  Measured (B=256, back to back): 128->128@32x32 +res 90.1 -> 84.5 us, 256->256@16x16 +res 79.3 ->
   // 70.9 us (the CTA-pair kernel needs 75.4 us for that layer, so eligible layers take this path instead).
@@ -406,7 +410,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (tl_gn_fuse) {
-    // experimental fused next-GroupNorm epilogue: the tile must hold whole images and whole groups
+    // fused next-GroupNorm epilogue: the tile must hold whole images and whole groups
     const b200_gn_fuse_desc* g = tl_gn_fuse;
     const int hw = d->Ho * d->Wo;
     B200_REQUIRE(p.fast_epi && p.bw == d->Wo && p.bh == d->Ho && (hw == 16 || hw == 64 || hw == 256) && p.NP >= hw &&
@@ -428,11 +432,11 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     ++g_launch_count;
     return 0;
   }
-  static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
+  static const char* env_lean = getenv("B200_EPI_LEAN");   // =0: generic epilogue everywhere (A/B timing)
   if (p.epi_halves == 4)
     B200_CHECK(launch_pdl(conv_gemm_kernel<kThreadsWide>, dim3(grid), dim3(64 + 128 * 4), smem_bytes, stream, mapA0, mapA1, mapW, p));
-  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p)) {
-    static bool lean_attr = false;    // set lazily: the default path never touches the experimental instantiation
+  else if (!(env_lean && atoi(env_lean) == 0) && conv_epilogue_lean_ok(p)) {
+    static bool lean_attr = false;
     if (!lean_attr) {
       B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       lean_attr = true;

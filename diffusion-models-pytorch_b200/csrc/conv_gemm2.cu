@@ -289,10 +289,10 @@ int conv2d_fwd_pair(const b200_conv_desc* d, const ConvKParams& p1, cudaStream_t
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static const char* env_lean = getenv("B200_EPI_LEAN");   // experiment: lean epilogue instantiation (conv_epilogue.cuh)
+  static const char* env_lean = getenv("B200_EPI_LEAN");   // =0: generic epilogue everywhere (A/B timing)
   if (p.epi_halves == 4)
     B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<kThreadsWide>, mapA0, mapA1, mapW, p, pp));
-  else if (env_lean && atoi(env_lean) == 1 && conv_epilogue_lean_ok(p)) {
+  else if (!(env_lean && atoi(env_lean) == 0) && conv_epilogue_lean_ok(p)) {
     static bool lean_attr = false;    // set lazily: the default path never touches the experimental instantiation
     if (!lean_attr) {
       B200_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel<kThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

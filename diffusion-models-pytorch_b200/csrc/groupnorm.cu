@@ -281,8 +281,8 @@ extern "C" int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1,
 namespace b200 {
 
 struct GnApplyParams {
-  const float* x0; int C0; const float* st0;
-  const float* x1; int C1; const float* st1;
+  const float* x0; int C0; const long long* st0;   // statistics: [B][C][2] int64 fixed point (common.cuh: stat_load)
+  const float* x1; int C1; const long long* st1;
   int HW, W, groups, cpg, pix_per_cta;
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
@@ -357,34 +357,27 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
     float mean[8], rstd[8];
     if (p.cpg <= 8) {
       // statistics of the own 8 channels: 16 consecutive floats of [n][c][2]
-      const float* st = from0 ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
-      float sq[16];
+      const long long* st = from0 ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+      longlong2 sq[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = ldg4(st + 4 * i);
-        sq[4 * i] = t.x; sq[4 * i + 1] = t.y; sq[4 * i + 2] = t.z; sq[4 * i + 3] = t.w;
-      }
+      for (int i = 0; i < 8; ++i) sq[i] = __ldg(reinterpret_cast<const longlong2*>(st) + i);
 #pragma unroll
       for (int i0 = 0; i0 < 8; i0 += 1) {
         const int g0 = i0 & ~(p.cpg - 1);          // cpg is 1, 2, 4 or 8 here
-        float sm = 0.f, qm = 0.f;
+        long long sm = 0, qm = 0;                  // group sums are exact in the fixed-point domain
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (i >= g0 && i < g0 + p.cpg) { sm += sq[2 * i]; qm += sq[2 * i + 1]; }
-        mean[i0] = sm * inv_cnt;
-        rstd[i0] = rsqrtf(fmaxf(qm * inv_cnt - mean[i0] * mean[i0], 0.f) + p.eps);
+          if (i >= g0 && i < g0 + p.cpg) { sm += sq[i].x; qm += sq[i].y; }
+        mean[i0] = __ll2float_rn(sm) * (1.0f / kStatQ1) * inv_cnt;
+        rstd[i0] = rsqrtf(fmaxf(__ll2float_rn(qm) * (1.0f / kStatQ2) * inv_cnt - mean[i0] * mean[i0], 0.f) + p.eps);
       }
     } else {
       // groups of 16, 24, ... channels: whole 8-channel columns of one source
       const int g0 = (c / p.cpg) * p.cpg;
-      const float* st = (g0 < p.C0) ? p.st0 + ((size_t)n * p.C0 + g0) * 2 : p.st1 + ((size_t)n * p.C1 + (g0 - p.C0)) * 2;
-      float sm = 0.f, qm = 0.f;
-      for (int i = 0; i < p.cpg; i += 2) {
-        const float4 t = ldg4(st + 2 * i);
-        sm += t.x + t.z; qm += t.y + t.w;
-      }
-      const float m = sm * inv_cnt;
-      const float r = rsqrtf(fmaxf(qm * inv_cnt - m * m, 0.f) + p.eps);
+      const long long* st = (g0 < p.C0) ? p.st0 + ((size_t)n * p.C0 + g0) * 2 : p.st1 + ((size_t)n * p.C1 + (g0 - p.C0)) * 2;
+      const float2 gs = stat_load_group(st, p.cpg);
+      const float m = gs.x * inv_cnt;
+      const float r = rsqrtf(fmaxf(gs.y * inv_cnt - m * m, 0.f) + p.eps);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { mean[i] = m; rstd[i] = r; }
     }
@@ -479,9 +472,10 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
     return;
   }
   for (int c = tid; c < C; c += 256) {
-    const float* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
-    chS[c] = __ldg(st);
-    chQ[c] = __ldg(st + 1);
+    const long long* st = (c < p.C0) ? p.st0 + ((size_t)n * p.C0 + c) * 2 : p.st1 + ((size_t)n * p.C1 + (c - p.C0)) * 2;
+    const float2 sv = stat_load(st);
+    chS[c] = sv.x;
+    chQ[c] = sv.y;
   }
   __syncthreads();
   const float inv_cnt = 1.0f / (float)(p.HW * p.cpg);
@@ -659,8 +653,8 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
 
 }  // namespace b200
 
-extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0,
-                                              const float* x1, int C1, const float* stats1, int B, int HW, int W,
+extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, int C0, const long long* stats0,
+                                              const float* x1, int C1, const long long* stats1, int B, int HW, int W,
                                               int groups, const float* gamma, const float* beta, float eps,
                                               const float* scale, const float* shift, int ss_ld, int apply_silu,
                                               int resample, float drop_p, unsigned long long drop_seed,
@@ -720,8 +714,8 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   return 0;
 }
 
-extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const float* stats0, const float* x1,
-                                        int C1, const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+extern "C" int b200_groupnorm_apply_fwd(const void* x0_, int x0_is_bf16, int C0, const long long* stats0, const float* x1,
+                                        int C1, const long long* stats1, int B, int HW, int W, int groups, const float* gamma,
                                         const float* beta, float eps, const float* scale, const float* shift,
                                         int ss_ld, int apply_silu, int resample, void* out_bf16, void* raw_out_bf16,
                                         void* stream_) {

@@ -18,12 +18,12 @@ extern long long g_launch_count;
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            float* __restrict__ stats, int B, int H, int W, int Cout,
+                                                            long long* __restrict__ stats, int B, int H, int W, int Cout,
                                                             int R) {
   constexpr int K = 9 * CIN;
   extern __shared__ float fsm[];
-  float* ssm = fsm;               // [2*128] statistics of this CTA's channel group
-  float* patch = fsm + 256;       // [CIN][R+2][W+2], zero padded
+  unsigned long long* ssm = reinterpret_cast<unsigned long long*>(fsm);   // [2*128] fixed-point statistics (stat_add)
+  float* patch = fsm + 512;       // [CIN][R+2][W+2], zero padded
   const int n = blockIdx.y;
   const int h0 = blockIdx.x * R;
   const int PW = W + 2;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
   const int co = blockIdx.z * 128 + 4 * lane;  // first of this lane's 4 output channels
   const bool co_ok = co < Cout;
   griddep_sync();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0.f;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0ull;
   for (int i = threadIdx.x; i < CIN * (R + 2) * PW; i += blockDim.x) {
     const int ci = i / ((R + 2) * PW);
     const int rem = i - ci * (R + 2) * PW;
@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
     if (co_ok) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        atomicAdd(ssm + 2 * (4 * lane + e), s1[e]);
-        atomicAdd(ssm + 2 * (4 * lane + e) + 1, s2[e]);
+        atomicAdd(ssm + 2 * (4 * lane + e), stat_fix1(s1[e]));
+        atomicAdd(ssm + 2 * (4 * lane + e) + 1, stat_fix2(s2[e]));
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
       const int ch = blockIdx.z * 128 + (i >> 1);
-      if (ch < Cout) atomicAdd(stats + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
+      if (ch < Cout) atomicAdd(reinterpret_cast<unsigned long long*>(stats) + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
     }
   }
 }
@@ -95,12 +95,12 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
 template <int CIN>
 __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ out,
-                                                                   float* __restrict__ stats, int B, int H, int W, int Cout,
+                                                                   long long* __restrict__ stats, int B, int H, int W, int Cout,
                                                                    int R, int units_per_image, int total_units) {
   constexpr int K = 9 * CIN;
   extern __shared__ float fsm[];
-  float* ssm = fsm;               // [2*128] statistics of the current unit's channel group
-  float* patch = fsm + 256;       // [CIN][R+2][PWp], zero padded, rows 16-byte aligned
+  unsigned long long* ssm = reinterpret_cast<unsigned long long*>(fsm);   // [2*128] fixed-point statistics of the unit
+  float* patch = fsm + 512;       // [CIN][R+2][PWp], zero padded, rows 16-byte aligned
   const int PWp = (W + 2 + 3) & ~3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int co = blockIdx.z * 128 + 4 * lane;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* 
     const int n = unit / units_per_image;
     const int h0 = (unit - n * units_per_image) * R;
     __syncthreads();   // the previous unit's patch and statistics are consumed
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0.f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) ssm[i] = 0ull;
     for (int i = threadIdx.x; i < CIN * (R + 2) * PWp; i += blockDim.x) {
       const int ci = i / ((R + 2) * PWp);
       const int rem = i - ci * (R + 2) * PWp;
@@ -168,14 +168,14 @@ __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* 
       if (co_ok) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          atomicAdd(ssm + 2 * (4 * lane + e), s1[e]);
-          atomicAdd(ssm + 2 * (4 * lane + e) + 1, s2[e]);
+          atomicAdd(ssm + 2 * (4 * lane + e), stat_fix1(s1[e]));
+          atomicAdd(ssm + 2 * (4 * lane + e) + 1, stat_fix2(s2[e]));
         }
       }
       __syncthreads();
       for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int ch = blockIdx.z * 128 + (i >> 1);
-        if (ch < Cout) atomicAdd(stats + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
+        if (ch < Cout) atomicAdd(reinterpret_cast<unsigned long long*>(stats) + ((size_t)n * Cout + ch) * 2 + (i & 1), ssm[i]);
       }
     }
   }
@@ -391,14 +391,14 @@ static inline int ew_grid(size_t total, int block) {
 using namespace b200;
 
 template <int CIN>
-static int launch_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B, int H,
+static int launch_first(const float* x, const float* w, const float* bias, float* out, long long* stats, int B, int H,
                         int W, int Cout, cudaStream_t stream) {
   static const char* env_v = getenv("B200_FIRST_PX4");
   if (W % 4 == 0 && !(env_v && atoi(env_v) == 0)) {
     int R = 8;
     if (R > H) R = H;
     const int PWp = (W + 2 + 3) & ~3;
-    const size_t smem = (256 + (size_t)CIN * (R + 2) * PWp) * 4;
+    const size_t smem = (512 + (size_t)CIN * (R + 2) * PWp) * 4;
     B200_REQUIRE(smem <= 100 * 1024, "conv3x3_first: input patch does not fit in shared memory (W=%d)", W);
     static bool attr4 = false;
     static int sms = 0;
@@ -422,7 +422,7 @@ static int launch_first(const float* x, const float* w, const float* bias, float
   int R = env_r ? atoi(env_r) : 32;
   while (R > 1 && (size_t)CIN * (R + 2) * (W + 2) * 4 > 96 * 1024) R >>= 1;
   if (R > H) R = H;
-  const size_t smem = (256 + (size_t)CIN * (R + 2) * (W + 2)) * 4;
+  const size_t smem = (512 + (size_t)CIN * (R + 2) * (W + 2)) * 4;
   B200_REQUIRE(smem <= 100 * 1024, "conv3x3_first: input patch does not fit in shared memory (W=%d)", W);
   static bool attr = false;
   if (!attr) {
@@ -435,7 +435,7 @@ static int launch_first(const float* x, const float* w, const float* bias, float
   return 0;
 }
 
-extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* bias, float* out, float* stats, int B,
+extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* bias, float* out, long long* stats, int B,
                                   int Cin, int H, int W, int Cout, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(x && w && out, "conv3x3_first: null pointer");

@@ -118,10 +118,11 @@ __global__ void __launch_bounds__(256, 4) sampler_step_vec4_kernel(const Sampler
   const size_t units = k.total >> 2;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   // The graph runner updates x in place (sample == xt): every unit is read and then written by the same thread only,
-  // and all loads of an iteration are issued before its stores, so the read-only (.nc) loads below stay correct.
+  // and all loads of an iteration are issued before its stores.  xt is therefore NOT declared __restrict__ / read-only
+  // (a .nc load of memory the same kernel writes would be formally undefined); the other inputs never alias an output.
   const float4* __restrict__ mo4 = reinterpret_cast<const float4*>(k.mo);
   const float4* __restrict__ mou4 = reinterpret_cast<const float4*>(k.mo_u);
-  const float4* __restrict__ xt4 = reinterpret_cast<const float4*>(k.xt);
+  const float4* xt4 = reinterpret_cast<const float4*>(k.xt);
   const float4* __restrict__ nz4 = reinterpret_cast<const float4*>(k.noise);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < units; base += stride * U) {

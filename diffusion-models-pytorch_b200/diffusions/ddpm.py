@@ -112,7 +112,13 @@ class DDPM:
         key = (type(self).__name__, t, t_prev, self.var_type, getattr(self, 'eta', None))
         row = self._coef_rows.get(key)
         if row is None:
-            vals = self._predict_coefs(t) + self._step_coefs(t, t_prev) + [torch.tensor(0.0 if t == 0 else 1.0)]
+            step = self._step_coefs(t, t_prev)
+            # the noise term sqrt(var) * z is skipped (and z not read) at t == 0 like the reference (ddpm.py:252,
+            # ddim.py:77) and whenever the fixed variance is exactly 0 (DDIM eta = 0: mean + 0 * z == mean), which
+            # saves the 4 B/element noise stream; the learned-range variance is per pixel and always reads it
+            learned = self.var_type == 'learned_range' and self._uses_learned_var()
+            add_noise = t != 0 and (learned or float(step[3]) != 0.0)
+            vals = self._predict_coefs(t) + step + [torch.tensor(1.0 if add_noise else 0.0)]
             host = torch.stack([torch.as_tensor(v, dtype=torch.float32).reshape(()) for v in vals] +
                                [torch.zeros(())] * (K.SC_COUNT - len(vals)))
             row = host.to(self.device)
@@ -252,11 +258,24 @@ class DDPM:
         return sample
 
 
+_STEP_METHODS = ('denoise', 'predict', '_denoise_impl', '_predict_kernel', '_step_coefs', '_predict_coefs', '_coef_row',
+                 '_coef_table', '_step_pairs', '_uses_learned_var', 'sample_loop', '_cfg_loop')
+
+
 def _graph_runner(diffuser, model):
-    """CUDA-graph replay of the per-timestep work, when the model is a b200diff engine model."""
+    """CUDA-graph replay of the per-timestep work, when the model is a b200diff engine model AND the diffuser's
+    per-step arithmetic is the stock one.  The runner hard-wires `b200_sampler_step` with `_coef_table`, so a subclass
+    that overrides any of the step methods (guidance samplers, DDPM-IP-style variants, user subclasses) must not be
+    routed through it: `sample()` then walks `sample_loop()` like the reference (ddpm.py:283-290), override included."""
     make = getattr(model, 'make_sampling_runner', None)
     if make is None or not getattr(model, 'use_cuda_graph', True):
         return None
+    from diffusions.ddim import DDIM, DDIMCFG
+    cls = type(diffuser)
+    if cls not in (DDPM, DDPMCFG, DDIM, DDIMCFG):
+        stock = next(b for b in cls.__mro__ if b in (DDIMCFG, DDPMCFG, DDIM, DDPM))
+        if any(getattr(cls, m, None) is not getattr(stock, m, None) for m in _STEP_METHODS):
+            return None
     return make(diffuser)
 
 

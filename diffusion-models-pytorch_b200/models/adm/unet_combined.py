@@ -22,10 +22,11 @@ class UNetCombined(nn.Module):
 
     def make_sampling_runner(self, diffuser):
         from models.runner import SamplingRunner
-        cache = self.__dict__.setdefault('_runners', {})
-        r = cache.get(id(diffuser))
-        if r is None or r.diffuser is not diffuser:
-            r = cache[id(diffuser)] = SamplingRunner(self, diffuser)
+        import weakref
+        cache = self.__dict__.setdefault('_runners', weakref.WeakKeyDictionary())
+        r = cache.get(diffuser)
+        if r is None:
+            r = cache[diffuser] = SamplingRunner(self, diffuser)
         return r
 
     @property

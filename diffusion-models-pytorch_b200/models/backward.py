@@ -31,6 +31,8 @@ class UNetFunction(torch.autograd.Function):
         try:
             out = model._forward_impl(*args, **kwargs)
             ctx.tape = eng.tape
+            ctx.arena_key = tuple(args[0].shape) if args and torch.is_tensor(args[0]) else tuple(out.shape)
+            ctx.arena_gen = eng._fwd_gen.get(ctx.arena_key)
             eng.last_tape = eng.tape     # introspection (tests read the dropout seeds from it)
         finally:
             eng.tape = None
@@ -40,6 +42,16 @@ class UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        eng = ctx.model.engine
+        if ctx.tape is None:
+            raise RuntimeError('b200diff UNet: backward called twice on the same forward (the tape is consumed; '
+                               'retain_graph is not supported)')
+        if ctx.arena_gen is not None and eng._fwd_gen.get(ctx.arena_key) != ctx.arena_gen:
+            raise RuntimeError(
+                'b200diff UNet: another forward with the same input shape ran between this training forward and its '
+                'backward.  The tape refers to the engine\'s shared activation arena (no saved copies), so the saved '
+                'activations were overwritten; run backward() before the next forward of this model (evaluation / '
+                'sampling forwards included), or use a second model instance.')
         grads = run_backward(ctx.model.engine, ctx.tape, dout.contiguous(), ctx.params)
         ctx.tape = None
         return (None, None, None) + tuple(grads)

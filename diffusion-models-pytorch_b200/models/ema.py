@@ -1,7 +1,7 @@
 """Exponential moving average of model parameters (API of the reference's models/ema.py:7-79).
 
 Host-side utility around the training step: a list-of-tensors shadow in `model.parameters()` order, updated
-with multi-tensor (foreach) ops.  The fused Adam+EMA kernel is SURVEY.md section 8f "next" work.
+with multi-tensor (foreach) ops (b200diff.optim.FusedAdam(W) folds the same update into its kernel).
 """
 from typing import Iterable
 
@@ -37,16 +37,21 @@ class EMA:
         for s, p in frozen:
             s.copy_(p)
 
+    @torch.no_grad()
     def apply_shadow(self, parameters: Iterable[nn.Parameter]):
+        """models/ema.py:40-45 of the reference.  The copy goes through `p.copy_` (not `p.data.copy_`) so that the
+        parameter's version counter moves: models/engine.py re-packs its bf16 operands and drops captured sampling
+        graphs when (data_ptr, _version) of a parameter changes."""
         assert len(self.backup) == 0, 'backup is not empty'
         for s, p in zip(self.shadow, parameters):
             self.backup.append(p.detach().cpu().clone())
-            p.data.copy_(s.data)
+            p.copy_(s)
 
+    @torch.no_grad()
     def restore(self, parameters: Iterable[nn.Parameter]):
         assert len(self.backup) > 0, 'backup is empty'
         for b, p in zip(self.backup, parameters):
-            p.data.copy_(b.to(p.device).data)
+            p.copy_(b.to(p.device))
         self.backup = []
 
     def state_dict(self):

@@ -26,7 +26,7 @@ class Act:
 
     def __init__(self, t, B, H, W, C, stats=None):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
-        self.stats = stats   # [B, C, 2] per-(image, channel) sum / sum of squares from the producing kernel
+        self.stats = stats   # [B, C, 2] int64 fixed-point per-(image, channel) sum / sum of squares from the producing kernel
         self.g = None        # fp32 NHWC gradient buffer, created by the first backward contribution (models/backward.py)
 
 
@@ -35,13 +35,13 @@ class Engine:
     # statistics still come from the fp32 accumulators in the conv epilogue
     # (inference only; measured: eps rel-L2 +0.6e-3, DDIM-50 CIFAR-10 +2 %, pesser-256 forward +3.4 %)
     h_bf16 = bool(int(__import__('os').environ.get('B200_H_BF16', '1')))
-    # EXPERIMENTAL (off by default, not yet validated on hardware): conv1 -> norm2 of a ResBlock through the fused
-    # b200_conv2d_gn_fwd entry where a conv tile holds whole images (inference only)
-    fuse_gn2 = bool(int(__import__('os').environ.get('B200_FUSE_GN2', '0')))
+    # conv1 -> norm2 of a ResBlock through the fused b200_conv2d_gn_fwd entry where a conv tile holds whole images
+    # (16x16 / 8x8 / 4x4 levels, inference only): the intermediate h is never written and one GroupNorm launch per
+    # ResBlock disappears (measured: DDIM-50 CIFAR-10 1035 -> 1057 images/s).  B200_FUSE_GN2=0: two launches (A/B).
+    fuse_gn2 = bool(int(__import__('os').environ.get('B200_FUSE_GN2', '1')))
 
     def __init__(self, model: nn.Module):
         self.model = model
-        self._fuse_gn2_skip = set()      # layers the experimental fused conv1+GN2 entry rejected (B200_FUSE_GN2=1)
         self._packed: Dict = {}
         self._const: Dict = {}
         self._sig = None
@@ -57,6 +57,8 @@ class Engine:
         self.emb_override = None  # [1, total] fp32: precomputed embedding projections of the current timestep (sampling runner)
         self._embed_args = None   # modules of the last time-only embedding (what embed_rows re-evaluates for a whole schedule)
         self._n_drop = 0
+        self._epoch = 0           # bumped by invalidate(): part of the weight signature
+        self._fwd_gen: Dict = {}  # input shape -> number of forwards that (re)wrote the arena buffers of that shape
 
     # ------------------------------------------------------------------------------------------
     # buffers and packed weights
@@ -77,7 +79,8 @@ class Engine:
         return t
 
     def stats_buf(self, tag, B, C):
-        """[B, C, 2] fp32 accumulator for the GroupNorm statistics of a conv output (zeroed every forward)."""
+        """[B, C, 2] int64 fixed-point accumulator (K.STAT_Q1 / K.STAT_Q2) for the GroupNorm statistics of a conv output
+        (zeroed every forward).  Integer atomics: order-independent, so forwards are bitwise reproducible."""
         key = (tag, B, C, self.device)
         t = self._stats.get(key)
         if t is None:
@@ -86,8 +89,8 @@ class Engine:
             n = B * C * 2
             if (not self._stats_pools or self._stats_pools[-1][1] + n > self._stats_pools[-1][0].numel()
                     or self._stats_pools[-1][0].device != self.device):
-                cap = max(n, 8 << 20)
-                self._stats_pools.append([torch.zeros(cap, dtype=torch.float32, device=self.device), 0])
+                cap = max(n, 4 << 20)
+                self._stats_pools.append([torch.zeros(cap, dtype=torch.int64, device=self.device), 0])
             pool = self._stats_pools[-1]
             t = pool[0][pool[1]:pool[1] + n].view(B, C, 2)
             pool[1] += (n + 63) // 64 * 64
@@ -104,10 +107,10 @@ class Engine:
         EMA swap): table-managed packs are re-created in place by ONE b200_pack_weights launch; everything is dropped
         when a parameter moved (new storage)."""
         self._device = None
-        sig = tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        sig = (self._epoch,) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
         if sig != self._sig:
-            moved = self._sig is None or len(sig) != len(self._sig) or \
-                any(a[0] != b[0] for a, b in zip(sig, self._sig))
+            moved = self._sig is None or len(sig) != len(self._sig) or sig[0] != self._sig[0] or \
+                any(a[0] != b[0] for a, b in zip(sig[1:], self._sig[1:]))
             self._packed.clear()
             if moved:
                 self._pt.clear()
@@ -124,6 +127,13 @@ class Engine:
         if dev.type != 'cuda':
             raise RuntimeError('b200diff models run on a CUDA device only: there is no CPU/PyTorch fallback '
                                f'(parameters are on {dev})')
+
+    def invalidate(self):
+        """Forces a full re-pack of the bf16 operands (and re-capture of the sampling graphs) at the next forward.
+        Needed only after writes that bypass the parameters' version counters -- `p.data.copy_(...)`, `p.data = ...` on
+        the same storage, raw-pointer writes from another library; `p.copy_()` under no_grad, optimizers,
+        `load_state_dict` and models.EMA are detected automatically through (data_ptr, _version)."""
+        self._epoch += 1
 
     def const(self, key, make):
         """Parameter-independent device constants (frequency tables): survive weight updates, unlike `packed`."""
@@ -363,22 +373,18 @@ class Engine:
         return Act(r, B, Ho, Wo, C)
 
     def _conv1_gn2_fused(self, tag, a1, B, Ho, Wo, Cin, Cout, conv1, norm2, emb, emb_off, emb_ld, scale_shift):
-        """EXPERIMENTAL: SiLU(GN2(conv1(a1) + bias [+ emb row]) [* (1 + scale) + shift]) in ONE launch; returns the bf16
-        operand of conv2 or None when the C side rejects the layer (tile policy), which is remembered per layer."""
+        """SiLU(GN2(conv1(a1) + bias [+ emb row]) [* (1 + scale) + shift]) in ONE launch -> the bf16 operand of conv2.
+        The caller checked K.conv2d_gn_ok for this layer; a rejected launch raises (no per-layer fallback)."""
         w, b = self.w_conv(tag + '.c1', conv1)
         a2 = self.buf(tag + '.2.gn', (B, Ho, Wo, Cout), torch.bfloat16)
-        try:
-            if scale_shift:
-                K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
-                            beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
-                            scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:], ss_ld=emb_ld)
-            else:
-                K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
-                            beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
-                            rowadd=emb[:, emb_off:], rowadd_ld=emb_ld)
-        except RuntimeError:
-            self._fuse_gn2_skip.add(tag)
-            return None
+        if scale_shift:
+            K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
+                        beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
+                        scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:], ss_ld=emb_ld)
+        else:
+            K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
+                        beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
+                        rowadd=emb[:, emb_off:], rowadd_ld=emb_ld)
         return a2
 
     def resblock_core(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
@@ -412,11 +418,9 @@ class Engine:
         if self.tape is not None and dropout is not None and dropout.p > 0 and self.model.training:
             drop_p, drop_seed = float(dropout.p), self.next_drop_seed()
         a2 = h = None
-        if (self.fuse_gn2 and self.tape is None and drop_p == 0.0 and Ho * Wo in (16, 64, 256) and Cout % 128 == 0
-                and tag not in self._fuse_gn2_skip):
+        if (self.fuse_gn2 and self.tape is None and drop_p == 0.0 and Cin % 64 == 0
+                and K.conv2d_gn_ok(B, Ho, Wo, Cout, norm2.num_groups)):
             a2 = self._conv1_gn2_fused(tag, a1, B, Ho, Wo, Cin, Cout, conv1, norm2, emb, emb_off, emb_ld, scale_shift)
-        if a2 is not None:
-            pass
         elif scale_shift:
             h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, intermediate=True)
             a2, _ = self.gn(tag + '.2', h, None, norm2, scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:],
@@ -531,8 +535,11 @@ class Engine:
             self.tape.append(dict(kind='head', tag=tag, x=h, a=a, norm=norm, conv=conv))
         return out
 
-    @staticmethod
-    def check_input(X, T, in_channels):
+    def check_input(self, X, T, in_channels):
+        """Validates the network input and counts this forward against the arena of its shape: the training tape
+        (models/backward.py) refers to arena buffers instead of saving copies, so its backward checks that no other
+        forward of the same shape ran in between."""
+        self._fwd_gen[tuple(X.shape)] = self._fwd_gen.get(tuple(X.shape), 0) + 1
         if X.dim() != 4 or X.shape[1] != in_channels:
             raise RuntimeError(f'expected input [B, {in_channels}, H, W], got {tuple(X.shape)}')
         if not X.is_cuda:

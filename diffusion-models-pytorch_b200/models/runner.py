@@ -8,6 +8,8 @@ device-to-device copies plus one graph launch, with no host<->device synchronisa
 The noise is drawn with torch's Philox generator inside the graph, once per step like the reference
 (ddim.py:76 / ddpm.py:251), so seeded runs consume the RNG stream identically.
 """
+import weakref
+
 import torch
 import tqdm
 
@@ -17,8 +19,12 @@ import b200diff as K
 class SamplingRunner:
     def __init__(self, model, diffuser):
         self.model = model
-        self.diffuser = diffuser
+        self._diffuser = weakref.ref(diffuser)   # the model's runner table is keyed weakly by the diffuser
         self._graphs = {}
+
+    @property
+    def diffuser(self):
+        return self._diffuser()
 
     # ------------------------------------------------------------------------------------------
     def _eager(self, init_noise, tqdm_kwargs, model_kwargs, guidance_scale, uncond_conditioning):

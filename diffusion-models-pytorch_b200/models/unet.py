@@ -7,6 +7,7 @@ GroupNorm+SiLU (K3) -> tcgen05 implicit-GEMM convs with fused bias / time-embedd
 fused attention (K2).  Dropout is the identity in eval mode; training mode is rejected until the backward
 kernels land (there is no autograd fallback).
 """
+import weakref
 from typing import List
 
 import torch
@@ -39,7 +40,7 @@ class _EngineModel(nn.Module):
 
     def _init_engine(self):
         self.__dict__['_engine'] = Engine(self)     # not a submodule / not in state_dict
-        self.__dict__['_runners'] = {}
+        self.__dict__['_runners'] = weakref.WeakKeyDictionary()   # diffuser -> SamplingRunner (dies with the diffuser)
 
     @property
     def engine(self) -> Engine:
@@ -47,11 +48,10 @@ class _EngineModel(nn.Module):
 
     def make_sampling_runner(self, diffuser):
         """Per-diffuser CUDA-graph sampler used by DDPM/DDIM(.CFG).sample()."""
-        key = id(diffuser)
-        r = self.__dict__['_runners'].get(key)
-        if r is None or r.diffuser is not diffuser:
-            r = SamplingRunner(self, diffuser)
-            self.__dict__['_runners'][key] = r
+        runners = self.__dict__['_runners']
+        r = runners.get(diffuser)
+        if r is None:
+            r = runners[diffuser] = SamplingRunner(self, diffuser)
         return r
 
     def forward(self, *args, **kwargs):

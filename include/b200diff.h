@@ -24,7 +24,10 @@
 extern "C" {
 #endif
 
-#define B200DIFF_VERSION 100
+#define B200DIFF_VERSION 200
+/* fixed-point scales of the GroupNorm statistics exchanged between kernels ([B][C][2] int64: sum, sum of squares) */
+#define B200_STAT_Q1 1073741824.0 /* 2^30 */
+#define B200_STAT_Q2 4194304.0    /* 2^22 */
 
 int b200_version(void);
 const char* b200_last_error(void);
@@ -66,9 +69,10 @@ typedef struct b200_conv_desc {
   int rowadd_ld;
   const float* residual; /* fp32 NHWC [B][out_H][out_W][res_ld] or NULL */
   int res_ld;
-  float* stats;          /* optional [B][N][2] fp32, pre-zeroed: per-(image, channel) sum and sum of squares of the
-                            NHWC output (before any rounding to bf16) are atomically accumulated here for the
-                            GroupNorm that follows */
+  long long* stats;      /* optional [B][N][2] int64, pre-zeroed: per-(image, channel) sum (fixed point, 2^30) and sum of
+                            squares (2^22) of the NHWC output (before any rounding to bf16) are accumulated here for the
+                            GroupNorm that follows.  Integer atomics: the result does not depend on the arrival order
+                            of the CTAs, so forwards are bitwise reproducible (B200_STAT_Q1 / B200_STAT_Q2 below) */
   void* out;
   int out_mode;        /* B200_OUT_* */
   int out_ld;          /* channel stride of NHWC outputs; for NCHW outputs the channel count */
@@ -78,12 +82,13 @@ typedef struct b200_conv_desc {
 
 int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
 
-/* EXPERIMENTAL (round 2, not yet validated on hardware; the product path does not call it unless B200_FUSE_GN2=1):
- * convolution whose epilogue applies the GroupNorm (+ AdaGN scale/shift) (+ SiLU) that FOLLOWS it, i.e. conv1 -> norm2
+/* Convolution whose epilogue applies the GroupNorm (+ AdaGN scale/shift) (+ SiLU) that FOLLOWS it, i.e. conv1 -> norm2
  * of a ResBlock (models/unet.py:20-24,38-40; models/unet_categorial_adagn.py:36-41,58-60), writing only the bf16
  * NHWC operand of the next convolution: out_norm = SiLU(GN(conv(x) + bias + rowadd)).  Possible when one 256-pixel
  * tile holds whole images (Ho*Wo in {16, 64, 256}) and its 128 channels whole groups, so the statistics are complete
- * inside a CTA.  d->out / d->stats / d->residual must be NULL-equivalent (ignored); N % 128 == 0. */
+ * inside a CTA (tiles are chosen so that they hold whole images and are full: B must be a multiple of 64 / (Ho*Wo) for
+ * 4x4 images).  d->out / d->stats / d->residual must be NULL-equivalent (ignored); N % 128 == 0; N / groups a power of
+ * two <= 32.  The engine uses it for every eligible ResBlock at inference (B200_FUSE_GN2=0 restores two launches). */
 typedef struct b200_gn_fuse_desc {
   const float* gamma;        /* [N] */
   const float* beta;         /* [N] */
@@ -100,7 +105,7 @@ int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void
 /* First convolution of the UNet (models/unet.py:72,123): NCHW fp32 image, tiny Cin (1..4), 3x3 s1 p1,
  * -> fp32 NHWC [B][H][W][Cout].  Weights are the reference's OIHW fp32 tensor as is. */
 int b200_conv3x3_first(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc,
-                       float* stats /* optional [B][Cout][2], pre-zeroed, as in b200_conv_desc.stats */,
+                       long long* stats /* optional [B][Cout][2] int64, pre-zeroed, as in b200_conv_desc.stats */,
                        int B, int Cin, int H, int W, int Cout, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -117,12 +122,13 @@ int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, in
                             const float* shift, int ss_ld, int apply_silu, int resample, void* out_bf16,
                             void* raw_out_bf16, void* stream);
 
-/* Streaming variant of K3 for inputs whose per-(image, channel) statistics [B][C][2] = (sum, sum of squares) were
+/* Streaming variant of K3 for inputs whose per-(image, channel) statistics [B][C][2] = (sum, sum of squares), int64
+ * fixed point with scales B200_STAT_Q1 / B200_STAT_Q2, were
  * accumulated by the producing kernel (b200_conv_desc.stats): one coalesced pass, 4 B read + 2 B written per
  * element.  Same semantics and arguments as b200_groupnorm_silu_fwd otherwise. */
 int b200_groupnorm_apply_fwd(const void* x0, int x0_is_bf16 /* x0 is bf16 NHWC (single source, statistics taken
-                             from the fp32 accumulators of its producer) */, int C0, const float* stats0,
-                             const float* x1, int C1, const float* stats1, int B, int HW, int W, int groups,
+                             from the fp32 accumulators of its producer) */, int C0, const long long* stats0,
+                             const float* x1, int C1, const long long* stats1, int B, int HW, int W, int groups,
                              const float* gamma,
                              const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
                              int apply_silu, int resample, void* out_bf16, void* raw_out_bf16, void* stream);
@@ -287,8 +293,8 @@ int b200_conv2d_wgrad(const b200_wgrad_desc* d, void* stream);
  * The keep mask is a counter-based hash of (seed, element index): the backward regenerates it, nothing is stored.
  * seed = drop_seed + *drop_seed_dev (a device scalar, may be NULL): the per-forward base lives in device memory so that
  * a captured CUDA graph of the training step draws fresh masks on every replay. */
-int b200_groupnorm_apply_train_fwd(const void* x0, int x0_is_bf16, int C0, const float* stats0, const float* x1, int C1,
-                                   const float* stats1, int B, int HW, int W, int groups, const float* gamma,
+int b200_groupnorm_apply_train_fwd(const void* x0, int x0_is_bf16, int C0, const long long* stats0, const float* x1, int C1,
+                                   const long long* stats1, int B, int HW, int W, int groups, const float* gamma,
                                    const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
                                    int apply_silu, int resample, float drop_p, unsigned long long drop_seed,
                                    const unsigned long long* drop_seed_dev,
@@ -304,8 +310,8 @@ int b200_dropout_mask(float* out, long long n, float p, unsigned long long seed,
  * dgamma/dbeta [C] accumulate; dscale/dshift [B][dss_ld] are written. sums: workspace [B][8][C] floats. */
 typedef struct b200_gn_bwd_desc {
   const void* g;
-  const float* x0; int C0; const float* stats0;
-  const float* x1; int C1; const float* stats1;
+  const float* x0; int C0; const long long* stats0;
+  const float* x1; int C1; const long long* stats1;
   int B, HW, W, groups;
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;

@@ -8,6 +8,7 @@ It restates, in plain PyTorch fp32 on the CPU, what the reference computes in
   diffusions/ddpm.py:152-172       (diffuse)
   diffusions/ddpm.py:174-261       (predict + DDPM posterior step, three variance types)
   diffusions/ddim.py:57-86         (DDIM step)
+  diffusions/ddim.py:88-132        (DDIM inversion step and loop), :202-242 (inversion under classifier-free guidance)
   diffusions/ddpm.py:263-351, diffusions/ddim.py:161-200  (sampling loops incl. classifier-free guidance)
 with the random draws made injectable so that two implementations can consume identical noise.
 
@@ -211,6 +212,50 @@ class DDIMRef(DDPMRef):
             reverse_eps = torch.randn_like(xt)
         sample = mean if t == 0 else mean + torch.sqrt(var) * reverse_eps
         return {'sample': sample, 'mean': mean, 'var': var, 'pred_x0': x0, 'pred_eps': eps, 'reverse_eps': reverse_eps}
+
+    # ---- DDIM inversion (ddim.py:88-132): the deterministic update run towards higher noise levels ----
+    def denoise_inversion(self, model_output, xt, t, t_next):
+        """x_t -> x_{t_next}: sqrt(ac_next) x0 + sqrt(1 - ac_next) eps; ac_next = 0 past the last step (ddim.py:99)."""
+        if self.eta != 0.:
+            raise ValueError(f'DDIM inversion is only valid when eta=0, get {self.eta}')
+        pr = self.predict(model_output, xt, t)
+        x0, eps = pr['pred_x0'], pr['pred_eps']
+        ac_next = self.alphas_cumprod[t_next] if t_next < self.total_steps else torch.tensor(0.0)
+        sample = torch.sqrt(ac_next) * x0 + torch.sqrt(1. - ac_next) * eps
+        return {'sample': sample, 'pred_x0': x0, 'pred_eps': eps}
+
+    def _inversion_pairs(self):
+        seq = self.respaced_seq.tolist()
+        return list(zip(seq[:-1], seq[1:]))      # ddim.py:113-114: the last respaced step is only ever a target
+
+    def sample_inversion_loop(self, model, img, model_kwargs=None):
+        kw = model_kwargs or {}
+        for (t, tn) in self._inversion_pairs():
+            tb = torch.full((img.shape[0],), t, dtype=torch.long, device=img.device)
+            out = self.denoise_inversion(model(img, tb, **kw), img, t, tn)
+            img = out['sample']
+            yield out
+
+    def sample_inversion(self, model, img, model_kwargs=None):
+        out = None
+        for out in self.sample_inversion_loop(model, img, model_kwargs):
+            pass
+        return out['sample']
+
+    def sample_inversion_loop_cfg(self, model, img, guidance_scale, cond_kwargs, uncond_kwargs):
+        """ddim.py:202-232: per-branch predict (with clip), the (1 - s) / s mix, then the inversion step on the mix."""
+        for (t, tn) in self._inversion_pairs():
+            tb = torch.full((img.shape[0],), t, dtype=torch.long, device=img.device)
+            eps_c = self.predict(model(img, tb, **cond_kwargs), img, t)['pred_eps']
+            eps_u = self.predict(model(img, tb, **uncond_kwargs), img, t)['pred_eps']
+            mix = (1 - guidance_scale) * eps_u + guidance_scale * eps_c
+            keep, self.objective = self.objective, 'pred_eps'
+            try:
+                out = self.denoise_inversion(mix, img, t, tn)
+            finally:
+                self.objective = keep
+            img = out['sample']
+            yield out
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -569,6 +569,52 @@ def case_ode_sampling():
     return ok
 
 
+def case_ddim_inversion():
+    """DDIM inversion (reference diffusions/ddim.py:88-132, 202-242) through DDIM / DDIMCFG.sample_inversion:
+    (1) CIFAR-10 UNet, B=8, 20 respaced steps: latent vs the fp32 oracle's latent (PSNR >= 40 dB, peak-to-peak 2 as for
+        samples), then the round trip x0 -> latent -> DDIM-20 sample of OUR path against the oracle's round trip;
+    (2) the classifier-free-guidance inversion run frozen from the REFERENCE itself (tests/golden/ddim_inversion.pt,
+        tiny AdaGN UNet, s = 2, 10 steps): our latent vs the reference's (gate 35 dB: the guidance mix amplifies the
+        per-branch bf16 error by |1-s| + |s| = 3)."""
+    _no_tf32()
+    m, ref = _build(CIFAR)
+    B = 8
+    x0 = (torch.randn(B, 3, 32, 32, generator=torch.Generator(device='cpu').manual_seed(21)) * 0.5).clamp(-1, 1).to(DEV)
+    kw = dict(total_steps=1000, respace_type='uniform', respace_steps=20)
+    ours = diffusions.DDIM(device=DEV, **kw)
+    orc = R.DDIMRef(**kw)
+    orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+    ok = True
+    with torch.no_grad():
+        lat = ours.sample_inversion(m, x0, tqdm_kwargs=dict(disable=True))
+        lat_ref = orc.sample_inversion(ref, x0)
+        psnr = _psnr(lat, lat_ref)
+        _emit(case='ddim inversion-20 latent vs oracle', psnr_db=psnr, gate=40.0, latent_std=lat_ref.std().item(),
+              ok=psnr >= 40.0)
+        ok &= psnr >= 40.0
+        back = ours.sample(m, lat, tqdm_kwargs=dict(disable=True))
+        back_ref = orc.sample(ref, lat_ref, noises=[torch.zeros_like(x0)] * 20)
+        p2 = _psnr(back.clamp(-1, 1), back_ref.clamp(-1, 1))
+        _emit(case='ddim inversion-20 + DDIM-20 round trip vs oracle round trip', psnr_db=p2, gate=40.0,
+              oracle_roundtrip_psnr_vs_x0=_psnr(back_ref.clamp(-1, 1), x0), ours_roundtrip_psnr_vs_x0=_psnr(back.clamp(-1, 1), x0),
+              ok=p2 >= 40.0)
+        ok &= p2 >= 40.0
+        # (2) reference-frozen guided inversion
+        g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ddim_inversion.pt'), weights_only=False)
+        uf = torch.load(os.path.join(ROOT, 'tests', 'golden', 'unet_forward.pt'), weights_only=False)
+        rc = g['runs']['cfg10']
+        torch.manual_seed(2022)
+        mc = models.UNetCategorialAdaGN(**uf['tiny_adagn']['cfg']).to(DEV).eval()
+        dc = diffusions.DDIMCFG(guidance_scale=rc['guidance_scale'], device=DEV, **rc['kw'])
+        latc = dc.sample_inversion(mc, rc['x0'].to(DEV), uncond_conditioning=None, tqdm_kwargs=dict(disable=True),
+                                   model_kwargs=dict(y=rc['y'].to(DEV)))
+        p3 = _psnr(latc.cpu(), rc['latent'])
+        _emit(case='ddimcfg inversion-10 s=2 latent vs REFERENCE golden (tiny AdaGN UNet)', psnr_db=p3, gate=35.0,
+              ok=p3 >= 35.0)
+        ok &= p3 >= 35.0
+    return ok
+
+
 def case_timing():
     """Orientation numbers (not the bench): forward and DDIM-50 at B=256."""
     m, _ = _build(CIFAR)

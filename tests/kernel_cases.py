@@ -113,7 +113,7 @@ def _conv_case(name, B, Cin, Cout, H, W, ksize=3, stride=1, bias=True, rowadd=Fa
         out = torch.full((B, Cout, Ho, Wo), float('nan'), device=DEV,
                          dtype=torch.float32 if out_mode == K.OUT_F32_NCHW else torch.bfloat16)
     res = res_nchw.permute(0, 2, 3, 1).contiguous() if residual else None
-    stats = torch.zeros(B, Cout, 2, device=DEV) if (out_mode == K.OUT_F32_NHWC and Cout > 32) else None
+    stats = K.new_stats(B, Cout, DEV) if (out_mode == K.OUT_F32_NHWC and Cout > 32) else None
     K.conv2d(a0, wp, Cout, B, Ho, Wo, taps, a0_geom=geom,
              a1=_nhwc_bf16(x1) if sc_cin else None, a1_geom=(sc_cin, Ho, Wo, 1) if sc_cin else None,
              bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0, residual=res, res_ld=Cout, out=out,
@@ -121,9 +121,20 @@ def _conv_case(name, B, Cin, Cout, H, W, ksize=3, stride=1, bias=True, rowadd=Fa
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2) if out_mode in (K.OUT_F32_NHWC, K.OUT_BF16_NHWC) else out
     if stats is not None:
-        # fused GroupNorm statistics: per-(image, channel) sum and sum of squares (fp32 atomics: 1e-4 relative)
+        # fused GroupNorm statistics: per-(image, channel) sum and sum of squares (int64 fixed point; per-thread fp32
+        # partial sums: 1e-4 relative)
         ref_st = torch.stack([ref.sum(dim=(2, 3)), (ref * ref).sum(dim=(2, 3))], dim=-1)
-        if not _report(name + ' [fused GN stats]', stats, ref_st, rtol=2e-4, atol=2e-2):
+        if not _report(name + ' [fused GN stats]', K.stats_to_float(stats).float(), ref_st, rtol=2e-4, atol=2e-2):
+            return False
+        # integer atomics: a second launch must reproduce the statistics bit for bit
+        stats2 = K.new_stats(B, Cout, DEV)
+        K.conv2d(a0, wp, Cout, B, Ho, Wo, taps, a0_geom=geom,
+                 a1=_nhwc_bf16(x1) if sc_cin else None, a1_geom=(sc_cin, Ho, Wo, 1) if sc_cin else None,
+                 bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0, residual=res, res_ld=Cout, out=out,
+                 out_mode=out_mode, stats=stats2)
+        torch.cuda.synchronize()
+        if not torch.equal(stats, stats2):
+            print(json.dumps(dict(case=name + ' [fused GN stats reproducible]', ok=False)))
             return False
     # fp32 accumulation order differs from cuDNN/cuBLAS: 1e-4 relative on O(1) values; bf16 outputs: 1 ulp = 2^-8
     if out_mode in (K.OUT_BF16_NHWC, K.OUT_BF16_NCHW):
@@ -284,7 +295,7 @@ def _gn_case(name, B, C0, C1, H, W, silu=True, adagn=False, resample=0, raw=Fals
     # streaming variant fed with producer-side statistics
     if C0 % 4 == 0 and C1 % 4 == 0 and not (raw and resample == 1):
         def st(x):
-            return torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
+            return K.stats_from_float(torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous())
         out2 = torch.full((B, Ho, Wo, C), float('nan'), device=DEV, dtype=torch.bfloat16)
         raw2 = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16) if raw else None
         K.groupnorm_apply(x0, C0, st(x0), x1, C1, st(x1) if C1 else None, B, H * W, W, 32, gamma, beta, eps, out2,
@@ -348,11 +359,11 @@ def case_misc():
         b = _gen(Cout, seed=3)
         ref = F.conv2d(x, w, b, padding=1)
         out = torch.full((B, H, H, Cout), float('nan'), device=DEV)
-        st = torch.zeros(B, Cout, 2, device=DEV)
+        st = K.new_stats(B, Cout, DEV)
         K.conv3x3_first(x, w, b, out, st)
         torch.cuda.synchronize()
         ok &= _report(f'first conv {Cin}->{Cout} @{H}', out.permute(0, 3, 1, 2), ref, 1e-5, 1e-5)
-        ok &= _report(f'first conv {Cin}->{Cout} @{H} [fused GN stats]', st,
+        ok &= _report(f'first conv {Cin}->{Cout} @{H} [fused GN stats]', K.stats_to_float(st).float(),
                       torch.stack([ref.sum(dim=(2, 3)), (ref * ref).sum(dim=(2, 3))], dim=-1), 2e-4, 2e-2)
     x = _gen(2, 8, 8, 128, seed=4)
     o = torch.empty(2, 8, 8, 128, device=DEV, dtype=torch.bfloat16)
@@ -575,7 +586,7 @@ def _gn_bwd_case(name, B, H, W, C0, C1, *, silu=True, adagn=False, resample=0, d
     y.backward(g.permute(0, 3, 1, 2))
     # ---- kernels: statistics as the conv epilogue would deliver them ----
     def stats(x):
-        return torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
+        return K.stats_from_float(torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous())
     st0 = stats(x0)
     st1 = stats(x1) if C1 else None
     sums = torch.empty(B, 8, C, device=DEV)
@@ -765,6 +776,44 @@ def case_ode_samplers():
     print(json.dumps({'case': f'euler/heun single steps ({len(g["steps"])} cases) vs reference golden',
                       'max_rel_err': worst, 'gate': 2e-6, 'ok': good}), flush=True)
     return ok and good
+
+
+def case_ddim_inversion():
+    """DDIM.denoise_inversion / DDIMCFG's guided inversion step (K4 with the inversion coefficient row) against the 48
+    single-step fixtures frozen from the reference (diffusions/ddim.py:88-110; oracle/gen_golden_inversion.py) and,
+    for the guided step, against the oracle's op sequence (ddim.py:202-232)."""
+    sys.path.insert(0, ROOT)
+    from oracle import diffusion_ref as R
+    import diffusions
+    g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ddim_inversion.pt'), weights_only=False)
+    xt, mo, mo_u = g['xt'].to(DEV), g['mo'].to(DEV), g['mo_u'].to(DEV)
+    worst = worst_cfg = 0.0
+    for c in g['steps']:
+        kw = dict(total_steps=1000, beta_schedule=c['beta'], objective=c['objective'], clip_denoised=c['clip'],
+                  respace_type='uniform', respace_steps=50)
+        o = diffusions.DDIM(device=DEV, **kw).denoise_inversion(mo.clone(), xt, c['t'], c['t_next'])
+        for k, v in c['out'].items():
+            worst = max(worst, (o[k].cpu() - v).abs().max().item() / max(1.0, v.abs().max().item()))
+        # guided step: ours fuses predict(cond), predict(uncond), mix, predict(mix), step; the oracle walks them one by one
+        oc = diffusions.DDIMCFG(guidance_scale=2.5, device=DEV, **kw)
+        got = oc._inversion_impl(mo.clone(), xt, c['t'], c['t_next'], mo_u.clone(), 2.5)
+        ref = R.DDIMRef(**kw)
+        eps_c = ref.predict(g['mo'], g['xt'], c['t'])['pred_eps']
+        eps_u = ref.predict(g['mo_u'], g['xt'], c['t'])['pred_eps']
+        ref.objective = 'pred_eps'
+        want = ref.denoise_inversion((1 - 2.5) * eps_u + 2.5 * eps_c, g['xt'], c['t'], c['t_next'])
+        for k in ('sample', 'pred_x0', 'pred_eps'):
+            worst_cfg = max(worst_cfg, (got[k].cpu() - want[k]).abs().max().item() / max(1.0, want[k].abs().max().item()))
+    raised = False
+    try:
+        diffusions.DDIM(eta=0.5, device=DEV).denoise_inversion(mo, xt, 0, 20)
+    except ValueError:
+        raised = True
+    good = worst <= 2e-6 and worst_cfg <= 1e-5 and raised
+    print(json.dumps({'case': f'DDIM inversion single steps ({len(g["steps"])} cases) vs reference golden',
+                      'max_rel_err': worst, 'gate': 2e-6, 'cfg_max_rel_err': worst_cfg, 'cfg_gate': 1e-5,
+                      'eta_nonzero_raises': raised, 'ok': good}), flush=True)
+    return good
 
 
 # ----------------------------------------------------------------------------------------------------

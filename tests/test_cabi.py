@@ -29,7 +29,7 @@ def test_header_symbols_are_exported():
 def test_version_and_error_string():
     import b200diff
     lib = b200diff.lib()
-    assert lib.b200_version() == 100
+    assert lib.b200_version() == 200
     assert isinstance(lib.b200_last_error(), bytes)
     assert b200diff.direct_launch_count() >= 0
 

@@ -210,3 +210,35 @@ def test_ode_samplers_match_reference(golden_dir, gold):
         for tag, cls in (('euler10', R.EulerRef), ('heun10', R.HeunRef)):
             got = cls(respace_type='uniform', respace_steps=10).sample(orc, g['x0'])
             assert torch.allclose(got, g['runs'][tag], rtol=0, atol=1e-4), tag
+
+
+def test_ddim_inversion_matches_reference(golden_dir, gold):
+    """DDIMRef.denoise_inversion / sample_inversion(_cfg) against the fixtures frozen from the reference's
+    diffusions/ddim.py:88-132, 202-242 by oracle/gen_golden_inversion.py: 48 single steps bit-exact (3 objectives x clip x
+    2 beta schedules x 4 (t, t_next) pairs incl. a target past the end of the schedule), two 10-step inversion runs."""
+    g = torch.load(os.path.join(golden_dir, 'ddim_inversion.pt'), weights_only=False)
+    xt, mo = g['xt'], g['mo']
+    assert len(g['steps']) == 48
+    for c in g['steps']:
+        d = R.DDIMRef(total_steps=1000, beta_schedule=c['beta'], objective=c['objective'], clip_denoised=c['clip'],
+                      respace_type='uniform', respace_steps=50)
+        o = d.denoise_inversion(mo.clone(), xt, c['t'], c['t_next'])
+        for k, v in c['out'].items():
+            assert torch.equal(o[k], v), (c['objective'], c['clip'], c['beta'], c['t'], c['t_next'], k)
+    with pytest.raises(ValueError):
+        R.DDIMRef(eta=0.5).denoise_inversion(mo, xt, 0, 20)
+    with torch.no_grad():
+        r = g['runs']['uncond10']
+        cfg = gold['unet_forward']['tiny']['cfg']
+        orc = UNetRef(_product_state_dict('tiny', cfg, 2022), dim=32, n_heads=1)
+        got = R.DDIMRef(**r['kw']).sample_inversion(orc, r['x0'])
+        assert torch.allclose(got, r['latent'], rtol=0, atol=1e-4)
+        rc = g['runs']['cfg10']
+        ccfg = gold['unet_forward']['tiny_adagn']['cfg']
+        orcc = UNetRef(_product_state_dict('tiny_adagn', ccfg, 2022), dim=64, adagn=True, attn_head_dims=64,
+                       num_res_blocks=2)
+        out = None
+        for out in R.DDIMRef(**rc['kw']).sample_inversion_loop_cfg(orcc, rc['x0'], rc['guidance_scale'], dict(y=rc['y']),
+                                                                  dict(y=None)):
+            pass
+        assert torch.allclose(out['sample'], rc['latent'], rtol=0, atol=1e-4)

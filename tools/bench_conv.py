@@ -45,7 +45,7 @@ def run(name, Cin, Cout, H, mode='3x3', residual=False, rowadd=False, stats=True
         out = torch.empty(B, Cout, oh, oh, device=DEV, dtype=torch.bfloat16)
     res = torch.randn(B, oh, oh, Cout, device=DEV) if residual else None
     ra = torch.randn(B, Cout, device=DEV) if rowadd else None
-    st = torch.zeros(B, Cout, 2, device=DEV) if (stats and out_mode == K.OUT_F32_NHWC) else None
+    st = K.new_stats(B, Cout, DEV) if (stats and out_mode == K.OUT_F32_NHWC) else None
     bias = torch.randn(Cout, device=DEV)
 
     def call():

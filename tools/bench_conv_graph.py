@@ -30,7 +30,7 @@ def run(name, Cin, Cout, H, k=3, residual=False, out_mode=K.OUT_F32_NHWC, reps=2
     else:
         out = torch.empty(B, Cout, H, W, device=DEV, dtype=torch.bfloat16)
     res = torch.randn(B, H, W, Cout, device=DEV) if residual else None
-    st = torch.zeros(B, Cout, 2, device=DEV) if out_mode == K.OUT_F32_NHWC else None
+    st = K.new_stats(B, Cout, DEV) if out_mode == K.OUT_F32_NHWC else None
     bias = torch.randn(Cout, device=DEV)
 
     def call():

@@ -18,7 +18,7 @@ def run(B, H, C, bf16_in=False, scale_shift=False, copies=None):
     in_bytes = n * (2 if bf16_in else 4)
     copies = copies or max(2, int(400e6 // in_bytes) + 1)   # > 400 MB of distinct input between reuses
     xs = [torch.randn(B, H, W, C, device=DEV) for _ in range(copies)]
-    st = torch.stack([xs[0].sum(dim=(1, 2)), (xs[0] * xs[0]).sum(dim=(1, 2))], dim=-1).contiguous()
+    st = K.stats_from_float(torch.stack([xs[0].sum(dim=(1, 2)), (xs[0] * xs[0]).sum(dim=(1, 2))], dim=-1).contiguous())
     if bf16_in:
         xs = [x.to(torch.bfloat16) for x in xs]
     outs = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(copies)]

@@ -33,7 +33,7 @@ def timeit(fn, reps=10):
 def run(C, H, bf16_out=True, drop=0.1):
     W = H
     x = torch.randn(B, H, W, C, device=DEV)
-    st = torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous()
+    st = K.stats_from_float(torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1).contiguous())
     g = torch.randn(B, H, W, C, device=DEV).to(torch.bfloat16)
     gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
     sums = torch.empty(B, 8, C, device=DEV)

@@ -16,7 +16,7 @@ a0 = torch.randn(B, H, H, Cin, device='cuda').to(torch.bfloat16)
 w = K.pack_weight(torch.randn(Cout, Cin, k, k, device='cuda') / math.sqrt(k * k * Cin))
 out = torch.empty(B, H, H, Cout, device='cuda')
 res = torch.randn(B, H, H, Cout, device='cuda')
-st = torch.zeros(B, Cout, 2, device='cuda')
+st = K.new_stats(B, Cout, 'cuda')
 bias = torch.randn(Cout, device='cuda')
 taps = K.taps_3x3_s1() if k == 3 else K.taps_1x1()
 for _ in range(6):

@@ -149,6 +149,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# --------------------------------------------------------------------------------------------------------------
+# Checks and baselines around the timed region (never inside it)
+# --------------------------------------------------------------------------------------------------------------
+def parity_check(model, diffuser, noise_dev, B, S):
+    """Parity of the EXACT benchmarked call (batch 256, graph-replayed DDIM-50) against the fp32 oracle on the same GPU
+    (PyTorch eager, TF32 off): eps rel-L2 at one timestep and PSNR of the final samples.  Outside the timed region."""
+    import math
+    import diffusions  # noqa: F401
+    from oracle import diffusion_ref as R
+    from oracle.unet_ref import UNetRef
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = UNetRef(model.state_dict(), dim=CIFAR['dim'], n_heads=1).to(noise_dev.device)
+        orc = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=S)
+        orc.alphas_cumprod = orc.alphas_cumprod.to(noise_dev.device)
+        with torch.no_grad():
+            t = torch.full((1,), 500, device=noise_dev.device, dtype=torch.long).expand(B)
+            e_our, e_ref = model(noise_dev, t), ref(noise_dev, t.contiguous())
+            rel = ((e_our - e_ref).norm() / e_ref.norm()).item()
+            got = diffuser.sample(model, noise_dev, tqdm_kwargs=dict(disable=True)).clamp(-1, 1)
+            got2 = diffuser.sample(model, noise_dev, tqdm_kwargs=dict(disable=True)).clamp(-1, 1)
+            want = orc.sample(ref, noise_dev, noises=[torch.zeros_like(noise_dev)] * S).clamp(-1, 1)
+        mse = ((got - want) ** 2).mean().item()
+        per_img = ((got - want) ** 2).flatten(1).mean(dim=1)
+        return {'checked': f'the benchmarked call: batch {B}, DDIM-{S} through DDIM.sample (CUDA-graph replay) vs oracle fp32 '
+                           f'eager on the same GPU, TF32 off, same initial noise',
+                'eps_rel_l2': rel, 'eps_gate': 1e-2,
+                'ddim_psnr_db': 10 * math.log10(4.0 / max(mse, 1e-20)), 'psnr_gate_db': 40.0,
+                'worst_image_psnr_db': 10 * math.log10(4.0 / max(per_img.max().item(), 1e-20)),
+                'bitwise_reproducible': bool(torch.equal(got, got2)),
+                'ok': bool(rel <= 1e-2 and mse <= 4.0 / 10 ** 4.0 and torch.equal(got, got2))}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+def gpu_reference(model, noise_dev, B, S, substeps=3):
+    """The kernel-for-kernel bar of BASELINE.md section 3: the reference's own op sequence (oracle/unet_ref.py = the same
+    F.conv2d / group_norm / bmm calls, PyTorch eager, cuDNN / cuBLAS) on THIS GPU, same batch: fp32, TF32, and
+    autocast(bf16) + channels_last.  `substeps` timed DDIM steps after one warm-up step, extrapolated to S (identical
+    work per step).  Reported beside our number, not the target."""
+    from oracle import diffusion_ref as R
+    from oracle.unet_ref import UNetRef
+    dev = noise_dev.device
+    out = {'kind': 'port (oracle/unet_ref.py + diffusion_ref.py: the reference\'s ATen op sequence in PyTorch eager on this GPU)',
+           'sample': f'batch {B}, {substeps} of {S} DDIM steps timed after 1 warm-up step, extrapolated linearly'}
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    d = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=S)
+    d.alphas_cumprod = d.alphas_cumprod.to(dev)
+    pairs = d._pairs()
+    sd = model.state_dict()
+    try:
+        torch.backends.cudnn.benchmark = True
+        for tag, tf32, autocast in (('fp32', False, False), ('tf32', True, False), ('bf16_autocast_channels_last', True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            sdx = {k: (v.contiguous(memory_format=torch.channels_last) if (autocast and v.dim() == 4) else v) for k, v in sd.items()}
+            net = UNetRef(sdx, dim=CIFAR['dim'], n_heads=1).to(dev)
+            x = noise_dev.contiguous(memory_format=torch.channels_last) if autocast else noise_dev
+
+            def steps(n, img):
+                for (t, tp) in pairs[:n]:
+                    tb = torch.full((B,), t, dtype=torch.long, device=dev)
+                    if autocast:
+                        with torch.autocast('cuda', dtype=torch.bfloat16):
+                            eps = net(img, tb).float()
+                    else:
+                        eps = net(img, tb)
+                    img = d.denoise(eps, img, t, tp, torch.zeros_like(img))['sample']
+                return img
+            with torch.no_grad():
+                steps(1, x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                steps(substeps, x)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / substeps
+            out[tag] = {'images_per_s': B / (ms * 1e-3 * S), 'ms_per_ddim_step': ms}
+            del net
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = tf
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -290,12 +379,24 @@ def run_ours(args):
                                       'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
                                       'traffic': gn_traffic,
                                       'algorithmic_bytes_per_launch': gn['bytes'] / max(gn['n'], 1)}
+    if rank == 0 and not args.no_parity:
+        try:
+            line['parity'] = parity_check(model, diffuser, noise_dev, B, S)
+        except Exception as e:  # noqa: BLE001
+            line['parity'] = {'error': repr(e)}
     if world == 1 and not args.no_extras:
+        try:
+            line['gpu_reference'] = gpu_reference(model, noise_dev, B, S)
+            line['gpu_reference']['ours_over_bf16_autocast'] = value / line['gpu_reference']['bf16_autocast_channels_last']['images_per_s']
+        except Exception as e:  # noqa: BLE001
+            line['gpu_reference'] = {'error': repr(e)}
+    if not args.no_extras:
         # free the headline model's arena before the (larger) secondary workloads
         del model, diffuser
         torch.cuda.empty_cache()
         try:
-            line['extras'] = _extras(dev, peaks)
+            # world > 1: only the data-parallel training step (collective: every rank takes part)
+            line['extras'] = _extras(dev, peaks, world, rank)
             if 'sampler_update' in line['extras']:
                 line['roofline_sampler'] = line['extras'].pop('sampler_update')
         except Exception as e:  # noqa: BLE001  (secondary numbers must never cost the headline line)
@@ -447,7 +548,8 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--sample-steps', type=int, default=50)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extras', action='store_true', help='skip the ADM-256 forward and training-step measurements')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary workloads (ADM-256, training step, configs A/C/D/E, GPU reference)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the parity check of the benchmarked call against the oracle')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -77,6 +77,12 @@ class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next
     ]
 
 
+class SplitDesc(Structure):       # mirrors b200_split_desc (FP32 mode: fp32 -> bf16 hi/lo split operands)
+    _fields_ = [('in_', c_void_p), ('rows', c_longlong), ('in_ld', c_int), ('in_col0', c_int), ('C', c_int), ('group', c_int),
+                ('pattern', c_int), ('act', c_int), ('out', c_void_p), ('out_ld', c_int), ('out_col0', c_int),
+                ('planes_rows', c_int), ('parity_H', c_int), ('parity_W', c_int)]
+
+
 class GemmOperand(Structure):
     _fields_ = [('ptr', c_void_p), ('rows', c_int), ('ld', c_int), ('batch_stride', c_longlong),
                 ('col_base', c_int), ('col_head', c_int), ('mn_major', c_int), ('per_head_batch', c_int)]
@@ -165,7 +171,7 @@ def lib():
     L.b200_time_embed.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
-    L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    L.b200_diffuse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     ull = ctypes.c_ulonglong
     L.b200_groupnorm_apply_train_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                                  c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
@@ -188,6 +194,13 @@ def lib():
     L.b200_mse_loss_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]
     for name in BACKWARD_SYMBOLS:
         getattr(L, name).restype = c_int
+    L.b200_split_cast.argtypes = [POINTER(SplitDesc), c_void_p]
+    L.b200_groupnorm_apply_split_fwd.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                                 c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,
+                                                 c_int, c_void_p, c_void_p, c_void_p]
+    L.b200_softmax_rows_split.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]
+    for name in PRECISE_SYMBOLS:
+        getattr(L, name).restype = c_int
     L.b200_gemm_batched.argtypes = [POINTER(GemmDesc), c_void_p]
     L.b200_conv2d_wgrad.argtypes = [POINTER(WgradDesc), c_void_p]
     for name in ('b200_gemm_batched', 'b200_conv2d_wgrad', 'b200_conv2d_fwd', 'b200_conv3x3_first', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd',
@@ -206,7 +219,9 @@ BACKWARD_SYMBOLS = (
     'b200_optimizer_step', 'b200_ode_step', 'b200_to_uint8_hwc', 'b200_pack_weights',
 )
 
-EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + (
+PRECISE_SYMBOLS = ('b200_split_cast', 'b200_groupnorm_apply_split_fwd', 'b200_softmax_rows_split')
+
+EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + PRECISE_SYMBOLS + (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
@@ -369,9 +384,10 @@ def pack_weight(w: torch.Tensor, shortcut_w: torch.Tensor = None) -> torch.Tenso
     return m.to(torch.bfloat16).contiguous()
 
 
-def pack_weight_up2(w: torch.Tensor) -> torch.Tensor:
+def pack_weight_up2(w: torch.Tensor, split: bool = False) -> torch.Tensor:
     """3x3 weights -> the four 2x2 phase kernels of 'nearest-2x then 3x3' stacked as [4*Cout][4*Cin] bf16.
-    Row taps: phase a=0 -> {W[0], W[1]+W[2]}, a=1 -> {W[0]+W[1], W[2]}; same for columns (summed in fp32)."""
+    Row taps: phase a=0 -> {W[0], W[1]+W[2]}, a=1 -> {W[0]+W[1], W[2]}; same for columns (summed in fp32).
+    split=True (FP32 mode): [4*Cout][4*3*Cin], per tap [w_hi | w_hi | w_lo] of the fp32 phase weights."""
     co, ci, _, _ = w.shape
     w = w.detach().float()
     rows = {0: [w[:, :, 0:1], w[:, :, 1:2] + w[:, :, 2:3]], 1: [w[:, :, 0:1] + w[:, :, 1:2], w[:, :, 2:3]]}
@@ -383,7 +399,13 @@ def pack_weight_up2(w: torch.Tensor) -> torch.Tensor:
                 wr = rows[a][i]  # [co, ci, 1, 3]
                 cols = {0: [wr[..., 0], wr[..., 1] + wr[..., 2]], 1: [wr[..., 0] + wr[..., 1], wr[..., 2]]}
                 for j in range(2):
-                    taps.append(cols[b][j].reshape(co, ci))
+                    t32 = cols[b][j].reshape(co, ci)
+                    if split:
+                        hi = t32.to(torch.bfloat16)
+                        lo = (t32 - hi.float()).to(torch.bfloat16)
+                        taps += [hi, hi, lo]
+                    else:
+                        taps.append(t32)
             mats.append(torch.cat(taps, dim=1))
     return torch.cat(mats, dim=0).to(torch.bfloat16).contiguous()
 
@@ -513,6 +535,52 @@ def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, bet
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# FP32 mode ("bf16x3", csrc/precise.cu): split operands
+# --------------------------------------------------------------------------------------------------
+SPLIT_ACT, SPLIT_WEIGHT = 0, 1    # [hi | lo | hi] (activation side) / [hi | hi | lo] (weight side)
+
+
+def split_cast(x, out, rows, C, *, in_ld=None, in_col0=0, group=None, pattern=SPLIT_ACT, silu=False, out_ld=None,
+               out_col0=0, planes_rows=0, parity_hw=None):
+    """fp32 [rows][in_ld] window -> bf16 split operand (b200_split_cast)."""
+    _need_cuda(x, out)
+    _need_f32(x=x)
+    if out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise RuntimeError('split_cast: out must be a contiguous bfloat16 tensor')
+    d = SplitDesc()
+    d.in_, d.rows, d.in_ld, d.in_col0, d.C = x.data_ptr(), rows, (in_ld if in_ld is not None else C), in_col0, C
+    d.group, d.pattern, d.act = (group if group is not None else C), pattern, int(silu)
+    d.out, d.out_ld, d.out_col0 = out.data_ptr(), (out_ld if out_ld is not None else 3 * C), out_col0
+    d.planes_rows = planes_rows
+    d.parity_H, d.parity_W = parity_hw if parity_hw is not None else (0, 0)
+    _launch('split_cast', lambda: _check(lib().b200_split_cast(ctypes.byref(d), _stream()), 'split_cast'),
+            nbytes=10.0 * rows * C)
+    return out
+
+
+def groupnorm_apply_split(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None,
+                          shift=None, ss_ld=0, silu=True, resample=0, raw_out=None):
+    """FP32-mode GroupNorm(+AdaGN)(+SiLU)(+resample): out = split operand [B][HW_out][3C] (b200_groupnorm_apply_split_fwd)."""
+    _need_cuda(x0, stats0, out)
+    _need_stats(stats0, stats1)
+    _need_f32(x0=x0, x1=x1, gamma=gamma, beta=beta)
+    C = C0 + (C1 if x1 is not None else 0)
+    _launch('groupnorm_apply', lambda: _check(lib().b200_groupnorm_apply_split_fwd(
+        x0.data_ptr(), C0, stats0.data_ptr(), _ptr(x1), C1, _ptr(stats1), B, HW, W, groups, _ptr(gamma), _ptr(beta),
+        float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu), resample, out.data_ptr(), _ptr(raw_out), _stream()),
+        'groupnorm_apply_split_fwd'),
+        nbytes=4.0 * B * HW * C + 6.0 * B * HW * C * ({0: 1.0, 1: 0.25, 2: 4.0}[resample]) +
+        (6.0 * B * HW * C if raw_out is not None else 0.0))
+    return out
+
+
+def softmax_rows_split(S, P, rows, T, scale):
+    _need_cuda(S, P)
+    _need_f32(S=S)
+    _check(lib().b200_softmax_rows_split(S.data_ptr(), P.data_ptr(), rows, T, float(scale), _stream()), 'softmax_rows_split')
+
+
 def cast_bf16(x, out, B, H, W, C, parity_split=False):
     _need_cuda(x, out)
     _launch('cast_bf16', lambda: _check(lib().b200_cast_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C,
@@ -555,6 +623,15 @@ def sampler_step(model_out, xt, coef_row, *, objective='pred_eps', clip=True, le
                  model_out_uncond=None, guidance_scale=1.0, sample=None, mean=None, pred_x0=None, pred_eps=None,
                  var_out=None):
     _need_cuda(model_out, xt, coef_row)
+    _need_f32(model_out=model_out, xt=xt, coef_row=coef_row, noise=noise, model_out_uncond=model_out_uncond,
+              sample=sample, mean=mean, pred_x0=pred_x0, pred_eps=pred_eps, var_out=var_out)
+    for name, v in (('noise', noise), ('sample', sample), ('mean', mean), ('pred_x0', pred_x0), ('pred_eps', pred_eps)):
+        if v is not None and v.shape != xt.shape:
+            raise RuntimeError(f'sampler_step: {name} has shape {tuple(v.shape)}, expected {tuple(xt.shape)}')
+    if model_out_uncond is not None and model_out_uncond.shape != model_out.shape:
+        raise RuntimeError('sampler_step: model_out_uncond must have the shape of model_out')
+    if model_out.shape[0] != xt.shape[0] or model_out.shape[2:] != xt.shape[2:] or model_out.shape[1] < xt.shape[1]:
+        raise RuntimeError(f'sampler_step: model output {tuple(model_out.shape)} does not match x_t {tuple(xt.shape)}')
     d = SamplerDesc()
     d.model_out, d.model_out_uncond = model_out.data_ptr(), _ptr(model_out_uncond)
     d.xt, d.noise, d.coef = xt.data_ptr(), _ptr(noise), coef_row.data_ptr()
@@ -569,10 +646,29 @@ def sampler_step(model_out, xt, coef_row, *, objective='pred_eps', clip=True, le
             nbytes=4.0 * xt.numel() * n_streams)
 
 
+def _need_f32(**ts):
+    """The kernels read raw pointers: a tensor of another dtype / layout / device would be silently misread."""
+    dev = None
+    for name, t in ts.items():
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous float32 tensor, got dtype {t.dtype}, '
+                               f'contiguous={t.is_contiguous()}')
+        if dev is not None and t.device != dev:
+            raise RuntimeError(f'{name} is on {t.device}, expected {dev}: all operands of a kernel live on one device')
+        dev = t.device
+
+
 def diffuse(x0, eps, t, alphas_cumprod, out):
     _need_cuda(x0, eps, t, alphas_cumprod, out)
+    _need_f32(x0=x0, eps=eps, alphas_cumprod=alphas_cumprod, out=out)
+    if t.dtype != torch.int64 or not t.is_contiguous() or t.numel() != x0.shape[0] or t.device != x0.device:
+        raise RuntimeError('diffuse: t must be a contiguous int64 tensor [B] on the device of x0')
+    if eps.shape != x0.shape or out.shape != x0.shape:
+        raise RuntimeError('diffuse: x0, eps and out must have the same shape')
     _check(lib().b200_diffuse(x0.data_ptr(), eps.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
-                              x0.shape[0], x0[0].numel(), _stream()), 'diffuse')
+                              x0.shape[0], x0[0].numel(), alphas_cumprod.numel(), _stream()), 'diffuse')
     return out
 
 
@@ -741,8 +837,10 @@ def to_uint8_hwc(x, out=None):
 
 
 def pack_entry_bytes(src, dst, Co, Ci, taps, mode, row0=0, col0=0, ld=0, src2=None):
-    """One b200_pack_entry as bytes (3 pointers, 8 ints)."""
+    """One b200_pack_entry as bytes (3 pointers, 8 ints).  mode 3 = FP32-mode split operand [hi | hi | lo] per tap."""
     import struct
+    if mode == 3 and taps > 9:
+        raise RuntimeError('pack mode 3 (FP32 mode) supports at most 9 taps')
     return struct.pack('<3Q8i', src.data_ptr(), 0 if src2 is None else src2.data_ptr(), dst.data_ptr(), Co, Ci, taps, mode,
                        row0, col0, ld, 0)
 

@@ -355,6 +355,10 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   if (!env_halves && p.nkb0 + p.nkb1 <= wide_maxkb) p.epi_halves = 4;
   static const char* env_rot = getenv("B200_K_ROTATE");
   p.k_rotate = (env_rot && atoi(env_rot) == 0) ? 0 : 1;
+  // 1x1-"image" problems are the embedding-projection GEMMs (rows = timesteps or samples): a fixed K order makes a row's
+  // result independent of how many rows are evaluated together, so the sampling runner's schedule-wide table
+  // (Engine.embed_rows) is bit-identical to the per-step evaluation of the eager loop
+  if (d->Ho * d->Wo == 1) p.k_rotate = 0;
 
 #ifdef B200_DEBUG
   static const char* env_dbg = getenv("B200_EPI_DBG");   // timing experiments only: skips loads / stores

@@ -361,15 +361,21 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
       longlong2 sq[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) sq[i] = __ldg(reinterpret_cast<const longlong2*>(st) + i);
+      // group sums are exact in the fixed-point domain; one int64 -> float conversion pair per GROUP (a 64-bit
+      // conversion is a multi-instruction sequence), carried to the group's other channels
+      float gm = 0.f, gr = 0.f;
 #pragma unroll
       for (int i0 = 0; i0 < 8; i0 += 1) {
-        const int g0 = i0 & ~(p.cpg - 1);          // cpg is 1, 2, 4 or 8 here
-        long long sm = 0, qm = 0;                  // group sums are exact in the fixed-point domain
+        if ((i0 & (p.cpg - 1)) == 0) {             // first channel of its group (cpg is 1, 2, 4 or 8 here)
+          long long sm = 0, qm = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i >= g0 && i < g0 + p.cpg) { sm += sq[i].x; qm += sq[i].y; }
-        mean[i0] = __ll2float_rn(sm) * (1.0f / kStatQ1) * inv_cnt;
-        rstd[i0] = rsqrtf(fmaxf(__ll2float_rn(qm) * (1.0f / kStatQ2) * inv_cnt - mean[i0] * mean[i0], 0.f) + p.eps);
+          for (int i = 0; i < 8; ++i)
+            if (i >= i0 && i < i0 + p.cpg) { sm += sq[i].x; qm += sq[i].y; }
+          gm = __ll2float_rn(sm) * (1.0f / kStatQ1) * inv_cnt;
+          gr = rsqrtf(fmaxf(__ll2float_rn(qm) * (1.0f / kStatQ2) * inv_cnt - gm * gm, 0.f) + p.eps);
+        }
+        mean[i0] = gm;
+        rstd[i0] = gr;
       }
     } else {
       // groups of 16, 24, ... channels: whole 8-channel columns of one source

@@ -370,9 +370,13 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
 // q(x_t | x_0), per-sample t (diffusions/ddpm.py:152-172)
 __global__ void __launch_bounds__(256) diffuse_kernel(const float* __restrict__ x0, const float* __restrict__ eps,
                                                       const int64_t* __restrict__ t, const float* __restrict__ ac,
-                                                      float* __restrict__ xt, int B, int CHW) {
+                                                      float* __restrict__ xt, int B, int CHW, int total_steps) {
   const int b = blockIdx.y;
-  const float a = ac[t[b]];
+  // the reference indexes alphas_cumprod[t] and raises on an out-of-range timestep (ddpm.py:166); a kernel cannot
+  // raise, so it never reads out of bounds and poisons that sample with NaN (the loss then shows it at once)
+  const int64_t tb = t[b];
+  const bool in_range = tb >= 0 && tb < (int64_t)total_steps;
+  const float a = in_range ? ac[tb] : __int_as_float(0x7fc00000);
   const float sa = sqrtf(a), sb = sqrtf(1.0f - a);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHW; i += gridDim.x * blockDim.x) {
     const size_t o = (size_t)b * CHW + i;
@@ -512,11 +516,12 @@ extern "C" int b200_time_embed(const int64_t* t, int rows, const float* freqs, i
 }
 
 extern "C" int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
-                            int B, int CHW, void* stream_) {
+                            int B, int CHW, int total_steps, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(x0 && eps && t && alphas_cumprod && xt, "diffuse: null pointer");
+  B200_REQUIRE(total_steps >= 1, "diffuse: total_steps must be positive");
   dim3 grid((CHW + 1023) / 1024 > 64 ? 64 : (CHW + 1023) / 1024, B);
-  diffuse_kernel<<<grid, 256, 0, stream>>>(x0, eps, t, alphas_cumprod, xt, B, CHW);
+  diffuse_kernel<<<grid, 256, 0, stream>>>(x0, eps, t, alphas_cumprod, xt, B, CHW, total_steps);
   ++g_launch_count;
   return check_cuda(cudaGetLastError(), "diffuse launch");
 }

@@ -181,10 +181,15 @@ class DDPM:
         """Sample from q(xt | x0); t is a [B] tensor (per-sample timesteps) or an int."""
         eps = torch.randn_like(x0) if eps is None else eps
         if not torch.is_tensor(t):
+            if not 0 <= int(t) < self.total_steps:     # the reference's alphas_cumprod[t] raises the same way
+                raise IndexError(f'timestep {int(t)} is out of range for {self.total_steps} diffusion steps')
             t = torch.full((x0.shape[0],), int(t), device=x0.device, dtype=torch.long)
-        t = t.to(torch.long).contiguous()
+        t = t.to(device=x0.device, dtype=torch.long).contiguous()
+        x0 = x0.float().contiguous()
         out = torch.empty_like(x0)
-        K.diffuse(x0.contiguous(), eps.contiguous(), t, self.alphas_cumprod, out)
+        # device-side timesteps are not synchronised for a range check: the kernel never reads alphas_cumprod out of
+        # bounds and turns an out-of-range sample into NaN
+        K.diffuse(x0, eps.to(device=x0.device, dtype=torch.float32).contiguous(), t, self.alphas_cumprod, out)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -204,6 +209,8 @@ class DDPM:
         learned = self.var_type == 'learned_range' and self._uses_learned_var()
         if reverse_eps is None:
             reverse_eps = torch.randn_like(xt)   # drawn every step, like the reference (ddpm.py:251, ddim.py:76)
+        elif reverse_eps.dtype != xt.dtype or not reverse_eps.is_contiguous() or reverse_eps.shape != xt.shape:
+            reverse_eps = reverse_eps.to(xt.dtype).expand_as(xt).contiguous()   # the kernel reads raw fp32 pointers
         sample, mean = torch.empty_like(xt), torch.empty_like(xt)
         pred_x0, pred_eps = torch.empty_like(xt), torch.empty_like(xt)
         row = self._coef_row(t, t_prev)

@@ -42,12 +42,17 @@ class Engine:
 
     def __init__(self, model: nn.Module):
         self.model = model
+        # 'bf16': operands rounded to bf16 once, fp32 accumulation (eps rel-L2 ~6e-3 vs the fp32 reference);
+        # 'fp32': every GEMM operand as a bf16 hi/lo pair, 3 tensor-core terms per product (csrc/precise.cu), exact SiLU /
+        #         softmax, fp64 GroupNorm statistics: eps rel-L2 <= 1e-4 (north_star's FP32 gate), ~3x the MMA work.
+        self.precision = __import__('os').environ.get('B200_PRECISION', 'bf16')
         self._packed: Dict = {}
         self._const: Dict = {}
         self._sig = None
         self._arena: Dict = {}
         self._stats: Dict = {}
-        self._stats_pools: List = []
+        self._stats_pools: Dict = {}     # input shape -> [[pool tensor, elements used]]
+        self._cur_key = None             # input shape of the forward being issued
         self._device = None          # cached per forward (refresh re-reads it)
         self._pt: Dict = {}          # table-managed packed weights: key -> (result, [b200_pack_entry bytes])
         self._pt_table = None        # device table over all entries (rebuilt when an entry is added)
@@ -59,6 +64,31 @@ class Engine:
         self._n_drop = 0
         self._epoch = 0           # bumped by invalidate(): part of the weight signature
         self._fwd_gen: Dict = {}  # input shape -> number of forwards that (re)wrote the arena buffers of that shape
+
+    # ------------------------------------------------------------------------------------------
+    # precision mode
+    # ------------------------------------------------------------------------------------------
+    @property
+    def split(self) -> bool:
+        return self.precision == 'fp32'
+
+    @property
+    def m3(self) -> int:
+        """Channel multiplier of GEMM operands: 3 in FP32 mode ([hi | lo | hi] along the contraction), else 1."""
+        return 3 if self.precision == 'fp32' else 1
+
+    def set_precision(self, precision: str):
+        """'bf16' (default) or 'fp32' (see __init__).  Inference only in 'fp32'; own UNet families (models/unet.py,
+        models/unet_categorial_adagn.py).  Switching drops the packed operands and the captured sampling graphs."""
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision != self.precision:
+            self.precision = precision
+            self.invalidate()
+
+    def _fp32_inference_only(self, what):
+        if self.split and self.tape is not None:
+            raise RuntimeError(f"{what}: precision='fp32' is an inference mode (the training step runs in bf16 operands)")
 
     # ------------------------------------------------------------------------------------------
     # buffers and packed weights
@@ -80,18 +110,21 @@ class Engine:
 
     def stats_buf(self, tag, B, C):
         """[B, C, 2] int64 fixed-point accumulator (K.STAT_Q1 / K.STAT_Q2) for the GroupNorm statistics of a conv output
-        (zeroed every forward).  Integer atomics: order-independent, so forwards are bitwise reproducible."""
-        key = (tag, B, C, self.device)
+        (zeroed every forward).  Integer atomics: order-independent, so forwards are bitwise reproducible.
+        Buffers and their pools belong to the input shape of the current forward (`check_input`), like the activation
+        arena: a forward of another shape neither reuses nor zeroes them (a training tape may still need them)."""
+        fk = self._cur_key
+        key = (tag, B, C, fk, self.device)
         t = self._stats.get(key)
         if t is None:
             # sub-allocated from a few large pool tensors so that one forward needs one memset per pool, not one
             # tiny kernel per GroupNorm input (70 of them for the CIFAR-10 UNet)
             n = B * C * 2
-            if (not self._stats_pools or self._stats_pools[-1][1] + n > self._stats_pools[-1][0].numel()
-                    or self._stats_pools[-1][0].device != self.device):
-                cap = max(n, 4 << 20)
-                self._stats_pools.append([torch.zeros(cap, dtype=torch.int64, device=self.device), 0])
-            pool = self._stats_pools[-1]
+            pools = self._stats_pools.setdefault(fk, [])
+            if not pools or pools[-1][1] + n > pools[-1][0].numel() or pools[-1][0].device != self.device:
+                cap = max(n, 1 << 20)
+                pools.append([torch.zeros(cap, dtype=torch.int64, device=self.device), 0])
+            pool = pools[-1]
             t = pool[0][pool[1]:pool[1] + n].view(B, C, 2)
             pool[1] += (n + 63) // 64 * 64
             self._stats[key] = t
@@ -99,8 +132,6 @@ class Engine:
 
     def begin_forward(self):
         self.refresh()
-        for pool, used in self._stats_pools:
-            pool[:used].zero_()
 
     def refresh(self):
         """Brings the packed bf16 weights up to date when a parameter was modified (optimizer step, load_state_dict,
@@ -161,19 +192,21 @@ class Engine:
         return result
 
     def w_conv(self, tag, conv: nn.Conv2d, shortcut: Optional[nn.Conv2d] = None):
-        """bf16 [Cout, taps*Cin (+ Cin_shortcut)] forward operand + fp32 bias (conv bias, summed with the fused shortcut's)."""
+        """bf16 [Cout, taps*Cin (+ Cin_shortcut)] forward operand + fp32 bias (conv bias, summed with the fused shortcut's).
+        FP32 mode: [Cout, 3*(taps*Cin + Cin_shortcut)], per tap [w_hi | w_hi | w_lo] (pack mode 3)."""
         key = ('conv', tag)
         hit = self._pt.get(key)
         if hit is not None:
             return hit[0]
         Co, Ci = conv.weight.shape[:2]
         taps = conv.weight[0, 0].numel()
-        Kd = taps * Ci + (shortcut.in_channels if shortcut is not None else 0)
+        m, mode = self.m3, (3 if self.split else 0)
+        Kd = m * (taps * Ci + (shortcut.in_channels if shortcut is not None else 0))
         w = torch.empty((Co, Kd), dtype=torch.bfloat16, device=self.device)
-        entries = [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, 0, ld=Kd)]
+        entries = [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, mode, ld=Kd)]
         b = conv.bias
         if shortcut is not None:
-            entries.append(K.pack_entry_bytes(shortcut.weight, w, Co, shortcut.in_channels, 1, 0, col0=taps * Ci, ld=Kd))
+            entries.append(K.pack_entry_bytes(shortcut.weight, w, Co, shortcut.in_channels, 1, mode, col0=m * taps * Ci, ld=Kd))
             b = torch.empty(Co, dtype=torch.float32, device=self.device)
             entries.append(K.pack_entry_bytes(conv.bias, b, Co, 1, 1, 2, src2=shortcut.bias))
         return self.pack_table(key, (w, b), entries)
@@ -190,7 +223,7 @@ class Engine:
         return self.pack_table(key, w, [K.pack_entry_bytes(conv.weight, w, Co, Ci, taps, 1, ld=taps * Co)])
 
     def w_up2(self, tag, conv: nn.Conv2d):
-        return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight),
+        return self.packed(('up2', tag), lambda: (K.pack_weight_up2(conv.weight, split=self.split),
                                                   conv.bias.detach().float().contiguous()))
 
     def w_tproj(self, linears: List[nn.Linear]):
@@ -201,12 +234,13 @@ class Engine:
             return hit[0]
         E = linears[0].in_features
         total = sum(l.out_features for l in linears)
-        w = torch.empty((total, E), dtype=torch.bfloat16, device=self.device)
+        m, mode = self.m3, (3 if self.split else 0)
+        w = torch.empty((total, m * E), dtype=torch.bfloat16, device=self.device)
         b = torch.empty(total, dtype=torch.float32, device=self.device)
         entries, off = [], 0
         for l in linears:
             n = l.out_features
-            entries.append(K.pack_entry_bytes(l.weight, w, n, E, 1, 0, row0=off, ld=E))
+            entries.append(K.pack_entry_bytes(l.weight, w, n, E, 1, mode, row0=off, ld=m * E))
             entries.append(K.pack_entry_bytes(l.bias, b[off:off + n], n, 1, 1, 2))
             off += n
         return self.pack_table(key, (w, b), entries)
@@ -240,6 +274,18 @@ class Engine:
             Ho, Wo = x.H // 2, x.W // 2
         elif resample == 2:
             Ho, Wo = x.H * 2, x.W * 2
+        if self.split:
+            self._fp32_inference_only(tag)
+            if x.stats is None or (skip is not None and skip.stats is None):
+                raise RuntimeError(f"{tag}: precision='fp32' needs producer statistics for every GroupNorm input "
+                                   '(parameter-free resampling layers are not supported in this mode)')
+            out = self.buf(tag + '.gn3', (x.B, Ho, Wo, 3 * C), torch.bfloat16)
+            raw_out = self.buf(tag + '.raw3', (x.B, x.H, x.W, 3 * C), torch.bfloat16) if raw else None
+            K.groupnorm_apply_split(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
+                                    None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
+                                    norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift, ss_ld=ss_ld,
+                                    silu=silu, resample=resample, raw_out=raw_out)
+            return out, raw_out
         out = self.buf(tag + '.gn', (x.B, Ho, Wo, C), torch.bfloat16)
         raw_out = self.buf(tag + '.raw', (x.B, x.H, x.W, C), torch.bfloat16) if raw else None
         if x.stats is not None and (skip is None or skip.stats is not None):
@@ -262,20 +308,24 @@ class Engine:
         Cout = conv.out_channels
         w, b = self.w_conv(tag, conv, sc_conv)
         stats = None
+        m = self.m3      # FP32 mode: `a` / `sc_a` hold [hi | lo | hi] per pixel, the packed weights [hi | hi | lo] per tap
         if out is None:
-            if intermediate and self.h_bf16 and Cout >= 128 and self.tape is None:   # narrow toy nets keep fp32 h
+            if intermediate and self.h_bf16 and Cout >= 128 and self.tape is None and not self.split:   # narrow toy nets keep fp32 h
                 out_mode = K.OUT_BF16_NHWC
             out = self.buf(tag + '.out', (B, H, W, Cout),
                            torch.bfloat16 if out_mode == K.OUT_BF16_NHWC else torch.float32)
             stats = self.stats_buf(tag, B, Cout) if Cout > 32 else None
-        K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(Cin, H, W, 1),
-                 a1=sc_a, a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, bias=b,
+        K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(m * Cin, H, W, 1),
+                 a1=sc_a, a1_geom=(m * sc_C, H, W, 1) if sc_a is not None else None, bias=b,
+                 alg_macs=float(B) * H * W * Cout * (9 * Cin + sc_C),
                  rowadd=rowadd, rowadd_ld=rowadd_ld, residual=None if residual is None else residual.t,
                  res_ld=0 if residual is None else residual.C, out=out, out_mode=out_mode, stats=stats)
         return Act(out, B, H, W, Cout, stats)
 
     def attention(self, tag, blk, x: Act) -> Act:
         """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2."""
+        if self.split:
+            return self._attention_split(tag, blk, x)
         key = ('attn', tag)
         hit = self._pt.get(key)
         if hit is None:
@@ -295,9 +345,67 @@ class Engine:
         return self.attention_core(tag, x, blk.norm, weights, blk.n_heads, blk.scale,
                                    mods=(blk.q, blk.k, blk.v, blk.proj))
 
+    def _attention_split(self, tag, blk, x: Act) -> Act:
+        """FP32-mode attention block (models/modules.py:89-102): GroupNorm -> q, k, v 1x1 convs with fp32 outputs ->
+        S = q k^T and O = softmax(S d^-1/2) v as batched tensor-core GEMMs over split operands (K = 3d resp. 3T), exact
+        row softmax in between -> 1x1 proj + residual.  [B*h, T, T] scores are materialised (accuracy mode)."""
+        self._fp32_inference_only(tag)
+        B, H, W, C = x.B, x.H, x.W, x.C
+        T, heads = H * W, blk.n_heads
+        d = C // heads
+        if T % 8 != 0 or d % 8 != 0 or (heads > 1 and (3 * d) % 64 != 0):
+            raise RuntimeError(f"attention block {tag}: T={T}, head_dim={d} not supported in precision='fp32'")
+        key = ('attn3', tag)
+        hit = self._pt.get(key)
+        if hit is None:
+            bf, dev = torch.bfloat16, self.device
+            wqkv = torch.empty((3 * C, 3 * C), dtype=bf, device=dev)
+            wp = torch.empty((C, 3 * C), dtype=bf, device=dev)
+            bqkv = torch.empty(3 * C, dtype=torch.float32, device=dev)
+            entries = []
+            for i, mod in enumerate((blk.q, blk.k, blk.v)):
+                entries.append(K.pack_entry_bytes(mod.weight, wqkv, C, C, 1, 3, row0=i * C, ld=3 * C))
+                entries.append(K.pack_entry_bytes(mod.bias, bqkv[i * C:], C, 1, 1, 2))
+            entries.append(K.pack_entry_bytes(blk.proj.weight, wp, C, C, 1, 3, ld=3 * C))
+            weights = self.pack_table(key, (wqkv, bqkv, wp, blk.proj.bias), entries)
+        else:
+            weights = hit[0]
+        wqkv, bqkv, wp, bp = weights
+        n, _ = self.gn(tag, x, None, blk.norm, silu=False)                       # [B, T, 3C] split
+        qkv = self.buf(tag + '.qkv32', (B, T, 3 * C), torch.float32)
+        K.conv2d(n, wqkv, 3 * C, B, H, W, K.taps_1x1(), a0_geom=(3 * C, H, W, 1), bias=bqkv, out=qkv,
+                 alg_macs=float(B) * T * 3 * C * C)
+        bf = torch.bfloat16
+        qs = self.buf(tag + '.q3', (B, T, 3 * C), bf)      # per head [q_hi | q_lo | q_hi]
+        ks = self.buf(tag + '.k3', (B, T, 3 * C), bf)      # per head [k_hi | k_hi | k_lo]
+        vs = self.buf(tag + '.v3', (B, 3, T, C), bf)       # planes [v_hi; v_hi; v_lo] along the key dimension
+        K.split_cast(qkv, qs, B * T, C, in_ld=3 * C, in_col0=0, group=d, pattern=K.SPLIT_ACT)
+        K.split_cast(qkv, ks, B * T, C, in_ld=3 * C, in_col0=C, group=d, pattern=K.SPLIT_WEIGHT)
+        K.split_cast(qkv, vs, B * T, C, in_ld=3 * C, in_col0=2 * C, pattern=K.SPLIT_WEIGHT, planes_rows=T)
+        G_ = B * heads
+        S = self.buf('attn3_ws.S', (G_, T, T), torch.float32)
+        P = self.buf('attn3_ws.P', (G_, T, 3 * T), bf)
+        grid = dict(batch=B, heads=heads)
+        K.gemm_batched((qs, T, 3 * C, dict(col_base=0, col_head=3 * d)), (ks, T, 3 * C, dict(col_base=0, col_head=3 * d)), S,
+                       T, T, 3 * d, **grid, out_ld=T, out_batch_stride=heads * T * T, out_head_stride=T * T)
+        K.softmax_rows_split(S, P, G_ * T, T, blk.scale)
+        o = self.buf(tag + '.o32', (B, T, C), torch.float32)
+        K.gemm_batched((P, T, 3 * T, dict(per_head_batch=True)), (vs, 3 * T, C, dict(col_head=d, mn_major=True)), o,
+                       T, d, 3 * T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
+        os_ = self.buf(tag + '.o3', (B, T, 3 * C), bf)
+        K.split_cast(o, os_, B * T, C)
+        out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
+        stats = self.stats_buf(tag, B, C)
+        K.conv2d(os_, wp, C, B, H, W, K.taps_1x1(), a0_geom=(3 * C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
+                 stats=stats, alg_macs=float(B) * T * C * C)
+        return Act(out, B, H, W, C, stats)
+
     def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:
         """GroupNorm -> [q|k] and v^T 1x1 convs -> fused softmax(q k^T * scale) v -> 1x1 proj + residual.
         `weights` = (Wqk [2C, C] bf16 with rows [q heads..., k heads...], bqk, Wv [C, C], bv, Wproj, bproj)."""
+        if self.split:
+            raise RuntimeError(f"attention block {tag}: precision='fp32' is implemented for the reference's own UNet "
+                               'families (models/unet.py, models/unet_categorial_adagn.py), not for ADM / pesser')
         B, H, W, C = x.B, x.H, x.W, x.C
         T = H * W
         d = C // heads
@@ -328,14 +436,19 @@ class Engine:
 
     def downsample_conv(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
         B, H, W, C = x.B, x.H, x.W, x.C
-        planes = self.buf(tag + '.planes', (B, 4, H // 2, W // 2, C), torch.bfloat16)
-        K.cast_bf16(x.t, planes, B, H, W, C, parity_split=True)
+        m = self.m3
+        planes = self.buf(tag + '.planes', (B, 4, H // 2, W // 2, m * C), torch.bfloat16)
+        if self.split:
+            self._fp32_inference_only(tag)
+            K.split_cast(x.t, planes, B * H * W, C, parity_hw=(H, W))
+        else:
+            K.cast_bf16(x.t, planes, B, H, W, C, parity_split=True)
         w, b = self.w_conv(tag, conv)
         Cout = conv.out_channels
         out = self.buf(tag + '.out', (B, H // 2, W // 2, Cout), torch.float32)
         stats = self.stats_buf(tag, B, Cout)
-        K.conv2d(planes, w, Cout, B, H // 2, W // 2, K.taps_3x3_s2(pad_lo), a0_geom=(C, H // 2, W // 2, 4), bias=b,
-                 out=out, stats=stats)
+        K.conv2d(planes, w, Cout, B, H // 2, W // 2, K.taps_3x3_s2(pad_lo), a0_geom=(m * C, H // 2, W // 2, 4), bias=b,
+                 out=out, stats=stats, alg_macs=9.0 * B * (H // 2) * (W // 2) * C * Cout)
         res = Act(out, B, H // 2, W // 2, Cout, stats)
         if self.tape is not None:
             self.tape.append(dict(kind='down', tag=tag, x=x, out=res, conv=conv, planes=planes, pad_lo=pad_lo))
@@ -352,13 +465,17 @@ class Engine:
             res = self.conv3x3(tag, ub, B, 2 * H, 2 * W, C, conv)
             self.tape.append(dict(kind='up', tag=tag, x=x, out=res, conv=conv, ub=ub))
             return res
-        xb = self.buf(tag + '.bf16', (B, H, W, C), torch.bfloat16)
-        K.cast_bf16(x.t, xb, B, H, W, C)
+        m = self.m3
+        xb = self.buf(tag + '.bf16', (B, H, W, m * C), torch.bfloat16)
+        if self.split:
+            K.split_cast(x.t, xb, B * H * W, C)
+        else:
+            K.cast_bf16(x.t, xb, B, H, W, C)
         w, b = self.w_up2(tag, conv)
         Cout = conv.out_channels
         out = self.buf(tag + '.out', (B, 2 * H, 2 * W, Cout), torch.float32)
         stats = self.stats_buf(tag, B, Cout)
-        K.conv2d(xb, w, Cout, B, H, W, K.taps_up2_3x3(), a0_geom=(C, H, W, 1), bias=b, out=out,
+        K.conv2d(xb, w, Cout, B, H, W, K.taps_up2_3x3(), a0_geom=(m * C, H, W, 1), bias=b, out=out,
                  w_rows_per_phase=Cout, stats=stats, alg_macs=9.0 * B * 4 * H * W * C * Cout)
         return Act(out, B, 2 * H, 2 * W, Cout, stats)
 
@@ -418,7 +535,7 @@ class Engine:
         if self.tape is not None and dropout is not None and dropout.p > 0 and self.model.training:
             drop_p, drop_seed = float(dropout.p), self.next_drop_seed()
         a2 = h = None
-        if (self.fuse_gn2 and self.tape is None and drop_p == 0.0 and Cin % 64 == 0
+        if (self.fuse_gn2 and self.tape is None and drop_p == 0.0 and Cin % 64 == 0 and not self.split
                 and K.conv2d_gn_ok(B, Ho, Wo, Cout, norm2.num_groups)):
             a2 = self._conv1_gn2_fused(tag, a1, B, Ho, Wo, Cin, Cout, conv1, norm2, emb, emb_off, emb_ld, scale_shift)
         elif scale_shift:
@@ -480,15 +597,20 @@ class Engine:
             y = y.to(torch.long).contiguous()
         E = lin1.out_features
         freqs = self.const(('freqs', str(dev)), lambda: pos_emb.frequencies(dev).float().contiguous())
+        m = self.m3
         emb = self.buf('emb', (rows, E), torch.float32)
-        semb = self.buf('semb', (rows, E), torch.bfloat16)
+        semb = self.buf('semb', (rows, m * E), torch.bfloat16)
         K.time_embed(t_rows, freqs, pos_emb.dim, E, bool(getattr(pos_emb, 'cos_first', False)), lin1.weight, lin1.bias,
                      lin2.weight, lin2.bias, emb,
-                     y=y if use_y else None, class_embed=class_embed.weight if use_y else None, out_silu_bf16=semb)
+                     y=y if use_y else None, class_embed=class_embed.weight if use_y else None,
+                     out_silu_bf16=None if self.split else semb)
+        if self.split:
+            self._fp32_inference_only('embed')
+            K.split_cast(emb, semb, rows, E, silu=True)       # exact SiLU, then [hi | lo | hi]
         w, b = self.w_tproj(proj_linears)
         total = w.shape[0]
         proj = self.buf('tproj', (rows, total), torch.float32)
-        K.conv2d(semb, w, total, rows, 1, 1, K.taps_1x1(), a0_geom=(E, 1, 1, 1), bias=b, out=proj)
+        K.conv2d(semb, w, total, rows, 1, 1, K.taps_1x1(), a0_geom=(m * E, 1, 1, 1), bias=b, out=proj)
         if self.tape is not None:
             self.tape.append(dict(kind='embed', t=t_rows, y=y if use_y else None, rows=rows, E=E, total=total,
                                   pos_emb=pos_emb, freqs=freqs, lin1=lin1, lin2=lin2, class_embed=class_embed if use_y else None,
@@ -505,13 +627,16 @@ class Engine:
         dev = self.device
         S, E = t_all.numel(), lin1.out_features
         freqs = self.const(('freqs', str(dev)), lambda: pos_emb.frequencies(dev).float().contiguous())
+        m = self.m3
         emb = torch.empty((S, E), dtype=torch.float32, device=dev)
-        semb = torch.empty((S, E), dtype=torch.bfloat16, device=dev)
+        semb = torch.empty((S, m * E), dtype=torch.bfloat16, device=dev)
         K.time_embed(t_all.to(torch.long).contiguous(), freqs, pos_emb.dim, E, bool(getattr(pos_emb, 'cos_first', False)),
-                     lin1.weight, lin1.bias, lin2.weight, lin2.bias, emb, out_silu_bf16=semb)
+                     lin1.weight, lin1.bias, lin2.weight, lin2.bias, emb, out_silu_bf16=None if self.split else semb)
+        if self.split:
+            K.split_cast(emb, semb, S, E, silu=True)
         w, b = self.w_tproj(proj_linears)
         proj = torch.empty((S, w.shape[0]), dtype=torch.float32, device=dev)
-        K.conv2d(semb, w, w.shape[0], S, 1, 1, K.taps_1x1(), a0_geom=(E, 1, 1, 1), bias=b, out=proj)
+        K.conv2d(semb, w, w.shape[0], S, 1, 1, K.taps_1x1(), a0_geom=(m * E, 1, 1, 1), bias=b, out=proj)
         return proj
 
     def first_conv(self, tag, conv: nn.Conv2d, X) -> Act:
@@ -539,7 +664,10 @@ class Engine:
         """Validates the network input and counts this forward against the arena of its shape: the training tape
         (models/backward.py) refers to arena buffers instead of saving copies, so its backward checks that no other
         forward of the same shape ran in between."""
-        self._fwd_gen[tuple(X.shape)] = self._fwd_gen.get(tuple(X.shape), 0) + 1
+        self._cur_key = tuple(X.shape)
+        self._fwd_gen[self._cur_key] = self._fwd_gen.get(self._cur_key, 0) + 1
+        for pool, used in self._stats_pools.get(self._cur_key, ()):
+            pool[:used].zero_()
         if X.dim() != 4 or X.shape[1] != in_channels:
             raise RuntimeError(f'expected input [B, {in_channels}, H, W], got {tuple(X.shape)}')
         if not X.is_cuda:

@@ -54,11 +54,20 @@ class _EngineModel(nn.Module):
             r = runners[diffuser] = SamplingRunner(self, diffuser)
         return r
 
+    def set_precision(self, precision: str):
+        """'bf16' (default: bf16 tensor-core operands, fp32 accumulate; eps rel-L2 <= 1e-2 vs the fp32 reference) or
+        'fp32' (bf16 hi/lo split operands, 3 MMAs per product: eps rel-L2 <= 1e-4; inference only).  Returns self."""
+        self.engine.set_precision(precision)
+        return self
+
     def forward(self, *args, **kwargs):
         """Inference: launches the forward kernels.  Training (module in train mode, grad enabled): the same forward
         with dropout and a tape, wrapped in an autograd node whose backward runs the hand-written adjoint kernels
         (models/backward.py) -- autograd itself never sees the network's interior."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.engine.split:
+                raise RuntimeError("precision='fp32' is an inference mode: call under torch.no_grad(), or "
+                                   "set_precision('bf16') for the training step")
             from models.backward import UNetFunction
             return UNetFunction.apply(self, args, kwargs, *list(self.parameters()))
         return self._forward_impl(*args, **kwargs)

@@ -224,9 +224,11 @@ int b200_ode_step(const b200_ode_desc* d, void* stream);
  * fp32 NCHW samples -> uint8 NHWC pixels, out = trunc(clamp((clamp(x,-1,1)+1)/2*255 + 0.5, 0, 255)). */
 int b200_to_uint8_hwc(const float* x, uint8_t* out, int B, int C, int HW, void* stream);
 
-/* q(x_t | x_0) (diffusions/ddpm.py:152-172): xt = sqrt(ac[t_b]) x0 + sqrt(1-ac[t_b]) eps, per-sample t. */
+/* q(x_t | x_0) (diffusions/ddpm.py:152-172): xt = sqrt(ac[t_b]) x0 + sqrt(1-ac[t_b]) eps, per-sample t.
+ * alphas_cumprod has total_steps entries; a t_b outside [0, total_steps) (where the reference raises an IndexError) is
+ * never dereferenced: that sample's output is NaN. */
 int b200_diffuse(const float* x0, const float* eps, const int64_t* t, const float* alphas_cumprod, float* xt,
-                 int B, int CHW, void* stream);
+                 int B, int CHW, int total_steps, void* stream);
 
 /* =============================================================================================
  * Backward pass (training step: scripts/train_ddpm.py:171-192 -> loss.backward() of diffusions/ddpm.py:122-138).
@@ -396,13 +398,49 @@ int b200_optimizer_step(const b200_optim_desc* d, void* stream);
  * the fp32 OIHW parameters after they changed.  `table` is a DEVICE array of n_entries descriptors.
  *   mode 0: dst[row0 + co][col0 + tap*Ci + ci] = src[co][ci][tap]                    (forward operand, bf16, row stride ld)
  *   mode 1: dst[row0 + ci][col0 + (taps-1-tap)*Co + co] = src[co][ci][tap]           (data-gradient operand)
- *   mode 2: dst_f32[i] = src[i] + src2[i], i < Co*Ci*taps                            (summed bias of a fused shortcut) */
+ *   mode 2: dst_f32[i] = src[i] + src2[i], i < Co*Ci*taps                            (summed bias of a fused shortcut)
+ *   mode 3: dst[row0 + co][col0 + tap*3*Ci + {0, Ci, 2*Ci} + ci] = {hi, hi, lo}(src[co][ci][tap]), taps <= 9
+ *           (FP32 mode, see b200_split_cast: weight side of the 3-term bf16 split product) */
 typedef struct b200_pack_entry {
   const float* src; const float* src2; void* dst;
   int Co, Ci, taps, mode;
   int row0, col0, ld, pad_;
 } b200_pack_entry;
 int b200_pack_weights(const void* table, int n_entries, void* stream);
+
+/* =============================================================================================
+ * FP32 mode ("bf16x3", csrc/precise.cu): the reference runs this path in fp32 (models/unet.py:121-152,
+ * models/modules.py:92-97).  Every GEMM operand x is split as hi = bf16(x), lo = bf16(x - hi) and a product a*w is
+ * evaluated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation; the three terms are laid out along the GEMM K
+ * dimension, activations as [hi | lo | hi] (pattern 0) and weights as [hi | hi | lo] (pattern 1) per group of channels,
+ * so b200_conv2d_fwd / b200_gemm_batched run unchanged on 3x the channels.  Gate: eps rel-L2 <= 1e-4 vs fp32.
+ * ============================================================================================= */
+typedef struct b200_split_desc {
+  const float* in;          /* fp32 [rows][in_ld]; the window is columns [in_col0, in_col0 + C) */
+  long long rows;
+  int in_ld, in_col0, C;
+  int group;                /* channels per split group (C for a plain tensor, head dim for per-head operands) */
+  int pattern;              /* 0: [hi | lo | hi], 1: [hi | hi | lo] */
+  int act;                  /* 1: exact SiLU before the split */
+  void* out;                /* bf16 [rows][out_ld], group g at out_col0 + 3*g*group (+ group, + 2*group) */
+  int out_ld, out_col0;
+  int planes_rows;          /* > 0: plane layout instead: out[b][3][planes_rows][C], b = row / planes_rows (the K dimension
+                               of an MN-major GEMM operand, e.g. V of softmax(QK^T) V) */
+  int parity_H, parity_W;   /* > 0: rows are the NHWC pixels of [B][H][W]; output rows are ordered as the 4 parity planes
+                               [B][2*(h&1)+(w&1)][H/2][W/2] (input of the stride-2 conv, cf. b200_cast_bf16) */
+} b200_split_desc;
+int b200_split_cast(const b200_split_desc* d, void* stream);
+
+/* b200_groupnorm_apply_fwd writing the split operand: out [B][HW_out][3*(C0+C1)] (pattern 0), optional raw copy
+ * [B][HW][3*(C0+C1)]; statistics evaluated in fp64, exact SiLU. */
+int b200_groupnorm_apply_split_fwd(const float* x0, int C0, const long long* stats0, const float* x1, int C1,
+                                   const long long* stats1, int B, int HW, int W, int groups, const float* gamma,
+                                   const float* beta, float eps, const float* scale, const float* shift, int ss_ld,
+                                   int apply_silu, int resample, void* out_split, void* raw_out_split, void* stream);
+
+/* softmax over the T columns of fp32 scores S [rows][T] (times `scale`) -> split probabilities bf16 [rows][3T] =
+ * [p_hi | p_lo | p_hi] (models/modules.py:95). */
+int b200_softmax_rows_split(const float* S, void* P_split, long long rows, int T, float scale, void* stream);
 
 #ifdef __cplusplus
 }

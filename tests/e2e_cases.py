@@ -115,14 +115,18 @@ def case_ddim50():
             eps_rel.append(_rel_l2(e_our, e_ref))
             xt = orc.denoise(e_ref, xt, t, tp, torch.zeros_like(xt))['sample']
     psnr_g, psnr_e = _psnr(got_graph.clamp(-1, 1), want.clamp(-1, 1)), _psnr(got_eager.clamp(-1, 1), want.clamp(-1, 1))
-    # the fused GroupNorm statistics are accumulated with fp32 atomics, so two runs agree to rounding, not bitwise
-    # (gate: the two runs must agree far better than either agrees with the fp32 oracle: PSNR >= 50 dB)
+    # GroupNorm statistics are accumulated with integer (fixed-point) atomics, so a forward is bitwise reproducible:
+    # the CUDA-graph replay, the eager loop and a second graph run must give identical bits
     gdiff = (got_graph - got_eager).abs().max().item()
     gpsnr = _psnr(got_graph, got_eager)
-    same = gpsnr >= 50.0
+    with torch.no_grad():
+        torch.manual_seed(7)
+        got_graph2 = ours.sample(m, x0, tqdm_kwargs=dict(disable=True))
+    same = bool(torch.equal(got_graph, got_eager)) and bool(torch.equal(got_graph, got_graph2))
+    _emit(case='ddim50 run-to-run bitwise (graph vs graph)', ok=bool(torch.equal(got_graph, got_graph2)))
     _emit(case='ddim50 final sample PSNR (graph)', psnr_db=psnr_g, gate=40.0, ok=psnr_g >= 40.0)
     _emit(case='ddim50 final sample PSNR (eager loop)', psnr_db=psnr_e, gate=40.0, ok=psnr_e >= 40.0)
-    _emit(case='ddim50 graph replay vs eager loop', max_abs_diff=gdiff, psnr_db=gpsnr, gate=50.0, ok=same)
+    _emit(case='ddim50 graph replay vs eager loop (bitwise)', max_abs_diff=gdiff, psnr_db=gpsnr, gate='torch.equal', ok=same)
     _emit(case='ddim50 per-step eps rel-L2 along oracle trajectory', max=max(eps_rel), mean=sum(eps_rel) / len(eps_rel),
           gate=1e-2, ok=max(eps_rel) <= 1e-2)
     return ok and psnr_g >= 40.0 and psnr_e >= 40.0 and same and max(eps_rel) <= 1e-2
@@ -148,13 +152,13 @@ def case_ddpm_noise():
             b = out['sample']
             noises.append(out['reverse_eps'])
         want = orc.sample(ref, x0, noises=noises)
-    # same RNG stream => same trajectory up to the rounding noise of the atomically accumulated GN statistics
+    # same RNG stream + order-independent (integer) statistics atomics => the same trajectory, bit for bit
     gdiff = (a - b).abs().max().item()
     gpsnr = _psnr(a, b)
-    same = gpsnr >= 50.0
+    same = bool(torch.equal(a, b))
     psnr = _psnr(b.clamp(-1, 1), want.clamp(-1, 1))
-    _emit(case='ddpm20 graph replay vs eager loop (same RNG stream)', max_abs_diff=gdiff, psnr_db=gpsnr, gate=50.0,
-          ok=same)
+    _emit(case='ddpm20 graph replay vs eager loop (same RNG stream, bitwise)', max_abs_diff=gdiff, psnr_db=gpsnr,
+          gate='torch.equal', ok=same)
     _emit(case='ddpm20 vs oracle with identical injected noise', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
     return same and psnr >= 40.0
 
@@ -191,17 +195,33 @@ def case_cfg():
         want = None
         for out in orc.sample_loop_cfg(ref, x, 3.0, dict(y=y), dict(y=None), noises=[torch.zeros_like(x)] * 50):
             want = out['sample']
-    # The 40 dB gate of BASELINE.json is stated for the headline (unguided) DDIM-50 run.  With guidance scale 3 the
-    # mix (1-s) eps_u + s eps_c amplifies the per-branch bf16 error by up to |1-s| + |s| = 5 (about 14 dB), so this
-    # case is gated below 40 dB and the measured value is reported as is.  The guided trajectory amplifies rounding-level
-    # differences (the fused GroupNorm statistics are accumulated with atomics, so two runs of the same code differ in
-    # the last bits): observed 34.75 / 35.27 / 35.7 dB over runs of the same inputs, hence a 33 dB gate (the principled
-    # bound is 40 - 14 = 26 dB).
+        # Context for the gate below: what the REFERENCE's own reduced-precision path does on the same inputs -- the same
+        # fp32 oracle modules run under torch.autocast(bfloat16) (cuDNN / cuBLAS bf16 kernels, fp32 accumulate).
+        ac_out = None
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            for out in orc.sample_loop_cfg(lambda a, b, **kw: ref(a, b, **kw).float(), x, 3.0, dict(y=y), dict(y=None),
+                                           noises=[torch.zeros_like(x)] * 50):
+                ac_out = out['sample']
+        ac_psnr = _psnr(ac_out.float().clamp(-1, 1), want.clamp(-1, 1))
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            e_ac = ref(x, t, y).float()
+        ac_rel = _rel_l2(e_ac, ref(x, t, y))
+        _emit(case='context: fp32 oracle under torch.autocast(bf16), same inputs', ddimcfg50_psnr_db=ac_psnr,
+              eps_rel_l2=ac_rel, ok=True)
+    # BASELINE.json's 40 dB gate at guidance scale 3 is met by precision='fp32' (case fp32_mode: same inputs).  In bf16 the
+    # mix (1-s) eps_u + s eps_c amplifies the per-branch operand-rounding error by up to |1-s| + |s| = 5 (14 dB): measured
+    # 36.8 dB (deterministic since the statistics atomics became order-independent), against 32.7 dB for the reference's
+    # own modules under torch.autocast(bfloat16) on the same inputs (whose per-step eps error, 1.26e-2, also misses the
+    # 1e-2 eps gate that this path meets at 7.6e-3).  bf16 gate: at least the autocast reference's PSNR and >= 35 dB.
+    gate = max(35.0, ac_psnr)
     for tag, gg in (('graph', got), ('eager loop', got_e)):
         psnr = _psnr(gg.clamp(-1, 1), want.clamp(-1, 1))
-        _emit(case=f'ddimcfg50 s=3 final sample PSNR ({tag})', psnr_db=psnr, gate=33.0, ok=psnr >= 33.0)
-        ok &= psnr >= 33.0
-    return ok
+        _emit(case=f'ddimcfg50 s=3 final sample PSNR, bf16 operands ({tag})', psnr_db=psnr, gate=gate,
+              autocast_bf16_reference_psnr_db=ac_psnr, ok=psnr >= gate)
+        ok &= psnr >= gate
+    same = bool(torch.equal(got, got_e))
+    _emit(case='ddimcfg50 graph replay vs eager loop (bitwise)', ok=same)
+    return ok and same
 
 
 def _family_product(c):
@@ -572,7 +592,7 @@ def case_ode_sampling():
 def case_ddim_inversion():
     """DDIM inversion (reference diffusions/ddim.py:88-132, 202-242) through DDIM / DDIMCFG.sample_inversion:
     (1) CIFAR-10 UNet, B=8, 20 respaced steps: latent vs the fp32 oracle's latent (PSNR >= 40 dB, peak-to-peak 2 as for
-        samples), then the round trip x0 -> latent -> DDIM-20 sample of OUR path against the oracle's round trip;
+        samples) and every single step along the oracle's trajectory (rel-L2 <= 1e-2);
     (2) the classifier-free-guidance inversion run frozen from the REFERENCE itself (tests/golden/ddim_inversion.pt,
         tiny AdaGN UNet, s = 2, 10 steps): our latent vs the reference's (gate 35 dB: the guidance mix amplifies the
         per-branch bf16 error by |1-s| + |s| = 3)."""
@@ -594,11 +614,22 @@ def case_ddim_inversion():
         ok &= psnr >= 40.0
         back = ours.sample(m, lat, tqdm_kwargs=dict(disable=True))
         back_ref = orc.sample(ref, lat_ref, noises=[torch.zeros_like(x0)] * 20)
+        # informational only: with random-init weights 20-step inversion + sampling does not reconstruct x0 (the oracle's
+        # own round trip sits at ~9 dB), so the two round trips are chaotic trajectories, not a parity measure
         p2 = _psnr(back.clamp(-1, 1), back_ref.clamp(-1, 1))
-        _emit(case='ddim inversion-20 + DDIM-20 round trip vs oracle round trip', psnr_db=p2, gate=40.0,
+        _emit(case='info: inversion-20 + DDIM-20 round trips, ours vs oracle (not gated)', psnr_db=p2,
               oracle_roundtrip_psnr_vs_x0=_psnr(back_ref.clamp(-1, 1), x0), ours_roundtrip_psnr_vs_x0=_psnr(back.clamp(-1, 1), x0),
-              ok=p2 >= 40.0)
-        ok &= p2 >= 40.0
+              ok=True)
+        # gated instead: every inversion step on the ORACLE's trajectory (same x_t into both paths): x_{t_next} rel-L2
+        xt, worst = x0, 0.0
+        for (t_, tn) in orc._inversion_pairs():
+            tb = torch.full((B,), t_, device=DEV)
+            o_ref = orc.denoise_inversion(ref(xt, tb), xt, t_, tn)
+            o_our = ours.denoise_inversion(m(xt, tb), xt, t_, tn)
+            worst = max(worst, _rel_l2(o_our['sample'], o_ref['sample']))
+            xt = o_ref['sample']
+        _emit(case='ddim inversion per-step x_{t_next} rel-L2 along the oracle trajectory', max=worst, gate=1e-2, ok=worst <= 1e-2)
+        ok &= worst <= 1e-2
         # (2) reference-frozen guided inversion
         g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ddim_inversion.pt'), weights_only=False)
         uf = torch.load(os.path.join(ROOT, 'tests', 'golden', 'unet_forward.pt'), weights_only=False)
@@ -613,6 +644,186 @@ def case_ddim_inversion():
               ok=p3 >= 35.0)
         ok &= p3 >= 35.0
     return ok
+
+
+def case_fp32_mode():
+    """precision='fp32' (bf16 hi/lo split operands, 3 tensor-core terms per product; BASELINE.json north_star: "1e-4 in
+    FP32/TF32 mode") against the fp32 oracle with TF32 off (reference models/unet.py:121-152 runs this path in fp32):
+    per-step eps rel-L2 <= 1e-4 for the CIFAR-10, MNIST and CFG (cond / uncond) UNets, DDIM-50 final samples and
+    DDIMCFG-50 at guidance scale 3 (the configuration whose bf16 run sits at ~36 dB) >= 40 dB, graph == eager bitwise,
+    and switching back to 'bf16' restores the bf16 results bit for bit."""
+    _no_tf32()
+    ok = True
+    for name, cfg, B in (('cifar10', CIFAR, 8), ('mnist', MNIST, 8)):
+        m, ref = _build(cfg)
+        x = torch.randn(B, cfg['in_channels'], 32, 32, generator=torch.Generator(device='cpu').manual_seed(1)).to(DEV)
+        t = torch.tensor([20, 500, 980, 7, 250, 640, 811, 999][:B], device=DEV)
+        with torch.no_grad():
+            bf = m(x, t).clone()
+            m.set_precision('fp32')
+            got = m(x, t).clone()
+            want = ref(x, t)
+            rel = _rel_l2(got, want)
+            _emit(case=f'fp32 mode unet forward {name} B={B}', rel_l2=rel, gate=1e-4, bf16_rel_l2=_rel_l2(bf, want), ok=rel <= 1e-4)
+            ok &= rel <= 1e-4
+            tu = torch.full((1,), 500, device=DEV).expand(B)
+            rel_u = _rel_l2(m(x, tu), ref(x, tu.contiguous()))
+            _emit(case=f'fp32 mode unet forward {name} uniform t', rel_l2=rel_u, gate=1e-4, ok=rel_u <= 1e-4)
+            ok &= rel_u <= 1e-4
+            if name == 'cifar10':
+                ours = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, device=DEV)
+                orc = R.DDIMRef(total_steps=1000, respace_type='uniform', respace_steps=50)
+                orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+                g1 = ours.sample(m, x, tqdm_kwargs=dict(disable=True))
+                e1 = None
+                for out in ours.sample_loop(m, x, tqdm_kwargs=dict(disable=True)):
+                    e1 = out['sample']
+                w1 = orc.sample(ref, x, noises=[torch.zeros_like(x)] * 50)
+                psnr = _psnr(g1.clamp(-1, 1), w1.clamp(-1, 1))
+                same = bool(torch.equal(g1, e1))
+                _emit(case='fp32 mode ddim50 final sample PSNR', psnr_db=psnr, gate=40.0, graph_equals_eager=same,
+                      ok=psnr >= 40.0 and same)
+                ok &= psnr >= 40.0 and same
+            m.set_precision('bf16')
+            back = bool(torch.equal(m(x, t), bf))
+            _emit(case=f'fp32 mode {name}: back to bf16 restores the bf16 output bitwise', ok=back)
+            ok &= back
+        m.train()
+        raised = False
+        try:
+            m.set_precision('fp32')
+            m(x, t)
+        except RuntimeError:
+            raised = True
+        m.set_precision('bf16')
+        _emit(case=f'fp32 mode {name}: training forward refused', ok=raised)
+        ok &= raised
+        del m, ref
+    # CFG UNet (AdaGN, up/down ResBlocks, 4-head attention at 16x16 and 8x8) and guided sampling
+    cfg = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+               num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+    torch.manual_seed(2022)
+    m = models.UNetCategorialAdaGN(**cfg).to(DEV).eval().set_precision('fp32')
+    ref = UNetRef(m.state_dict(), dim=128, adagn=True, attn_head_dims=64, num_res_blocks=2).to(DEV)
+    B = 8
+    x = torch.randn(B, 3, 32, 32, generator=torch.Generator(device='cpu').manual_seed(5)).to(DEV)
+    y = (torch.arange(B) % 10).to(DEV)
+    t = torch.tensor([20, 500, 980, 7, 250, 640, 811, 999], device=DEV)
+    with torch.no_grad():
+        for tag, yy in (('cond', y), ('uncond', None)):
+            rel = _rel_l2(m(x, t, yy), ref(x, t, yy))
+            _emit(case=f'fp32 mode adagn unet forward [{tag}]', rel_l2=rel, gate=1e-4, ok=rel <= 1e-4)
+            ok &= rel <= 1e-4
+        ours = diffusions.DDIMCFG(guidance_scale=3.0, total_steps=1000, beta_schedule='cosine', respace_type='uniform',
+                                  respace_steps=50, device=DEV)
+        orc = R.DDIMRef(total_steps=1000, beta_schedule='cosine', respace_type='uniform', respace_steps=50)
+        orc.alphas_cumprod = orc.alphas_cumprod.to(DEV)
+        got = ours.sample(m, x, tqdm_kwargs=dict(disable=True), model_kwargs=dict(y=y))
+        want = None
+        for out in orc.sample_loop_cfg(ref, x, 3.0, dict(y=y), dict(y=None), noises=[torch.zeros_like(x)] * 50):
+            want = out['sample']
+        psnr = _psnr(got.clamp(-1, 1), want.clamp(-1, 1))
+        _emit(case='fp32 mode ddimcfg50 s=3 final sample PSNR', psnr_db=psnr, gate=40.0, ok=psnr >= 40.0)
+        ok &= psnr >= 40.0
+    return ok
+
+
+def case_engine_hygiene():
+    """Round-1 review items, as behaviour tests on the MNIST-width UNet:
+    (1) models.EMA.apply_shadow / restore (the reference's sample-with-EMA flow, scripts/train_ddpm.py + models/ema.py:40-52)
+        re-pack the engine's bf16 operands and re-capture the sampling graph: forward and DDIM sample after apply_shadow
+        are bit-identical to a model loaded from the EMA state dict; restore brings the original outputs back;
+    (2) writes that bypass version counters (p.data.copy_) are picked up after Engine.invalidate();
+    (3) a second forward of the same shape between a training forward and its backward raises instead of returning
+        gradients computed from overwritten activations;
+    (4) a DDIM subclass that overrides denoise() is not routed through the CUDA-graph runner: sample() == sample_loop()."""
+    _no_tf32()
+    ok = True
+    m, _ = _build(MNIST)
+    B = 4
+    x = torch.randn(B, 1, 32, 32, generator=torch.Generator(device='cpu').manual_seed(3)).to(DEV)
+    t = torch.tensor([5, 300, 650, 990], device=DEV)
+    d = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=5, device=DEV)
+    quiet = dict(disable=True)
+    with torch.no_grad():
+        out0 = m(x, t).clone()
+        smp0 = d.sample(m, x, tqdm_kwargs=quiet).clone()
+        ema = models.EMA(m.parameters(), decay=0.99)
+        g = torch.Generator(device='cpu').manual_seed(4)
+        for sh in ema.shadow:                                    # make the shadow differ from the live weights
+            sh.mul_(0.9).add_(0.02 * torch.randn(sh.shape, generator=g).to(DEV))
+        torch.manual_seed(2022)
+        m2 = models.UNet(**MNIST).to(DEV).eval()
+        for p2, sh in zip(m2.parameters(), ema.shadow):
+            p2.copy_(sh)
+        want_out, want_smp = m2(x, t).clone(), d.sample(m2, x, tqdm_kwargs=quiet).clone()
+        ema.apply_shadow(m.parameters())
+        got_out, got_smp = m(x, t).clone(), d.sample(m, x, tqdm_kwargs=quiet).clone()
+        e1 = bool(torch.equal(got_out, want_out)) and bool(torch.equal(got_smp, want_smp)) and not bool(torch.equal(got_out, out0))
+        _emit(case='EMA.apply_shadow -> forward / DDIM sample == model loaded from the EMA weights (bitwise)', ok=e1,
+              max_abs_diff_fwd=(got_out - want_out).abs().max().item(), max_abs_diff_sample=(got_smp - want_smp).abs().max().item())
+        ema.restore(m.parameters())
+        e2 = bool(torch.equal(m(x, t), out0)) and bool(torch.equal(d.sample(m, x, tqdm_kwargs=quiet), smp0))
+        _emit(case='EMA.restore -> original forward / sample (bitwise)', ok=e2)
+        # (2) .data writes do not move version counters: invalidate() is the documented hook
+        for p_, sh in zip(m.parameters(), ema.shadow):
+            p_.data.copy_(sh)
+        m.engine.invalidate()
+        e3 = bool(torch.equal(m(x, t), want_out)) and bool(torch.equal(d.sample(m, x, tqdm_kwargs=quiet), want_smp))
+        _emit(case='p.data.copy_ + Engine.invalidate() -> re-packed weights, re-captured graph (bitwise)', ok=e3)
+    ok &= e1 and e2 and e3
+    # (3) tape guard
+    m.train()
+    ddpm = diffusions.DDPM(total_steps=1000, device=DEV)
+    loss = ddpm.loss_func(m, x.clamp(-1, 1), t, eps=torch.randn_like(x))
+    with torch.no_grad():
+        m.eval()
+        m(x, t)                  # same input shape: overwrites the arena buffers the tape refers to
+        m.train()
+    raised = False
+    try:
+        loss.backward()
+    except RuntimeError as e:
+        raised = 'another forward' in str(e)
+    _emit(case='backward after an interleaved same-shape forward raises', ok=raised)
+    ok &= raised
+    for p_ in m.parameters():
+        p_.grad = None
+    loss = ddpm.loss_func(m, x.clamp(-1, 1), t, eps=torch.randn_like(x))
+    with torch.no_grad():
+        m.eval()
+        m(x[:2], t[:2])          # a different shape uses other buffers: allowed
+        m.train()
+    loss.backward()
+    fin = all(p_.grad is not None and bool(torch.isfinite(p_.grad).all()) for p_ in m.parameters())
+    _emit(case='backward after an interleaved forward of another shape still works', ok=fin)
+    ok &= fin
+    m.eval()
+
+    # (4) subclass with its own denoise(): no graph runner
+    class HalfStepDDIM(diffusions.DDIM):
+        def denoise(self, model_output, xt, t, t_prev, reverse_eps=None):
+            out = super().denoise(model_output, xt, t, t_prev, reverse_eps)
+            out['sample'] = 0.5 * (out['sample'] + xt)
+            return out
+
+    h = HalfStepDDIM(total_steps=1000, respace_type='uniform', respace_steps=5, device=DEV)
+    with torch.no_grad():
+        a = h.sample(m, x, tqdm_kwargs=quiet)
+        b = None
+        for o in h.sample_loop(m, x, tqdm_kwargs=quiet):
+            b = o['sample']
+        stock = d.sample(m, x, tqdm_kwargs=quiet)
+    e4 = bool(torch.equal(a, b)) and not bool(torch.equal(a, stock))
+    _emit(case='subclass overriding denoise(): sample() == sample_loop() (override honoured, no graph runner)', ok=e4)
+    import gc
+    import weakref
+    wr = weakref.ref(h)
+    del h
+    gc.collect()
+    e5 = wr() is None and len(m.__dict__['_runners']) <= 2
+    _emit(case='runner table holds diffusers weakly', ok=e5, runners=len(m.__dict__['_runners']))
+    return ok and e4 and e5
 
 
 def case_timing():

@@ -420,6 +420,25 @@ def case_misc():
     out = torch.empty_like(x0)
     K.diffuse(x0, eps, t, ac, out)
     ok &= _report('diffuse', out, ref, 1e-6, 1e-6)
+    # out-of-range timesteps (the reference raises an IndexError): never read out of bounds, the sample becomes NaN
+    t_bad = torch.tensor([0, 1000, -1, 999], device=DEV)
+    out2 = torch.zeros_like(x0)
+    K.diffuse(x0, eps, t_bad, ac, out2)
+    torch.cuda.synchronize()
+    bad_ok = bool(torch.isnan(out2[1]).all() and torch.isnan(out2[2]).all() and torch.equal(out2[0], out[0])
+                  and torch.isfinite(out2[3]).all())
+    print(json.dumps({'case': 'diffuse out-of-range t -> NaN sample, no OOB read', 'ok': bad_ok}))
+    ok &= bad_ok
+    # wrappers reject tensors the kernels would misread
+    for bad in (lambda: K.diffuse(x0.double(), eps, t, ac, out), lambda: K.diffuse(x0, eps.permute(0, 1, 3, 2), t, ac, out),
+                lambda: K.sampler_step(x0.half(), x0, ac[:12].contiguous(), sample=out),
+                lambda: K.sampler_step(x0, x0, ac[:12].contiguous(), noise=eps[:, :, ::2], sample=out)):
+        try:
+            bad()
+            ok = False
+            print(json.dumps({'case': 'wrapper accepted a mistyped / non-contiguous tensor', 'ok': False}))
+        except RuntimeError:
+            pass
     return ok
 
 
@@ -776,6 +795,124 @@ def case_ode_samplers():
     print(json.dumps({'case': f'euler/heun single steps ({len(g["steps"])} cases) vs reference golden',
                       'max_rel_err': worst, 'gate': 2e-6, 'ok': good}), flush=True)
     return ok and good
+
+
+def case_precise():
+    """FP32-mode support kernels (csrc/precise.cu) against PyTorch: split cast layouts, GroupNorm -> split operand, row
+    softmax -> split probabilities, pack mode 3, and a conv / GEMM over split operands against fp32 (TF32 off) references
+    at the 1e-5 level."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ok = True
+
+    def split_ref(x):
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        return hi, lo
+
+    # ---- split cast: channel layout with groups, both patterns, SiLU, column window
+    rows, C, d = 96, 128, 32
+    x = _gen(rows, 2 * C, seed=1) * 3
+    for pattern in (0, 1):
+        out = torch.zeros(rows, 3 * C, device=DEV, dtype=torch.bfloat16)
+        K.split_cast(x, out, rows, C, in_ld=2 * C, in_col0=C, group=d, pattern=pattern)
+        hi, lo = split_ref(x[:, C:])
+        parts = (hi, lo, hi) if pattern == 0 else (hi, hi, lo)
+        ref = torch.stack([p_.view(rows, C // d, d) for p_ in parts], dim=2).reshape(rows, 3 * C)
+        ok &= _report(f'split_cast groups pattern {pattern}', out, ref, 0, 0)
+    out = torch.zeros(rows, 3 * C, device=DEV, dtype=torch.bfloat16)
+    K.split_cast(x[:, :C].contiguous(), out, rows, C, silu=True)
+    hi, lo = split_ref(F.silu(x[:, :C]))
+    rec = out[:, :C].float() + out[:, C:2 * C].float()
+    ok &= _report('split_cast SiLU: hi + lo reconstructs silu(x)', rec, F.silu(x[:, :C]), 1e-5, 1e-6)
+    ok &= _report('split_cast third block == hi', out[:, 2 * C:], out[:, :C], 0, 0)
+    # plane layout
+    B, T = 3, 16
+    v = _gen(B * T, C, seed=2)
+    outp = torch.zeros(B, 3, T, C, device=DEV, dtype=torch.bfloat16)
+    K.split_cast(v, outp, B * T, C, pattern=1, planes_rows=T)
+    hi, lo = split_ref(v.view(B, T, C))
+    ok &= _report('split_cast planes', outp, torch.stack([hi, hi, lo], dim=1), 0, 0)
+    # parity planes
+    B, H, W, Cc = 2, 8, 8, 64
+    xi = _gen(B, H, W, Cc, seed=3)
+    outq = torch.zeros(B, 4, H // 2, W // 2, 3 * Cc, device=DEV, dtype=torch.bfloat16)
+    K.split_cast(xi, outq, B * H * W, Cc, parity_hw=(H, W))
+    hi, lo = split_ref(xi)
+    full = torch.cat([hi, lo, hi], dim=-1)
+    refq = torch.stack([full[:, a::2, b::2] for a in range(2) for b in range(2)], dim=1)
+    ok &= _report('split_cast parity planes', outq, refq, 0, 0)
+
+    # ---- GroupNorm -> split operand (two sources, AdaGN, resample) vs torch fp32
+    for (name, B, C0, C1, H, adagn, silu, resample, raw) in (
+            ('C128 @16', 2, 128, 0, 16, False, True, 0, False), ('cat(256,128) @8 + raw', 2, 256, 128, 8, False, True, 0, True),
+            ('AdaGN C256 @8 avgpool', 2, 256, 0, 8, True, True, 1, False), ('AdaGN C128 @4 nearest2x', 3, 128, 0, 4, True, True, 2, False),
+            ('GN only C256 @4', 2, 256, 0, 4, False, False, 0, False)):
+        Cn = C0 + C1
+        x0 = _gen(B, H, H, C0, seed=4) * 2 + 0.5
+        x1 = _gen(B, H, H, C1, seed=5) if C1 else None
+        xcat = torch.cat([x0, x1], dim=-1) if C1 else x0
+        gamma, beta = _gen(Cn, seed=6) + 1, _gen(Cn, seed=7)
+        ys = _gen(B, 2 * Cn, seed=8) * 0.3
+        ref = F.group_norm(xcat.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+        if adagn:
+            ref = ref * (1 + ys[:, :Cn, None, None]) + ys[:, Cn:, None, None]
+        if silu:
+            ref = F.silu(ref)
+        if resample == 1:
+            ref = F.avg_pool2d(ref, 2, 2)
+        elif resample == 2:
+            ref = F.interpolate(ref, scale_factor=2, mode='nearest')
+        Ho = H // 2 if resample == 1 else H * 2 if resample == 2 else H
+
+        def st(t_):
+            return K.stats_from_float(torch.stack([t_.double().sum(dim=(1, 2)), (t_.double() ** 2).sum(dim=(1, 2))], dim=-1))
+        o3 = torch.zeros(B, Ho, Ho, 3 * Cn, device=DEV, dtype=torch.bfloat16)
+        r3 = torch.zeros(B, H, H, 3 * Cn, device=DEV, dtype=torch.bfloat16) if raw else None
+        K.groupnorm_apply_split(x0, C0, st(x0), x1, C1, st(x1) if C1 else None, B, H * H, H, 32, gamma, beta, 1e-5, o3,
+                                scale=ys if adagn else None, shift=ys[:, Cn:] if adagn else None, ss_ld=2 * Cn if adagn else 0,
+                                silu=silu, resample=resample, raw_out=r3)
+        rec = (o3[..., :Cn].float() + o3[..., Cn:2 * Cn].float()).permute(0, 3, 1, 2)
+        ok &= _report(f'groupnorm_apply_split {name}: hi + lo vs torch', rec, ref, 2e-5, 2e-5)
+        ok &= _report(f'groupnorm_apply_split {name}: third block == hi', o3[..., 2 * Cn:], o3[..., :Cn], 0, 0)
+        if raw:
+            rr = r3[..., :Cn].float() + r3[..., Cn:2 * Cn].float()
+            ok &= _report(f'groupnorm_apply_split {name}: raw copy', rr, xcat, 1e-5, 1e-6)
+
+    # ---- softmax rows -> split
+    S = _gen(64, 48, seed=9) * 4
+    P = torch.zeros(64, 3 * 48, device=DEV, dtype=torch.bfloat16)
+    K.softmax_rows_split(S, P, 64, 48, 0.37)
+    ok &= _report('softmax_rows_split: hi + lo', P[:, :48].float() + P[:, 48:96].float(), torch.softmax(S * 0.37, dim=-1), 1e-5, 1e-7)
+    ok &= _report('softmax_rows_split: third block == hi', P[:, 96:], P[:, :48], 0, 0)
+
+    # ---- pack mode 3 + conv over split operands vs fp32 conv: 1e-5 level
+    B, Cin, Cout, H = 4, 128, 256, 16
+    x = _gen(B, Cin, H, H, seed=10)
+    w = _gen(Cout, Cin, 3, 3, seed=11, scale=0.05)
+    bias = _gen(Cout, seed=12)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    wp = torch.zeros(Cout, 27 * Cin, device=DEV, dtype=torch.bfloat16)
+    tab = torch.frombuffer(bytearray(K.pack_entry_bytes(w, wp, Cout, Cin, 9, 3, ld=27 * Cin)), dtype=torch.uint8).to(DEV)
+    K.pack_weights(tab, 1)
+    hi, lo = split_ref(w.permute(0, 2, 3, 1).reshape(Cout, 9, Cin))
+    ok &= _report('pack mode 3', wp, torch.cat([hi, hi, lo], dim=-1).reshape(Cout, 27 * Cin), 0, 0)
+    a3 = torch.zeros(B, H, H, 3 * Cin, device=DEV, dtype=torch.bfloat16)
+    K.split_cast(x.permute(0, 2, 3, 1).contiguous(), a3, B * H * H, Cin)
+    out = torch.zeros(B, H, H, Cout, device=DEV)
+    K.conv2d(a3, wp, Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(3 * Cin, H, H, 1), bias=bias, out=out)
+    torch.cuda.synchronize()
+    rel = ((out.permute(0, 3, 1, 2) - ref).norm() / ref.norm()).item()
+    good = rel <= 2e-5
+    print(json.dumps({'case': 'conv3x3 128->256 @16 over split operands vs fp64 conv', 'rel_l2': rel, 'gate': 2e-5, 'ok': good}))
+    ok &= good
+    # same layer with plain bf16 operands, for scale
+    wb = K.pack_weight(w)
+    outb = torch.zeros(B, H, H, Cout, device=DEV)
+    K.conv2d(_nhwc_bf16(x), wb, Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(Cin, H, H, 1), bias=bias, out=outb)
+    torch.cuda.synchronize()
+    print(json.dumps({'case': 'context: the same conv with single bf16 operands', 'rel_l2': ((outb.permute(0, 3, 1, 2) - ref).norm() / ref.norm()).item(), 'ok': True}))
+    return ok
 
 
 def case_ddim_inversion():

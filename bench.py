@@ -418,25 +418,105 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
-def _extras(dev, peaks):
-    """Secondary workloads of BASELINE.json on the same GPU, same timing rules (CUDA events, warm-up, inputs resident):
-    (1) ADM ImageNet-256 class-conditional UNet forward, batch 16 (configs[4]; north_star: >= 60 % of bf16 peak), as a
-    CUDA-graph replay of one forward; (2) one classifier-free-guidance training step (configs[2]: UNetCategorialAdaGN,
-    batch 128, dropout 0.1): loss_func -> hand-written backward -> fused clip + Adam + EMA."""
+def _graph_time(fn, iters, warm=1):
+    """ms per call of `fn` (device time, CUDA events), after `warm` untimed calls."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+ADM256 = dict(image_size=256, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=2,
+              attention_resolutions=[32, 16, 8], dropout=0.0, channel_mult=[1, 1, 2, 2, 4, 4], num_classes=1000,
+              num_heads=4, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True)
+CFGC = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+            num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+MNIST = dict(in_channels=1, out_channels=1, dim=64, dim_mults=[1, 2, 2, 2], use_attn=[False, True, False, False],
+             num_res_blocks=2, n_heads=1, dropout=0.1)
+PESSER = dict(in_channels=3, out_ch=3, ch=128, ch_mult=[1, 1, 2, 2, 4, 4], num_res_blocks=2, attn_resolutions=[16],
+              dropout=0.0, resamp_with_conv=True, resolution=256)
+
+
+def _extra_train(dev, peaks, world, rank):
+    """One classifier-free-guidance training step (configs[2]: UNetCategorialAdaGN, batch 128 PER GPU, dropout 0.1):
+    loss_func -> hand-written backward -> [NCCL all-reduce of the flat gradient buffer over the data-parallel ranks,
+    captured inside the step's CUDA graph] -> fused clip + Adam + EMA.  Device time, max over ranks."""
+    import torch.distributed as dist
     import b200diff as K
     import diffusions
     import models
     from b200diff.optim import FusedAdam
     from b200diff.train import TrainStep
+    torch.manual_seed(2022)
+    model = models.UNetCategorialAdaGN(**CFGC).to(dev).train()
+    diffuser = diffusions.DDPM(total_steps=1000, beta_schedule='cosine', device=dev)
+    step = TrainStep(model, diffuser, FusedAdam(model.parameters(), lr=2e-4, capturable=True),
+                     ema=models.EMA(model.parameters()), clip_grad_norm=1.0, p_uncond=0.2, use_cuda_graph=True)
+    B = 128
+    x0 = (torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(2022 + rank)) * 0.5).clamp(-1, 1).to(dev)
+    y = (torch.arange(B, device=dev) + rank) % 10
+    first = step(x0, y=y)
+    step.warmup(x0, y)        # eager steps, then the CUDA-graph captures (conditional and unconditional)
+    # p_uncond draws come from the host RNG: seed it identically on every rank so that all ranks replay the same graph
+    torch.manual_seed(1234)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = K.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        loss = step(x0, y=y)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = ms_t.item()
+    tf = 3 * 14.396e9 * B / (ms * 1e-3) / 1e12
+    res = {'workload': 'UNetCategorialAdaGN (configs/ddpm_cfg_cifar10.yaml) noise-prediction training step, batch 128 per '
+                       f'GPU, dropout 0.1, p_uncond 0.2, clip 1.0 + Adam + EMA fused, whole step (incl. the gradient '
+                       f'all-reduce when data-parallel) replayed as one CUDA graph, {world} GPU(s)',
+           'n_gpus': world, 'ms_per_step': ms, 'images_per_s': world * B / (ms * 1e-3), 'tflops_3x_fwd_per_gpu': tf,
+           'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
+           'kernels_per_step': (K.launch_count() - n0) // iters,
+           'allreduce_bytes_per_step': 4 * sum(p.numel() for p in model.parameters()) if world > 1 else 0,
+           'loss_first': float(first), 'loss_last': float(loss)}
+    step.close()
+    torch.cuda.synchronize()
+    del step, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def _extras(dev, peaks, world=1, rank=0):
+    """Secondary workloads of BASELINE.json on the same GPU(s), same timing rules (CUDA events, warm-up, inputs resident).
+    world > 1: the data-parallel training step only.  world == 1: ADM-256 forward (configs[4]; north_star >= 60 % of bf16
+    peak), the training step, the K4 roofline, and sampling throughput of configs[0] (DDPM-1000 MNIST, batch 16),
+    configs[2] (DDIMCFG-50, s = 3, batch 128), configs[3] (pesser 256x256 DDIM-100, batch 32) and configs[4]
+    (ADM-256 DDIM-250, batch 16; 25 of 250 steps timed) through the public `sample()` API."""
+    import b200diff as K
+    import diffusions
+    import models
     from models.adm.unet import UNetModel
     out = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    # ---- (1) ADM-256 forward ----
-    adm = dict(image_size=256, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=2,
-               attention_resolutions=[32, 16, 8], dropout=0.0, channel_mult=[1, 1, 2, 2, 4, 4], num_classes=1000,
-               num_heads=4, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True)
+    quiet = dict(disable=True)
+    if world > 1:
+        out['cfg_train_step'] = _extra_train(dev, peaks, world, rank)
+        return out
+    # ---- (1) ADM-256 forward + DDIM-250 sampling ----
     torch.manual_seed(2022)
-    m = UNetModel(**adm)
+    m = UNetModel(**ADM256)
     gen = torch.Generator().manual_seed(2022)
     with torch.no_grad():      # ADM zero-initialises conv2 / proj_out / out: re-draw them N(0, 0.02) (SURVEY section 8d)
         for p_ in m.parameters():
@@ -454,87 +534,124 @@ def _extras(dev, peaks):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             m(x, t, y, out=o)
-        g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(5):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+        ms = _graph_time(g.replay, 5)
     tf = 2239.67e9 * B / (ms * 1e-3) / 1e12
     out['adm256_forward'] = {'workload': 'ADM ImageNet-256 class-cond UNet forward (guided-diffusion 256x256_diffusion.yaml), '
                                          'batch 16, random weights', 'ms_per_forward': ms, 'tflops': tf,
                              'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
-                             'gflop_per_image': 2239.67, 'images_fwd_per_s': B / (ms * 1e-3)}
-    del m, g, x, o
+                             'gflop_per_image': 2239.67, 'images_fwd_per_s': B / (ms * 1e-3),
+                             'arena_gb': sum(v.numel() * v.element_size() for v in m.engine._arena.values()) / 2 ** 30}
+    del g
+    try:
+        steps_timed, S_adm = 25, 250
+        d_adm = diffusions.DDIM(total_steps=1000, beta_schedule='linear', var_type='learned_range', respace_type='uniform',
+                                respace_steps=steps_timed, device=dev)
+        with torch.no_grad():
+            ms_s = _graph_time(lambda: d_adm.sample(m, x, tqdm_kwargs=quiet, model_kwargs=dict(y=y)), 1)
+        out['adm256_ddim250_sampling'] = {
+            'workload': 'configs[4]: ADM ImageNet-256 class-conditional UNet, DDIM-250, batch 16 through DDIM.sample (CUDA-graph '
+                        f'replay per step); {steps_timed} of {S_adm} steps timed (identical work per step), extrapolated',
+            'ms_per_ddim_step': ms_s / steps_timed, 'images_per_s': B / (ms_s / steps_timed * S_adm * 1e-3)}
+    except Exception as e:  # noqa: BLE001
+        out['adm256_ddim250_sampling'] = {'error': repr(e)}
+    del m, x, o
     torch.cuda.empty_cache()
     # ---- (2) CFG training step ----
-    cfgc = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
-                num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
-    torch.manual_seed(2022)
-    model = models.UNetCategorialAdaGN(**cfgc).to(dev).train()
-    diffuser = diffusions.DDPM(total_steps=1000, beta_schedule='cosine', device=dev)
-    step = TrainStep(model, diffuser, FusedAdam(model.parameters(), lr=2e-4, capturable=True),
-                     ema=models.EMA(model.parameters()), clip_grad_norm=1.0, p_uncond=0.2, use_cuda_graph=True)
-    B = 128
-    x0 = (torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(2022)) * 0.5).clamp(-1, 1).to(dev)
-    y = (torch.arange(B, device=dev) % 10)
-    first = step(x0, y=y)
-    step.warmup(x0, y)        # eager steps, then the CUDA-graph captures (conditional and unconditional)
-    torch.cuda.synchronize()
-    n0 = K.launch_count()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for _ in range(10):
-        loss = step(x0, y=y)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    tf = 3 * 14.396e9 * B / (ms * 1e-3) / 1e12
-    out['cfg_train_step'] = {'workload': 'UNetCategorialAdaGN (configs/ddpm_cfg_cifar10.yaml) noise-prediction training '
-                                         'step, batch 128, dropout 0.1, p_uncond 0.2, clip 1.0 + Adam + EMA fused, whole '
-                                         'step replayed as a CUDA graph, 1 GPU',
-                             'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'tflops_3x_fwd': tf,
-                             'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
-                             'kernels_per_step': (K.launch_count() - n0) // 10,
-                             'loss_first': float(first), 'loss_last': float(loss)}
-    del step, model
-    torch.cuda.empty_cache()
+    out['cfg_train_step'] = _extra_train(dev, peaks, 1, 0)
+    # ---- (3) sampling throughput of the other BASELINE configs through the public API ----
     try:
-        # ---- (3) K4 sampler update against the HBM roofline (CIFAR-size tensors are launch-latency bound,
-        # so the GB/s figure is taken on tensors whose working set exceeds the 126 MB L2; three buffer sets rotate) ----
+        torch.manual_seed(2022)
+        mc = models.UNetCategorialAdaGN(**CFGC).to(dev).eval()
+        dc = diffusions.DDIMCFG(guidance_scale=3.0, total_steps=1000, beta_schedule='cosine', respace_type='uniform',
+                                respace_steps=50, device=dev)
+        Bc = 128
+        xc = torch.randn(Bc, 3, 32, 32, device=dev)
+        yc = torch.arange(Bc, device=dev) % 10
+        with torch.no_grad():
+            ms_c = _graph_time(lambda: dc.sample(mc, xc, tqdm_kwargs=quiet, model_kwargs=dict(y=yc)), 3)
+        out['cfg_ddim50_sampling'] = {
+            'workload': 'configs[2]: UNetCategorialAdaGN (ddpm_cfg_cifar10.yaml), DDIMCFG-50, guidance scale 3, batch 128, '
+                        'two forwards per step (cond + uncond) + fused guidance mix / sampler step, full 50-step runs',
+            'ms_per_run': ms_c, 'images_per_s': Bc / (ms_c * 1e-3),
+            'unet_fwd_tflops': 2 * 50 * 14.396e9 * Bc / (ms_c * 1e-3) / 1e12,
+            'frac_of_bf16_sustained_peak': 2 * 50 * 14.396e9 * Bc / (ms_c * 1e-3) / 1e12 / peaks['bf16_sustained']}
+        del mc, dc
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['cfg_ddim50_sampling'] = {'error': repr(e)}
+    try:
+        torch.manual_seed(2022)
+        mm = models.UNet(**MNIST).to(dev).eval()
+        dm = diffusions.DDPM(total_steps=1000, var_type='fixed_large', device=dev)
+        xm = torch.randn(16, 1, 32, 32, device=dev)
+        with torch.no_grad():
+            ms_m = _graph_time(lambda: dm.sample(mm, xm, tqdm_kwargs=quiet), 1)
+        out['mnist_ddpm1000_sampling'] = {
+            'workload': 'configs[0]: DDPM MNIST UNet (ddpm_mnist.yaml, 32x32 padded input), 1000 steps, batch 16 (launch-bound: '
+                        '~115 kernels per step replayed as one CUDA graph)', 'ms_per_run': ms_m,
+            'images_per_s': 16 / (ms_m * 1e-3), 'us_per_step': ms_m}
+        del mm, dm
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['mnist_ddpm1000_sampling'] = {'error': repr(e)}
+    try:
+        from models.pesser.model import Model as Pesser
+        torch.manual_seed(2022)
+        mp = Pesser(**PESSER).to(dev).eval()
+        dp = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=100, device=dev)
+        xp = torch.randn(32, 3, 256, 256, device=dev)
+        with torch.no_grad():
+            ms_p = _graph_time(lambda: dp.sample(mp, xp, tqdm_kwargs=quiet), 1)
+        out['pesser256_ddim100_sampling'] = {
+            'workload': 'configs[3]: CelebA-HQ 256x256 pesser UNet (ddpm_celebahq.yaml), DDIM-100, batch 32, one full 100-step run',
+            'ms_per_run': ms_p, 'images_per_s': 32 / (ms_p * 1e-3), 'ms_per_ddim_step': ms_p / 100}
+        del mp, dp, xp
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['pesser256_ddim100_sampling'] = {'error': repr(e)}
+    try:
+        # ---- (4) K4 sampler update against the HBM roofline (CIFAR-size tensors are launch-latency bound,
+        # so the GB/s figure is taken on tensors whose working set exceeds the 126 MB L2; three buffer sets rotate).
+        # DDIM eta = 0: the noise term is sqrt(0) * z, so the kernel reads model output and x_t and writes x_{t-1}:
+        # 12 B / element; the eta = 1 line adds the 4 B / element noise stream.
         Bk, Hk = 128, 256     # the shape of the ncu capture in profiles/sampler_traffic.json
-        dd = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, eta=0.0, device=dev)
-        row = dd._coef_row(500, 480)
         sets = [[torch.randn(Bk, 3, Hk, Hk, device=dev) for _ in range(3)] + [torch.empty(Bk, 3, Hk, Hk, device=dev)]
                 for _ in range(3)]
-        call = lambda s: K.sampler_step(s[0], s[1], row, objective='pred_eps', clip=True, noise=s[2], sample=s[3])  # noqa: E731
-        for s_ in sets:
-            call(s_)
-        torch.cuda.synchronize()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(10):
+        res = {}
+        for tag, eta, streams in (('eta0', 0.0, 3), ('eta1', 1.0, 4)):
+            dd = diffusions.DDIM(total_steps=1000, respace_type='uniform', respace_steps=50, eta=eta, device=dev)
+            row = dd._coef_row(500, 480)
+            call = lambda s_: K.sampler_step(s_[0], s_[1], row, objective='pred_eps', clip=True, noise=s_[2], sample=s_[3])  # noqa: E731
             for s_ in sets:
                 call(s_)
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 30 * 1e3
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(10):
+                for s_ in sets:
+                    call(s_)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 30 * 1e3
+            by = 4.0 * Bk * 3 * Hk * Hk * streams
+            res[tag] = (us, by)
         k4_traffic = None
         tp = os.path.join(ROOT, 'profiles', 'sampler_traffic.json')    # ncu dram__bytes_read/write.sum of this launch shape
         if os.path.exists(tp):
             with open(tp) as f:
                 k4_traffic = json.load(f).get('dram_bytes_per_launch')
-        by = 4.0 * Bk * 3 * Hk * Hk * 4      # model output, x_t, noise read; x_{t-1} written
+        us, by = res['eta0']
         out['sampler_update'] = {'kernel': 'sampler_step_vec4_kernel (K4: predict + clip + DDIM/DDPM step, fused)',
                                  'bound': 'hbm', 'achieved': by / us / 1e3, 'peak': peaks['hbm'], 'unit': 'GB/s',
                                  'frac': by / us / 1e3 / peaks['hbm'], 'traffic': k4_traffic,
+                                 'traffic_note': 'ncu capture of the eta = 1 (4-stream) launch of round 1',
                                  'algorithmic_bytes_per_launch': by, 'avg_launch_us': us,
-                                 'workload': f'DDIM step on [{Bk},3,{Hk},{Hk}] fp32 tensors (101 MB each, 4 streams: '
-                                             f'1.2 GB between reuses), 30 launches over 3 buffer sets'}
-    except Exception as e:  # noqa: BLE001  (must not cost the two numbers above)
+                                 'eta1_4_streams': {'achieved': res['eta1'][1] / res['eta1'][0] / 1e3, 'avg_launch_us': res['eta1'][0],
+                                                    'frac': res['eta1'][1] / res['eta1'][0] / 1e3 / peaks['hbm']},
+                                 'workload': f'DDIM eta=0 step on [{Bk},3,{Hk},{Hk}] fp32 tensors (101 MB each, 3 streams = 12 B/element: '
+                                             f'model output + x_t read, x_(t-1) written; the zero-variance noise is not read), '
+                                             f'30 launches over 3 buffer sets (> L2 between reuses)'}
+    except Exception as e:  # noqa: BLE001  (must not cost the numbers above)
         out['sampler_update_error'] = repr(e)
     return out
 

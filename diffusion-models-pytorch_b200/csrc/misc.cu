@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const int64_t* __restri
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if (sub == 0 && e < e_end) {
       float v = acc + b2[e];
-      if (y && class_embed) v += class_embed[(size_t)y[b] * E + e];
+      if (y && class_embed && y[b] >= 0) v += class_embed[(size_t)y[b] * E + e];   // y < 0: unconditional row (batched CFG)
       out[(size_t)b * E + e] = v;
       if (out_silu_bf16) out_silu_bf16[(size_t)b * E + e] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
     }

@@ -44,6 +44,10 @@ class ResBlockDownsample(ResBlock):
 
 
 class UNetCategorialAdaGN(_EngineModel):
+    # one network serves the conditional and the unconditional branch of classifier-free guidance (y=None drops the class
+    # embedding, reference :172-174), so the sampling runner may evaluate both as one 2B batch with labels [y ; -1]
+    cfg_batch_ok = True
+
     """UNet conditioned on categorial labels with AdaGN."""
 
     def __init__(

@@ -219,8 +219,22 @@ def case_cfg():
         _emit(case=f'ddimcfg50 s=3 final sample PSNR, bf16 operands ({tag})', psnr_db=psnr, gate=gate,
               autocast_bf16_reference_psnr_db=ac_psnr, ok=psnr >= gate)
         ok &= psnr >= gate
-    same = bool(torch.equal(got, got_e))
-    _emit(case='ddimcfg50 graph replay vs eager loop (bitwise)', ok=same)
+    # sample() evaluates both guidance branches as ONE 2B forward with labels [y ; -1] (models/runner.py), the generator
+    # API runs the reference's two forwards: same arithmetic per image, different tile schedules, so the two agree to
+    # rounding (amplified by the guided trajectory), not bitwise; with B200_CFG_BATCH=0 they are bit-identical.
+    gp = _psnr(got, got_e)
+    _emit(case='ddimcfg50 batched-guidance graph vs two-forward eager loop', psnr_db=gp, gate=50.0, ok=gp >= 50.0)
+    ok &= gp >= 50.0
+    os.environ['B200_CFG_BATCH'] = '0'
+    try:
+        with torch.no_grad():
+            d2 = diffusions.DDIMCFG(guidance_scale=3.0, total_steps=1000, beta_schedule='cosine',
+                                    respace_type='uniform', respace_steps=50, device=DEV)
+            got_2f = d2.sample(m, x, tqdm_kwargs=dict(disable=True), model_kwargs=dict(y=y))
+    finally:
+        os.environ.pop('B200_CFG_BATCH', None)
+    same = bool(torch.equal(got_2f, got_e))
+    _emit(case='ddimcfg50 two-forward graph replay vs eager loop (bitwise)', ok=same)
     return ok and same
 
 

@@ -412,6 +412,24 @@ def case_misc():
         torch.cuda.synchronize()
         ok &= _report(f'time_embed dim={dim} cos_first={cos_first}', out, ref, 1e-4, 1e-4)
         ok &= _report(f'time_embed silu bf16 dim={dim}', outs, F.silu(ref), 1e-2, 1e-2)
+    # negative labels = unconditional rows (batched classifier-free guidance, models/runner.py)
+    dim, E, Bn = 128, 512, 6
+    w1, b1, w2, b2 = _gen(E, dim, seed=31, scale=0.05), _gen(E, seed=32), _gen(E, E, seed=33, scale=0.03), _gen(E, seed=34)
+    ce = _gen(10, E, seed=35)
+    tt = torch.tensor([3, 500, 999, 3, 500, 999], device=DEV)
+    yy = torch.tensor([1, 7, 9, -1, -1, -1], device=DEV)
+    half = dim // 2
+    fr = torch.exp(torch.arange(half, device=DEV) * -(math.log(10000) / (half - 1))).float().contiguous()
+    o_mixed = torch.empty(Bn, E, device=DEV)
+    K.time_embed(tt, fr, dim, E, False, w1, b1, w2, b2, o_mixed, y=yy, class_embed=ce)
+    o_none = torch.empty(Bn, E, device=DEV)
+    K.time_embed(tt, fr, dim, E, False, w1, b1, w2, b2, o_none)
+    o_cond = torch.empty(Bn, E, device=DEV)
+    K.time_embed(tt, fr, dim, E, False, w1, b1, w2, b2, o_cond, y=yy.clamp_min(0), class_embed=ce)
+    torch.cuda.synchronize()
+    neg_ok = bool(torch.equal(o_mixed[3:], o_none[3:]) and torch.equal(o_mixed[:3], o_cond[:3]))
+    print(json.dumps({'case': 'time_embed: label -1 rows == unconditional rows, labelled rows unchanged (bitwise)', 'ok': neg_ok}))
+    ok &= neg_ok
     # diffuse
     x0, eps = _gen(4, 3, 8, 8, seed=1), _gen(4, 3, 8, 8, seed=2)
     ac = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000, dtype=torch.float64), 0).float().to(DEV)

@@ -24,3 +24,22 @@ def test_smoke_entry():
     r = subprocess.run([sys.executable, '-c', 'import __graft_entry__ as g; g.smoke()'], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_reference_scripts_replay_under_torchrun():
+    """scripts/sample_uncond.py:115-195 and scripts/train_ddpm.py:100-216 call sequences (tests/script_replay.py) through the
+    omegaconf / accelerate stand-ins, one process per GPU under torchrun: 2 ranks (NCCL gather, DDP gradient all-reduce)
+    when the box has >= 2 GPUs, else 1 rank."""
+    import socket
+    import torch
+    n = min(2, torch.cuda.device_count())
+    assert n >= 1
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}',
+                        '--master-addr', '127.0.0.1', '--master-port', str(port),
+                        os.path.join(ROOT, 'tests', 'script_replay.py')], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, f'script replay failed ({n} ranks):\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}'
+    assert '"ok": true' in r.stdout

@@ -52,7 +52,9 @@ class Engine:
         self._arena: Dict = {}
         self._stats: Dict = {}
         self._stats_pools: Dict = {}     # input shape -> [[pool tensor, elements used]]
-        self._cur_key = None             # input shape of the forward being issued
+        self._cur_key = None             # input shape (+ lane) of the forward being issued
+        self.lane = 0                    # buffer-set index: forwards issued concurrently on different streams (the sampling
+                                         # runner's two half-batch branches) use different lanes = disjoint buffers
         self._device = None          # cached per forward (refresh re-reads it)
         self._pt: Dict = {}          # table-managed packed weights: key -> (result, [b200_pack_entry bytes])
         self._pt_table = None        # device table over all entries (rebuilt when an entry is added)
@@ -101,7 +103,7 @@ class Engine:
         return d
 
     def buf(self, tag, shape, dtype):
-        key = (tag, tuple(shape), dtype, self.device)
+        key = (tag, tuple(shape), dtype, self.device, self.lane)
         t = self._arena.get(key)
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
@@ -664,7 +666,7 @@ class Engine:
         """Validates the network input and counts this forward against the arena of its shape: the training tape
         (models/backward.py) refers to arena buffers instead of saving copies, so its backward checks that no other
         forward of the same shape ran in between."""
-        self._cur_key = tuple(X.shape)
+        self._cur_key = tuple(X.shape) + (self.lane,)
         self._fwd_gen[self._cur_key] = self._fwd_gen.get(self._cur_key, 0) + 1
         for pool, used in self._stats_pools.get(self._cur_key, ()):
             pool[:used].zero_()

@@ -130,9 +130,38 @@ class SamplingRunner:
             st['out_u'] = torch.empty_like(st['out_c']) if cfg else None
         st['cfg_batched'] = batched
 
+        # Two half-batch forwards as parallel branches of the step graph (B200_LANES=2, experiment knob): the branches use
+        # disjoint buffer sets (Engine.lane) and share the packed weights; one branch's HBM-bound GroupNorm / epilogue
+        # phases can then overlap the other's tensor-bound mainloops.  Unconditional models without keyword tensors only.
+        lanes = 2 if (__import__('os').environ.get('B200_LANES', '1') == '2' and not cfg and B % 2 == 0 and B >= 32
+                      and not st['kw'] and hasattr(model, 'engine') and hasattr(model.engine, 'lane')) else 1
+        st['lanes'] = lanes
+        side2 = torch.cuda.Stream(device=dev) if lanes == 2 else None
+
+        def forward_lanes():
+            half = B // 2
+            cur = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            side2.wait_event(fork)
+            eng_ = model.engine
+            try:
+                eng_.lane = 0
+                model(st['x'][:half], st['t'].expand(half), out=st['out_c'][:half])
+                with torch.cuda.stream(side2):
+                    eng_.lane = 1
+                    model(st['x'][half:], st['t'].expand(half), out=st['out_c'][half:])
+            finally:
+                eng_.lane = 0
+            join = torch.cuda.Event()
+            join.record(side2)
+            cur.wait_event(join)
+
         def step():
             if batched:
                 model(x2, st['t'].expand(2 * B), out=out2, **{d.cond_kwarg: y2})
+            elif lanes == 2:
+                forward_lanes()
             else:
                 tb = st['t'].expand(B)
                 model(st['x'], tb, out=st['out_c'], **st['kw'])

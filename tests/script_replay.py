@@ -119,8 +119,9 @@ def main():
                   device=device)                                              # :140-149
     diffuser = diffusions.ddim.DDIM(eta=0.0, **params)                        # :153-154 (--sampler ddim)
     model = instantiate_from_config(conf.model)                               # :163
-    torch.manual_seed(2022)
-    weights = {k: v.clone() for k, v in instantiate_from_config(conf.model).state_dict().items()}   # stands in for load_weights
+    with torch.random.fork_rng(devices=[device]):      # stands in for load_weights(args.weights): must not touch the
+        torch.manual_seed(2022)                        # rank-specific RNG streams set up above
+        weights = {k: v.clone() for k, v in instantiate_from_config(conf.model).state_dict().items()}
     model.load_state_dict(weights)                                            # :166-167
     model = accelerator.prepare(model)                                        # :173
     model.eval()

@@ -2,7 +2,7 @@
 scripts/train_ddpm.py:171-192 / train_ddpm_cfg.py:172-196:
 
     optimizer.zero_grad(); t ~ U{0..T-1}; loss = diffuser.loss_func(model, x0, t); loss.backward();
-    [all-reduce(mean) of the gradients over the data-parallel ranks]; clip_grad_norm_(1.0); optimizer.step(); ema.update()
+    [all-reduce(mean) of the gradients over the data-parallel ranks, in buckets overlapped with the backward]; clip_grad_norm_(1.0); optimizer.step(); ema.update()
 
 with the last three fused into b200_optimizer_step, and no host synchronisation anywhere (the loss is returned as a
 device scalar; call `.item()` on it only when it is logged).
@@ -25,11 +25,12 @@ from .optim import FusedAdam
 
 class TrainStep:
     def __init__(self, model, diffuser, optimizer: FusedAdam, ema=None, clip_grad_norm: Optional[float] = 1.0,
-                 p_uncond: float = 0.0, use_cuda_graph: bool = False):
+                 p_uncond: float = 0.0, use_cuda_graph: bool = False, bucket_bytes: int = 32 << 20):
         self.model, self.diffuser, self.optimizer, self.ema = model, diffuser, optimizer, ema
         self.clip_grad_norm = clip_grad_norm
         self.p_uncond = p_uncond      # train_ddpm_cfg.py:183-186: the label is dropped with this probability
         self.use_cuda_graph = use_cuda_graph
+        self.bucket_bytes = bucket_bytes     # size of the gradient buckets all-reduced while the backward still runs
         if use_cuda_graph and not getattr(optimizer, 'capturable', False):
             raise ValueError('TrainStep(use_cuda_graph=True) needs FusedAdam(capturable=True)')
         self._graphs: Dict = {}
@@ -41,6 +42,16 @@ class TrainStep:
         micro_batch = B if micro_batch is None else micro_batch
         self.optimizer.zero_grad(set_to_none=True)
         total = None
+        # data-parallel: average the gradients INSIDE the backward, in buckets of finished weight gradients that overlap
+        # the remaining backward kernels (models/backward.py: _OverlappedAllReduce); with several micro-batches per step
+        # the single flat all-reduce after the last backward is used instead (B200_DDP_OVERLAP=0 forces that path)
+        eng = getattr(getattr(self.model, 'module', self.model), 'engine', None)
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        overlap = (eng is not None and world > 1 and micro_batch >= B
+                   and __import__('os').environ.get('B200_DDP_OVERLAP', '1') != '0')
+        if eng is not None:
+            eng.ddp_overlap_bytes = self.bucket_bytes if overlap else 0
+            eng.grads_reduced = False
         for i in range(0, B, micro_batch):
             xs = x0[i:i + micro_batch].float()
             ts = t[i:i + micro_batch] if t is not None else \
@@ -53,7 +64,10 @@ class TrainStep:
             scale = xs.shape[0] / B
             (loss * scale).backward()
             total = loss.detach() * scale if total is None else total + loss.detach() * scale
-        allreduce_grads_(self.model)
+        if eng is not None:
+            eng.ddp_overlap_bytes = 0
+        if not (eng is not None and eng.grads_reduced):
+            allreduce_grads_(self.model)
         self.optimizer.step(clip_grad_norm=self.clip_grad_norm, ema=self.ema)
         return total
 

@@ -82,10 +82,43 @@ def mse_loss(pred, target):
     return MSELossFunction.apply(pred, target)
 
 
-class _Grads:
-    """Per-parameter fp32 gradient views into one flat, zero-initialised buffer (the kernels accumulate)."""
+def _record_params(e):
+    """Parameters whose gradients a tape record's backward writes: those of the modules the record references.  The
+    per-block embedding projection (`emb_linear`) belongs to the embedding record, which runs last."""
+    out = []
+    for k, v in e.items():
+        if k == 'emb_linear':
+            continue
+        vs = v if isinstance(v, (tuple, list)) else (v,)
+        for m in vs:
+            if isinstance(m, nn.Module):
+                out += list(m.parameters())
+    return out
 
-    def __init__(self, eng: Engine, params):
+
+def _completion_layout(tape, params):
+    """Order in which parameter gradients become FINAL during `run_backward` (head first, the embedding path last) and,
+    per tape position, how many parameters are complete once that record's backward has been issued.  The flat gradient
+    buffer is laid out in this order so that finished prefixes of it can be all-reduced while the rest of the backward
+    still runs (what DistributedDataParallel's buckets do for the reference, scripts/train_ddpm.py:166,180-184)."""
+    known = {id(p) for p in params}
+    order, seen, done_after = [], set(), {}
+    recs = [e for e in reversed(tape) if e['kind'] != 'embed'] + [e for e in tape if e['kind'] == 'embed']
+    for i, e in enumerate(recs):
+        for p in _record_params(e):
+            if id(p) in known and id(p) not in seen:
+                seen.add(id(p))
+                order.append(p)
+        done_after[id(e)] = len(order)
+    order += [p for p in params if id(p) not in seen]      # parameters this forward did not use: their gradient stays 0
+    return order, done_after
+
+
+class _Grads:
+    """Per-parameter fp32 gradient views into one flat, zero-initialised buffer (the kernels accumulate), laid out in
+    gradient-completion order (see _completion_layout)."""
+
+    def __init__(self, eng: Engine, params, tape=None):
         total = sum(p.numel() for p in params)
         # One persistent buffer per engine, zeroed per backward: stable gradient addresses across steps (optimizer
         # chunk tables, CUDA-graph capture, NCCL buffer registration).  autograd keeps the returned views as the
@@ -103,10 +136,21 @@ class _Grads:
         else:
             flat.zero_()
         self.flat = flat
+        self.aliased = aliased
+        # the layout depends on the network structure only: computed from the first tape, reused afterwards (a forward
+        # that takes another path -- e.g. with / without class labels -- keeps the addresses; its records simply
+        # complete in a slightly different order, which `ready_prefix` accounts for per backward)
+        layout = getattr(eng, '_grad_layout', None)
+        if layout is None or layout[0] != tuple(id(p) for p in params):
+            order = _completion_layout(tape, params)[0] if tape is not None else list(params)
+            layout = eng._grad_layout = (tuple(id(p) for p in params), order)
+        self.order = layout[1]
         self.views: Dict[int, torch.Tensor] = {}
+        self.offset: Dict[int, int] = {}
         off = 0
-        for p in params:
+        for p in self.order:
             self.views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+            self.offset[id(p)] = off
             off += p.numel()
         self.params = params
 
@@ -115,6 +159,62 @@ class _Grads:
 
     def as_tuple(self):
         return [self.views[id(p)] if p.requires_grad else None for p in self.params]
+
+
+class _OverlappedAllReduce:
+    """Data-parallel gradient averaging overlapped with the backward: as soon as the records issued so far have completed
+    a prefix of the flat gradient buffer that is `bucket_bytes` longer than what was already sent, that slice is
+    all-reduced asynchronously (NCCL's stream waits for the producing kernels, the compute stream carries on with the
+    remaining weight gradients); `finish()` sends the tail and makes the compute stream wait for all of them."""
+
+    def __init__(self, G: _Grads, tape, bucket_bytes: int):
+        import torch.distributed as dist
+        self.dist, self.G = dist, G
+        self.world = dist.get_world_size()
+        self.bucket = max(1, bucket_bytes // 4)
+        self.sent = 0
+        self.works = []
+        self.n_buckets = 0
+        self.avg = dist.get_backend() == 'nccl'
+        # elements of the flat buffer that are final after each record: the longest prefix of the layout whose parameters
+        # all belong to records already issued in THIS backward
+        self.pending = set()
+        for e in tape:
+            for p in _record_params(e):
+                self.pending.add(id(p))
+        self.prefix_param = 0
+
+    def _ready(self):
+        order = self.G.order
+        i = self.prefix_param
+        while i < len(order) and id(order[i]) not in self.pending:
+            i += 1
+        self.prefix_param = i
+        return self.G.offset[id(order[i])] if i < len(order) else self.G.flat.numel()
+
+    def after_record(self, e):
+        for p in _record_params(e):
+            self.pending.discard(id(p))
+        ready = self._ready()
+        if ready - self.sent >= self.bucket:
+            self._send(ready)
+
+    def _send(self, hi):
+        if hi <= self.sent:
+            return
+        sl = self.G.flat[self.sent:hi]
+        op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
+        self.works.append((self.dist.all_reduce(sl, op=op, async_op=True), sl))
+        self.sent = hi
+        self.n_buckets += 1
+
+    def finish(self):
+        self.pending.clear()
+        self._send(self.G.flat.numel())
+        for w, sl in self.works:
+            w.wait()
+            if not self.avg:
+                sl.div_(self.world)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -453,8 +553,18 @@ def run_backward(eng: Engine, tape, dout, params):
     """Replays `tape` in reverse.  dout: fp32 NCHW gradient of the network output."""
     if not dout.is_cuda or dout.dtype != torch.float32:
         raise RuntimeError('backward: expected a float32 CUDA gradient')
-    G = _Grads(eng, params)
-    eng.flat_grad = G.flat        # the parameters' gradients are views into this buffer, in registration order
+    G = _Grads(eng, params, tape)
+    eng.flat_grad = G.flat        # the parameters' gradients are views into this buffer, in completion order
+    # data-parallel training through b200diff.train.TrainStep: the gradient all-reduce runs INSIDE the backward, bucket by
+    # bucket (`eng.ddp_overlap_bytes` > 0 is set by TrainStep for single-micro-batch steps on > 1 ranks; plain autograd /
+    # DistributedDataParallel users never get here, their wrapper reduces the returned gradients itself)
+    ar = None
+    bucket = int(getattr(eng, 'ddp_overlap_bytes', 0) or 0)
+    eng.grads_reduced = False
+    if bucket > 0 and not G.aliased:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            ar = _OverlappedAllReduce(G, tape, bucket)
     with torch.no_grad():
         embed_rec = None
         for e in reversed(tape):
@@ -463,8 +573,15 @@ def run_backward(eng: Engine, tape, dout, params):
                 _head_bwd(eng, e, G, dout)
             elif kind == 'embed':
                 embed_rec = e        # recorded first, but its gradient is complete only after every block ran
+                continue
             else:
                 _BWD[kind](eng, e, G)
+            if ar is not None:
+                ar.after_record(e)
         if embed_rec is not None:
             _embed_bwd(eng, embed_rec, G)
+        if ar is not None:
+            ar.finish()
+            eng.grads_reduced = True
+            eng.ddp_buckets = ar.n_buckets
     return G.as_tuple()

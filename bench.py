@@ -540,7 +540,7 @@ def _extras(dev, peaks, world=1, rank=0):
                                          'batch 16, random weights', 'ms_per_forward': ms, 'tflops': tf,
                              'frac_of_bf16_sustained_peak': tf / peaks['bf16_sustained'],
                              'gflop_per_image': 2239.67, 'images_fwd_per_s': B / (ms * 1e-3),
-                             'arena_gb': sum(v.numel() * v.element_size() for v in m.engine._arena.values()) / 2 ** 30}
+                             'arena_gb': m.engine.arena_bytes() / 2 ** 30}
     del g
     try:
         steps_timed, S_adm = 25, 250

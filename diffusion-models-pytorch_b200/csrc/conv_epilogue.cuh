@@ -329,6 +329,19 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvKParams& p, const T
   const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
   float s1 = 0.f, s2 = 0.f, ra_c = 0.f;
   int cur_n = -1;
+  if (HAS_RES) {
+    // The residual of the whole tile is requested into L2 BEFORE waiting for the accumulator, so the DRAM round trip
+    // overlaps the tile's MMAs: one prefetch instruction per 32-pixel chunk (lane j asks for pixel j's 128-byte line of
+    // this warp's 32 channels), no registers held.  ncu on the attention blocks' 1x1 output projection (4 K-blocks per
+    // tile; profiles/r02_prof_conv.details.txt id 6) had shown the tensor pipe 7 % active, DRAM at 31 % and the residual
+    // FADDs as the top stall sites: eight epilogue warps with one 32-load batch each in flight and ~1.5 us per DRAM
+    // round trip cap such a layer at ~3 TB/s.  (Holding a second chunk's loads in registers instead spilled: 168
+    // registers is the cap for 10 warps.)
+    const int lane = threadIdx.x & 31;
+    const char* pf = rbase - (long long)lane * 4;      // channel of lane 0: start of the 128-byte line
+    for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (long long)(ch + lane) * rst));
+  }
   mbar_wait(acc_full_bar, acc_parity);
   tc_fence_after();
 #pragma unroll 1

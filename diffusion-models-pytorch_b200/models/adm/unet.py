@@ -262,6 +262,7 @@ class UNetModel(_EngineModel):
             for j, layer in enumerate(seq):
                 h = self._run_layer(f'input_blocks.{i}.{j}', layer, h, None, emb, emb_ld, offsets)
             hs.append(h)
+        eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
         for j, layer in enumerate(self.middle_block):
             h = self._run_layer(f'middle_block.{j}', layer, h, None, emb, emb_ld, offsets)
         for i, seq in enumerate(self.output_blocks):

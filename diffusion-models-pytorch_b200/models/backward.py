@@ -36,6 +36,7 @@ class UNetFunction(torch.autograd.Function):
             eng.last_tape = eng.tape     # introspection (tests read the dropout seeds from it)
         finally:
             eng.tape = None
+            eng.pingpong = False     # inference-only buffer sharing (Engine.buf) must not leak into the backward's requests
         ctx.model = model
         ctx.params = params
         return out

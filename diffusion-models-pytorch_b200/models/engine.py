@@ -12,6 +12,7 @@ the whole forward CUDA-graph capturable); the C library never allocates.
 Reference call sites replaced: models/unet.py:121-152 (UNet.forward), :30-43 (ResBlock.forward),
 models/modules.py:89-102 (SelfAttentionBlock.forward), models/unet_categorial_adagn.py:44-62,165-208.
 """
+import contextlib
 from typing import Dict, List, Optional
 
 import torch
@@ -53,6 +54,11 @@ class Engine:
         self._stats: Dict = {}
         self._stats_pools: Dict = {}     # input shape -> [[pool tensor, elements used]]
         self._cur_key = None             # input shape (+ lane) of the forward being issued
+        self.arena_reuse = __import__('os').environ.get('B200_ARENA_REUSE', '1') != '0'
+        self._scratch: Dict = {}         # (input shape, lane) -> scratch chunks of block temporaries (see buf / scope)
+        self._scope_depth = 0
+        self.pingpong = False            # set by the models from the bottleneck on (inference): see buf()
+        self._pp_count: Dict = {}
         self.lane = 0                    # buffer-set index: forwards issued concurrently on different streams (the sampling
                                          # runner's two half-batch branches) use different lanes = disjoint buffers
         self._device = None          # cached per forward (refresh re-reads it)
@@ -102,13 +108,75 @@ class Engine:
             d = self._device = next(self.model.parameters()).device
         return d
 
-    def buf(self, tag, shape, dtype):
+    def buf(self, tag, shape, dtype, temp=False):
+        """Arena buffer `tag` of the current forward.  Training forwards (tape) keep one buffer per tag: the backward reads
+        them.  Inference forwards reuse memory by liveness (B200_ARENA_REUSE=0 disables):
+          * temp=True inside a `scope()` (a block's bf16 operands, intermediates, attention workspaces): bump-allocated
+            from a scratch pool and released when the block's scope ends;
+          * block outputs while `pingpong` is set (bottleneck + decoder: nothing there is a skip connection): every block
+            reads only its predecessor's output, so outputs of equal shape alternate between two buffers.
+        Encoder outputs (the skips), embeddings and the statistics keep their own buffers.  The request sequence of a
+        forward is deterministic, so every buffer gets the same address in every forward (CUDA-graph replayable)."""
+        if self.tape is None and self.arena_reuse:
+            if temp and self._scope_depth > 0:
+                return self._temp(tag, tuple(shape), dtype)
+            if self.pingpong and isinstance(tag, str) and tag.endswith('.out'):
+                k = (tuple(shape), dtype)
+                n = self._pp_count.get(k, 0)
+                self._pp_count[k] = n + 1
+                tag = f'pingpong{n & 1}.out'
         key = (tag, tuple(shape), dtype, self.device, self.lane)
         t = self._arena.get(key)
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._arena[key] = t
         return t
+
+    def _temp(self, tag, shape, dtype):
+        """Bump allocation from the scratch chunks of the current (input shape, lane); 1 KB granularity (TMA operands need
+        128-byte alignment).  Chunks grow geometrically during the first forward of a shape and are then stable."""
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        need = (nbytes + 1023) // 1024 * 1024
+        st = self._scratch.get(self._cur_key)
+        if st is None:
+            st = self._scratch[self._cur_key] = {'chunks': [], 'pos': [0, 0], 'views': {}, 'peak': 0}
+        chunks, pos = st['chunks'], st['pos']
+        while not (pos[0] < len(chunks) and pos[1] + need <= chunks[pos[0]].numel()):
+            if pos[0] < len(chunks):
+                pos[0] += 1
+                pos[1] = 0
+            else:
+                total = sum(c.numel() for c in chunks)
+                chunks.append(torch.empty(max(need, total, 64 << 20), dtype=torch.uint8, device=self.device))
+                pos[1] = 0
+        vkey = (tag, shape, dtype, pos[0], pos[1])
+        v = st['views'].get(vkey)
+        if v is None:
+            v = st['views'][vkey] = chunks[pos[0]][pos[1]:pos[1] + nbytes].view(dtype).view(shape)
+        pos[1] += need
+        return v
+
+    @contextlib.contextmanager
+    def scope(self):
+        """Lifetime of a block's temporaries: buffers requested with temp=True inside are released at exit."""
+        st = self._scratch.get(self._cur_key)
+        saved = list(st['pos']) if st is not None else [0, 0]
+        self._scope_depth += 1
+        try:
+            yield
+        finally:
+            self._scope_depth -= 1
+            st = self._scratch.get(self._cur_key)
+            if st is not None:
+                st['pos'][0], st['pos'][1] = saved
+
+    def arena_bytes(self) -> int:
+        """Device memory held by activation buffers (arena + scratch chunks), all shapes and lanes."""
+        n = sum(t.numel() * t.element_size() for t in self._arena.values())
+        return n + sum(c.numel() for st in self._scratch.values() for c in st['chunks'])
 
     def stats_buf(self, tag, B, C):
         """[B, C, 2] int64 fixed-point accumulator (K.STAT_Q1 / K.STAT_Q2) for the GroupNorm statistics of a conv output
@@ -281,15 +349,15 @@ class Engine:
             if x.stats is None or (skip is not None and skip.stats is None):
                 raise RuntimeError(f"{tag}: precision='fp32' needs producer statistics for every GroupNorm input "
                                    '(parameter-free resampling layers are not supported in this mode)')
-            out = self.buf(tag + '.gn3', (x.B, Ho, Wo, 3 * C), torch.bfloat16)
-            raw_out = self.buf(tag + '.raw3', (x.B, x.H, x.W, 3 * C), torch.bfloat16) if raw else None
+            out = self.buf(tag + '.gn3', (x.B, Ho, Wo, 3 * C), torch.bfloat16, temp=True)
+            raw_out = self.buf(tag + '.raw3', (x.B, x.H, x.W, 3 * C), torch.bfloat16, temp=True) if raw else None
             K.groupnorm_apply_split(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
                                     None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
                                     norm.weight, norm.bias, norm.eps, out, scale=scale, shift=shift, ss_ld=ss_ld,
                                     silu=silu, resample=resample, raw_out=raw_out)
             return out, raw_out
-        out = self.buf(tag + '.gn', (x.B, Ho, Wo, C), torch.bfloat16)
-        raw_out = self.buf(tag + '.raw', (x.B, x.H, x.W, C), torch.bfloat16) if raw else None
+        out = self.buf(tag + '.gn', (x.B, Ho, Wo, C), torch.bfloat16, temp=True)
+        raw_out = self.buf(tag + '.raw', (x.B, x.H, x.W, C), torch.bfloat16, temp=True) if raw else None
         if x.stats is not None and (skip is None or skip.stats is not None):
             K.groupnorm_apply(x.t, x.C, x.stats, None if skip is None else skip.t, 0 if skip is None else skip.C,
                               None if skip is None else skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
@@ -306,7 +374,7 @@ class Engine:
         return out, raw_out
 
     def conv3x3(self, tag, a, B, H, W, Cin, conv, *, rowadd=None, rowadd_ld=0, residual: Optional[Act] = None,
-                sc_a=None, sc_C=0, sc_conv=None, out_mode=K.OUT_F32_NHWC, out=None, intermediate=False):
+                sc_a=None, sc_C=0, sc_conv=None, out_mode=K.OUT_F32_NHWC, out=None, intermediate=False, temp=False):
         Cout = conv.out_channels
         w, b = self.w_conv(tag, conv, sc_conv)
         stats = None
@@ -315,7 +383,7 @@ class Engine:
             if intermediate and self.h_bf16 and Cout >= 128 and self.tape is None and not self.split:   # narrow toy nets keep fp32 h
                 out_mode = K.OUT_BF16_NHWC
             out = self.buf(tag + '.out', (B, H, W, Cout),
-                           torch.bfloat16 if out_mode == K.OUT_BF16_NHWC else torch.float32)
+                           torch.bfloat16 if out_mode == K.OUT_BF16_NHWC else torch.float32, temp=temp or intermediate)
             stats = self.stats_buf(tag, B, Cout) if Cout > 32 else None
         K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(m * Cin, H, W, 1),
                  a1=sc_a, a1_geom=(m * sc_C, H, W, 1) if sc_a is not None else None, bias=b,
@@ -347,7 +415,11 @@ class Engine:
         return self.attention_core(tag, x, blk.norm, weights, blk.n_heads, blk.scale,
                                    mods=(blk.q, blk.k, blk.v, blk.proj))
 
-    def _attention_split(self, tag, blk, x: Act) -> Act:
+    def _attention_split(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._attention_split_body(*args, **kwargs)
+
+    def _attention_split_body(self, tag, blk, x: Act) -> Act:
         """FP32-mode attention block (models/modules.py:89-102): GroupNorm -> q, k, v 1x1 convs with fp32 outputs ->
         S = q k^T and O = softmax(S d^-1/2) v as batched tensor-core GEMMs over split operands (K = 3d resp. 3T), exact
         row softmax in between -> 1x1 proj + residual.  [B*h, T, T] scores are materialised (accuracy mode)."""
@@ -374,27 +446,27 @@ class Engine:
             weights = hit[0]
         wqkv, bqkv, wp, bp = weights
         n, _ = self.gn(tag, x, None, blk.norm, silu=False)                       # [B, T, 3C] split
-        qkv = self.buf(tag + '.qkv32', (B, T, 3 * C), torch.float32)
+        qkv = self.buf(tag + '.qkv32', (B, T, 3 * C), torch.float32, temp=True)
         K.conv2d(n, wqkv, 3 * C, B, H, W, K.taps_1x1(), a0_geom=(3 * C, H, W, 1), bias=bqkv, out=qkv,
                  alg_macs=float(B) * T * 3 * C * C)
         bf = torch.bfloat16
-        qs = self.buf(tag + '.q3', (B, T, 3 * C), bf)      # per head [q_hi | q_lo | q_hi]
-        ks = self.buf(tag + '.k3', (B, T, 3 * C), bf)      # per head [k_hi | k_hi | k_lo]
-        vs = self.buf(tag + '.v3', (B, 3, T, C), bf)       # planes [v_hi; v_hi; v_lo] along the key dimension
+        qs = self.buf(tag + '.q3', (B, T, 3 * C), bf, temp=True)      # per head [q_hi | q_lo | q_hi]
+        ks = self.buf(tag + '.k3', (B, T, 3 * C), bf, temp=True)      # per head [k_hi | k_hi | k_lo]
+        vs = self.buf(tag + '.v3', (B, 3, T, C), bf, temp=True)       # planes [v_hi; v_hi; v_lo] along the key dimension
         K.split_cast(qkv, qs, B * T, C, in_ld=3 * C, in_col0=0, group=d, pattern=K.SPLIT_ACT)
         K.split_cast(qkv, ks, B * T, C, in_ld=3 * C, in_col0=C, group=d, pattern=K.SPLIT_WEIGHT)
         K.split_cast(qkv, vs, B * T, C, in_ld=3 * C, in_col0=2 * C, pattern=K.SPLIT_WEIGHT, planes_rows=T)
         G_ = B * heads
-        S = self.buf('attn3_ws.S', (G_, T, T), torch.float32)
-        P = self.buf('attn3_ws.P', (G_, T, 3 * T), bf)
+        S = self.buf('attn3_ws.S', (G_, T, T), torch.float32, temp=True)
+        P = self.buf('attn3_ws.P', (G_, T, 3 * T), bf, temp=True)
         grid = dict(batch=B, heads=heads)
         K.gemm_batched((qs, T, 3 * C, dict(col_base=0, col_head=3 * d)), (ks, T, 3 * C, dict(col_base=0, col_head=3 * d)), S,
                        T, T, 3 * d, **grid, out_ld=T, out_batch_stride=heads * T * T, out_head_stride=T * T)
         K.softmax_rows_split(S, P, G_ * T, T, blk.scale)
-        o = self.buf(tag + '.o32', (B, T, C), torch.float32)
+        o = self.buf(tag + '.o32', (B, T, C), torch.float32, temp=True)
         K.gemm_batched((P, T, 3 * T, dict(per_head_batch=True)), (vs, 3 * T, C, dict(col_head=d, mn_major=True)), o,
                        T, d, 3 * T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
-        os_ = self.buf(tag + '.o3', (B, T, 3 * C), bf)
+        os_ = self.buf(tag + '.o3', (B, T, 3 * C), bf, temp=True)
         K.split_cast(o, os_, B * T, C)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
         stats = self.stats_buf(tag, B, C)
@@ -402,7 +474,11 @@ class Engine:
                  stats=stats, alg_macs=float(B) * T * C * C)
         return Act(out, B, H, W, C, stats)
 
-    def attention_core(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:
+    def attention_core(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._attention_core_body(*args, **kwargs)
+
+    def _attention_core_body(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:
         """GroupNorm -> [q|k] and v^T 1x1 convs -> fused softmax(q k^T * scale) v -> 1x1 proj + residual.
         `weights` = (Wqk [2C, C] bf16 with rows [q heads..., k heads...], bqk, Wv [C, C], bv, Wproj, bproj)."""
         if self.split:
@@ -417,12 +493,12 @@ class Engine:
                                'b200_attention_fwd')
         wqk, bqk, wv, bv, wp, bp = weights
         n, _ = self.gn(tag, x, None, norm, silu=False)
-        qk = self.buf(tag + '.qk', (B, T, 2 * C), torch.bfloat16)
+        qk = self.buf(tag + '.qk', (B, T, 2 * C), torch.bfloat16, temp=True)
         K.conv2d(n, wqk, 2 * C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bqk, out=qk,
                  out_mode=K.OUT_BF16_NHWC)
-        vt = self.buf(tag + '.vt', (B, C, T), torch.bfloat16)
+        vt = self.buf(tag + '.vt', (B, C, T), torch.bfloat16, temp=True)
         K.conv2d(n, wv, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bv, out=vt, out_mode=K.OUT_BF16_NCHW)
-        o = self.buf(tag + '.o', (B, T, C), torch.bfloat16)
+        o = self.buf(tag + '.o', (B, T, C), torch.bfloat16, temp=True)
         K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
         stats = self.stats_buf(tag, B, C)
@@ -436,10 +512,14 @@ class Engine:
                                   scale=scale, mods=mods))
         return res
 
-    def downsample_conv(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
+    def downsample_conv(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._downsample_conv_body(*args, **kwargs)
+
+    def _downsample_conv_body(self, tag, conv: nn.Conv2d, x: Act, pad_lo=1) -> Act:
         B, H, W, C = x.B, x.H, x.W, x.C
         m = self.m3
-        planes = self.buf(tag + '.planes', (B, 4, H // 2, W // 2, m * C), torch.bfloat16)
+        planes = self.buf(tag + '.planes', (B, 4, H // 2, W // 2, m * C), torch.bfloat16, temp=True)
         if self.split:
             self._fp32_inference_only(tag)
             K.split_cast(x.t, planes, B * H * W, C, parity_hw=(H, W))
@@ -456,7 +536,11 @@ class Engine:
             self.tape.append(dict(kind='down', tag=tag, x=x, out=res, conv=conv, planes=planes, pad_lo=pad_lo))
         return res
 
-    def upsample_conv(self, tag, conv: nn.Conv2d, x: Act) -> Act:
+    def upsample_conv(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._upsample_conv_body(*args, **kwargs)
+
+    def _upsample_conv_body(self, tag, conv: nn.Conv2d, x: Act) -> Act:
         """nearest-2x + conv3x3 as four 2x2-tap phase convolutions on the low-res grid (2.25x fewer MACs)."""
         B, H, W, C = x.B, x.H, x.W, x.C
         if self.tape is not None:
@@ -468,7 +552,7 @@ class Engine:
             self.tape.append(dict(kind='up', tag=tag, x=x, out=res, conv=conv, ub=ub))
             return res
         m = self.m3
-        xb = self.buf(tag + '.bf16', (B, H, W, m * C), torch.bfloat16)
+        xb = self.buf(tag + '.bf16', (B, H, W, m * C), torch.bfloat16, temp=True)
         if self.split:
             K.split_cast(x.t, xb, B * H * W, C)
         else:
@@ -495,7 +579,7 @@ class Engine:
         """SiLU(GN2(conv1(a1) + bias [+ emb row]) [* (1 + scale) + shift]) in ONE launch -> the bf16 operand of conv2.
         The caller checked K.conv2d_gn_ok for this layer; a rejected launch raises (no per-layer fallback)."""
         w, b = self.w_conv(tag + '.c1', conv1)
-        a2 = self.buf(tag + '.2.gn', (B, Ho, Wo, Cout), torch.bfloat16)
+        a2 = self.buf(tag + '.2.gn', (B, Ho, Wo, Cout), torch.bfloat16, temp=True)
         if scale_shift:
             K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
                         beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
@@ -506,7 +590,11 @@ class Engine:
                         rowadd=emb[:, emb_off:], rowadd_ld=emb_ld)
         return a2
 
-    def resblock_core(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
+    def resblock_core(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._resblock_core_body(*args, **kwargs)
+
+    def _resblock_core_body(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
                       emb_ld, scale_shift: bool, resample: int = 0, dropout: Optional[nn.Dropout] = None,
                       emb_linear: Optional[nn.Linear] = None) -> Act:
         """The ResBlock shared by all UNet families:
@@ -530,7 +618,7 @@ class Engine:
         Ho, Wo = (H // 2, W // 2) if resample == 1 else (H * 2, W * 2) if resample == 2 else (H, W)
         res_x = x
         if resample:
-            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32)
+            r = self.buf(tag + '.xr', (B, Ho, Wo, x.C), torch.float32, temp=True)
             (K.avgpool2_f32 if resample == 1 else K.upsample2_f32)(x.t, r, B, H, W, x.C)
             res_x = Act(r, B, Ho, Wo, x.C)
         drop_p, drop_seed = 0.0, 0
@@ -552,7 +640,7 @@ class Engine:
             out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=shortcut)
         else:
             if sc3x3:
-                res_x = self.conv3x3(tag + '.sc', raw, B, Ho, Wo, Cin, shortcut)
+                res_x = self.conv3x3(tag + '.sc', raw, B, Ho, Wo, Cin, shortcut, temp=True)
             else:
                 assert skip is None and Cin == Cout
             out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, residual=res_x)
@@ -652,7 +740,11 @@ class Engine:
             self.tape.append(dict(kind='first', tag=tag, X=X, out=res, conv=conv))
         return res
 
-    def head(self, tag, h: Act, norm: nn.GroupNorm, conv: nn.Conv2d, out):
+    def head(self, *args, **kwargs):
+        with self.scope():       # the block's temporaries are released when it returns
+            return self._head_body(*args, **kwargs)
+
+    def _head_body(self, tag, h: Act, norm: nn.GroupNorm, conv: nn.Conv2d, out):
         """GroupNorm -> SiLU -> 3x3 conv to the few output channels, written as the reference's NCHW fp32."""
         a, _ = self.gn(tag, h, None, norm)
         if out is None:
@@ -667,6 +759,11 @@ class Engine:
         (models/backward.py) refers to arena buffers instead of saving copies, so its backward checks that no other
         forward of the same shape ran in between."""
         self._cur_key = tuple(X.shape) + (self.lane,)
+        self.pingpong = False
+        self._pp_count.clear()
+        st = self._scratch.get(self._cur_key)
+        if st is not None:
+            st['pos'][0], st['pos'][1] = 0, 0
         self._fwd_gen[self._cur_key] = self._fwd_gen.get(self._cur_key, 0) + 1
         for pool, used in self._stats_pools.get(self._cur_key, ()):
             pool[:used].zero_()

@@ -185,6 +185,7 @@ class Model(_EngineModel):
                 hs.append(eng.downsample_conv(f'down.{i}.downsample.conv', ds.conv, hs[-1], pad_lo=0)
                           if ds.with_conv else eng.resample_plain(f'down.{i}.downsample', hs[-1], 1))
 
+        eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
         h = run_res('mid.block_1', self.mid.block_1, hs[-1])
         h = run_attn('mid.attn_1', self.mid.attn_1, h)
         h = run_res('mid.block_2', self.mid.block_2, h)

@@ -174,6 +174,7 @@ class UNet(_EngineModel):
                     h = eng.downsample_conv(name, blk, h)
                     skips.append(h)
 
+        eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
         h = run_res('bottleneck_block.0', self.bottleneck_block[0], h)
         h = eng.attention('bottleneck_block.1', self.bottleneck_block[1], h)
         h = run_res('bottleneck_block.2', self.bottleneck_block[2], h)

@@ -227,15 +227,26 @@ def case_cfg():
     # rounding (amplified by the guided trajectory), not bitwise; with B200_CFG_BATCH=0 they are bit-identical.
     gp = _psnr(got, got_e)
     _emit(case='info: ddimcfg50 batched-guidance graph vs two-forward eager loop (chaotic trajectory, not gated)', psnr_db=gp, ok=True)
-    # gated: ONE batched forward over [x ; x] with labels [y ; -1] against the two separate forwards (same weights / inputs):
-    # the halves differ only by fp32 accumulation order and the few bf16 roundings it flips
+    # gated: ONE batched forward over [x ; x] with labels [y ; -1] against the oracle's cond / uncond forwards (1e-2 like every
+    # bf16 forward), and -- to pin the label handling exactly -- against the two separate forwards in precision='fp32',
+    # where rounding noise does not mask a structural difference.  (In bf16 two schedules of the same arithmetic differ by
+    # ~6e-3: once a perturbation exceeds ~1e-4 it flips a sizeable fraction of the bf16 rounding decisions downstream, so
+    # the rounding noise of the two runs decorrelates; identical images at different batch positions show the same.)
     with torch.no_grad():
         B2 = x.shape[0]
-        both = m(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, torch.full_like(y, -1)]))
-        r_c, r_u = _rel_l2(both[:B2], m(x, t, y)), _rel_l2(both[B2:], m(x, t, None))
-    _emit(case='batched guidance forward [y ; -1] vs separate cond / uncond forwards', rel_l2_cond=r_c, rel_l2_uncond=r_u,
-          gate=1e-3, ok=max(r_c, r_u) <= 1e-3)
-    ok &= max(r_c, r_u) <= 1e-3
+        x2, t2, y2 = torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, torch.full_like(y, -1)])
+        both = m(x2, t2, y2)
+        r_c, r_u = _rel_l2(both[:B2], ref(x, t, y)), _rel_l2(both[B2:], ref(x, t, None))
+        _emit(case='batched guidance forward [y ; -1] vs oracle cond / uncond', rel_l2_cond=r_c, rel_l2_uncond=r_u, gate=1e-2,
+              ok=max(r_c, r_u) <= 1e-2)
+        ok &= max(r_c, r_u) <= 1e-2
+        m.set_precision('fp32')
+        both = m(x2, t2, y2)
+        f_c, f_u = _rel_l2(both[:B2], m(x, t, y)), _rel_l2(both[B2:], m(x, t, None))
+        m.set_precision('bf16')
+        _emit(case="batched [y ; -1] vs separate cond / uncond forwards, precision='fp32'", rel_l2_cond=f_c, rel_l2_uncond=f_u,
+              gate=1e-4, ok=max(f_c, f_u) <= 1e-4)
+        ok &= max(f_c, f_u) <= 1e-4
     os.environ['B200_CFG_BATCH'] = '0'
     try:
         with torch.no_grad():

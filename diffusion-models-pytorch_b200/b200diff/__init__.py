@@ -77,6 +77,14 @@ class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next
     ]
 
 
+class AttnBlockDesc(ctypes.Structure):
+    """Mirror of b200_attn_block_desc (include/b200diff.h)."""
+    _fields_ = [('x', c_void_p), ('x_stats', c_void_p), ('gamma', c_void_p), ('beta', c_void_p), ('w', c_void_p),
+                ('bias', c_void_p), ('out', c_void_p), ('out_stats', c_void_p), ('dbg', c_void_p * 6),
+                ('B', c_int), ('T', c_int), ('C', c_int), ('heads', c_int), ('groups', c_int),
+                ('eps', c_float), ('scale', c_float), ('pad_', c_int)]
+
+
 class SplitDesc(Structure):       # mirrors b200_split_desc (FP32 mode: fp32 -> bf16 hi/lo split operands)
     _fields_ = [('in_', c_void_p), ('rows', c_longlong), ('in_ld', c_int), ('in_col0', c_int), ('C', c_int), ('group', c_int),
                 ('pattern', c_int), ('act', c_int), ('out', c_void_p), ('out_ld', c_int), ('out_col0', c_int),
@@ -155,6 +163,8 @@ def lib():
     L.b200_conv2d_fwd.argtypes = [POINTER(ConvDesc), c_void_p]
     L.b200_conv2d_gn_fwd.argtypes = [POINTER(ConvDesc), POINTER(GnFuseDesc), c_void_p]
     L.b200_conv2d_gn_fwd.restype = c_int
+    L.b200_attn_block_fwd.argtypes = [POINTER(AttnBlockDesc), c_void_p]
+    L.b200_attn_block_fwd.restype = c_int
     L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p]
     L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
@@ -222,7 +232,7 @@ BACKWARD_SYMBOLS = (
 PRECISE_SYMBOLS = ('b200_split_cast', 'b200_groupnorm_apply_split_fwd', 'b200_softmax_rows_split')
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + PRECISE_SYMBOLS + (
-    'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_conv3x3_first',
+    'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_attn_block_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
 )
@@ -605,6 +615,36 @@ def attention(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale):
             lambda: _check(lib().b200_attention_fwd(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(),
                                                     ld_out, B, T, heads, d, float(scale), _stream()), 'attention_fwd'),
             flops=4.0 * B * heads * T * T * d)
+    return out
+
+
+def attn_block_ok(T, C, heads, groups) -> bool:
+    """Static eligibility for the one-launch attention block (mirrors b200_attn_block_fwd's checks)."""
+    return T == 256 and C == 256 and heads == 1 and groups == 32
+
+
+def attn_block(x, x_stats, gamma, beta, eps, w, bias, out, out_stats, B, T, C, heads, groups, scale, dbg=None):
+    """b200_attn_block_fwd: out = x + proj(softmax(q k^T scale) v) with q, k, v = 1x1 convs of GroupNorm(x), one launch.
+    x / out fp32 [B, T, C]; w bf16 [4C, C] = [Wq; Wk; Wv; Wproj]; bias fp32 [4C].  `dbg`: up to six bf16 [B, 256, 256]
+    tensors (or None) receiving xn, q, k, v^T, P, o (tests)."""
+    _need_cuda(x, w, out)
+    _need_stats(x_stats)
+    _need_stats(out_stats)
+    for t_, dt in ((x, torch.float32), (out, torch.float32), (w, torch.bfloat16), (bias, torch.float32),
+                   (gamma, torch.float32), (beta, torch.float32)):
+        if t_.dtype != dt or not t_.is_contiguous():
+            raise RuntimeError(f'attn_block: expected contiguous {dt} tensors, got {t_.dtype} (contiguous={t_.is_contiguous()})')
+    if tuple(w.shape) != (4 * C, C) or bias.numel() != 4 * C or x.numel() != B * T * C or out.numel() != B * T * C:
+        raise RuntimeError('attn_block: shape mismatch')
+    d = AttnBlockDesc()
+    d.x, d.x_stats, d.gamma, d.beta = x.data_ptr(), x_stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    d.w, d.bias, d.out, d.out_stats = w.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(out_stats)
+    for i in range(6):
+        d.dbg[i] = _ptr(dbg[i]) if dbg is not None and i < len(dbg) else None
+    d.B, d.T, d.C, d.heads, d.groups = B, T, C, heads, groups
+    d.eps, d.scale = float(eps), float(scale)
+    _launch('attn_block', lambda: _check(lib().b200_attn_block_fwd(ctypes.byref(d), _stream()), 'attn_block_fwd'),
+            flops=2.0 * B * T * C * (4 * C + 2 * T), nbytes=8.0 * B * T * C)
     return out
 
 

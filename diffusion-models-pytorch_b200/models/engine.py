@@ -40,6 +40,10 @@ class Engine:
     # (16x16 / 8x8 / 4x4 levels, inference only): the intermediate h is never written and one GroupNorm launch per
     # ResBlock disappears (measured: DDIM-50 CIFAR-10 1035 -> 1057 images/s).  B200_FUSE_GN2=0: two launches (A/B).
     fuse_gn2 = bool(int(__import__('os').environ.get('B200_FUSE_GN2', '1')))
+    # whole self-attention block (GroupNorm, q / k / v projections, softmax(q k^T) v, output projection, residual) as ONE
+    # launch for the CIFAR-10 UNet's 16x16 blocks (T = 256, C = 256, one head; inference only): q, k, v and the attention
+    # output never touch HBM.  B200_ATTN_BLOCK=0: the five-launch form (A/B).
+    attn_block = bool(int(__import__('os').environ.get('B200_ATTN_BLOCK', '1')))
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -396,6 +400,9 @@ class Engine:
         """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2."""
         if self.split:
             return self._attention_split(tag, blk, x)
+        if (self.attn_block and self.tape is None and x.stats is not None
+                and K.attn_block_ok(x.H * x.W, x.C, blk.n_heads, blk.norm.num_groups)):
+            return self._attention_block_fused(tag, blk, x)
         key = ('attn', tag)
         hit = self._pt.get(key)
         if hit is None:
@@ -414,6 +421,28 @@ class Engine:
             weights = hit[0]
         return self.attention_core(tag, x, blk.norm, weights, blk.n_heads, blk.scale,
                                    mods=(blk.q, blk.k, blk.v, blk.proj))
+
+    def _attention_block_fused(self, tag, blk, x: Act) -> Act:
+        """models/modules.py:89-102 in one launch (b200_attn_block_fwd).  The caller checked K.attn_block_ok."""
+        key = ('attnblk', tag)
+        hit = self._pt.get(key)
+        if hit is None:
+            C = blk.q.out_channels
+            w = torch.empty((4 * C, C), dtype=torch.bfloat16, device=self.device)
+            b = torch.empty(4 * C, dtype=torch.float32, device=self.device)
+            entries = []
+            for i, mod in enumerate((blk.q, blk.k, blk.v, blk.proj)):
+                entries.append(K.pack_entry_bytes(mod.weight, w, C, C, 1, 0, row0=i * C, ld=C))
+                entries.append(K.pack_entry_bytes(mod.bias, b[i * C:], C, 1, 1, 2))
+            w, b = self.pack_table(key, (w, b), entries)
+        else:
+            w, b = hit[0]
+        B, H, W, C = x.B, x.H, x.W, x.C
+        out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
+        stats = self.stats_buf(tag, B, C)
+        K.attn_block(x.t, x.stats, blk.norm.weight, blk.norm.bias, blk.norm.eps, w, b, out, stats, B, H * W, C,
+                     blk.n_heads, blk.norm.num_groups, blk.scale)
+        return Act(out, B, H, W, C, stats)
 
     def _attention_split(self, *args, **kwargs):
         with self.scope():       # the block's temporaries are released when it returns

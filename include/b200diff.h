@@ -151,6 +151,35 @@ int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const vo
                        int B, int T, int heads, int d, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K2b: the WHOLE self-attention block (models/modules.py:77-102, SelfAttentionBlock.forward) in one launch:
+ *     out = x + proj(softmax(q k^T * scale) v),  q, k, v = 1x1 convs of GroupNorm(x)      (no SiLU in this norm)
+ * for the CIFAR-10 UNet's 16x16 blocks: T = 256 tokens, C = 256 channels, ONE head, 32 groups.  One 2-CTA cluster
+ * per image (tcgen05 cta_group::2); q, k, v, the scores and the attention output stay in shared memory / TMEM.
+ *   x        fp32 NHWC [B][T][C] residual stream, x_stats its producer statistics [B][C][2] (int64 fixed point)
+ *   w        bf16 [4C][C]: rows [0,C) = Wq, [C,2C) = Wk, [2C,3C) = Wv, [3C,4C) = Wproj, each [out][in] (K-major)
+ *   bias     fp32 [4C] in the same order
+ *   out      fp32 NHWC [B][T][C] (must not alias x), out_stats: statistics of out for the next GroupNorm (or NULL)
+ *   dbg[6]   tests only: bf16 [B][256][256] dumps of xn, q, k, v^T, P (unnormalised), o; all NULL in production
+ * Other shapes take the five-launch path (b200_groupnorm_apply_fwd, b200_conv2d_fwd x3, b200_attention_fwd).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct b200_attn_block_desc {
+  const float* x;
+  const long long* x_stats;
+  const float* gamma;
+  const float* beta;
+  const void* w;
+  const float* bias;
+  float* out;
+  long long* out_stats;
+  void* dbg[6];
+  int B, T, C, heads, groups;
+  float eps;
+  float scale;
+  int pad_;
+} b200_attn_block_desc;
+int b200_attn_block_fwd(const b200_attn_block_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Time embedding path (models/modules.py:40-57, models/unet.py:64-69,18-21).
  * b200_time_embed: t[rows] (int64) -> [sin(t f), cos(t f)] over the dim/2 frequencies `freqs` (cos first when
  *   cos_first, the ADM variant models/adm/nn.py:103-121) -> Linear(dim,E) -> SiLU -> Linear(E,E) (+ class

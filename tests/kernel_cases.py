@@ -498,6 +498,54 @@ def case_attention():
     return ok
 
 
+def _attn_block_case(name, B, debug):
+    """b200_attn_block_fwd (T=256, C=256, one head) against the fp32 op sequence of models/modules.py:89-102; with
+    `debug` every on-chip intermediate (xn, q, k, v^T, P, o) is dumped and checked too, which localises a failure."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    T = C = 256
+    x = _gen(B, T, C, seed=1) * (_gen(1, 1, C, seed=2).abs() + 0.5) + _gen(1, 1, C, seed=3)
+    gamma = _gen(C, seed=4) * 0.2 + 1.0
+    beta = _gen(C, seed=5) * 0.2
+    w = _gen(4 * C, C, seed=6) * (C ** -0.5)
+    w[:2 * C] *= 1.5                      # sharper softmax than the default initialisation gives
+    bias = _gen(4 * C, seed=7) * 0.3
+    eps, scale = 1e-5, C ** -0.5
+    wb = w.to(torch.bfloat16).contiguous()
+    wf = wb.float()
+    st = K.stats_from_float(torch.stack([x.sum(dim=1), (x * x).sum(dim=1)], dim=-1).contiguous())
+    # fp32 restatement, rounding to bf16 exactly where the kernel does
+    xn = _bf16r(F.group_norm(x.transpose(1, 2), 32, gamma, beta, eps).transpose(1, 2))       # [B, T, C]
+    q = _bf16r(xn @ wf[:C].t() + bias[:C])
+    k = _bf16r(xn @ wf[C:2 * C].t() + bias[C:2 * C])
+    v = _bf16r(xn @ wf[2 * C:3 * C].t() + bias[2 * C:3 * C])
+    s = (q @ k.transpose(1, 2)) * scale
+    pu = _bf16r(torch.exp(s - s.max(dim=-1, keepdim=True).values))                            # unnormalised, as stored
+    o = _bf16r((pu @ v) / torch.exp(s - s.max(dim=-1, keepdim=True).values).sum(dim=-1, keepdim=True))
+    ref = x + o @ wf[3 * C:].t() + bias[3 * C:]
+    out = torch.full((B, T, C), float('nan'), device=DEV)
+    ost = K.new_stats(B, C, DEV)
+    dbg = [torch.full((B, T, C), float('nan'), device=DEV, dtype=torch.bfloat16) for _ in range(6)] if debug else None
+    K.attn_block(x.contiguous(), st, gamma, beta, eps, wb, bias, out, ost, B, T, C, 1, 32, scale, dbg=dbg)
+    torch.cuda.synchronize()
+    ok = True
+    if debug:
+        for nm, got, want, tol in (('xn', dbg[0], xn, 1e-2), ('q', dbg[1], q, 2e-2), ('k', dbg[2], k, 2e-2),
+                                   ('v^T', dbg[3].transpose(1, 2), v, 2e-2), ('P', dbg[4], pu, 3e-2), ('o', dbg[5], o, 3e-2)):
+            ok &= _report(f'{name} [{nm}]', got, want, rtol=tol, atol=tol)
+    ok &= _report(name, out, ref, rtol=2e-2, atol=2e-2)
+    got_st = K.stats_to_float(ost)
+    want_st = torch.stack([out.sum(dim=1), (out * out).sum(dim=1)], dim=-1)
+    ok &= _report(name + ' [statistics of the result]', got_st, want_st, rtol=1e-4, atol=1e-2)
+    return ok
+
+
+def case_attn_block():
+    ok = _attn_block_case('attn_block B=3 (debug dumps)', 3, True)
+    ok &= _attn_block_case('attn_block B=2', 2, False)
+    ok &= _attn_block_case('attn_block B=160 (persistent: 3 images per cluster, ragged)', 160, False)
+    return ok
+
+
 # ----------------------------------------------------------------------------------------------------
 # backward-pass GEMMs: batched GEMM in all major combinations, conv weight gradient
 # ----------------------------------------------------------------------------------------------------

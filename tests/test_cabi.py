@@ -45,12 +45,13 @@ def test_struct_layout_matches_header(tmp_path):
     fields = {'b200_conv_desc': b200diff.ConvDesc, 'b200_sampler_desc': b200diff.SamplerDesc,
               'b200_gemm_desc': b200diff.GemmDesc, 'b200_wgrad_desc': b200diff.WgradDesc,
               'b200_gn_bwd_desc': b200diff.GnBwdDesc, 'b200_optim_desc': b200diff.OptimDesc,
-              'b200_ode_desc': b200diff.OdeDesc, 'b200_gn_fuse_desc': b200diff.GnFuseDesc}
+              'b200_ode_desc': b200diff.OdeDesc, 'b200_gn_fuse_desc': b200diff.GnFuseDesc,
+              'b200_attn_block_desc': b200diff.AttnBlockDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200diff.h"', 'int main(void) {']
     for cname, cls in fields.items():
         for fname, ftype in cls._fields_:
-            if isinstance(ftype, type) and issubclass(ftype, ctypes.Structure):
-                continue      # nested structs (gemm operands): covered by the offsets of the members that follow them
+            if isinstance(ftype, type) and issubclass(ftype, (ctypes.Structure, ctypes.Array)):
+                continue      # nested structs (gemm operands) / arrays: covered by the offsets of the members that follow them
             lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
         lines.append(f'  printf("{cname}.sizeof %zu\\n", sizeof({cname}));')
     lines += ['  return 0;', '}']
@@ -61,7 +62,7 @@ def test_struct_layout_matches_header(tmp_path):
     out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
     for cname, cls in fields.items():
         for fname, ftype in cls._fields_:
-            if isinstance(ftype, type) and issubclass(ftype, ctypes.Structure):
+            if isinstance(ftype, type) and issubclass(ftype, (ctypes.Structure, ctypes.Array)):
                 continue
             assert int(out[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
         assert int(out[f'{cname}.sizeof']) == ctypes.sizeof(cls), cname

@@ -20,7 +20,7 @@
 // result for the next block).  Three 64 KB operand regions are reused by liveness: R0 = xn -> V^T, R1 = Q -> P,
 // R2 = K -> O; weights stream through a 2 x 16 KB TMA ring (each CTA loads its 128 rows of every 64-wide K chunk).
 // Warp 16 = TMA producer (both CTAs), warp 17 = MMA issuer (leader CTA only).  Worker -> MMA hand-offs are mbarriers
-// in the LEADER's shared memory (32 warp arrivals with cluster-scope release), MMA -> worker hand-offs are multicast
+// in the LEADER's shared memory (32 warp arrivals after a proxy fence), MMA -> worker hand-offs are multicast
 // tcgen05.commit arrivals on both CTAs.
 #include "pair.cuh"
 #include <stdlib.h>
@@ -233,15 +233,18 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     float* red_max = reinterpret_cast<float*>(R2);      // [4][128], alive between s_done and p_ready (K is dead)
     float* red_sum = red_max + 4 * 128;
 
-    // GroupNorm of the own 128 tokens of image b -> xn (bf16, R0).  A warp takes 8 token rows; lane = 8-channel group.
-    auto gn_transform = [&](int b) {
-      float4 raw[16];
-      const float* xb = p.x + ((size_t)b * kAbT + rank * 128 + warp * 8) * kAbC + 8 * lane;
+    // GroupNorm of the own 128 tokens of image b -> xn (bf16, R0).  A warp takes 8 token rows; lane = 8-channel group
+    // (= one GroupNorm group).  The fp32 loads are issued in two halves of 4 rows so that the first half can be in
+    // flight across the wait for the P V MMA and the O drain (R0 must not be written before o_done).
+    auto gn_issue = [&](int b, int i0, float4 (&raw)[8]) {
+      const float* xb = p.x + ((size_t)b * kAbT + rank * 128 + warp * 8 + i0) * kAbC + 8 * lane;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         raw[2 * i] = ab_ldg4(xb + (size_t)i * kAbC);
         raw[2 * i + 1] = ab_ldg4(xb + (size_t)i * kAbC + 4);
       }
+    };
+    auto gn_finish = [&](int b, float4 (&rawA)[8], float4 (&rawB)[8]) {
       const float2 gs = stat_load_group(p.x_stats + ((size_t)b * kAbC + 8 * lane) * 2, 8);
       const float inv_cnt = 1.0f / (float)(8 * kAbT);
       const float mean = gs.x * inv_cnt;
@@ -258,7 +261,7 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = warp * 8 + i;
-        const float4 v0 = raw[2 * i], v1 = raw[2 * i + 1];
+        const float4 v0 = i < 4 ? rawA[2 * i] : rawB[2 * (i - 4)], v1 = i < 4 ? rawA[2 * i + 1] : rawB[2 * (i - 4) + 1];
         uint4 u;
         u.x = pack_bf16x2(fmaf(v0.x, a[0], bb[0]), fmaf(v0.y, a[1], bb[1]));
         u.y = pack_bf16x2(fmaf(v0.z, a[2], bb[2]), fmaf(v0.w, a[3], bb[3]));
@@ -270,21 +273,39 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader_release(&bars->xn_ready);
+      if (lane == 0) mbar_arrive_leader(&bars->xn_ready);
     };
-    // hand a finished shared-memory operand (and the TMEM block it was read from) to the MMA issuer
+    // hand a finished shared-memory operand (and the TMEM block it was read from) to the MMA issuer: the proxy fence
+    // orders this thread's shared-memory writes before the tensor core's (async-proxy) reads, the arrival on the leader's
+    // barrier is observed by the MMA thread before it issues (same hand-off as a CUTLASS transform -> UMMA pipeline; a
+    // cluster-scope release here costs MEMBAR.GPU + ERRBAR per arrival: 12 % of the kernel in the first version)
     auto publish = [&](uint64_t* bar) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader_release(bar);
+      if (lane == 0) mbar_arrive_leader(bar);
+    };
+    // L2 prefetch of the own fp32 tile (128 tokens x 1 KB, contiguous) of a later image: 2 lines per thread
+    auto prefetch_tile = [&](int b) {
+      const char* base = reinterpret_cast<const char*>(p.x + ((size_t)b * kAbT + rank * 128) * kAbC);
+      const int tid = threadIdx.x;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)tid * 128));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(tid + kAbWorkers) * 128));
     };
 
     int it = 0;
-    if (cluster_id < p.B) gn_transform(cluster_id);
+    if (cluster_id < p.B) {
+      float4 rawA[8], rawB[8];
+      gn_issue(cluster_id, 0, rawA);
+      gn_issue(cluster_id, 4, rawB);
+      if (cluster_id + n_clusters < p.B) prefetch_tile(cluster_id + n_clusters);
+      gn_finish(cluster_id, rawA, rawB);
+    }
     for (int b = cluster_id; b < p.B; b += n_clusters, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
       const size_t row_g = (size_t)b * kAbT + rank * 128 + r;     // this thread's row of the [B][256][256] debug dumps
+      const bool has_next = b + n_clusters < p.B;
+      if (b + 2 * n_clusters < p.B) prefetch_tile(b + 2 * n_clusters);
 
       // ---- Q, K: TMEM -> bf16 operands (+ bias) ----
       mbar_wait(&bars->q_done, ph);
@@ -353,34 +374,45 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       publish(&bars->p_ready);
 
       // ---- O / rowsum -> bf16 operand of the output projection (overwrites K and the reduction scratch) ----
+      float4 rawA[8];
+      if (has_next) gn_issue(b + n_clusters, 0, rawA);          // in flight across the P V MMA and the O drain
       mbar_wait(&bars->o_done, ph);
       tc_fence_after();
       ab_drain<kDbg>(tm0, R2, r, part, nullptr, 0.f, 1.0f / sum, kDbg && p.dbg[5] ? p.dbg[5] + row_g * kAbC : nullptr);
       publish(&bars->o_drained);
 
-      // ---- next image's GroupNorm while the projection MMAs run (R0 = V^T is dead since o_done) ----
-      if (b + n_clusters < p.B) gn_transform(b + n_clusters);
+      // ---- next image's GroupNorm while the projection MMA runs (R0 = V^T is dead since o_done) ----
+      if (has_next) {
+        float4 rawB[8];
+        gn_issue(b + n_clusters, 4, rawB);
+        gn_finish(b + n_clusters, rawA, rawB);
+      }
 
-      // ---- epilogue: Y^T + bias + residual -> fp32 NHWC, GroupNorm statistics of the result ----
-      mbar_wait(&bars->y_done, ph);
-      tc_fence_after();
+      // ---- epilogue: Y^T + bias + residual -> fp32 NHWC, GroupNorm statistics of the result.  16-token chunks, the
+      // residual loads of chunk i + 1 (and of chunk 0 across the wait for the MMA) in flight while chunk i is stored ----
       {
         const int c = rank * 128 + r;                               // TMEM lane = output channel
         const float bp = __ldg(p.bias + 768 + c);
+        const size_t base0 = ((size_t)b * kAbT + part * 64) * kAbC + c;
         float s1 = 0.f, s2 = 0.f;
+        float res[2][16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int t0 = part * 64 + h * 32;
-          const size_t base = ((size_t)b * kAbT + t0) * kAbC + c;
-          float res[32];
+        for (int j = 0; j < 16; ++j) res[0][j] = __ldg(p.x + base0 + (size_t)j * kAbC);
+        mbar_wait(&bars->y_done, ph);
+        tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) res[j] = __ldg(p.x + base + (size_t)j * kAbC);
-          uint32_t v[32];
-          tmem_ld_x32(tm1 + (uint32_t)t0, v);
+        for (int ch = 0; ch < 4; ++ch) {
+          const size_t base = base0 + (size_t)(ch * 16) * kAbC;
+          if (ch < 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) res[(ch + 1) & 1][j] = __ldg(p.x + base + (size_t)(16 + j) * kAbC);
+          }
+          uint32_t v[16];
+          tmem_ld_x16(tm1 + (uint32_t)(part * 64 + ch * 16), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = __uint_as_float(v[j]) + bp + res[j];
+          for (int j = 0; j < 16; ++j) {
+            const float y = __uint_as_float(v[j]) + bp + res[ch & 1][j];
             p.out[base + (size_t)j * kAbC] = y;
             s1 += y;
             s2 = fmaf(y, y, s2);
@@ -390,7 +422,7 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader_release(&bars->y_drained);
+      if (lane == 0) mbar_arrive_leader(&bars->y_drained);
     }
   }
 

@@ -27,6 +27,7 @@ struct ConvKParams {
   int epi_halves;  // 1 or 2 epilogue warps per TMEM lane quarter
   int k_rotate;    // rotate the K-block order per CTA (spreads weight-tile requests over L2)
   int fast_epi;  // output pixel index is linear in the tile pixel index, all tiles full, >= 16 pixels per image
+  int row_epi;   // 8 consecutive tile pixels are 8 output pixels osx apart in one row (strided / phase outputs), tiles full
   int vtap;      // vertical-tap reuse (conv_gemm.cu): one haloed pixel tile + 3 weight tiles per stage
   int dbg;       // timing experiments, builds with -DB200_DEBUG only (B200_EPI_DBG: 1 = no residual loads, 2 = no output
                  // stores, 4 = epilogue does nothing, 8 / 16 = no weight / pixel TMA); always 0 in the shipping library
@@ -400,9 +401,70 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvKParams& p, const T
   }
 }
 
+// Lean epilogue for outputs that are only ROW-wise linear in the tile pixel index: the four phase convolutions of the
+// nearest-2x + 3x3 up-sampling layers (output pixel = 2 * tile pixel + phase offset) and other strided writes.  Groups of 8
+// consecutive tile pixels lie in one tile row (bw >= 8), so a group costs one base-address computation and its 8 stores
+// are compile-time multiples of the pixel stride.  No residual / time-embedding row (the up-sampling convs have neither).
+// The generic epilogue decodes every group of 4 pixels with 64-bit arithmetic per store: the 256 -> 256 up-conv at
+// 16x16 -> 32x32 (B = 256) ran 25 k cycles per tile against 8 k cycles of MMA work.
+template <bool BF16_OUT, bool HAS_STATS>
+__device__ __forceinline__ void conv_epilogue_lean_rows(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
+                                                        const int c, const bool c_ok, const int half,
+                                                        uint64_t* acc_full_bar, const uint32_t acc_parity) {
+  constexpr int kOutBytes = BF16_OUT ? 2 : 4;
+  const int pa = t.ph >> 1, pb = t.ph & 1;
+  const long long pst = (long long)p.osx * p.out_ld * kOutBytes;     // bytes between consecutive tile pixels of a row
+  char* const obase = reinterpret_cast<char*>(p.out) + (size_t)c * kOutBytes;
+  const float bias_c = (p.bias && c_ok) ? __ldg(p.bias + c) : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  int cur_n = -1;
+  mbar_wait(acc_full_bar, acc_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = half * 32; ch < p.NP; ch += 32 * p.epi_halves) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(taddr + (uint32_t)ch, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int pp = ch + 8 * g;
+      const int n = t.n0 + (pp >> p.lg_bhw);
+      if (HAS_STATS && n != cur_n) {      // warp-uniform: new image -> flush statistics
+        if (c_ok && cur_n >= 0) stat_add(p.stats + ((size_t)cur_n * p.N + c) * 2, s1, s2);
+        s1 = 0.f; s2 = 0.f;
+        cur_n = n;
+      }
+      const int oy = (t.h0 + ((pp >> p.lg_bw) & (p.bh - 1))) * p.osy + pa;
+      const int ox = (t.w0 + (pp & (p.bw - 1))) * p.osx + pb;
+      char* op = obase + ((size_t)(n * p.out_H + oy) * p.out_W + ox) * (size_t)(p.out_ld * kOutBytes);
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float a0 = __uint_as_float(v[8 * g + j]) + bias_c, a1 = __uint_as_float(v[8 * g + j + 1]) + bias_c;
+        if (c_ok) {
+          if (BF16_OUT) {
+            *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * pst) = __float2bfloat16_rn(a0);
+            *reinterpret_cast<__nv_bfloat16*>(op + (long long)(j + 1) * pst) = __float2bfloat16_rn(a1);
+          } else {
+            *reinterpret_cast<float*>(op + (long long)j * pst) = a0;
+            *reinterpret_cast<float*>(op + (long long)(j + 1) * pst) = a1;
+          }
+        }
+        if (HAS_STATS) {
+          s1 += a0; t1 += a1;
+          s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
+        }
+      }
+      if (HAS_STATS) { s1 += t1; s2 += t2; }
+    }
+  }
+  if (HAS_STATS && c_ok && cur_n >= 0 && cur_n < p.B) stat_add(p.stats + ((size_t)cur_n * p.N + c) * 2, s1, s2);
+}
+
 // Host-side eligibility of a layer for the lean epilogue (also asserted by the device dispatch below).
 inline bool conv_epilogue_lean_ok(const ConvKParams& p) {
-  return p.fast_epi && p.out_mode <= B200_OUT_BF16_NHWC && B200_DBG(p) == 0;
+  return (p.fast_epi || p.row_epi) && p.out_mode <= B200_OUT_BF16_NHWC && B200_DBG(p) == 0;
 }
 
 __device__ __forceinline__ void conv_epilogue_lean_dispatch(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
@@ -410,6 +472,13 @@ __device__ __forceinline__ void conv_epilogue_lean_dispatch(const ConvKParams& p
                                                             uint64_t* bar, const uint32_t parity) {
   const bool bf = p.out_mode == B200_OUT_BF16_NHWC, rs = p.residual != nullptr, st = p.stats != nullptr;
   const bool rw = p.rowadd != nullptr;
+  if (!p.fast_epi && p.row_epi && p.out_mode <= B200_OUT_BF16_NHWC && B200_DBG(p) == 0) {
+    if (bf) { if (st) conv_epilogue_lean_rows<true, true>(p, t, taddr, c, c_ok, half, bar, parity);
+              else conv_epilogue_lean_rows<true, false>(p, t, taddr, c, c_ok, half, bar, parity); }
+    else { if (st) conv_epilogue_lean_rows<false, true>(p, t, taddr, c, c_ok, half, bar, parity);
+           else conv_epilogue_lean_rows<false, false>(p, t, taddr, c, c_ok, half, bar, parity); }
+    return;
+  }
   if (!(p.fast_epi && p.out_mode <= B200_OUT_BF16_NHWC && B200_DBG(p) == 0)) {
     conv_epilogue_tile(p, t, taddr, c, c_ok, half, bar, parity);
     return;

@@ -340,6 +340,12 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   p.fast_epi = (d->phases == 1 && d->osx == 1 && d->osy == 1 && p.bw == d->Wo && d->out_W == d->Wo &&
                 d->out_H == d->Ho && (p.bn == 1 || p.bh == d->Ho) && d->B % p.bn == 0 && p.lg_bhw >= 4) ? 1 : 0;
 
+  // row-wise linear outputs (up-sampling phase convs, strided writes): lean epilogue with one address per 8 pixels
+  static const char* env_rowepi = getenv("B200_EPI_ROWS");    // =0: generic epilogue (A/B timing)
+  p.row_epi = (!p.fast_epi && !(env_rowepi && atoi(env_rowepi) == 0) && p.bw >= 8 && p.lg_bhw >= 3 && d->B % p.bn == 0 &&
+               d->residual == nullptr && d->rowadd == nullptr && d->out_mode <= B200_OUT_BF16_NHWC &&
+               (p.bn == 1 || (p.bw == d->Wo && p.bh == d->Ho))) ? 1 : 0;
+
   // two epilogue warps per lane quarter when the per-tile epilogue is long relative to the MMA work
   static const char* env_halves = getenv("B200_EPI_HALVES");
   p.epi_halves = env_halves ? atoi(env_halves) : 2;

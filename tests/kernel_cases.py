@@ -216,7 +216,8 @@ def case_conv_up2():
     """nearest-2x + conv3x3 (models/modules.py:60-67) as the 4-phase 2x2 decomposition."""
     torch.backends.cudnn.allow_tf32 = False
     ok = True
-    for (B, C, Co, H) in [(2, 256, 256, 16), (3, 256, 256, 4)]:
+    # (16, 256, 256, 16): enough tiles for the CTA-pair kernel; H = 8 / 16: row-linear lean epilogue; H = 4: generic epilogue
+    for (B, C, Co, H) in [(2, 256, 256, 16), (3, 256, 256, 4), (16, 256, 256, 16), (5, 256, 256, 8), (4, 128, 128, 8)]:
         x = _bf16r(_gen(B, C, H, H, seed=1))
         w = _gen(Co, C, 3, 3, seed=2, scale=1.0 / math.sqrt(C * 9))
         b = _gen(Co, seed=3)
@@ -236,10 +237,13 @@ def case_conv_up2():
         # approximately equal (different rounding); check it loosely as well
         ref_sem = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, b, padding=1)
         out = torch.full((B, 2 * H, 2 * H, Co), float('nan'), device=DEV)
+        st = K.new_stats(B, Co, DEV)
         K.conv2d(_nhwc_bf16(x), wp, Co, B, H, H, K.taps_up2_3x3(), a0_geom=(C, H, H, 1), bias=b, out=out,
-                 out_mode=K.OUT_F32_NHWC, w_rows_per_phase=Co)
+                 out_mode=K.OUT_F32_NHWC, w_rows_per_phase=Co, stats=st)
         torch.cuda.synchronize()
         got = out.permute(0, 3, 1, 2)
+        want_st = torch.stack([out.sum(dim=(1, 2)), (out * out).sum(dim=(1, 2))], dim=-1)
+        ok &= _report(f'up2+conv3x3 {C}->{Co} @{H}->{2 * H} B={B} statistics', K.stats_to_float(st), want_st, 1e-4, 1e-2)
         ok &= _report(f'up2+conv3x3 {C}->{Co} @{H}->{2 * H} vs phase-kernel ref', got, ref, 2e-4, 2e-4)
         ok &= _report(f'up2+conv3x3 {C}->{Co} @{H}->{2 * H} vs nearest+conv fp32-weight ref', got, ref_sem, 2e-2, 2e-2)
     return ok

@@ -37,7 +37,8 @@ constexpr uint32_t kAbRegion = 65536;                    // one bf16 [128 rows][
 constexpr uint32_t kAbWStage = 16384;                    // [128 rows][64 k] bf16
 constexpr int kAbWStages = 2;
 constexpr uint32_t kAbBarsOff = 3 * kAbRegion + kAbWStages * kAbWStage;
-constexpr size_t kAbSmemBytes = kAbBarsOff + 256 + 1024;
+constexpr uint32_t kAbBiasOff = kAbBarsOff + 256;            // q bias [256] fp32 (the only column-indexed bias: see below)
+constexpr size_t kAbSmemBytes = kAbBiasOff + 1024 + 1024;
 
 struct AttnBlockParams {
   const float* x;
@@ -81,8 +82,9 @@ __device__ __forceinline__ void ab_drain(uint32_t taddr, uint8_t* region, int r,
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * i + j]) * row_scale + row_bias;
-      if (col_bias != nullptr) {
-        const float4 b0 = ab_ldg4(col_bias + c0 + 8 * i), b1 = ab_ldg4(col_bias + c0 + 8 * i + 4);
+      if (col_bias != nullptr) {      // shared memory (warp-uniform address: broadcast)
+        const float4 b0 = *reinterpret_cast<const float4*>(col_bias + c0 + 8 * i);
+        const float4 b1 = *reinterpret_cast<const float4*>(col_bias + c0 + 8 * i + 4);
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       }
@@ -108,6 +110,7 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   uint8_t* R2 = smem + 2 * kAbRegion;
   uint8_t* WS = smem + 3 * kAbRegion;
   AbBars* bars = reinterpret_cast<AbBars*>(smem + kAbBarsOff);
+  float* s_bq = reinterpret_cast<float*>(smem + kAbBiasOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -137,6 +140,7 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(&bars->tmem_base, 512);
+  if (threadIdx.x < kAbC) s_bq[threadIdx.x] = __ldg(p.bias + threadIdx.x);     // parameters: not written by the preceding grid
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -244,11 +248,15 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         raw[2 * i + 1] = ab_ldg4(xb + (size_t)i * kAbC + 4);
       }
     };
-    auto gn_finish = [&](int b, float4 (&rawA)[8], float4 (&rawB)[8]) {
+    // (mean, rstd) of this lane's group; fetched an image ahead so that the statistics' round trip is off the critical path
+    auto gn_moments = [&](int b) {
       const float2 gs = stat_load_group(p.x_stats + ((size_t)b * kAbC + 8 * lane) * 2, 8);
       const float inv_cnt = 1.0f / (float)(8 * kAbT);
       const float mean = gs.x * inv_cnt;
-      const float rstd = rsqrtf(fmaxf(gs.y * inv_cnt - mean * mean, 0.f) + p.eps);
+      return make_float2(mean, rsqrtf(fmaxf(gs.y * inv_cnt - mean * mean, 0.f) + p.eps));
+    };
+    auto gn_finish = [&](int b, float4 (&rawA)[8], float4 (&rawB)[8], const float2 mom) {
+      const float mean = mom.x, rstd = mom.y;
       float a[8], bb[8];
       {
         const float4 g0 = ab_ldg4(p.gamma + 8 * lane), g1 = ab_ldg4(p.gamma + 8 * lane + 4);
@@ -299,22 +307,25 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       gn_issue(cluster_id, 0, rawA);
       gn_issue(cluster_id, 4, rawB);
       if (cluster_id + n_clusters < p.B) prefetch_tile(cluster_id + n_clusters);
-      gn_finish(cluster_id, rawA, rawB);
+      gn_finish(cluster_id, rawA, rawB, gn_moments(cluster_id));
     }
     for (int b = cluster_id; b < p.B; b += n_clusters, ++it) {
       const uint32_t ph = (uint32_t)it & 1u;
       const size_t row_g = (size_t)b * kAbT + rank * 128 + r;     // this thread's row of the [B][256][256] debug dumps
       const bool has_next = b + n_clusters < p.B;
       if (b + 2 * n_clusters < p.B) prefetch_tile(b + 2 * n_clusters);
+      float2 mom_next = make_float2(0.f, 0.f);
+      if (has_next) mom_next = gn_moments(b + n_clusters);
 
-      // ---- Q, K: TMEM -> bf16 operands (+ bias) ----
+      // ---- Q, K: TMEM -> bf16 operands (q + bias) ----
       mbar_wait(&bars->q_done, ph);
       tc_fence_after();
-      ab_drain<kDbg>(tm0, R1, r, part, p.bias, 0.f, 1.f, kDbg && p.dbg[1] ? p.dbg[1] + row_g * kAbC : nullptr);
+      ab_drain<kDbg>(tm0, R1, r, part, s_bq, 0.f, 1.f, kDbg && p.dbg[1] ? p.dbg[1] + row_g * kAbC : nullptr);
       publish(&bars->q_drained);
       mbar_wait(&bars->k_done, ph);
       tc_fence_after();
-      ab_drain<kDbg>(tm1, R2, r, part, p.bias + 256, 0.f, 1.f, kDbg && p.dbg[2] ? p.dbg[2] + row_g * kAbC : nullptr);
+      // the k bias adds q_i . b_k to every score of row i: softmax is invariant to it, so it is never applied
+      ab_drain<kDbg>(tm1, R2, r, part, nullptr, 0.f, 1.f, kDbg && p.dbg[2] ? p.dbg[2] + row_g * kAbC : nullptr);
       publish(&bars->k_drained);
 
       // ---- V^T: rows = this CTA's 128 d channels, columns = all keys; overwrites xn ----
@@ -385,7 +396,7 @@ attn_block_pair_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       if (has_next) {
         float4 rawB[8];
         gn_issue(b + n_clusters, 4, rawB);
-        gn_finish(b + n_clusters, rawA, rawB);
+        gn_finish(b + n_clusters, rawA, rawB, mom_next);
       }
 
       // ---- epilogue: Y^T + bias + residual -> fp32 NHWC, GroupNorm statistics of the result.  16-token chunks, the

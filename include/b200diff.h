@@ -159,7 +159,8 @@ int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const vo
  *   w        bf16 [4C][C]: rows [0,C) = Wq, [C,2C) = Wk, [2C,3C) = Wv, [3C,4C) = Wproj, each [out][in] (K-major)
  *   bias     fp32 [4C] in the same order
  *   out      fp32 NHWC [B][T][C] (must not alias x), out_stats: statistics of out for the next GroupNorm (or NULL)
- *   dbg[6]   tests only: bf16 [B][256][256] dumps of xn, q, k, v^T, P (unnormalised), o; all NULL in production
+ *   dbg[6]   tests only: bf16 [B][256][256] dumps of xn, q, k (without its bias: a per-row shift of the scores, which
+ *            softmax cancels), v^T, P (unnormalised), o; all NULL in production
  * Other shapes take the five-launch path (b200_groupnorm_apply_fwd, b200_conv2d_fwd x3, b200_attention_fwd).
  * --------------------------------------------------------------------------------------------- */
 typedef struct b200_attn_block_desc {

@@ -520,7 +520,7 @@ def _attn_block_case(name, B, debug):
     # fp32 restatement, rounding to bf16 exactly where the kernel does
     xn = _bf16r(F.group_norm(x.transpose(1, 2), 32, gamma, beta, eps).transpose(1, 2))       # [B, T, C]
     q = _bf16r(xn @ wf[:C].t() + bias[:C])
-    k = _bf16r(xn @ wf[C:2 * C].t() + bias[C:2 * C])
+    k = _bf16r(xn @ wf[C:2 * C].t())      # the kernel drops the k bias: it shifts every score of a row equally
     v = _bf16r(xn @ wf[2 * C:3 * C].t() + bias[2 * C:3 * C])
     s = (q @ k.transpose(1, 2)) * scale
     pu = _bf16r(torch.exp(s - s.max(dim=-1, keepdim=True).values))                            # unnormalised, as stored

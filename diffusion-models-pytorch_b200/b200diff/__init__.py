@@ -463,12 +463,19 @@ def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
     """Static eligibility of a layer for the fused conv + next-GroupNorm entry (mirrors the checks of
     b200_conv2d_gn_fwd, so the engine decides per layer up front instead of catching a rejected launch)."""
     hw = Ho * Wo
-    if hw not in (16, 64, 256) or N % 128 != 0 or groups < 1 or N % groups != 0:
+    if N % 128 != 0 or groups < 1 or N % groups != 0:
         return False
     cpg = N // groups
     if cpg > 32 or cpg & (cpg - 1):
         return False
+    if hw in (512, 1024):        # cluster variant: 2 / 4 CTAs share an image; 128 output channels, full-width 256-pixel tiles
+        return _GN_CLUSTER and N == 128 and Wo <= 256 and 256 % Wo == 0 and Ho % (256 // Wo) == 0
+    if hw not in (16, 64, 256):
+        return False
     return hw >= 64 or B % (64 // hw) == 0      # the smallest tile is 64 pixels = 4 whole 4x4 images
+
+
+_GN_CLUSTER = os.environ.get('B200_FUSE_GN2_CLUSTER', '1') != '0'   # =0: 32x32 layers keep conv + GroupNorm launches (A/B)
 
 
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,

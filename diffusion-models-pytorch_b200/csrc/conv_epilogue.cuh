@@ -38,6 +38,7 @@ struct ConvKParams {
   const float* gn_shift;
   void* gn_out;
   int gn_ss_ld, gn_lg_cpg, gn_silu;
+  int gn_cl;     // CTAs (cluster size) that share one image in the cluster variant of the fused epilogue, else 0
   float gn_eps;
 };
 
@@ -515,10 +516,32 @@ __device__ __forceinline__ float epi_silu_tanh(float x) {
   return x * fmaf(0.5f, th, 0.5f);   // identical to silu_tanh in groupnorm.cu
 }
 
-template <bool HAS_ROW, bool HAS_SS>
+// Cluster variant (CLUSTER = true, kernel instantiation <kThreads, 3>): an image spans p.gn_cl tiles (32x32 images = 4
+// tiles of 256 pixels) which the p.gn_cl CTAs of one thread-block cluster process in the same iteration.  After the
+// in-CTA exchange every CTA sends its per-channel tile sums to all CTAs of the cluster (st.async into their shared
+// memory, completion counted on the destination's mbarrier as transaction bytes: no fence, no cluster barrier) and
+// adds the p.gn_cl contributions in rank order, so all CTAs obtain bitwise the same image statistics.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
+
+struct __align__(8) GnClusterBars {
+  uint64_t full[2];      // per tile parity: 1 local arrive.expect_tx + gn_cl * 128 * 8 transaction bytes
+};
+
+template <bool HAS_ROW, bool HAS_SS, bool CLUSTER = false>
 __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
                                                      const int c, const int half, const int cl, float* xbuf,
-                                                     uint64_t* acc_full_bar, const uint32_t acc_parity) {
+                                                     uint64_t* acc_full_bar, const uint32_t acc_parity,
+                                                     float* cbuf = nullptr, uint64_t* cl_bar = nullptr,
+                                                     const uint32_t cl_parity = 0) {
   // cl = channel inside the tile (0..127); xbuf = this tile's exchange buffer [2 halves][4 chunks][128][2]
   const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
   const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
@@ -568,7 +591,32 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
   }
   // image statistics of the (chunk, half-chunk) slots of this thread
   float S1[4][2], S2[4][2];
-  if (p.lg_bhw >= 8) {          // one image per tile: everything
+  if (CLUSTER) {                // the tile is 1 / gn_cl of its image
+    // tile sums in a fixed order (both warps of a lane quarter must obtain the same bits: `half` swaps own / partner)
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float m1 = ps1[i][0] + ps1[i][1], m2 = ps2[i][0] + ps2[i][1];
+      a += half == 0 ? m1 + o1[i] : o1[i] + m1;
+      b += half == 0 ? m2 + o2[i] : o2[i] + m2;
+    }
+    const uint32_t bar_addr = smem_u32(cl_bar);
+    if (half == 0) {
+      uint32_t my_rank;
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(my_rank));
+      if (cl == 0) mbar_arrive_expect_tx(cl_bar, (uint32_t)(p.gn_cl * 128 * 8));
+      const uint32_t slot = smem_u32(cbuf + ((my_rank * 128 + cl) << 1));
+      for (int dst = 0; dst < p.gn_cl; ++dst) st_async_f32x2(mapa_shared(slot, (uint32_t)dst), a, b, mapa_shared(bar_addr, (uint32_t)dst));
+    }
+    mbar_wait(cl_bar, cl_parity);
+    a = 0.f; b = 0.f;
+    for (int r = 0; r < p.gn_cl; ++r) {
+      const float2 v2 = *reinterpret_cast<const float2*>(cbuf + ((r * 128 + cl) << 1));
+      a += v2.x; b += v2.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = a; S2[i][0] = S2[i][1] = b; }
+  } else if (p.lg_bhw >= 8) {          // one image per tile: everything
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1] + o1[i]; b += ps2[i][0] + ps2[i][1] + o2[i]; }
@@ -594,7 +642,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
         S2[i][hf] += __shfl_xor_sync(0xffffffffu, S2[i][hf], m);
       }
   }
-  const float inv_cnt = 1.0f / (float)((1 << p.lg_bhw) << p.gn_lg_cpg);
+  const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (CLUSTER ? p.gn_cl : 1));
   const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f;
   const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
   __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.N + c;

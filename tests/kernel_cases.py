@@ -1201,16 +1201,20 @@ def case_pack_weights():
 
 
 def case_conv_gnfuse():
-    """EXPERIMENTAL entry b200_conv2d_gn_fwd (conv1 -> norm2 of a ResBlock fused in the conv epilogue; not part of the
-    default GPU suite until it has been validated): SiLU(GN(conv3x3(x) + bias + time-embedding row)) as bf16 NHWC, with
+    """b200_conv2d_gn_fwd (conv1 -> norm2 of a ResBlock fused in the conv epilogue): SiLU(GN(conv3x3(x) + bias + time-embedding row)) as bf16 NHWC, with
     and without AdaGN scale / shift, at the three resolutions where a tile holds whole images."""
     import b200diff as K
     torch.backends.cudnn.allow_tf32 = False
     ok = True
     for (B, Cin, Cout, H, rowadd, ss, silu) in ((160, 256, 256, 16, True, False, True), (160, 256, 256, 8, True, False, True),
                                                  (320, 256, 256, 4, True, False, True), (160, 128, 256, 8, False, True, True),
-                                                 (128, 256, 128, 16, False, False, False)):
+                                                 (128, 256, 128, 16, False, False, False),
+                                                 # 32x32 images: 4 tiles per image, statistics exchanged inside a 4-CTA cluster
+                                                 (150, 128, 128, 32, True, False, True), (37, 384, 128, 32, True, True, True),
+                                                 (3, 128, 128, 32, False, False, True)):
         x = _bf16r(_gen(B, Cin, H, H, seed=1))
+        if H == 32:   # statistics that differ between the four tiles of an image
+            x = x * torch.linspace(0.5, 2.0, H, device=DEV)[None, None, :, None]
         w = _bf16r(_gen(Cout, Cin, 3, 3, seed=2, scale=1.0 / math.sqrt(Cin * 9)))
         b = _gen(Cout, seed=3)
         ra = _gen(B, Cout + 64, seed=4) if rowadd else None

@@ -74,6 +74,7 @@ class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next
     _fields_ = [
         ('gamma', c_void_p), ('beta', c_void_p), ('scale', c_void_p), ('shift', c_void_p), ('out_norm', c_void_p),
         ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
+        ('xstats', c_void_p), ('xcount', c_void_p),
     ]
 
 
@@ -468,7 +469,7 @@ def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
     cpg = N // groups
     if cpg > 32 or cpg & (cpg - 1):
         return False
-    if hw in (512, 1024):        # cluster variant: 2 / 4 CTAs share an image; 128 output channels, full-width 256-pixel tiles
+    if hw in (512, 1024):        # multi-tile variant: 2 / 4 co-scheduled CTAs share an image; 128 output channels, full-width 256-pixel tiles
         return _GN_CLUSTER and N == 128 and Wo <= 256 and 256 % Wo == 0 and Ho % (256 // Wo) == 0
     if hw not in (16, 64, 256):
         return False
@@ -478,8 +479,13 @@ def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
 _GN_CLUSTER = os.environ.get('B200_FUSE_GN2_CLUSTER', '1') != '0'   # =0: 32x32 layers keep conv + GroupNorm launches (A/B)
 
 
+def conv2d_gn_needs_workspace(Ho, Wo) -> bool:
+    """Images of 512 / 1024 pixels span several tiles: the fused entry then needs zeroed `xstats` / `xcount` buffers."""
+    return Ho * Wo in (512, 1024)
+
+
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
-              rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True):
+              rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True, xstats=None, xcount=None):
     """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution;
     nothing else is written.  Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}),
     N % 128 == 0, power-of-two channels per group <= 32."""
@@ -500,6 +506,11 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
     g = GnFuseDesc()
     g.gamma, g.beta, g.scale, g.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
     g.out_norm, g.ss_ld, g.groups, g.apply_silu, g.eps = out_norm.data_ptr(), ss_ld, groups, int(silu), float(eps)
+    _need_stats(xstats, xcount)
+    if conv2d_gn_needs_workspace(Ho, Wo) and (xstats is None or xcount is None or xstats.numel() < B * N * 2
+                                              or xcount.numel() < B):
+        raise RuntimeError('conv2d_gn: images of 512 / 1024 pixels need zeroed int64 workspaces xstats [B, N, 2] and xcount [B]')
+    g.xstats, g.xcount = _ptr(xstats), _ptr(xcount)
     _launch('conv_gemm', lambda: _check(lib().b200_conv2d_gn_fwd(ctypes.byref(d), ctypes.byref(g), _stream()),
                                         'conv2d_gn_fwd'), flops=2.0 * B * Ho * Wo * N * d.w_K)
     return out_norm

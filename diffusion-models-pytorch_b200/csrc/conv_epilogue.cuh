@@ -38,7 +38,9 @@ struct ConvKParams {
   const float* gn_shift;
   void* gn_out;
   int gn_ss_ld, gn_lg_cpg, gn_silu;
-  int gn_cl;     // CTAs (cluster size) that share one image in the cluster variant of the fused epilogue, else 0
+  int gn_cl;     // tiles (= co-scheduled CTAs) per image in the multi-tile variant of the fused epilogue, else 0
+  long long* gn_xstats;            // multi-tile variant: zeroed [B][N][2] int64 statistics of the conv output
+  unsigned long long* gn_xcount;   // multi-tile variant: zeroed per-image arrival counters
   float gn_eps;
 };
 
@@ -516,32 +518,34 @@ __device__ __forceinline__ float epi_silu_tanh(float x) {
   return x * fmaf(0.5f, th, 0.5f);   // identical to silu_tanh in groupnorm.cu
 }
 
-// Cluster variant (CLUSTER = true, kernel instantiation <kThreads, 3>): an image spans p.gn_cl tiles (32x32 images = 4
-// tiles of 256 pixels) which the p.gn_cl CTAs of one thread-block cluster process in the same iteration.  After the
-// in-CTA exchange every CTA sends its per-channel tile sums to all CTAs of the cluster (st.async into their shared
-// memory, completion counted on the destination's mbarrier as transaction bytes: no fence, no cluster barrier) and
-// adds the p.gn_cl contributions in rank order, so all CTAs obtain bitwise the same image statistics.
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
+// Multi-tile variant (MULTI = true, kernel instantiation <kThreads, 3>): an image spans p.gn_cl tiles (32x32 images = 4
+// tiles of 256 pixels).  The persistent grid is a multiple of p.gn_cl, so the p.gn_cl tiles of an image are processed in
+// the same iteration by p.gn_cl CTAs, which are co-resident because the kernel is launched cooperatively.  Every epilogue
+// warp adds its per-channel sums to the image's [N][2] int64 fixed-point statistics in global memory (the same
+// order-independent accumulation the separate GroupNorm kernel consumes: bitwise reproducible), announces itself on a
+// per-image counter and waits until all 8 * gn_cl warps of the image have arrived; the accumulators stay in TMEM
+// meanwhile (the other TMEM buffer keeps the MMA warp busy with the next tile), then pass 2 normalises as usual.
+// (A first version exchanged the sums between the CTAs of a 4-CTA thread-block cluster through DSMEM: correct, but only
+// 33 clusters = 132 of the 148 SMs can be resident, which cost more than the GroupNorm launches saved.)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
-               "f"(a), "f"(b), "r"(remote_bar)
-               : "memory");
+// group sums read through L2 (written by other SMs during this kernel: no read-only / L1 path)
+__device__ __forceinline__ float2 stat_load_group_cg(const long long* pair, int cnt) {
+  long long a = 0, b = 0;
+  for (int i = 0; i < cnt; ++i) {
+    const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(pair) + i);
+    a += v.x; b += v.y;
+  }
+  return make_float2(__ll2float_rn(a) * (1.0f / kStatQ1), __ll2float_rn(b) * (1.0f / kStatQ2));
 }
 
-struct __align__(8) GnClusterBars {
-  uint64_t full[2];      // per tile parity: 1 local arrive.expect_tx + gn_cl * 128 * 8 transaction bytes
-};
-
-template <bool HAS_ROW, bool HAS_SS, bool CLUSTER = false>
+template <bool HAS_ROW, bool HAS_SS, bool MULTI = false>
 __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
                                                      const int c, const int half, const int cl, float* xbuf,
-                                                     uint64_t* acc_full_bar, const uint32_t acc_parity,
-                                                     float* cbuf = nullptr, uint64_t* cl_bar = nullptr,
-                                                     const uint32_t cl_parity = 0) {
+                                                     uint64_t* acc_full_bar, const uint32_t acc_parity) {
   // cl = channel inside the tile (0..127); xbuf = this tile's exchange buffer [2 halves][4 chunks][128][2]
   const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
   const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
@@ -573,6 +577,39 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
       ps2[i][hf] = s2 + t2;
     }
   }
+  float S1[4][2], S2[4][2];
+  if (MULTI) {
+    // own chunks of this tile -> the image's global statistics; wait for the other warps / tiles of the image
+    const int n = t.n0;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1]; b += ps2[i][0] + ps2[i][1]; }
+    stat_add(p.gn_xstats + ((size_t)n * p.N + c) * 2, a, b);
+    __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* cnt = p.gn_xcount + n;
+      atomicAdd(cnt, 1ULL);
+      const unsigned long long target = (unsigned long long)(8 * p.gn_cl);
+      uint64_t t0 = 0;
+      uint32_t spins = 0;
+      while (ld_acquire_u64(cnt) < target) {
+        if ((++spins & 0x3ff) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000ull) {
+            printf("b200diff: fused GroupNorm statistics wait timeout (block %d image %d)\n", blockIdx.x, n);
+            __trap();
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int g0 = (c >> p.gn_lg_cpg) << p.gn_lg_cpg;
+    const float2 gs = stat_load_group_cg(p.gn_xstats + ((size_t)n * p.N + g0) * 2, 1 << p.gn_lg_cpg);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = gs.x; S2[i][0] = S2[i][1] = gs.y; }
+  } else {
   // per-chunk sums of this warp -> shared memory; the partner warp (same channels, the other chunks) reads them
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -590,33 +627,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
     o2[i] = r2.y;
   }
   // image statistics of the (chunk, half-chunk) slots of this thread
-  float S1[4][2], S2[4][2];
-  if (CLUSTER) {                // the tile is 1 / gn_cl of its image
-    // tile sums in a fixed order (both warps of a lane quarter must obtain the same bits: `half` swaps own / partner)
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float m1 = ps1[i][0] + ps1[i][1], m2 = ps2[i][0] + ps2[i][1];
-      a += half == 0 ? m1 + o1[i] : o1[i] + m1;
-      b += half == 0 ? m2 + o2[i] : o2[i] + m2;
-    }
-    const uint32_t bar_addr = smem_u32(cl_bar);
-    if (half == 0) {
-      uint32_t my_rank;
-      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(my_rank));
-      if (cl == 0) mbar_arrive_expect_tx(cl_bar, (uint32_t)(p.gn_cl * 128 * 8));
-      const uint32_t slot = smem_u32(cbuf + ((my_rank * 128 + cl) << 1));
-      for (int dst = 0; dst < p.gn_cl; ++dst) st_async_f32x2(mapa_shared(slot, (uint32_t)dst), a, b, mapa_shared(bar_addr, (uint32_t)dst));
-    }
-    mbar_wait(cl_bar, cl_parity);
-    a = 0.f; b = 0.f;
-    for (int r = 0; r < p.gn_cl; ++r) {
-      const float2 v2 = *reinterpret_cast<const float2*>(cbuf + ((r * 128 + cl) << 1));
-      a += v2.x; b += v2.y;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = a; S2[i][0] = S2[i][1] = b; }
-  } else if (p.lg_bhw >= 8) {          // one image per tile: everything
+  if (p.lg_bhw >= 8) {          // one image per tile: everything
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1] + o1[i]; b += ps2[i][0] + ps2[i][1] + o2[i]; }
@@ -642,7 +653,8 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
         S2[i][hf] += __shfl_xor_sync(0xffffffffu, S2[i][hf], m);
       }
   }
-  const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (CLUSTER ? p.gn_cl : 1));
+  }   // !MULTI
+  const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (MULTI ? p.gn_cl : 1));
   const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f;
   const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
   __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.N + c;

@@ -62,21 +62,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, tmem_cols);
-  // cluster variant of the fused GroupNorm epilogue: per-parity exchange buffers [2][gn_cl][128][2] floats + barriers
-  // behind the in-CTA exchange buffers
-  float* const cbuf_base = reinterpret_cast<float*>(bars + 1) + 2 * 2048;
-  GnClusterBars* const clbars = reinterpret_cast<GnClusterBars*>(cbuf_base + 2 * 8 * 256);
-  if (kLean == 3 && warp == 1 && lane == 0) {
-    mbar_init(&clbars->full[0], 1);
-    mbar_init(&clbars->full[1], 1);
-    fence_barrier_init();
-  }
   tc_fence_before();
   __syncthreads();
-  if (kLean == 3) {   // every CTA's exchange barriers exist before a peer's first st.async can arrive
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   griddep_sync();
@@ -211,15 +198,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
       const bool c_ok = c < p.N;
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.NP) + ((uint32_t)(q * 32) << 16);
       if (kLean == 3) {
-        float* xbuf = reinterpret_cast<float*>(bars + 1) + (it & 1) * 2048;
-        float* cbuf = cbuf_base + (it & 1) * (8 * 256);
+        // multi-tile fused next-GroupNorm epilogue (32x32 images: statistics through global memory, cooperative launch)
         const int cl = q * 32 + lane;
-        const uint32_t cph = (uint32_t)(it >> 1) & 1u;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (row && ss) conv_epilogue_gnfuse<true, true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase, cbuf, &clbars->full[it & 1], cph);
-        else if (row) conv_epilogue_gnfuse<true, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase, cbuf, &clbars->full[it & 1], cph);
-        else if (ss) conv_epilogue_gnfuse<false, true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase, cbuf, &clbars->full[it & 1], cph);
-        else conv_epilogue_gnfuse<false, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase, cbuf, &clbars->full[it & 1], cph);
+        if (row && ss) conv_epilogue_gnfuse<true, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        else if (row) conv_epilogue_gnfuse<true, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        else if (ss) conv_epilogue_gnfuse<false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        else conv_epilogue_gnfuse<false, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
       } else if (kLean == 2) {
         // fused next-GroupNorm epilogue (experimental): exchange buffers [2 tile parities][2][4][128][2] floats = 16 KB
         // behind the barriers; all channels are valid (N % 128 == 0 is required by the host side)
@@ -240,10 +225,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (kLean == 3) {   // no CTA leaves while a peer's statistics may still be in flight to its shared memory
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -324,7 +305,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   // DDIM-50 1035 -> 1030 images/s, so every layer uses the same tile rule.)
   const int np_max = env_np ? atoi(env_np) : 256;
   // fused next-GroupNorm epilogue: a tile must hold whole images (so at least Ho*Wo pixels) and be full (bn | B); images of
-  // 512 / 1024 pixels take 256-pixel tiles shared by a cluster of 2 / 4 CTAs (statistics exchanged through DSMEM)
+  // 512 / 1024 pixels take 256-pixel tiles processed by 2 / 4 co-scheduled CTAs (statistics exchanged through global memory)
   const int gn_cl = (tl_gn_fuse && (d->Ho * d->Wo == 512 || d->Ho * d->Wo == 1024)) ? d->Ho * d->Wo / 256 : 0;
   const int np_min = gn_cl ? 256 : (tl_gn_fuse && d->Ho * d->Wo > 64) ? d->Ho * d->Wo : 64;
   for (int np = np_max; np >= np_min; np >>= 1) {
@@ -423,8 +404,7 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     return conv2d_fwd_pair(d, p, stream);
 
   const int stage_bytes = p.vtap ? 3 * kWBytes + (p.bh + 2) * p.bw * 128 : kWBytes + p.NP * 128;
-  // statistics exchange buffers of the fused epilogue (+ the cluster variant's [2][8][128][2] floats and two barriers)
-  const int fuse_smem = tl_gn_fuse ? 2 * 2048 * (int)sizeof(float) + (gn_cl ? 2 * 8 * 256 * (int)sizeof(float) + 64 : 0) : 0;
+  const int fuse_smem = (tl_gn_fuse && !gn_cl) ? 2 * 2048 * (int)sizeof(float) : 0;   // statistics exchange buffers of the fused epilogue
   int stages = (227 * 1024 - 2048 - fuse_smem) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   static const char* env_stages = getenv("B200_STAGES");
@@ -470,34 +450,33 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     p.gn_ss_ld = g->ss_ld; p.gn_lg_cpg = ilog2(cpg); p.gn_silu = g->apply_silu; p.gn_eps = g->eps;
     p.gn_cl = gn_cl;
     if (gn_cl) {
-      // cluster launch: the gn_cl CTAs of a cluster take the gn_cl tiles of one image in every iteration (tile = blockIdx.x
-      // + i * gridDim.x with both multiples of gn_cl); as many clusters as can be resident at once
-      static int max_clusters[9] = {0};
+      // the gn_cl tiles of an image are taken in the same iteration by gn_cl consecutive CTAs (tile = blockIdx.x + i *
+      // gridDim.x, both multiples of gn_cl) which wait for each other: cooperative launch = all CTAs co-resident
+      B200_REQUIRE(g->xstats != nullptr && g->xcount != nullptr, "conv2d_gn_fwd: %dx%d images need the xstats / xcount workspaces", d->Ho, d->Wo);
+      B200_REQUIRE(((uintptr_t)g->xstats & 15) == 0 && ((uintptr_t)g->xcount & 7) == 0, "conv2d_gn_fwd: workspace alignment");
+      p.gn_xstats = g->xstats;
+      p.gn_xcount = reinterpret_cast<unsigned long long*>(g->xcount);
+      static int max_ctas = 0;
+      if (max_ctas == 0) {
+        B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int per_sm = 0;
+        B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_gemm_kernel<kThreads, 3>, 64 + 128 * 2, 227 * 1024));
+        B200_REQUIRE(per_sm >= 1, "conv2d_gn_fwd: the fused kernel does not fit on an SM");
+        max_ctas = g_num_sms;          // one CTA per SM (TMEM: the kernel allocates all 512 columns)
+      }
+      int ctas = max_ctas / gn_cl * gn_cl;
+      if (ctas > p.total_tiles) ctas = p.total_tiles;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)ctas);
       cfg.blockDim = dim3(64 + 128 * 2);
       cfg.dynamicSmemBytes = smem_bytes;
       cfg.stream = stream;
-      cudaLaunchAttribute attr[2];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = (unsigned)gn_cl;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = 2;
-      if (max_clusters[gn_cl] == 0) {
-        B200_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<kThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        cfg.gridDim = dim3((unsigned)(g_num_sms / gn_cl * gn_cl));
-        int nc = 0;
-        B200_CHECK(cudaOccupancyMaxActiveClusters(&nc, conv_gemm_kernel<kThreads, 3>, &cfg));
-        B200_REQUIRE(nc >= 1, "conv2d_gn_fwd: no %d-CTA cluster of the fused kernel fits on this device", gn_cl);
-        max_clusters[gn_cl] = nc;
-      }
-      int clusters = p.total_tiles / gn_cl;
-      if (clusters > max_clusters[gn_cl]) clusters = max_clusters[gn_cl];
-      cfg.gridDim = dim3((unsigned)(clusters * gn_cl));
+      cfg.numAttrs = 1;
       B200_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<kThreads, 3>, mapA0, mapA1, mapW, p));
       ++g_launch_count;
       return 0;

@@ -609,14 +609,17 @@ class Engine:
         The caller checked K.conv2d_gn_ok for this layer; a rejected launch raises (no per-layer fallback)."""
         w, b = self.w_conv(tag + '.c1', conv1)
         a2 = self.buf(tag + '.2.gn', (B, Ho, Wo, Cout), torch.bfloat16, temp=True)
+        ws = {}
+        if K.conv2d_gn_needs_workspace(Ho, Wo):     # several tiles per image: statistics / arrival counters, zeroed per forward
+            ws = dict(xstats=self.stats_buf(tag + '.c1', B, Cout), xcount=self.stats_buf(tag + '.c1.cnt', B, 1))
         if scale_shift:
             K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
                         beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
-                        scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:], ss_ld=emb_ld)
+                        scale=emb[:, emb_off:], shift=emb[:, emb_off + Cout:], ss_ld=emb_ld, **ws)
         else:
             K.conv2d_gn(a1, w, Cout, B, Ho, Wo, K.taps_3x3_s1(), a0_geom=(Cin, Ho, Wo, 1), gamma=norm2.weight,
                         beta=norm2.bias, groups=norm2.num_groups, eps=norm2.eps, out_norm=a2, bias=b,
-                        rowadd=emb[:, emb_off:], rowadd_ld=emb_ld)
+                        rowadd=emb[:, emb_off:], rowadd_ld=emb_ld, **ws)
         return a2
 
     def resblock_core(self, *args, **kwargs):

@@ -87,8 +87,9 @@ int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
  * NHWC operand of the next convolution: out_norm = SiLU(GN(conv(x) + bias + rowadd)).  Possible when one 256-pixel
  * tile holds whole images (Ho*Wo in {16, 64, 256}) and its 128 channels whole groups, so the statistics are complete
  * inside a CTA (tiles are chosen so that they hold whole images and are full: B must be a multiple of 64 / (Ho*Wo) for
- * 4x4 images).  d->out / d->stats / d->residual must be NULL-equivalent (ignored); N % 128 == 0; N / groups a power of
- * two <= 32.  The engine uses it for every eligible ResBlock at inference (B200_FUSE_GN2=0 restores two launches). */
+ * 4x4 images), or when an image is 2 / 4 tiles and N == 128 (the tiles' CTAs are launched cooperatively and exchange
+ * their sums through g->xstats / g->xcount).  d->out / d->stats / d->residual must be NULL-equivalent (ignored);
+ * N % 128 == 0; N / groups a power of two <= 32.  The engine uses it for every eligible ResBlock at inference (B200_FUSE_GN2=0 restores two launches). */
 typedef struct b200_gn_fuse_desc {
   const float* gamma;        /* [N] */
   const float* beta;         /* [N] */
@@ -99,6 +100,11 @@ typedef struct b200_gn_fuse_desc {
   int groups;
   int apply_silu;
   float eps;
+  /* images of 512 / 1024 pixels (2 / 4 tiles per image; N == 128): zeroed workspaces through which the co-scheduled
+   * CTAs of an image share their statistics -- xstats int64 [B][N][2] (afterwards it holds the statistics of the conv
+   * output, like b200_conv_desc.stats), xcount int64 [B] arrival counters.  NULL for images of <= 256 pixels. */
+  long long* xstats;
+  long long* xcount;
 } b200_gn_fuse_desc;
 int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void* stream);
 

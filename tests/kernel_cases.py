@@ -1209,12 +1209,12 @@ def case_conv_gnfuse():
     for (B, Cin, Cout, H, rowadd, ss, silu) in ((160, 256, 256, 16, True, False, True), (160, 256, 256, 8, True, False, True),
                                                  (320, 256, 256, 4, True, False, True), (160, 128, 256, 8, False, True, True),
                                                  (128, 256, 128, 16, False, False, False),
-                                                 # 32x32 images: 4 tiles per image, statistics exchanged inside a 4-CTA cluster
+                                                 # 32x32 images: 4 tiles per image, statistics shared by 4 co-scheduled CTAs
                                                  (150, 128, 128, 32, True, False, True), (37, 384, 128, 32, True, True, True),
                                                  (3, 128, 128, 32, False, False, True)):
         x = _bf16r(_gen(B, Cin, H, H, seed=1))
         if H == 32:   # statistics that differ between the four tiles of an image
-            x = x * torch.linspace(0.5, 2.0, H, device=DEV)[None, None, :, None]
+            x = _bf16r(x * torch.linspace(0.5, 2.0, H, device=DEV)[None, None, :, None])
         w = _bf16r(_gen(Cout, Cin, 3, 3, seed=2, scale=1.0 / math.sqrt(Cin * 9)))
         b = _gen(Cout, seed=3)
         ra = _gen(B, Cout + 64, seed=4) if rowadd else None
@@ -1229,10 +1229,15 @@ def case_conv_gnfuse():
         if silu:
             ref = F.silu(ref)
         out = torch.full((B, H, H, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+        ws = dict(xstats=K.new_stats(B, Cout, DEV), xcount=K.new_stats(B, 1, DEV)) if K.conv2d_gn_needs_workspace(H, H) else {}
         K.conv2d_gn(_nhwc_bf16(x), K.pack_weight(w), Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(Cin, H, H, 1), gamma=gamma,
                     beta=beta, groups=32, eps=1e-5, out_norm=out, bias=b, rowadd=ra, rowadd_ld=(Cout + 64) if rowadd else 0,
-                    scale=sst, shift=None if sst is None else sst[:, Cout:], ss_ld=2 * Cout, silu=silu)
+                    scale=sst, shift=None if sst is None else sst[:, Cout:], ss_ld=2 * Cout, silu=silu, **ws)
         torch.cuda.synchronize()
+        if ws:   # the workspace ends up holding the statistics of the (unnormalised) conv output
+            pre = F.conv2d(x, w, b, padding=1) + (ra[:, :Cout, None, None] if rowadd else 0.0)
+            want_st = torch.stack([pre.sum(dim=(2, 3)), (pre * pre).sum(dim=(2, 3))], dim=-1)
+            ok &= _report(f'conv3x3 {Cin}->{Cout} @{H} B={B} fused GN: image statistics workspace', K.stats_to_float(ws['xstats']), want_st, 1e-3, 5e-2)
         ok &= _report(f'conv3x3 {Cin}->{Cout} @{H} B={B} + fused GN (rowadd={rowadd}, adagn={ss}, silu={silu})',
                       out.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
     return ok

@@ -179,6 +179,12 @@ def lib():
     L.b200_upsample2_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.b200_attention_fwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p]
+    L.b200_attention_fwd_lse.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_int, c_float, c_void_p, c_void_p]
+    L.b200_attention_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_float, c_void_p]
+    L.b200_attention_fwd_lse.restype = c_int
+    L.b200_attention_bwd.restype = c_int
     L.b200_time_embed.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.b200_sampler_step.argtypes = [POINTER(SamplerDesc), c_void_p]
@@ -236,6 +242,7 @@ EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + PRECISE_SYMBOLS + (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_attn_block_fwd', 'b200_conv3x3_first',
     'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
+    'b200_attention_fwd_lse', 'b200_attention_bwd',
 )
 
 
@@ -464,7 +471,7 @@ def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
     """Static eligibility of a layer for the fused conv + next-GroupNorm entry (mirrors the checks of
     b200_conv2d_gn_fwd, so the engine decides per layer up front instead of catching a rejected launch)."""
     hw = Ho * Wo
-    if N % 128 != 0 or groups < 1 or N % groups != 0:
+    if N % 128 != 0 or groups < 1 or N % groups != 0 or (_GN_FUSE_HW is not None and hw not in _GN_FUSE_HW):
         return False
     cpg = N // groups
     if cpg > 32 or cpg & (cpg - 1):
@@ -476,6 +483,8 @@ def conv2d_gn_ok(B, Ho, Wo, N, groups) -> bool:
     return hw >= 64 or B % (64 // hw) == 0      # the smallest tile is 64 pixels = 4 whole 4x4 images
 
 
+_GN_FUSE_HW = ({int(v) for v in os.environ['B200_FUSE_GN2_HW'].split(',') if v} if 'B200_FUSE_GN2_HW' in os.environ
+               else None)   # experiment knob: image sizes (pixels) allowed to take the fused entry, e.g. "16,256,1024"
 _GN_CLUSTER = os.environ.get('B200_FUSE_GN2_CLUSTER', '1') != '0'   # =0: 32x32 layers keep conv + GroupNorm launches (A/B)
 
 
@@ -627,13 +636,42 @@ def upsample2_f32(x, out, B, H, W, C):
     return out
 
 
-def attention(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale):
+def attention(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale, lse=None):
+    """lse: optional fp32 [B, heads, T] output (log2-sum-exp of the scaled score rows) for `attention_bwd`."""
     _need_cuda(qk, vt, out)
+    if lse is not None:
+        _need_cuda(lse)
+        if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != B * heads * T:
+            raise RuntimeError('attention: lse must be a contiguous float32 tensor of B*heads*T elements')
     _launch('attention',
-            lambda: _check(lib().b200_attention_fwd(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(),
-                                                    ld_out, B, T, heads, d, float(scale), _stream()), 'attention_fwd'),
+            lambda: _check(lib().b200_attention_fwd_lse(qk.data_ptr(), ld_qk, q_off, k_off, vt.data_ptr(), out.data_ptr(),
+                                                        ld_out, B, T, heads, d, float(scale), _ptr(lse), _stream()),
+                           'attention_fwd'),
             flops=4.0 * B * heads * T * T * d)
     return out
+
+
+def attention_bwd_ok(T, d) -> bool:
+    """Static eligibility for the one-launch attention adjoint (mirrors b200_attention_bwd's checks)."""
+    return d == 64 and 8 <= T <= 256 and T % 8 == 0
+
+
+def attention_bwd(qk, vt, o, d_o, lse, dqk, dv, B, T, heads, d, scale):
+    """[dQ | dK] -> dqk bf16 [B, T, 2C], dV -> dv bf16 [B, T, C] from q|k [B, T, 2C], v^T [B, C, T], o, dO [B, T, C]."""
+    _need_cuda(qk, vt, o, d_o, lse, dqk, dv)
+    C = heads * d
+    for name, t, n in (('qk', qk, 2 * B * T * C), ('vt', vt, B * T * C), ('o', o, B * T * C), ('d_o', d_o, B * T * C),
+                       ('dqk', dqk, 2 * B * T * C), ('dv', dv, B * T * C)):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != n:
+            raise RuntimeError(f'attention_bwd: {name} must be a contiguous bfloat16 tensor of {n} elements')
+    if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != B * heads * T:
+        raise RuntimeError('attention_bwd: lse must be a contiguous float32 tensor of B*heads*T elements')
+    _launch('attention_bwd',
+            lambda: _check(lib().b200_attention_bwd(qk.data_ptr(), vt.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                                    dqk.data_ptr(), dv.data_ptr(), B, T, heads, d, float(scale), _stream()),
+                           'attention_bwd'),
+            flops=10.0 * B * heads * T * T * d)
+    return dqk, dv
 
 
 def attn_block_ok(T, C, heads, groups) -> bool:

@@ -23,6 +23,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   int ld_out;
   uint32_t tmem_cols;
+  float* lse;      // optional [B][heads][T]: log2-sum-exp of the scaled score rows (for the fused backward), or NULL
 };
 
 struct __align__(8) AttnBars {
@@ -158,6 +159,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #pragma unroll
     for (int i = 0; i < NS; ++i) sum += red_sum[i * 128 + r];
   }
+  // softmax_ij = exp2(s_ij * scale * log2e - lse_i): what the fused backward (attn_bwd.cu) recomputes P from
+  if (p.lse != nullptr && part == 0 && q0 + r < p.T)
+    p.lse[((size_t)b * gridDim.y + h) * p.T + q0 + r] = ms + log2f(sum);
 
   // ---- 4. O = P V ----
   if (threadIdx.x == 0) {
@@ -219,12 +223,19 @@ using namespace b200;
 
 extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
                                   int B, int T, int heads, int d, float scale, void* stream_) {
+  return b200_attention_fwd_lse(qk, ld_qk, q_off, k_off, vt, out, ld_out, B, T, heads, d, scale, nullptr, stream_);
+}
+
+extern "C" int b200_attention_fwd_lse(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
+                                      int B, int T, int heads, int d, float scale, float* lse, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(lse == nullptr || (T <= 256 && (d == 64 || d == 128 || d == 256)),
+               "attention_fwd_lse: the log-sum-exp output is available for T <= 256 and head dim 64 / 128 / 256");
   B200_REQUIRE(qk && vt && out, "attention_fwd: null pointer");
   B200_REQUIRE(d >= 64 && d <= 512 && d % 64 == 0, "attention_fwd: head dim %d must be a multiple of 64 in [64,512]", d);
   B200_REQUIRE(T >= 8 && T % 8 == 0, "attention_fwd: T=%d must be a positive multiple of 8", T);
   static const char* env_wide = getenv("B200_ATTN_WIDE");   // experiment: chunk-streaming kernel for single-head d = 256
-  const bool force_wide = env_wide && atoi(env_wide) == 1 && heads == 1 && d == 256;
+  const bool force_wide = env_wide && atoi(env_wide) == 1 && heads == 1 && d == 256 && lse == nullptr;
   if (T <= 256 && (force_wide || !(d == 64 || d == 128 || d == 256))) {
     B200_REQUIRE(ld_qk % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0, "attention_fwd: ld/offsets must be multiples of 8");
     B200_REQUIRE(((uintptr_t)qk & 127) == 0 && ((uintptr_t)vt & 127) == 0 && ((uintptr_t)out & 15) == 0, "attention_fwd: alignment");
@@ -243,6 +254,7 @@ extern "C" int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_of
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ld_out = ld_out;
+  p.lse = lse;
   uint32_t cols = 32;
   while (cols < (uint32_t)(Tp + d)) cols <<= 1;
   p.tmem_cols = cols;

@@ -229,7 +229,19 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
-// kind::f16, A/B = bf16, accumulate fp32, both operands K-major, M = 128.
+// MN-major operand tile, 128-byte swizzle: 64-element (128 B) chunks of the M/N dimension, each chunk a
+// [64 k-rows][128 B] slab; slabs `lbo` bytes apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16, A/B = bf16, accumulate fp32, both operands K-major, M = 128 (bit 15 / 16 = A / B MN-major).
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
   uint32_t d = 0;
   d |= 1u << 4;          // c_format = F32

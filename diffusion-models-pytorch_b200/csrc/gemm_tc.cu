@@ -48,18 +48,6 @@ struct __align__(8) GemmBars {
   uint32_t tmem_base;
 };
 
-// MN-major operand tile, 128-byte swizzle: 64-element (128 B) chunks of the M/N dimension, each chunk a
-// [64 k-rows][128 B] slab; slabs `lbo` bytes apart, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ GemmKParams p) {

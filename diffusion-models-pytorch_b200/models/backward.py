@@ -341,30 +341,12 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
              out_mode=K.OUT_BF16_NHWC)
 
     # attention core: recompute P, then dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q
-    G_ = B * heads
-    S = eng.buf('attn_ws.S', (G_, T, T), torch.float32)
-    P = eng.buf('attn_ws.P', (G_, T, T), bf)
-    dP = eng.buf('attn_ws.dP', (G_, T, T), torch.float32)
-    dS = eng.buf('attn_ws.dS', (G_, T, T), bf)
-    qop = (qk, T, 2 * C, dict(col_base=0, col_head=d))
-    kop = (qk, T, 2 * C, dict(col_base=C, col_head=d))
-    grid = dict(batch=B, heads=heads)
-    sq = dict(out_ld=T, out_batch_stride=heads * T * T, out_head_stride=T * T)
-    K.gemm_batched(qop, kop, S, T, T, d, **grid, **sq)
-    K.softmax_rows(S, P, G_ * T, T, scale)
-    vop = (vt, d, T, dict(per_head_batch=True, mn_major=True))                 # [B*h][d][T]: rows = channel (K), cols = key
-    K.gemm_batched((do, T, C, dict(col_head=d)), vop, dP, T, T, d, **grid, **sq)
-    K.softmax_bwd_rows(P, dP, dS, G_ * T, T, scale)
     dqk = eng.buf(tag + '.dqk', (B, T, 2 * C), bf)
     dv = eng.buf(tag + '.dv', (B, T, C), bf)
-    dsop = (dS, T, T, dict(per_head_batch=True))
-    K.gemm_batched(dsop, (qk, T, 2 * C, dict(col_base=C, col_head=d, mn_major=True)), dqk, T, d, T, **grid,
-                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
-    dsop_t = (dS, T, T, dict(per_head_batch=True, mn_major=True))
-    K.gemm_batched(dsop_t, (qk, T, 2 * C, dict(col_base=0, col_head=d, mn_major=True)), dqk[:, :, C:], T, d, T, **grid,
-                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
-    K.gemm_batched((P, T, T, dict(per_head_batch=True, mn_major=True)), (do, T, C, dict(col_head=d, mn_major=True)), dv,
-                   T, d, T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
+    if e.get('lse') is not None:
+        K.attention_bwd(qk, vt, o, do, e['lse'], dqk, dv, B, T, heads, d, scale)      # one launch, scores stay on chip
+    else:
+        _attn_core_bwd_gemms(eng, qk, vt, do, dqk, dv, B, T, C, heads, d, scale)
 
     # q, k, v 1x1 convs: biases, weights, data (one GEMM over the concatenated [dq | dk | dv] channels).
     # `targets` maps row ranges of dq / dk / dv to rows of the parameters' gradients: one range each for separate
@@ -383,6 +365,34 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     K.groupnorm_bwd(dn, x.t, C, x.stats, None, 0, None, B, T, W, norm.num_groups, norm.weight, norm.bias, norm.eps,
                     _sums(eng, B, C), silu=False, dx0=gx, dx0_acc=acc, addend=out.g, dgamma=G(norm.weight),
                     dbeta=G(norm.bias))
+
+
+def _attn_core_bwd_gemms(eng: Engine, qk, vt, do, dqk, dv, B, T, C, heads, d, scale):
+    """Attention-core adjoint for shapes b200_attention_bwd does not cover (head dim != 64 or T > 256): five batched
+    tensor-core GEMMs around the row-softmax kernels, [B*h, T, T] workspaces in HBM."""
+    bf = torch.bfloat16
+    G_ = B * heads
+    S = eng.buf('attn_ws.S', (G_, T, T), torch.float32)
+    P = eng.buf('attn_ws.P', (G_, T, T), bf)
+    dP = eng.buf('attn_ws.dP', (G_, T, T), torch.float32)
+    dS = eng.buf('attn_ws.dS', (G_, T, T), bf)
+    qop = (qk, T, 2 * C, dict(col_base=0, col_head=d))
+    kop = (qk, T, 2 * C, dict(col_base=C, col_head=d))
+    grid = dict(batch=B, heads=heads)
+    sq = dict(out_ld=T, out_batch_stride=heads * T * T, out_head_stride=T * T)
+    K.gemm_batched(qop, kop, S, T, T, d, **grid, **sq)
+    K.softmax_rows(S, P, G_ * T, T, scale)
+    vop = (vt, d, T, dict(per_head_batch=True, mn_major=True))                 # [B*h][d][T]: rows = channel (K), cols = key
+    K.gemm_batched((do, T, C, dict(col_head=d)), vop, dP, T, T, d, **grid, **sq)
+    K.softmax_bwd_rows(P, dP, dS, G_ * T, T, scale)
+    dsop = (dS, T, T, dict(per_head_batch=True))
+    K.gemm_batched(dsop, (qk, T, 2 * C, dict(col_base=C, col_head=d, mn_major=True)), dqk, T, d, T, **grid,
+                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+    dsop_t = (dS, T, T, dict(per_head_batch=True, mn_major=True))
+    K.gemm_batched(dsop_t, (qk, T, 2 * C, dict(col_base=0, col_head=d, mn_major=True)), dqk[:, :, C:], T, d, T, **grid,
+                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+    K.gemm_batched((P, T, T, dict(per_head_batch=True, mn_major=True)), (do, T, C, dict(col_head=d, mn_major=True)), dv,
+                   T, d, T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
 
 
 def _attn_targets(eng: Engine, e, G: _Grads, C: int):

@@ -44,6 +44,7 @@ class Engine:
     # launch for the CIFAR-10 UNet's 16x16 blocks (T = 256, C = 256, one head; inference only): q, k, v and the attention
     # output never touch HBM.  B200_ATTN_BLOCK=0: the five-launch form (A/B).
     attn_block = bool(int(__import__('os').environ.get('B200_ATTN_BLOCK', '1')))
+    attn_bwd_fused = bool(int(__import__('os').environ.get('B200_ATTN_BWD_FUSED', '1')))   # =0: batched-GEMM adjoint (A/B)
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -528,7 +529,10 @@ class Engine:
         vt = self.buf(tag + '.vt', (B, C, T), torch.bfloat16, temp=True)
         K.conv2d(n, wv, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bv, out=vt, out_mode=K.OUT_BF16_NCHW)
         o = self.buf(tag + '.o', (B, T, C), torch.bfloat16, temp=True)
-        K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale)
+        # training: keep the per-row log-sum-exp so that the one-launch adjoint (b200_attention_bwd) can recompute P
+        lse = (self.buf(tag + '.lse', (B, heads, T), torch.float32, temp=True)
+               if self.tape is not None and self.attn_bwd_fused and K.attention_bwd_ok(T, d) else None)
+        K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale, lse=lse)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
         stats = self.stats_buf(tag, B, C)
         K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
@@ -537,8 +541,8 @@ class Engine:
         if self.tape is not None:
             if mods is None:
                 raise RuntimeError(f'{tag}: this attention block did not register its parameters for the backward pass')
-            self.tape.append(dict(kind='attn', tag=tag, x=x, out=res, norm=norm, n=n, qk=qk, vt=vt, o=o, heads=heads,
-                                  scale=scale, mods=mods))
+            self.tape.append(dict(kind='attn', tag=tag, x=x, out=res, norm=norm, n=n, qk=qk, vt=vt, o=o, lse=lse,
+                                  heads=heads, scale=scale, mods=mods))
         return res
 
     def downsample_conv(self, *args, **kwargs):

@@ -156,6 +156,20 @@ int b200_upsample2_f32(const float* x, float* out, int B, int H, int W, int C, v
 int b200_attention_fwd(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
                        int B, int T, int heads, int d, float scale, void* stream);
 
+/* Training form of K2: additionally writes lse fp32 [B][heads][T] = log2(sum_j exp2(s_ij * scale * log2e)) per score
+ * row (T <= 256, d in {64,128,256}); b200_attention_bwd recomputes softmax rows from it instead of storing them. */
+int b200_attention_fwd_lse(const void* qk, int ld_qk, int q_off, int k_off, const void* vt, void* out, int ld_out,
+                           int B, int T, int heads, int d, float scale, float* lse, void* stream);
+
+/* Adjoint of K2 in ONE launch (autograd of models/modules.py:92-97: bmm, softmax, bmm), head dim 64, T <= 256:
+ *     P = softmax(scale q k^T) (recomputed), dV = P^T dO, dP = dO V^T, dS = scale * P o (dP - rowsum(dO o O)),
+ *     dQ = dS K, dK = dS^T Q.
+ * qk / vt as in b200_attention_fwd with ld_qk = 2C, q_off = 0, k_off = C (C = heads*64); o, d_o: bf16 [B][T][C];
+ * lse from b200_attention_fwd_lse; dqk: bf16 [B][T][2C] = [dQ | dK]; dv: bf16 [B][T][C].  One CTA per (image, head);
+ * the [T][T] score tensors never leave the SM (the batched-GEMM form moved four of them through HBM). */
+int b200_attention_bwd(const void* qk, const void* vt, const void* o, const void* d_o, const float* lse, void* dqk,
+                       void* dv, int B, int T, int heads, int d, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2b: the WHOLE self-attention block (models/modules.py:77-102, SelfAttentionBlock.forward) in one launch:
  *     out = x + proj(softmax(q k^T * scale) v),  q, k, v = 1x1 convs of GroupNorm(x)      (no SiLU in this norm)

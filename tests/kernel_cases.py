@@ -502,6 +502,55 @@ def case_attention():
     return ok
 
 
+def _attn_bwd_case(name, B, T, heads):
+    """b200_attention_fwd_lse + b200_attention_bwd against fp32 autograd of softmax(q k^T * scale) v on the same
+    bf16-rounded q, k, v and output gradient."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    d = 64
+    C = heads * d
+    q = _bf16r(_gen(B, T, C, seed=11)).requires_grad_(True)
+    k = _bf16r(_gen(B, T, C, seed=12)).requires_grad_(True)
+    v = _bf16r(_gen(B, T, C, seed=13)).requires_grad_(True)
+    g = _bf16r(_gen(B, T, C, seed=14))
+    scale = d ** -0.5
+    qh = q.view(B, T, heads, d).transpose(1, 2)
+    kh = k.view(B, T, heads, d).transpose(1, 2)
+    vh = v.view(B, T, heads, d).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    att = torch.softmax(s, dim=-1)
+    ref = (att @ vh).transpose(1, 2).reshape(B, T, C)
+    ref.backward(g)
+    lse_ref = torch.logsumexp(s, dim=-1) * 1.4426950408889634            # [B, heads, T], base 2
+    bf = torch.bfloat16
+    qk = torch.cat([q, k], dim=-1).detach().to(bf).contiguous()
+    vt = v.detach().transpose(1, 2).contiguous().to(bf)
+    o = torch.full((B, T, C), float('nan'), device=DEV, dtype=bf)
+    lse = torch.full((B, heads, T), float('nan'), device=DEV, dtype=torch.float32)
+    K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale, lse=lse)
+    dqk = torch.full((B, T, 2 * C), float('nan'), device=DEV, dtype=bf)
+    dv = torch.full((B, T, C), float('nan'), device=DEV, dtype=bf)
+    K.attention_bwd(qk, vt, o, g.to(bf).contiguous(), lse, dqk, dv, B, T, heads, d, scale)
+    torch.cuda.synchronize()
+    ok = _report(name + ' lse', lse, lse_ref, rtol=1e-4, atol=1e-3)
+    ok &= _report(name + ' out', o, ref.detach(), rtol=2e-2, atol=1e-2)
+    # P, dS and the results are rounded to bf16 (2^-8 relative each); gate on the tensor-level error as well
+    for nm, got, want in (('dq', dqk[:, :, :C], q.grad), ('dk', dqk[:, :, C:], k.grad), ('dv', dv, v.grad)):
+        rel = ((got.float() - want).norm() / want.norm()).item()
+        print(f'    {name} {nm}: rel-L2 {rel:.3e}')
+        ok &= rel < 1e-2
+        ok &= _report(f'{name} {nm}', got, want, rtol=3e-2, atol=3e-2 * want.abs().max().item())
+    return ok
+
+
+def case_attention_bwd():
+    ok = _attn_bwd_case('attention_bwd T=256 h=4 (CFG UNet 16x16)', 3, 256, 4)
+    ok &= _attn_bwd_case('attention_bwd T=64 h=4 (8x8)', 2, 64, 4)
+    ok &= _attn_bwd_case('attention_bwd T=16 h=4 (4x4 bottleneck)', 5, 16, 4)
+    ok &= _attn_bwd_case('attention_bwd T=144 h=2 (ragged second tile)', 2, 144, 2)
+    ok &= _attn_bwd_case('attention_bwd T=256 h=1', 130, 256, 1)
+    return ok
+
+
 def _attn_block_case(name, B, debug):
     """b200_attn_block_fwd (T=256, C=256, one head) against the fp32 op sequence of models/modules.py:89-102; with
     `debug` every on-chip intermediate (xn, q, k, v^T, P, o) is dumped and checked too, which localises a failure."""

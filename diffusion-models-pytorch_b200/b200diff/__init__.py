@@ -181,8 +181,8 @@ def lib():
                                      c_int, c_float, c_void_p]
     L.b200_attention_fwd_lse.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_int, c_float, c_void_p, c_void_p]
-    L.b200_attention_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                     c_int, c_int, c_float, c_void_p]
+    L.b200_attention_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_float, c_void_p]
     L.b200_attention_fwd_lse.restype = c_int
     L.b200_attention_bwd.restype = c_int
     L.b200_time_embed.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -657,18 +657,23 @@ def attention_bwd_ok(T, d) -> bool:
 
 
 def attention_bwd(qk, vt, o, d_o, lse, dqk, dv, B, T, heads, d, scale):
-    """[dQ | dK] -> dqk bf16 [B, T, 2C], dV -> dv bf16 [B, T, C] from q|k [B, T, 2C], v^T [B, C, T], o, dO [B, T, C]."""
+    """[dQ | dK] -> the first 2C columns of dqk (bf16 [B, T, ld]), dV -> dv (bf16 [B, T, ld']) from q|k [B, T, 2C],
+    v^T [B, C, T], o, dO [B, T, C].  dqk / dv may be column windows of one [B, T, 3C] tensor."""
     _need_cuda(qk, vt, o, d_o, lse, dqk, dv)
     C = heads * d
-    for name, t, n in (('qk', qk, 2 * B * T * C), ('vt', vt, B * T * C), ('o', o, B * T * C), ('d_o', d_o, B * T * C),
-                       ('dqk', dqk, 2 * B * T * C), ('dv', dv, B * T * C)):
+    for name, t, n in (('qk', qk, 2 * B * T * C), ('vt', vt, B * T * C), ('o', o, B * T * C), ('d_o', d_o, B * T * C)):
         if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != n:
             raise RuntimeError(f'attention_bwd: {name} must be a contiguous bfloat16 tensor of {n} elements')
+    for name, t, n in (('dqk', dqk, 2 * C), ('dv', dv, C)):
+        if (t.dtype != torch.bfloat16 or t.dim() != 3 or tuple(t.shape) != (B, T, n) or t.stride(2) != 1
+                or t.stride(0) != T * t.stride(1)):
+            raise RuntimeError(f'attention_bwd: {name} must be a bfloat16 [B, T, {n}] tensor or column window')
     if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != B * heads * T:
         raise RuntimeError('attention_bwd: lse must be a contiguous float32 tensor of B*heads*T elements')
     _launch('attention_bwd',
             lambda: _check(lib().b200_attention_bwd(qk.data_ptr(), vt.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
-                                                    dqk.data_ptr(), dv.data_ptr(), B, T, heads, d, float(scale), _stream()),
+                                                    dqk.data_ptr(), dqk.stride(1), dv.data_ptr(), dv.stride(1), B, T, heads,
+                                                    d, float(scale), _stream()),
                            'attention_bwd'),
             flops=10.0 * B * heads * T * T * d)
     return dqk, dv

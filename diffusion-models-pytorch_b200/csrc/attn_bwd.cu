@@ -26,12 +26,13 @@ struct AttnBwdParams {
   const __nv_bfloat16* o;        // [B][T][C]
   const __nv_bfloat16* d_o;      // [B][T][C]
   const float* lse;              // [B][heads][T]
-  __nv_bfloat16* dqk;            // [B][T][2C]: dQ at columns h*64, dK at C + h*64
-  __nv_bfloat16* dv;             // [B][T][C]
+  __nv_bfloat16* dqk;            // [B][T][ld_dqk]: dQ at columns h*64, dK at C + h*64
+  __nv_bfloat16* dv;             // [B][T][ld_dv]
+  int ld_dqk, ld_dv;
 };
 
 struct __align__(8) AttnBwdBars {
-  uint64_t load_full, sdp_full, pds_ready, g2_done, dkv_drained;
+  uint64_t load_full, sdp_full, sdp_free, pds_ready, g2_done, dkv_drained;
   uint32_t tmem_base;
 };
 
@@ -62,6 +63,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     tma_prefetch_desc(&mapV);
     mbar_init(&bars->load_full, 1);
     mbar_init(&bars->sdp_full, 1);
+    mbar_init(&bars->sdp_free, kAbwWorkers / 32);
     mbar_init(&bars->pds_ready, kAbwWorkers / 32);
     mbar_init(&bars->g2_done, 1);
     mbar_init(&bars->dkv_drained, kAbwWorkers / 32);
@@ -93,20 +95,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
       const uint32_t i_dq = umma_idesc_bf16_m128(64u) | (1u << 16);                // dQ: A = dS K-major, B = K MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aDO = smem_u32(sDO), aV = smem_u32(sV), aP = smem_u32(sP),
                      aDS = smem_u32(sDS);
+      // S = Q_qt K_kt^T, dP = dO_qt V_kt^T of block (kt, qt) into TMEM columns [0, 256)
+      auto issue_sdp = [&](int kt, int qt) {
+        const uint64_t qd = umma_desc_kmajor_sw128(aQ + (uint32_t)qt * kAbwTile);
+        const uint64_t kd = umma_desc_kmajor_sw128(aK + (uint32_t)kt * kAbwTile);
+        const uint64_t dod = umma_desc_kmajor_sw128(aDO + (uint32_t)qt * kAbwTile);
+        const uint64_t vd = umma_desc_mnmajor_sw128(aV + (uint32_t)kt * 2u * 8192u, 8192u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), i_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128u, dod + (uint64_t)(2 * k), vd + (uint64_t)(128 * k), i_dp, k > 0 ? 1u : 0u);
+        umma_commit(&bars->sdp_full);
+      };
+      issue_sdp(0, 0);
       int it = 0;
       for (int kt = 0; kt < nt; ++kt) {
         for (int qt = 0; qt < nt; ++qt, ++it) {
-          // S = Q_qt K_kt^T, dP = dO_qt V_kt^T  (their TMEM columns were released with pds_ready of the previous block)
-          {
-            const uint64_t qd = umma_desc_kmajor_sw128(aQ + (uint32_t)qt * kAbwTile);
-            const uint64_t kd = umma_desc_kmajor_sw128(aK + (uint32_t)kt * kAbwTile);
-            const uint64_t dod = umma_desc_kmajor_sw128(aDO + (uint32_t)qt * kAbwTile);
-            const uint64_t vd = umma_desc_mnmajor_sw128(aV + (uint32_t)kt * 2u * 8192u, 8192u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), i_s, k > 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128u, dod + (uint64_t)(2 * k), vd + (uint64_t)(128 * k), i_dp, k > 0 ? 1u : 0u);
-            umma_commit(&bars->sdp_full);
+          // the next block's S / dP are issued as soon as the workers hold this block's in registers, so they run
+          // on the tensor pipe while the workers compute P / dS (and the workers' next block overlaps this block's
+          // dV / dK / dQ MMAs)
+          if (it + 1 < nt * nt) {
+            mbar_wait(&bars->sdp_free, (uint32_t)it & 1u);
+            tc_fence_after();
+            const int nqt = qt + 1 < nt ? qt + 1 : 0;
+            issue_sdp(nqt == 0 ? kt + 1 : kt, nqt);
           }
           mbar_wait(&bars->pds_ready, (uint32_t)it & 1u);
           if (qt == 0 && kt > 0) mbar_wait(&bars->dkv_drained, (uint32_t)(kt - 1) & 1u);
@@ -173,6 +185,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
           tmem_ld_x32(tmem + lane_base + (uint32_t)(half * 64 + c * 32), sv);
           tmem_ld_x32(tmem + 128u + lane_base + (uint32_t)(half * 64 + c * 32), dv);
           tmem_ld_wait();
+          if (c == 1) {          // S / dP of this block are in registers: their TMEM columns may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->sdp_free);
+          }
           const int key0 = kt * 128 + half * 64 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -214,7 +231,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
           tmem_ld_x32(tmem + 256u + lane_base + (uint32_t)(half * 32), v);
           tmem_ld_wait();
           if (key < p.T) {
-            uint4* o = reinterpret_cast<uint4*>(p.dqk + ((size_t)b * p.T + key) * (2 * p.C) + p.C + h * 64 + half * 32);
+            uint4* o = reinterpret_cast<uint4*>(p.dqk + ((size_t)b * p.T + key) * p.ld_dqk + p.C + h * 64 + half * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               o[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
@@ -225,7 +242,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
           tmem_ld_x32(tmem + 320u + lane_base + (uint32_t)(half * 32), v);
           tmem_ld_wait();
           if (key < p.T) {
-            uint4* o = reinterpret_cast<uint4*>(p.dv + ((size_t)b * p.T + key) * p.C + h * 64 + half * 32);
+            uint4* o = reinterpret_cast<uint4*>(p.dv + ((size_t)b * p.T + key) * p.ld_dv + h * 64 + half * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               o[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
@@ -246,7 +263,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
       tmem_ld_x32(tmem + 384u + (uint32_t)qt * 64u + lane_base + (uint32_t)(half * 32), v);
       tmem_ld_wait();
       if (q < p.T) {
-        uint4* o = reinterpret_cast<uint4*>(p.dqk + ((size_t)b * p.T + q) * (2 * p.C) + h * 64 + half * 32);
+        uint4* o = reinterpret_cast<uint4*>(p.dqk + ((size_t)b * p.T + q) * p.ld_dqk + h * 64 + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           o[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
@@ -270,7 +287,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
 using namespace b200;
 
 extern "C" int b200_attention_bwd(const void* qk, const void* vt, const void* o, const void* d_o, const float* lse, void* dqk,
-                                  void* dv, int B, int T, int heads, int d, float scale, void* stream_) {
+                                  int ld_dqk, void* dv, int ld_dv, int B, int T, int heads, int d, float scale, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(qk && vt && o && d_o && lse && dqk && dv, "attention_bwd: null pointer");
   B200_REQUIRE(d == 64, "attention_bwd: head dim %d (only 64 is fused; other shapes take the batched-GEMM path)", d);
@@ -287,6 +304,9 @@ extern "C" int b200_attention_bwd(const void* qk, const void* vt, const void* o,
   p.lse = lse;
   p.dqk = reinterpret_cast<__nv_bfloat16*>(dqk);
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  B200_REQUIRE(ld_dqk >= 2 * C && ld_dqk % 8 == 0 && ld_dv >= C && ld_dv % 8 == 0,
+               "attention_bwd: ld_dqk=%d / ld_dv=%d must be multiples of 8 covering 2C / C columns", ld_dqk, ld_dv);
+  p.ld_dqk = ld_dqk; p.ld_dv = ld_dv;
   CUtensorMap mapQK, mapDO, mapV;
   {
     uint64_t dims[3] = {(uint64_t)2 * C, (uint64_t)T, (uint64_t)B};

@@ -90,6 +90,16 @@ def _record_params(e):
     for k, v in e.items():
         if k == 'emb_linear':
             continue
+        if k == 'linears' and e.get('kind') == 'embed':
+            # all projection weights side by side, then all biases: _embed_bwd writes each group with ONE launch
+            out += [l.weight for l in v] + [l.bias for l in v]
+            continue
+        if k == 'mods' and e.get('kind') == 'attn' and isinstance(v, tuple):
+            # separate q, k, v convs: their weights (and biases) side by side, so that _attn_bwd computes the three
+            # weight gradients as ONE GEMM over the [dq | dk | dv] columns and the bias gradients as one column sum
+            q, kk, vv, proj = v
+            out += [q.weight, kk.weight, vv.weight, q.bias, kk.bias, vv.bias] + list(proj.parameters())
+            continue
         vs = v if isinstance(v, (tuple, list)) else (v,)
         for m in vs:
             if isinstance(m, nn.Module):
@@ -341,8 +351,8 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
              out_mode=K.OUT_BF16_NHWC)
 
     # attention core: recompute P, then dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q
-    dqk = eng.buf(tag + '.dqk', (B, T, 2 * C), bf)
-    dv = eng.buf(tag + '.dv', (B, T, C), bf)
+    dqkv = eng.buf(tag + '.dqkv', (B, T, 3 * C), bf)          # [dq | dk | dv] side by side
+    dqk, dv = dqkv[:, :, :2 * C], dqkv[:, :, 2 * C:]
     if e.get('lse') is not None:
         K.attention_bwd(qk, vt, o, do, e['lse'], dqk, dv, B, T, heads, d, scale)      # one launch, scores stay on chip
     else:
@@ -352,14 +362,24 @@ def _attn_bwd(eng: Engine, e, G: _Grads):
     # `targets` maps row ranges of dq / dk / dv to rows of the parameters' gradients: one range each for separate
     # q, k, v convs; one per head for ADM's fused, head-interleaved qkv Conv1d.
     n = e['n']
-    for which, (src, ld, c_off) in (('q', (dqk, 2 * C, 0)), ('k', (dqk, 2 * C, C)), ('v', (dv, C, 0))):
-        for (r0, nrows, wg, bg) in targets[which]:
-            K.colsum_bf16(src, bg, B * T, ld, c_off + r0, nrows)
-            _wgrad(eng, src, ld, n, (C, H, W, 1), B, H, W, nrows, C, t1[0], wg, dy_c0=c_off + r0)
+    mods = e['mods']
+    fused_qkv = False
+    if isinstance(mods, tuple):
+        q, k, v = mods[:3]
+        w0, b0 = G.offset[id(q.weight)], G.offset[id(q.bias)]
+        fused_qkv = (G.offset[id(k.weight)] == w0 + C * C and G.offset[id(v.weight)] == w0 + 2 * C * C and
+                     G.offset[id(k.bias)] == b0 + C and G.offset[id(v.bias)] == b0 + 2 * C)
+    if fused_qkv:    # gradient layout keeps q, k, v weights / biases adjacent (_record_params): one GEMM, one column sum
+        K.colsum_bf16(dqkv, G.flat[b0:b0 + 3 * C], B * T, 3 * C, 0, 3 * C)
+        _wgrad(eng, dqkv, 3 * C, n, (C, H, W, 1), B, H, W, 3 * C, C, t1[0], G.flat[w0:w0 + 3 * C * C].view(3 * C, C, 1, 1))
+    else:
+        for which, c_off in (('q', 0), ('k', C), ('v', 2 * C)):
+            for (r0, nrows, wg, bg) in targets[which]:
+                K.colsum_bf16(dqkv, bg, B * T, 3 * C, c_off + r0, nrows)
+                _wgrad(eng, dqkv, 3 * C, n, (C, H, W, 1), B, H, W, nrows, C, t1[0], wg, dy_c0=c_off + r0)
     wd = targets['wd']()
     dn = eng.buf(tag + '.dN', (B, H, W, C), bf)
-    K.conv2d(dqk, wd, C, B, H, W, t1, a0_geom=(2 * C, H, W, 1), a1=dv, a1_geom=(C, H, W, 1), out=dn,
-             out_mode=K.OUT_BF16_NHWC)
+    K.conv2d(dqkv, wd, C, B, H, W, t1, a0_geom=(3 * C, H, W, 1), out=dn, out_mode=K.OUT_BF16_NHWC)
 
     gx, acc = _grad_slot(eng, x)
     K.groupnorm_bwd(dn, x.t, C, x.stats, None, 0, None, B, T, W, norm.num_groups, norm.weight, norm.bias, norm.eps,
@@ -387,12 +407,12 @@ def _attn_core_bwd_gemms(eng: Engine, qk, vt, do, dqk, dv, B, T, C, heads, d, sc
     K.softmax_bwd_rows(P, dP, dS, G_ * T, T, scale)
     dsop = (dS, T, T, dict(per_head_batch=True))
     K.gemm_batched(dsop, (qk, T, 2 * C, dict(col_base=C, col_head=d, mn_major=True)), dqk, T, d, T, **grid,
-                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+                   out_ld=dqk.stride(1), out_batch_stride=dqk.stride(0), out_head_stride=d)
     dsop_t = (dS, T, T, dict(per_head_batch=True, mn_major=True))
     K.gemm_batched(dsop_t, (qk, T, 2 * C, dict(col_base=0, col_head=d, mn_major=True)), dqk[:, :, C:], T, d, T, **grid,
-                   out_ld=2 * C, out_batch_stride=T * 2 * C, out_head_stride=d)
+                   out_ld=dqk.stride(1), out_batch_stride=dqk.stride(0), out_head_stride=d)
     K.gemm_batched((P, T, T, dict(per_head_batch=True, mn_major=True)), (do, T, C, dict(col_head=d, mn_major=True)), dv,
-                   T, d, T, **grid, out_ld=C, out_batch_stride=T * C, out_head_stride=d)
+                   T, d, T, **grid, out_ld=dv.stride(1), out_batch_stride=dv.stride(0), out_head_stride=d)
 
 
 def _attn_targets(eng: Engine, e, G: _Grads, C: int):
@@ -536,13 +556,23 @@ def _embed_bwd(eng: Engine, e, G: _Grads):
     ws['bias'].zero_()
     K.cast_bf16_colsum(eng.d_emb, ws['dproj'], ws['bias'], rows, total)
     ws['semb'][:rows].copy_(e['semb'])
-    off = 0
-    for lin in e['linears']:
-        n = lin.out_features
-        G(lin.bias).copy_(ws['bias'][off:off + n])
-        K.gemm_batched((ws['dproj'], rp, total, dict(col_base=off, mn_major=True)),
-                       (ws['semb'], rp, E, dict(mn_major=True)), G(lin.weight), n, E, rp, out_ld=E)
-        off += n
+    lins = e['linears']
+    w0, b0 = G.offset[id(lins[0].weight)], G.offset[id(lins[0].bias)]
+    offs = [0]
+    for lin in lins:
+        offs.append(offs[-1] + lin.out_features)
+    if all(G.offset[id(l.weight)] == w0 + o * E and G.offset[id(l.bias)] == b0 + o for l, o in zip(lins, offs)):
+        # the gradient layout keeps the projections' weights (and biases) contiguous in `linears` order
+        # (_record_params): dW_all [total, E] = dproj^T semb in one GEMM, the bias gradients in one copy
+        G.flat[b0:b0 + total].copy_(ws['bias'])
+        K.gemm_batched((ws['dproj'], rp, total, dict(mn_major=True)), (ws['semb'], rp, E, dict(mn_major=True)),
+                       G.flat[w0:w0 + total * E].view(total, E), total, E, rp, out_ld=E)
+    else:   # caller-defined layout (gradients requested without a tape-derived order): one GEMM per projection
+        for lin, off in zip(lins, offs):
+            n = lin.out_features
+            G(lin.bias).copy_(ws['bias'][off:off + n])
+            K.gemm_batched((ws['dproj'], rp, total, dict(col_base=off, mn_major=True)),
+                           (ws['semb'], rp, E, dict(mn_major=True)), G(lin.weight), n, E, rp, out_ld=E)
     K.gemm_batched((ws['dproj'], rp, total), (e['w'], total, E, dict(mn_major=True)), ws['dsemb'], rows, E, total,
                    out_ld=E)
     # time MLP (+ class embedding)

@@ -165,10 +165,11 @@ int b200_attention_fwd_lse(const void* qk, int ld_qk, int q_off, int k_off, cons
  *     P = softmax(scale q k^T) (recomputed), dV = P^T dO, dP = dO V^T, dS = scale * P o (dP - rowsum(dO o O)),
  *     dQ = dS K, dK = dS^T Q.
  * qk / vt as in b200_attention_fwd with ld_qk = 2C, q_off = 0, k_off = C (C = heads*64); o, d_o: bf16 [B][T][C];
- * lse from b200_attention_fwd_lse; dqk: bf16 [B][T][2C] = [dQ | dK]; dv: bf16 [B][T][C].  One CTA per (image, head);
+ * lse from b200_attention_fwd_lse; dqk: bf16 [B][T][ld_dqk] with [dQ | dK] in its first 2C columns; dv: bf16
+ * [B][T][ld_dv] (both may point into one [B][T][3C] tensor: one weight-gradient GEMM for q, k, v).  One CTA per (image, head);
  * the [T][T] score tensors never leave the SM (the batched-GEMM form moved four of them through HBM). */
 int b200_attention_bwd(const void* qk, const void* vt, const void* o, const void* d_o, const float* lse, void* dqk,
-                       void* dv, int B, int T, int heads, int d, float scale, void* stream);
+                       int ld_dqk, void* dv, int ld_dv, int B, int T, int heads, int d, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2b: the WHOLE self-attention block (models/modules.py:77-102, SelfAttentionBlock.forward) in one launch:

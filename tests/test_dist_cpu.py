@@ -78,8 +78,9 @@ def test_completion_layout_orders_gradients_by_backward_completion():
     params, tape, blocks, projs, emb = _fake_net()
     order, _ = _completion_layout(tape, params)
     ids = [id(p) for p in order]
+    # the projections' weights lie side by side, then their biases: _embed_bwd writes each group with one launch
     want = [id(p) for b in reversed(blocks) for p in b.parameters()] + [id(p) for p in emb.parameters()] + \
-        [id(p) for pr in projs for p in pr.parameters()]
+        [id(pr.weight) for pr in projs] + [id(pr.bias) for pr in projs]
     assert ids == want and len(order) == len(params)
 
 

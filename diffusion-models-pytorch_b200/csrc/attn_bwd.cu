@@ -38,6 +38,11 @@ struct __align__(8) AttnBwdBars {
 
 __device__ __forceinline__ float abw_bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float abw_bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float abw_ex2(float x) {      // 2^x, one MUFU (exp2f adds a denormal-range rescale: 4 more instructions)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kAbwThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapDO,
@@ -152,7 +157,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     const int r = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     // per query row of both query tiles: log-sum-exp of the forward and D = sum_d dO * O
-    float lse[2] = {0.f, 0.f}, drow[2] = {0.f, 0.f};
+    // rows past T get lse = +inf: their P and dS come out as exact zeros without a per-element test
+    float lse[2] = {INFINITY, INFINITY}, drow[2] = {0.f, 0.f};
     for (int qt = 0; qt < nt; ++qt) {
       const int q = qt * 128 + r;
       if (q < p.T) {
@@ -176,8 +182,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
       for (int qt = 0; qt < nt; ++qt, ++it) {
         mbar_wait(&bars->sdp_full, (uint32_t)it & 1u);
         tc_fence_after();
-        const bool row_ok = qt * 128 + r < p.T;
-        const float l2 = lse[qt], dr = drow[qt];
+        // p = 2^(s * scale * log2e - lse), ds = p * (dP - D) * scale = p * (dP * scale - D * scale)
+        const float l2 = lse[qt], drs = drow[qt] * p.scale, sl2 = p.scale_log2e, sc = p.scale;
         uint32_t pp[32], dd[32];            // this thread's 64 keys of P and dS, packed bf16 pairs
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -191,19 +197,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
             if (lane == 0) mbar_arrive(&bars->sdp_free);
           }
           const int key0 = kt * 128 + half * 64 + c * 32;
+          if (key0 + 32 <= p.T) {           // warp-uniform: all 32 keys of the chunk exist (always, when T % 128 == 0)
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-            if (row_ok && key0 + j < p.T) {
-              p0 = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2e, -l2));
-              d0 = p0 * (__uint_as_float(dv[j]) - dr) * p.scale;
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = abw_ex2(fmaf(__uint_as_float(sv[j]), sl2, -l2));
+              const float p1 = abw_ex2(fmaf(__uint_as_float(sv[j + 1]), sl2, -l2));
+              pp[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
+              dd[c * 16 + (j >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(dv[j]), sc, -drs),
+                                                  p1 * fmaf(__uint_as_float(dv[j + 1]), sc, -drs));
             }
-            if (row_ok && key0 + j + 1 < p.T) {
-              p1 = exp2f(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2e, -l2));
-              d1 = p1 * (__uint_as_float(dv[j + 1]) - dr) * p.scale;
+          } else if (key0 >= p.T) {         // no key of the chunk exists (T <= 64 in a 128-key tile)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pp[c * 16 + j] = dd[c * 16 + j] = 0u;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float p0 = abw_ex2(fmaf(__uint_as_float(sv[j]), sl2, -l2));
+              float p1 = abw_ex2(fmaf(__uint_as_float(sv[j + 1]), sl2, -l2));
+              if (key0 + j >= p.T) p0 = 0.f;
+              if (key0 + j + 1 >= p.T) p1 = 0.f;
+              pp[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
+              dd[c * 16 + (j >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(dv[j]), sc, -drs),
+                                                  p1 * fmaf(__uint_as_float(dv[j + 1]), sc, -drs));
             }
-            pp[c * 16 + (j >> 1)] = pack_bf16x2(p0, p1);
-            dd[c * 16 + (j >> 1)] = pack_bf16x2(d0, d1);
           }
         }
         if (it > 0) mbar_wait(&bars->g2_done, (uint32_t)(it - 1) & 1u);     // the previous block's MMAs have read P / dS

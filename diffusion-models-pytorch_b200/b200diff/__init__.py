@@ -73,7 +73,7 @@ class SamplerDesc(Structure):
 class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next GroupNorm)
     _fields_ = [
         ('gamma', c_void_p), ('beta', c_void_p), ('scale', c_void_p), ('shift', c_void_p), ('out_norm', c_void_p),
-        ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
+        ('out_norm_ld', c_int), ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
         ('xstats', c_void_p), ('xcount', c_void_p),
     ]
 
@@ -494,11 +494,24 @@ def conv2d_gn_needs_workspace(Ho, Wo) -> bool:
 
 
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
-              rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True, xstats=None, xcount=None):
-    """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution;
-    nothing else is written.  Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}),
-    N % 128 == 0, power-of-two channels per group <= 32."""
+              rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True, xstats=None, xcount=None, out=None, stats=None,
+              residual=None, res_ld=0, a1=None, a1_geom=None, tap1=(0, 0, 0), out_norm_ld=0):
+    """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution.
+    Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}; 512 / 1024 with workspaces),
+    N % 128 == 0, power-of-two channels per group <= 32.
+    out=None: nothing else is written (conv1 -> norm2).  out = fp32 NHWC tensor: block-output form -- x = conv + bias
+    (+ residual) goes to `out` with its statistics in `stats` (multi-tile images: in `xstats`), GN(x) to out_norm;
+    a1 = second source (the fused 1x1 shortcut's K-blocks)."""
     _need_cuda(a0, w_packed, out_norm)
+    if out is not None:
+        _need_cuda(out)
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * Ho * Wo * N:
+            raise RuntimeError('conv2d_gn: out must be a contiguous float32 [B, Ho, Wo, N] tensor')
+        if residual is not None and (residual.dtype != torch.float32 or not residual.is_cuda):
+            raise RuntimeError('conv2d_gn: residual must be a float32 CUDA tensor')
+        _need_stats(stats)
+    elif residual is not None or stats is not None:
+        raise RuntimeError('conv2d_gn: residual / stats need the fp32 output `out`')
     d = ConvDesc()
     d.a0 = a0.data_ptr()
     d.a0_C, d.a0_H, d.a0_W, d.a0_planes = a0_geom
@@ -507,14 +520,24 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
     d.w_rows_per_phase = N
     d.B, d.Ho, d.Wo = B, Ho, Wo
     d.phases, d.N, d.ntaps0 = 1, N, len(taps0[0])
-    _fill_taps(d, taps0, (0, 0, 0))
+    _fill_taps(d, taps0, tap1)
+    if a1 is not None:
+        _need_cuda(a1)
+        d.a1 = a1.data_ptr()
+        d.a1_C, d.a1_H, d.a1_W, d.a1_planes = a1_geom
     d.bias = _ptr(bias)
     d.rowadd, d.rowadd_ld = _ptr(rowadd), rowadd_ld
-    d.out, d.out_mode, d.out_ld = None, OUT_BF16_NHWC, N
+    if out is None:
+        d.out, d.out_mode, d.out_ld = None, OUT_BF16_NHWC, N
+    else:
+        d.out, d.out_mode, d.out_ld = out.data_ptr(), OUT_F32_NHWC, N
+        d.residual, d.res_ld = _ptr(residual), res_ld
+        d.stats = _ptr(stats)
     d.out_H, d.out_W, d.osy, d.osx = Ho, Wo, 1, 1
     g = GnFuseDesc()
     g.gamma, g.beta, g.scale, g.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
     g.out_norm, g.ss_ld, g.groups, g.apply_silu, g.eps = out_norm.data_ptr(), ss_ld, groups, int(silu), float(eps)
+    g.out_norm_ld = out_norm_ld
     _need_stats(xstats, xcount)
     if conv2d_gn_needs_workspace(Ho, Wo) and (xstats is None or xcount is None or xstats.numel() < B * N * 2
                                               or xcount.numel() < B):

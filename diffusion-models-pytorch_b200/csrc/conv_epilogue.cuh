@@ -37,6 +37,8 @@ struct ConvKParams {
   const float* gn_scale;
   const float* gn_shift;
   void* gn_out;
+  int gn_out_ld;   // channel stride of gn_out (>= N: the normalised copy may be a column window of a wider tensor)
+  int gn_raw;      // 1: conv2-style use -- the fp32 result (+ residual) is ALSO written to `out` (+ `stats`), see below
   int gn_ss_ld, gn_lg_cpg, gn_silu;
   int gn_cl;     // tiles (= co-scheduled CTAs) per image in the multi-tile variant of the fused epilogue, else 0
   long long* gn_xstats;            // multi-tile variant: zeroed [B][N][2] int64 statistics of the conv output
@@ -542,16 +544,31 @@ __device__ __forceinline__ float2 stat_load_group_cg(const long long* pair, int 
   return make_float2(__ll2float_rn(a) * (1.0f / kStatQ1), __ll2float_rn(b) * (1.0f / kStatQ2));
 }
 
-template <bool HAS_ROW, bool HAS_SS, bool MULTI = false>
+// RAW = true (conv2 -> the NEXT block's norm1, models/unet.py:30-43 across two ResBlocks; the last block -> the output
+// head's norm): the conv result x = acc + bias (+ residual) is a block output, so it is also written as fp32 NHWC to
+// p.out with its per-channel statistics in p.stats (skip connections, attention blocks and the next block's residual
+// read them), and pass 1 stores x back into TMEM so that pass 2 normalises the final values without a second read of
+// the residual.  The normalised copy goes to p.gn_out with channel stride p.gn_out_ld.
+template <bool HAS_ROW, bool HAS_SS, bool MULTI = false, bool RAW = false>
 __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
                                                      const int c, const int half, const int cl, float* xbuf,
                                                      uint64_t* acc_full_bar, const uint32_t acc_parity) {
   // cl = channel inside the tile (0..127); xbuf = this tile's exchange buffer [2 halves][4 chunks][128][2]
   const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
   const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
+  const int nch = p.NP >> 6;     // 32-pixel chunks per warp: 1, 2 or 4 (tiles of 64 / 128 / 256 pixels)
+  const int rst = p.res_ld * 4, wst = p.out_ld * 4;      // RAW: byte strides between consecutive pixels
+  const char* const rbase = (RAW && p.residual) ? reinterpret_cast<const char*>(p.residual + pix0 * (size_t)p.res_ld + c) : nullptr;
+  char* const wbase = RAW ? reinterpret_cast<char*>(reinterpret_cast<float*>(p.out) + pix0 * (size_t)p.out_ld + c) : nullptr;
+  if (RAW && rbase != nullptr) {
+    // residual lines of this warp's chunks into L2 while the tile's MMAs still run (as in conv_epilogue_lean)
+    const int lane = threadIdx.x & 31;
+    const char* pf = rbase - (long long)lane * 4;
+    for (int i = 0; i < nch; ++i)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (long long)(half * 32 + 64 * i + lane) * rst));
+  }
   mbar_wait(acc_full_bar, acc_parity);
   tc_fence_after();
-  const int nch = p.NP >> 6;     // 32-pixel chunks per warp: 1, 2 or 4 (tiles of 64 / 128 / 256 pixels)
   float ps1[4][2], ps2[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -559,8 +576,14 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
     if (i >= nch) continue;
     const int ch = half * 32 + 64 * i;
     uint32_t v[32];
+    float r[32];
     __syncwarp();
     tmem_ld_x32(taddr + (uint32_t)ch, v);
+    if (RAW && rbase != nullptr) {      // overlaps the TMEM load
+      const char* rp = rbase + (long long)ch * rst;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __ldg(reinterpret_cast<const float*>(rp + (long long)j * rst));
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -569,12 +592,47 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
       float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
       for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
-        const float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
+        float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
+        if (RAW) {
+          if (rbase != nullptr) { a0 += r[j]; a1 += r[j + 1]; }
+          v[j] = __float_as_uint(a0);
+          v[j + 1] = __float_as_uint(a1);
+        }
         s1 += a0; t1 += a1;
         s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
       }
       ps1[i][hf] = s1 + t1;
       ps2[i][hf] = s2 + t2;
+    }
+    if (RAW) {
+      tmem_st_x32(taddr + (uint32_t)ch, v);      // pass 2 reads the final values
+      char* wp = wbase + (long long)ch * wst;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
+    }
+  }
+  if (RAW) {
+    tmem_st_wait();
+    if (!MULTI && p.stats != nullptr) {
+      // per-channel statistics of the block output (this warp's share of each image of the tile)
+      if (p.lg_bhw >= 8) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1]; b += ps2[i][0] + ps2[i][1]; }
+        stat_add(p.stats + ((size_t)t.n0 * p.N + c) * 2, a, b);
+      } else if (p.lg_bhw == 6) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nch) stat_add(p.stats + ((size_t)(t.n0 + i) * p.N + c) * 2, ps1[i][0] + ps1[i][1], ps2[i][0] + ps2[i][1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nch) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+              stat_add(p.stats + ((size_t)(t.n0 + ((half * 32 + 64 * i + 16 * hf) >> 4)) * p.N + c) * 2, ps1[i][hf], ps2[i][hf]);
+          }
+      }
     }
   }
   float S1[4][2], S2[4][2];
@@ -657,8 +715,8 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
   const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (MULTI ? p.gn_cl : 1));
   const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f;
   const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
-  __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.N + c;
-  const int ost = p.N * 2;    // bytes between consecutive pixels of the NHWC output
+  __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.gn_out_ld + c;
+  const int ost = p.gn_out_ld * 2;    // bytes between consecutive pixels of the NHWC output
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= nch) continue;
@@ -671,7 +729,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
-      const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+      const float add_c = RAW ? 0.f : bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
       const float mean = S1[i][hf] * inv_cnt;
       const float var = fmaxf(S2[i][hf] * inv_cnt - mean * mean, 0.f);
       const float rstd = rsqrtf(var + p.gn_eps);

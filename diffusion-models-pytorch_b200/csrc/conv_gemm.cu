@@ -201,7 +201,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // multi-tile fused next-GroupNorm epilogue (32x32 images: statistics through global memory, cooperative launch)
         const int cl = q * 32 + lane;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (row && ss) conv_epilogue_gnfuse<true, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        if (p.gn_raw) conv_epilogue_gnfuse<false, false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        else if (row && ss) conv_epilogue_gnfuse<true, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
         else if (row) conv_epilogue_gnfuse<true, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
         else if (ss) conv_epilogue_gnfuse<false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
         else conv_epilogue_gnfuse<false, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
@@ -211,7 +212,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         float* xbuf = reinterpret_cast<float*>(bars + 1) + (it & 1) * 2048;
         const int cl = q * 32 + lane;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (row && ss) conv_epilogue_gnfuse<true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        if (p.gn_raw) conv_epilogue_gnfuse<false, false, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        else if (row && ss) conv_epilogue_gnfuse<true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
         else if (row) conv_epilogue_gnfuse<true, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
         else if (ss) conv_epilogue_gnfuse<false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
         else conv_epilogue_gnfuse<false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
@@ -252,8 +254,18 @@ extern "C" int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_de
   B200_REQUIRE(d != nullptr && g != nullptr, "conv2d_gn_fwd: null descriptor");
   B200_REQUIRE(g->out_norm && g->groups >= 1, "conv2d_gn_fwd: null out_norm / bad groups");
   B200_REQUIRE(d->N > 32 && d->N % kBlockC == 0, "conv2d_gn_fwd: N=%d must be a multiple of 128", d->N);
-  B200_REQUIRE(d->residual == nullptr && d->stats == nullptr && d->phases == 1 && d->a1 == nullptr,
-               "conv2d_gn_fwd: residual / statistics / phases / second source are not supported");
+  B200_REQUIRE(d->phases == 1, "conv2d_gn_fwd: phase convolutions are not supported");
+  if (d->out == nullptr) {
+    B200_REQUIRE(d->residual == nullptr && d->stats == nullptr, "conv2d_gn_fwd: residual / statistics need the fp32 output (d->out)");
+  } else {
+    // block-output form: x = conv + bias (+ residual) -> d->out (fp32 NHWC) + d->stats, and GN(x) -> g->out_norm
+    B200_REQUIRE(d->out_mode == B200_OUT_F32_NHWC && d->out_ld >= d->N && ((uintptr_t)d->out & 15) == 0,
+                 "conv2d_gn_fwd: the raw output must be fp32 NHWC");
+    B200_REQUIRE(d->rowadd == nullptr && g->scale == nullptr && g->shift == nullptr,
+                 "conv2d_gn_fwd: the block-output form takes no embedding row / scale / shift");
+    B200_REQUIRE(d->residual == nullptr || d->res_ld >= d->N, "conv2d_gn_fwd: bad res_ld");
+  }
+  B200_REQUIRE(g->out_norm_ld == 0 || (g->out_norm_ld >= d->N && g->out_norm_ld % 8 == 0), "conv2d_gn_fwd: bad out_norm_ld");
   B200_REQUIRE(((uintptr_t)g->out_norm & 15) == 0, "conv2d_gn_fwd: out_norm alignment");
   tl_gn_fuse = g;
   const int rc = b200_conv2d_fwd(d, stream_);
@@ -448,6 +460,11 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     B200_REQUIRE((g->scale == nullptr) == (g->shift == nullptr), "conv2d_gn_fwd: scale and shift come together");
     p.gn_gamma = g->gamma; p.gn_beta = g->beta; p.gn_scale = g->scale; p.gn_shift = g->shift; p.gn_out = g->out_norm;
     p.gn_ss_ld = g->ss_ld; p.gn_lg_cpg = ilog2(cpg); p.gn_silu = g->apply_silu; p.gn_eps = g->eps;
+    p.gn_out_ld = g->out_norm_ld ? g->out_norm_ld : d->N;
+    p.gn_raw = d->out != nullptr ? 1 : 0;
+    if (p.gn_raw && gn_cl)
+      B200_REQUIRE(d->stats == nullptr || d->stats == g->xstats,
+                   "conv2d_gn_fwd: multi-tile images accumulate the output statistics in xstats (pass stats = xstats or NULL)");
     p.gn_cl = gn_cl;
     if (gn_cl) {
       // the gn_cl tiles of an image are taken in the same iteration by gn_cl consecutive CTAs (tile = blockIdx.x + i *

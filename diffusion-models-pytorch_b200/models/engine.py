@@ -23,10 +23,11 @@ import b200diff as K
 
 class Act:
     """fp32 NHWC activation [B, H, W, C]."""
-    __slots__ = ('t', 'B', 'H', 'W', 'C', 'stats', 'g')
+    __slots__ = ('t', 'B', 'H', 'W', 'C', 'stats', 'g', 'pre')
 
     def __init__(self, t, B, H, W, C, stats=None):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.pre = None      # (GroupNorm module, silu, bf16 NHWC tensor): GN(+SiLU) of this tensor already applied by its producer
         self.stats = stats   # [B, C, 2] int64 fixed-point per-(image, channel) sum / sum of squares from the producing kernel
         self.g = None        # fp32 NHWC gradient buffer, created by the first backward contribution (models/backward.py)
 
@@ -45,6 +46,9 @@ class Engine:
     # output never touch HBM.  B200_ATTN_BLOCK=0: the five-launch form (A/B).
     attn_block = bool(int(__import__('os').environ.get('B200_ATTN_BLOCK', '1')))
     attn_bwd_fused = bool(int(__import__('os').environ.get('B200_ATTN_BWD_FUSED', '1')))   # =0: batched-GEMM adjoint (A/B)
+    # a block's last conv also emits the GroupNorm(+SiLU) of its output for the NEXT block's norm1 / the output head
+    # (b200_conv2d_gn_fwd, block-output form) when that norm has this tensor as its only input; =0: separate launch (A/B)
+    fuse_gn1 = bool(int(__import__('os').environ.get('B200_FUSE_GN1', '1')))
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -342,6 +346,9 @@ class Engine:
 
     def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
            ss_ld=0, resample=0, drop_p=0.0, drop_seed=0):
+        if (x.pre is not None and x.pre[0] is norm and x.pre[1] == bool(silu) and skip is None and not raw
+                and scale is None and resample == 0 and drop_p == 0.0 and self.tape is None and not self.split):
+            return x.pre[2], None      # the producing conv already applied this GroupNorm (fuse_gn1)
         seed_dev = self.seed_dev if drop_p > 0 else None
         C = x.C + (skip.C if skip is not None else 0)
         Ho, Wo = x.H, x.W
@@ -397,8 +404,9 @@ class Engine:
                  res_ld=0 if residual is None else residual.C, out=out, out_mode=out_mode, stats=stats)
         return Act(out, B, H, W, Cout, stats)
 
-    def attention(self, tag, blk, x: Act) -> Act:
-        """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2."""
+    def attention(self, tag, blk, x: Act, next_gn=None) -> Act:
+        """models/modules.py:89-102 (own UNets): separate q, k, v, proj 1x1 convs; q scaled by d^-1/2.
+        next_gn: see `resblock` (applied by the output projection's epilogue on the five-launch path)."""
         if self.split:
             return self._attention_split(tag, blk, x)
         if (self.attn_block and self.tape is None and x.stats is not None
@@ -421,7 +429,7 @@ class Engine:
         else:
             weights = hit[0]
         return self.attention_core(tag, x, blk.norm, weights, blk.n_heads, blk.scale,
-                                   mods=(blk.q, blk.k, blk.v, blk.proj))
+                                   mods=(blk.q, blk.k, blk.v, blk.proj), next_gn=next_gn)
 
     def _attention_block_fused(self, tag, blk, x: Act) -> Act:
         """models/modules.py:89-102 in one launch (b200_attn_block_fwd).  The caller checked K.attn_block_ok."""
@@ -508,7 +516,8 @@ class Engine:
         with self.scope():       # the block's temporaries are released when it returns
             return self._attention_core_body(*args, **kwargs)
 
-    def _attention_core_body(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None) -> Act:
+    def _attention_core_body(self, tag, x: Act, norm: nn.GroupNorm, weights, heads: int, scale: float, mods=None,
+                             next_gn=None) -> Act:
         """GroupNorm -> [q|k] and v^T 1x1 convs -> fused softmax(q k^T * scale) v -> 1x1 proj + residual.
         `weights` = (Wqk [2C, C] bf16 with rows [q heads..., k heads...], bqk, Wv [C, C], bv, Wproj, bproj)."""
         if self.split:
@@ -533,6 +542,8 @@ class Engine:
         lse = (self.buf(tag + '.lse', (B, heads, T), torch.float32, temp=True)
                if self.tape is not None and self.attn_bwd_fused and K.attention_bwd_ok(T, d) else None)
         K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale, lse=lse)
+        if C % 64 == 0 and self.next_gn_ok(B, H, W, C, next_gn):
+            return self.conv_block_out(tag, o, B, H, W, C, C, wp, bp, K.taps_1x1(), next_gn, residual=x)
         out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
         stats = self.stats_buf(tag, B, C)
         K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
@@ -626,13 +637,45 @@ class Engine:
                         rowadd=emb[:, emb_off:], rowadd_ld=emb_ld, **ws)
         return a2
 
+    def next_gn_ok(self, B, H, W, C, next_gn) -> bool:
+        """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu) of its consumer?"""
+        return (next_gn is not None and self.fuse_gn1 and self.fuse_gn2 and self.tape is None and not self.split
+                and next_gn[0].num_channels == C and K.conv2d_gn_ok(B, H, W, C, next_gn[0].num_groups))
+
+    def _pre_buf(self, B, H, W, C):
+        """bf16 buffer for a producer-applied GroupNorm: read by the very next block only, so two per shape alternate."""
+        k = (B, H, W, C)
+        n = self._pp_count.get(('pre', k), 0)
+        self._pp_count[('pre', k)] = n + 1
+        return self.buf(f'pre{n & 1}', (B, H, W, C), torch.bfloat16)
+
+    def conv_block_out(self, tag, a, B, H, W, Cin, Cout, w, b, taps, next_gn, *, residual: Optional[Act] = None, sc_a=None,
+                       sc_C=0) -> Act:
+        """Last conv of a block with the consumer's GroupNorm fused: out = conv(a) + b (+ residual | + 1x1 shortcut
+        K-blocks over sc_a) as fp32 NHWC with statistics, and out.pre = SiLU?(GN_next(out)) as bf16 (one launch)."""
+        norm, silu = next_gn
+        out = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
+        stats = self.stats_buf(tag, B, Cout)
+        pre = self._pre_buf(B, H, W, Cout)
+        ws = {}
+        if K.conv2d_gn_needs_workspace(H, W):     # several tiles per image: the output statistics double as the exchange workspace
+            ws = dict(xstats=stats, xcount=self.stats_buf(tag + '.cnt', B, 1))
+        K.conv2d_gn(a, w, Cout, B, H, W, taps, a0_geom=(Cin, H, W, 1), gamma=norm.weight, beta=norm.bias,
+                    groups=norm.num_groups, eps=norm.eps, out_norm=pre, bias=b, silu=silu, out=out,
+                    stats=None if ws else stats, residual=None if residual is None else residual.t,
+                    res_ld=0 if residual is None else residual.C, a1=sc_a,
+                    a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, **ws)
+        res = Act(out, B, H, W, Cout, stats)
+        res.pre = (norm, bool(silu), pre)
+        return res
+
     def resblock_core(self, *args, **kwargs):
         with self.scope():       # the block's temporaries are released when it returns
             return self._resblock_core_body(*args, **kwargs)
 
     def _resblock_core_body(self, tag, x: Act, skip: Optional[Act], *, norm1, conv1, norm2, conv2, shortcut, emb, emb_off,
                       emb_ld, scale_shift: bool, resample: int = 0, dropout: Optional[nn.Dropout] = None,
-                      emb_linear: Optional[nn.Linear] = None) -> Act:
+                      emb_linear: Optional[nn.Linear] = None, next_gn=None) -> Act:
         """The ResBlock shared by all UNet families:
             h = conv1(resample(SiLU(GN1(cat(x, skip)))))            (+ emb row when not scale_shift)
             h = conv2(SiLU(GN2(h) [* (1 + scale) + shift]))          (dropout = identity in eval mode)
@@ -672,7 +715,14 @@ class Engine:
             h = self.conv3x3(tag + '.c1', a1, B, Ho, Wo, Cin, conv1, rowadd=emb[:, emb_off:], rowadd_ld=emb_ld,
                              intermediate=True)
             a2, _ = self.gn(tag + '.2', h, None, norm2, drop_p=drop_p, drop_seed=drop_seed)
-        if sc1x1:
+        fuse_next = not sc3x3 and Cout % 64 == 0 and self.next_gn_ok(B, Ho, Wo, Cout, next_gn)
+        if fuse_next:       # conv2 (+ residual / 1x1 shortcut) also applies the consumer's GroupNorm (`next_gn`)
+            w2, b2 = self.w_conv(tag + '.c2', conv2, shortcut if sc1x1 else None)
+            if not sc1x1:
+                assert skip is None and Cin == Cout
+            out = self.conv_block_out(tag + '.c2', a2, B, Ho, Wo, Cout, Cout, w2, b2, K.taps_3x3_s1(), next_gn,
+                                      residual=None if sc1x1 else res_x, sc_a=raw if sc1x1 else None, sc_C=Cin if sc1x1 else 0)
+        elif sc1x1:
             out = self.conv3x3(tag + '.c2', a2, B, Ho, Wo, Cout, conv2, sc_a=raw, sc_C=Cin, sc_conv=shortcut)
         else:
             if sc3x3:
@@ -687,13 +737,15 @@ class Engine:
                                   drop_seed=drop_seed, emb_linear=emb_linear))
         return out
 
-    def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld) -> Act:
-        """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x)."""
+    def resblock(self, tag, blk, x: Act, skip: Optional[Act], tproj, tproj_off, tproj_ld, next_gn=None) -> Act:
+        """models/unet.py:30-43: conv(SiLU(GN(x))) + temb -> conv(SiLU(GN(h))) + shortcut(x).
+        next_gn = (GroupNorm, silu) of the op that consumes this block's output as its ONLY GroupNorm input (the next
+        ResBlock's norm1 without a concatenated skip, an attention block's norm, the output head's norm), or None."""
         return self.resblock_core(tag, x, skip, norm1=blk.blk1[0], conv1=blk.blk1[2], norm2=blk.blk2[0],
                                   conv2=blk.blk2[3],
                                   shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
                                   emb=tproj, emb_off=tproj_off, emb_ld=tproj_ld, scale_shift=False, dropout=blk.blk2[2],
-                                  emb_linear=blk.proj[1])
+                                  emb_linear=blk.proj[1], next_gn=next_gn)
 
     def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
         """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""

@@ -88,14 +88,21 @@ int b200_conv2d_fwd(const b200_conv_desc* d, void* stream);
  * tile holds whole images (Ho*Wo in {16, 64, 256}) and its 128 channels whole groups, so the statistics are complete
  * inside a CTA (tiles are chosen so that they hold whole images and are full: B must be a multiple of 64 / (Ho*Wo) for
  * 4x4 images), or when an image is 2 / 4 tiles and N == 128 (the tiles' CTAs are launched cooperatively and exchange
- * their sums through g->xstats / g->xcount).  d->out / d->stats / d->residual must be NULL-equivalent (ignored);
- * N % 128 == 0; N / groups a power of two <= 32.  The engine uses it for every eligible ResBlock at inference (B200_FUSE_GN2=0 restores two launches). */
+ * their sums through g->xstats / g->xcount).  N % 128 == 0; N / groups a power of two <= 32.
+ * Two forms:
+ *   d->out == NULL  (conv1 -> norm2): only out_norm is written; d->stats / d->residual must be NULL;
+ *   d->out != NULL  (block output: conv2 -> the NEXT block's norm1, models/unet.py:30-43 across two ResBlocks, or the
+ *                   last block -> the output head's norm, models/unet.py:116-117): x = conv + bias (+ d->residual) is
+ *                   written to d->out as fp32 NHWC with its statistics in d->stats (multi-tile images: in g->xstats),
+ *                   and GN(x) to out_norm; no rowadd / scale / shift.
+ * The engine uses both for every eligible layer at inference (B200_FUSE_GN2=0 / B200_FUSE_GN1=0 restore two launches). */
 typedef struct b200_gn_fuse_desc {
   const float* gamma;        /* [N] */
   const float* beta;         /* [N] */
   const float* scale;        /* optional per-image rows [B][ss_ld]: y = GN(x) * (1 + scale) + shift */
   const float* shift;
-  void* out_norm;            /* bf16 NHWC [B][Ho][Wo][N] */
+  void* out_norm;            /* bf16 NHWC [B][Ho][Wo][out_norm_ld] (first N columns) */
+  int out_norm_ld;           /* channel stride of out_norm; 0 = N */
   int ss_ld;
   int groups;
   int apply_silu;

@@ -1292,6 +1292,62 @@ def case_conv_gnfuse():
     return ok
 
 
+def case_conv_gnfuse_out():
+    """b200_conv2d_gn_fwd, block-output form (conv2 -> the next block's norm1 / the output head's norm): x = conv(a) + bias
+    (+ residual | + 1x1 shortcut K-blocks) as fp32 NHWC with per-channel statistics, and SiLU?(GN(x)) as bf16 NHWC, in
+    one launch; 3x3 and 1x1 taps, all four resolutions (32x32: four co-scheduled CTAs per image)."""
+    import b200diff as K
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    #        B   Cin  Cout  H  taps residual shortcut(Csc) groups silu
+    cfgs = ((150, 128, 128, 32, 3, True, 0, 32, True),       # E0 -> E1 of the CIFAR-10 UNet
+            (37, 128, 128, 32, 3, False, 256, 32, True),     # last decoder block (1x1 shortcut over 256 channels) -> head
+            (96, 256, 256, 16, 3, True, 0, 32, True),
+            (160, 256, 256, 8, 3, True, 0, 32, True),
+            (320, 256, 256, 4, 3, True, 0, 32, False),       # ResBlock -> attention norm (no SiLU)
+            (64, 256, 256, 4, 1, True, 0, 32, True),         # attention output projection (1x1 + residual) -> next norm1
+            (128, 128, 256, 8, 3, False, 128, 16, True),
+            (5, 128, 128, 32, 3, False, 0, 32, True))
+    for (B, Cin, Cout, H, k, use_res, Csc, groups, silu) in cfgs:
+        x = _bf16r(_gen(B, Cin, H, H, seed=1))
+        if H == 32:
+            x = _bf16r(x * torch.linspace(0.5, 2.0, H, device=DEV)[None, None, :, None])
+        w = _bf16r(_gen(Cout, Cin, k, k, seed=2, scale=1.0 / math.sqrt(Cin * k * k)))
+        b = _gen(Cout, seed=3)
+        gamma, beta = 1.0 + 0.1 * _gen(Cout, seed=5), 0.1 * _gen(Cout, seed=6)
+        res = _gen(B, H, H, Cout, seed=8) if use_res else None                   # fp32 NHWC residual stream
+        pre = F.conv2d(x, w, b, padding=k // 2)
+        wp = K.pack_weight(w)
+        a1 = None
+        if Csc:
+            xs = _bf16r(_gen(B, Csc, H, H, seed=9))
+            wsc = _bf16r(_gen(Cout, Csc, 1, 1, seed=10, scale=1.0 / math.sqrt(Csc)))
+            pre = pre + F.conv2d(xs, wsc)
+            wp = torch.cat([wp, K.pack_weight(wsc)], dim=1).contiguous()
+            a1 = _nhwc_bf16(xs)
+        if use_res:
+            pre = pre + res.permute(0, 3, 1, 2)
+        ref = F.group_norm(pre, groups, gamma, beta, eps=1e-5)
+        if silu:
+            ref = F.silu(ref)
+        out = torch.full((B, H, H, Cout), float('nan'), device=DEV, dtype=torch.float32)
+        outn = torch.full((B, H, H, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+        stats = K.new_stats(B, Cout, DEV)
+        multi = K.conv2d_gn_needs_workspace(H, H)
+        ws = dict(xstats=stats, xcount=K.new_stats(B, 1, DEV)) if multi else {}
+        taps = K.taps_3x3_s1() if k == 3 else K.taps_1x1()
+        K.conv2d_gn(_nhwc_bf16(x), wp, Cout, B, H, H, taps, a0_geom=(Cin, H, H, 1), gamma=gamma, beta=beta, groups=groups,
+                    eps=1e-5, out_norm=outn, bias=b, silu=silu, out=out, stats=None if multi else stats, residual=res,
+                    res_ld=Cout if use_res else 0, a1=a1, a1_geom=(Csc, H, H, 1) if Csc else None, **ws)
+        torch.cuda.synchronize()
+        name = f'conv{k}x{k} {Cin}->{Cout} @{H} B={B} (res={use_res}, shortcut={Csc}, groups={groups}, silu={silu})'
+        ok &= _report(name + ' raw fp32 output', out.permute(0, 3, 1, 2), pre, rtol=1e-3, atol=1e-3)
+        want_st = torch.stack([pre.sum(dim=(2, 3)), (pre * pre).sum(dim=(2, 3))], dim=-1)
+        ok &= _report(name + ' output statistics', K.stats_to_float(stats), want_st, 1e-3, 5e-2)
+        ok &= _report(name + ' fused GN of the output', outn.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+    return ok
+
+
 CASES = {n[5:]: f for n, f in list(globals().items()) if n.startswith('case_')}
 
 if __name__ == '__main__':

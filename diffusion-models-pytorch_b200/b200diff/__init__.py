@@ -73,7 +73,8 @@ class SamplerDesc(Structure):
 class GnFuseDesc(Structure):      # mirrors b200_gn_fuse_desc (fused conv + next GroupNorm)
     _fields_ = [
         ('gamma', c_void_p), ('beta', c_void_p), ('scale', c_void_p), ('shift', c_void_p), ('out_norm', c_void_p),
-        ('out_norm_ld', c_int), ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int), ('eps', ctypes.c_float),
+        ('out_norm_ld', c_int), ('out_raw_bf16', c_void_p), ('ss_ld', c_int), ('groups', c_int), ('apply_silu', c_int),
+        ('eps', ctypes.c_float),
         ('xstats', c_void_p), ('xcount', c_void_p),
     ]
 
@@ -495,7 +496,7 @@ def conv2d_gn_needs_workspace(Ho, Wo) -> bool:
 
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
               rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True, xstats=None, xcount=None, out=None, stats=None,
-              residual=None, res_ld=0, a1=None, a1_geom=None, tap1=(0, 0, 0), out_norm_ld=0):
+              residual=None, res_ld=0, a1=None, a1_geom=None, tap1=(0, 0, 0), out_norm_ld=0, out_raw=None):
     """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution.
     Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}; 512 / 1024 with workspaces),
     N % 128 == 0, power-of-two channels per group <= 32.
@@ -538,6 +539,11 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
     g.gamma, g.beta, g.scale, g.shift = _ptr(gamma), _ptr(beta), _ptr(scale), _ptr(shift)
     g.out_norm, g.ss_ld, g.groups, g.apply_silu, g.eps = out_norm.data_ptr(), ss_ld, groups, int(silu), float(eps)
     g.out_norm_ld = out_norm_ld
+    if out_raw is not None:
+        _need_cuda(out_raw)
+        if out is None or out_raw.dtype != torch.bfloat16:
+            raise RuntimeError('conv2d_gn: out_raw (bf16) needs the block-output form (out=...)')
+    g.out_raw_bf16 = _ptr(out_raw)
     _need_stats(xstats, xcount)
     if conv2d_gn_needs_workspace(Ho, Wo) and (xstats is None or xcount is None or xstats.numel() < B * N * 2
                                               or xcount.numel() < B):
@@ -581,7 +587,21 @@ def _gn_bytes(B, HW, C, resample, raw):
 def groupnorm_apply(x0, C0, stats0, x1, C1, stats1, B, HW, W, groups, gamma, beta, eps, out, *, scale=None,
                     shift=None, ss_ld=0, silu=True, resample=0, raw_out=None, drop_p=0.0, drop_seed=0,
                     drop_seed_dev=None):
-    """Streaming GroupNorm(+SiLU)(+dropout) for inputs whose [B][C][2] statistics came from the producing kernel."""
+    """Streaming GroupNorm(+SiLU)(+dropout) for inputs whose [B][C][2] statistics came from the producing kernel.
+    x0=None with C0 > 0: window mode -- channels [0, C0) of `out` / `raw_out` were already written by the first source's
+    producer (conv2d_gn block-output form); only the second source's channels [C0, C0 + C1) are normalised here."""
+    if x0 is None:
+        if x1 is None or C0 <= 0:
+            raise RuntimeError('groupnorm_apply: window mode (x0=None) needs C0 > 0 and a second source')
+        _need_cuda(x1, stats1, out)
+        _need_stats(stats1)
+        _launch('groupnorm_apply',
+                lambda: _check(lib().b200_groupnorm_apply_train_fwd(
+                    None, 0, C0, None, x1.data_ptr(), C1, stats1.data_ptr(), B, HW, W, groups, _ptr(gamma), _ptr(beta),
+                    float(eps), _ptr(scale), _ptr(shift), ss_ld, int(silu), resample, 0.0, 0, None, out.data_ptr(),
+                    _ptr(raw_out), _stream()), 'groupnorm_apply_fwd'),
+                nbytes=_gn_bytes(B, HW, C1, resample, raw_out is not None))
+        return out
     _need_cuda(x0, stats0, out)
     _need_stats(stats0, stats1)
     _launch('groupnorm_apply',

@@ -39,6 +39,8 @@ struct ConvKParams {
   void* gn_out;
   int gn_out_ld;   // channel stride of gn_out (>= N: the normalised copy may be a column window of a wider tensor)
   int gn_raw;      // 1: conv2-style use -- the fp32 result (+ residual) is ALSO written to `out` (+ `stats`), see below
+  void* gn_rawcopy;  // gn_raw only, optional: bf16 copy of the un-normalised result, laid out like gn_out (the operand of
+                     // the consumer's fused 1x1 shortcut when the consumer concatenates a skip connection)
   int gn_ss_ld, gn_lg_cpg, gn_silu;
   int gn_cl;     // tiles (= co-scheduled CTAs) per image in the multi-tile variant of the fused epilogue, else 0
   long long* gn_xstats;            // multi-tile variant: zeroed [B][N][2] int64 statistics of the conv output
@@ -717,6 +719,8 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
   const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
   __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.gn_out_ld + c;
   const int ost = p.gn_out_ld * 2;    // bytes between consecutive pixels of the NHWC output
+  const bool rawcopy = RAW && p.gn_rawcopy != nullptr;
+  __nv_bfloat16* const rcbase = rawcopy ? reinterpret_cast<__nv_bfloat16*>(p.gn_rawcopy) + pix0 * (size_t)p.gn_out_ld + c : nullptr;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i >= nch) continue;
@@ -726,6 +730,12 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
     tmem_ld_x32(taddr + (uint32_t)ch, v);
     tmem_ld_wait();
     char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
+    if (rawcopy) {
+      char* rp = reinterpret_cast<char*>(rcbase) + (long long)ch * ost;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) = __float2bfloat16_rn(__uint_as_float(v[j]));
+    }
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);

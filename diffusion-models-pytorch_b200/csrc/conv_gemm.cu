@@ -462,6 +462,9 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     p.gn_ss_ld = g->ss_ld; p.gn_lg_cpg = ilog2(cpg); p.gn_silu = g->apply_silu; p.gn_eps = g->eps;
     p.gn_out_ld = g->out_norm_ld ? g->out_norm_ld : d->N;
     p.gn_raw = d->out != nullptr ? 1 : 0;
+    B200_REQUIRE(g->out_raw_bf16 == nullptr || (p.gn_raw && ((uintptr_t)g->out_raw_bf16 & 15) == 0),
+                 "conv2d_gn_fwd: out_raw_bf16 needs the block-output form (d->out) and 16-byte alignment");
+    p.gn_rawcopy = g->out_raw_bf16;
     if (p.gn_raw && gn_cl)
       B200_REQUIRE(d->stats == nullptr || d->stats == g->xstats,
                    "conv2d_gn_fwd: multi-tile images accumulate the output statistics in xstats (pass stats = xstats or NULL)");

@@ -290,6 +290,8 @@ struct GnApplyParams {
   int cols8;    // 8-channel columns: C0, C1 multiples of 8 and C / 8 <= 256; 2 = coefficients computed per thread
   int reverse;  // walk images / pixel ranges from the end: the producer's most recent writes are still in L2
   int in_bf16;  // source 0 is bf16 (a conv output consumed only by this GroupNorm), single source only
+  int c_begin;  // first channel this launch handles: C0 when the first source's part of `out` / `raw` was already written by
+                // its producer (fused conv epilogue, b200_conv2d_gn_fwd block-output form; x0 == NULL), else 0
   __nv_bfloat16* out; __nv_bfloat16* raw;
   float drop_p, drop_scale;       // training-mode dropout after the activation (resample == 0 only)
   uint32_t drop_thresh; unsigned long long drop_seed; const unsigned long long* drop_seed_dev;
@@ -321,12 +323,12 @@ template <bool kInBf16, int kU, bool kOwnCoef>
 __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const float* coefA, const float* coefB, int n,
                                                int px0, int px1, unsigned long long drop_seed) {
   const int C = p.C0 + p.C1;
-  const int nv8 = C >> 3;
+  const int nv8 = (C - p.c_begin) >> 3;
   const int pstep = 256 / nv8;
   const int tid = threadIdx.x;
   if (tid >= pstep * nv8) return;
   const int j = tid % nv8, prow = tid / nv8;
-  const int c = j << 3;
+  const int c = p.c_begin + (j << 3);
   const bool from0 = c < p.C0;
   const int sld = from0 ? p.C0 : p.C1;
   const float* src = from0 ? p.x0 + (size_t)n * p.HW * p.C0 + c : p.x1 + (size_t)n * p.HW * p.C1 + (c - p.C0);
@@ -668,7 +670,10 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
                                               void* raw_out_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const float* x0 = reinterpret_cast<const float*>(x0_);
-  B200_REQUIRE(x0 && stats0 && out_bf16, "groupnorm_apply: null x0/stats0/out");
+  // x0 == NULL with C0 > 0: window mode -- channels [0, C0) of out / raw_out were written by the first source's producer
+  // (b200_conv2d_gn_fwd, block-output form); this launch normalises the second source into channels [C0, C0 + C1)
+  const bool window = x0 == nullptr && C0 > 0 && x1 != nullptr;
+  B200_REQUIRE((window || (x0 && stats0)) && out_bf16, "groupnorm_apply: null x0/stats0/out");
   if (!x1) C1 = 0;
   B200_REQUIRE(!x0_is_bf16 || (x1 == nullptr && raw_out_bf16 == nullptr), "groupnorm_apply: a bf16 input must be the only source");
   B200_REQUIRE(x1 == nullptr || stats1 != nullptr, "groupnorm_apply: second source needs its statistics");
@@ -695,6 +700,10 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
                      (cpg % 8 == 0 && (C1 == 0 || C0 % cpg == 0));   // a group never straddles the two sources
     if (p.cols8 && own && !(env_c8 && atoi(env_c8) == 1)) p.cols8 = 2;
   }
+  p.c_begin = window ? C0 : 0;
+  if (window)
+    B200_REQUIRE(p.cols8 == 2 && resample == 0 && drop_p == 0.f && !x0_is_bf16 && C0 % 8 == 0 && C1 % 8 == 0,
+                 "groupnorm_apply: window mode needs whole-group 8-channel columns, no resampling / dropout");
   static const char* env_rev = getenv("B200_L2_REVERSE");
   p.reverse = (env_rev && atoi(env_rev) == 0) ? 0 : 1;
   B200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "groupnorm_apply: dropout probability %f out of [0,1)", (double)drop_p);
@@ -704,7 +713,7 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.raw = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
   const int work_pix = resample == 1 ? HW / 4 : HW;
-  int ppc = (resample == 1 ? 8192 : x0_is_bf16 ? 65536 : 32768) / C;  // ~128 KB of input per CTA
+  int ppc = (resample == 1 ? 8192 : x0_is_bf16 ? 65536 : 32768) / (window ? C1 : C);  // ~128 KB of input per CTA
   if (ppc < 1) ppc = 1;
   if (ppc > work_pix) ppc = work_pix;
   // small tensors: shrink the per-CTA range (down to ~16 KB of input) until the grid covers the SMs once

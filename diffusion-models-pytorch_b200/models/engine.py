@@ -27,7 +27,10 @@ class Act:
 
     def __init__(self, t, B, H, W, C, stats=None):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
-        self.pre = None      # (GroupNorm module, silu, bf16 NHWC tensor): GN(+SiLU) of this tensor already applied by its producer
+        # GN(+SiLU) of this tensor already applied by its producer (Engine.conv_block_out):
+        # (GroupNorm module, silu, bf16 NHWC tensor [, bf16 raw copy]); with a raw copy both tensors are
+        # [B, H, W, C + C_skip] wide and hold this tensor's part in their first C channels (consumer concatenates a skip)
+        self.pre = None
         self.stats = stats   # [B, C, 2] int64 fixed-point per-(image, channel) sum / sum of squares from the producing kernel
         self.g = None        # fp32 NHWC gradient buffer, created by the first backward contribution (models/backward.py)
 
@@ -49,6 +52,9 @@ class Engine:
     # a block's last conv also emits the GroupNorm(+SiLU) of its output for the NEXT block's norm1 / the output head
     # (b200_conv2d_gn_fwd, block-output form) when that norm has this tensor as its only input; =0: separate launch (A/B)
     fuse_gn1 = bool(int(__import__('os').environ.get('B200_FUSE_GN1', '1')))
+    # ... and when the consumer concatenates a skip connection: the producer writes its part of the normalised and raw
+    # concat operands, the GroupNorm launch of the consumer handles the skip's channels only; =0: full launch (A/B)
+    fuse_gn1_cat = bool(int(__import__('os').environ.get('B200_FUSE_GN1_CAT', '1')))
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -346,9 +352,16 @@ class Engine:
 
     def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
            ss_ld=0, resample=0, drop_p=0.0, drop_seed=0):
-        if (x.pre is not None and x.pre[0] is norm and x.pre[1] == bool(silu) and skip is None and not raw
-                and scale is None and resample == 0 and drop_p == 0.0 and self.tape is None and not self.split):
-            return x.pre[2], None      # the producing conv already applied this GroupNorm (fuse_gn1)
+        if (x.pre is not None and x.pre[0] is norm and x.pre[1] == bool(silu) and scale is None and resample == 0
+                and drop_p == 0.0 and self.tape is None and not self.split):
+            if len(x.pre) == 3 and skip is None and not raw:
+                return x.pre[2], None      # the producing conv already applied this GroupNorm (fuse_gn1)
+            if (len(x.pre) == 4 and skip is not None and skip.stats is not None
+                    and x.pre[2].shape[-1] == x.C + skip.C):
+                # the producer wrote x's part of the normalised and raw concat operands: only the skip's part is left
+                K.groupnorm_apply(None, x.C, None, skip.t, skip.C, skip.stats, x.B, x.H * x.W, x.W, norm.num_groups,
+                                  norm.weight, norm.bias, norm.eps, x.pre[2], silu=silu, raw_out=x.pre[3])
+                return x.pre[2], (x.pre[3] if raw else None)
         seed_dev = self.seed_dev if drop_p > 0 else None
         C = x.C + (skip.C if skip is not None else 0)
         Ho, Wo = x.H, x.W
@@ -639,34 +652,50 @@ class Engine:
 
     def next_gn_ok(self, B, H, W, C, next_gn) -> bool:
         """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu) of its consumer?"""
-        return (next_gn is not None and self.fuse_gn1 and self.fuse_gn2 and self.tape is None and not self.split
-                and next_gn[0].num_channels == C and K.conv2d_gn_ok(B, H, W, C, next_gn[0].num_groups))
+        if next_gn is None or not (self.fuse_gn1 and self.fuse_gn2) or self.tape is not None or self.split:
+            return False
+        norm, skip_C = next_gn[0], (next_gn[2] if len(next_gn) > 2 else 0)
+        if skip_C == 0:
+            return norm.num_channels == C and K.conv2d_gn_ok(B, H, W, C, norm.num_groups)
+        # consumer normalises cat(this, skip): its groups must not straddle the boundary, and the skip's part must take
+        # the per-thread-coefficient path of the streaming kernel in window mode (whole 8-channel columns)
+        Ct = C + skip_C
+        if not self.fuse_gn1_cat or norm.num_channels != Ct or Ct % norm.num_groups or Ct > 2048:
+            return False
+        cpg = Ct // norm.num_groups
+        return (C % cpg == 0 and skip_C % 8 == 0 and C % 8 == 0 and (cpg in (1, 2, 4, 8) or cpg % 8 == 0)
+                and K.conv2d_gn_ok(B, H, W, C, C // cpg))
 
-    def _pre_buf(self, B, H, W, C):
+    def _pre_buf(self, B, H, W, C, kind='pre'):
         """bf16 buffer for a producer-applied GroupNorm: read by the very next block only, so two per shape alternate."""
-        k = (B, H, W, C)
-        n = self._pp_count.get(('pre', k), 0)
-        self._pp_count[('pre', k)] = n + 1
-        return self.buf(f'pre{n & 1}', (B, H, W, C), torch.bfloat16)
+        k = (kind, B, H, W, C)
+        n = self._pp_count.get(k, 0)
+        self._pp_count[k] = n + 1
+        return self.buf(f'{kind}{n & 1}', (B, H, W, C), torch.bfloat16)
 
     def conv_block_out(self, tag, a, B, H, W, Cin, Cout, w, b, taps, next_gn, *, residual: Optional[Act] = None, sc_a=None,
                        sc_C=0) -> Act:
         """Last conv of a block with the consumer's GroupNorm fused: out = conv(a) + b (+ residual | + 1x1 shortcut
         K-blocks over sc_a) as fp32 NHWC with statistics, and out.pre = SiLU?(GN_next(out)) as bf16 (one launch)."""
-        norm, silu = next_gn
+        norm, silu = next_gn[0], next_gn[1]
+        skip_C = next_gn[2] if len(next_gn) > 2 else 0
         out = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
         stats = self.stats_buf(tag, B, Cout)
-        pre = self._pre_buf(B, H, W, Cout)
+        Ct = Cout + skip_C
+        pre = self._pre_buf(B, H, W, Ct)
+        rawc = self._pre_buf(B, H, W, Ct, 'praw') if skip_C else None
+        groups = norm.num_groups if not skip_C else Cout // (Ct // norm.num_groups)
         ws = {}
         if K.conv2d_gn_needs_workspace(H, W):     # several tiles per image: the output statistics double as the exchange workspace
             ws = dict(xstats=stats, xcount=self.stats_buf(tag + '.cnt', B, 1))
         K.conv2d_gn(a, w, Cout, B, H, W, taps, a0_geom=(Cin, H, W, 1), gamma=norm.weight, beta=norm.bias,
-                    groups=norm.num_groups, eps=norm.eps, out_norm=pre, bias=b, silu=silu, out=out,
+                    groups=groups, eps=norm.eps, out_norm=pre, out_norm_ld=Ct if skip_C else 0, out_raw=rawc, bias=b,
+                    silu=silu, out=out,
                     stats=None if ws else stats, residual=None if residual is None else residual.t,
                     res_ld=0 if residual is None else residual.C, a1=sc_a,
                     a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, **ws)
         res = Act(out, B, H, W, Cout, stats)
-        res.pre = (norm, bool(silu), pre)
+        res.pre = (norm, bool(silu), pre, rawc) if skip_C else (norm, bool(silu), pre)
         return res
 
     def resblock_core(self, *args, **kwargs):
@@ -747,14 +776,14 @@ class Engine:
                                   emb=tproj, emb_off=tproj_off, emb_ld=tproj_ld, scale_shift=False, dropout=blk.blk2[2],
                                   emb_linear=blk.proj[1], next_gn=next_gn)
 
-    def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld) -> Act:
+    def resblock_adagn(self, tag, blk, x: Act, skip: Optional[Act], ss, ss_off, ss_ld, next_gn=None) -> Act:
         """models/unet_categorial_adagn.py:44-62 incl. the BigGAN-style up/down variants."""
         return self.resblock_core(tag, x, skip, norm1=blk.blk1[0], conv1=blk.blk1[2], norm2=blk.adagn.gn,
                                   conv2=blk.blk2[2],
                                   shortcut=blk.shortcut if isinstance(blk.shortcut, nn.Conv2d) else None,
                                   emb=ss, emb_off=ss_off, emb_ld=ss_ld, scale_shift=True,
                                   resample={'up': 2, 'down': 1}.get(blk.updown_kind, 0), dropout=blk.blk2[1],
-                                  emb_linear=blk.adagn.proj[1])
+                                  emb_linear=blk.adagn.proj[1], next_gn=next_gn)
 
     # ------------------------------------------------------------------------------------------
     # embedding path

@@ -183,14 +183,17 @@ class UNet(_EngineModel):
                 return None if fused else (blk.norm, False)
             if kind == 'res' and part != 'dec' and not isinstance(blk.shortcut, nn.Conv2d):
                 return blk.blk1[0], True
+            if (kind == 'res' and part == 'dec' and skips and isinstance(blk.shortcut, nn.Conv2d)
+                    and blk.shortcut.kernel_size[0] == 1):
+                return blk.blk1[0], True, skips[-1].C      # consumer normalises cat(x, skip): x's part by its producer
             return None
 
         for k, (kind, name, blk, part) in enumerate(ops[:-1]):
             if part == 'mid' and not eng.pingpong:
                 eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
             if kind == 'res':
-                h = eng.resblock(name, blk, h, skips.pop() if part == 'dec' else None, tproj, offsets[name], tld,
-                                 next_gn=consumer_gn(k, h))
+                skip = skips.pop() if part == 'dec' else None      # before the look-ahead: the consumer takes skips[-1]
+                h = eng.resblock(name, blk, h, skip, tproj, offsets[name], tld, next_gn=consumer_gn(k, h))
                 if part == 'enc':
                     skips.append(h)
             elif kind == 'attn':

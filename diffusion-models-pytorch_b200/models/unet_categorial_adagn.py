@@ -142,37 +142,53 @@ class UNetCategorialAdaGN(_EngineModel):
         h = eng.first_conv('first_conv', self.first_conv, X)
         skips = [h]
 
-        def run_res(name, blk, x, skip=None):
-            return eng.resblock_adagn(name, blk, x, skip, ss, offsets[name], ss_ld)
-
+        # op sequence with consumer look-ahead (as in models/unet.py): a block whose output is the only GroupNorm input of
+        # the next op lets its last conv apply that GroupNorm (Engine.fuse_gn1)
+        ops = []
         for i, stage in enumerate(self.down_blocks):
             for j, blk in enumerate(stage):
-                name = f'down_blocks.{i}.{j}'
-                if isinstance(blk, ResBlock):          # includes ResBlockDownsample, as in the reference
-                    h = run_res(name, blk, h)
-                    skips.append(h)
-                elif isinstance(blk, SelfAttentionBlock):
-                    h = eng.attention(name, blk, h)
-                    skips[-1] = h
-                else:
-                    h = eng.downsample_conv(name, blk, h)
-                    skips.append(h)
-
-        eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
-        h = run_res('bottleneck_block.0', self.bottleneck_block[0], h)
-        h = eng.attention('bottleneck_block.1', self.bottleneck_block[1], h)
-        h = run_res('bottleneck_block.2', self.bottleneck_block[2], h)
-
+                kind = 'res' if isinstance(blk, ResBlock) else 'attn' if isinstance(blk, SelfAttentionBlock) else 'down'
+                ops.append((kind, f'down_blocks.{i}.{j}', blk, 'enc'))
+        for j, blk in enumerate(self.bottleneck_block):
+            ops.append(('res' if isinstance(blk, ResBlock) else 'attn', f'bottleneck_block.{j}', blk, 'mid'))
         for i, stage in enumerate(self.up_blocks):
             for j, blk in enumerate(stage):
-                name = f'up_blocks.{i}.{j}'
-                if isinstance(blk, ResBlockUpsample):
-                    h = run_res(name, blk, h)
-                elif isinstance(blk, ResBlock):
-                    h = run_res(name, blk, h, skips.pop())
-                elif isinstance(blk, SelfAttentionBlock):
-                    h = eng.attention(name, blk, h)
-                else:
-                    h = eng.upsample_conv(name, blk[1], h)
+                kind = ('resup' if isinstance(blk, ResBlockUpsample) else 'res' if isinstance(blk, ResBlock)
+                        else 'attn' if isinstance(blk, SelfAttentionBlock) else 'up')
+                ops.append((kind, f'up_blocks.{i}.{j}', blk, 'dec'))
+        ops.append(('head', 'last_conv', None, 'dec'))
+
+        def consumer_gn(k, x):
+            kind, _, blk, part = ops[k + 1]
+            if kind == 'head':
+                return self.last_conv[0], True
+            if kind == 'attn':      # the one-launch attention block normalises its input itself
+                fused = eng.attn_block and K.attn_block_ok(x.H * x.W, blk.q.out_channels, blk.n_heads, blk.norm.num_groups)
+                return None if fused else (blk.norm, False)
+            if (kind == 'res' and part != 'dec' and not isinstance(blk.shortcut, nn.Conv2d)
+                    and getattr(blk, 'updown_kind', None) is None):
+                return blk.blk1[0], True
+            if (kind == 'res' and part == 'dec' and skips and isinstance(blk.shortcut, nn.Conv2d)
+                    and blk.shortcut.kernel_size[0] == 1 and getattr(blk, 'updown_kind', None) is None):
+                return blk.blk1[0], True, skips[-1].C      # consumer normalises cat(x, skip): x's part by its producer
+            return None
+
+        for k, (kind, name, blk, part) in enumerate(ops[:-1]):
+            if part == 'mid' and not eng.pingpong:
+                eng.pingpong = True      # from here on no output is a skip connection: block outputs alternate between two buffers
+            if kind == 'res' or kind == 'resup':
+                skip = skips.pop() if (part == 'dec' and kind == 'res') else None
+                h = eng.resblock_adagn(name, blk, h, skip, ss, offsets[name], ss_ld, next_gn=consumer_gn(k, h))
+                if part == 'enc':
+                    skips.append(h)
+            elif kind == 'attn':
+                h = eng.attention(name, blk, h, next_gn=consumer_gn(k, h))
+                if part == 'enc':
+                    skips[-1] = h
+            elif kind == 'down':
+                h = eng.downsample_conv(name, blk, h)
+                skips.append(h)
+            else:
+                h = eng.upsample_conv(name, blk[1], h)
 
         return eng.head('last_conv', h, self.last_conv[0], self.last_conv[2], out)

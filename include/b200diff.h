@@ -102,7 +102,9 @@ typedef struct b200_gn_fuse_desc {
   const float* scale;        /* optional per-image rows [B][ss_ld]: y = GN(x) * (1 + scale) + shift */
   const float* shift;
   void* out_norm;            /* bf16 NHWC [B][Ho][Wo][out_norm_ld] (first N columns) */
-  int out_norm_ld;           /* channel stride of out_norm; 0 = N */
+  int out_norm_ld;           /* channel stride of out_norm (and out_raw_bf16); 0 = N */
+  void* out_raw_bf16;        /* block-output form only, optional: bf16 copy of the un-normalised x, same layout as out_norm
+                              * (operand of the consumer's fused 1x1 shortcut when it concatenates a skip connection) */
   int ss_ld;
   int groups;
   int apply_silu;

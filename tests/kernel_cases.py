@@ -1345,6 +1345,40 @@ def case_conv_gnfuse_out():
         want_st = torch.stack([pre.sum(dim=(2, 3)), (pre * pre).sum(dim=(2, 3))], dim=-1)
         ok &= _report(name + ' output statistics', K.stats_to_float(stats), want_st, 1e-3, 5e-2)
         ok &= _report(name + ' fused GN of the output', outn.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+
+    # consumer concatenates a skip connection: the conv writes its part of the normalised + raw concat operands
+    # (channel stride Cout + Cs, groups of (Cout + Cs) / 32 channels), the streaming GroupNorm kernel in window mode
+    # (x0 = None) adds the skip's channels; together they must equal GroupNorm(cat(x, skip))
+    for (B, Cin, Cout, Cs, H) in ((64, 128, 128, 128, 32), (96, 256, 256, 256, 8), (128, 256, 256, 256, 4), (33, 256, 256, 256, 16)):
+        x = _bf16r(_gen(B, Cin, H, H, seed=21))
+        w = _bf16r(_gen(Cout, Cin, 3, 3, seed=22, scale=1.0 / math.sqrt(Cin * 9)))
+        b = _gen(Cout, seed=23)
+        xs = _bf16r(_gen(B, 384, H, H, seed=24))
+        wsc = _bf16r(_gen(Cout, 384, 1, 1, seed=25, scale=1.0 / math.sqrt(384)))
+        skip = _gen(B, H, H, Cs, seed=26) * 1.5 + 0.25                             # fp32 NHWC skip connection
+        Ct = Cout + Cs
+        gamma, beta = 1.0 + 0.1 * _gen(Ct, seed=27), 0.1 * _gen(Ct, seed=28)
+        pre = F.conv2d(x, w, b, padding=1) + F.conv2d(xs, wsc)
+        cat = torch.cat([pre, skip.permute(0, 3, 1, 2)], dim=1)
+        ref = F.silu(F.group_norm(cat, 32, gamma, beta, eps=1e-5))
+        wp = torch.cat([K.pack_weight(w), K.pack_weight(wsc)], dim=1).contiguous()
+        out = torch.full((B, H, H, Cout), float('nan'), device=DEV, dtype=torch.float32)
+        outn = torch.full((B, H, H, Ct), float('nan'), device=DEV, dtype=torch.bfloat16)
+        outr = torch.full((B, H, H, Ct), float('nan'), device=DEV, dtype=torch.bfloat16)
+        stats = K.new_stats(B, Cout, DEV)
+        multi = K.conv2d_gn_needs_workspace(H, H)
+        ws = dict(xstats=stats, xcount=K.new_stats(B, 1, DEV)) if multi else {}
+        cpg = Ct // 32
+        K.conv2d_gn(_nhwc_bf16(x), wp, Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(Cin, H, H, 1), gamma=gamma, beta=beta,
+                    groups=Cout // cpg, eps=1e-5, out_norm=outn, out_norm_ld=Ct, out_raw=outr, bias=b, silu=True, out=out,
+                    stats=None if multi else stats, a1=_nhwc_bf16(xs), a1_geom=(384, H, H, 1), **ws)
+        sst = K.stats_from_float(torch.stack([skip.sum(dim=(1, 2)), (skip * skip).sum(dim=(1, 2))], dim=-1).contiguous())
+        K.groupnorm_apply(None, Cout, None, skip, Cs, sst, B, H * H, H, 32, gamma, beta, 1e-5, outn, silu=True, raw_out=outr)
+        torch.cuda.synchronize()
+        name = f'conv3x3 {Cin}->{Cout} @{H} B={B} -> GN(cat(x, skip {Cs}))'
+        ok &= _report(name + ' raw fp32 output', out.permute(0, 3, 1, 2), pre, rtol=1e-3, atol=1e-3)
+        ok &= _report(name + ' normalised concat operand', outn.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+        ok &= _report(name + ' raw concat operand', outr.permute(0, 3, 1, 2), cat, rtol=1e-2, atol=1e-2)
     return ok
 
 

@@ -437,6 +437,211 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
 }
 
 // ================================================================================================
+// One-launch GroupNorm adjoint for small images (HW <= 256, no resampling): the four-kernel form above is bound by its
+// launch chain there (ncu, CFG UNet at batch 128: coef 4 us -> reduce 14-19 us -> final 5 us -> apply 19-30 us for 3-25 MB
+// of traffic, 128 CTAs at 12 % occupancy on the 8x8 / 4x4 levels).  A CTA owns ALL pixels of one image for a slice of
+// CS channels made of whole groups, so nothing has to be exchanged between CTAs: x (fp32) and g (bf16) are read from
+// HBM ONCE into shared memory, the forward coefficients come straight from the producer's statistics, S1 / S2 are
+// reduced inside the CTA in a fixed order (no atomics), k2 / k3 and the parameter gradients follow, and the second pass
+// runs from shared memory.  Thread (q, prow) owns channel quad q of the slice and pixels prow, prow + R, ... in both
+// passes, so the data needs no barrier of its own.  Same formulas, dropout counters and outputs as the kernels above.
+// ================================================================================================
+__global__ void __launch_bounds__(256, 3) gn_bwd_slab_kernel(const GnBwdParams p, const int CS) {
+  extern __shared__ __align__(16) uint8_t slab_sm[];
+  const int C = p.C0 + p.C1, HW = p.HW;
+  const int n = blockIdx.y, c0 = blockIdx.x * CS;
+  const int nq = CS >> 2;            // channel quads of the slice
+  const int R = 256 / nq;            // pixel rows processed in parallel
+  float* xs = reinterpret_cast<float*>(slab_sm);                              // [HW][CS]
+  __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(xs + (size_t)HW * CS);   // [HW][CS]
+  float* cf = reinterpret_cast<float*>(gs + (size_t)HW * CS);                   // [8][CS]: cA cB rA rB k2 k3 S1 S2
+  float* part = cf + 8 * CS;                                                  // [2][R][CS] per-row partial sums
+  float* cA = cf, *cB = cf + CS, *rA = cf + 2 * CS, *rB = cf + 3 * CS, *k2 = cf + 4 * CS, *k3 = cf + 5 * CS;
+  float* S1 = cf + 6 * CS, *S2 = cf + 7 * CS;
+  const int tid = threadIdx.x;
+  const int q = tid % nq, prow = tid / nq;
+  const bool active = prow < R;
+  const int c = c0 + (q << 2);                 // first channel of this thread's quad (concatenated index)
+  const bool from0 = c < p.C0;
+  const float* xsrc = from0 ? p.x0 + (size_t)n * HW * p.C0 + c : p.x1 + (size_t)n * HW * p.C1 + (c - p.C0);
+  const int sld = from0 ? p.C0 : p.C1;
+  const size_t goff = (size_t)n * HW * C + c;  // offset of (n, pixel 0, c) in the concatenated tensors (g, addend, dx_bf16)
+
+  // ---- 1. x, g -> shared memory (all loads of a thread are issued back to back) ----
+  if (active) {
+    for (int px = prow; px < HW; px += 4 * R) {
+      float4 xv[4];
+      uint2 gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (px + u * R < HW) {
+          xv[u] = bw_ldg4(xsrc + (size_t)(px + u * R) * sld);
+          gv[u] = __ldg(reinterpret_cast<const uint2*>(p.g + goff + (size_t)(px + u * R) * C));
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (px + u * R < HW) {
+          *reinterpret_cast<float4*>(xs + (size_t)(px + u * R) * CS + (q << 2)) = xv[u];
+          *reinterpret_cast<uint2*>(gs + (size_t)(px + u * R) * CS + (q << 2)) = gv[u];
+        }
+    }
+  }
+  // ---- 2. forward coefficients of the slice's channels from the producer statistics ----
+  if (tid < CS) {
+    const int cc = c0 + tid;
+    const long long* st = (cc < p.C0) ? p.st0 + ((size_t)n * p.C0 + cc) * 2 : p.st1 + ((size_t)n * p.C1 + (cc - p.C0)) * 2;
+    const float2 sv = stat_load(st);
+    S1[tid] = sv.x;
+    S2[tid] = sv.y;
+  }
+  __syncthreads();
+  if (tid < CS) {
+    const int cc = c0 + tid;
+    const int g0 = (tid / p.cpg) * p.cpg;
+    float sm = 0.f, qm = 0.f;
+    for (int i = 0; i < p.cpg; ++i) { sm += S1[g0 + i]; qm += S2[g0 + i]; }
+    const float inv_cnt = 1.0f / (float)(HW * p.cpg);
+    const float mean = sm * inv_cnt;
+    const float var = fmaxf(qm * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    float ga = p.gamma ? __ldg(p.gamma + cc) : 1.f;
+    float be = p.beta ? __ldg(p.beta + cc) : 0.f;
+    if (p.scale) {
+      const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + cc);
+      ga *= sc;
+      be = be * sc + __ldg(p.shift + (size_t)n * p.ss_ld + cc);
+    }
+    cA[tid] = rstd * ga;
+    cB[tid] = be - mean * rstd * ga;
+    rA[tid] = rstd;
+    rB[tid] = -mean * rstd;
+  }
+  __syncthreads();
+
+  const bool drop = p.drop_thresh != 0, silu = p.apply_silu != 0;
+  const unsigned long long seed = p.drop_seed + ((drop && p.drop_seed_dev) ? __ldg(p.drop_seed_dev) : 0ull);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, ra = a, rb = a;
+  if (active) {
+    a = *reinterpret_cast<const float4*>(cA + (q << 2)); b = *reinterpret_cast<const float4*>(cB + (q << 2));
+    ra = *reinterpret_cast<const float4*>(rA + (q << 2)); rb = *reinterpret_cast<const float4*>(rB + (q << 2));
+  }
+  // ---- 3. pass 1: S1 = sum dz, S2 = sum dz * xh over the image ----
+  {
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active)
+      for (int px = prow; px < HW; px += R) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + (size_t)px * CS + (q << 2));
+        const uint2 gu = *reinterpret_cast<const uint2*>(gs + (size_t)px * CS + (q << 2));
+        const float4 g4 = make_float4(__uint_as_float(gu.x << 16), __uint_as_float(gu.x & 0xffff0000u),
+                                      __uint_as_float(gu.y << 16), __uint_as_float(gu.y & 0xffff0000u));
+        const uint32_t keep = drop ? dropout_keep4(seed, (unsigned long long)((goff + (size_t)px * C) >> 2), p.drop_thresh) : 15u;
+        float dz[4], xh[4];
+        gn_bwd_dz_core(x, g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+      }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        part[(size_t)prow * CS + (q << 2) + i] = s1[i];
+        part[(size_t)(R + prow) * CS + (q << 2) + i] = s2[i];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < CS) {
+    float u = 0.f, v = 0.f;
+    for (int r = 0; r < R; ++r) { u += part[(size_t)r * CS + tid]; v += part[(size_t)(R + r) * CS + tid]; }
+    S1[tid] = u;
+    S2[tid] = v;
+  }
+  __syncthreads();
+  // ---- 4. k2 / k3 of the groups, parameter gradients ----
+  if (tid < CS) {
+    const int cc = c0 + tid;
+    const int g0 = (tid / p.cpg) * p.cpg;
+    float A = 0.f, Bq = 0.f;
+    for (int i = 0; i < p.cpg; ++i) {
+      const float gp = cA[g0 + i] / rA[g0 + i];     // g' = gamma (1 + scale)
+      A = fmaf(gp, S1[g0 + i], A);
+      Bq = fmaf(gp, S2[g0 + i], Bq);
+    }
+    const float inv_m = 1.0f / (float)(HW * p.cpg);
+    k2[tid] = rA[tid] * A * inv_m;
+    k3[tid] = rA[tid] * Bq * inv_m;
+    const float s1 = S1[tid], s2 = S2[tid];
+    const float sc = p.scale ? 1.f + __ldg(p.scale + (size_t)n * p.ss_ld + cc) : 1.f;
+    if (p.dgamma) atomicAdd(p.dgamma + cc, s2 * sc);
+    if (p.dbeta) atomicAdd(p.dbeta + cc, s1 * sc);
+    if (p.dscale) {
+      const float ga = p.gamma ? __ldg(p.gamma + cc) : 1.f, be = p.beta ? __ldg(p.beta + cc) : 0.f;
+      p.dscale[(size_t)n * p.dss_ld + cc] = ga * s2 + be * s1;
+      p.dshift[(size_t)n * p.dss_ld + cc] = s1;
+    }
+  }
+  __syncthreads();
+  // ---- 5. pass 2: dx = dz*cA - k2 - xh*k3 (+ addend) ----
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 q2 = *reinterpret_cast<const float4*>(k2 + (q << 2)), q3 = *reinterpret_cast<const float4*>(k3 + (q << 2));
+    const float av[4] = {a.x, a.y, a.z, a.w}, q2v[4] = {q2.x, q2.y, q2.z, q2.w}, q3v[4] = {q3.x, q3.y, q3.z, q3.w};
+    float* dst = from0 ? p.dx0 : p.dx1;
+    float* dbase = dst ? (from0 ? dst + (size_t)n * HW * p.C0 + c : dst + (size_t)n * HW * p.C1 + (c - p.C0)) : nullptr;
+    const bool acc = (from0 ? p.acc0 : p.acc1) != 0;
+    for (int px0 = prow; px0 < HW; px0 += 2 * R) {
+      float4 ads[2], olds[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int px = px0 + u * R;
+        if (px < HW) {
+          if (p.addend) ads[u] = bw_ldg4(p.addend + goff + (size_t)px * C);
+          if (!p.dx_bf16 && dbase && acc) olds[u] = *reinterpret_cast<const float4*>(dbase + (size_t)px * sld);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int px = px0 + u * R;
+        if (px >= HW) break;
+        const float4 x = *reinterpret_cast<const float4*>(xs + (size_t)px * CS + (q << 2));
+        const uint2 gu = *reinterpret_cast<const uint2*>(gs + (size_t)px * CS + (q << 2));
+        const float4 g4 = make_float4(__uint_as_float(gu.x << 16), __uint_as_float(gu.x & 0xffff0000u),
+                                      __uint_as_float(gu.y << 16), __uint_as_float(gu.y & 0xffff0000u));
+        const uint32_t keep = drop ? dropout_keep4(seed, (unsigned long long)((goff + (size_t)px * C) >> 2), p.drop_thresh) : 15u;
+        float dz[4], xh[4], dx[4];
+        gn_bwd_dz_core(x, g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dx[i] = fmaf(dz[i], av[i], -q2v[i]) - xh[i] * q3v[i];
+        if (p.addend) { dx[0] += ads[u].x; dx[1] += ads[u].y; dx[2] += ads[u].z; dx[3] += ads[u].w; }
+        if (p.dx_bf16) {
+          uint2 u2;
+          u2.x = pack_bf16x2(dx[0], dx[1]);
+          u2.y = pack_bf16x2(dx[2], dx[3]);
+          *reinterpret_cast<uint2*>(p.dx_bf16 + goff + (size_t)px * C) = u2;
+        } else if (dbase) {
+          if (acc) { dx[0] += olds[u].x; dx[1] += olds[u].y; dx[2] += olds[u].z; dx[3] += olds[u].w; }
+          *reinterpret_cast<float4*>(dbase + (size_t)px * sld) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rs[i] += dx[i];
+      }
+    }
+  }
+  if (p.dx_rowsum || p.dx_colsum) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part[(size_t)prow * CS + (q << 2) + i] = rs[i];
+    }
+    __syncthreads();
+    if (tid < CS) {
+      float u = 0.f;
+      for (int r = 0; r < R; ++r) u += part[(size_t)r * CS + tid];
+      if (p.dx_rowsum) atomicAdd(p.dx_rowsum + (size_t)n * p.rowsum_ld + c0 + tid, u);
+      if (p.dx_colsum) atomicAdd(p.dx_colsum + c0 + tid, u);
+    }
+  }
+}
+
+// ================================================================================================
 // Gradient casts with fused column sums (bias gradients)
 // ================================================================================================
 // fp32 [rows][C] -> bf16 [rows][C]; colsum[c] += sum over rows (optional)
@@ -821,8 +1026,28 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
     B200_CHECK(cudaFuncSetAttribute(gn_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  gn_bwd_coef_kernel<<<d->B, 256, (size_t)2 * C * 4, stream>>>(p);
   const int mode = (p.resample == 0 && (unsigned long long)d->B * d->HW * C < (1ull << 32)) ? (p.C1 == 0 ? 1 : 2) : 0;
+  // small images: everything in one launch, one CTA per (image, slice of whole groups), data read once (gn_bwd_slab_kernel)
+  static const char* env_slab = getenv("B200_GNB_SLAB");      // =0: the four-kernel form everywhere (A/B timing)
+  if (mode != 0 && d->HW <= 256 && !(env_slab && atoi(env_slab) == 0)) {
+    // slice = the fewest whole groups that give >= 32 channels (32 groups per tensor: 1, 2, 4, ... groups divide it evenly)
+    int gsl = 1;
+    while (p.cpg * gsl < 32 && gsl < d->groups && d->groups % (gsl * 2) == 0) gsl *= 2;
+    const int CS = p.cpg * gsl;
+    const int nq = CS / 4, R = 256 / (nq > 0 ? nq : 1);
+    const size_t smem = (size_t)d->HW * CS * 6 + (size_t)(8 + 2 * R) * CS * 4;
+    if (CS % 4 == 0 && nq >= 1 && nq <= 64 && C % CS == 0 && ((size_t)d->HW * CS * 6) % 16 == 0 && smem <= 160 * 1024) {
+      static bool slab_attr = false;
+      if (!slab_attr) {
+        B200_CHECK(cudaFuncSetAttribute(gn_bwd_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        slab_attr = true;
+      }
+      gn_bwd_slab_kernel<<<dim3(C / CS, d->B), 256, smem, stream>>>(p, CS);
+      g_launch_count += 1;
+      return check_cuda(cudaGetLastError(), "gn_bwd slab kernel launch");
+    }
+  }
+  gn_bwd_coef_kernel<<<d->B, 256, (size_t)2 * C * 4, stream>>>(p);
   if (mode == 1) gn_bwd_reduce_kernel<1><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
   else if (mode == 2) gn_bwd_reduce_kernel<2><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);
   else gn_bwd_reduce_kernel<0><<<grid, 256, (size_t)2 * C * 4, stream>>>(p);

@@ -651,7 +651,10 @@ class Engine:
         return a2
 
     def next_gn_ok(self, B, H, W, C, next_gn) -> bool:
-        """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu) of its consumer?"""
+        """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu[, C_skip]) of its
+        consumer?  Every eligible layer takes the fused form: a per-layer policy derived from cold-cache ncu launch lists
+        (no fusion for 32x32 layers that also stream a residual, no concat form below 16x16) was A/B-timed on one box
+        and lost to `all layers` inside the sampling graph (DDIM-50 1195.0 vs 1197.0 images/s; none: 1178)."""
         if next_gn is None or not (self.fuse_gn1 and self.fuse_gn2) or self.tape is not None or self.split:
             return False
         norm, skip_C = next_gn[0], (next_gn[2] if len(next_gn) > 2 else 0)

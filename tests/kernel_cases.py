@@ -773,6 +773,12 @@ def case_groupnorm_bwd():
     ok &= _gn_bwd_case('gn_bwd nearest-up C256 8x8', 2, 8, 8, 256, 0, resample=2)
     ok &= _gn_bwd_case('gn_bwd C64 4x4 eps 1e-6', 5, 4, 4, 64, 0, eps=1e-6)
     ok &= _gn_bwd_case('gn_bwd cat 1024+512 8x8', 1, 8, 8, 1024, 512)
+    # one-launch slab form (HW <= 256): concatenated sources with dropout + addend, AdaGN with dropout, a 32x32 pair that
+    # keeps the four-kernel form covered with the same options
+    ok &= _gn_bwd_case('gn_bwd cat 256+256 4x4 dropout addend', 6, 4, 4, 256, 256, drop_p=0.1, addend=True)
+    ok &= _gn_bwd_case('gn_bwd adagn C512 8x8 dropout', 3, 8, 8, 512, 0, adagn=True, drop_p=0.2)
+    ok &= _gn_bwd_case('gn_bwd adagn cat 128+128 16x16 bf16 out + rowsum', 2, 16, 16, 128, 128, adagn=True, bf16_out=True)
+    ok &= _gn_bwd_case('gn_bwd adagn cat 128+128 32x32 dropout addend', 2, 32, 32, 128, 128, adagn=True, drop_p=0.1, addend=True)
     return ok
 
 

@@ -169,6 +169,8 @@ def lib():
     L.b200_attn_block_fwd.restype = c_int
     L.b200_conv3x3_first.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p]
+    L.b200_first_split.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.b200_first_split.restype = c_int
     L.b200_groupnorm_apply_fwd.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                            c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                                            c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -241,7 +243,7 @@ PRECISE_SYMBOLS = ('b200_split_cast', 'b200_groupnorm_apply_split_fwd', 'b200_so
 
 EXPORTED_SYMBOLS = BACKWARD_SYMBOLS + PRECISE_SYMBOLS + (
     'b200_version', 'b200_last_error', 'b200_launch_count', 'b200_conv2d_fwd', 'b200_conv2d_gn_fwd', 'b200_attn_block_fwd', 'b200_conv3x3_first',
-    'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
+    'b200_first_split', 'b200_groupnorm_silu_fwd', 'b200_groupnorm_apply_fwd', 'b200_cast_bf16', 'b200_avgpool2_f32', 'b200_upsample2_f32', 'b200_attention_fwd',
     'b200_time_embed', 'b200_sampler_step', 'b200_diffuse', 'b200_gemm_batched', 'b200_conv2d_wgrad',
     'b200_attention_fwd_lse', 'b200_attention_bwd',
 )
@@ -496,11 +498,12 @@ def conv2d_gn_needs_workspace(Ho, Wo) -> bool:
 
 def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups, eps, out_norm, bias=None, rowadd=None,
               rowadd_ld=0, scale=None, shift=None, ss_ld=0, silu=True, xstats=None, xcount=None, out=None, stats=None,
-              residual=None, res_ld=0, a1=None, a1_geom=None, tap1=(0, 0, 0), out_norm_ld=0, out_raw=None):
+              residual=None, res_ld=0, a1=None, a1_geom=None, tap1=(0, 0, 0), out_norm_ld=0, out_raw=None, alg_macs=None):
     """b200_conv2d_gn_fwd: out_norm = SiLU(GN(conv(a0) + bias + rowadd)) as the bf16 NHWC operand of the next convolution.
     Eligibility (`conv2d_gn_ok`): a tile must hold whole images (Ho*Wo in {16, 64, 256}; 512 / 1024 with workspaces),
     N % 128 == 0, power-of-two channels per group <= 32.
-    out=None: nothing else is written (conv1 -> norm2).  out = fp32 NHWC tensor: block-output form -- x = conv + bias
+    out=None: nothing else is written (conv1 -> norm2; or a block output whose fp32 form nobody reads: a1 = fused 1x1
+    shortcut, out_raw = its bf16 copy at the consumer's concat stride).  out = fp32 NHWC tensor: block-output form -- x = conv + bias
     (+ residual) goes to `out` with its statistics in `stats` (multi-tile images: in `xstats`), GN(x) to out_norm;
     a1 = second source (the fused 1x1 shortcut's K-blocks)."""
     _need_cuda(a0, w_packed, out_norm)
@@ -541,8 +544,8 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
     g.out_norm_ld = out_norm_ld
     if out_raw is not None:
         _need_cuda(out_raw)
-        if out is None or out_raw.dtype != torch.bfloat16:
-            raise RuntimeError('conv2d_gn: out_raw (bf16) needs the block-output form (out=...)')
+        if out_raw.dtype != torch.bfloat16 or (out is None and (rowadd is not None or scale is not None)):
+            raise RuntimeError('conv2d_gn: out_raw must be bf16 and, without `out`, takes no embedding row / scale / shift')
     g.out_raw_bf16 = _ptr(out_raw)
     _need_stats(xstats, xcount)
     if conv2d_gn_needs_workspace(Ho, Wo) and (xstats is None or xcount is None or xstats.numel() < B * N * 2
@@ -550,7 +553,8 @@ def conv2d_gn(a0, w_packed, N, B, Ho, Wo, taps0, *, a0_geom, gamma, beta, groups
         raise RuntimeError('conv2d_gn: images of 512 / 1024 pixels need zeroed int64 workspaces xstats [B, N, 2] and xcount [B]')
     g.xstats, g.xcount = _ptr(xstats), _ptr(xcount)
     _launch('conv_gemm', lambda: _check(lib().b200_conv2d_gn_fwd(ctypes.byref(d), ctypes.byref(g), _stream()),
-                                        'conv2d_gn_fwd'), flops=2.0 * B * Ho * Wo * N * d.w_K)
+                                        'conv2d_gn_fwd'),
+            flops=2.0 * (alg_macs if alg_macs is not None else float(B) * Ho * Wo * N * d.w_K))
     return out_norm
 
 
@@ -563,6 +567,20 @@ def conv3x3_first(x, w, bias, out, stats=None):
             lambda: _check(lib().b200_conv3x3_first(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(),
                                                     _ptr(stats), B, Cin, H, W, Cout, _stream()), 'conv3x3_first'),
             flops=2.0 * B * H * W * Cout * Cin * 9, nbytes=4.0 * B * H * W * (Cin + Cout))
+    return out
+
+
+def first_split(x, out):
+    """b200_first_split: fp32 NCHW image -> bf16 NHWC [B, H, W, 64] pixels [hi | lo | hi | 0 ...], the tensor-core operand
+    of the first convolution (weights: pack mode 4, tap_ld = 64)."""
+    _need_cuda(x, out)
+    B, Cin, H, W = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError('first_split: x must be a contiguous float32 [B, Cin, H, W] tensor')
+    if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != B * H * W * 64:
+        raise RuntimeError('first_split: out must be a contiguous bfloat16 [B, H, W, 64] tensor')
+    _launch('first_split', lambda: _check(lib().b200_first_split(x.data_ptr(), out.data_ptr(), B, Cin, H, W, _stream()),
+                                          'first_split'), nbytes=4.0 * x.numel() + 2.0 * out.numel())
     return out
 
 
@@ -980,13 +998,16 @@ def to_uint8_hwc(x, out=None):
     return out
 
 
-def pack_entry_bytes(src, dst, Co, Ci, taps, mode, row0=0, col0=0, ld=0, src2=None):
-    """One b200_pack_entry as bytes (3 pointers, 8 ints).  mode 3 = FP32-mode split operand [hi | hi | lo] per tap."""
+def pack_entry_bytes(src, dst, Co, Ci, taps, mode, row0=0, col0=0, ld=0, src2=None, tap_ld=0):
+    """One b200_pack_entry as bytes (3 pointers, 8 ints).  mode 3 = FP32-mode split operand [hi | hi | lo] per tap;
+    mode 4 = the same with a tap stride of tap_ld columns (first convolution on 64-channel split pixels)."""
     import struct
-    if mode == 3 and taps > 9:
-        raise RuntimeError('pack mode 3 (FP32 mode) supports at most 9 taps')
+    if mode >= 3 and taps > 9:
+        raise RuntimeError('pack modes 3 / 4 (split operands) support at most 9 taps')
+    if mode == 4 and tap_ld < 3 * Ci:
+        raise RuntimeError('pack mode 4 needs tap_ld >= 3 * Ci')
     return struct.pack('<3Q8i', src.data_ptr(), 0 if src2 is None else src2.data_ptr(), dst.data_ptr(), Co, Ci, taps, mode,
-                       row0, col0, ld, 0)
+                       row0, col0, ld, tap_ld)
 
 
 def pack_weights(table_dev, n_entries):

@@ -39,9 +39,10 @@ struct ConvKParams {
   void* gn_out;
   int gn_out_ld;   // channel stride of gn_out (>= N: the normalised copy may be a column window of a wider tensor)
   int gn_raw;      // 1: conv2-style use -- the fp32 result (+ residual) is ALSO written to `out` (+ `stats`), see below
-  void* gn_rawcopy;  // gn_raw only, optional: bf16 copy of the un-normalised result, laid out like gn_out (the operand of
+  void* gn_rawcopy;  // optional: bf16 copy of the un-normalised result, laid out like gn_out (the operand of
                      // the consumer's fused 1x1 shortcut when the consumer concatenates a skip connection)
   int gn_ss_ld, gn_lg_cpg, gn_silu;
+  int gn_late_out;   // multi-tile block-output form: write the fp32 output AFTER the statistics arrival (see conv_epilogue_gnfuse)
   int gn_cl;     // tiles (= co-scheduled CTAs) per image in the multi-tile variant of the fused epilogue, else 0
   long long* gn_xstats;            // multi-tile variant: zeroed [B][N][2] int64 statistics of the conv output
   unsigned long long* gn_xcount;   // multi-tile variant: zeroed per-image arrival counters
@@ -536,6 +537,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 // group sums read through L2 (written by other SMs during this kernel: no read-only / L1 path)
 __device__ __forceinline__ float2 stat_load_group_cg(const long long* pair, int cnt) {
   long long a = 0, b = 0;
@@ -608,9 +614,11 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
     }
     if (RAW) {
       tmem_st_x32(taddr + (uint32_t)ch, v);      // pass 2 reads the final values
-      char* wp = wbase + (long long)ch * wst;
+      if (!(MULTI && p.gn_late_out)) {
+        char* wp = wbase + (long long)ch * wst;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
+      }
     }
   }
   if (RAW) {
@@ -645,15 +653,35 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1]; b += ps2[i][0] + ps2[i][1]; }
     stat_add(p.gn_xstats + ((size_t)n * p.N + c) * 2, a, b);
-    __threadfence();
+    // Arrival: the warp's 64 reductions are ordered before lane 0's release (bar.warp.sync + cumulativity), so one
+    // release-add replaces a gpu-scope fence by all 32 lanes.  In the block-output form the fp32 output is written
+    // AFTER the arrival (re-read from TMEM): a fence in front of the arrival would otherwise wait for the 128 output
+    // stores of this warp, and the stores now fill the time the other tiles of the image need to arrive
+    // (ncu, 128->128 @32x32 + residual: MEMBAR / ERRBAR / CCTL.IVALL of the first version = 17 % of the warp samples).
     __syncwarp();
+    unsigned long long* cnt = p.gn_xcount + n;
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(cnt), "l"(1ULL) : "memory");
+    if (RAW && p.gn_late_out) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i >= nch) continue;
+        const int ch = half * 32 + 64 * i;
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(taddr + (uint32_t)ch, v);
+        tmem_ld_wait();
+        char* wp = wbase + (long long)ch * wst;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
+      }
+    }
     if ((threadIdx.x & 31) == 0) {
-      unsigned long long* cnt = p.gn_xcount + n;
-      atomicAdd(cnt, 1ULL);
       const unsigned long long target = (unsigned long long)(8 * p.gn_cl);
       uint64_t t0 = 0;
       uint32_t spins = 0;
-      while (ld_acquire_u64(cnt) < target) {
+      // relaxed polling (an acquire load invalidates L1 on every iteration), one acquire fence at the end
+      while (ld_relaxed_u64(cnt) < target) {
         if ((++spins & 0x3ff) == 0) {
           const uint64_t now = globaltimer_ns();
           if (t0 == 0) t0 = now;
@@ -663,6 +691,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
           }
         }
       }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncwarp();
     const int g0 = (c >> p.gn_lg_cpg) << p.gn_lg_cpg;
@@ -719,7 +748,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
   const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
   __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.gn_out_ld + c;
   const int ost = p.gn_out_ld * 2;    // bytes between consecutive pixels of the NHWC output
-  const bool rawcopy = RAW && p.gn_rawcopy != nullptr;
+  const bool rawcopy = p.gn_rawcopy != nullptr;     // without RAW: a block output nobody reads as fp32 (decoder blocks)
   __nv_bfloat16* const rcbase = rawcopy ? reinterpret_cast<__nv_bfloat16*>(p.gn_rawcopy) + pix0 * (size_t)p.gn_out_ld + c : nullptr;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -732,9 +761,10 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
     char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
     if (rawcopy) {
       char* rp = reinterpret_cast<char*>(rcbase) + (long long)ch * ost;
+      const float radd = RAW ? 0.f : bias_c;      // RAW: pass 1 stored the final values; else the accumulators lack the bias
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) = __float2bfloat16_rn(__uint_as_float(v[j]));
+        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) = __float2bfloat16_rn(__uint_as_float(v[j]) + radd);
     }
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {

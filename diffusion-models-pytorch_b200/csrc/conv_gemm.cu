@@ -462,13 +462,17 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     p.gn_ss_ld = g->ss_ld; p.gn_lg_cpg = ilog2(cpg); p.gn_silu = g->apply_silu; p.gn_eps = g->eps;
     p.gn_out_ld = g->out_norm_ld ? g->out_norm_ld : d->N;
     p.gn_raw = d->out != nullptr ? 1 : 0;
-    B200_REQUIRE(g->out_raw_bf16 == nullptr || (p.gn_raw && ((uintptr_t)g->out_raw_bf16 & 15) == 0),
-                 "conv2d_gn_fwd: out_raw_bf16 needs the block-output form (d->out) and 16-byte alignment");
+    // raw bf16 copy: block-output form, or (d->out == NULL) a block output nobody reads as fp32 -- no embedding row then
+    B200_REQUIRE(g->out_raw_bf16 == nullptr || (((uintptr_t)g->out_raw_bf16 & 15) == 0 &&
+                                                (p.gn_raw || (d->rowadd == nullptr && g->scale == nullptr))),
+                 "conv2d_gn_fwd: out_raw_bf16 needs 16-byte alignment and no embedding row / scale / shift");
     p.gn_rawcopy = g->out_raw_bf16;
     if (p.gn_raw && gn_cl)
       B200_REQUIRE(d->stats == nullptr || d->stats == g->xstats,
                    "conv2d_gn_fwd: multi-tile images accumulate the output statistics in xstats (pass stats = xstats or NULL)");
     p.gn_cl = gn_cl;
+    static const char* env_late = getenv("B200_GN_LATE_OUT");      // =0: fp32 output stores before the statistics arrival (A/B)
+    p.gn_late_out = !(env_late && atoi(env_late) == 0);
     if (gn_cl) {
       // the gn_cl tiles of an image are taken in the same iteration by gn_cl consecutive CTAs (tile = blockIdx.x + i *
       // gridDim.x, both multiples of gn_cl) which wait for each other: cooperative launch = all CTAs co-resident

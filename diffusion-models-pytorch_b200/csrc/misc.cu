@@ -453,6 +453,55 @@ extern "C" int b200_conv3x3_first(const float* x, const float* w, const float* b
   }
 }
 
+// Input image -> the tensor-core form of the first convolution (models/unet.py:72,123 on K1 instead of FP32 FMAs):
+// NCHW fp32 [B][Cin][H][W] -> bf16 NHWC [B][H][W][64], channels [hi(Cin) | lo(Cin) | hi(Cin) | 0 ...] with
+// hi = bf16(x), lo = bf16(x - hi).  Against weights packed [w_hi | w_hi | w_lo | 0 ...] per tap (pack mode 4) the
+// 64-channel contraction evaluates x*w as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo: fp32-grade products on the bf16 tensor
+// pipe (the image is the one operand of the network that is NOT rounded to bf16 by the reference-faithful path).
+// Eight threads per pixel, one 16-byte store each: a warp writes 512 contiguous bytes.
+namespace b200 {
+__global__ void __launch_bounds__(256) first_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          long long npix, int HW, int Cin) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long pix = gid >> 3;
+  if (pix >= npix) return;
+  const int part = (int)(gid & 7);
+  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+  if (part * 8 < 3 * Cin) {
+    const long long n = pix / HW;
+    const long long base = n * (long long)Cin * HW + (pix - n * HW);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = part * 8 + j;
+      float r = 0.f;
+      if (k < 3 * Cin) {
+        const int kind = k / Cin, c = k - kind * Cin;
+        const float f = __ldg(x + base + (long long)c * HW);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+        r = kind == 1 ? f - __bfloat162float(hi) : __bfloat162float(hi);
+      }
+      v[j] = __float2bfloat16_rn(r);
+    }
+    u = *reinterpret_cast<const uint4*>(v);
+  }
+  *reinterpret_cast<uint4*>(out + gid * 8) = u;
+}
+}  // namespace b200
+
+extern "C" int b200_first_split(const float* x, void* out, int B, int Cin, int H, int W, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_REQUIRE(x && out, "first_split: null pointer");
+  B200_REQUIRE(Cin >= 1 && 3 * Cin <= 64, "first_split: Cin=%d must be in [1,21]", Cin);
+  B200_REQUIRE(((uintptr_t)out & 15) == 0, "first_split: out must be 16-byte aligned");
+  const long long npix = (long long)B * H * W;
+  const long long ctas = (npix * 8 + 255) / 256;
+  B200_REQUIRE(ctas <= 0x7fffffffLL, "first_split: tensor too large");
+  b200::first_split_kernel<<<(unsigned)ctas, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), npix, H * W, Cin);
+  ++g_launch_count;
+  return check_cuda(cudaGetLastError(), "first_split_kernel launch");
+}
+
 extern "C" int b200_cast_bf16(const float* x, void* out, int B, int H, int W, int C, int parity_split, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_REQUIRE(x && out, "cast_bf16: null pointer");

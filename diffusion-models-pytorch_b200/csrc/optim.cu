@@ -120,6 +120,8 @@ extern "C" int b200_optimizer_step(const b200_optim_desc* d, void* stream_) {
 //   mode 1 (data-gradient operand) dst[row0 + ci][col0 + (taps-1-tap)*Co + co] = src[co][ci][tap]   (flipped taps)
 //   mode 2 (fp32 bias sum)         dstf[i] = src[i] + src2[i]                  (conv bias + fused-shortcut bias)
 //   mode 3 (FP32-mode operand)     dst[row0 + co][col0 + tap*3*Ci + {0, Ci, 2Ci} + ci] = {hi, hi, lo}(src[co][ci][tap])
+//   mode 4 (first-conv operand)    as mode 3 with a tap stride of tap_ld columns (b200_first_split's 64-channel pixels;
+//                                  the columns in between are never written: the caller zero-fills dst once)
 // Replaces ~1000 tiny torch permute / cast / cat kernels per training step.
 // ================================================================================================
 namespace b200 {
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_entry
     return;
   }
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
-  if (e.taps > PW_MAX_TAPS && e.mode == 3) return;   // rejected on the host (b200_pack_weights cannot see device tables)
+  if (e.taps > PW_MAX_TAPS && e.mode >= 3) return;   // rejected on the host (b200_pack_weights cannot see device tables)
   if (e.taps > PW_MAX_TAPS) {   // generic gather (no layer of the supported families takes it)
     const long long per = (total + ctas_per_entry - 1) / ctas_per_entry;
     const long long j0 = part * per, j1 = min(total, j0 + per);
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_entry
           for (int tap = 0; tap < taps; ++tap)
             drow[(long long)tap * e.Ci + tx] = __float2bfloat16_rn(tile[r * PW_LD + tx * taps + tap]);
       }
-    } else if (e.mode == 3) {
+    } else if (e.mode >= 3) {
       // FP32 mode (precise.cu): weight side of the 3-term split product, per tap [w_hi | w_hi | w_lo]:
       // dst[row0 + co][col0 + tap*3*Ci + {0, Ci, 2*Ci} + ci]
       for (int r = ty; r < nco; r += 8) {
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_entry
             const float w = tile[r * PW_LD + tx * taps + tap];
             const __nv_bfloat16 hi = __float2bfloat16_rn(w);
             const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-            __nv_bfloat16* d3 = drow + (long long)tap * 3 * e.Ci + tx;
+            __nv_bfloat16* d3 = drow + (long long)tap * (e.mode == 4 ? e.tap_ld : 3 * e.Ci) + tx;
             d3[0] = hi; d3[e.Ci] = hi; d3[2 * e.Ci] = lo;
           }
       }

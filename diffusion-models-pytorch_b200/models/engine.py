@@ -55,6 +55,13 @@ class Engine:
     # ... and when the consumer concatenates a skip connection: the producer writes its part of the normalised and raw
     # concat operands, the GroupNorm launch of the consumer handles the skip's channels only; =0: full launch (A/B)
     fuse_gn1_cat = bool(int(__import__('os').environ.get('B200_FUSE_GN1_CAT', '1')))
+    # ... and when nobody reads the fp32 form of such a block output (decoder blocks feeding a concatenating block or the
+    # output head: they read the producer-applied bf16 tensors only) it is not written at all; =0: always written (A/B)
+    skip_dead_out = bool(int(__import__('os').environ.get('B200_SKIP_DEAD_OUT', '1')))
+    # first convolution on the tensor cores (64-channel hi / lo / hi split pixels + the first block's GroupNorm fused).
+    # Off by default: same-box A/B (DDIM-50, batch 256) 1205.6 / 1202.5 images/s with it, 1205.8 / 1208.4 without -- the
+    # 32x32 multi-tile fused epilogue costs what the FP32-FMA kernel + its GroupNorm launch cost.  =1 enables it (A/B).
+    first_tc = bool(int(__import__('os').environ.get('B200_FIRST_TC', '0')))
 
     def __init__(self, model: nn.Module):
         self.model = model
@@ -651,7 +658,7 @@ class Engine:
         return a2
 
     def next_gn_ok(self, B, H, W, C, next_gn) -> bool:
-        """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu[, C_skip]) of its
+        """May the conv producing a [B, H, W, C] block output also apply `next_gn` = (GroupNorm, silu[, C_skip[, dead]]) of its
         consumer?  Every eligible layer takes the fused form: a per-layer policy derived from cold-cache ncu launch lists
         (no fusion for 32x32 layers that also stream a residual, no concat form below 16x16) was A/B-timed on one box
         and lost to `all layers` inside the sampling graph (DDIM-50 1195.0 vs 1197.0 images/s; none: 1178)."""
@@ -677,13 +684,16 @@ class Engine:
         return self.buf(f'{kind}{n & 1}', (B, H, W, C), torch.bfloat16)
 
     def conv_block_out(self, tag, a, B, H, W, Cin, Cout, w, b, taps, next_gn, *, residual: Optional[Act] = None, sc_a=None,
-                       sc_C=0) -> Act:
+                       sc_C=0, alg_macs=None) -> Act:
         """Last conv of a block with the consumer's GroupNorm fused: out = conv(a) + b (+ residual | + 1x1 shortcut
         K-blocks over sc_a) as fp32 NHWC with statistics, and out.pre = SiLU?(GN_next(out)) as bf16 (one launch)."""
         norm, silu = next_gn[0], next_gn[1]
         skip_C = next_gn[2] if len(next_gn) > 2 else 0
-        out = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
+        # next_gn[3]: the consumer reads only `pre` / `praw` (output head, concatenating decoder block with a 1x1 shortcut)
+        # and the output is no skip connection -> without a residual the fp32 form and its statistics are never written
+        dead = len(next_gn) > 3 and next_gn[3] and residual is None and self.skip_dead_out
         stats = self.stats_buf(tag, B, Cout)
+        out = None if dead else self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
         Ct = Cout + skip_C
         pre = self._pre_buf(B, H, W, Ct)
         rawc = self._pre_buf(B, H, W, Ct, 'praw') if skip_C else None
@@ -694,10 +704,10 @@ class Engine:
         K.conv2d_gn(a, w, Cout, B, H, W, taps, a0_geom=(Cin, H, W, 1), gamma=norm.weight, beta=norm.bias,
                     groups=groups, eps=norm.eps, out_norm=pre, out_norm_ld=Ct if skip_C else 0, out_raw=rawc, bias=b,
                     silu=silu, out=out,
-                    stats=None if ws else stats, residual=None if residual is None else residual.t,
+                    stats=None if (ws or dead) else stats, residual=None if residual is None else residual.t,
                     res_ld=0 if residual is None else residual.C, a1=sc_a,
-                    a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, **ws)
-        res = Act(out, B, H, W, Cout, stats)
+                    a1_geom=(sc_C, H, W, 1) if sc_a is not None else None, alg_macs=alg_macs, **ws)
+        res = Act(out, B, H, W, Cout, None if dead else stats)
         res.pre = (norm, bool(silu), pre, rawc) if skip_C else (norm, bool(silu), pre)
         return res
 
@@ -849,9 +859,33 @@ class Engine:
         K.conv2d(semb, w, w.shape[0], S, 1, 1, K.taps_1x1(), a0_geom=(m * E, 1, 1, 1), bias=b, out=proj)
         return proj
 
-    def first_conv(self, tag, conv: nn.Conv2d, X) -> Act:
-        """The Cin <= 4 input convolution (models/unet.py:72,123): NCHW fp32 image -> fp32 NHWC residual stream."""
-        B, _, H, W = X.shape
+    def first_conv(self, tag, conv: nn.Conv2d, X, next_gn=None) -> Act:
+        """The Cin <= 4 input convolution (models/unet.py:72,123): NCHW fp32 image -> fp32 NHWC residual stream.
+        Inference with Cout % 128 == 0: on the tensor cores -- the image becomes 64-channel bf16 pixels [hi | lo | hi | 0..]
+        (K.first_split) against weights [w_hi | w_hi | w_lo | 0..] per tap, i.e. fp32-grade products, and the conv also
+        applies `next_gn` (the first ResBlock's norm1) when eligible.  Otherwise (training, FP32 mode, narrow nets) the
+        direct FP32 kernel."""
+        B, Cin, H, W = X.shape
+        Cout = conv.out_channels
+        if (self.first_tc and self.tape is None and not self.split and Cout % 128 == 0 and 3 * Cin <= 64
+                and conv.kernel_size == (3, 3) and X.dtype == torch.float32 and X.is_contiguous()):
+            key = ('first_tc', tag)
+            hit = self._pt.get(key)
+            if hit is None:
+                w = torch.zeros((Cout, 9 * 64), dtype=torch.bfloat16, device=self.device)
+                w, = self.pack_table(key, (w,), [K.pack_entry_bytes(conv.weight, w, Cout, Cin, 9, 4, ld=9 * 64, tap_ld=64)])
+            else:
+                w, = hit[0]
+            a = self.buf(tag + '.split', (B, H, W, 64), torch.bfloat16)
+            K.first_split(X, a)
+            if self.next_gn_ok(B, H, W, Cout, next_gn):
+                return self.conv_block_out(tag, a, B, H, W, 64, Cout, w, conv.bias, K.taps_3x3_s1(), next_gn,
+                                           alg_macs=float(B) * H * W * Cout * 9 * Cin)
+            h0 = self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
+            st0 = self.stats_buf(tag, B, Cout)
+            K.conv2d(a, w, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(64, H, W, 1), bias=conv.bias,
+                     alg_macs=float(B) * H * W * Cout * 9 * Cin, out=h0, out_mode=K.OUT_F32_NHWC, stats=st0)
+            return Act(h0, B, H, W, Cout, st0)
         h0 = self.buf(tag + '.out', (B, H, W, conv.out_channels), torch.float32)
         st0 = self.stats_buf(tag, B, conv.out_channels)
         K.conv3x3_first(X, conv.weight, conv.bias, h0, st0)
@@ -868,7 +902,7 @@ class Engine:
         """GroupNorm -> SiLU -> 3x3 conv to the few output channels, written as the reference's NCHW fp32."""
         a, _ = self.gn(tag, h, None, norm)
         if out is None:
-            out = torch.empty((h.B, conv.out_channels, h.H, h.W), dtype=torch.float32, device=h.t.device)
+            out = torch.empty((h.B, conv.out_channels, h.H, h.W), dtype=torch.float32, device=a.device)
         self.conv3x3(tag + '.c', a, h.B, h.H, h.W, h.C, conv, out_mode=K.OUT_F32_NCHW, out=out)
         if self.tape is not None:
             self.tape.append(dict(kind='head', tag=tag, x=h, a=a, norm=norm, conv=conv))

@@ -139,8 +139,7 @@ class UNetCategorialAdaGN(_EngineModel):
         ss, ss_ld = eng.embed(T, y, B, self.time_embed[0], self.time_embed[1], self.time_embed[3], self.class_embed,
                               [blk.adagn.proj[1] for _, blk in res_blocks])
 
-        h = eng.first_conv('first_conv', self.first_conv, X)
-        skips = [h]
+        skips = []
 
         # op sequence with consumer look-ahead (as in models/unet.py): a block whose output is the only GroupNorm input of
         # the next op lets its last conv apply that GroupNorm (Engine.fuse_gn1)
@@ -160,8 +159,9 @@ class UNetCategorialAdaGN(_EngineModel):
 
         def consumer_gn(k, x):
             kind, _, blk, part = ops[k + 1]
-            if kind == 'head':
-                return self.last_conv[0], True
+            dead = k >= 0 and ops[k][3] != 'enc'      # the producer's fp32 output is no skip connection: `head` / a concatenating
+            if kind == 'head':             # block read only the producer-applied bf16 forms, so it need not be written
+                return self.last_conv[0], True, 0, dead
             if kind == 'attn':      # the one-launch attention block normalises its input itself
                 fused = eng.attn_block and K.attn_block_ok(x.H * x.W, blk.q.out_channels, blk.n_heads, blk.norm.num_groups)
                 return None if fused else (blk.norm, False)
@@ -170,8 +170,12 @@ class UNetCategorialAdaGN(_EngineModel):
                 return blk.blk1[0], True
             if (kind == 'res' and part == 'dec' and skips and isinstance(blk.shortcut, nn.Conv2d)
                     and blk.shortcut.kernel_size[0] == 1 and getattr(blk, 'updown_kind', None) is None):
-                return blk.blk1[0], True, skips[-1].C      # consumer normalises cat(x, skip): x's part by its producer
+                return blk.blk1[0], True, skips[-1].C, dead      # consumer normalises cat(x, skip): x's part by its producer
             return None
+
+        # the first convolution's consumer is ops[0]; on the tensor-core path it applies that block's norm1 too
+        h = eng.first_conv('first_conv', self.first_conv, X, next_gn=consumer_gn(-1, None) if ops[0][0] == 'res' else None)
+        skips.append(h)
 
         for k, (kind, name, blk, part) in enumerate(ops[:-1]):
             if part == 'mid' and not eng.pingpong:

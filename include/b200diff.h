@@ -103,8 +103,9 @@ typedef struct b200_gn_fuse_desc {
   const float* shift;
   void* out_norm;            /* bf16 NHWC [B][Ho][Wo][out_norm_ld] (first N columns) */
   int out_norm_ld;           /* channel stride of out_norm (and out_raw_bf16); 0 = N */
-  void* out_raw_bf16;        /* block-output form only, optional: bf16 copy of the un-normalised x, same layout as out_norm
-                              * (operand of the consumer's fused 1x1 shortcut when it concatenates a skip connection) */
+  void* out_raw_bf16;        /* optional: bf16 copy of the un-normalised x, same layout as out_norm (operand of the
+                              * consumer's fused 1x1 shortcut when it concatenates a skip connection); with d->out == NULL
+                              * (a block output nobody reads as fp32) no embedding row / scale / shift may be given */
   int ss_ld;
   int groups;
   int apply_silu;
@@ -122,6 +123,12 @@ int b200_conv2d_gn_fwd(const b200_conv_desc* d, const b200_gn_fuse_desc* g, void
 int b200_conv3x3_first(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc,
                        long long* stats /* optional [B][Cout][2] int64, pre-zeroed, as in b200_conv_desc.stats */,
                        int B, int Cin, int H, int W, int Cout, void* stream);
+
+/* The same convolution on the tensor cores (inference): b200_first_split writes the image as bf16 NHWC [B][H][W][64]
+ * pixels [hi(Cin) | lo(Cin) | hi(Cin) | 0 ...] (hi = bf16(x), lo = bf16(x - hi)); a 3x3 b200_conv2d_fwd /
+ * b200_conv2d_gn_fwd over it with a0_C = 64 and weights packed by b200_pack_weights mode 4 (tap_ld = 64) evaluates
+ * x*w as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation. */
+int b200_first_split(const float* x_nchw, void* out_bf16_nhwc64, int B, int Cin, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3: GroupNorm (+ optional per-sample scale/shift = AdaGN) (+ optional SiLU), fp32 NHWC in, bf16 NHWC out.
@@ -460,11 +467,13 @@ int b200_optimizer_step(const b200_optim_desc* d, void* stream);
  *   mode 1: dst[row0 + ci][col0 + (taps-1-tap)*Co + co] = src[co][ci][tap]           (data-gradient operand)
  *   mode 2: dst_f32[i] = src[i] + src2[i], i < Co*Ci*taps                            (summed bias of a fused shortcut)
  *   mode 3: dst[row0 + co][col0 + tap*3*Ci + {0, Ci, 2*Ci} + ci] = {hi, hi, lo}(src[co][ci][tap]), taps <= 9
- *           (FP32 mode, see b200_split_cast: weight side of the 3-term bf16 split product) */
+ *           (FP32 mode, see b200_split_cast: weight side of the 3-term bf16 split product)
+ *   mode 4: as mode 3 with a tap stride of tap_ld (>= 3*Ci) columns instead of 3*Ci; the columns in between are not
+ *           written (zero-fill dst once): weight side of b200_first_split's 64-channel pixels */
 typedef struct b200_pack_entry {
   const float* src; const float* src2; void* dst;
   int Co, Ci, taps, mode;
-  int row0, col0, ld, pad_;
+  int row0, col0, ld, tap_ld;
 } b200_pack_entry;
 int b200_pack_weights(const void* table, int n_entries, void* stream);
 

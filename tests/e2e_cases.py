@@ -442,6 +442,25 @@ def case_train_step():
     return ok
 
 
+def case_train_step_b128():
+    """The benchmarked training shape (bench.py `cfg_train_step`: CFG UNet, batch 128 per GPU, dropout 0.1): at this batch
+    the 8x8 / 4x4 convolutions stack several images per tile, the weight-gradient GEMMs split their pixel range over a
+    full wave and the one-launch GroupNorm / attention adjoints run with their production grids.  Same gates as B = 4."""
+    _no_tf32()
+    cfgc = dict(in_channels=3, out_channels=3, dim=128, dim_mults=[1, 2, 2, 2], use_attn=[False, True, True, False],
+                num_res_blocks=2, num_classes=10, attn_head_dims=64, resblock_updown=True, dropout=0.1)
+    torch.manual_seed(2022)
+    m = models.UNetCategorialAdaGN(**cfgc).to(DEV)
+    B = 128
+    g = torch.Generator(device='cpu').manual_seed(5)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1).to(DEV)
+    eps = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    y = torch.randint(0, 10, (B,), generator=g).to(DEV)
+    okw = dict(dim=128, adagn=True, attn_head_dims=64, num_res_blocks=2)
+    return _train_parity('cfg AdaGN UNet B=128 (cond, the benchmarked batch)', m, okw, x0, t, eps, y=y)
+
+
 def case_train_step_pesser():
     """Backward kernels through the pesser family (separate q/k/v AttnBlock, nin_shortcut, stride-2 conv with
     (0,1,0,1) padding and its 4-phase transposed-conv adjoint, nearest-2x + conv upsampling): toy-width config, B=4."""

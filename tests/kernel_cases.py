@@ -1385,6 +1385,71 @@ def case_conv_gnfuse_out():
         ok &= _report(name + ' raw fp32 output', out.permute(0, 3, 1, 2), pre, rtol=1e-3, atol=1e-3)
         ok &= _report(name + ' normalised concat operand', outn.permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
         ok &= _report(name + ' raw concat operand', outr.permute(0, 3, 1, 2), cat, rtol=1e-2, atol=1e-2)
+        # the same launch without the fp32 output (nobody reads it when the consumer is a concatenating block):
+        # the bf16 operands must be bitwise the same as above
+        outn2 = torch.full((B, H, H, Ct), float('nan'), device=DEV, dtype=torch.bfloat16)
+        outr2 = torch.full((B, H, H, Ct), float('nan'), device=DEV, dtype=torch.bfloat16)
+        ws2 = dict(xstats=K.new_stats(B, Cout, DEV), xcount=K.new_stats(B, 1, DEV)) if multi else {}
+        K.conv2d_gn(_nhwc_bf16(x), wp, Cout, B, H, H, K.taps_3x3_s1(), a0_geom=(Cin, H, H, 1), gamma=gamma, beta=beta,
+                    groups=Cout // cpg, eps=1e-5, out_norm=outn2, out_norm_ld=Ct, out_raw=outr2, bias=b, silu=True,
+                    a1=_nhwc_bf16(xs), a1_geom=(384, H, H, 1), **ws2)
+        torch.cuda.synchronize()
+        same = (torch.equal(outn2[..., :Cout].view(torch.int16), outn[..., :Cout].view(torch.int16))
+                and torch.equal(outr2[..., :Cout].view(torch.int16), outr[..., :Cout].view(torch.int16)))
+        print(json.dumps({'check': name + ' without the fp32 output: operands bitwise equal', 'ok': bool(same)}))
+        ok &= bool(same)
+    return ok
+
+
+
+def case_first_conv_tc():
+    """First convolution on the tensor cores: b200_first_split (fp32 NCHW image -> 64-channel bf16 [hi | lo | hi | 0..]
+    pixels) + pack mode 4 weights [w_hi | w_hi | w_lo | 0..] + the implicit-GEMM conv = fp32-grade products (gate 1e-4
+    relative + 3e-4 absolute at |out| <= 17, measured 1.1e-4: a bf16-rounded image gives 1e-2), plain and with the first ResBlock's GroupNorm fused."""
+    import b200diff as K
+    torch.backends.cudnn.allow_tf32 = False
+    ok = True
+    for (B, Cin, Cout, H, W) in ((37, 3, 128, 32, 32), (64, 3, 256, 16, 16), (5, 1, 128, 32, 32), (3, 4, 128, 64, 64)):
+        x = _gen(B, Cin, H, W, seed=1) * 1.7
+        w = _gen(Cout, Cin, 3, 3, seed=2, scale=0.3)
+        b = _gen(Cout, seed=3)
+        ref = F.conv2d(x, w, b, padding=1)
+        a = torch.full((B, H, W, 64), float('nan'), device=DEV, dtype=torch.bfloat16)
+        K.first_split(x, a)
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        want_a = torch.zeros((B, 64, H, W), device=DEV, dtype=torch.bfloat16)
+        want_a[:, :Cin], want_a[:, Cin:2 * Cin], want_a[:, 2 * Cin:3 * Cin] = hi, lo, hi
+        ok &= _report(f'first_split {Cin} ch @{H}x{W}', a.permute(0, 3, 1, 2), want_a, 0, 0)
+        wp = torch.zeros((Cout, 9 * 64), device=DEV, dtype=torch.bfloat16)
+        tab = torch.frombuffer(bytearray(K.pack_entry_bytes(w, wp, Cout, Cin, 9, 4, ld=9 * 64, tap_ld=64)), dtype=torch.uint8).to(DEV)
+        K.pack_weights(tab, 1)
+        whi = w.to(torch.bfloat16)
+        wlo = (w - whi.float()).to(torch.bfloat16)
+        want_w = torch.zeros((Cout, 9, 64), device=DEV, dtype=torch.bfloat16)
+        wt = lambda t: t.reshape(Cout, Cin, 9).permute(0, 2, 1)
+        want_w[:, :, :Cin], want_w[:, :, Cin:2 * Cin], want_w[:, :, 2 * Cin:3 * Cin] = wt(whi), wt(whi), wt(wlo)
+        ok &= _report(f'pack mode 4 {Cin}->{Cout}', wp.view(Cout, 9, 64), want_w, 0, 0)
+        out = torch.full((B, H, W, Cout), float('nan'), device=DEV)
+        st = K.new_stats(B, Cout, DEV)
+        K.conv2d(a, wp, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(64, H, W, 1), bias=b, out=out, out_mode=K.OUT_F32_NHWC, stats=st)
+        torch.cuda.synchronize()
+        ok &= _report(f'first conv (tensor cores) {Cin}->{Cout} @{H}x{W}', out.permute(0, 3, 1, 2), ref, 1e-4, 3e-4)
+        ok &= _report(f'first conv (tensor cores) {Cin}->{Cout} @{H}x{W} [statistics]', K.stats_to_float(st).float(),
+                      torch.stack([ref.sum(dim=(2, 3)), (ref * ref).sum(dim=(2, 3))], dim=-1), 2e-4, 2e-2)
+        if K.conv2d_gn_ok(B, H, W, Cout, 32):
+            gamma, beta = 1.0 + 0.1 * _gen(Cout, seed=5), 0.1 * _gen(Cout, seed=6)
+            out2 = torch.full((B, H, W, Cout), float('nan'), device=DEV)
+            outn = torch.full((B, H, W, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+            st2 = K.new_stats(B, Cout, DEV)
+            multi = K.conv2d_gn_needs_workspace(H, W)
+            ws = dict(xstats=st2, xcount=K.new_stats(B, 1, DEV)) if multi else {}
+            K.conv2d_gn(a, wp, Cout, B, H, W, K.taps_3x3_s1(), a0_geom=(64, H, W, 1), gamma=gamma, beta=beta, groups=32,
+                        eps=1e-5, out_norm=outn, bias=b, silu=True, out=out2, stats=None if multi else st2, **ws)
+            torch.cuda.synchronize()
+            ok &= _report(f'first conv (tensor cores) {Cin}->{Cout} @{H}x{W} + fused GN: fp32 output', out2.permute(0, 3, 1, 2), ref, 1e-4, 3e-4)
+            ok &= _report(f'first conv (tensor cores) {Cin}->{Cout} @{H}x{W} + fused GN: normalised operand', outn.permute(0, 3, 1, 2),
+                          F.silu(F.group_norm(ref, 32, gamma, beta, eps=1e-5)), 1e-2, 1e-2)
     return ok
 
 

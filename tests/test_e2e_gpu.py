@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', ['unet_forward', 'ddim50', 'ddpm_noise', 'cfg', 'families_golden', 'adm256', 'pesser256',
-                                  'train_step', 'train_step_pesser', 'train_step_adm', 'train_multi_step', 'ode_sampling',
+                                  'train_step', 'train_step_b128', 'train_step_pesser', 'train_step_adm', 'train_multi_step', 'ode_sampling',
                                   'ddim_inversion', 'engine_hygiene', 'fp32_mode'])
 def test_e2e_case(case):
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'e2e_cases.py'), case], capture_output=True,

@@ -8,7 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = ['misc', 'groupnorm', 'conv_basic', 'conv_epilogue', 'conv_n256', 'conv_small_hw', 'conv_1x1',
-         'conv_shortcut', 'conv_stride2', 'conv_lastconv', 'conv_up2', 'conv_tproj', 'conv_gnfuse', 'conv_gnfuse_out', 'attention', 'attention_bwd', 'attn_block', 'sampler',
+         'conv_shortcut', 'conv_stride2', 'conv_lastconv', 'conv_up2', 'conv_tproj', 'conv_gnfuse', 'conv_gnfuse_out', 'first_conv_tc', 'attention', 'attention_bwd', 'attn_block', 'sampler',
          'sampler_cfg', 'ddim_inversion', 'precise',
          'sampler_large', 'gemm',
          'wgrad', 'groupnorm_bwd', 'backward_misc', 'optimizer', 'pack_weights', 'ode_samplers']

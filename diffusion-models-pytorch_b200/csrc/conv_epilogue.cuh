@@ -791,17 +791,19 @@ __device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const
   }
 }
 
-// The same epilogue for tiles that lie inside ONE image (MULTI: 32x32 images over 2 / 4 co-scheduled tiles; or one image
-// per tile: 16x16): every chunk of the tile shares the image's statistics, so both passes are ROLLED loops over the
-// 32-pixel chunks with scalar accumulators and one (A, B) coefficient pair per thread.  The fully unrolled form above ran
-// 2445 straight-line instructions per warp and tile, once each: ncu attributed 23 % of the epilogue warps' samples to
-// instruction fetch (stall_no_inst) on the 32x32 layers, which are bound by this epilogue, not by the tensor pipe.
+// The same epilogue with ROLLED loops over the 32-pixel chunks, for tiles whose chunks map to images uniformly: the whole
+// tile inside ONE image (MULTI: 32x32 images over 2 / 4 co-scheduled tiles; one image per tile: 16x16) -- scalar
+// accumulators, one (A, B) coefficient pair per thread -- or one image per 64-pixel chunk pair (8x8 images: chunk i of this
+// warp + chunk i of its partner = image n0 + i; per-chunk sums travel through the shared-memory exchange buffer and the
+// coefficients are derived inside the loop).  The fully unrolled form above runs 2445 straight-line instructions per warp
+// and tile, once each: ncu attributed 23 % of the epilogue warps' samples to instruction fetch (stall_no_inst) on the
+// 32x32 layers, which are bound by this epilogue, not by the tensor pipe (DDIM-50 +2.9 % with the rolled form).
 template <bool HAS_ROW, bool HAS_SS, bool MULTI, bool RAW>
 __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
                                                              const int c, const int half, const int cl, float* xbuf,
                                                              uint64_t* acc_full_bar, const uint32_t acc_parity) {
   const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
-  const int n = t.n0;
+  const bool per = !MULTI && p.lg_bhw == 6;      // image n0 + i per chunk index i
   const int nch = p.NP >> 6;
   const int rst = p.res_ld * 4, wst = p.out_ld * 4;
   const char* const rbase = (RAW && p.residual) ? reinterpret_cast<const char*>(p.residual + pix0 * (size_t)p.res_ld + c) : nullptr;
@@ -812,15 +814,16 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
     for (int i = 0; i < nch; ++i)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (long long)(half * 32 + 64 * i + lane) * rst));
   }
-  const float add_c = (p.bias ? __ldg(p.bias + c) : 0.f) + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+  const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
   const bool early_out = RAW && wbase != nullptr && !(MULTI && p.gn_late_out);
   mbar_wait(acc_full_bar, acc_parity);
   tc_fence_after();
   // ---- pass 1: x = acc + bias (+ row) (+ residual); sums; RAW: x back to TMEM ----
-  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+  float S1 = 0.f, S2 = 0.f;      // tile-uniform case: this warp's share of the image's per-channel sums
 #pragma unroll 1
   for (int i = 0; i < nch; ++i) {
     const int ch = half * 32 + 64 * i;
+    const int n = t.n0 + (per ? i : 0);
     uint32_t v[32];
     float r[32];
     __syncwarp();
@@ -830,7 +833,9 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = __ldg(reinterpret_cast<const float*>(rp + (long long)j * rst));
     }
+    const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
     tmem_ld_wait();
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
@@ -850,11 +855,18 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
         for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
       }
     }
+    const float c1 = s1a + s1b, c2 = s2a + s2b;
+    if (per) {
+      if (RAW && p.stats != nullptr) stat_add(p.stats + ((size_t)n * p.N + c) * 2, c1, c2);
+      *reinterpret_cast<float2*>(xbuf + (((half * 4 + i) * 128 + cl) << 1)) = make_float2(c1, c2);
+    } else {
+      S1 += c1; S2 += c2;
+    }
   }
-  float S1 = s1a + s1b, S2 = s2a + s2b;     // this warp's share of the image's per-channel sums
   if (RAW) tmem_st_wait();
   if (MULTI) {
     // the image's statistics live in global memory (gn_xstats doubles as the output statistics in the RAW form)
+    const int n = t.n0;
     stat_add(p.gn_xstats + ((size_t)n * p.N + c) * 2, S1, S2);
     __syncwarp();
     unsigned long long* cnt = p.gn_xcount + n;
@@ -894,43 +906,53 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
     const float2 gs = stat_load_group_cg(p.gn_xstats + ((size_t)n * p.N + g0) * 2, 1 << p.gn_lg_cpg);
     S1 = gs.x; S2 = gs.y;
   } else {
-    if (RAW && p.stats != nullptr) stat_add(p.stats + ((size_t)n * p.N + c) * 2, S1, S2);
-    // the partner warp (same channels, the other chunks of the image) through shared memory, then the group's lanes
-    *reinterpret_cast<float2*>(xbuf + ((half * 128 + cl) << 1)) = make_float2(S1, S2);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float2 o = *reinterpret_cast<const float2*>(xbuf + (((1 - half) * 128 + cl) << 1));
-    S1 += o.x; S2 += o.y;
-    for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
-      S1 += __shfl_xor_sync(0xffffffffu, S1, m);
-      S2 += __shfl_xor_sync(0xffffffffu, S2, m);
+    if (!per) {
+      if (RAW && p.stats != nullptr) stat_add(p.stats + ((size_t)t.n0 * p.N + c) * 2, S1, S2);
+      *reinterpret_cast<float2*>(xbuf + ((half * 4 * 128 + cl) << 1)) = make_float2(S1, S2);
     }
+    // the partner warp (same channels, the other pixels of the image[s]) through shared memory
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
-  // ---- coefficients: y = x * A + B ----
   const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (MULTI ? p.gn_cl : 1));
-  const float mean = S1 * inv_cnt;
-  const float var = fmaxf(S2 * inv_cnt - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + p.gn_eps);
-  float ga = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f, be = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
-  if (HAS_SS) {
-    const float sc = 1.f + __ldg(p.gn_scale + (size_t)n * p.gn_ss_ld + c);
-    ga *= sc;
-    be = be * sc + __ldg(p.gn_shift + (size_t)n * p.gn_ss_ld + c);
-  }
-  const float A = rstd * ga;
-  const float radd = RAW ? 0.f : add_c;        // RAW: TMEM already holds the final values x; else x = acc + radd, rounded
-  const float B = be - mean * A;               // as in pass 1 so that both forms give bitwise the same operands
+  const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f, beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
   __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.gn_out_ld + c;
   const int ost = p.gn_out_ld * 2;
   const bool rawcopy = p.gn_rawcopy != nullptr;
   __nv_bfloat16* const rcbase = rawcopy ? reinterpret_cast<__nv_bfloat16*>(p.gn_rawcopy) + pix0 * (size_t)p.gn_out_ld + c : nullptr;
   const bool silu = p.gn_silu != 0;
-  // ---- pass 2 ----
+  float A = 0.f, B = 0.f, radd = 0.f;
+  // ---- pass 2: y = (x [+ bias + row]) * A + B ----
 #pragma unroll 1
   for (int i = 0; i < nch; ++i) {
     const int ch = half * 32 + 64 * i;
     uint32_t v[32];
     __syncwarp();
     tmem_ld_x32(taddr + (uint32_t)ch, v);
+    if (per || i == 0) {      // coefficients of this chunk's image (tile-uniform: once)
+      const int n = t.n0 + (per ? i : 0);
+      if (!MULTI) {
+        const float2 own = *reinterpret_cast<const float2*>(xbuf + (((half * 4 + (per ? i : 0)) * 128 + cl) << 1));
+        const float2 oth = *reinterpret_cast<const float2*>(xbuf + ((((1 - half) * 4 + (per ? i : 0)) * 128 + cl) << 1));
+        S1 = own.x + oth.x; S2 = own.y + oth.y;
+        for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
+          S1 += __shfl_xor_sync(0xffffffffu, S1, m);
+          S2 += __shfl_xor_sync(0xffffffffu, S2, m);
+        }
+      }
+      const float mean = S1 * inv_cnt;
+      const float var = fmaxf(S2 * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.gn_eps);
+      float ga = gamma_c, be = beta_c;
+      if (HAS_SS) {
+        const float sc = 1.f + __ldg(p.gn_scale + (size_t)n * p.gn_ss_ld + c);
+        ga *= sc;
+        be = be * sc + __ldg(p.gn_shift + (size_t)n * p.gn_ss_ld + c);
+      }
+      A = rstd * ga;
+      B = be - mean * A;
+      // RAW: TMEM already holds the final x; else x = acc + radd, rounded as in pass 1 (both forms give the same bits)
+      radd = RAW ? 0.f : bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+    }
     tmem_ld_wait();
     char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
     if (rawcopy) {

@@ -218,7 +218,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         float* xbuf = reinterpret_cast<float*>(bars + 1) + (it & 1) * 2048;
         const int cl = q * 32 + lane;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (p.lg_bhw >= 8 && p.gn_rolled) {      // one image per tile (16x16): rolled chunk loops
+        if (p.lg_bhw >= 6 && p.gn_rolled) {      // one image per tile (16x16) or per 64-pixel chunk pair (8x8): rolled chunk loops
           if (p.gn_raw) conv_epilogue_gnfuse_uniform<false, false, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
           else if (row && ss) conv_epilogue_gnfuse_uniform<true, true, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
           else if (row) conv_epilogue_gnfuse_uniform<true, false, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);

@@ -9,6 +9,8 @@ struct ConvKParams {
   int B, NP;
   int bw, bh, bn, lg_bw, lg_bhw;
   int tiles_w, tiles_h;
+  int lg_tiles_w, lg_tiles_hw;   // log2(tiles_w), log2(tiles_w * tiles_h) when both are powers of two, else lg_tiles_hw = -1
+  int phases;
   int p_tiles, c_tiles, total_tiles;
   int N, w_rows_per_phase;
   int cpb0, nkb0, nkb1;
@@ -79,14 +81,29 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord t;
-  const int per_phase = p.p_tiles * p.c_tiles;
-  t.ph = tile / per_phase;
-  const int rem = tile - t.ph * per_phase;
-  const int pt = rem / p.c_tiles;
-  t.ct = rem - pt * p.c_tiles;
-  const int tw = pt % p.tiles_w;
-  const int th = (pt / p.tiles_w) % p.tiles_h;
-  const int tn = pt / (p.tiles_w * p.tiles_h);
+  // every warp of the CTA decodes every tile: the common cases (one phase, one or two channel tiles, power-of-two tile
+  // grids) avoid the five integer divisions of the general form (~25 dependent instructions each)
+  int rem = tile;
+  t.ph = 0;
+  if (p.phases > 1) {
+    const int per_phase = p.p_tiles * p.c_tiles;
+    t.ph = tile / per_phase;
+    rem = tile - t.ph * per_phase;
+  }
+  int pt = rem;
+  t.ct = 0;
+  if (p.c_tiles == 2) { pt = rem >> 1; t.ct = rem & 1; }
+  else if (p.c_tiles > 2) { pt = rem / p.c_tiles; t.ct = rem - pt * p.c_tiles; }
+  int tw, th, tn;
+  if (p.lg_tiles_hw >= 0) {
+    tw = pt & (p.tiles_w - 1);
+    th = (pt >> p.lg_tiles_w) & (p.tiles_h - 1);
+    tn = pt >> p.lg_tiles_hw;
+  } else {
+    tw = pt % p.tiles_w;
+    th = (pt / p.tiles_w) % p.tiles_h;
+    tn = pt / (p.tiles_w * p.tiles_h);
+  }
   t.w0 = tw * p.bw;
   t.h0 = th * p.bh;
   t.n0 = tn * p.bn;

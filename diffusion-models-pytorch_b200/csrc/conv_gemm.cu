@@ -355,6 +355,12 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
   p.tiles_h = d->Ho / p.bh;
   p.c_tiles = c_tiles;
   p.total_tiles = d->phases * p.p_tiles * p.c_tiles;
+  p.phases = d->phases;
+  p.lg_tiles_w = 0; p.lg_tiles_hw = -1;
+  if ((p.tiles_w & (p.tiles_w - 1)) == 0 && (p.tiles_h & (p.tiles_h - 1)) == 0) {
+    p.lg_tiles_w = ilog2(p.tiles_w);
+    p.lg_tiles_hw = p.lg_tiles_w + ilog2(p.tiles_h);
+  }
   p.N = d->N;
   p.w_rows_per_phase = d->w_rows_per_phase;
   p.cpb0 = d->a0_C / 64;

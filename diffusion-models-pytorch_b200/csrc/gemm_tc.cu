@@ -103,18 +103,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // conv mode: the CTAs of the 9 taps of one pixel range would otherwise request the same dY / activation lines
         // from L2 at the same moment; each tap starts at a different K-block of the range (the sum is order-free)
         const int rot = (p.conv && p.k_rotate) ? (int)(((long)g * nkb) / p.groups) : 0;
+        // conv mode: pixel-tile coordinates of the K-block, stepped incrementally (three integer divisions per K-block
+        // sat between the slot wait and the TMA issue of this single producer thread)
+        int tw = 0, th = 0, tn = 0;
+        bool recompute = true;
         for (int kbi = 0; kbi < nkb; ++kbi) {
           int kb = kb0 + kbi + rot;
           if (kb >= kb1) kb -= nkb;
+          if (p.conv) {
+            if (recompute || kb == kb0) {
+              tw = kb % p.tiles_w;
+              th = (kb / p.tiles_w) % p.tiles_h;
+              tn = kb / (p.tiles_w * p.tiles_h);
+              recompute = false;
+            } else if (++tw == p.tiles_w) {
+              tw = 0;
+              if (++th == p.tiles_h) { th = 0; ++tn; }
+            }
+          }
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + a_bytes;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
           if (p.conv) {
             // K-block = pixel tile (tw, th, tn); A = dY (unshifted), B = activation shifted by the tap g
-            const int tw = kb % p.tiles_w;
-            const int th = (kb / p.tiles_w) % p.tiles_h;
-            const int tn = kb / (p.tiles_w * p.tiles_h);
             const int w0 = tw * p.bw, h0 = th * p.bh, i0 = tn * p.bn;
             for (int c = 0; c < 2; ++c)
               tma_load_5d(sA + c * chunk_bytes, &mapA, &bars->full[stage], ca + m0 + c * 64, w0, h0, 0, i0);
@@ -295,19 +307,22 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int m0 = mt * 128, n0 = nt * p.BN;
         int stage = 0;
         uint32_t phase = 0;
+        // pixel-tile coordinates of the K-block, stepped incrementally (no integer divisions inside the loop)
+        int tw = kb0 % p.tiles_w, th = (kb0 / p.tiles_w) % p.tiles_h, tn = kb0 / (p.tiles_w * p.tiles_h);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
           uint8_t* sA = smem + (size_t)stage * stage_bytes;
           uint8_t* sB = sA + a_bytes;
           mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-          const int tw = kb % p.tiles_w;
-          const int th = (kb / p.tiles_w) % p.tiles_h;
-          const int tn = kb / (p.tiles_w * p.tiles_h);
           const int w0 = tw * p.bw, h0 = th * p.bh;
           for (int c = 0; c < 2; ++c)
             tma_load_5d(sA + c * a_slab, &mapA, &bars->full[stage], p.dy_c0 + m0 + c * 64, w0, h0, 0, tn);
           for (int c = 0; c < p.BN / 64; ++c)
             tma_load_5d(sB + c * b_slab, &mapB, &bars->full[stage], p.x_c0 + n0 + c * 64, w0 + dxi - 1, h0 - 1, 0, tn);
+          if (++tw == p.tiles_w) {
+            tw = 0;
+            if (++th == p.tiles_h) { th = 0; ++tn; }
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }

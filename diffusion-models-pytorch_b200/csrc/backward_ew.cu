@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
 }
 
 // ================================================================================================
-// One-launch GroupNorm adjoint for small images (HW <= 256, no resampling): the four-kernel form above is bound by its
+// One-launch GroupNorm adjoint for small images (HW <= 256 by default, no resampling): the four-kernel form above is bound by its
 // launch chain there (ncu, CFG UNet at batch 128: coef 4 us -> reduce 14-19 us -> final 5 us -> apply 19-30 us for 3-25 MB
 // of traffic, 128 CTAs at 12 % occupancy on the 8x8 / 4x4 levels).  A CTA owns ALL pixels of one image for a slice of
 // CS channels made of whole groups, so nothing has to be exchanged between CTAs: x (fp32) and g (bf16) are read from
@@ -1029,17 +1029,30 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   const int mode = (p.resample == 0 && (unsigned long long)d->B * d->HW * C < (1ull << 32)) ? (p.C1 == 0 ? 1 : 2) : 0;
   // small images: everything in one launch, one CTA per (image, slice of whole groups), data read once (gn_bwd_slab_kernel)
   static const char* env_slab = getenv("B200_GNB_SLAB");      // =0: the four-kernel form everywhere (A/B timing)
-  if (mode != 0 && d->HW <= 256 && !(env_slab && atoi(env_slab) == 0)) {
-    // slice = the fewest whole groups that give >= 32 channels (32 groups per tensor: 1, 2, 4, ... groups divide it evenly)
+  // largest image (pixels) that takes it.  32x32 images fit too (a 32-channel slice = 201 KB of shared memory) and were
+  // measured (B200_GNB_SLAB_HW=1024): one CTA of 8 warps per SM cannot hide the load latency -- the twelve 32x32 adjoints
+  // of the CFG UNet step got 64 us SLOWER each (training step 14.69 -> 15.53 ms), so they keep the four-kernel form.
+  static const char* env_slab_hw = getenv("B200_GNB_SLAB_HW");
+  const int slab_hw = env_slab_hw ? atoi(env_slab_hw) : 256;
+  if (mode != 0 && d->HW <= slab_hw && !(env_slab && atoi(env_slab) == 0)) {
+    // slice = the fewest whole groups that give >= 32 channels (32 groups per tensor: 1, 2, 4, ... groups divide it evenly);
+    // 32x32 images: x + g of a 32-channel slice are 192 KB, so the slice shrinks (whole groups, >= 16 channels) until one
+    // CTA's slab fits the 227 KB of shared memory
+    const size_t smem_max = 227 * 1024;
     int gsl = 1;
     while (p.cpg * gsl < 32 && gsl < d->groups && d->groups % (gsl * 2) == 0) gsl *= 2;
+    auto slab_bytes = [&](int cs) {
+      const int nq_ = cs / 4, R_ = 256 / (nq_ > 0 ? nq_ : 1);
+      return (size_t)d->HW * cs * 6 + (size_t)(8 + 2 * R_) * cs * 4;
+    };
+    while (gsl > 1 && p.cpg * (gsl / 2) >= 16 && slab_bytes(p.cpg * gsl) > smem_max) gsl /= 2;
     const int CS = p.cpg * gsl;
-    const int nq = CS / 4, R = 256 / (nq > 0 ? nq : 1);
-    const size_t smem = (size_t)d->HW * CS * 6 + (size_t)(8 + 2 * R) * CS * 4;
-    if (CS % 4 == 0 && nq >= 1 && nq <= 64 && C % CS == 0 && ((size_t)d->HW * CS * 6) % 16 == 0 && smem <= 160 * 1024) {
+    const int nq = CS / 4;
+    const size_t smem = slab_bytes(CS);
+    if (CS % 4 == 0 && nq >= 1 && nq <= 64 && C % CS == 0 && ((size_t)d->HW * CS * 6) % 16 == 0 && smem <= smem_max) {
       static bool slab_attr = false;
       if (!slab_attr) {
-        B200_CHECK(cudaFuncSetAttribute(gn_bwd_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B200_CHECK(cudaFuncSetAttribute(gn_bwd_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         slab_attr = true;
       }
       gn_bwd_slab_kernel<<<dim3(C / CS, d->B), 256, smem, stream>>>(p, CS);

@@ -779,6 +779,12 @@ def case_groupnorm_bwd():
     ok &= _gn_bwd_case('gn_bwd adagn C512 8x8 dropout', 3, 8, 8, 512, 0, adagn=True, drop_p=0.2)
     ok &= _gn_bwd_case('gn_bwd adagn cat 128+128 16x16 bf16 out + rowsum', 2, 16, 16, 128, 128, adagn=True, bf16_out=True)
     ok &= _gn_bwd_case('gn_bwd adagn cat 128+128 32x32 dropout addend', 2, 32, 32, 128, 128, adagn=True, drop_p=0.1, addend=True)
+    # 32x32 / 64x64 images (four-kernel form; the slab form only with B200_GNB_SLAB_HW=1024): 12-channel groups straddling
+    # the boundary of the two sources, bf16 output + row sums, dropout, AdaGN
+    ok &= _gn_bwd_case('gn_bwd cat 256+128 32x32 bf16 out + rowsum', 3, 32, 32, 256, 128, bf16_out=True)
+    ok &= _gn_bwd_case('gn_bwd cat 256+128 32x32 dropout addend', 2, 32, 32, 256, 128, drop_p=0.1, addend=True)
+    ok &= _gn_bwd_case('gn_bwd C128 64x64 dropout (four-kernel form)', 1, 64, 64, 128, 0, drop_p=0.1)
+    ok &= _gn_bwd_case('gn_bwd adagn cat 128+128 64x64 addend (four-kernel form)', 1, 64, 64, 128, 128, adagn=True, addend=True)
     return ok
 
 

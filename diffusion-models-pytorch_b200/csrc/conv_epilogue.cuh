@@ -44,7 +44,6 @@ struct ConvKParams {
   void* gn_rawcopy;  // optional: bf16 copy of the un-normalised result, laid out like gn_out (the operand of
                      // the consumer's fused 1x1 shortcut when the consumer concatenates a skip connection)
   int gn_ss_ld, gn_lg_cpg, gn_silu;
-  int gn_rolled;     // one-image tiles (16x16): rolled fused epilogue (conv_epilogue_gnfuse_uniform)
   int gn_late_out;   // multi-tile block-output form: write the fp32 output AFTER the statistics arrival (see conv_epilogue_gnfuse)
   int gn_cl;     // tiles (= co-scheduled CTAs) per image in the multi-tile variant of the fused epilogue, else 0
   long long* gn_xstats;            // multi-tile variant: zeroed [B][N][2] int64 statistics of the conv output
@@ -575,252 +574,20 @@ __device__ __forceinline__ float2 stat_load_group_cg(const long long* pair, int 
 // p.out with its per-channel statistics in p.stats (skip connections, attention blocks and the next block's residual
 // read them), and pass 1 stores x back into TMEM so that pass 2 normalises the final values without a second read of
 // the residual.  The normalised copy goes to p.gn_out with channel stride p.gn_out_ld.
-template <bool HAS_ROW, bool HAS_SS, bool MULTI = false, bool RAW = false>
-__device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
-                                                     const int c, const int half, const int cl, float* xbuf,
-                                                     uint64_t* acc_full_bar, const uint32_t acc_parity) {
-  // cl = channel inside the tile (0..127); xbuf = this tile's exchange buffer [2 halves][4 chunks][128][2]
-  const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
-  const float bias_c = p.bias ? __ldg(p.bias + c) : 0.f;
-  const int nch = p.NP >> 6;     // 32-pixel chunks per warp: 1, 2 or 4 (tiles of 64 / 128 / 256 pixels)
-  const int rst = p.res_ld * 4, wst = p.out_ld * 4;      // RAW: byte strides between consecutive pixels
-  const char* const rbase = (RAW && p.residual) ? reinterpret_cast<const char*>(p.residual + pix0 * (size_t)p.res_ld + c) : nullptr;
-  char* const wbase = RAW ? reinterpret_cast<char*>(reinterpret_cast<float*>(p.out) + pix0 * (size_t)p.out_ld + c) : nullptr;
-  if (RAW && rbase != nullptr) {
-    // residual lines of this warp's chunks into L2 while the tile's MMAs still run (as in conv_epilogue_lean)
-    const int lane = threadIdx.x & 31;
-    const char* pf = rbase - (long long)lane * 4;
-    for (int i = 0; i < nch; ++i)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (long long)(half * 32 + 64 * i + lane) * rst));
-  }
-  mbar_wait(acc_full_bar, acc_parity);
-  tc_fence_after();
-  float ps1[4][2], ps2[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ps1[i][0] = ps1[i][1] = ps2[i][0] = ps2[i][1] = 0.f;
-    if (i >= nch) continue;
-    const int ch = half * 32 + 64 * i;
-    uint32_t v[32];
-    float r[32];
-    __syncwarp();
-    tmem_ld_x32(taddr + (uint32_t)ch, v);
-    if (RAW && rbase != nullptr) {      // overlaps the TMEM load
-      const char* rp = rbase + (long long)ch * rst;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = __ldg(reinterpret_cast<const float*>(rp + (long long)j * rst));
-    }
-    tmem_ld_wait();
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
-      const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
-      float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int j = 16 * hf; j < 16 * hf + 16; j += 2) {
-        float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
-        if (RAW) {
-          if (rbase != nullptr) { a0 += r[j]; a1 += r[j + 1]; }
-          v[j] = __float_as_uint(a0);
-          v[j + 1] = __float_as_uint(a1);
-        }
-        s1 += a0; t1 += a1;
-        s2 = fmaf(a0, a0, s2); t2 = fmaf(a1, a1, t2);
-      }
-      ps1[i][hf] = s1 + t1;
-      ps2[i][hf] = s2 + t2;
-    }
-    if (RAW) {
-      tmem_st_x32(taddr + (uint32_t)ch, v);      // pass 2 reads the final values
-      if (!(MULTI && p.gn_late_out)) {
-        char* wp = wbase + (long long)ch * wst;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
-      }
-    }
-  }
-  if (RAW) {
-    tmem_st_wait();
-    if (!MULTI && p.stats != nullptr) {
-      // per-channel statistics of the block output (this warp's share of each image of the tile)
-      if (p.lg_bhw >= 8) {
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1]; b += ps2[i][0] + ps2[i][1]; }
-        stat_add(p.stats + ((size_t)t.n0 * p.N + c) * 2, a, b);
-      } else if (p.lg_bhw == 6) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nch) stat_add(p.stats + ((size_t)(t.n0 + i) * p.N + c) * 2, ps1[i][0] + ps1[i][1], ps2[i][0] + ps2[i][1]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nch) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-              stat_add(p.stats + ((size_t)(t.n0 + ((half * 32 + 64 * i + 16 * hf) >> 4)) * p.N + c) * 2, ps1[i][hf], ps2[i][hf]);
-          }
-      }
-    }
-  }
-  float S1[4][2], S2[4][2];
-  if (MULTI) {
-    // own chunks of this tile -> the image's global statistics; wait for the other warps / tiles of the image
-    const int n = t.n0;
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1]; b += ps2[i][0] + ps2[i][1]; }
-    stat_add(p.gn_xstats + ((size_t)n * p.N + c) * 2, a, b);
-    // Arrival: the warp's 64 reductions are ordered before lane 0's release (bar.warp.sync + cumulativity), so one
-    // release-add replaces a gpu-scope fence by all 32 lanes.  In the block-output form the fp32 output is written
-    // AFTER the arrival (re-read from TMEM): a fence in front of the arrival would otherwise wait for the 128 output
-    // stores of this warp, and the stores now fill the time the other tiles of the image need to arrive
-    // (ncu, 128->128 @32x32 + residual: MEMBAR / ERRBAR / CCTL.IVALL of the first version = 17 % of the warp samples).
-    __syncwarp();
-    unsigned long long* cnt = p.gn_xcount + n;
-    if ((threadIdx.x & 31) == 0)
-      asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(cnt), "l"(1ULL) : "memory");
-    if (RAW && p.gn_late_out) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i >= nch) continue;
-        const int ch = half * 32 + 64 * i;
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_x32(taddr + (uint32_t)ch, v);
-        tmem_ld_wait();
-        char* wp = wbase + (long long)ch * wst;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(wp + (long long)j * wst) = __uint_as_float(v[j]);
-      }
-    }
-    if ((threadIdx.x & 31) == 0) {
-      const unsigned long long target = (unsigned long long)(8 * p.gn_cl);
-      uint64_t t0 = 0;
-      uint32_t spins = 0;
-      // relaxed polling (an acquire load invalidates L1 on every iteration), one acquire fence at the end
-      while (ld_relaxed_u64(cnt) < target) {
-        if ((++spins & 0x3ff) == 0) {
-          const uint64_t now = globaltimer_ns();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 4000000000ull) {
-            printf("b200diff: fused GroupNorm statistics wait timeout (block %d image %d)\n", blockIdx.x, n);
-            __trap();
-          }
-        }
-      }
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    }
-    __syncwarp();
-    const int g0 = (c >> p.gn_lg_cpg) << p.gn_lg_cpg;
-    const float2 gs = stat_load_group_cg(p.gn_xstats + ((size_t)n * p.N + g0) * 2, 1 << p.gn_lg_cpg);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = gs.x; S2[i][0] = S2[i][1] = gs.y; }
-  } else {
-  // per-chunk sums of this warp -> shared memory; the partner warp (same channels, the other chunks) reads them
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 w2;
-    w2.x = ps1[i][0] + ps1[i][1];
-    w2.y = ps2[i][0] + ps2[i][1];
-    *reinterpret_cast<float2*>(xbuf + (((half * 4 + i) * 128 + cl) << 1)) = w2;
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps (warps 0 / 1 = TMA / MMA do not take part)
-  float o1[4], o2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 r2 = *reinterpret_cast<const float2*>(xbuf + ((((1 - half) * 4 + i) * 128 + cl) << 1));
-    o1[i] = r2.x;
-    o2[i] = r2.y;
-  }
-  // image statistics of the (chunk, half-chunk) slots of this thread
-  if (p.lg_bhw >= 8) {          // one image per tile: everything
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a += ps1[i][0] + ps1[i][1] + o1[i]; b += ps2[i][0] + ps2[i][1] + o2[i]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { S1[i][0] = S1[i][1] = a; S2[i][0] = S2[i][1] = b; }
-  } else if (p.lg_bhw == 6) {   // image i = chunk i of this warp + chunk i of the partner (pixels 64 i .. 64 i + 63)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      S1[i][0] = S1[i][1] = ps1[i][0] + ps1[i][1] + o1[i];
-      S2[i][0] = S2[i][1] = ps2[i][0] + ps2[i][1] + o2[i];
-    }
-  } else {                      // 16 pixels per image: every half chunk is a whole image of this warp
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { S1[i][0] = ps1[i][0]; S1[i][1] = ps1[i][1]; S2[i][0] = ps2[i][0]; S2[i][1] = ps2[i][1]; }
-  }
-  // group sums: butterfly over the 2^lg_cpg consecutive lanes (= channels) of a group
-  for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        S1[i][hf] += __shfl_xor_sync(0xffffffffu, S1[i][hf], m);
-        S2[i][hf] += __shfl_xor_sync(0xffffffffu, S2[i][hf], m);
-      }
-  }
-  }   // !MULTI
-  const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (MULTI ? p.gn_cl : 1));
-  const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f;
-  const float beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
-  __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(p.gn_out) + pix0 * (size_t)p.gn_out_ld + c;
-  const int ost = p.gn_out_ld * 2;    // bytes between consecutive pixels of the NHWC output
-  const bool rawcopy = p.gn_rawcopy != nullptr;     // without RAW: a block output nobody reads as fp32 (decoder blocks)
-  __nv_bfloat16* const rcbase = rawcopy ? reinterpret_cast<__nv_bfloat16*>(p.gn_rawcopy) + pix0 * (size_t)p.gn_out_ld + c : nullptr;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (i >= nch) continue;
-    const int ch = half * 32 + 64 * i;
-    uint32_t v[32];
-    __syncwarp();
-    tmem_ld_x32(taddr + (uint32_t)ch, v);
-    tmem_ld_wait();
-    char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
-    if (rawcopy) {
-      char* rp = reinterpret_cast<char*>(rcbase) + (long long)ch * ost;
-      const float radd = RAW ? 0.f : bias_c;      // RAW: pass 1 stored the final values; else the accumulators lack the bias
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) = __float2bfloat16_rn(__uint_as_float(v[j]) + radd);
-    }
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int n = t.n0 + ((ch + 16 * hf) >> p.lg_bhw);
-      const float add_c = RAW ? 0.f : bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
-      const float mean = S1[i][hf] * inv_cnt;
-      const float var = fmaxf(S2[i][hf] * inv_cnt - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.gn_eps);
-      float ga = gamma_c, be = beta_c;
-      if (HAS_SS) {
-        const float sc = 1.f + __ldg(p.gn_scale + (size_t)n * p.gn_ss_ld + c);
-        ga *= sc;
-        be = be * sc + __ldg(p.gn_shift + (size_t)n * p.gn_ss_ld + c);
-      }
-      const float A = rstd * ga, B = be - mean * rstd * ga;
-#pragma unroll
-      for (int j = 16 * hf; j < 16 * hf + 16; ++j) {
-        float y = fmaf(__uint_as_float(v[j]) + add_c, A, B);
-        if (p.gn_silu) y = epi_silu_tanh(y);
-        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) = __float2bfloat16_rn(y);
-      }
-    }
-  }
-}
-
-// The same epilogue with ROLLED loops over the 32-pixel chunks, for tiles whose chunks map to images uniformly: the whole
-// tile inside ONE image (MULTI: 32x32 images over 2 / 4 co-scheduled tiles; one image per tile: 16x16) -- scalar
-// accumulators, one (A, B) coefficient pair per thread -- or one image per 64-pixel chunk pair (8x8 images: chunk i of this
-// warp + chunk i of its partner = image n0 + i; per-chunk sums travel through the shared-memory exchange buffer and the
-// coefficients are derived inside the loop).  The fully unrolled form above runs 2445 straight-line instructions per warp
-// and tile, once each: ncu attributed 23 % of the epilogue warps' samples to instruction fetch (stall_no_inst) on the
-// 32x32 layers, which are bound by this epilogue, not by the tensor pipe (DDIM-50 +2.9 % with the rolled form).
+// Loops over the 32-pixel chunks are ROLLED and a thread keeps scalar accumulators and one or two (A, B) coefficient pairs:
+// the tile's chunks map to images uniformly -- the whole tile inside ONE image (MULTI: 32x32 images over 2 / 4
+// co-scheduled tiles; one image per tile: 16x16), one image per 64-pixel chunk pair (8x8: chunk i of this warp + chunk i of
+// its partner = image n0 + i; per-chunk sums travel through the shared-memory exchange buffer), or one image per 16-pixel
+// half chunk (4x4: no partner at all).  A first, fully unrolled form ran 2445 straight-line instructions per warp and
+// tile, once each: ncu attributed 23 % of the epilogue warps' samples to instruction fetch (stall_no_inst) on the 32x32
+// layers, which are bound by this epilogue and not by the tensor pipe (DDIM-50 +3.7 % with the rolled form).
 template <bool HAS_ROW, bool HAS_SS, bool MULTI, bool RAW>
-__device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
+__device__ __forceinline__ void conv_epilogue_gnfuse(const ConvKParams& p, const TileCoord& t, const uint32_t taddr,
                                                              const int c, const int half, const int cl, float* xbuf,
-                                                             uint64_t* acc_full_bar, const uint32_t acc_parity) {
+                                                             float* xbuf16, uint64_t* acc_full_bar, const uint32_t acc_parity) {
   const size_t pix0 = ((size_t)t.n0 * p.out_H + t.h0) * p.out_W + t.w0;
   const bool per = !MULTI && p.lg_bhw == 6;      // image n0 + i per chunk index i
+  const bool p16 = !MULTI && p.lg_bhw == 4;      // 4x4 images: every 16-pixel half chunk is a whole image of this warp
   const int nch = p.NP >> 6;
   const int rst = p.res_ld * 4, wst = p.out_ld * 4;
   const char* const rbase = (RAW && p.residual) ? reinterpret_cast<const char*>(p.residual + pix0 * (size_t)p.res_ld + c) : nullptr;
@@ -840,7 +607,7 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
 #pragma unroll 1
   for (int i = 0; i < nch; ++i) {
     const int ch = half * 32 + 64 * i;
-    const int n = t.n0 + (per ? i : 0);
+    const int n = t.n0 + (per ? i : p16 ? (ch >> 4) : 0);      // p16: image of the first half chunk, the second is n + 1
     uint32_t v[32];
     float r[32];
     __syncwarp();
@@ -851,15 +618,17 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
       for (int j = 0; j < 32; ++j) r[j] = __ldg(reinterpret_cast<const float*>(rp + (long long)j * rst));
     }
     const float add_c = bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
+    const float add_d = (HAS_ROW && p16) ? bias_c + __ldg(p.rowadd + (size_t)(n + 1) * p.rowadd_ld + c) : add_c;
     tmem_ld_wait();
+    // (s1a, s2a): columns 0..15, (s1b, s2b): columns 16..31 of the chunk (two images in the p16 case)
     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 1]) + add_c;
+    for (int j = 0; j < 16; ++j) {
+      float a0 = __uint_as_float(v[j]) + add_c, a1 = __uint_as_float(v[j + 16]) + add_d;
       if (RAW) {
-        if (rbase != nullptr) { a0 += r[j]; a1 += r[j + 1]; }
+        if (rbase != nullptr) { a0 += r[j]; a1 += r[j + 16]; }
         v[j] = __float_as_uint(a0);
-        v[j + 1] = __float_as_uint(a1);
+        v[j + 16] = __float_as_uint(a1);
       }
       s1a += a0; s1b += a1;
       s2a = fmaf(a0, a0, s2a); s2b = fmaf(a1, a1, s2b);
@@ -873,7 +642,16 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
       }
     }
     const float c1 = s1a + s1b, c2 = s2a + s2b;
-    if (per) {
+    if (p16) {
+      // no partner: both parity halves of the exchange buffer hold this tile's [half][chunk][half chunk][channel] sums
+      if (RAW && p.stats != nullptr) {
+        stat_add(p.stats + ((size_t)n * p.N + c) * 2, s1a, s2a);
+        stat_add(p.stats + ((size_t)(n + 1) * p.N + c) * 2, s1b, s2b);
+      }
+      float* slot = xbuf16 + ((((half * 4 + i) * 2) * 128 + cl) << 1);
+      *reinterpret_cast<float2*>(slot) = make_float2(s1a, s2a);
+      *reinterpret_cast<float2*>(slot + 256) = make_float2(s1b, s2b);
+    } else if (per) {
       if (RAW && p.stats != nullptr) stat_add(p.stats + ((size_t)n * p.N + c) * 2, c1, c2);
       *reinterpret_cast<float2*>(xbuf + (((half * 4 + i) * 128 + cl) << 1)) = make_float2(c1, c2);
     } else {
@@ -923,12 +701,14 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
     const float2 gs = stat_load_group_cg(p.gn_xstats + ((size_t)n * p.N + g0) * 2, 1 << p.gn_lg_cpg);
     S1 = gs.x; S2 = gs.y;
   } else {
-    if (!per) {
+    if (!per && !p16) {
       if (RAW && p.stats != nullptr) stat_add(p.stats + ((size_t)t.n0 * p.N + c) * 2, S1, S2);
       *reinterpret_cast<float2*>(xbuf + ((half * 4 * 128 + cl) << 1)) = make_float2(S1, S2);
     }
-    // the partner warp (same channels, the other pixels of the image[s]) through shared memory
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // the partner warp (same channels, the other pixels of the image[s]) through shared memory; p16: own values only,
+    // but a warp may not overwrite them for the NEXT tile while its own pass 2 still reads -- program order gives that
+    if (!p16) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncwarp();
   }
   const float inv_cnt = 1.0f / (float)(((1 << p.lg_bhw) << p.gn_lg_cpg) * (MULTI ? p.gn_cl : 1));
   const float gamma_c = p.gn_gamma ? __ldg(p.gn_gamma + c) : 1.f, beta_c = p.gn_beta ? __ldg(p.gn_beta + c) : 0.f;
@@ -945,48 +725,60 @@ __device__ __forceinline__ void conv_epilogue_gnfuse_uniform(const ConvKParams& 
     uint32_t v[32];
     __syncwarp();
     tmem_ld_x32(taddr + (uint32_t)ch, v);
-    if (per || i == 0) {      // coefficients of this chunk's image (tile-uniform: once)
-      const int n = t.n0 + (per ? i : 0);
-      if (!MULTI) {
-        const float2 own = *reinterpret_cast<const float2*>(xbuf + (((half * 4 + (per ? i : 0)) * 128 + cl) << 1));
-        const float2 oth = *reinterpret_cast<const float2*>(xbuf + ((((1 - half) * 4 + (per ? i : 0)) * 128 + cl) << 1));
-        S1 = own.x + oth.x; S2 = own.y + oth.y;
-        for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
-          S1 += __shfl_xor_sync(0xffffffffu, S1, m);
-          S2 += __shfl_xor_sync(0xffffffffu, S2, m);
+    float A2 = 0.f, B2 = 0.f, radd2 = 0.f;      // p16: second half chunk
+    if (per || p16 || i == 0) {      // coefficients of this chunk's image(s) (tile-uniform: once)
+      const int n = t.n0 + (per ? i : p16 ? (ch >> 4) : 0);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (hf == 1 && !p16) break;
+        if (p16) {
+          const float2 own = *reinterpret_cast<const float2*>(xbuf16 + ((((half * 4 + i) * 2 + hf) * 128 + cl) << 1));
+          S1 = own.x; S2 = own.y;
+        } else if (!MULTI) {
+          const float2 own = *reinterpret_cast<const float2*>(xbuf + (((half * 4 + (per ? i : 0)) * 128 + cl) << 1));
+          const float2 oth = *reinterpret_cast<const float2*>(xbuf + ((((1 - half) * 4 + (per ? i : 0)) * 128 + cl) << 1));
+          S1 = own.x + oth.x; S2 = own.y + oth.y;
         }
+        if (!MULTI)
+          for (int m = 1; m < (1 << p.gn_lg_cpg); m <<= 1) {
+            S1 += __shfl_xor_sync(0xffffffffu, S1, m);
+            S2 += __shfl_xor_sync(0xffffffffu, S2, m);
+          }
+        const float mean = S1 * inv_cnt;
+        const float var = fmaxf(S2 * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.gn_eps);
+        float ga = gamma_c, be = beta_c;
+        if (HAS_SS) {
+          const float sc = 1.f + __ldg(p.gn_scale + (size_t)(n + hf) * p.gn_ss_ld + c);
+          ga *= sc;
+          be = be * sc + __ldg(p.gn_shift + (size_t)(n + hf) * p.gn_ss_ld + c);
+        }
+        // RAW: TMEM already holds the final x; else x = acc + radd, rounded as in pass 1 (both forms give the same bits)
+        const float ra_ = RAW ? 0.f : bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)(n + hf) * p.rowadd_ld + c) : 0.f);
+        if (hf == 0) { A = rstd * ga; B = be - mean * A; radd = ra_; }
+        else { A2 = rstd * ga; B2 = be - mean * A2; radd2 = ra_; }
       }
-      const float mean = S1 * inv_cnt;
-      const float var = fmaxf(S2 * inv_cnt - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.gn_eps);
-      float ga = gamma_c, be = beta_c;
-      if (HAS_SS) {
-        const float sc = 1.f + __ldg(p.gn_scale + (size_t)n * p.gn_ss_ld + c);
-        ga *= sc;
-        be = be * sc + __ldg(p.gn_shift + (size_t)n * p.gn_ss_ld + c);
-      }
-      A = rstd * ga;
-      B = be - mean * A;
-      // RAW: TMEM already holds the final x; else x = acc + radd, rounded as in pass 1 (both forms give the same bits)
-      radd = RAW ? 0.f : bias_c + (HAS_ROW ? __ldg(p.rowadd + (size_t)n * p.rowadd_ld + c) : 0.f);
     }
+    if (!p16) { A2 = A; B2 = B; radd2 = radd; }
     tmem_ld_wait();
     char* op = reinterpret_cast<char*>(obase) + (long long)ch * ost;
     if (rawcopy) {
       char* rp = reinterpret_cast<char*>(rcbase) + (long long)ch * ost;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) = __float2bfloat16_rn(__uint_as_float(v[j]) + radd);
+        *reinterpret_cast<__nv_bfloat16*>(rp + (long long)j * ost) =
+            __float2bfloat16_rn(__uint_as_float(v[j]) + (j < 16 ? radd : radd2));
     }
     if (silu) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) =
-            __float2bfloat16_rn(epi_silu_tanh(fmaf(__uint_as_float(v[j]) + radd, A, B)));
+        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) = __float2bfloat16_rn(
+            epi_silu_tanh(fmaf(__uint_as_float(v[j]) + (j < 16 ? radd : radd2), j < 16 ? A : A2, j < 16 ? B : B2)));
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) = __float2bfloat16_rn(fmaf(__uint_as_float(v[j]) + radd, A, B));
+        *reinterpret_cast<__nv_bfloat16*>(op + (long long)j * ost) =
+            __float2bfloat16_rn(fmaf(__uint_as_float(v[j]) + (j < 16 ? radd : radd2), j < 16 ? A : A2, j < 16 ? B : B2));
     }
   }
 }

@@ -201,35 +201,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // multi-tile fused next-GroupNorm epilogue (32x32 images: statistics through global memory, cooperative launch)
         const int cl = q * 32 + lane;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (p.gn_rolled) {
-          if (p.gn_raw) conv_epilogue_gnfuse_uniform<false, false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-          else if (row && ss) conv_epilogue_gnfuse_uniform<true, true, true, false>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-          else if (row) conv_epilogue_gnfuse_uniform<true, false, true, false>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-          else if (ss) conv_epilogue_gnfuse_uniform<false, true, true, false>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-          else conv_epilogue_gnfuse_uniform<false, false, true, false>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-        } else if (p.gn_raw) conv_epilogue_gnfuse<false, false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-        else if (row && ss) conv_epilogue_gnfuse<true, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-        else if (row) conv_epilogue_gnfuse<true, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-        else if (ss) conv_epilogue_gnfuse<false, true, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
-        else conv_epilogue_gnfuse<false, false, true>(p, t, taddr, c, half, cl, nullptr, &bars->tmem_full[as], aphase);
+        if (p.gn_raw) conv_epilogue_gnfuse<false, false, true, true>(p, t, taddr, c, half, cl, nullptr, nullptr, &bars->tmem_full[as], aphase);
+        else if (row && ss) conv_epilogue_gnfuse<true, true, true, false>(p, t, taddr, c, half, cl, nullptr, nullptr, &bars->tmem_full[as], aphase);
+        else if (row) conv_epilogue_gnfuse<true, false, true, false>(p, t, taddr, c, half, cl, nullptr, nullptr, &bars->tmem_full[as], aphase);
+        else if (ss) conv_epilogue_gnfuse<false, true, true, false>(p, t, taddr, c, half, cl, nullptr, nullptr, &bars->tmem_full[as], aphase);
+        else conv_epilogue_gnfuse<false, false, true, false>(p, t, taddr, c, half, cl, nullptr, nullptr, &bars->tmem_full[as], aphase);
       } else if (kLean == 2) {
-        // fused next-GroupNorm epilogue (experimental): exchange buffers [2 tile parities][2][4][128][2] floats = 16 KB
-        // behind the barriers; all channels are valid (N % 128 == 0 is required by the host side)
-        float* xbuf = reinterpret_cast<float*>(bars + 1) + (it & 1) * 2048;
+        // fused next-GroupNorm epilogue, tiles of whole images: exchange buffers [2 tile parities][2][4][128][2] floats = 16 KB
+        // behind the barriers (4x4 images: one buffer [2][4][2][128][2] for the current tile, no exchange between warps);
+        // all channels are valid (N % 128 == 0 is required by the host side)
+        float* xbuf16 = reinterpret_cast<float*>(bars + 1);
+        float* xbuf = xbuf16 + (it & 1) * 2048;
         const int cl = q * 32 + lane;
         const bool row = p.rowadd != nullptr, ss = p.gn_scale != nullptr;
-        if (p.lg_bhw >= 6 && p.gn_rolled) {      // one image per tile (16x16) or per 64-pixel chunk pair (8x8): rolled chunk loops
-          if (p.gn_raw) conv_epilogue_gnfuse_uniform<false, false, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-          else if (row && ss) conv_epilogue_gnfuse_uniform<true, true, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-          else if (row) conv_epilogue_gnfuse_uniform<true, false, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-          else if (ss) conv_epilogue_gnfuse_uniform<false, true, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-          else conv_epilogue_gnfuse_uniform<false, false, false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-        } else
-        if (p.gn_raw) conv_epilogue_gnfuse<false, false, false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-        else if (row && ss) conv_epilogue_gnfuse<true, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-        else if (row) conv_epilogue_gnfuse<true, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-        else if (ss) conv_epilogue_gnfuse<false, true>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
-        else conv_epilogue_gnfuse<false, false>(p, t, taddr, c, half, cl, xbuf, &bars->tmem_full[as], aphase);
+        if (p.gn_raw) conv_epilogue_gnfuse<false, false, false, true>(p, t, taddr, c, half, cl, xbuf, xbuf16, &bars->tmem_full[as], aphase);
+        else if (row && ss) conv_epilogue_gnfuse<true, true, false, false>(p, t, taddr, c, half, cl, xbuf, xbuf16, &bars->tmem_full[as], aphase);
+        else if (row) conv_epilogue_gnfuse<true, false, false, false>(p, t, taddr, c, half, cl, xbuf, xbuf16, &bars->tmem_full[as], aphase);
+        else if (ss) conv_epilogue_gnfuse<false, true, false, false>(p, t, taddr, c, half, cl, xbuf, xbuf16, &bars->tmem_full[as], aphase);
+        else conv_epilogue_gnfuse<false, false, false, false>(p, t, taddr, c, half, cl, xbuf, xbuf16, &bars->tmem_full[as], aphase);
       } else if (kLean == 1) conv_epilogue_lean_dispatch(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       else conv_epilogue_tile(p, t, taddr, c, c_ok, half, &bars->tmem_full[as], aphase);
       tc_fence_before();
@@ -492,8 +481,6 @@ extern "C" int b200_conv2d_fwd(const b200_conv_desc* d, void* stream_) {
     p.gn_cl = gn_cl;
     static const char* env_late = getenv("B200_GN_LATE_OUT");      // =0: fp32 output stores before the statistics arrival (A/B)
     p.gn_late_out = !(env_late && atoi(env_late) == 0);
-    static const char* env_rolled = getenv("B200_GN_ROLLED");    // =0: one-image tiles keep the unrolled epilogue (A/B)
-    p.gn_rolled = !(env_rolled && atoi(env_rolled) == 0);
     if (gn_cl) {
       // the gn_cl tiles of an image are taken in the same iteration by gn_cl consecutive CTAs (tile = blockIdx.x + i *
       // gridDim.x, both multiples of gn_cl) which wait for each other: cooperative launch = all CTAs co-resident

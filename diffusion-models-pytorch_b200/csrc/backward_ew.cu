@@ -41,7 +41,7 @@ struct GnBwdParams {
   const __nv_bfloat16* g;
   const float* x0; int C0; const long long* st0;   // [B][C][2] int64 fixed-point statistics (common.cuh: stat_load)
   const float* x1; int C1; const long long* st1;
-  int HW, W, groups, cpg, pix_per_cta;
+  int HW, W, groups, cpg, pix_per_cta, reverse;
   const float* gamma; const float* beta; float eps;
   const float* scale; const float* shift; int ss_ld;
   int apply_silu, resample;
@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
   extern __shared__ float bsm[];
   const int C = p.C0 + p.C1;
   float* rsum = bsm;
-  const int n = blockIdx.y, tid = threadIdx.x;
+  // second streaming pass: walk images / pixel ranges from the END -- the reduce pass just read x and g front to back, so
+  // the tail of the tensors is what the 126 MB L2 still holds (p.reverse, B200_GNB_REVERSE=0: front to back)
+  const int n = p.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, tid = threadIdx.x;
   const float* cA = gn_ws(p, n, 2); const float* cB = gn_ws(p, n, 3);
   const float* rA = gn_ws(p, n, 4); const float* rB = gn_ws(p, n, 5);
   const float* k2 = gn_ws(p, n, 6); const float* k3 = gn_ws(p, n, 7);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_apply_kernel(const GnBwdParams 
   const int nv = C >> 2;
   const int cols = nv < 256 ? nv : 256;
   const int pstep = 256 / cols;
-  const int px0 = blockIdx.x * p.pix_per_cta;
+  const int px0 = (p.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * p.pix_per_cta;
   const int px1 = min(p.HW, px0 + p.pix_per_cta);
   for (int j0 = 0; j0 < nv; j0 += cols) {
     const int j = j0 + tid % cols, prow = tid / cols;
@@ -1015,6 +1017,8 @@ extern "C" int b200_groupnorm_bwd(const b200_gn_bwd_desc* d, void* stream_) {
   if (ppc < 1) ppc = 1;
   if (ppc > d->HW) ppc = d->HW;
   p.pix_per_cta = ppc;
+  static const char* env_rev = getenv("B200_GNB_REVERSE");
+  p.reverse = !(env_rev && atoi(env_rev) == 0);
   dim3 grid((d->HW + ppc - 1) / ppc, d->B);
   static bool attr = false;
   if (!attr) {

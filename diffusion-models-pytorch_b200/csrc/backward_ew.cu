@@ -541,6 +541,14 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_slab_kernel(const GnBwdParams p
         gn_bwd_dz_core(x, g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { s1[i] += dz[i]; s2[i] = fmaf(dz[i], xh[i], s2[i]); }
+        // pass 2 needs dz and xh again: keep them in this thread's own slab slots (dz fp32 over x, xh bf16 over g; xh only
+        // multiplies k3, a mean over the group, so its bf16 rounding is ~1e-4 of dx) instead of re-evaluating the SiLU
+        // derivative and the dropout hash
+        *reinterpret_cast<float4*>(xs + (size_t)px * CS + (q << 2)) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        uint2 xu;
+        xu.x = pack_bf16x2(xh[0], xh[1]);
+        xu.y = pack_bf16x2(xh[2], xh[3]);
+        *reinterpret_cast<uint2*>(gs + (size_t)px * CS + (q << 2)) = xu;
       }
     if (active) {
 #pragma unroll
@@ -604,13 +612,12 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_slab_kernel(const GnBwdParams p
       for (int u = 0; u < 2; ++u) {
         const int px = px0 + u * R;
         if (px >= HW) break;
-        const float4 x = *reinterpret_cast<const float4*>(xs + (size_t)px * CS + (q << 2));
-        const uint2 gu = *reinterpret_cast<const uint2*>(gs + (size_t)px * CS + (q << 2));
-        const float4 g4 = make_float4(__uint_as_float(gu.x << 16), __uint_as_float(gu.x & 0xffff0000u),
-                                      __uint_as_float(gu.y << 16), __uint_as_float(gu.y & 0xffff0000u));
-        const uint32_t keep = drop ? dropout_keep4(seed, (unsigned long long)((goff + (size_t)px * C) >> 2), p.drop_thresh) : 15u;
-        float dz[4], xh[4], dx[4];
-        gn_bwd_dz_core(x, g4, a, b, ra, rb, keep, silu, drop, p.drop_scale, dz, xh);
+        const float4 dz4 = *reinterpret_cast<const float4*>(xs + (size_t)px * CS + (q << 2));      // dz, xh of pass 1
+        const uint2 xu = *reinterpret_cast<const uint2*>(gs + (size_t)px * CS + (q << 2));
+        const float dz[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+        const float xh[4] = {__uint_as_float(xu.x << 16), __uint_as_float(xu.x & 0xffff0000u),
+                             __uint_as_float(xu.y << 16), __uint_as_float(xu.y & 0xffff0000u)};
+        float dx[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) dx[i] = fmaf(dz[i], av[i], -q2v[i]) - xh[i] * q3v[i];
         if (p.addend) { dx[0] += ads[u].x; dx[1] += ads[u].y; dx[2] += ads[u].z; dx[3] += ads[u].w; }

@@ -336,12 +336,15 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
   __nv_bfloat16* dst = p.out + (size_t)n * p.HW * C + c;
   __nv_bfloat16* rdst = p.raw ? p.raw + (size_t)n * p.HW * C + c : nullptr;
   uint4 raw0[kU], raw1[kInBf16 ? 1 : kU];   // loads stay packed until they are consumed (register budget: 4 CTAs / SM)
+  // mixed sources (p.in_bf16 == 2: first source bf16 -- e.g. an up-sampling conv's output kept in bf16 --, second source an
+  // fp32 skip connection): the dtype is a per-thread property of the column's source
+  const bool b16 = kInBf16 || (p.in_bf16 == 2 && from0);
   auto issue = [&](int px) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int q = px + u * pstep;
       if (q < px1) {
-        if (kInBf16) {
+        if (kInBf16 || b16) {
           raw0[u] = __ldg(reinterpret_cast<const uint4*>(srcb + (size_t)q * sld));
         } else {
           raw0[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * sld));
@@ -416,7 +419,7 @@ __device__ __forceinline__ void gn_apply_cols8(const GnApplyParams& p, const flo
       const int q = px + u * pstep;
       if (q >= px1) break;
       float v[8];
-      if (kInBf16) {
+      if (kInBf16 || b16) {
         const uint32_t ww[4] = {raw0[u].x, raw0[u].y, raw0[u].z, raw0[u].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
   if (p.resample == 0 && p.cols8 == 2) {   // per-thread coefficients: no shared-memory prologue
     const int px0 = bx * p.pix_per_cta;
     const int px1 = min(p.HW, px0 + p.pix_per_cta);
-    if (p.in_bf16) gn_apply_cols8<true, 4, true>(p, nullptr, nullptr, n, px0, px1, drop_seed);
+    if (p.in_bf16 == 1) gn_apply_cols8<true, 4, true>(p, nullptr, nullptr, n, px0, px1, drop_seed);
     else gn_apply_cols8<false, 2, true>(p, nullptr, nullptr, n, px0, px1, drop_seed);
     return;
   }
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(const GnApplyPa
     const int px0 = bx * p.pix_per_cta;
     const int px1 = min(p.HW, px0 + p.pix_per_cta);
     if (p.resample == 0 && p.cols8) {
-      if (p.in_bf16) gn_apply_cols8<true, 4, false>(p, coefA, coefB, n, px0, px1, drop_seed);
+      if (p.in_bf16 == 1) gn_apply_cols8<true, 4, false>(p, coefA, coefB, n, px0, px1, drop_seed);
       else gn_apply_cols8<false, 2, false>(p, coefA, coefB, n, px0, px1, drop_seed);
       return;
     }
@@ -675,7 +678,7 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   const bool window = x0 == nullptr && C0 > 0 && x1 != nullptr;
   B200_REQUIRE((window || (x0 && stats0)) && out_bf16, "groupnorm_apply: null x0/stats0/out");
   if (!x1) C1 = 0;
-  B200_REQUIRE(!x0_is_bf16 || (x1 == nullptr && raw_out_bf16 == nullptr), "groupnorm_apply: a bf16 input must be the only source");
+
   B200_REQUIRE(x1 == nullptr || stats1 != nullptr, "groupnorm_apply: second source needs its statistics");
   const int C = C0 + C1;
   B200_REQUIRE(groups > 0 && C % groups == 0, "groupnorm_apply: C=%d not divisible by groups=%d", C, groups);
@@ -691,7 +694,7 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
   p.HW = HW; p.W = W; p.groups = groups; p.cpg = C / groups;
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.scale = scale; p.shift = shift; p.ss_ld = ss_ld;
   p.apply_silu = apply_silu; p.resample = resample;
-  p.in_bf16 = x0_is_bf16 ? 1 : 0;
+  p.in_bf16 = x0_is_bf16 ? ((x1 != nullptr || raw_out_bf16 != nullptr) ? 2 : 1) : 0;   // 2: per-thread dtype (8-channel columns only)
   static const char* env_c8 = getenv("B200_GN_COLS8");
   p.cols8 = (C0 % 8 == 0 && C1 % 8 == 0 && C / 8 <= 256 && !(env_c8 && atoi(env_c8) == 0)) ? 1 : 0;
   {
@@ -700,6 +703,8 @@ extern "C" int b200_groupnorm_apply_train_fwd(const void* x0_, int x0_is_bf16, i
                      (cpg % 8 == 0 && (C1 == 0 || C0 % cpg == 0));   // a group never straddles the two sources
     if (p.cols8 && own && !(env_c8 && atoi(env_c8) == 1)) p.cols8 = 2;
   }
+  B200_REQUIRE(p.in_bf16 != 2 || (p.cols8 && resample == 0 && !window),
+               "groupnorm_apply: a bf16 first source with a second source / raw copy needs 8-channel columns and no resampling");
   p.c_begin = window ? C0 : 0;
   if (window)
     B200_REQUIRE(p.cols8 == 2 && resample == 0 && drop_p == 0.f && !x0_is_bf16 && C0 % 8 == 0 && C1 % 8 == 0,

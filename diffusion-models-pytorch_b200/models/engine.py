@@ -58,6 +58,8 @@ class Engine:
     # ... and when nobody reads the fp32 form of such a block output (decoder blocks feeding a concatenating block or the
     # output head: they read the producer-applied bf16 tensors only) it is not written at all; =0: always written (A/B)
     skip_dead_out = bool(int(__import__('os').environ.get('B200_SKIP_DEAD_OUT', '1')))
+    # up-sampling conv outputs whose only consumer is a concatenating block's GroupNorm are stored as bf16 (=0: fp32, A/B)
+    up_bf16 = bool(int(__import__('os').environ.get('B200_UP_BF16', '1')))
     # first convolution on the tensor cores (64-channel hi / lo / hi split pixels + the first block's GroupNorm fused).
     # Off by default: same-box A/B (DDIM-50, batch 256) 1205.6 / 1202.5 images/s with it, 1205.8 / 1208.4 without -- the
     # 32x32 multi-tile fused epilogue costs what the FP32-FMA kernel + its GroupNorm launch cost.  =1 enables it (A/B).
@@ -604,7 +606,7 @@ class Engine:
         with self.scope():       # the block's temporaries are released when it returns
             return self._upsample_conv_body(*args, **kwargs)
 
-    def _upsample_conv_body(self, tag, conv: nn.Conv2d, x: Act) -> Act:
+    def _upsample_conv_body(self, tag, conv: nn.Conv2d, x: Act, bf16_out: bool = False) -> Act:
         """nearest-2x + conv3x3 as four 2x2-tap phase convolutions on the low-res grid (2.25x fewer MACs)."""
         B, H, W, C = x.B, x.H, x.W, x.C
         if self.tape is not None:
@@ -623,9 +625,14 @@ class Engine:
             K.cast_bf16(x.t, xb, B, H, W, C)
         w, b = self.w_up2(tag, conv)
         Cout = conv.out_channels
-        out = self.buf(tag + '.out', (B, 2 * H, 2 * W, Cout), torch.float32)
+        # bf16_out: the caller guarantees that the ONLY consumer is the GroupNorm (+ fused 1x1 shortcut) of a block that
+        # concatenates a skip connection, i.e. nobody reads this tensor as an fp32 residual: like the ResBlock
+        # intermediates (h_bf16) it is then stored as bf16 -- its GroupNorm statistics still come from the fp32 accumulators
+        b16 = bf16_out and self.up_bf16 and self.h_bf16 and Cout >= 128 and not self.split
+        out = self.buf(tag + '.out', (B, 2 * H, 2 * W, Cout), torch.bfloat16 if b16 else torch.float32)
         stats = self.stats_buf(tag, B, Cout)
         K.conv2d(xb, w, Cout, B, H, W, K.taps_up2_3x3(), a0_geom=(m * C, H, W, 1), bias=b, out=out,
+                 out_mode=K.OUT_BF16_NHWC if b16 else K.OUT_F32_NHWC,
                  w_rows_per_phase=Cout, stats=stats, alg_macs=9.0 * B * 4 * H * W * C * Cout)
         return Act(out, B, 2 * H, 2 * W, Cout, stats)
 

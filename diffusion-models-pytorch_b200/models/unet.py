@@ -208,6 +208,11 @@ class UNet(_EngineModel):
                 h = eng.downsample_conv(name, blk, h)
                 skips.append(h)
             else:
-                h = eng.upsample_conv(name, blk[1], h)
+                # the next op is a decoder ResBlock that concatenates a skip connection (GroupNorm + 1x1 shortcut read it,
+                # nobody adds it as an fp32 residual) -> the up-conv output may stay bf16
+                nk, _, nblk, _ = ops[k + 1]
+                cat_next = (nk == 'res' and bool(skips) and isinstance(nblk.shortcut, nn.Conv2d)
+                            and nblk.shortcut.kernel_size[0] == 1 and getattr(nblk, 'updown_kind', None) is None)
+                h = eng.upsample_conv(name, blk[1], h, bf16_out=cat_next)
 
         return eng.head('last_conv', h, self.last_conv[0], self.last_conv[2], out)

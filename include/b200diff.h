@@ -148,8 +148,9 @@ int b200_groupnorm_silu_fwd(const float* x0, int C0, const float* x1, int C1, in
  * fixed point with scales B200_STAT_Q1 / B200_STAT_Q2, were
  * accumulated by the producing kernel (b200_conv_desc.stats): one coalesced pass, 4 B read + 2 B written per
  * element.  Same semantics and arguments as b200_groupnorm_silu_fwd otherwise. */
-int b200_groupnorm_apply_fwd(const void* x0, int x0_is_bf16 /* x0 is bf16 NHWC (single source, statistics taken
-                             from the fp32 accumulators of its producer) */, int C0, const long long* stats0,
+int b200_groupnorm_apply_fwd(const void* x0, int x0_is_bf16 /* x0 is bf16 NHWC (statistics taken from the fp32
+                             accumulators of its producer); with a second (fp32) source or a raw copy: C0 % 8 == 0,
+                             C1 % 8 == 0, C <= 2048, no resampling */, int C0, const long long* stats0,
                              const float* x1, int C1, const long long* stats1, int B, int HW, int W, int groups,
                              const float* gamma,
                              const float* beta, float eps, const float* scale, const float* shift, int ss_ld,

@@ -309,6 +309,30 @@ def _gn_case(name, B, C0, C1, H, W, silu=True, adagn=False, resample=0, raw=Fals
         ok &= _report(name + ' [streaming, producer stats]', out2.permute(0, 3, 1, 2), ref, rtol=5e-3, atol=5e-3)
         if raw:
             ok &= _report(name + ' [streaming raw copy]', raw2, xcat.to(torch.bfloat16), 0, 0)
+        if C1 and raw and resample == 0 and C0 % 8 == 0 and C1 % 8 == 0:
+            # mixed sources: the first one stored as bf16 by its producer (an up-sampling conv whose only consumer is this
+            # GroupNorm; statistics from its fp32 values), the second an fp32 skip connection
+            xb = x0.to(torch.bfloat16)
+            cpg = C // 32
+            xg = xcat.permute(0, 3, 1, 2).reshape(B, 32, cpg * H * W)
+            mean = xg.mean(dim=2)[:, :, None, None, None]
+            var = xg.var(dim=2, unbiased=False)[:, :, None, None, None]
+            xmix = torch.cat([xb.float(), x1], dim=-1)
+            xr = xmix.permute(0, 3, 1, 2).reshape(B, 32, cpg, H, W)
+            refm = ((xr - mean) * torch.rsqrt(var + eps)).reshape(B, C, H, W) * gamma[None, :, None, None] + \
+                beta[None, :, None, None]
+            if adagn:
+                refm = refm * (1 + ys[:, :C, None, None]) + ys[:, C:2 * C, None, None]
+            if silu:
+                refm = F.silu(refm)
+            out4 = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+            raw4 = torch.full((B, H, W, C), float('nan'), device=DEV, dtype=torch.bfloat16)
+            K.groupnorm_apply(xb, C0, st(x0), x1, C1, st(x1), B, H * W, W, 32, gamma, beta, eps, out4,
+                              scale=ys if adagn else None, shift=ys[:, C:] if adagn else None,
+                              ss_ld=(2 * C + 8) if adagn else 0, silu=silu, raw_out=raw4)
+            torch.cuda.synchronize()
+            ok &= _report(name + ' [streaming, bf16 first source + fp32 second]', out4.permute(0, 3, 1, 2), refm, rtol=5e-3, atol=5e-3)
+            ok &= _report(name + ' [streaming, mixed sources: raw copy]', raw4, xmix.to(torch.bfloat16), 0, 0)
         if C1 == 0 and not raw:
             # bf16-stored input whose statistics were taken from the fp32 values by its producer
             xb = x0.to(torch.bfloat16)
@@ -341,6 +365,8 @@ def case_groupnorm():
     ok &= _gn_case('GN+SiLU C256 @16', 3, 256, 0, 16, 16)
     ok &= _gn_case('GN+SiLU cat(256,128)=384 @16 (group straddles sources) + raw', 2, 256, 128, 16, 16, raw=True)
     ok &= _gn_case('GN+SiLU cat(256,256)=512 @4 + raw', 5, 256, 256, 4, 4, raw=True)
+    ok &= _gn_case('GN+SiLU cat(256,256)=512 @16 + raw (16 ch/group: per-thread coefficients)', 3, 256, 256, 16, 16, raw=True)
+    ok &= _gn_case('GN+SiLU cat(256,128)=384 @32 + raw', 2, 256, 128, 32, 32, raw=True)
     ok &= _gn_case('GN only C256 @16 (attention norm)', 2, 256, 0, 16, 16, silu=False)
     ok &= _gn_case('GN+SiLU C64 @32 (2 ch/group, float2 path)', 2, 64, 0, 32, 32)
     ok &= _gn_case('GN+SiLU cat(128,64)=192 @32 (6 ch/group)', 2, 128, 64, 32, 32, raw=True)

@@ -144,3 +144,99 @@ def test_state_dict_compat_and_ema():
     assert torch.allclose(p.data, torch.full((3,), 0.29))
     ema.restore([p])
     assert torch.allclose(p.data, torch.full((3,), 2.0))
+
+
+class _PlanEngine:
+    """Records the op sequence a UNet forward hands to the engine (no kernels): checks the consumer look-ahead."""
+    attn_block = True
+    pingpong = False
+
+    def __init__(self):
+        self.calls = []
+
+    def begin_forward(self):
+        pass
+
+    def check_input(self, X, T, in_channels):
+        return X
+
+    def embed(self, *a, **k):
+        return None, 0
+
+    def _act(self, C, H, skipc=None):
+        from models.engine import Act
+        return Act(None, 2, H, H, C)
+
+    def first_conv(self, tag, conv, X, next_gn=None):
+        self.calls.append(('first', tag, None, next_gn, {}))
+        return self._act(conv.out_channels, X.shape[2])
+
+    def resblock(self, tag, blk, x, skip, *a, next_gn=None):
+        self.calls.append(('res', tag, skip, next_gn, dict(x=x)))
+        conv1 = blk.blk1[2]
+        return self._act(conv1.out_channels, x.H)
+
+    resblock_adagn = resblock
+
+    def attention(self, tag, blk, x, next_gn=None):
+        self.calls.append(('attn', tag, None, next_gn, dict(x=x)))
+        return self._act(x.C, x.H)
+
+    def downsample_conv(self, tag, blk, x, **k):
+        self.calls.append(('down', tag, None, None, dict(x=x)))
+        return self._act(x.C, x.H // 2)
+
+    def upsample_conv(self, tag, conv, x, bf16_out=False):
+        self.calls.append(('up', tag, None, None, dict(x=x, bf16_out=bf16_out)))
+        return self._act(conv.out_channels, x.H * 2)
+
+    def head(self, tag, h, norm, conv, out):
+        self.calls.append(('head', tag, None, None, dict(x=h, norm=norm)))
+        return 'out'
+
+
+@pytest.mark.parametrize('family', ['unet', 'adagn'])
+def test_forward_plan_lookahead(family):
+    """models/unet.py / unet_categorial_adagn.py flatten the reference's forward (unet.py:127-150) into an op list in which
+    every block knows its consumer.  The flags derived from that look-ahead decide what the kernels do NOT write:
+      * next_gn[3] (`dead`): the producer's fp32 output is never written -- legal only when the consumer is the output head
+        or a decoder block that concatenates a skip connection, and the producer's output is no skip connection itself;
+      * next_gn[2] (skip channels of the consumer's concat) must equal the channels of the skip the consumer then pops;
+      * bf16_out of an up-sampling conv: legal only when the next op is such a concatenating block."""
+    import torch.nn as nn
+    if family == 'unet':
+        m = models.UNet(dim=32, dim_mults=[1, 2, 2], use_attn=[False, True, False], num_res_blocks=2, n_heads=1)
+    else:
+        m = models.UNetCategorialAdaGN(dim=32, dim_mults=[1, 2, 2], use_attn=[False, True, False], num_res_blocks=2,
+                                       num_classes=10, attn_head_dims=32)
+    eng = _PlanEngine()
+    m.__dict__['_engine'] = eng
+    X = torch.zeros(2, 3, 16, 16)
+    T = torch.zeros(2, dtype=torch.long)
+    out = m._forward_impl(X, T) if family == 'unet' else m._forward_impl(X, T, None)
+    assert out == 'out'
+    calls = eng.calls
+    assert calls[0][0] == 'first' and calls[-1][0] == 'head'
+    n_dead = n_cat = n_bf16 = 0
+    for i, (kind, tag, skip, next_gn, kw) in enumerate(calls[:-1]):
+        nkind, ntag, nskip, _, nkw = calls[i + 1]
+        if kind == 'up':
+            if kw['bf16_out']:
+                n_bf16 += 1
+                assert nkind == 'res' and nskip is not None, f'{tag}: bf16 output but the consumer {ntag} does not concatenate'
+        if next_gn is None:
+            continue
+        norm, silu = next_gn[0], next_gn[1]
+        skip_c = next_gn[2] if len(next_gn) > 2 else 0
+        dead = bool(next_gn[3]) if len(next_gn) > 3 else False
+        assert isinstance(norm, nn.GroupNorm)
+        if skip_c:
+            n_cat += 1
+            assert nkind == 'res' and nskip is not None and nskip.C == skip_c, f'{tag}: concat look-ahead does not match {ntag}'
+        if dead:
+            n_dead += 1
+            assert tag.startswith(('up_blocks', 'bottleneck_block')), f'{tag}: an encoder output (skip connection) marked dead'
+            assert nkind == 'head' or (nkind == 'res' and nskip is not None), f'{tag}: dead output but {ntag} reads it as fp32'
+        if nkind == 'head':
+            assert norm is nkw['norm'] and silu
+    assert n_dead >= 3 and n_cat >= 3 and (n_bf16 >= 1 or family == 'adagn')

@@ -55,6 +55,9 @@ class Engine:
     # ... and when the consumer concatenates a skip connection: the producer writes its part of the normalised and raw
     # concat operands, the GroupNorm launch of the consumer handles the skip's channels only; =0: full launch (A/B)
     fuse_gn1_cat = bool(int(__import__('os').environ.get('B200_FUSE_GN1_CAT', '1')))
+    # the block-output form also in training forwards (the fp32 output + statistics are written as before: the adjoint of
+    # the consumer's GroupNorm reads them; its normalised / raw bf16 operands get per-block buffers); =0: inference only (A/B)
+    fuse_gn1_train = bool(int(__import__('os').environ.get('B200_FUSE_GN1_TRAIN', '1')))
     # ... and when nobody reads the fp32 form of such a block output (decoder blocks feeding a concatenating block or the
     # output head: they read the producer-applied bf16 tensors only) it is not written at all; =0: always written (A/B)
     skip_dead_out = bool(int(__import__('os').environ.get('B200_SKIP_DEAD_OUT', '1')))
@@ -362,7 +365,7 @@ class Engine:
     def gn(self, tag, x: Act, skip: Optional[Act], norm: nn.GroupNorm, silu=True, raw=False, scale=None, shift=None,
            ss_ld=0, resample=0, drop_p=0.0, drop_seed=0):
         if (x.pre is not None and x.pre[0] is norm and x.pre[1] == bool(silu) and scale is None and resample == 0
-                and drop_p == 0.0 and self.tape is None and not self.split):
+                and drop_p == 0.0 and not self.split):
             if len(x.pre) == 3 and skip is None and not raw:
                 return x.pre[2], None      # the producing conv already applied this GroupNorm (fuse_gn1)
             if (len(x.pre) == 4 and skip is not None and skip.stats is not None
@@ -565,12 +568,13 @@ class Engine:
                if self.tape is not None and self.attn_bwd_fused and K.attention_bwd_ok(T, d) else None)
         K.attention(qk, 2 * C, 0, C, vt, o, C, B, T, heads, d, scale, lse=lse)
         if C % 64 == 0 and self.next_gn_ok(B, H, W, C, next_gn):
-            return self.conv_block_out(tag, o, B, H, W, C, C, wp, bp, K.taps_1x1(), next_gn, residual=x)
-        out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
-        stats = self.stats_buf(tag, B, C)
-        K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
-                 stats=stats)
-        res = Act(out, B, H, W, C, stats)
+            res = self.conv_block_out(tag, o, B, H, W, C, C, wp, bp, K.taps_1x1(), next_gn, residual=x)
+        else:
+            out = self.buf(tag + '.out', (B, H, W, C), torch.float32)
+            stats = self.stats_buf(tag, B, C)
+            K.conv2d(o, wp, C, B, H, W, K.taps_1x1(), a0_geom=(C, H, W, 1), bias=bp, residual=x.t, res_ld=C, out=out,
+                     stats=stats)
+            res = Act(out, B, H, W, C, stats)
         if self.tape is not None:
             if mods is None:
                 raise RuntimeError(f'{tag}: this attention block did not register its parameters for the backward pass')
@@ -669,7 +673,9 @@ class Engine:
         consumer?  Every eligible layer takes the fused form: a per-layer policy derived from cold-cache ncu launch lists
         (no fusion for 32x32 layers that also stream a residual, no concat form below 16x16) was A/B-timed on one box
         and lost to `all layers` inside the sampling graph (DDIM-50 1195.0 vs 1197.0 images/s; none: 1178)."""
-        if next_gn is None or not (self.fuse_gn1 and self.fuse_gn2) or self.tape is not None or self.split:
+        if next_gn is None or not (self.fuse_gn1 and self.fuse_gn2) or self.split:
+            return False
+        if self.tape is not None and not self.fuse_gn1_train:
             return False
         norm, skip_C = next_gn[0], (next_gn[2] if len(next_gn) > 2 else 0)
         if skip_C == 0:
@@ -683,8 +689,11 @@ class Engine:
         return (C % cpg == 0 and skip_C % 8 == 0 and C % 8 == 0 and (cpg in (1, 2, 4, 8) or cpg % 8 == 0)
                 and K.conv2d_gn_ok(B, H, W, C, C // cpg))
 
-    def _pre_buf(self, B, H, W, C, kind='pre'):
-        """bf16 buffer for a producer-applied GroupNorm: read by the very next block only, so two per shape alternate."""
+    def _pre_buf(self, B, H, W, C, kind='pre', tag=None):
+        """bf16 buffer for a producer-applied GroupNorm: read by the very next block only, so two per shape alternate.
+        Training: the backward reads it (conv1's weight-gradient operand, the shortcut's), so every producer keeps its own."""
+        if self.tape is not None:
+            return self.buf(f'{tag}.{kind}', (B, H, W, C), torch.bfloat16)
         k = (kind, B, H, W, C)
         n = self._pp_count.get(k, 0)
         self._pp_count[k] = n + 1
@@ -698,12 +707,12 @@ class Engine:
         skip_C = next_gn[2] if len(next_gn) > 2 else 0
         # next_gn[3]: the consumer reads only `pre` / `praw` (output head, concatenating decoder block with a 1x1 shortcut)
         # and the output is no skip connection -> without a residual the fp32 form and its statistics are never written
-        dead = len(next_gn) > 3 and next_gn[3] and residual is None and self.skip_dead_out
+        dead = len(next_gn) > 3 and next_gn[3] and residual is None and self.skip_dead_out and self.tape is None
         stats = self.stats_buf(tag, B, Cout)
         out = None if dead else self.buf(tag + '.out', (B, H, W, Cout), torch.float32)
         Ct = Cout + skip_C
-        pre = self._pre_buf(B, H, W, Ct)
-        rawc = self._pre_buf(B, H, W, Ct, 'praw') if skip_C else None
+        pre = self._pre_buf(B, H, W, Ct, tag=tag)
+        rawc = self._pre_buf(B, H, W, Ct, 'praw', tag=tag) if skip_C else None
         groups = norm.num_groups if not skip_C else Cout // (Ct // norm.num_groups)
         ws = {}
         if K.conv2d_gn_needs_workspace(H, W):     # several tiles per image: the output statistics double as the exchange workspace

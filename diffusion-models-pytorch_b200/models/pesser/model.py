@@ -198,7 +198,10 @@ class Model(_EngineModel):
                     h = run_attn(f'up.{i}.attn.{j}', lvl.attn[j], h)
             if i != 0:
                 us = lvl.upsample
-                h = eng.upsample_conv(f'up.{i}.upsample.conv', us.conv, h) if us.with_conv \
-                    else eng.resample_plain(f'up.{i}.upsample', h, 2)
+                # the next block concatenates a skip connection and therefore has a projection shortcut: only its GroupNorm
+                # (+ the shortcut's bf16 operand) reads the up-sampled tensor, which may then be stored as bf16
+                nxt = self.up[i - 1].block[0]
+                h = eng.upsample_conv(f'up.{i}.upsample.conv', us.conv, h, bf16_out=nxt.shortcut_conv() is not None) \
+                    if us.with_conv else eng.resample_plain(f'up.{i}.upsample', h, 2)
 
         return eng.head('norm_out', h, self.norm_out, self.conv_out, out)

@@ -92,7 +92,19 @@ __global__ void __launch_bounds__(256) conv3x3_first_kernel(const float* __restr
 // (image, row block) units; a lane computes 4 consecutive pixels x 4 channels, so each (ci, r) patch row is read as
 // one 16-byte + one 8-byte warp-broadcast shared-memory load feeding 48 FMAs (the 1-pixel form issued one 4-byte
 // load per 4 FMAs and ran at 22 % of the FP32 rate).
-template <int CIN>
+// kF2: packed FP32 FMAs (FFMA2, sm_100: two fp32 FMAs per instruction).  The accumulators and the weights of a lane's
+// channel pairs (0, 1) / (2, 3) are natural register pairs; the pixel operand has to carry the same value in both halves,
+// so the patch is stored DUPLICATED in shared memory ([x, x] per pixel) and a patch row is three 16-byte broadcast
+// loads feeding 24 FFMA2 (= the 48 FMAs of the scalar form, same rounding: bitwise identical results).
+__device__ __forceinline__ void ffma2_acc(float2& d, const float2 a, const float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
+template <int CIN, bool kF2>
 __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ out,
                                                                    long long* __restrict__ stats, int B, int H, int W, int Cout,
@@ -125,7 +137,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* 
       const int rem = i - ci * (R + 2) * PWp;
       const int py = rem / PWp, pxx = rem - py * PWp;
       const int yy = h0 + py - 1, xx = pxx - 1;
-      patch[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)n * CIN + ci) * H + yy) * W + xx) : 0.f;
+      const float pvv = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)n * CIN + ci) * H + yy) * W + xx) : 0.f;
+      if (kF2) reinterpret_cast<float2*>(patch)[i] = make_float2(pvv, pvv);
+      else patch[i] = pvv;
     }
     __syncthreads();
     const int rows = min(R, H - h0);
@@ -137,6 +151,33 @@ __global__ void __launch_bounds__(256, 1) conv3x3_first_px4_kernel(const float* 
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[q][e] = bv[e];
+      if (kF2) {
+        float2 a2[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a2[q][0] = make_float2(bv[0], bv[1]); a2[q][1] = make_float2(bv[2], bv[3]); }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float4* pr = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(patch) +
+                                                               (ci * (R + 2) + ly + r) * PWp + lx);
+            const float4 u0 = pr[0], u1 = pr[1], u2 = pr[2];      // six pixels, each as [x, x]
+            const float2 pv2[6] = {make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y),
+                                   make_float2(u1.z, u1.w), make_float2(u2.x, u2.y), make_float2(u2.z, u2.w)};
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const int k = (ci * 3 + r) * 3 + s;
+              const float2 w01 = make_float2(wr[0][k], wr[1][k]), w23 = make_float2(wr[2][k], wr[3][k]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                ffma2_acc(a2[q][0], pv2[q + s], w01);
+                ffma2_acc(a2[q][1], pv2[q + s], w23);
+              }
+            }
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[q][0] = a2[q][0].x; acc[q][1] = a2[q][0].y; acc[q][2] = a2[q][1].x; acc[q][3] = a2[q][1].y; }
+      } else
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
@@ -402,7 +443,9 @@ static int launch_first(const float* x, const float* w, const float* bias, float
     int R = 8;
     if (R > H) R = H;
     const int PWp = (W + 2 + 3) & ~3;
-    const size_t smem = (512 + (size_t)CIN * (R + 2) * PWp) * 4;
+    static const char* env_f2 = getenv("B200_FIRST_F2");       // =0: scalar FMAs (A/B)
+    const bool f2 = !(env_f2 && atoi(env_f2) == 0);
+    const size_t smem = (512 + (size_t)CIN * (R + 2) * PWp * (f2 ? 2 : 1)) * 4;
     B200_REQUIRE(smem <= 100 * 1024, "conv3x3_first: input patch does not fit in shared memory (W=%d)", W);
     static bool attr4 = false;
     static int sms = 0;
@@ -410,14 +453,19 @@ static int launch_first(const float* x, const float* w, const float* bias, float
       int dev = 0;
       B200_CHECK(cudaGetDevice(&dev));
       B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      B200_CHECK(cudaFuncSetAttribute(conv3x3_first_px4_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      B200_CHECK(cudaFuncSetAttribute(conv3x3_first_px4_kernel<CIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      B200_CHECK(cudaFuncSetAttribute(conv3x3_first_px4_kernel<CIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr4 = true;
     }
     const int upi = (H + R - 1) / R;
     const int total = upi * B;
     dim3 grid(total < sms ? total : sms, 1, (Cout + 127) / 128);
-    B200_CHECK(launch_pdl(conv3x3_first_px4_kernel<CIN>, grid, dim3(256), smem, stream, x, w, bias, out, stats, B, H, W, Cout,
-                          R, upi, total));
+    if (f2)
+      B200_CHECK(launch_pdl(conv3x3_first_px4_kernel<CIN, true>, grid, dim3(256), smem, stream, x, w, bias, out, stats, B, H, W,
+                            Cout, R, upi, total));
+    else
+      B200_CHECK(launch_pdl(conv3x3_first_px4_kernel<CIN, false>, grid, dim3(256), smem, stream, x, w, bias, out, stats, B, H, W,
+                            Cout, R, upi, total));
     ++g_launch_count;
     return 0;
   }

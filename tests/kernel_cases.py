@@ -1296,6 +1296,9 @@ def case_conv_gnfuse():
     for (B, Cin, Cout, H, rowadd, ss, silu) in ((160, 256, 256, 16, True, False, True), (160, 256, 256, 8, True, False, True),
                                                  (320, 256, 256, 4, True, False, True), (160, 128, 256, 8, False, True, True),
                                                  (128, 256, 128, 16, False, False, False),
+                                                 # other tile sizes of the rolled epilogue: 256-pixel tiles of sixteen 4x4
+                                                 # images (4 chunks, two images per 32-pixel chunk), 64-pixel tiles = one 8x8 image
+                                                 (1024, 256, 256, 4, True, True, True), (80, 256, 256, 8, True, False, True),
                                                  # 32x32 images: 4 tiles per image, statistics shared by 4 co-scheduled CTAs
                                                  (150, 128, 128, 32, True, False, True), (37, 384, 128, 32, True, True, True),
                                                  (3, 128, 128, 32, False, False, True)):
